@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Mpixels/s for thumbnail(4K -> 512, lanczos3).
+
+Workload = BASELINE.json configs[1]: vips_thumbnail 4096x4096 uchar RGBA -> 512x512,
+a batch of 1024 synthetic frames per GPU (64 GiB resident in HBM, >> the 126 MB L2).  A "step" is
+one pass of the fused thumbnail kernel over the whole batch, frames resident in HBM.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+  python bench.py --impl reference ...                      CPU arm (the oracle port
+                                                            of the reference algorithm)
+
+torch is used only for device memory, CUDA events/streams and torch.distributed.
+The kernels are libvips_b200/libvb200.so, called through its C ABI.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 4096
+BANDS = 4
+TARGET = 512
+MPIX_PER_FRAME = W * H / 1e6
+METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
+WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class CpuArm:
+    """The reference algorithm on the host cores: the oracle port (liboracle_fast.so),
+    one frame per worker thread (the reference's inter-image threading model)."""
+
+    def __init__(self, n_frames, threads):
+        import numpy as np
+        from oracle import pyoracle
+        fast = os.path.join(ROOT, "oracle", "liboracle_fast.so")
+        if not os.path.exists(fast):
+            pyoracle.build()
+        self.L = C.CDLL(fast)
+        self.n, self.threads = n_frames, threads
+        rng = np.random.default_rng(1234)
+        one = rng.integers(0, 256, (H, W, BANDS), dtype=np.uint8)
+        self.a = np.stack([np.roll(one, 7 * i, axis=1) for i in range(n_frames)])
+        self.out = np.empty((n_frames, TARGET, TARGET, BANDS), np.uint8)
+
+    def step(self):
+        t = time.perf_counter()
+        rc = self.L.orc_thumbnail_image_batch(C.c_void_p(self.a.ctypes.data), self.n, W, H, BANDS, TARGET, TARGET,
+                                              0, 1, C.c_void_p(self.out.ctypes.data), TARGET, TARGET, self.threads)
+        assert rc == 0
+        return time.perf_counter() - t
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    frames = max(threads, 8)
+    arm = CpuArm(frames, threads)
+    for _ in range(args.warmup):
+        arm.step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        arm.step()
+    dt = time.perf_counter() - t
+    v = frames * args.steps * MPIX_PER_FRAME / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD.replace("device-resident", "host RAM"), "frames_per_step": frames},
+        "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+                         "sample": "%d 4096x4096 RGBA frames per step, one frame per thread, oracle port of the "
+                                   "reference chain (libvips itself cannot be built here: no GLib)" % frames},
+        "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--frames", type=int, default=1024, help="synthetic frames resident per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
+    ap.add_argument("--cpu-frames", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    import libvips_b200 as vb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    vb.init(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    vb.set_stream(stream.cuda_stream)
+
+    plan = vb.ThumbnailPlan(W, H, BANDS, TARGET)
+    assert plan.fused, "the fused kernel must be the path under measurement"
+    assert (plan.out_width, plan.out_height) == (TARGET, TARGET)
+
+    # synthetic frames, generated on the device (seeded per rank); frame 0 is the shared
+    # numpy-seeded frame used for the cross-rank parity check below
+    F = args.frames
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    frames = torch.empty((F, H, W, BANDS), dtype=torch.uint8, device=dev)
+    for i in range(0, F, 16):
+        n = min(16, F - i)
+        frames[i:i + n] = torch.randint(0, 256, (n, H, W, BANDS), dtype=torch.uint8, device=dev, generator=g)
+    common = np.random.default_rng(1234).integers(0, 256, (H, W, BANDS), dtype=np.uint8)
+    frames[0].copy_(torch.from_numpy(common))
+    outs = torch.empty((F, TARGET, TARGET, BANDS), dtype=torch.uint8, device=dev)
+
+    def step():
+        plan.run_device(frames.data_ptr(), outs.data_ptr(), F)
+
+    # correctness gate before timing: frame 0 against the oracle (rank 0), same checksum on all ranks
+    step()
+    torch.cuda.synchronize()
+    csum = outs[0].to(torch.int64).sum()
+    if rank == 0:
+        from oracle import pyoracle
+        want = pyoracle.thumbnail_image(common, TARGET)
+        assert np.array_equal(outs[0].cpu().numpy(), want), "GPU thumbnail differs from the oracle"
+    if dist:
+        lo, hi = csum.clone(), csum.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert int(lo) == int(hi), "ranks disagree on the shared frame"
+
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = vb.launch_count()
+    barrier()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    barrier()
+    launches = vb.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+
+    value = world * F * args.steps * MPIX_PER_FRAME / (total_ms_max / 1e3)
+
+    # roofline of the dominant (only) kernel: algorithmic bytes / mean launch duration on this rank
+    peak, peak_src = peaks()
+    kern_ms = sum(per_step) / len(per_step)
+    bytes_per_launch = plan.bytes_per_frame * F
+    achieved = bytes_per_launch / (kern_ms / 1e3) / 1e9
+
+    # end to end through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside the timed region
+    e2e = None
+    E = args.e2e_frames
+    L = vb.lib()
+    hin = L.vb200_host_alloc(E * plan.in_frame_bytes)
+    hout = L.vb200_host_alloc(E * plan.out_frame_bytes)
+    if hin and hout:
+        src = np.frombuffer((C.c_uint8 * (E * plan.in_frame_bytes)).from_address(hin), dtype=np.uint8)
+        one = np.random.default_rng(99 + rank).integers(0, 256, plan.in_frame_bytes, dtype=np.uint8)
+        for i in range(E):
+            src[i * plan.in_frame_bytes:(i + 1) * plan.in_frame_bytes] = np.roll(one, 4 * i)
+        for _ in range(2):
+            plan.run_host_ptr(hin, hout, E)
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            plan.run_host_ptr(hin, hout, E)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * E * n_e2e * MPIX_PER_FRAME / float(te.item()), "unit": "Mpixels/s",
+               "h2d_bytes_per_step": E * plan.in_frame_bytes, "d2h_bytes_per_step": E * plan.out_frame_bytes,
+               "frames_per_step": E, "steps": n_e2e, "host_memory": "pinned (vb200_host_alloc)",
+               "api": "vb200_thumbnail_batch_host"}
+    if hin:
+        L.vb200_host_free(hin)
+    if hout:
+        L.vb200_host_free(hout)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = host_threads()
+        arm = CpuArm(args.cpu_frames, threads)
+        arm.step()
+        secs = min(arm.step() for _ in range(2))
+        v = args.cpu_frames * MPIX_PER_FRAME / secs
+        cpu = {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "port",
+               "sample": "%d 4096x4096 RGBA frames, %.1f s, oracle port (liboracle_fast.so), one frame per thread"
+                         % (args.cpu_frames, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "frame": "4096x4096x4 u8",
+                       "output": "512x512x4 u8", "l2": "inputs (%.1f GiB per GPU) larger than L2" % (F * plan.in_frame_bytes / 2**30),
+                       "sharding": "independent frames per rank, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "thumbnail_fused_kernel<4,true>",
+                         "bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,246 @@
+/* vb200.h -- C ABI of libvb200.so, the sm_100a replacement for libvips'
+ * per-tile pixel hot path (resample / convolution / colour generate callbacks).
+ *
+ * Plain C, plain pointers and sizes.  Every entry point returns 0 on success
+ * and -1 on error with a message appended to a thread-local buffer read with
+ * vb200_error_buffer() -- the convention of vips_error()/vips_error_buffer()
+ * (reference: libvips/iofuncs/error.c:214,329).
+ *
+ * There is NO CPU fallback inside this library: every pixel is produced by a
+ * CUDA kernel.  Unsupported formats return -1 so the host (libvips) keeps its
+ * own C generate function for them, exactly as it does today behind
+ * vips_vector_isenabled() (reference: resample/reducev.cpp:985-1016).
+ *
+ * "reference:" comments cite the libvips 8.19 interface each item replaces.
+ */
+#ifndef VB200_H
+#define VB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ enums */
+
+/* reference: VipsBandFormat, include/vips/image.h:121-132 (same values) */
+typedef enum {
+	VB200_FORMAT_UCHAR = 0,
+	VB200_FORMAT_CHAR = 1,
+	VB200_FORMAT_USHORT = 2,
+	VB200_FORMAT_SHORT = 3,
+	VB200_FORMAT_UINT = 4,
+	VB200_FORMAT_INT = 5,
+	VB200_FORMAT_FLOAT = 6,
+	VB200_FORMAT_COMPLEX = 7,
+	VB200_FORMAT_DOUBLE = 8,
+	VB200_FORMAT_DPCOMPLEX = 9
+} VB200BandFormat;
+
+/* reference: VipsInterpretation, include/vips/image.h:94-117 (same values) */
+typedef enum {
+	VB200_INTERPRETATION_MULTIBAND = 0,
+	VB200_INTERPRETATION_B_W = 1,
+	VB200_INTERPRETATION_XYZ = 12,
+	VB200_INTERPRETATION_LAB = 13,
+	VB200_INTERPRETATION_LABS = 21,
+	VB200_INTERPRETATION_sRGB = 22,
+	VB200_INTERPRETATION_RGB16 = 25,
+	VB200_INTERPRETATION_GREY16 = 26,
+	VB200_INTERPRETATION_scRGB = 28
+} VB200Interpretation;
+
+/* reference: VipsKernel, include/vips/resample.h:41-51 (same values) */
+typedef enum {
+	VB200_KERNEL_NEAREST = 0,
+	VB200_KERNEL_LINEAR = 1,
+	VB200_KERNEL_CUBIC = 2,
+	VB200_KERNEL_MITCHELL = 3,
+	VB200_KERNEL_LANCZOS2 = 4,
+	VB200_KERNEL_LANCZOS3 = 5,
+	VB200_KERNEL_MKS2013 = 6,
+	VB200_KERNEL_MKS2021 = 7
+} VB200Kernel;
+
+/* reference: VipsSize, include/vips/resample.h:53-59 */
+typedef enum {
+	VB200_SIZE_BOTH = 0,
+	VB200_SIZE_UP = 1,
+	VB200_SIZE_DOWN = 2,
+	VB200_SIZE_FORCE = 3
+} VB200Size;
+
+/* reference: VipsPrecision, include/vips/basic.h:106-111 */
+typedef enum {
+	VB200_PRECISION_INTEGER = 0,
+	VB200_PRECISION_FLOAT = 1,
+	VB200_PRECISION_APPROXIMATE = 2
+} VB200Precision;
+
+typedef enum {
+	VB200_HOST = 0,	 /* data is host memory */
+	VB200_DEVICE = 1 /* data is device memory on the current device */
+} VB200Where;
+
+/* ------------------------------------------------------------------ types */
+
+/* reference: VipsRect, include/vips/rect.h:40-46 */
+typedef struct {
+	int left;
+	int top;
+	int width;
+	int height;
+} VB200Rect;
+
+/* The header fields of VipsImage the pixel path reads (include/vips/image.h:189-260)
+ * plus where the pixels are.  Pixels are row-major, band-interleaved; bpl is
+ * the line stride in bytes (VIPS_REGION_LSKIP / VIPS_IMAGE_SIZEOF_LINE).
+ */
+typedef struct {
+	int Xsize;
+	int Ysize;
+	int Bands;
+	int BandFmt; /* VB200BandFormat */
+	int Type;	 /* VB200Interpretation */
+	int where;	 /* VB200Where */
+	void *data;
+	size_t bpl;
+} VB200Image;
+
+/* reference: VipsRegion {im, valid, data, bpl}, include/vips/region.h:96-130.
+ * data points at pixel (valid.left, valid.top); VIPS_REGION_ADDR(reg, x, y) ==
+ * data + (y - valid.top) * bpl + (x - valid.left) * sizeof_pel.
+ */
+typedef struct {
+	VB200Image im; /* header of the image the region is on (im.data unused) */
+	VB200Rect valid;
+	void *data;
+	int bpl;
+} VB200Region;
+
+/* ---------------------------------------------------------------- runtime */
+
+/* reference: vips_init()/vips_shutdown(), iofuncs/init.c */
+int vb200_init(int device);
+void vb200_shutdown(void);
+/* reference: vips_error_buffer()/vips_error_clear(), iofuncs/error.c:329,350 */
+const char *vb200_error_buffer(void);
+void vb200_error_clear(void);
+/* reference: vips_vector_isenabled(), iofuncs/vector.cpp:98-110 */
+int vb200_isenabled(void);
+/* The CUDA stream (cudaStream_t) device-resident calls are queued on, per
+ * calling thread; NULL = the legacy default stream.  Host-image calls use the
+ * library's own staging streams.
+ */
+void vb200_set_stream(void *cuda_stream);
+void *vb200_get_stream(void);
+/* reference: --vips-tile-width/--vips-tile-height/--vips-fatstrip-height/
+ * --vips-thinstrip-height, iofuncs/init.c:893-905, thread.c:74-77.  The tile
+ * geometry decides the rects generate() sees and therefore the sequential
+ * coordinate stepping of reducev/reduceh (reducev.cpp:548-611).
+ */
+void vb200_set_tile_geometry(int tile_width, int tile_height, int fatstrip_height, int thinstrip_height);
+/* Number of kernels this library has launched in this process. */
+uint64_t vb200_launch_count(void);
+void vb200_image_free(VB200Image *image);
+size_t vb200_format_sizeof(int band_format);
+
+/* ------------------------------------------------- resample: whole-image ops
+ *
+ * in->where selects host or device pixels.  If out->data is NULL the library
+ * allocates it in the same memory space (free with vb200_image_free); otherwise
+ * out->data/out->bpl are used as given and must be large enough.  The rest of
+ * *out is filled in.
+ */
+
+/* reference: vips_shrinkv()/vips_shrinkh(), resample/shrinkv.c:474, shrinkh.c:357 */
+int vb200_shrinkv(const VB200Image *in, VB200Image *out, int vshrink, int ceil_mode);
+int vb200_shrinkh(const VB200Image *in, VB200Image *out, int hshrink, int ceil_mode);
+/* reference: vips_reducev()/vips_reduceh(), resample/reducev.cpp:859, reduceh.cpp:396 */
+int vb200_reducev(const VB200Image *in, VB200Image *out, double vshrink, int kernel, double gap);
+int vb200_reduceh(const VB200Image *in, VB200Image *out, double hshrink, int kernel, double gap);
+/* reference: vips_reduce(), resample/reduce.c:97-119 (reducev then reduceh) */
+int vb200_reduce(const VB200Image *in, VB200Image *out, double hshrink, double vshrink, int kernel, double gap);
+/* reference: vips_resize(), resample/resize.c:135-311.  gap < 0 = default 2.0 */
+int vb200_resize(const VB200Image *in, VB200Image *out, double scale, double vscale, int kernel, double gap);
+/* reference: vips_premultiply()/vips_unpremultiply(), conversion/premultiply.c:215,
+ * unpremultiply.c:272.  max_alpha <= 0 = vips_interpretation_max_alpha(in->Type).
+ */
+int vb200_premultiply(const VB200Image *in, VB200Image *out, double max_alpha, int uchar_mode);
+int vb200_unpremultiply(const VB200Image *in, VB200Image *out, double max_alpha, int uchar_mode);
+/* reference: vips_thumbnail_image(), resample/thumbnail.c:2000 (image source,
+ * no ICC, no crop/rotate).  height <= 0 = width.
+ */
+int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int height, int size, int linear);
+
+/* ------------------------------------------- resample: generate()-shaped ops
+ *
+ * reference: VipsGenerateFn, include/vips/image.h:151-154.  Fill out->valid
+ * from the input region, which must cover the rect the reference generate
+ * function would vips_region_prepare() (reducev.cpp:539-544 etc.) on the
+ * EMBEDDED input image.  Host pointers; staged through the device.
+ */
+typedef struct {
+	int n_point;
+	int kernel;
+	double residual_shrink; /* residual_vshrink / residual_hshrink */
+	double offset;			/* voffset / hoffset */
+} VB200ReduceParams;
+
+int vb200_reducev_gen(const VB200Region *out, const VB200Region *in, const VB200ReduceParams *params);
+int vb200_reduceh_gen(const VB200Region *out, const VB200Region *in, const VB200ReduceParams *params);
+int vb200_shrinkv_gen(const VB200Region *out, const VB200Region *in, int vshrink);
+int vb200_shrinkh_gen(const VB200Region *out, const VB200Region *in, int hshrink);
+
+/* -------------------------------------------- resample: scanline kernel seam
+ *
+ * reference: resample/presample.h:74-87.  Same names, same signatures: a
+ * replacement .so can be linked in place of the Highway objects.  Host
+ * pointers; each call stages its scanlines through the device.
+ */
+void vips_reducev_uchar_hwy(uint8_t *pout, uint8_t *pin, int n, int ne, int lskip, const short *k);
+void vips_reduceh_uchar_hwy(uint8_t *pout, uint8_t *pin, int n, int width, int bands, short *cs[65], double X,
+	double hshrink);
+void vips_shrinkh_uchar_hwy(uint8_t *pout, uint8_t *pin, int width, int hshrink, int bands);
+void vips_shrinkv_add_line_uchar_hwy(uint8_t *pin, int ne, unsigned int *sum);
+void vips_shrinkv_write_line_uchar_hwy(uint8_t *pout, int ne, int vshrink, unsigned int *sum);
+
+/* ------------------------------------------------ thumbnail: batched stream
+ *
+ * The CUDA-stream tile pump that replaces vips_sink_memory + vips_threadpool_run
+ * (reference: iofuncs/sinkmemory.c:324, threadpool.c:625) for a batch of
+ * same-shaped frames: one fused kernel per op chain
+ * premultiply -> shrinkv -> reducev -> shrinkh -> reduceh -> unpremultiply.
+ */
+typedef struct VB200ThumbnailPlan VB200ThumbnailPlan;
+
+VB200ThumbnailPlan *vb200_thumbnail_plan_new(int width, int height, int bands, int band_format, int has_alpha,
+	int target_width, int target_height, int size, int linear);
+void vb200_thumbnail_plan_free(VB200ThumbnailPlan *plan);
+int vb200_thumbnail_plan_output(const VB200ThumbnailPlan *plan, int *out_width, int *out_height);
+/* Frames are contiguous: frame i at in + i * in_frame_stride bytes. */
+int vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
+	size_t out_frame_stride, int n_frames);
+/* Host frames (pinned or pageable); H2D / kernel / D2H overlapped on the
+ * library's streams.  Returns after the last output frame has landed.
+ */
+int vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
+	size_t out_frame_stride, int n_frames);
+/* 1 if the plan runs the single fused kernel, 0 if it chains the leaf kernels
+ * (other band counts, one-axis shrinks, or a window that does not fit on chip).
+ */
+int vb200_thumbnail_plan_is_fused(const VB200ThumbnailPlan *plan);
+/* Algorithmic HBM bytes one frame moves through the fused kernel. */
+size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
+
+/* pinned host memory for the pump (cudaHostAlloc / cudaFreeHost) */
+void *vb200_host_alloc(size_t bytes);
+void vb200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* VB200_H */

@@ -1,0 +1,274 @@
+"""libvips_b200 -- Python mirror of the libvips operator interface for the
+B200-native pixel hot path, bound over the C ABI of libvb200.so (include/vb200.h).
+
+The class and method names follow pyvips / the libvips C API
+(vips_reducev, vips_resize, vips_thumbnail_image, vips_conv, vips_colourspace ...)
+so tests read like the reference's own test-suite.  All pixels are produced by
+CUDA kernels inside libvb200.so: there is no CPU fallback here, and importing
+the operators without the built library (or calling them without a GPU) raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libvb200.so")
+_lib = None
+
+HOST, DEVICE = 0, 1
+
+FORMATS = {np.dtype(np.uint8): 0, np.dtype(np.int8): 1, np.dtype(np.uint16): 2, np.dtype(np.int16): 3,
+           np.dtype(np.uint32): 4, np.dtype(np.int32): 5, np.dtype(np.float32): 6, np.dtype(np.float64): 8}
+DTYPES = {v: k for k, v in FORMATS.items()}
+KERNELS = {"nearest": 0, "linear": 1, "cubic": 2, "mitchell": 3, "lanczos2": 4, "lanczos3": 5,
+           "mks2013": 6, "mks2021": 7}
+SIZES = {"both": 0, "up": 1, "down": 2, "force": 3}
+PRECISIONS = {"integer": 0, "float": 1, "approximate": 2}
+INTERPRETATIONS = {"multiband": 0, "b-w": 1, "xyz": 12, "lab": 13, "labs": 21, "srgb": 22, "rgb16": 25,
+                   "grey16": 26, "scrgb": 28}
+
+
+class Error(Exception):
+    """Raised with the text of vb200_error_buffer(), like pyvips.Error."""
+
+
+class CImage(C.Structure):
+    _fields_ = [("Xsize", C.c_int), ("Ysize", C.c_int), ("Bands", C.c_int), ("BandFmt", C.c_int),
+                ("Type", C.c_int), ("where", C.c_int), ("data", C.c_void_p), ("bpl", C.c_size_t)]
+
+
+class CRect(C.Structure):
+    _fields_ = [("left", C.c_int), ("top", C.c_int), ("width", C.c_int), ("height", C.c_int)]
+
+
+class CRegion(C.Structure):
+    _fields_ = [("im", CImage), ("valid", CRect), ("data", C.c_void_p), ("bpl", C.c_int)]
+
+
+class CReduceParams(C.Structure):
+    _fields_ = [("n_point", C.c_int), ("kernel", C.c_int), ("residual_shrink", C.c_double),
+                ("offset", C.c_double)]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load libvb200.so.  Fails loudly if the CUDA extension is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise Error("libvb200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.vb200_error_buffer.restype = C.c_char_p
+        L.vb200_launch_count.restype = C.c_uint64
+        L.vb200_get_stream.restype = C.c_void_p
+        L.vb200_set_stream.argtypes = [C.c_void_p]
+        L.vb200_format_sizeof.restype = C.c_size_t
+        L.vb200_host_alloc.restype = C.c_void_p
+        L.vb200_host_alloc.argtypes = [C.c_size_t]
+        L.vb200_host_free.argtypes = [C.c_void_p]
+        IP = C.POINTER(CImage)
+        L.vb200_shrinkv.argtypes = [IP, IP, C.c_int, C.c_int]
+        L.vb200_shrinkh.argtypes = [IP, IP, C.c_int, C.c_int]
+        L.vb200_reducev.argtypes = [IP, IP, C.c_double, C.c_int, C.c_double]
+        L.vb200_reduceh.argtypes = [IP, IP, C.c_double, C.c_int, C.c_double]
+        L.vb200_reduce.argtypes = [IP, IP, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.vb200_resize.argtypes = [IP, IP, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.vb200_premultiply.argtypes = [IP, IP, C.c_double, C.c_int]
+        L.vb200_unpremultiply.argtypes = [IP, IP, C.c_double, C.c_int]
+        L.vb200_thumbnail_image.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vb200_image_free.argtypes = [IP]
+        L.vb200_thumbnail_plan_new.restype = C.c_void_p
+        L.vb200_thumbnail_plan_new.argtypes = [C.c_int] * 9
+        L.vb200_thumbnail_plan_free.argtypes = [C.c_void_p]
+        L.vb200_thumbnail_plan_output.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.vb200_thumbnail_plan_bytes_per_frame.restype = C.c_size_t
+        L.vb200_thumbnail_plan_bytes_per_frame.argtypes = [C.c_void_p]
+        L.vb200_thumbnail_plan_is_fused.argtypes = [C.c_void_p]
+        L.vb200_thumbnail_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                   C.c_int]
+        L.vb200_thumbnail_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                                 C.c_int]
+        RP = C.POINTER(CRegion)
+        L.vb200_reducev_gen.argtypes = [RP, RP, C.POINTER(CReduceParams)]
+        L.vb200_reduceh_gen.argtypes = [RP, RP, C.POINTER(CReduceParams)]
+        L.vb200_shrinkv_gen.argtypes = [RP, RP, C.c_int]
+        L.vb200_shrinkh_gen.argtypes = [RP, RP, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().vb200_error_buffer().decode()
+        lib().vb200_error_clear()
+        raise Error(msg.strip() or "vb200 call failed")
+
+
+def init(device=0):
+    _check(lib().vb200_init(device))
+
+
+def shutdown():
+    lib().vb200_shutdown()
+
+
+def launch_count():
+    return int(lib().vb200_launch_count())
+
+
+def set_stream(handle):
+    lib().vb200_set_stream(C.c_void_p(handle))
+
+
+def set_tile_geometry(tile_width=0, tile_height=0, fatstrip_height=0, thinstrip_height=0):
+    lib().vb200_set_tile_geometry(tile_width, tile_height, fatstrip_height, thinstrip_height)
+
+
+def _k(kernel):
+    return KERNELS[kernel] if isinstance(kernel, str) else int(kernel)
+
+
+def _interp(name):
+    return INTERPRETATIONS[name] if isinstance(name, str) else int(name)
+
+
+class Image:
+    """A host image (numpy array, H x W x Bands) with libvips-style operators."""
+
+    def __init__(self, array, interpretation=None):
+        a = np.ascontiguousarray(array)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        if a.dtype not in FORMATS:
+            raise Error("unsupported dtype %s" % a.dtype)
+        self.array = a
+        if interpretation is None:
+            interpretation = "b-w" if a.shape[2] < 3 else "srgb"
+        self.interpretation = _interp(interpretation)
+
+    # pyvips-style constructors / accessors
+    @staticmethod
+    def new_from_array(array, interpretation=None):
+        return Image(array, interpretation)
+
+    def numpy(self):
+        return self.array
+
+    @property
+    def width(self):
+        return self.array.shape[1]
+
+    @property
+    def height(self):
+        return self.array.shape[0]
+
+    @property
+    def bands(self):
+        return self.array.shape[2]
+
+    @property
+    def format(self):
+        return self.array.dtype
+
+    def avg(self):
+        return float(self.array.mean())
+
+    def _c(self):
+        a = self.array
+        return CImage(a.shape[1], a.shape[0], a.shape[2], FORMATS[a.dtype], self.interpretation, HOST,
+                      C.c_void_p(a.ctypes.data), a.strides[0])
+
+    def _call(self, fn, *args):
+        cin = self._c()
+        cout = CImage()
+        _check(fn(C.byref(cin), C.byref(cout), *args))
+        n = cout.Ysize * cout.bpl
+        buf = (C.c_uint8 * n).from_address(cout.data)
+        dt = DTYPES[cout.BandFmt]
+        arr = np.frombuffer(buf, dtype=dt).reshape(cout.Ysize, cout.Xsize, cout.Bands).copy()
+        lib().vb200_image_free(C.byref(cout))
+        return Image(arr, cout.Type)
+
+    # ---- resample
+    def shrinkv(self, vshrink, ceil=False):
+        return self._call(lib().vb200_shrinkv, int(vshrink), int(ceil))
+
+    def shrinkh(self, hshrink, ceil=False):
+        return self._call(lib().vb200_shrinkh, int(hshrink), int(ceil))
+
+    def reducev(self, vshrink, kernel="lanczos3", gap=0.0):
+        return self._call(lib().vb200_reducev, float(vshrink), _k(kernel), float(gap))
+
+    def reduceh(self, hshrink, kernel="lanczos3", gap=0.0):
+        return self._call(lib().vb200_reduceh, float(hshrink), _k(kernel), float(gap))
+
+    def reduce(self, hshrink, vshrink, kernel="lanczos3", gap=0.0):
+        return self._call(lib().vb200_reduce, float(hshrink), float(vshrink), _k(kernel), float(gap))
+
+    def resize(self, scale, vscale=None, kernel="lanczos3", gap=2.0):
+        return self._call(lib().vb200_resize, float(scale), float(scale if vscale is None else vscale),
+                          _k(kernel), float(gap))
+
+    def premultiply(self, max_alpha=0.0, uchar=False):
+        return self._call(lib().vb200_premultiply, float(max_alpha), int(uchar))
+
+    def unpremultiply(self, max_alpha=0.0, uchar=False):
+        return self._call(lib().vb200_unpremultiply, float(max_alpha), int(uchar))
+
+    def thumbnail_image(self, width, height=None, size="both", linear=False):
+        return self._call(lib().vb200_thumbnail_image, int(width), int(height or 0), SIZES[size], int(linear))
+
+
+class ThumbnailPlan:
+    """The batched tile pump (vb200_thumbnail_plan_* in include/vb200.h)."""
+
+    def __init__(self, width, height, bands=4, target_width=512, target_height=None, size="both",
+                 has_alpha=None, linear=False):
+        if has_alpha is None:
+            has_alpha = bands in (2, 4)
+        self.width, self.height, self.bands = width, height, bands
+        self._p = lib().vb200_thumbnail_plan_new(width, height, bands, 0, int(has_alpha), target_width,
+                                                 target_height or 0, SIZES[size], int(linear))
+        if not self._p:
+            _check(-1)
+        ow, oh = C.c_int(), C.c_int()
+        lib().vb200_thumbnail_plan_output(self._p, C.byref(ow), C.byref(oh))
+        self.out_width, self.out_height = ow.value, oh.value
+        self.in_frame_bytes = width * height * bands
+        self.out_frame_bytes = self.out_width * self.out_height * bands
+        self.bytes_per_frame = int(lib().vb200_thumbnail_plan_bytes_per_frame(self._p))
+        self.fused = bool(lib().vb200_thumbnail_plan_is_fused(self._p))
+
+    def close(self):
+        if self._p:
+            lib().vb200_thumbnail_plan_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_device(self, in_ptr, out_ptr, n_frames, in_stride=None, out_stride=None):
+        """Device pointers (ints); queued on the stream set with set_stream()."""
+        _check(lib().vb200_thumbnail_batch_device(self._p, C.c_void_p(in_ptr), in_stride or self.in_frame_bytes,
+                                                  C.c_void_p(out_ptr), out_stride or self.out_frame_bytes,
+                                                  n_frames))
+
+    def run_host_ptr(self, in_ptr, out_ptr, n_frames):
+        _check(lib().vb200_thumbnail_batch_host(self._p, C.c_void_p(in_ptr), self.in_frame_bytes,
+                                                C.c_void_p(out_ptr), self.out_frame_bytes, n_frames))
+
+    def run_host(self, frames):
+        """frames: uint8 array [n, H, W, bands] in host memory -> [n, OH, OW, bands]."""
+        frames = np.ascontiguousarray(frames)
+        assert frames.dtype == np.uint8 and frames.shape[1:] == (self.height, self.width, self.bands)
+        out = np.empty((frames.shape[0], self.out_height, self.out_width, self.bands), np.uint8)
+        self.run_host_ptr(frames.ctypes.data, out.ctypes.data, frames.shape[0])
+        return out

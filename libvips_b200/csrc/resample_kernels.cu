@@ -1,0 +1,849 @@
+/* resample_kernels.cu -- leaf resample kernels (one per reference generate
+ * function) for every real band format except double, on device-resident
+ * images.  The headline uchar RGBA thumbnail chain has its own fused kernel
+ * (thumbnail_fused.cu); these are the general-format / general-band path and
+ * the building blocks of vb200_resize().
+ *
+ * reference arithmetic:
+ *   shrinkv   resample/shrinkv.c:158-266   (ADD, UCHAR_AVG, USHORT_AVG, IAVG, FAVG)
+ *   shrinkh   resample/shrinkh.c:78-152    (UCHAR_SHRINK, USHORT_SHRINK, ISHRINK, FSHRINK)
+ *   reducev   resample/reducev.cpp:420-496 (reducev_block + *_tab finalizers)
+ *   reduceh   resample/reduceh.cpp:145-193 (reduce_sum per band + finalizers)
+ *   pre/unpre conversion/premultiply.c:86-166, unpremultiply.c:85-222
+ * Edge pixels: every vips_embed(..., EXTEND_COPY) in front of these ops
+ * (conversion/embed.c:300-336) is clamp addressing here.
+ *
+ * Float paths accumulate in double with explicit round-to-nearest mul/add
+ * (__dmul_rn/__dadd_rn) so nvcc cannot contract them into FMAs: the reference
+ * build (x86-64 baseline) has none.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "vb200_internal.h"
+
+namespace vb200 {
+
+namespace {
+
+template <typename T> struct Acc { typedef int type; };
+template <> struct Acc<uint32_t> { typedef long long type; };
+template <> struct Acc<int32_t> { typedef long long type; };
+template <> struct Acc<float> { typedef double type; };
+
+template <typename T> struct Limits;
+template <> struct Limits<uint8_t> { static constexpr long long lo = 0, hi = 255; static constexpr bool sgn = false; };
+template <> struct Limits<int8_t> { static constexpr long long lo = -128, hi = 127; static constexpr bool sgn = true; };
+template <> struct Limits<uint16_t> { static constexpr long long lo = 0, hi = 65535; static constexpr bool sgn = false; };
+template <> struct Limits<int16_t> { static constexpr long long lo = -32768, hi = 32767; static constexpr bool sgn = true; };
+template <> struct Limits<uint32_t> { static constexpr long long lo = 0, hi = 4294967295LL; static constexpr bool sgn = false; };
+template <> struct Limits<int32_t> { static constexpr long long lo = -2147483648LL, hi = 2147483647LL; static constexpr bool sgn = true; };
+
+__device__ __forceinline__ int
+clampi(int v, int lo, int hi)
+{
+	return max(lo, min(v, hi));
+}
+
+/* unsigned_fixed_round / signed_fixed_round + VIPS_CLIP, templates.h:150-210 */
+template <typename T, typename IT>
+__device__ __forceinline__ T
+fixed_finalize(IT sum)
+{
+	IT v;
+	if (Limits<T>::sgn) {
+		const int round_by = sum >= 0 ? (VB200_INTERPOLATE_SCALE >> 1) : -(VB200_INTERPOLATE_SCALE >> 1);
+		v = (sum + round_by) >> VB200_INTERPOLATE_SHIFT;
+	}
+	else
+		v = (sum + (VB200_INTERPOLATE_SCALE >> 1)) >> VB200_INTERPOLATE_SHIFT;
+	long long w = v;
+	w = w < Limits<T>::lo ? Limits<T>::lo : (w > Limits<T>::hi ? Limits<T>::hi : w);
+	return (T) w;
+}
+
+/* ------------------------------------------------------------------ shrinkv */
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+shrinkv_kernel(const T *__restrict__ in, size_t in_bpl, int in_h, T *__restrict__ out, size_t out_bpl, int ne,
+	int vshrink, unsigned int mult8, unsigned long long mult16)
+{
+	typedef typename Acc<T>::type ACC;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= ne)
+		return;
+
+	const char *base = (const char *) in;
+	ACC sum = 0;
+	for (int k = 0; k < vshrink; k++) {
+		const int row = min(y * vshrink + k, in_h - 1);
+		const T v = ((const T *) (base + (size_t) row * in_bpl))[x];
+		sum += (ACC) v;
+	}
+
+	T *q = (T *) ((char *) out + (size_t) y * out_bpl) + x;
+	const int amend = vshrink / 2;
+	if constexpr (sizeof(T) == 1 && !Limits<T>::sgn)
+		*q = (T) ((((unsigned int) ((int) sum + amend)) * mult8) >> 24);
+	else if constexpr (sizeof(T) == 2 && !Limits<T>::sgn)
+		*q = (T) (((unsigned long long) ((int) sum + amend) * mult16) >> 32);
+	else
+		*q = (T) ((sum + (ACC) amend) / (ACC) vshrink);
+}
+
+template <>
+__global__ void __launch_bounds__(256)
+shrinkv_kernel<float>(const float *__restrict__ in, size_t in_bpl, int in_h, float *__restrict__ out, size_t out_bpl,
+	int ne, int vshrink, unsigned int, unsigned long long)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= ne)
+		return;
+	const char *base = (const char *) in;
+	double sum = 0.0;
+	for (int k = 0; k < vshrink; k++) {
+		const int row = min(y * vshrink + k, in_h - 1);
+		sum = __dadd_rn(sum, (double) ((const float *) (base + (size_t) row * in_bpl))[x]);
+	}
+	const double inv = 1.0 / vshrink;
+	((float *) ((char *) out + (size_t) y * out_bpl))[x] = (float) __dmul_rn(sum, inv);
+}
+
+/* uchar, 4 elements per thread: one 32-bit load per row, two 16-bit lanes per
+ * accumulator word (a lane holds at most 255 * vshrink <= 65535).
+ */
+__global__ void __launch_bounds__(256)
+shrinkv_u8x4_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uint8_t *__restrict__ out,
+	size_t out_bpl, int nwords, int vshrink, unsigned int mult8)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= nwords)
+		return;
+	unsigned int lo = 0, hi = 0; /* bytes 0,2 and bytes 1,3 */
+	for (int k = 0; k < vshrink; k++) {
+		const int row = min(y * vshrink + k, in_h - 1);
+		const unsigned int v = __ldg((const unsigned int *) (in + (size_t) row * in_bpl) + x);
+		lo += v & 0x00ff00ffu;
+		hi += (v >> 8) & 0x00ff00ffu;
+	}
+	const unsigned int amend = vshrink / 2;
+	const unsigned int b0 = (((lo & 0xffffu) + amend) * mult8) >> 24;
+	const unsigned int b2 = (((lo >> 16) + amend) * mult8) >> 24;
+	const unsigned int b1 = (((hi & 0xffffu) + amend) * mult8) >> 24;
+	const unsigned int b3 = (((hi >> 16) + amend) * mult8) >> 24;
+	((unsigned int *) (out + (size_t) y * out_bpl))[x] = (b0 & 0xff) | ((b1 & 0xff) << 8) | ((b2 & 0xff) << 16) | (b3 << 24);
+}
+
+/* ------------------------------------------------------------------ shrinkh */
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+shrinkh_kernel(const T *__restrict__ in, size_t in_bpl, int in_w, T *__restrict__ out, size_t out_bpl, int out_w,
+	int bands, int hshrink, unsigned int mult8, unsigned long long mult16)
+{
+	typedef typename Acc<T>::type ACC;
+	const int e = blockIdx.x * blockDim.x + threadIdx.x; /* output element on the row */
+	const int y = blockIdx.y;
+	if (e >= out_w * bands)
+		return;
+	const int x = e / bands;
+	const int b = e - x * bands;
+	const T *p = (const T *) ((const char *) in + (size_t) y * in_bpl);
+	T *q = (T *) ((char *) out + (size_t) y * out_bpl) + e;
+	const int amend = hshrink / 2;
+
+	if constexpr (sizeof(T) <= 2) {
+		int sum = amend;
+		for (int k = 0; k < hshrink; k++)
+			sum += p[(size_t) min(x * hshrink + k, in_w - 1) * bands + b];
+		if constexpr (sizeof(T) == 1 && !Limits<T>::sgn)
+			*q = (T) (((unsigned int) sum * mult8) >> 24);
+		else if constexpr (sizeof(T) == 2 && !Limits<T>::sgn)
+			*q = (T) (((unsigned long long) sum * mult16) >> 32);
+		else
+			*q = (T) (sum / hshrink);
+	}
+	else {
+		long long sum = amend;
+		for (int k = 0; k < hshrink; k++)
+			sum += p[(size_t) min(x * hshrink + k, in_w - 1) * bands + b];
+		*q = (T) (sum / hshrink);
+	}
+}
+
+template <>
+__global__ void __launch_bounds__(256)
+shrinkh_kernel<float>(const float *__restrict__ in, size_t in_bpl, int in_w, float *__restrict__ out, size_t out_bpl,
+	int out_w, int bands, int hshrink, unsigned int, unsigned long long)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (e >= out_w * bands)
+		return;
+	const int x = e / bands;
+	const int b = e - x * bands;
+	const float *p = (const float *) ((const char *) in + (size_t) y * in_bpl);
+	double sum = 0.0;
+	for (int k = 0; k < hshrink; k++)
+		sum = __dadd_rn(sum, (double) p[(size_t) min(x * hshrink + k, in_w - 1) * bands + b]);
+	const double inv = 1.0 / hshrink;
+	((float *) ((char *) out + (size_t) y * out_bpl))[e] = (float) __dmul_rn(sum, inv);
+}
+
+/* ------------------------------------------------------------------ reducev */
+
+struct AxisDev {
+	const int *first;
+	const int *phase;
+	const short *ms;
+	const double *mf;
+	int n_point;
+	int embed;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+reducev_kernel(const T *__restrict__ in, size_t in_bpl, int in_h, T *__restrict__ out, size_t out_bpl, int ne,
+	AxisDev t)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= ne)
+		return;
+	const int py = t.first[y] - t.embed;
+	const int n = t.n_point;
+	const char *base = (const char *) in;
+	T *q = (T *) ((char *) out + (size_t) y * out_bpl) + x;
+
+	if constexpr (sizeof(T) == 4) {
+		/* 32-bit ints: int64 sum */
+		const short *c = t.ms + (size_t) t.phase[y] * n;
+		long long sum = 0;
+		for (int i = 0; i < n; i++) {
+			const int row = clampi(py + i, 0, in_h - 1);
+			sum += (long long) c[i] * (long long) ((const T *) (base + (size_t) row * in_bpl))[x];
+		}
+		*q = fixed_finalize<T, long long>(sum);
+	}
+	else {
+		const short *c = t.ms + (size_t) t.phase[y] * n;
+		int sum = 0;
+		for (int i = 0; i < n; i++) {
+			const int row = clampi(py + i, 0, in_h - 1);
+			sum += (int) c[i] * (int) ((const T *) (base + (size_t) row * in_bpl))[x];
+		}
+		*q = fixed_finalize<T, int>(sum);
+	}
+}
+
+template <>
+__global__ void __launch_bounds__(256)
+reducev_kernel<float>(const float *__restrict__ in, size_t in_bpl, int in_h, float *__restrict__ out, size_t out_bpl,
+	int ne, AxisDev t)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= ne)
+		return;
+	const int py = t.first[y] - t.embed;
+	const int n = t.n_point;
+	const double *c = t.mf + (size_t) t.phase[y] * n;
+	const char *base = (const char *) in;
+	double sum = 0.0;
+	for (int i = 0; i < n; i++) {
+		const int row = clampi(py + i, 0, in_h - 1);
+		sum = __dadd_rn(sum, __dmul_rn(c[i], (double) ((const float *) (base + (size_t) row * in_bpl))[x]));
+	}
+	((float *) ((char *) out + (size_t) y * out_bpl))[x] = (float) sum;
+}
+
+/* uchar, 4 bytes per thread */
+__global__ void __launch_bounds__(256)
+reducev_u8x4_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uint8_t *__restrict__ out,
+	size_t out_bpl, int nwords, AxisDev t)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= nwords)
+		return;
+	const int py = t.first[y] - t.embed;
+	const int n = t.n_point;
+	const short *c = t.ms + (size_t) t.phase[y] * n;
+	int s0 = 2048, s1 = 2048, s2 = 2048, s3 = 2048;
+	for (int i = 0; i < n; i++) {
+		const int row = clampi(py + i, 0, in_h - 1);
+		const unsigned int v = __ldg((const unsigned int *) (in + (size_t) row * in_bpl) + x);
+		const int ci = c[i];
+		s0 += ci * (int) (v & 0xff);
+		s1 += ci * (int) ((v >> 8) & 0xff);
+		s2 += ci * (int) ((v >> 16) & 0xff);
+		s3 += ci * (int) (v >> 24);
+	}
+	const unsigned int b0 = clampi(s0 >> 12, 0, 255), b1 = clampi(s1 >> 12, 0, 255);
+	const unsigned int b2 = clampi(s2 >> 12, 0, 255), b3 = clampi(s3 >> 12, 0, 255);
+	((unsigned int *) (out + (size_t) y * out_bpl))[x] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+/* ------------------------------------------------------------------ reduceh */
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduceh_kernel(const T *__restrict__ in, size_t in_bpl, int in_w, T *__restrict__ out, size_t out_bpl, int out_w,
+	int bands, AxisDev t)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (e >= out_w * bands)
+		return;
+	const int x = e / bands;
+	const int z = e - x * bands;
+	const int ix = t.first[x] - t.embed;
+	const int n = t.n_point;
+	const T *p = (const T *) ((const char *) in + (size_t) y * in_bpl) + z;
+	T *q = (T *) ((char *) out + (size_t) y * out_bpl) + e;
+	const short *c = t.ms + (size_t) t.phase[x] * n;
+
+	if constexpr (sizeof(T) == 4) {
+		long long sum = 0;
+		for (int i = 0; i < n; i++)
+			sum += (long long) c[i] * (long long) p[(size_t) clampi(ix + i, 0, in_w - 1) * bands];
+		*q = fixed_finalize<T, long long>(sum);
+	}
+	else {
+		int sum = 0;
+		for (int i = 0; i < n; i++)
+			sum += (int) c[i] * (int) p[(size_t) clampi(ix + i, 0, in_w - 1) * bands];
+		*q = fixed_finalize<T, int>(sum);
+	}
+}
+
+template <>
+__global__ void __launch_bounds__(256)
+reduceh_kernel<float>(const float *__restrict__ in, size_t in_bpl, int in_w, float *__restrict__ out, size_t out_bpl,
+	int out_w, int bands, AxisDev t)
+{
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (e >= out_w * bands)
+		return;
+	const int x = e / bands;
+	const int z = e - x * bands;
+	const int ix = t.first[x] - t.embed;
+	const int n = t.n_point;
+	const float *p = (const float *) ((const char *) in + (size_t) y * in_bpl) + z;
+	const double *c = t.mf + (size_t) t.phase[x] * n;
+	double sum = 0.0;
+	for (int i = 0; i < n; i++)
+		sum = __dadd_rn(sum, __dmul_rn(c[i], (double) p[(size_t) clampi(ix + i, 0, in_w - 1) * bands]));
+	((float *) ((char *) out + (size_t) y * out_bpl))[e] = (float) sum;
+}
+
+/* ------------------------------------------------- premultiply / unpremultiply */
+
+/* uchar -> uchar 8.8 LUT path.  The LUT is built in the prologue with IEEE
+ * double mul/div (correctly rounded on host and device alike):
+ *   pre:   scale[i] = (int) (256 * clip(i) / max_alpha)          premultiply.c:253-259
+ *   unpre: scale[i] = clip == 0 ? 0 : (int) (256 * max_alpha / clip)  unpremultiply.c:313-324
+ * out = (in * scale[alpha] + 128) >> 8 stored as a byte (no clip).
+ */
+template <bool UNPRE>
+__global__ void __launch_bounds__(256)
+premul_u8_kernel(const uint8_t *__restrict__ in, size_t in_bpl, uint8_t *__restrict__ out, size_t out_bpl, int w,
+	int bands, double max_alpha)
+{
+	__shared__ int scale[256];
+	{
+		const int i = threadIdx.x;
+		const double clip = fmax(0.0, fmin(max_alpha, (double) i));
+		if (UNPRE)
+			scale[i] = clip == 0 ? 0 : (int) __ddiv_rn(__dmul_rn(256.0, max_alpha), clip);
+		else
+			scale[i] = (int) __ddiv_rn(__dmul_rn(256.0, clip), max_alpha);
+	}
+	__syncthreads();
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= w)
+		return;
+	const uint8_t *p = in + (size_t) y * in_bpl + (size_t) x * bands;
+	uint8_t *q = out + (size_t) y * out_bpl + (size_t) x * bands;
+	if (bands == 4) {
+		const unsigned int v = *(const unsigned int *) p;
+		const int s = scale[v >> 24];
+		const unsigned int r = (((v & 0xff) * s + 128) >> 8) & 0xff;
+		const unsigned int g = ((((v >> 8) & 0xff) * s + 128) >> 8) & 0xff;
+		const unsigned int b = ((((v >> 16) & 0xff) * s + 128) >> 8) & 0xff;
+		*(unsigned int *) q = r | (g << 8) | (b << 16) | (v & 0xff000000u);
+		return;
+	}
+	const uint8_t alpha = p[bands - 1];
+	const int s = scale[alpha];
+	int i;
+	for (i = 0; i < bands - 1; i++)
+		q[i] = (uint8_t) ((p[i] * s + 128) >> 8);
+	q[i] = alpha;
+}
+
+/* PRE_* : OUT nalpha = (OUT) clip_alpha / max_alpha; q = p * nalpha  (premultiply.c:86-122) */
+template <typename IN>
+__global__ void __launch_bounds__(256)
+premul_float_kernel(const IN *__restrict__ in, size_t in_bpl, float *__restrict__ out, size_t out_bpl, int w,
+	int bands, double max_alpha)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= w)
+		return;
+	const IN *p = (const IN *) ((const char *) in + (size_t) y * in_bpl) + (size_t) x * bands;
+	float *q = (float *) ((char *) out + (size_t) y * out_bpl) + (size_t) x * bands;
+	const IN alpha = p[bands - 1];
+	/* VIPS_CLIP(0, alpha, max_alpha) is evaluated in double, assigned to IN */
+	const IN clip_alpha = (IN) fmax(0.0, fmin(max_alpha, (double) alpha));
+	const float nalpha = (float) __ddiv_rn((double) (float) clip_alpha, max_alpha);
+	int i;
+	for (i = 0; i < bands - 1; i++)
+		q[i] = __fmul_rn((float) p[i], nalpha);
+	q[i] = (float) alpha;
+}
+
+/* UNPRE_* / FUNPRE_*  (unpremultiply.c:85-183), alpha_band = bands - 1 */
+template <typename IN, bool FP>
+__global__ void __launch_bounds__(256)
+unpremul_float_kernel(const IN *__restrict__ in, size_t in_bpl, float *__restrict__ out, size_t out_bpl, int w,
+	int bands, double max_alpha)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= w)
+		return;
+	const IN *p = (const IN *) ((const char *) in + (size_t) y * in_bpl) + (size_t) x * bands;
+	float *q = (float *) ((char *) out + (size_t) y * out_bpl) + (size_t) x * bands;
+	const IN alpha = p[bands - 1];
+	float factor;
+	if (FP)
+		factor = fabs((double) alpha) < 0.01 ? 0.0f : (float) __ddiv_rn(max_alpha, (double) alpha);
+	else
+		factor = alpha == 0 ? 0.0f : (float) __ddiv_rn(max_alpha, (double) alpha);
+	for (int i = 0; i < bands - 1; i++)
+		q[i] = __fmul_rn(factor, (float) p[i]);
+	q[bands - 1] = (float) fmax(0.0, fmin(max_alpha, (double) alpha));
+}
+
+inline dim3
+row_grid(int elems, int rows, int threads = 256)
+{
+	return dim3((elems + threads - 1) / threads, rows);
+}
+
+bool
+aligned4(const void *p, size_t bpl)
+{
+	return (((uintptr_t) p) & 3) == 0 && (bpl & 3) == 0;
+}
+
+/* Upload an AxisTable as one packed block; the AxisDev points into it. */
+int
+upload_axis(const char *domain, const AxisTable &t, AxisDev *d, void **block, cudaStream_t s)
+{
+	const size_t n_first = t.first.size() * sizeof(int);
+	const size_t n_ms = t.ms.size() * sizeof(short);
+	const size_t n_mf = t.mf.size() * sizeof(double);
+	const size_t off_mf = 0;
+	const size_t off_first = off_mf + n_mf;
+	const size_t off_phase = off_first + n_first;
+	const size_t off_ms = off_phase + n_first;
+	const size_t total = off_ms + n_ms;
+
+	std::vector<char> host(total);
+	memcpy(&host[off_mf], t.mf.data(), n_mf);
+	memcpy(&host[off_first], t.first.data(), n_first);
+	memcpy(&host[off_phase], t.phase.data(), n_first);
+	memcpy(&host[off_ms], t.ms.data(), n_ms);
+
+	if (dev_alloc(domain, block, total, s))
+		return -1;
+	VB200_CUDA(domain, cudaMemcpyAsync(*block, host.data(), total, cudaMemcpyHostToDevice, s));
+	/* pageable source: the copy has been staged when the call returns */
+	char *b = (char *) *block;
+	d->mf = (const double *) (b + off_mf);
+	d->first = (const int *) (b + off_first);
+	d->phase = (const int *) (b + off_phase);
+	d->ms = (const short *) (b + off_ms);
+	d->n_point = t.n_point;
+	d->embed = t.embed;
+	return 0;
+}
+
+int
+check_launch(const char *domain, const char *what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return cuda_fail(domain, e, what);
+	count_launch();
+	return 0;
+}
+
+} // namespace
+
+/* ------------------------------------------------------------- launchers */
+
+int
+launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne,
+	int out_rows, int fmt, const AxisTable &t, cudaStream_t s)
+{
+	AxisDev d;
+	void *block = nullptr;
+	if (upload_axis(domain, t, &d, &block, s))
+		return -1;
+
+#define RV(T) reducev_kernel<T><<<row_grid(ne, out_rows), 256, 0, s>>>((const T *) in, in_bpl, in_h, (T *) out, out_bpl, ne, d)
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR:
+		if ((ne & 3) == 0 && aligned4(in, in_bpl) && aligned4(out, out_bpl))
+			reducev_u8x4_kernel<<<row_grid(ne / 4, out_rows), 256, 0, s>>>((const uint8_t *) in, in_bpl, in_h,
+				(uint8_t *) out, out_bpl, ne / 4, d);
+		else
+			RV(uint8_t);
+		break;
+	case VB200_FORMAT_CHAR: RV(int8_t); break;
+	case VB200_FORMAT_USHORT: RV(uint16_t); break;
+	case VB200_FORMAT_SHORT: RV(int16_t); break;
+	case VB200_FORMAT_UINT: RV(uint32_t); break;
+	case VB200_FORMAT_INT: RV(int32_t); break;
+	case VB200_FORMAT_FLOAT: RV(float); break;
+	default:
+		dev_free(block, s);
+		error(domain, "band format %d not supported on the device path", fmt);
+		return -1;
+	}
+#undef RV
+	int r = check_launch(domain, "reducev kernel");
+	dev_free(block, s);
+	return r;
+}
+
+int
+launch_reduceh(const char *domain, const void *in, size_t in_bpl, int in_w, void *out, size_t out_bpl, int bands,
+	int out_cols, int rows, int fmt, const AxisTable &t, cudaStream_t s)
+{
+	AxisDev d;
+	void *block = nullptr;
+	if (upload_axis(domain, t, &d, &block, s))
+		return -1;
+
+#define RH(T) reduceh_kernel<T><<<row_grid(out_cols * bands, rows), 256, 0, s>>>((const T *) in, in_bpl, in_w, (T *) out, out_bpl, out_cols, bands, d)
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR: RH(uint8_t); break;
+	case VB200_FORMAT_CHAR: RH(int8_t); break;
+	case VB200_FORMAT_USHORT: RH(uint16_t); break;
+	case VB200_FORMAT_SHORT: RH(int16_t); break;
+	case VB200_FORMAT_UINT: RH(uint32_t); break;
+	case VB200_FORMAT_INT: RH(int32_t); break;
+	case VB200_FORMAT_FLOAT: RH(float); break;
+	default:
+		dev_free(block, s);
+		error(domain, "band format %d not supported on the device path", fmt);
+		return -1;
+	}
+#undef RH
+	int r = check_launch(domain, "reduceh kernel");
+	dev_free(block, s);
+	return r;
+}
+
+/* ------------------------------------------------------------- device ops */
+
+int
+dev_shrinkv(const char *domain, const DevImage &in, DevImage *out, int vshrink, int ceil_mode, cudaStream_t s)
+{
+	if (vshrink < 1) {
+		error(domain, "shrink factors should be >= 1");
+		return -1;
+	}
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	if (vshrink == 1) {
+		*out = in;
+		out->owned = false;
+		return 0;
+	}
+	const int oh = shrink_size(in.h, vshrink, ceil_mode);
+	if (oh <= 0) {
+		error(domain, "image has shrunk to nothing");
+		return -1;
+	}
+	if (dev_image_new(domain, out, in.w, oh, in.bands, in.fmt, in.type, s))
+		return -1;
+	const int ne = in.w * in.bands;
+	const unsigned int mult8 = (unsigned int) ((1LL << 32) / ((1 << 8) * (long long) vshrink));
+	const unsigned long long mult16 = ((1ULL << 32) + vshrink - 1) / vshrink;
+
+#define SV(T) shrinkv_kernel<T><<<row_grid(ne, oh), 256, 0, s>>>((const T *) in.data, in.bpl, in.h, (T *) out->data, out->bpl, ne, vshrink, mult8, mult16)
+	switch (in.fmt) {
+	case VB200_FORMAT_UCHAR:
+		if ((ne & 3) == 0 && aligned4(in.data, in.bpl) && aligned4(out->data, out->bpl) && vshrink <= 257)
+			shrinkv_u8x4_kernel<<<row_grid(ne / 4, oh), 256, 0, s>>>((const uint8_t *) in.data, in.bpl, in.h,
+				(uint8_t *) out->data, out->bpl, ne / 4, vshrink, mult8);
+		else
+			SV(uint8_t);
+		break;
+	case VB200_FORMAT_CHAR: SV(int8_t); break;
+	case VB200_FORMAT_USHORT: SV(uint16_t); break;
+	case VB200_FORMAT_SHORT: SV(int16_t); break;
+	case VB200_FORMAT_UINT: SV(uint32_t); break;
+	case VB200_FORMAT_INT: SV(int32_t); break;
+	case VB200_FORMAT_FLOAT: SV(float); break;
+	}
+#undef SV
+	return check_launch(domain, "shrinkv kernel");
+}
+
+int
+dev_shrinkh(const char *domain, const DevImage &in, DevImage *out, int hshrink, int ceil_mode, cudaStream_t s)
+{
+	if (hshrink < 1) {
+		error(domain, "shrink factors should be >= 1");
+		return -1;
+	}
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	if (hshrink == 1) {
+		*out = in;
+		out->owned = false;
+		return 0;
+	}
+	const int ow = shrink_size(in.w, hshrink, ceil_mode);
+	if (ow <= 0) {
+		error(domain, "image has shrunk to nothing");
+		return -1;
+	}
+	if (dev_image_new(domain, out, ow, in.h, in.bands, in.fmt, in.type, s))
+		return -1;
+	const unsigned int mult8 = (unsigned int) ((1LL << 32) / ((1 << 8) * (long long) hshrink));
+	const unsigned long long mult16 = ((1ULL << 32) + hshrink - 1) / hshrink;
+
+#define SH(T) shrinkh_kernel<T><<<row_grid(ow * in.bands, in.h), 256, 0, s>>>((const T *) in.data, in.bpl, in.w, (T *) out->data, out->bpl, ow, in.bands, hshrink, mult8, mult16)
+	switch (in.fmt) {
+	case VB200_FORMAT_UCHAR: SH(uint8_t); break;
+	case VB200_FORMAT_CHAR: SH(int8_t); break;
+	case VB200_FORMAT_USHORT: SH(uint16_t); break;
+	case VB200_FORMAT_SHORT: SH(int16_t); break;
+	case VB200_FORMAT_UINT: SH(uint32_t); break;
+	case VB200_FORMAT_INT: SH(int32_t); break;
+	case VB200_FORMAT_FLOAT: SH(float); break;
+	}
+#undef SH
+	return check_launch(domain, "shrinkh kernel");
+}
+
+int
+dev_reducev_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel, int rect_h,
+	cudaStream_t s)
+{
+	AxisTable t;
+	build_axis_table(t, g.out_size, g.residual, g.offset, g.n_point, kernel, rect_h);
+	if (dev_image_new(domain, out, in.w, g.out_size, in.bands, in.fmt, in.type, s))
+		return -1;
+	return launch_reducev(domain, in.data, in.bpl, in.h, out->data, out->bpl, in.w * in.bands, g.out_size, in.fmt, t, s);
+}
+
+int
+dev_reduceh_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel, int rect_w,
+	cudaStream_t s)
+{
+	AxisTable t;
+	build_axis_table(t, g.out_size, g.residual, g.offset, g.n_point, kernel, rect_w);
+	if (dev_image_new(domain, out, g.out_size, in.h, in.bands, in.fmt, in.type, s))
+		return -1;
+	return launch_reduceh(domain, in.data, in.bpl, in.w, out->data, out->bpl, in.bands, g.out_size, in.h, in.fmt, t, s);
+}
+
+int
+dev_reducev(const char *domain, const DevImage &in, DevImage *out, double vshrink, int kernel, double gap, int rect_h,
+	cudaStream_t s)
+{
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	ReduceGeom g;
+	if (reduce_geometry(domain, in.h, vshrink, kernel, gap, &g))
+		return -1;
+	DevImage box;
+	if (dev_shrinkv(domain, in, &box, g.int_shrink, 1, s))
+		return -1;
+	if (g.n_point == 0) {
+		*out = box;
+		return 0;
+	}
+	int r = dev_reducev_pass(domain, box, out, g, kernel, rect_h, s);
+	dev_image_release(&box, s);
+	return r;
+}
+
+int
+dev_reduceh(const char *domain, const DevImage &in, DevImage *out, double hshrink, int kernel, double gap, int rect_w,
+	cudaStream_t s)
+{
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	ReduceGeom g;
+	if (reduce_geometry(domain, in.w, hshrink, kernel, gap, &g))
+		return -1;
+	DevImage box;
+	if (dev_shrinkh(domain, in, &box, g.int_shrink, 1, s))
+		return -1;
+	if (g.n_point == 0) {
+		*out = box;
+		return 0;
+	}
+	int r = dev_reduceh_pass(domain, box, out, g, kernel, rect_w, s);
+	dev_image_release(&box, s);
+	return r;
+}
+
+int
+dev_premultiply(const char *domain, const DevImage &in, DevImage *out, double max_alpha, int uchar_mode, cudaStream_t s)
+{
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	if (in.bands == 1) {
+		*out = in;
+		out->owned = false;
+		return 0;
+	}
+	if (max_alpha <= 0)
+		max_alpha = interpretation_max_alpha(in.type);
+	const bool lut = uchar_mode && in.fmt == VB200_FORMAT_UCHAR;
+	if (dev_image_new(domain, out, in.w, in.h, in.bands, lut ? VB200_FORMAT_UCHAR : VB200_FORMAT_FLOAT, in.type, s))
+		return -1;
+	const dim3 grid = row_grid(in.w, in.h);
+#define PM(T) premul_float_kernel<T><<<grid, 256, 0, s>>>((const T *) in.data, in.bpl, (float *) out->data, out->bpl, in.w, in.bands, max_alpha)
+	if (lut)
+		premul_u8_kernel<false><<<grid, 256, 0, s>>>((const uint8_t *) in.data, in.bpl, (uint8_t *) out->data,
+			out->bpl, in.w, in.bands, max_alpha);
+	else
+		switch (in.fmt) {
+		case VB200_FORMAT_UCHAR: PM(uint8_t); break;
+		case VB200_FORMAT_CHAR: PM(int8_t); break;
+		case VB200_FORMAT_USHORT: PM(uint16_t); break;
+		case VB200_FORMAT_SHORT: PM(int16_t); break;
+		case VB200_FORMAT_UINT: PM(uint32_t); break;
+		case VB200_FORMAT_INT: PM(int32_t); break;
+		case VB200_FORMAT_FLOAT: PM(float); break;
+		}
+#undef PM
+	return check_launch(domain, "premultiply kernel");
+}
+
+int
+dev_unpremultiply(const char *domain, const DevImage &in, DevImage *out, double max_alpha, int uchar_mode,
+	cudaStream_t s)
+{
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	if (in.bands == 1) {
+		*out = in;
+		out->owned = false;
+		return 0;
+	}
+	if (max_alpha <= 0)
+		max_alpha = interpretation_max_alpha(in.type);
+	const bool lut = uchar_mode && in.fmt == VB200_FORMAT_UCHAR;
+	if (dev_image_new(domain, out, in.w, in.h, in.bands, lut ? VB200_FORMAT_UCHAR : VB200_FORMAT_FLOAT, in.type, s))
+		return -1;
+	const dim3 grid = row_grid(in.w, in.h);
+#define UPM(T, FP) unpremul_float_kernel<T, FP><<<grid, 256, 0, s>>>((const T *) in.data, in.bpl, (float *) out->data, out->bpl, in.w, in.bands, max_alpha)
+	if (lut)
+		premul_u8_kernel<true><<<grid, 256, 0, s>>>((const uint8_t *) in.data, in.bpl, (uint8_t *) out->data,
+			out->bpl, in.w, in.bands, max_alpha);
+	else
+		switch (in.fmt) {
+		case VB200_FORMAT_UCHAR: UPM(uint8_t, false); break;
+		case VB200_FORMAT_CHAR: UPM(int8_t, false); break;
+		case VB200_FORMAT_USHORT: UPM(uint16_t, false); break;
+		case VB200_FORMAT_SHORT: UPM(int16_t, false); break;
+		case VB200_FORMAT_UINT: UPM(uint32_t, false); break;
+		case VB200_FORMAT_INT: UPM(int32_t, false); break;
+		case VB200_FORMAT_FLOAT: UPM(float, true); break;
+		}
+#undef UPM
+	return check_launch(domain, "unpremultiply kernel");
+}
+
+/* vips_resize, downsizing half: resize.c:150-231.  Upsizing (affine) is in
+ * affine.cu.
+ */
+int
+dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel, double gap,
+	cudaStream_t s)
+{
+	hscale = std::max(hscale, 1.0 / in.w);
+	vscale = std::max(vscale, 1.0 / in.h);
+	if (hscale > 1.0 || vscale > 1.0) {
+		error(domain, "upsizing is not on the device path yet");
+		return -1;
+	}
+	const double vs = vscale < 1.0 ? 1.0 / vscale : 1.0;
+	const double hs = hscale < 1.0 ? 1.0 / hscale : 1.0;
+
+	ReduceGeom gv, gh;
+	gv.int_shrink = gh.int_shrink = 1;
+	gh.out_size = in.w;
+	if (vs > 1.0 && reduce_geometry(domain, in.h, vs, kernel, gap, &gv))
+		return -1;
+	if (hs > 1.0 && reduce_geometry(domain, in.w, hs, kernel, gap, &gh))
+		return -1;
+
+	/* Sink tile geometry from the pipeline's demand hint: the minimum over
+	 * all ops (iofuncs/generate.c:275-293); shrinkv asks SMALLTILE
+	 * (shrinkv.c:553), reducev/reduceh FATSTRIP.  vips_get_tile_size,
+	 * iofuncs/thread.c:288-325.
+	 */
+	const TileGeometry tg = tile_geometry();
+	int tile_w, tile_h;
+	if (gv.int_shrink > 1) {
+		tile_w = tg.tile_width;
+		tile_h = tg.tile_height;
+	}
+	else {
+		tile_w = gh.out_size;
+		tile_h = tg.fatstrip_height;
+	}
+	/* shrinkh chunks its requests into fatstrip-height strips (shrinkh.c:247-272):
+	 * that is the rect height reducev sees when a shrinkh sits downstream.
+	 */
+	int rect_h = tile_h;
+	if (gh.int_shrink > 1)
+		rect_h = std::min(rect_h, tg.fatstrip_height);
+
+	DevImage mid = in;
+	mid.owned = false;
+	if (vs > 1.0 && dev_reducev(domain, in, &mid, vs, kernel, gap, rect_h, s))
+		return -1;
+	if (hs > 1.0) {
+		int r = dev_reduceh(domain, mid, out, hs, kernel, gap, tile_w, s);
+		dev_image_release(&mid, s);
+		return r;
+	}
+	*out = mid;
+	return 0;
+}
+
+} // namespace vb200

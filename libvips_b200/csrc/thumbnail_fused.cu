@@ -1,0 +1,919 @@
+/* thumbnail_fused.cu -- ONE kernel for the whole uchar RGBA thumbnail chain
+ *
+ *   premultiply(uchar) -> shrinkv(box) -> reducev(kernel) -> shrinkh(box) -> reduceh(kernel) -> unpremultiply(uchar)
+ *
+ * i.e. what vips_thumbnail_image() builds for an 8-bit image with alpha
+ * (reference: resample/thumbnail.c:848-902 -> resize.c:213-231 ->
+ * reducev.cpp:898-922 / reduceh.cpp:436-460), with every intermediate uchar
+ * rounding of the unfused reference chain reproduced bit for bit.
+ *
+ * Work decomposition (HBM-bound design: each input byte is read once from
+ * DRAM, the 13-tap windows live in shared memory, nothing but the final
+ * thumbnail is written back):
+ *
+ *   CTA      = a band of TW output columns x RPC output rows of one frame.
+ *   thread   = one INPUT pixel column of the band (incl. the reduceh halo).  It
+ *              streams down the rows with coalesced 32-bit loads (a warp reads
+ *              128 contiguous bytes per row), premultiplies, box-sums vshrink
+ *              rows in 16-bit SIMD lanes, and keeps its private window of
+ *              box-shrunk rows in a shared-memory column, stored as
+ *              byte-transposed ROW PAIRS so that one dp2a does two taps.
+ *   per chunk of K output rows:
+ *     stage V  every thread: produce the row pairs the chunk needs, then K
+ *              reducev outputs (dp2a over the pair window) -> rv[K][cols]
+ *     stage H1 box-sum hshrink adjacent columns of rv -> column PAIRS sh[K][..]
+ *     stage H2 one thread per output pixel: reduceh (dp2a over column pairs),
+ *              unpremultiply, 32-bit coalesced store.
+ *
+ * Sampling positions come from host tables built by the same sequential
+ * double additions as the reference's generate functions (see
+ * build_axis_table), so fractional shrinks and tile-dependent phases match.
+ */
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "vb200_internal.h"
+
+namespace vb200 {
+
+namespace {
+
+constexpr int kChunkRows = 8; /* K */
+constexpr int kMaxThreads = 640; /* 2 CTAs per SM */
+
+struct FusedParams {
+	/* input frame geometry */
+	int W, H;
+	size_t in_bpl;
+	/* vertical */
+	int VS;		  /* box shrink */
+	int Hs;		  /* rows after the box shrink */
+	int vembed;	  /* ceil(n_v / 2) - 1 */
+	int NPv;	  /* coefficient pairs per vertical set */
+	unsigned vmul8; /* ((1 << 32) / (256 * VS)) << 8, for umulhi */
+	int vshift;	  /* log2(VS) if VS is a power of two, else -1 */
+	/* horizontal */
+	int HS, Ws, hembed, NPh;
+	unsigned hmul8;
+	int hshift;
+	int OW, OH;
+	size_t out_bpl;
+	/* decomposition */
+	int TW;	 /* output columns per CTA */
+	int RPC; /* output rows per CTA */
+	int NT;	 /* threads per CTA == pair-buffer column stride */
+	int NEmax; /* max embedded shrinkh columns per band (even) */
+	int slots;	/* pair slots per column */
+	/* tables */
+	const int2 *vrow;  /* [OH] {first pair (embedded rows >> 1), coefficient set} */
+	const int2 *hcol;  /* [OW] {first pair (embedded cols >> 1), coefficient set} */
+	const int *vcoef;  /* [nvsets][NPv] packed s16x2 */
+	const int *hcoef;  /* [nhsets][NPh] */
+	int nvsets, nhsets;
+	/* alpha */
+	int premul;		  /* 1: premultiply/unpremultiply with max_alpha */
+	double max_alpha; /* LUTs are derived from it in the prologue */
+};
+
+__device__ __forceinline__ int
+dp2a_lo(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
+
+__device__ __forceinline__ int
+dp2a_hi(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
+
+__device__ __forceinline__ unsigned
+ld_stream(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+
+/* Box-sum VS premultiplied rows of one pixel column into 16-bit lanes:
+ * rb = r | b << 16, ga = g | a << 16, both pre-loaded with the rounding amend.
+ */
+template <int VS, bool PREMUL>
+__device__ __forceinline__ void
+box_rows(const unsigned (&px)[VS], int vs, const int *pscale, bool lut, unsigned amend2, unsigned &rb, unsigned &ga)
+{
+	rb = amend2;
+	ga = amend2;
+#pragma unroll
+	for (int k = 0; k < VS; k++) {
+		const unsigned x = px[k];
+		if (PREMUL) {
+			/* out = (in * scale[alpha] + 128) >> 8, premultiply.c:152-166;
+			 * for max_alpha 255 scale[a] = a + (a == 255).
+			 */
+			const unsigned a = x >> 24;
+			const unsigned s = lut ? (unsigned) pscale[a] : a + (a == 255u);
+			const unsigned prb = (((x & 0x00ff00ffu) * s + 0x00800080u) >> 8) & 0x00ff00ffu;
+			const unsigned pg = ((((x >> 8) & 0xffu) * s + 128u) >> 8) & 0xffu;
+			rb += prb;
+			ga += pg + (a << 16);
+		}
+		else {
+			rb += x & 0x00ff00ffu;
+			ga += (x >> 8) & 0x00ff00ffu;
+		}
+	}
+}
+
+/* ((sum + amend) * multiplier) >> 24 per 16-bit lane (shrinkv.c:218-227),
+ * amend already inside; result lanes are bytes.
+ */
+__device__ __forceinline__ unsigned
+box_average(unsigned lanes, unsigned mul8, int shift)
+{
+	if (shift >= 0)
+		return (lanes >> shift) & 0x00ff00ffu;
+	const unsigned lo = __umulhi(lanes & 0xffffu, mul8);
+	const unsigned hi = __umulhi(lanes >> 16, mul8);
+	return lo | (hi << 16);
+}
+
+template <int VS, bool PREMUL>
+__global__ void __launch_bounds__(kMaxThreads, 2)
+thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
+	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	const int NT = P.NT;
+	const int t = threadIdx.x;
+	const int vs = VS > 0 ? VS : P.VS;
+
+	/* shared memory carve-up */
+	uint2 *pairbuf = (uint2 *) smem_raw;							  /* [slots][NT] */
+	unsigned *rv = (unsigned *) (pairbuf + (size_t) P.slots * NT); /* [K][NT] */
+	uint2 *sh = (uint2 *) (rv + (size_t) kChunkRows * NT);		  /* [K][NEmax / 2] column pairs */
+	int *vcoef = (int *) (sh + (size_t) kChunkRows * (P.NEmax / 2));
+	int *hcoef = vcoef + P.nvsets * P.NPv;
+	int *pscale = hcoef + P.nhsets * P.NPh; /* [256] premultiply LUT */
+	int *uscale = pscale + 256;				/* [256] unpremultiply LUT */
+
+	for (int i = t; i < P.nvsets * P.NPv; i += NT)
+		vcoef[i] = P.vcoef[i];
+	for (int i = t; i < P.nhsets * P.NPh; i += NT)
+		hcoef[i] = P.hcoef[i];
+	if (PREMUL)
+		for (int i = t; i < 256; i += NT) {
+			/* premultiply.c:253-259, unpremultiply.c:313-324 (IEEE double, exact on device) */
+			const double clip = fmax(0.0, fmin(P.max_alpha, (double) i));
+			pscale[i] = (int) __ddiv_rn(__dmul_rn(256.0, clip), P.max_alpha);
+			uscale[i] = clip == 0 ? 0 : (int) __ddiv_rn(__dmul_rn(256.0, P.max_alpha), clip);
+		}
+	const bool lut = PREMUL && P.max_alpha != 255.0;
+
+	/* which band / rows / frame */
+	const int xa = blockIdx.x * P.TW;
+	const int xb = min(xa + P.TW, P.OW);
+	const int y_begin = blockIdx.y * P.RPC;
+	const int y_end = min(y_begin + P.RPC, P.OH);
+	const int frame = frame0 + blockIdx.z;
+	const uint8_t *fin = in + (size_t) frame * in_frame_stride;
+	uint8_t *fout = out + (size_t) frame * out_frame_stride;
+
+	/* embedded shrinkh columns of this band: [E0, E0 + NE), E0 even */
+	const int pair_h0 = __ldg(&P.hcol[xa]).x;
+	const int E0 = 2 * pair_h0;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh) - E0;
+
+	/* this thread's input pixel column (clamped: the two EXTEND_COPY embeds of
+	 * reduceh.cpp:515-521 and shrinkh.c:383)
+	 */
+	const bool col_active = t < NE * P.HS;
+	int in_col;
+	{
+		const int e = E0 + t / P.HS;
+		const int k = t - (t / P.HS) * P.HS;
+		const int sc = max(0, min(e - P.hembed, P.Ws - 1));
+		in_col = min(sc * P.HS + k, P.W - 1);
+	}
+	const unsigned *col_ptr = (const unsigned *) fin + in_col;
+
+	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
+
+	__syncthreads();
+
+	int pdone = INT_MIN; /* pairs < pdone are in the buffer */
+	int P0_prev = 0;
+
+	for (int ya = y_begin; ya < y_end; ya += kChunkRows) {
+		const int yb = min(ya + kChunkRows, y_end);
+		const int P0 = __ldg(&P.vrow[ya]).x;
+		const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+
+		if (col_active) {
+			/* -------- stage V.a: carry the window over from the last chunk */
+			int pfirst = P0;
+			if (pdone > P0) {
+				const int shift = P0 - P0_prev;
+				if (shift > 0)
+					for (int p = P0; p < pdone; p++)
+						pairbuf[(size_t) (p - P0) * NT + t] = pairbuf[(size_t) (p - P0 + shift) * NT + t];
+				pfirst = pdone;
+			}
+
+			/* -------- stage V.b: produce row pairs pfirst..P1 */
+			for (int p = pfirst; p <= P1; p++) {
+				unsigned rbA, gaA, rbB, gaB;
+				/* embedded reducev rows 2p, 2p+1 -> box-shrunk rows (EXTEND_COPY
+				 * embed of reducev.cpp:975-981) -> VS input rows each (the
+				 * round-up embed of shrinkv.c:501)
+				 */
+				const int sA = max(0, min(2 * p - P.vembed, P.Hs - 1));
+				const int sB = max(0, min(2 * p + 1 - P.vembed, P.Hs - 1));
+				if (VS > 0) {
+					unsigned pa[VS > 0 ? VS : 1], pb[VS > 0 ? VS : 1];
+#pragma unroll
+					for (int k = 0; k < VS; k++) {
+						const int ra = min(sA * VS + k, P.H - 1);
+						const int rb_ = min(sB * VS + k, P.H - 1);
+						pa[k] = ld_stream((const unsigned *) ((const char *) col_ptr + (size_t) ra * P.in_bpl));
+						pb[k] = ld_stream((const unsigned *) ((const char *) col_ptr + (size_t) rb_ * P.in_bpl));
+					}
+					box_rows<(VS > 0 ? VS : 1), PREMUL>(pa, vs, pscale, lut, amend2, rbA, gaA);
+					box_rows<(VS > 0 ? VS : 1), PREMUL>(pb, vs, pscale, lut, amend2, rbB, gaB);
+				}
+				else {
+					/* generic box height: one row at a time */
+					rbA = gaA = rbB = gaB = amend2;
+					for (int k = 0; k < vs; k++) {
+						unsigned one[1], rb1, ga1;
+						one[0] = ld_stream((const unsigned *) ((const char *) col_ptr + (size_t) min(sA * vs + k, P.H - 1) * P.in_bpl));
+						box_rows<1, PREMUL>(one, 1, pscale, lut, 0u, rb1, ga1);
+						rbA += rb1;
+						gaA += ga1;
+						one[0] = ld_stream((const unsigned *) ((const char *) col_ptr + (size_t) min(sB * vs + k, P.H - 1) * P.in_bpl));
+						box_rows<1, PREMUL>(one, 1, pscale, lut, 0u, rb1, ga1);
+						rbB += rb1;
+						gaB += ga1;
+					}
+				}
+				rbA = box_average(rbA, P.vmul8, P.vshift);
+				gaA = box_average(gaA, P.vmul8, P.vshift);
+				rbB = box_average(rbB, P.vmul8, P.vshift);
+				gaB = box_average(gaB, P.vmul8, P.vshift);
+				/* byte-transpose the pair: w.x = [rA rB bA bB], w.y = [gA gB aA aB] */
+				uint2 w;
+				w.x = __byte_perm(rbA, rbB, 0x6240);
+				w.y = __byte_perm(gaA, gaB, 0x6240);
+				pairbuf[(size_t) (p - P0) * NT + t] = w;
+			}
+
+			/* -------- stage V.c: reducev for the chunk's rows */
+			for (int y = ya; y < yb; y++) {
+				const int2 vr = __ldg(&P.vrow[y]);
+				const uint2 *win = pairbuf + (size_t) (vr.x - P0) * NT + t;
+				const int *cf = vcoef + vr.y * P.NPv;
+				int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+#pragma unroll 7
+				for (int k = 0; k < P.NPv; k++) {
+					const uint2 w = win[(size_t) k * NT];
+					const unsigned c = (unsigned) cf[k];
+					r = dp2a_lo(c, w.x, r);
+					b = dp2a_hi(c, w.x, b);
+					g = dp2a_lo(c, w.y, g);
+					a = dp2a_hi(c, w.y, a);
+				}
+				/* unsigned_fixed_round + VIPS_CLIP(0, v, 255), reducev.cpp:461-471 */
+				r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+				g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+				b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+				a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+				rv[(size_t) (y - ya) * NT + t] = (unsigned) r | ((unsigned) g << 8) | ((unsigned) b << 16) | ((unsigned) a << 24);
+			}
+		}
+		pdone = P1 + 1;
+		P0_prev = P0;
+
+		__syncthreads();
+
+		/* -------- stage H1: box-sum HS adjacent columns, emit column pairs
+		 * q = ((amend + sum) * multiplier) >> 24, shrinkh.c:78-93
+		 */
+		const int rows = yb - ya;
+		const int npairs = NE / 2;
+		const unsigned hamend2 = (unsigned) (P.HS / 2) * 0x00010001u;
+		for (int idx = t; idx < rows * npairs; idx += NT) {
+			const int k = idx / npairs;
+			const int j = idx - k * npairs;
+			const unsigned *src = rv + (size_t) k * NT + (size_t) (2 * j) * P.HS;
+			unsigned rbA = hamend2, gaA = hamend2, rbB = hamend2, gaB = hamend2;
+			for (int i = 0; i < P.HS; i++) {
+				const unsigned wA = src[i];
+				const unsigned wB = src[P.HS + i];
+				rbA += wA & 0x00ff00ffu;
+				gaA += (wA >> 8) & 0x00ff00ffu;
+				rbB += wB & 0x00ff00ffu;
+				gaB += (wB >> 8) & 0x00ff00ffu;
+			}
+			rbA = box_average(rbA, P.hmul8, P.hshift);
+			gaA = box_average(gaA, P.hmul8, P.hshift);
+			rbB = box_average(rbB, P.hmul8, P.hshift);
+			gaB = box_average(gaB, P.hmul8, P.hshift);
+			uint2 w;
+			w.x = __byte_perm(rbA, rbB, 0x6240);
+			w.y = __byte_perm(gaA, gaB, 0x6240);
+			sh[(size_t) k * (P.NEmax / 2) + j] = w;
+		}
+
+		__syncthreads();
+
+		/* -------- stage H2: reduceh + unpremultiply + store */
+		const int bw = xb - xa;
+		for (int idx = t; idx < rows * bw; idx += NT) {
+			const int k = idx / bw;
+			const int x = xa + (idx - k * bw);
+			const int2 hc = __ldg(&P.hcol[x]);
+			const uint2 *win = sh + (size_t) k * (P.NEmax / 2) + (hc.x - pair_h0);
+			const int *cf = hcoef + hc.y * P.NPh;
+			int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+#pragma unroll 7
+			for (int kk = 0; kk < P.NPh; kk++) {
+				const uint2 w = win[kk];
+				const unsigned c = (unsigned) cf[kk];
+				r = dp2a_lo(c, w.x, r);
+				b = dp2a_hi(c, w.x, b);
+				g = dp2a_lo(c, w.y, g);
+				a = dp2a_hi(c, w.y, a);
+			}
+			r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+			g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+			b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+			a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+			if (PREMUL) {
+				/* unpremultiply.c:209-222: byte store without clip */
+				const int s = uscale[a];
+				r = ((r * s + 128) >> 8) & 0xff;
+				g = ((g * s + 128) >> 8) & 0xff;
+				b = ((b * s + 128) >> 8) & 0xff;
+			}
+			*(unsigned *) (fout + (size_t) (ya + k) * P.out_bpl + (size_t) x * 4) =
+				(unsigned) r | ((unsigned) g << 8) | ((unsigned) b << 16) | ((unsigned) a << 24);
+		}
+		/* the next chunk's stage V writes pairbuf/rv (not read after H1) and its
+		 * H1 writes sh only after its own barrier: no third barrier needed.
+		 */
+	}
+}
+
+/* Pack a 65 x n table of short coefficients into parity-aligned s16x2 pairs:
+ * set (phase, parity) holds pairs k = 0..NP-1 = (c[2k - parity], c[2k + 1 - parity]).
+ */
+struct PairSets {
+	int NP = 0;
+	std::vector<int> coef;			   /* [nsets][NP] */
+	std::map<std::pair<int, int>, int> ids; /* (phase, parity) -> set */
+
+	int
+	get(const AxisTable &t, int phase, int parity)
+	{
+		auto key = std::make_pair(phase, parity);
+		auto it = ids.find(key);
+		if (it != ids.end())
+			return it->second;
+		const int id = (int) ids.size();
+		ids[key] = id;
+		const short *c = &t.ms[(size_t) phase * t.n_point];
+		for (int k = 0; k < NP; k++) {
+			const int i0 = 2 * k - parity, i1 = 2 * k + 1 - parity;
+			const int c0 = (i0 >= 0 && i0 < t.n_point) ? c[i0] : 0;
+			const int c1 = (i1 >= 0 && i1 < t.n_point) ? c[i1] : 0;
+			coef.push_back((int) (((unsigned) (c0 & 0xffff)) | ((unsigned) (c1 & 0xffff) << 16)));
+		}
+		return id;
+	}
+};
+
+} // namespace
+
+/* ------------------------------------------------------------------ plan */
+
+struct ThumbnailPlanImpl {
+	/* request */
+	int W = 0, H = 0, bands = 0, fmt = 0, has_alpha = 0;
+	int target_w = 0, target_h = 0, size = 0, linear = 0;
+	/* derived */
+	double hshrink = 1, vshrink = 1;
+	int OW = 0, OH = 0;
+	ReduceGeom gv{}, gh{};
+	bool premul = false;
+	bool fused = false;
+	int device = -1;
+	/* fused path */
+	FusedParams fp{};
+	void *tables = nullptr; /* one device block */
+	size_t smem = 0;
+	dim3 grid;
+	/* host pump */
+	static constexpr int kStreams = 3;
+	cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
+	void *stage_in[kStreams] = {nullptr, nullptr, nullptr};
+	void *stage_out[kStreams] = {nullptr, nullptr, nullptr};
+	int stage_frames = 0;
+};
+
+namespace {
+
+/* vips_thumbnail_calculate_shrink, thumbnail.c:413-466 (no crop, no rotate) */
+void
+thumbnail_shrink(int w, int h, int tw, int th, int size, double *hshrink, double *vshrink)
+{
+	double hs = (double) w / tw;
+	double vs = (double) h / th;
+	const bool horizontal = !(hs < vs);
+	if (size != VB200_SIZE_FORCE) {
+		if (horizontal)
+			vs = hs;
+		else
+			hs = vs;
+	}
+	if (size == VB200_SIZE_UP) {
+		hs = std::min(1.0, hs);
+		vs = std::min(1.0, vs);
+	}
+	else if (size == VB200_SIZE_DOWN) {
+		hs = std::max(1.0, hs);
+		vs = std::max(1.0, vs);
+	}
+	*hshrink = std::min(hs, (double) w);
+	*vshrink = std::min(vs, (double) h);
+}
+
+template <int VS, bool PREMUL>
+int
+launch_fused_t(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s)
+{
+	auto kern = thumbnail_fused_kernel<VS, PREMUL>;
+	static thread_local int configured_for = -1;
+	(void) configured_for;
+	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem));
+	for (int f0 = 0; f0 < n; f0 += 32768) {
+		dim3 grid = pl->grid;
+		grid.z = std::min(32768, n - f0);
+		kern<<<grid, pl->fp.NT, pl->smem, s>>>(pl->fp, (const uint8_t *) in, in_stride, (uint8_t *) out, out_stride, f0);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "thumbnail_fused_kernel launch");
+		count_launch();
+	}
+	return 0;
+}
+
+template <bool PREMUL>
+int
+launch_fused_vs(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
+	cudaStream_t s)
+{
+	switch (pl->fp.VS) {
+	case 1: return launch_fused_t<1, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 2: return launch_fused_t<2, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 3: return launch_fused_t<3, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 4: return launch_fused_t<4, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 5: return launch_fused_t<5, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 6: return launch_fused_t<6, PREMUL>(domain, pl, in, is, out, os, n, s);
+	case 8: return launch_fused_t<8, PREMUL>(domain, pl, in, is, out, os, n, s);
+	default: return launch_fused_t<0, PREMUL>(domain, pl, in, is, out, os, n, s);
+	}
+}
+
+int
+plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
+{
+	const TileGeometry tg = tile_geometry();
+	int tile_w, tile_h;
+	if (pl->gv.int_shrink > 1) {
+		tile_w = tg.tile_width;
+		tile_h = tg.tile_height;
+	}
+	else {
+		tile_w = pl->OW;
+		tile_h = tg.fatstrip_height;
+	}
+	int rect_h = tile_h;
+	if (pl->gh.int_shrink > 1)
+		rect_h = std::min(rect_h, tg.fatstrip_height);
+
+	AxisTable tv, th;
+	build_axis_table(tv, pl->OH, pl->gv.residual, pl->gv.offset, pl->gv.n_point, VB200_KERNEL_LANCZOS3, rect_h);
+	build_axis_table(th, pl->OW, pl->gh.residual, pl->gh.offset, pl->gh.n_point, VB200_KERNEL_LANCZOS3, tile_w);
+
+	PairSets sv, shh;
+	sv.NP = (pl->gv.n_point + 2) / 2;
+	shh.NP = (pl->gh.n_point + 2) / 2;
+	std::vector<int2> vrow(pl->OH), hcol(pl->OW);
+	for (int y = 0; y < pl->OH; y++) {
+		vrow[y].x = tv.first[y] >> 1;
+		vrow[y].y = sv.get(tv, tv.phase[y], tv.first[y] & 1);
+	}
+	for (int x = 0; x < pl->OW; x++) {
+		hcol[x].x = th.first[x] >> 1;
+		hcol[x].y = shh.get(th, th.phase[x], th.first[x] & 1);
+	}
+
+	FusedParams &fp = pl->fp;
+	fp.W = pl->W;
+	fp.H = pl->H;
+	fp.in_bpl = (size_t) pl->W * 4;
+	fp.VS = pl->gv.int_shrink;
+	fp.Hs = pl->gv.shrunk_size;
+	fp.vembed = tv.embed;
+	fp.NPv = sv.NP;
+	fp.vmul8 = (unsigned) (((1LL << 32) / (256LL * fp.VS)) << 8);
+	fp.vshift = -1;
+	for (int sft = 0; sft < 9; sft++)
+		if ((1 << sft) == fp.VS)
+			fp.vshift = sft;
+	fp.HS = pl->gh.int_shrink;
+	fp.Ws = pl->gh.shrunk_size;
+	fp.hembed = th.embed;
+	fp.NPh = shh.NP;
+	fp.hmul8 = (unsigned) (((1LL << 32) / (256LL * fp.HS)) << 8);
+	fp.hshift = -1;
+	for (int sft = 0; sft < 9; sft++)
+		if ((1 << sft) == fp.HS)
+			fp.hshift = sft;
+	fp.OW = pl->OW;
+	fp.OH = pl->OH;
+	fp.out_bpl = (size_t) pl->OW * 4;
+	fp.premul = pl->premul;
+	fp.max_alpha = 255.0;
+	fp.nvsets = (int) sv.ids.size();
+	fp.nhsets = (int) shh.ids.size();
+	if (fp.VS > 256 || fp.HS > 256)
+		return 1; /* 16-bit lanes would overflow: use the unfused path */
+
+	/* band width: as wide as the thread budget allows */
+	int TW = 64;
+	auto band_threads = [&](int tw, int *nemax) {
+		int worst = 0;
+		for (int xa = 0; xa < pl->OW; xa += tw) {
+			const int xb = std::min(xa + tw, pl->OW);
+			const int ne = 2 * (hcol[xb - 1].x + fp.NPh) - 2 * hcol[xa].x;
+			worst = std::max(worst, ne);
+		}
+		*nemax = worst;
+		return worst * fp.HS;
+	};
+	int nemax = 0;
+	while (TW > 4 && band_threads(TW, &nemax) > 640)
+		TW /= 2;
+	if (band_threads(TW, &nemax) > kMaxThreads)
+		return 1;
+	fp.TW = TW;
+	fp.NEmax = nemax;
+	fp.NT = std::min(kMaxThreads, ((nemax * fp.HS + 31) / 32) * 32);
+	fp.NT = std::max(fp.NT, 64);
+
+	/* rows per CTA: whole height when there are many frames; the batch entry
+	 * point overrides this per launch if it needs more CTAs
+	 */
+	fp.RPC = ((pl->OH + kChunkRows - 1) / kChunkRows) * kChunkRows;
+
+	/* pair slots: worst chunk */
+	int slots = 0;
+	for (int ya = 0; ya < pl->OH; ya += kChunkRows) {
+		const int yb = std::min(ya + kChunkRows, pl->OH);
+		slots = std::max(slots, vrow[yb - 1].x + fp.NPv - 1 - vrow[ya].x + 1);
+	}
+	fp.slots = slots;
+
+	pl->smem = (size_t) slots * fp.NT * 8 + (size_t) kChunkRows * fp.NT * 4 + (size_t) kChunkRows * (nemax / 2) * 8 +
+		(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 512) * 4;
+	if (pl->smem > 200 * 1024)
+		return 1;
+
+	/* upload tables as one block */
+	const size_t n_vrow = vrow.size() * sizeof(int2), n_hcol = hcol.size() * sizeof(int2);
+	const size_t n_vc = sv.coef.size() * 4, n_hc = shh.coef.size() * 4;
+	std::vector<char> host(n_vrow + n_hcol + n_vc + n_hc);
+	memcpy(&host[0], vrow.data(), n_vrow);
+	memcpy(&host[n_vrow], hcol.data(), n_hcol);
+	memcpy(&host[n_vrow + n_hcol], sv.coef.data(), n_vc);
+	memcpy(&host[n_vrow + n_hcol + n_vc], shh.coef.data(), n_hc);
+	VB200_CUDA(domain, cudaMalloc(&pl->tables, host.size()));
+	VB200_CUDA(domain, cudaMemcpy(pl->tables, host.data(), host.size(), cudaMemcpyHostToDevice));
+	char *b = (char *) pl->tables;
+	fp.vrow = (const int2 *) b;
+	fp.hcol = (const int2 *) (b + n_vrow);
+	fp.vcoef = (const int *) (b + n_vrow + n_hcol);
+	fp.hcoef = (const int *) (b + n_vrow + n_hcol + n_vc);
+
+	pl->grid = dim3((pl->OW + TW - 1) / TW, (pl->OH + fp.RPC - 1) / fp.RPC, 1);
+	return 0;
+}
+
+} // namespace
+
+int
+thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
+{
+	if (pl->fmt != VB200_FORMAT_UCHAR) {
+		error(domain, "only uchar frames are on the batched device path");
+		return -1;
+	}
+	if (pl->linear) {
+		error(domain, "linear thumbnails run through vb200_thumbnail_image()");
+		return -1;
+	}
+	thumbnail_shrink(pl->W, pl->H, pl->target_w, pl->target_h, pl->size, &pl->hshrink, &pl->vshrink);
+	if (pl->hshrink < 1.0 || pl->vshrink < 1.0) {
+		error(domain, "upsizing is not on the device path yet");
+		return -1;
+	}
+	/* vips_resize: scale = 1 / shrink, then reducev(1 / vscale) -- keep the double rounding */
+	double hscale = std::max(1.0 / pl->hshrink, 1.0 / pl->W);
+	double vscale = std::max(1.0 / pl->vshrink, 1.0 / pl->H);
+	const double vs = vscale < 1.0 ? 1.0 / vscale : 1.0;
+	const double hs = hscale < 1.0 ? 1.0 / hscale : 1.0;
+	pl->gv = ReduceGeom{pl->H, pl->H, 1, pl->H, 0, 1.0, 0.0};
+	pl->gh = ReduceGeom{pl->W, pl->W, 1, pl->W, 0, 1.0, 0.0};
+	if (vs > 1.0 && reduce_geometry(domain, pl->H, vs, VB200_KERNEL_LANCZOS3, 2.0, &pl->gv))
+		return -1;
+	if (hs > 1.0 && reduce_geometry(domain, pl->W, hs, VB200_KERNEL_LANCZOS3, 2.0, &pl->gh))
+		return -1;
+	pl->OW = pl->gh.out_size;
+	pl->OH = pl->gv.out_size;
+	/* thumbnail.c:848-861 */
+	pl->premul = pl->has_alpha && pl->hshrink != 1.0 && pl->vshrink != 1.0;
+
+	pl->fused = false;
+	if (pl->bands == 4 && pl->gv.n_point > 0 && pl->gh.n_point > 0) {
+		int r = plan_build_fused(domain, pl);
+		if (r < 0)
+			return -1;
+		pl->fused = r == 0;
+	}
+	return 0;
+}
+
+int
+thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s)
+{
+	if (n <= 0)
+		return 0;
+	if (pl->fused) {
+		/* enough CTAs to fill the machine: split rows when the batch is small */
+		FusedParams &fp = pl->fp;
+		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
+		int rpc = ((pl->OH + kChunkRows - 1) / kChunkRows) * kChunkRows;
+		while ((long long) bands_x * ((pl->OH + rpc - 1) / rpc) * n < 2 * 148 && rpc > 2 * kChunkRows)
+			rpc = ((rpc / 2 + kChunkRows - 1) / kChunkRows) * kChunkRows;
+		fp.RPC = rpc;
+		pl->grid = dim3(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+		return pl->premul ? launch_fused_vs<true>(domain, pl, in, in_stride, out, out_stride, n, s)
+						  : launch_fused_vs<false>(domain, pl, in, in_stride, out, out_stride, n, s);
+	}
+
+	/* unfused chain of leaf kernels, frame by frame */
+	for (int i = 0; i < n; i++) {
+		DevImage d, pre, res, fin;
+		d.w = pl->W;
+		d.h = pl->H;
+		d.bands = pl->bands;
+		d.fmt = pl->fmt;
+		d.type = pl->bands < 3 ? VB200_INTERPRETATION_B_W : VB200_INTERPRETATION_sRGB;
+		d.bpl = (size_t) pl->W * pl->bands;
+		d.data = (char *) in + (size_t) i * in_stride;
+		const DevImage *src = &d;
+		if (pl->premul) {
+			if (dev_premultiply(domain, d, &pre, 255.0, 1, s))
+				return -1;
+			src = &pre;
+		}
+		if (dev_resize(domain, *src, &res, 1.0 / pl->hshrink, 1.0 / pl->vshrink, VB200_KERNEL_LANCZOS3, 2.0, s))
+			return -1;
+		const DevImage *last = &res;
+		if (pl->premul) {
+			if (dev_unpremultiply(domain, res, &fin, 255.0, 1, s))
+				return -1;
+			last = &fin;
+		}
+		const size_t line = (size_t) last->w * last->bands;
+		VB200_CUDA(domain, cudaMemcpy2DAsync((char *) out + (size_t) i * out_stride, line, last->data, last->bpl, line,
+							   last->h, cudaMemcpyDeviceToDevice, s));
+		if (pl->premul) {
+			dev_image_release(&pre, s);
+			dev_image_release(&fin, s);
+		}
+		dev_image_release(&res, s);
+	}
+	return 0;
+}
+
+void
+thumbnail_plan_destroy(ThumbnailPlanImpl *pl)
+{
+	if (pl->tables)
+		cudaFree(pl->tables);
+	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
+		if (pl->stage_in[i])
+			cudaFree(pl->stage_in[i]);
+		if (pl->stage_out[i])
+			cudaFree(pl->stage_out[i]);
+		if (pl->streams[i])
+			cudaStreamDestroy(pl->streams[i]);
+	}
+}
+
+} // namespace vb200
+
+/* ------------------------------------------------------------------ C ABI */
+
+using namespace vb200;
+
+struct VB200ThumbnailPlan {
+	ThumbnailPlanImpl impl;
+};
+
+extern "C" VB200ThumbnailPlan *
+vb200_thumbnail_plan_new(int width, int height, int bands, int band_format, int has_alpha, int target_width,
+	int target_height, int size, int linear)
+{
+	const char *domain = "thumbnail_plan";
+	if (ensure_init(domain))
+		return nullptr;
+	if (width <= 0 || height <= 0 || bands <= 0 || target_width <= 0) {
+		error(domain, "bad frame geometry");
+		return nullptr;
+	}
+	auto *plan = new VB200ThumbnailPlan();
+	ThumbnailPlanImpl &pl = plan->impl;
+	pl.W = width;
+	pl.H = height;
+	pl.bands = bands;
+	pl.fmt = band_format;
+	pl.has_alpha = has_alpha;
+	pl.target_w = target_width;
+	pl.target_h = target_height > 0 ? target_height : target_width;
+	pl.size = size;
+	pl.linear = linear;
+	if (thumbnail_plan_init(domain, &pl)) {
+		thumbnail_plan_destroy(&pl);
+		delete plan;
+		return nullptr;
+	}
+	return plan;
+}
+
+extern "C" void
+vb200_thumbnail_plan_free(VB200ThumbnailPlan *plan)
+{
+	if (!plan)
+		return;
+	thumbnail_plan_destroy(&plan->impl);
+	delete plan;
+}
+
+extern "C" int
+vb200_thumbnail_plan_output(const VB200ThumbnailPlan *plan, int *out_width, int *out_height)
+{
+	if (!plan)
+		return -1;
+	if (out_width)
+		*out_width = plan->impl.OW;
+	if (out_height)
+		*out_height = plan->impl.OH;
+	return 0;
+}
+
+extern "C" size_t
+vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan)
+{
+	const ThumbnailPlanImpl &pl = plan->impl;
+	return (size_t) pl.W * pl.H * pl.bands + (size_t) pl.OW * pl.OH * pl.bands;
+}
+
+extern "C" int
+vb200_thumbnail_plan_is_fused(const VB200ThumbnailPlan *plan)
+{
+	return plan && plan->impl.fused;
+}
+
+extern "C" int
+vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
+	size_t out_frame_stride, int n_frames)
+{
+	const char *domain = "thumbnail_batch_device";
+	if (!plan || !in || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	return thumbnail_plan_run_device(domain, &plan->impl, in, in_frame_stride, out, out_frame_stride, n_frames,
+		current_stream());
+}
+
+/* The tile pump: a ring of kStreams device staging slots; for each slice of
+ * frames  H2D (pinned or pageable source) -> fused kernel -> D2H  on its own
+ * stream, so copy-in, compute and copy-out of consecutive slices overlap.
+ * Replaces vips_sink_memory + the threadpool on this path
+ * (reference: iofuncs/sinkmemory.c:171-274, threadpool.c:301-369).
+ */
+extern "C" int
+vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
+	size_t out_frame_stride, int n_frames)
+{
+	const char *domain = "thumbnail_batch_host";
+	if (!plan || !in || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	ThumbnailPlanImpl &pl = plan->impl;
+	const size_t in_frame = (size_t) pl.W * pl.H * pl.bands;
+	const size_t out_frame = (size_t) pl.OW * pl.OH * pl.bands;
+	/* slice size: ~64 MiB of input per slot */
+	const int per_slice = (int) std::max<size_t>(1, std::min<size_t>(n_frames, (64u << 20) / in_frame));
+	if (pl.stage_frames < per_slice) {
+		for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
+			if (pl.stage_in[i])
+				cudaFree(pl.stage_in[i]);
+			if (pl.stage_out[i])
+				cudaFree(pl.stage_out[i]);
+			pl.stage_in[i] = pl.stage_out[i] = nullptr;
+			VB200_CUDA(domain, cudaMalloc(&pl.stage_in[i], in_frame * per_slice));
+			VB200_CUDA(domain, cudaMalloc(&pl.stage_out[i], out_frame * per_slice));
+			if (!pl.streams[i])
+				VB200_CUDA(domain, cudaStreamCreateWithFlags(&pl.streams[i], cudaStreamNonBlocking));
+		}
+		pl.stage_frames = per_slice;
+	}
+
+	int slot = 0;
+	for (int f = 0; f < n_frames; f += per_slice, slot = (slot + 1) % ThumbnailPlanImpl::kStreams) {
+		const int n = std::min(per_slice, n_frames - f);
+		cudaStream_t s = pl.streams[slot];
+		/* the slot's previous slice must have drained before we overwrite it */
+		VB200_CUDA(domain, cudaStreamSynchronize(s));
+		VB200_CUDA(domain, cudaMemcpy2DAsync(pl.stage_in[slot], in_frame, (const char *) in + (size_t) f * in_frame_stride,
+							   in_frame_stride, in_frame, n, cudaMemcpyHostToDevice, s));
+		if (thumbnail_plan_run_device(domain, &pl, pl.stage_in[slot], in_frame, pl.stage_out[slot], out_frame, n, s))
+			return -1;
+		VB200_CUDA(domain, cudaMemcpy2DAsync((char *) out + (size_t) f * out_frame_stride, out_frame_stride,
+							   pl.stage_out[slot], out_frame, out_frame, n, cudaMemcpyDeviceToHost, s));
+	}
+	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++)
+		if (pl.streams[i])
+			VB200_CUDA(domain, cudaStreamSynchronize(pl.streams[i]));
+	return 0;
+}
+
+/* reference: vips_thumbnail_image(), resample/thumbnail.c:2000 */
+extern "C" int
+vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int height, int size, int linear)
+{
+	const char *domain = "thumbnail";
+	if (!in || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	if (linear) {
+		error(domain, "linear thumbnails are not on the device path yet");
+		return -1;
+	}
+	/* vips_image_hasalpha(): 2 or 4 bands (iofuncs/header.c) for 8-bit sRGB / B_W */
+	const int has_alpha = in->Bands == 2 || in->Bands == 4;
+	VB200ThumbnailPlan *plan = vb200_thumbnail_plan_new(in->Xsize, in->Ysize, in->Bands, in->BandFmt, has_alpha, width,
+		height, size, 0);
+	if (!plan)
+		return -1;
+	cudaStream_t s = current_stream();
+	DevImage din, dout;
+	int rc = to_device(domain, in, &din, s);
+	if (!rc && din.bpl != (size_t) din.w * din.bands) {
+		error(domain, "device frames must be packed");
+		rc = -1;
+	}
+	if (!rc)
+		rc = dev_image_new(domain, &dout, plan->impl.OW, plan->impl.OH, in->Bands, in->BandFmt, in->Type, s);
+	if (!rc)
+		rc = thumbnail_plan_run_device(domain, &plan->impl, din.data, 0, dout.data, 0, 1, s);
+	if (!rc)
+		rc = deliver(domain, &dout, in, out, s);
+	if (!rc && in->where == VB200_DEVICE)
+		cudaStreamSynchronize(s); /* the plan's tables die with it */
+	dev_image_release(&din, s);
+	vb200_thumbnail_plan_free(plan);
+	return rc;
+}

@@ -1,0 +1,122 @@
+/* vb200_internal.h -- shared declarations inside libvb200.so (not installed). */
+#ifndef VB200_INTERNAL_H
+#define VB200_INTERNAL_H
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "vb200.h"
+
+#define VB200_TRANSFORM_SHIFT 6 /* reference: include/vips/interpolate.h:109-118 */
+#define VB200_TRANSFORM_SCALE (1 << VB200_TRANSFORM_SHIFT)
+#define VB200_INTERPOLATE_SHIFT 12
+#define VB200_INTERPOLATE_SCALE (1 << VB200_INTERPOLATE_SHIFT)
+#define VB200_MAX_POINT 2000 /* reference: resample/presample.h:70 */
+#define VB200_ROUND_UINT(R) ((int) ((R) + 0.5))
+
+namespace vb200 {
+
+/* vips_error(domain, fmt, ...): append to the thread-local buffer. */
+void error(const char *domain, const char *fmt, ...);
+int cuda_fail(const char *domain, cudaError_t e, const char *what);
+
+#define VB200_CUDA(domain, call) \
+	do { \
+		cudaError_t e_ = (call); \
+		if (e_ != cudaSuccess) \
+			return vb200::cuda_fail(domain, e_, #call); \
+	} while (0)
+
+cudaStream_t current_stream();
+void count_launch(int n = 1);
+int ensure_init(const char *domain);
+
+struct TileGeometry {
+	int tile_width, tile_height, fatstrip_height, thinstrip_height;
+};
+TileGeometry tile_geometry();
+
+/* Device scratch, stream-ordered (cudaMallocAsync on the current stream). */
+int dev_alloc(const char *domain, void **p, size_t bytes, cudaStream_t s);
+void dev_free(void *p, cudaStream_t s);
+
+/* A device-resident image: the working type of every op. */
+struct DevImage {
+	int w = 0, h = 0, bands = 0, fmt = 0, type = 0;
+	void *data = nullptr;
+	size_t bpl = 0;
+	bool owned = false; /* free with dev_free on destruction of the holder */
+};
+
+size_t format_sizeof(int fmt);
+bool format_is_supported(int fmt); /* the 8 real formats minus double */
+
+/* Bring a VB200Image onto the device (no copy if it already is there). */
+int to_device(const char *domain, const VB200Image *in, DevImage *d, cudaStream_t s);
+/* Deliver a device image into *out following the allocate-or-fill contract. */
+int deliver(const char *domain, DevImage *d, const VB200Image *like, VB200Image *out, cudaStream_t s);
+/* Allocate an owned packed device image. */
+int dev_image_new(const char *domain, DevImage *d, int w, int h, int bands, int fmt, int type, cudaStream_t s);
+void dev_image_release(DevImage *d, cudaStream_t s);
+
+/* ------------------------------------------------------------ resample host */
+
+struct ReduceGeom {
+	int in_size, out_size, int_shrink, shrunk_size, n_point;
+	double residual, offset;
+};
+int reduce_get_points(int kernel, double shrink);
+void reduce_make_mask(double *c, int kernel, int n_points, double shrink, double x);
+int reduce_geometry(const char *domain, int in_size, double shrink, int kernel, double gap, ReduceGeom *g);
+int shrink_size(int in_size, int shrink, int ceil_mode);
+
+/* Per-output-row (or column) sampling table, built by the same sequential
+ * double additions vips_reducev_gen / vips_reduceh_gen perform per rect.
+ */
+struct AxisTable {
+	std::vector<int> first; /* (int) Y: first tap, in embedded coordinates */
+	std::vector<int> phase; /* ty / tx, 0..64 */
+	int n_point = 0;
+	int embed = 0; /* ceil(n_point / 2) - 1 */
+	std::vector<short> ms;	/* 65 x n_point, truncated x4096 */
+	std::vector<double> mf; /* 65 x n_point */
+};
+void build_axis_table(AxisTable &t, int out_size, double residual, double offset, int n_point, int kernel,
+	int rect_size, int rect_origin = 0, int count = -1);
+
+/* ------------------------------------------------------- resample device ops */
+
+int dev_shrinkv(const char *domain, const DevImage &in, DevImage *out, int vshrink, int ceil_mode, cudaStream_t s);
+int dev_shrinkh(const char *domain, const DevImage &in, DevImage *out, int hshrink, int ceil_mode, cudaStream_t s);
+int dev_reducev_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel,
+	int rect_h, cudaStream_t s);
+int dev_reduceh_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel,
+	int rect_w, cudaStream_t s);
+int dev_reducev(const char *domain, const DevImage &in, DevImage *out, double vshrink, int kernel, double gap,
+	int rect_h, cudaStream_t s);
+int dev_reduceh(const char *domain, const DevImage &in, DevImage *out, double hshrink, int kernel, double gap,
+	int rect_w, cudaStream_t s);
+int dev_premultiply(const char *domain, const DevImage &in, DevImage *out, double max_alpha, int uchar_mode,
+	cudaStream_t s);
+int dev_unpremultiply(const char *domain, const DevImage &in, DevImage *out, double max_alpha, int uchar_mode,
+	cudaStream_t s);
+int dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,
+	double gap, cudaStream_t s);
+
+double interpretation_max_alpha(int type);
+
+/* Launchers of the row/column-table kernels on raw device pointers (used by
+ * the generate()-shaped and scanline seams too).
+ */
+int launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne,
+	int out_rows, int fmt, const AxisTable &t, cudaStream_t s);
+int launch_reduceh(const char *domain, const void *in, size_t in_bpl, int in_w, void *out, size_t out_bpl, int bands,
+	int out_cols, int rows, int fmt, const AxisTable &t, cudaStream_t s);
+
+} // namespace vb200
+
+#endif

@@ -112,6 +112,8 @@ int orc_thumbnail_size(int w, int h, int target_w, int target_h, int size_mode, 
 	double *vshrink, int *ow, int *oh);
 int orc_thumbnail_image(const void *in, int w, int h, int bands, int target_w, int target_h, int size_mode,
 	int has_alpha, int tile_w, int tile_h, void *out);
+int orc_thumbnail_image_batch(const void *in, int n_frames, int w, int h, int bands, int target_w, int target_h,
+	int size_mode, int has_alpha, void *out, int ow, int oh, int n_threads);
 /* linear=TRUE variant (thumbnail.c:766-806, 971-987): sRGB->scRGB float, float
  * premultiply, float resize, float unpremultiply, scRGB->sRGB.
  */

@@ -1003,3 +1003,37 @@ orc_thumbnail_image(const void *in, int w, int h, int bands, int target_w, int t
 		return -1;
 	return orc_unpremultiply(res.data(), ow, oh, bands, ORC_FORMAT_UCHAR, 255.0, 1, out);
 }
+
+/* A batch of same-shaped frames, one frame per worker thread (the reference's
+ * inter-image parallelism: many caller threads each running a pipeline,
+ * doc/using-threads.md:61-95).  Used by bench.py's CPU baseline only.
+ */
+#include <atomic>
+#include <thread>
+
+extern "C" int
+orc_thumbnail_image_batch(const void *in, int n_frames, int w, int h, int bands, int target_w, int target_h,
+	int size_mode, int has_alpha, void *out, int ow, int oh, int n_threads)
+{
+	std::atomic<int> next{0}, rc{0};
+	auto work = [&]() {
+		for (;;) {
+			const int i = next.fetch_add(1);
+			if (i >= n_frames)
+				break;
+			const uint8_t *fi = (const uint8_t *) in + (size_t) i * w * h * bands;
+			uint8_t *fo = (uint8_t *) out + (size_t) i * ow * oh * bands;
+			if (orc_thumbnail_image(fi, w, h, bands, target_w, target_h, size_mode, has_alpha, 0, 0, fo))
+				rc = -1;
+		}
+	};
+	if (n_threads < 1)
+		n_threads = 1;
+	std::vector<std::thread> pool;
+	for (int t = 1; t < n_threads; t++)
+		pool.emplace_back(work);
+	work();
+	for (auto &t : pool)
+		t.join();
+	return rc;
+}

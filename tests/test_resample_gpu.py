@@ -1,0 +1,249 @@
+"""GPU parity: the CUDA resample path (through the C ABI) against the CPU oracle.
+
+Bit-exact for every integer format; float paths must be bit-identical too
+(double accumulation in the same order, no FMA contraction) -- asserted as
+max |diff| == 0, which is stricter than the 1 ULP the spec allows.
+
+Structure follows the reference's test/test-suite/test_resample.py: every
+format x kernel x factor, constant images, geometry/rounding, thumbnails.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALL_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32]
+KERNELS = ["nearest", "linear", "cubic", "mitchell", "lanczos2", "lanczos3", "mks2013", "mks2021"]
+
+
+def rand_image(rng, h, w, b, dt):
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        return (rng.random((h, w, b), dtype=np.float32) * 255).astype(dt)
+    info = np.iinfo(dt)
+    return rng.integers(info.min, int(info.max) + 1, (h, w, b), dtype=np.int64).astype(dt)
+
+
+def same(a, b):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    if not np.array_equal(a, b):
+        d = np.abs(a.astype(np.float64) - b.astype(np.float64))
+        idx = np.unravel_index(np.argmax(d), d.shape)
+        raise AssertionError("max diff %g at %s (%s vs %s), %d differing" % (d.max(), idx, a[idx], b[idx], (d > 0).sum()))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+@pytest.mark.parametrize("bands", [1, 3, 4])
+def test_shrink(vb, oracle, dt, bands):
+    rng = np.random.default_rng(11)
+    a = rand_image(rng, 67, 93, bands, dt)
+    for f in (2, 3, 4, 7):
+        for ceil in (False, True):
+            same(vb.Image(a).shrinkv(f, ceil=ceil).numpy(), oracle.shrinkv(a, f, ceil))
+            same(vb.Image(a).shrinkh(f, ceil=ceil).numpy(), oracle.shrinkh(a, f, ceil))
+
+
+@pytest.mark.parametrize("dt", ALL_DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_reduce_all_formats_kernels(vb, oracle, dt, kernel):
+    """test_resample.py:77-92 shape: formats x kernels x factors."""
+    rng = np.random.default_rng(5)
+    a = rand_image(rng, 61, 83, 3, dt)
+    for fac in (1.0, 1.1, 1.5, 1.999, 2.0, 3.3):
+        v = vb.Image(a).reducev(fac, kernel=kernel).numpy()
+        same(v, oracle.reducev(a, fac, kernel, 0.0, rect_h=16))
+        h = vb.Image(a).reduceh(fac, kernel=kernel).numpy()
+        same(h, oracle.reduceh(a, fac, kernel, 0.0, rect_w=0))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_constant_images_survive(vb, kernel):
+    """test_resample.py:94-103: a constant uchar image reduced x2 stays constant."""
+    for const in (0, 1, 2, 254, 255):
+        a = np.full((10, 10, 1), const, np.uint8)
+        r = vb.Image(a).reduce(2, 2, kernel=kernel).numpy()
+        assert r.shape == (5, 5, 1)
+        assert (r == const).all(), (kernel, const, r.ravel())
+
+
+def test_reduce_gap(vb, oracle):
+    rng = np.random.default_rng(7)
+    a = rand_image(rng, 301, 257, 4, np.uint8)
+    for fac in (4.0, 5.5, 8.0, 9.4):
+        same(vb.Image(a).reducev(fac, gap=2.0).numpy(), oracle.reducev(a, fac, "lanczos3", 2.0, rect_h=128))
+        same(vb.Image(a).reduceh(fac, gap=2.0).numpy(), oracle.reduceh(a, fac, "lanczos3", 2.0, rect_w=0))
+
+
+def test_reduce_49_tap(vb, oracle):
+    """BASELINE config 1 arithmetic (gap 0, shrink 8 => 49 taps) at a small size."""
+    rng = np.random.default_rng(8)
+    a = rand_image(rng, 512, 384, 4, np.uint8)
+    v = vb.Image(a).reducev(8.0).numpy()
+    same(v, oracle.reducev(a, 8.0, "lanczos3", 0.0, rect_h=16))
+    same(vb.Image(v).reduceh(8.0).numpy(), oracle.reduceh(v, 8.0, "lanczos3", 0.0, rect_w=0))
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.int16, np.float32])
+def test_premultiply_roundtrip_ops(vb, oracle, dt):
+    rng = np.random.default_rng(3)
+    for bands in (2, 4, 5):
+        a = rand_image(rng, 33, 47, bands, dt)
+        if np.dtype(dt).kind == "f":
+            a[..., -1] = rng.random((33, 47), dtype=np.float32) * 300 - 20  # incl. out-of-range alpha
+        ma = 255.0
+        same(vb.Image(a).premultiply(max_alpha=ma).numpy(), oracle.premultiply(a, ma, False))
+        same(vb.Image(a).unpremultiply(max_alpha=ma).numpy(), oracle.unpremultiply(a, ma, False))
+        if dt == np.uint8:
+            same(vb.Image(a).premultiply(uchar=True).numpy(), oracle.premultiply(a, 255.0, True))
+            same(vb.Image(a).unpremultiply(uchar=True).numpy(), oracle.unpremultiply(a, 255.0, True))
+
+
+def test_premultiply_all_alpha_values(vb, oracle):
+    """every (value, alpha) pair through both uchar LUT paths"""
+    v, al = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    a = np.stack([v, v[::-1], v.T, al], axis=-1)
+    same(vb.Image(a).premultiply(uchar=True).numpy(), oracle.premultiply(a, 255.0, True))
+    same(vb.Image(a).unpremultiply(uchar=True).numpy(), oracle.unpremultiply(a, 255.0, True))
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.float32])
+def test_resize(vb, oracle, dt):
+    """test_resample.py:113-146 geometry + parity"""
+    rng = np.random.default_rng(21)
+    a = rand_image(rng, 300, 401, 3, dt)
+    for scale in (0.25, 0.5, 0.37, 0.11, 0.9):
+        r = vb.Image(a).resize(scale).numpy()
+        same(r, oracle.resize(a, scale))
+    r = vb.Image(a).resize(0.3, vscale=0.7, kernel="cubic").numpy()
+    same(r, oracle.resize(a, 0.3, 0.7, kernel="cubic"))
+    # round-to-nearest sizing: 100x1 -> 50x1; 1600x1000 -> 10x6
+    assert vb.Image(np.zeros((1, 100, 1), np.uint8)).resize(0.5).numpy().shape == (1, 50, 1)
+    r = vb.Image(np.zeros((1000, 1600, 1), np.uint8)).resize(10.0 / 1600).numpy()
+    assert r.shape[:2] == (6, 10)
+
+
+def test_resize_edges_not_black(vb):
+    """test_resample.py:131-146: no black edge pixels at /8, /9.4, /16"""
+    a = np.full((600, 800, 3), 200, np.uint8)
+    for scale in (1 / 8.0, 1 / 9.4, 1 / 16.0):
+        r = vb.Image(a).resize(scale).numpy()
+        assert r[0].min() > 190 and r[-1].min() > 190 and r[:, 0].min() > 190 and r[:, -1].min() > 190
+
+
+def structured_rgba(h, w, kind, rng):
+    a = np.zeros((h, w, 4), np.uint8)
+    if kind == "random":
+        a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    elif kind.startswith("const"):
+        a[...] = int(kind[5:])
+    elif kind == "impulse":
+        a[..., 3] = 255
+        a[h // 2, w // 2] = 255
+    elif kind == "hramp":
+        a[...] = (np.arange(w) % 256).astype(np.uint8)[None, :, None]
+    elif kind == "vramp":
+        a[...] = (np.arange(h) % 256).astype(np.uint8)[:, None, None]
+    elif kind.startswith("alpha"):
+        a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        a[..., 3] = int(kind[5:])
+    return a
+
+
+@pytest.mark.parametrize("kind", ["random", "const0", "const1", "const254", "const255", "impulse", "hramp", "vramp",
+                                  "alpha0", "alpha1", "alpha128", "alpha255"])
+def test_thumbnail_rgba_fused_structured(vb, oracle, kind):
+    """SURVEY 8(d) structured cases through the fused kernel, 1024 -> 128 (shrink 8: the
+    BASELINE chain premultiply/shrinkv4/reducev13/shrinkh4/reduceh13/unpremultiply)."""
+    rng = np.random.default_rng(1234)
+    a = structured_rgba(1024, 1024, kind, rng)
+    plan = vb.ThumbnailPlan(1024, 1024, 4, 128)
+    assert plan.fused
+    same(plan.run_host(a[None])[0], oracle.thumbnail_image(a, 128))
+    same(vb.Image(a).thumbnail_image(128).numpy(), oracle.thumbnail_image(a, 128))
+
+
+@pytest.mark.parametrize("shape,target", [((997, 761), 100), ((761, 997), 100), ((640, 480), 64), ((300, 300), 150),
+                                           ((1000, 1000), 143), ((2048, 1024), 300), ((333, 1999), 77)])
+def test_thumbnail_rgba_odd_geometry(vb, oracle, shape, target):
+    """fractional residual shrinks, non-multiple sizes, edges: fused vs oracle"""
+    rng = np.random.default_rng(99)
+    a = rng.integers(0, 256, shape + (4,), dtype=np.uint8)
+    got = vb.Image(a).thumbnail_image(target).numpy()
+    same(got, oracle.thumbnail_image(a, target))
+
+
+@pytest.mark.parametrize("bands", [1, 2, 3])
+def test_thumbnail_other_bands(vb, oracle, bands):
+    rng = np.random.default_rng(17)
+    a = rng.integers(0, 256, (700, 900, bands), dtype=np.uint8)
+    same(vb.Image(a).thumbnail_image(120).numpy(), oracle.thumbnail_image(a, 120))
+
+
+def test_thumbnail_force_and_down(vb, oracle):
+    rng = np.random.default_rng(18)
+    a = rng.integers(0, 256, (800, 1200, 4), dtype=np.uint8)
+    same(vb.Image(a).thumbnail_image(100, 300, size="force").numpy(), oracle.thumbnail_image(a, 100, 300, "force"))
+    same(vb.Image(a).thumbnail_image(200, size="down").numpy(), oracle.thumbnail_image(a, 200, size="down"))
+
+
+def test_thumbnail_4k_full_size(vb, oracle):
+    """BASELINE config 2 frame: 4096x4096 RGBA -> 512x512, bit-exact."""
+    rng = np.random.default_rng(1234)
+    a = rng.integers(0, 256, (4096, 4096, 4), dtype=np.uint8)
+    same(vb.Image(a).thumbnail_image(512).numpy(), oracle.thumbnail_image(a, 512))
+
+
+def test_thumbnail_avg_preserved(vb):
+    """test_resample.py:171-205: thumbnail average within 1 of the source"""
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 256, (1000, 1500, 3), dtype=np.uint8)
+    t = vb.Image(a).thumbnail_image(100)
+    assert t.width == 100 and t.height == 67
+    assert abs(t.avg() - a.mean()) < 1
+
+
+def test_batch_device_and_pump(vb, oracle):
+    """device-resident batch API (torch only holds the memory) and the host pump"""
+    import torch
+    rng = np.random.default_rng(1234)
+    frames = rng.integers(0, 256, (5, 512, 768, 4), dtype=np.uint8)
+    plan = vb.ThumbnailPlan(768, 512, 4, 96)
+    want = np.stack([oracle.thumbnail_image(f, 96) for f in frames])
+    din = torch.from_numpy(frames).cuda()
+    dout = torch.zeros((5, plan.out_height, plan.out_width, 4), dtype=torch.uint8, device="cuda")
+    vb.set_stream(torch.cuda.current_stream().cuda_stream)
+    before = vb.launch_count()
+    plan.run_device(din.data_ptr(), dout.data_ptr(), 5)
+    torch.cuda.synchronize()
+    vb.set_stream(0)
+    assert vb.launch_count() > before
+    same(dout.cpu().numpy(), want)
+    same(plan.run_host(frames), want)
+
+
+def test_tile_invariance_exact_shrinks(vb):
+    """test/test_threading.sh invariant: output independent of tile geometry when
+    the shrink is exactly representable (shrink 8 here)."""
+    rng = np.random.default_rng(6)
+    a = rng.integers(0, 256, (1024, 1024, 4), dtype=np.uint8)
+    base = vb.Image(a).thumbnail_image(128).numpy()
+    try:
+        for tw, th in ((10, 10), (64, 64), (512, 512)):
+            vb.set_tile_geometry(tw, th)
+            same(vb.Image(a).thumbnail_image(128).numpy(), base)
+    finally:
+        vb.set_tile_geometry(128, 128, 16, 1)
+
+
+def test_tile_geometry_changes_phase_tables(vb, oracle):
+    """a non-representable shrink: results must follow the tile geometry the
+    reference would have used (sequential X += shrink per rect)"""
+    rng = np.random.default_rng(61)
+    a = rng.integers(0, 256, (999, 1001, 4), dtype=np.uint8)
+    try:
+        for tw, th in ((64, 64), (128, 128)):
+            vb.set_tile_geometry(tw, th)
+            same(vb.Image(a).thumbnail_image(123).numpy(), oracle.thumbnail_image(a, 123, tile=(tw, th)))
+    finally:
+        vb.set_tile_geometry(128, 128, 16, 1)
