@@ -12,6 +12,7 @@
 #define SHIM_VIPS_H
 
 #include <limits.h>
+#include <stdarg.h>
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -337,6 +338,7 @@ int vips_linecache(VipsImage *in, VipsImage **out, ...);
 int vips_tilecache(VipsImage *in, VipsImage **out, ...);
 int vips_cast(VipsImage *in, VipsImage **out, VipsBandFormat format, ...);
 int vips_copy(VipsImage *in, VipsImage **out, ...);
+int vips_call_split(const char *operation_name, va_list optional, ...);
 double vips_image_get_offset(const VipsImage *image);
 double vips_image_get_scale(const VipsImage *image);
 #define VIPS_MATRIX(I, X, Y) ((double *) VIPS_IMAGE_ADDR(I, X, Y))

@@ -1,0 +1,67 @@
+/* ref_api.c -- flat C entry points (for ctypes) over the reference's lazily
+ * evaluated pipeline objects.  TEST INFRASTRUCTURE ONLY.
+ */
+#include <vips/vips.h>
+
+int vips_shrinkv(VipsImage *in, VipsImage **out, int vshrink, ...);
+int vips_shrinkh(VipsImage *in, VipsImage **out, int hshrink, ...);
+int vips_reducev(VipsImage *in, VipsImage **out, double vshrink, ...);
+int vips_reduceh(VipsImage *in, VipsImage **out, double hshrink, ...);
+int vips_resize(VipsImage *in, VipsImage **out, double scale, ...);
+int vips_premultiply(VipsImage *in, VipsImage **out, ...);
+int vips_unpremultiply(VipsImage *in, VipsImage **out, ...);
+
+void *ref_image_new_from_memory(const void *data, int w, int h, int bands, int fmt, int type)
+{
+	return vips__shim_image_from_memory(data, w, h, bands, (VipsBandFormat) fmt, (VipsInterpretation) type);
+}
+int ref_image_width(void *im) { return ((VipsImage *) im)->Xsize; }
+int ref_image_height(void *im) { return ((VipsImage *) im)->Ysize; }
+int ref_image_bands(void *im) { return ((VipsImage *) im)->Bands; }
+int ref_image_format(void *im) { return ((VipsImage *) im)->BandFmt; }
+int ref_image_dhint(void *im) { return ((VipsImage *) im)->dhint; }
+int ref_image_write_to_memory(void *im, void *out, int tile_w, int tile_h)
+{
+	return vips__shim_write_to_memory((VipsImage *) im, out, tile_w, tile_h);
+}
+const char *ref_error(void) { return vips__shim_error(); }
+
+void *ref_shrinkv(void *in, int vshrink, int ceil_mode)
+{
+	VipsImage *out = NULL;
+	return vips_shrinkv((VipsImage *) in, &out, vshrink, "ceil", ceil_mode, NULL) ? NULL : out;
+}
+void *ref_shrinkh(void *in, int hshrink, int ceil_mode)
+{
+	VipsImage *out = NULL;
+	return vips_shrinkh((VipsImage *) in, &out, hshrink, "ceil", ceil_mode, NULL) ? NULL : out;
+}
+void *ref_reducev(void *in, double vshrink, int kernel, double gap)
+{
+	VipsImage *out = NULL;
+	return vips_reducev((VipsImage *) in, &out, vshrink, "kernel", kernel, "gap", gap, NULL) ? NULL : out;
+}
+void *ref_reduceh(void *in, double hshrink, int kernel, double gap)
+{
+	VipsImage *out = NULL;
+	return vips_reduceh((VipsImage *) in, &out, hshrink, "kernel", kernel, "gap", gap, NULL) ? NULL : out;
+}
+void *ref_resize(void *in, double scale, double vscale, int kernel, double gap)
+{
+	VipsImage *out = NULL;
+	return vips_resize((VipsImage *) in, &out, scale, "vscale", vscale, "kernel", kernel, "gap", gap, NULL) ? NULL : out;
+}
+void *ref_premultiply(void *in, double max_alpha, int uchar_mode)
+{
+	VipsImage *out = NULL;
+	int rc = max_alpha > 0 ? vips_premultiply((VipsImage *) in, &out, "max_alpha", max_alpha, "uchar", uchar_mode, NULL)
+						   : vips_premultiply((VipsImage *) in, &out, "uchar", uchar_mode, NULL);
+	return rc ? NULL : out;
+}
+void *ref_unpremultiply(void *in, double max_alpha, int uchar_mode)
+{
+	VipsImage *out = NULL;
+	int rc = max_alpha > 0 ? vips_unpremultiply((VipsImage *) in, &out, "max_alpha", max_alpha, "uchar", uchar_mode, NULL)
+						   : vips_unpremultiply((VipsImage *) in, &out, "uchar", uchar_mode, NULL);
+	return rc ? NULL : out;
+}
