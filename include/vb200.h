@@ -175,6 +175,17 @@ int vb200_unpremultiply(const VB200Image *in, VB200Image *out, double max_alpha,
  */
 int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int height, int size, int linear);
 
+/* ------------------------------------------------------------------ colour
+ *
+ * reference: vips_colourspace(), colour/colourspace.c:551-617.  The source
+ * space is in->Type.  Routes among sRGB (uchar), RGB16 (ushort), scRGB, XYZ,
+ * LAB (float) and LABS (short) run as ONE fused kernel; every reference step
+ * (sRGB2scRGB, scRGB2XYZ, XYZ2Lab, Lab2LabS, LabS2Lab, Lab2XYZ, XYZ2scRGB,
+ * scRGB2sRGB) keeps its own arithmetic.  Bands beyond the third are carried
+ * as vips_colour_build does (colour.c:196-291).
+ */
+int vb200_colourspace(const VB200Image *in, VB200Image *out, int space);
+
 /* ------------------------------------------- resample: generate()-shaped ops
  *
  * reference: VipsGenerateFn, include/vips/image.h:151-154.  Fill out->valid

@@ -81,6 +81,7 @@ def lib():
         L.vb200_premultiply.argtypes = [IP, IP, C.c_double, C.c_int]
         L.vb200_unpremultiply.argtypes = [IP, IP, C.c_double, C.c_int]
         L.vb200_thumbnail_image.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.vb200_colourspace.argtypes = [IP, IP, C.c_int]
         L.vb200_image_free.argtypes = [IP]
         L.vb200_thumbnail_plan_new.restype = C.c_void_p
         L.vb200_thumbnail_plan_new.argtypes = [C.c_int] * 9
@@ -222,6 +223,11 @@ class Image:
 
     def thumbnail_image(self, width, height=None, size="both", linear=False):
         return self._call(lib().vb200_thumbnail_image, int(width), int(height or 0), SIZES[size], int(linear))
+
+    # ---- colour
+    def colourspace(self, space, source_space=None):
+        src = self if source_space is None else Image(self.array, source_space)
+        return src._call(lib().vb200_colourspace, _interp(space))
 
 
 class ThumbnailPlan:

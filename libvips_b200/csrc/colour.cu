@@ -1,0 +1,600 @@
+/* colour.cu -- vips_colourspace() for sRGB / RGB16 / scRGB / XYZ / LAB / LABS as ONE
+ * fused kernel per route: each pixel is carried in registers through every
+ * step the reference would run as a separate operation with a float image in
+ * between (colourspace.c:223-497 route table; vips_colour_gen colour.c:119-156).
+ *
+ * Step arithmetic restates the reference's process_line functions exactly --
+ * same float/double mix, same evaluation order, explicit round-to-nearest
+ * intrinsics so nothing is contracted into an FMA:
+ *   sRGB2scRGB.c:71-107, scRGB2XYZ.c:58-79, XYZ2Lab.c:108-171, Lab2LabS.c:58-74,
+ *   LabS2Lab.c:54-69, Lab2XYZ.c:83-143, XYZ2scRGB.c:72-97 (LabQ2sRGB.c:263-284),
+ *   scRGB2sRGB.c:83-131 (LabQ2sRGB.c:290-361).
+ * LUTs (powf / cbrtf) are built on the HOST with the host libm, like the
+ * reference does (LabQ2sRGB.c:130-159, XYZ2Lab.c:91-106), and uploaded once.
+ * Bands beyond the third ride along exactly as vips_colour_build re-attaches
+ * them: rescale by max_alpha_after / max_alpha_before in float, then
+ * vips_cast to the step's output format (colour.c:252-291).
+ */
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "vb200_internal.h"
+
+namespace vb200 {
+
+namespace {
+
+constexpr int kQuant = 100000; /* QUANT_ELEMENTS, XYZ2Lab.c:66 */
+
+enum Step {
+	S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
+	S_scRGB2RGB16, S_RGB162scRGB
+};
+
+struct ColourTables {
+	const float *v2Y_8;	 /* [256] */
+	const int *Y2v_8;	 /* [257] */
+	const float *v2Y_16; /* [65536] */
+	const int *Y2v_16;	 /* [65537] */
+	const float *cbrt;	 /* [100000] */
+};
+
+struct StepInfo {
+	int step;
+	int out_fmt;   /* format of the step's output image */
+	float alpha_a; /* max_alpha_after / max_alpha_before, as float (vips_linear1 a1) */
+	int rescale;   /* alpha scale changes on this step */
+};
+
+struct RouteParams {
+	int n_steps;
+	StepInfo steps[6];
+	ColourTables t;
+	int w, bands;
+	size_t in_bpl, out_bpl;
+	int in_fmt, out_fmt;
+};
+
+std::mutex g_tables_lock;
+ColourTables g_tables[16];
+bool g_tables_ready[16];
+
+/* calcul_tables, LabQ2sRGB.c:130-159 */
+void
+host_rgb_tables(int range, std::vector<int> &Y2v, std::vector<float> &v2Y)
+{
+	Y2v.resize(range + 1);
+	v2Y.resize(range);
+	for (int i = 0; i < range; i++) {
+		float f = (float) i / (range - 1);
+		float v;
+		if (f <= 0.0031308)
+			v = 12.92F * f;
+		else
+			v = (1.0F + 0.055F) * powf(f, 1.0F / 2.4F) - 0.055F;
+		Y2v[i] = rintf((range - 1) * v);
+	}
+	Y2v[range] = Y2v[range - 1];
+	for (int i = 0; i < range; i++) {
+		float f = (float) i / (range - 1);
+		if (f <= 0.04045)
+			v2Y[i] = f / 12.92F;
+		else
+			v2Y[i] = powf((f + 0.055F) / (1 + 0.055F), 2.4F);
+	}
+}
+
+int
+get_tables(const char *domain, ColourTables *out)
+{
+	int dev = 0;
+	VB200_CUDA(domain, cudaGetDevice(&dev));
+	std::lock_guard<std::mutex> lock(g_tables_lock);
+	if (dev < 16 && g_tables_ready[dev]) {
+		*out = g_tables[dev];
+		return 0;
+	}
+	std::vector<int> y8, y16;
+	std::vector<float> v8, v16, cb(kQuant);
+	host_rgb_tables(256, y8, v8);
+	host_rgb_tables(65536, y16, v16);
+	/* table_init, XYZ2Lab.c:91-106 */
+	for (int i = 0; i < kQuant; i++) {
+		float Y = (double) i / kQuant;
+		if (Y < 0.008856)
+			cb[i] = 7.787F * Y + (16.0F / 116.0F);
+		else
+			cb[i] = cbrtf(Y);
+	}
+	const size_t bytes = (y8.size() + v8.size() + y16.size() + v16.size() + cb.size()) * 4;
+	char *block = nullptr;
+	VB200_CUDA(domain, cudaMalloc(&block, bytes));
+	char *p = block;
+	auto put = [&](const void *src, size_t n) {
+		cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+		char *at = p;
+		p += n;
+		return at;
+	};
+	ColourTables t;
+	t.v2Y_8 = (const float *) put(v8.data(), v8.size() * 4);
+	t.Y2v_8 = (const int *) put(y8.data(), y8.size() * 4);
+	t.v2Y_16 = (const float *) put(v16.data(), v16.size() * 4);
+	t.Y2v_16 = (const int *) put(y16.data(), y16.size() * 4);
+	t.cbrt = (const float *) put(cb.data(), cb.size() * 4);
+	VB200_CUDA(domain, cudaDeviceSynchronize());
+	if (dev < 16) {
+		g_tables[dev] = t;
+		g_tables_ready[dev] = true;
+	}
+	*out = t;
+	return 0;
+}
+
+/* ------------------------------------------------------------ device steps */
+
+/* x86 cvttss2si: out-of-range and NaN give INT_MIN (what "(int) nX" does in
+ * the reference build); CUDA's cast would saturate instead.
+ */
+__device__ __forceinline__ int
+x86_float_to_int(float v)
+{
+	if (!(v > -2147483904.0f && v < 2147483648.0f))
+		return INT_MIN;
+	return (int) v;
+}
+
+__device__ __forceinline__ float
+cbrt_lookup(const float *__restrict__ table, float nX)
+{
+	int i = x86_float_to_int(nX);
+	i = max(0, min(kQuant - 2, i));
+	const float f = __fsub_rn(nX, (float) i);
+	const float t0 = __ldg(table + i), t1 = __ldg(table + i + 1);
+	return __fadd_rn(t0, __fmul_rn(f, __fsub_rn(t1, t0)));
+}
+
+__device__ __forceinline__ void
+step_scRGB2XYZ(float &a, float &b, float &c)
+{
+	/* p * VIPS_D65_Y0 is a double product rounded to float */
+	const float R = (float) __dmul_rn((double) a, 100.0);
+	const float G = (float) __dmul_rn((double) b, 100.0);
+	const float B = (float) __dmul_rn((double) c, 100.0);
+	a = __fadd_rn(__fadd_rn(__fmul_rn(0.4124F, R), __fmul_rn(0.3576F, G)), __fmul_rn(0.1805F, B));
+	b = __fadd_rn(__fadd_rn(__fmul_rn(0.2126F, R), __fmul_rn(0.7152F, G)), __fmul_rn(0.0722F, B));
+	c = __fadd_rn(__fadd_rn(__fmul_rn(0.0193F, R), __fmul_rn(0.1192F, G)), __fmul_rn(0.9505F, B));
+}
+
+__device__ __forceinline__ void
+step_XYZ2scRGB(float &a, float &b, float &c)
+{
+	const float X = (float) __ddiv_rn((double) a, 100.0);
+	const float Y = (float) __ddiv_rn((double) b, 100.0);
+	const float Z = (float) __ddiv_rn((double) c, 100.0);
+	a = __fadd_rn(__fadd_rn(__fmul_rn(3.240625F, X), __fmul_rn(-1.537208F, Y)), __fmul_rn(-0.498629F, Z));
+	b = __fadd_rn(__fadd_rn(__fmul_rn(-0.968931F, X), __fmul_rn(1.875756F, Y)), __fmul_rn(0.041518F, Z));
+	c = __fadd_rn(__fadd_rn(__fmul_rn(0.055710F, X), __fmul_rn(-0.204021F, Y)), __fmul_rn(1.056996F, Z));
+}
+
+__device__ __forceinline__ void
+step_XYZ2Lab(const float *__restrict__ table, float &a, float &b, float &c)
+{
+	/* nX = QUANT_ELEMENTS * X / X0: float product, double quotient, float store */
+	const float nX = (float) __ddiv_rn((double) __fmul_rn(100000.0f, a), 95.0470);
+	const float nY = (float) __ddiv_rn((double) __fmul_rn(100000.0f, b), 100.0);
+	const float nZ = (float) __ddiv_rn((double) __fmul_rn(100000.0f, c), 108.8827);
+	const float cbx = cbrt_lookup(table, nX);
+	const float cby = cbrt_lookup(table, nY);
+	const float cbz = cbrt_lookup(table, nZ);
+	a = __fsub_rn(__fmul_rn(116.0F, cby), 16.0F);
+	b = __fmul_rn(500.0F, __fsub_rn(cbx, cby));
+	c = __fmul_rn(200.0F, __fsub_rn(cby, cbz));
+}
+
+__device__ __forceinline__ void
+step_Lab2XYZ(float &a, float &b, float &c)
+{
+	const double X0 = 95.0470, Y0 = 100.0, Z0 = 108.8827;
+	const float L = a, A = b, B = c;
+	double cby, tmp;
+	float X, Y, Z;
+
+	if ((double) L < 8.0) {
+		Y = (float) __ddiv_rn(__dmul_rn((double) L, Y0), 903.3);
+		cby = __dadd_rn(__dmul_rn(7.787, __ddiv_rn((double) Y, Y0)), 16.0 / 116.0);
+	}
+	else {
+		cby = __ddiv_rn(__dadd_rn((double) L, 16.0), 116.0);
+		Y = (float) __dmul_rn(__dmul_rn(__dmul_rn(Y0, cby), cby), cby);
+	}
+	tmp = __dadd_rn(__ddiv_rn((double) A, 500.0), cby);
+	if (tmp < 0.2069)
+		X = (float) __ddiv_rn(__dmul_rn(X0, __dsub_rn(tmp, 0.13793)), 7.787);
+	else
+		X = (float) __dmul_rn(__dmul_rn(__dmul_rn(X0, tmp), tmp), tmp);
+	tmp = __dsub_rn(cby, __ddiv_rn((double) B, 200.0));
+	if (tmp < 0.2069)
+		Z = (float) __ddiv_rn(__dmul_rn(Z0, __dsub_rn(tmp, 0.13793)), 7.787);
+	else
+		Z = (float) __dmul_rn(__dmul_rn(__dmul_rn(Z0, tmp), tmp), tmp);
+	a = X;
+	b = Y;
+	c = Z;
+}
+
+/* vips_col_scRGB2sRGB for one channel, LabQ2sRGB.c:323-353 */
+__device__ __forceinline__ int
+scRGB2sRGB_channel(const int *lut, int maxval, float R)
+{
+	float Yf = __fmul_rn(R, (float) maxval);
+	if (Yf < 0)
+		Yf = 0;
+	else if (Yf > maxval)
+		Yf = maxval;
+	const int Yi = (int) Yf;
+	const int l0 = lut[Yi], l1 = lut[Yi + 1];
+	const float v = __fadd_rn((float) l0, __fmul_rn((float) (l1 - l0), __fsub_rn(Yf, (float) Yi)));
+	return (int) rintf(v);
+}
+
+__device__ __forceinline__ double
+clipd(double lo, double v, double hi)
+{
+	/* VIPS_CLIP(A, V, B) = MAX(A, MIN(B, V)) with C's ?: on doubles */
+	const double m = hi < v ? hi : v;
+	return lo > m ? lo : m;
+}
+
+__device__ __forceinline__ double
+load_elem(const void *p, int fmt, int idx)
+{
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR: return ((const uint8_t *) p)[idx];
+	case VB200_FORMAT_CHAR: return ((const int8_t *) p)[idx];
+	case VB200_FORMAT_USHORT: return ((const uint16_t *) p)[idx];
+	case VB200_FORMAT_SHORT: return ((const int16_t *) p)[idx];
+	case VB200_FORMAT_UINT: return ((const uint32_t *) p)[idx];
+	case VB200_FORMAT_INT: return ((const int32_t *) p)[idx];
+	default: return ((const float *) p)[idx];
+	}
+}
+
+/* vips_cast of a value (conversion/cast.c:123-265): clip in double, truncate */
+__device__ __forceinline__ double
+cast_value(double v, int fmt)
+{
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR: return (double) (uint8_t) clipd(0, v, 255);
+	case VB200_FORMAT_USHORT: return (double) (uint16_t) clipd(0, v, 65535);
+	case VB200_FORMAT_SHORT: return (double) (int16_t) clipd(-32768, v, 32767);
+	case VB200_FORMAT_FLOAT: return (double) (float) v;
+	default: return v;
+	}
+}
+
+__device__ __forceinline__ void
+store_elem(void *p, int fmt, int idx, double v)
+{
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR: ((uint8_t *) p)[idx] = (uint8_t) v; break;
+	case VB200_FORMAT_USHORT: ((uint16_t *) p)[idx] = (uint16_t) v; break;
+	case VB200_FORMAT_SHORT: ((int16_t *) p)[idx] = (int16_t) v; break;
+	default: ((float *) p)[idx] = (float) v; break;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restrict__ in, void *__restrict__ out)
+{
+	__shared__ float s_v2Y_8[256];
+	__shared__ int s_Y2v_8[257];
+	for (int i = threadIdx.x; i < 257; i += blockDim.x) {
+		if (i < 256)
+			s_v2Y_8[i] = P.t.v2Y_8[i];
+		s_Y2v_8[i] = P.t.Y2v_8[i];
+	}
+	__syncthreads();
+
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= P.w)
+		return;
+	const char *pin = (const char *) in + (size_t) y * P.in_bpl;
+	char *pout = (char *) out + (size_t) y * P.out_bpl;
+	const int base = x * P.bands;
+
+	/* the pixel: integer inputs are held exactly in float until their LUT step */
+	float a = (float) load_elem(pin, P.in_fmt, base);
+	float b = (float) load_elem(pin, P.in_fmt, base + 1);
+	float c = (float) load_elem(pin, P.in_fmt, base + 2);
+	int ia = 0, ib = 0, ic = 0; /* integer outputs (sRGB / RGB16 / LabS) */
+
+	for (int s = 0; s < P.n_steps; s++) {
+		switch (P.steps[s].step) {
+		case S_sRGB2scRGB:
+			a = s_v2Y_8[(int) a];
+			b = s_v2Y_8[(int) b];
+			c = s_v2Y_8[(int) c];
+			break;
+		case S_RGB162scRGB:
+			a = __ldg(P.t.v2Y_16 + (int) a);
+			b = __ldg(P.t.v2Y_16 + (int) b);
+			c = __ldg(P.t.v2Y_16 + (int) c);
+			break;
+		case S_scRGB2XYZ:
+			step_scRGB2XYZ(a, b, c);
+			break;
+		case S_XYZ2Lab:
+			step_XYZ2Lab(P.t.cbrt, a, b, c);
+			break;
+		case S_Lab2XYZ:
+			step_Lab2XYZ(a, b, c);
+			break;
+		case S_XYZ2scRGB:
+			step_XYZ2scRGB(a, b, c);
+			break;
+		case S_LabS2Lab:
+			a = (float) __ddiv_rn((double) a, 32767.0 / 100.0);
+			b = (float) __ddiv_rn((double) b, 32768.0 / 128.0);
+			c = (float) __ddiv_rn((double) c, 32768.0 / 128.0);
+			break;
+		case S_Lab2LabS:
+			ia = (int) (short) clipd(0, __dmul_rn((double) a, 32767.0 / 100.0), 32767);
+			ib = (int) (short) clipd(-32768, __dmul_rn((double) b, 32768.0 / 128.0), 32767);
+			ic = (int) (short) clipd(-32768, __dmul_rn((double) c, 32768.0 / 128.0), 32767);
+			break;
+		case S_scRGB2sRGB:
+			if (isnan(a) || isnan(b) || isnan(c))
+				ia = ib = ic = 0;
+			else {
+				ia = scRGB2sRGB_channel(s_Y2v_8, 255, a);
+				ib = scRGB2sRGB_channel(s_Y2v_8, 255, b);
+				ic = scRGB2sRGB_channel(s_Y2v_8, 255, c);
+			}
+			break;
+		case S_scRGB2RGB16:
+			if (isnan(a) || isnan(b) || isnan(c))
+				ia = ib = ic = 0;
+			else {
+				ia = scRGB2sRGB_channel(P.t.Y2v_16, 65535, a);
+				ib = scRGB2sRGB_channel(P.t.Y2v_16, 65535, b);
+				ic = scRGB2sRGB_channel(P.t.Y2v_16, 65535, c);
+			}
+			break;
+		}
+	}
+
+	switch (P.out_fmt) {
+	case VB200_FORMAT_UCHAR:
+		((uint8_t *) pout)[base] = (uint8_t) ia;
+		((uint8_t *) pout)[base + 1] = (uint8_t) ib;
+		((uint8_t *) pout)[base + 2] = (uint8_t) ic;
+		break;
+	case VB200_FORMAT_USHORT:
+		((uint16_t *) pout)[base] = (uint16_t) ia;
+		((uint16_t *) pout)[base + 1] = (uint16_t) ib;
+		((uint16_t *) pout)[base + 2] = (uint16_t) ic;
+		break;
+	case VB200_FORMAT_SHORT:
+		((int16_t *) pout)[base] = (int16_t) ia;
+		((int16_t *) pout)[base + 1] = (int16_t) ib;
+		((int16_t *) pout)[base + 2] = (int16_t) ic;
+		break;
+	default:
+		((float *) pout)[base] = a;
+		((float *) pout)[base + 1] = b;
+		((float *) pout)[base + 2] = c;
+		break;
+	}
+
+	/* extra bands: colour.c:252-291 per step */
+	for (int e = 3; e < P.bands; e++) {
+		double v = load_elem(pin, P.in_fmt, base + e);
+		for (int s = 0; s < P.n_steps; s++) {
+			if (P.steps[s].rescale)
+				v = (double) __fadd_rn(__fmul_rn(P.steps[s].alpha_a, (float) v), 0.0f);
+			v = cast_value(v, P.steps[s].out_fmt);
+		}
+		store_elem(pout, P.out_fmt, base + e, v);
+	}
+}
+
+/* identity routes: a cast to the space's format (colourspace.c rows X -> X) */
+__global__ void __launch_bounds__(256)
+cast_kernel(const void *__restrict__ in, size_t in_bpl, int in_fmt, void *__restrict__ out, size_t out_bpl, int out_fmt,
+	int ne)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= ne)
+		return;
+	const char *pin = (const char *) in + (size_t) blockIdx.y * in_bpl;
+	char *pout = (char *) out + (size_t) blockIdx.y * out_bpl;
+	store_elem(pout, out_fmt, x, cast_value(load_elem(pin, in_fmt, x), out_fmt));
+}
+
+int
+space_format(int space)
+{
+	switch (space) {
+	case VB200_INTERPRETATION_sRGB: return VB200_FORMAT_UCHAR;
+	case VB200_INTERPRETATION_RGB16: return VB200_FORMAT_USHORT;
+	case VB200_INTERPRETATION_LABS: return VB200_FORMAT_SHORT;
+	default: return VB200_FORMAT_FLOAT;
+	}
+}
+
+/* The rows of the reference's route table among these spaces
+ * (colourspace.c:223-497), e.g. sRGB -> LAB = sRGB2scRGB, scRGB2XYZ, XYZ2Lab.
+ */
+int
+build_route(int from, int to, int *steps)
+{
+	const int XYZ = VB200_INTERPRETATION_XYZ, LAB = VB200_INTERPRETATION_LAB, LABS = VB200_INTERPRETATION_LABS;
+	const int sRGB = VB200_INTERPRETATION_sRGB, RGB16 = VB200_INTERPRETATION_RGB16, scRGB = VB200_INTERPRETATION_scRGB;
+	int n = 0;
+	bool known_from = from == XYZ || from == LAB || from == LABS || from == sRGB || from == RGB16 || from == scRGB;
+	bool known_to = to == XYZ || to == LAB || to == LABS || to == sRGB || to == RGB16 || to == scRGB;
+	if (!known_from || !known_to)
+		return -1;
+	if (from == to)
+		return 0;
+	if (from == sRGB) {
+		steps[n++] = S_sRGB2scRGB;
+		from = scRGB;
+	}
+	else if (from == RGB16) {
+		steps[n++] = S_RGB162scRGB;
+		from = scRGB;
+	}
+	else if (from == LABS) {
+		steps[n++] = S_LabS2Lab;
+		from = LAB;
+	}
+	if (from == to)
+		return n;
+	if (from == scRGB && (to == XYZ || to == LAB || to == LABS)) {
+		steps[n++] = S_scRGB2XYZ;
+		from = XYZ;
+	}
+	else if (from == LAB && to != LABS) {
+		steps[n++] = S_Lab2XYZ;
+		from = XYZ;
+	}
+	if (from == to)
+		return n;
+	if (from == XYZ && (to == LAB || to == LABS)) {
+		steps[n++] = S_XYZ2Lab;
+		from = LAB;
+	}
+	else if (from == XYZ) {
+		steps[n++] = S_XYZ2scRGB;
+		from = scRGB;
+	}
+	if (from == to)
+		return n;
+	if (from == LAB && to == LABS)
+		steps[n++] = S_Lab2LabS;
+	else if (from == scRGB && to == sRGB)
+		steps[n++] = S_scRGB2sRGB;
+	else if (from == scRGB && to == RGB16)
+		steps[n++] = S_scRGB2RGB16;
+	else
+		return -1;
+	return n;
+}
+
+void
+step_io(int step, int *in_fmt, int *out_fmt, int *out_type)
+{
+	switch (step) {
+	case S_sRGB2scRGB: *in_fmt = VB200_FORMAT_UCHAR; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_scRGB; break;
+	case S_RGB162scRGB: *in_fmt = VB200_FORMAT_USHORT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_scRGB; break;
+	case S_scRGB2XYZ: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_XYZ; break;
+	case S_XYZ2Lab: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_LAB; break;
+	case S_Lab2LabS: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_SHORT; *out_type = VB200_INTERPRETATION_LABS; break;
+	case S_LabS2Lab: *in_fmt = VB200_FORMAT_SHORT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_LAB; break;
+	case S_Lab2XYZ: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_XYZ; break;
+	case S_XYZ2scRGB: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_scRGB; break;
+	case S_scRGB2sRGB: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_UCHAR; *out_type = VB200_INTERPRETATION_sRGB; break;
+	default: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_USHORT; *out_type = VB200_INTERPRETATION_RGB16; break;
+	}
+}
+
+} // namespace
+
+int
+dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space, cudaStream_t s)
+{
+	int steps[8];
+	const int n = build_route(source_space, space, steps);
+	if (n < 0) {
+		error(domain, "no known route from %d to %d on the device path", source_space, space);
+		return -1;
+	}
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	const dim3 block(256);
+	if (n == 0) {
+		const int ofmt = space_format(space);
+		if (dev_image_new(domain, out, in.w, in.h, in.bands, ofmt, space, s))
+			return -1;
+		const int ne = in.w * in.bands;
+		cast_kernel<<<dim3((ne + 255) / 256, in.h), block, 0, s>>>(in.data, in.bpl, in.fmt, out->data, out->bpl, ofmt, ne);
+		count_launch();
+		return 0;
+	}
+	if (in.bands < 3) {
+		error(domain, "too few bands for operation");
+		return -1;
+	}
+	int first_in, o, t;
+	step_io(steps[0], &first_in, &o, &t);
+	if (in.fmt != first_in) {
+		/* the reference would insert a vips_cast first (colour.c:421-428, 338-342) */
+		error(domain, "source space %d wants band format %d, image has %d", source_space, first_in, in.fmt);
+		return -1;
+	}
+	RouteParams P;
+	memset(&P, 0, sizeof(P));
+	if (get_tables(domain, &P.t))
+		return -1;
+	P.n_steps = n;
+	int type = source_space;
+	for (int i = 0; i < n; i++) {
+		int ifmt, ofmt, otype;
+		step_io(steps[i], &ifmt, &ofmt, &otype);
+		const double before = interpretation_max_alpha(type), after = interpretation_max_alpha(otype);
+		P.steps[i].step = steps[i];
+		P.steps[i].out_fmt = ofmt;
+		P.steps[i].rescale = before != after;
+		P.steps[i].alpha_a = (float) (after / before);
+		type = otype;
+	}
+	P.w = in.w;
+	P.bands = in.bands;
+	P.in_fmt = in.fmt;
+	P.out_fmt = P.steps[n - 1].out_fmt;
+	if (dev_image_new(domain, out, in.w, in.h, in.bands, P.out_fmt, space, s))
+		return -1;
+	P.in_bpl = in.bpl;
+	P.out_bpl = out->bpl;
+	colour_route_kernel<<<dim3((in.w + 255) / 256, in.h), block, 0, s>>>(P, in.data, out->data);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return cuda_fail(domain, e, "colour_route_kernel");
+	count_launch();
+	return 0;
+}
+
+} // namespace vb200
+
+using namespace vb200;
+
+/* reference: vips_colourspace(), colour/colourspace.c:551-617.  The source
+ * space is in->Type (the reference guesses it, vips_image_guess_interpretation).
+ */
+extern "C" int
+vb200_colourspace(const VB200Image *in, VB200Image *out, int space)
+{
+	const char *domain = "colourspace";
+	if (!in || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	cudaStream_t s = current_stream();
+	DevImage din, dout;
+	if (to_device(domain, in, &din, s))
+		return -1;
+	int rc = dev_colourspace(domain, din, &dout, space, in->Type, s);
+	if (!rc)
+		rc = deliver(domain, &dout, in, out, s);
+	dev_image_release(&din, s);
+	return rc;
+}

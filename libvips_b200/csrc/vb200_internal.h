@@ -109,6 +109,10 @@ int dev_resize(const char *domain, const DevImage &in, DevImage *out, double hsc
 
 double interpretation_max_alpha(int type);
 
+/* colour.cu */
+int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space,
+	cudaStream_t s);
+
 /* Launchers of the row/column-table kernels on raw device pointers (used by
  * the generate()-shaped and scanline seams too).
  */

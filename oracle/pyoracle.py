@@ -178,3 +178,46 @@ def thumbnail_image(a, width, height=None, size="both", has_alpha=None, tile=(0,
     if fn(_p(a), w, h, b, width, height, SIZES[size], int(has_alpha), tile[0], tile[1], _p(out)):
         raise ValueError("thumbnail_image")
     return out
+
+
+# ------------------------------------------------------------------ colour
+STEPS = {"sRGB2scRGB": 1, "scRGB2XYZ": 2, "XYZ2Lab": 3, "Lab2LabS": 4, "LabS2Lab": 5, "Lab2XYZ": 6,
+         "XYZ2scRGB": 7, "scRGB2sRGB": 8, "scRGB2RGB16": 9, "RGB162scRGB": 10}
+SPACES = {"xyz": 12, "lab": 13, "labs": 21, "srgb": 22, "rgb16": 25, "scrgb": 28, "b-w": 1, "multiband": 0}
+# (input dtype the step wants, output dtype, output interpretation)
+STEP_IO = {1: (np.uint8, np.float32, 28), 10: (np.uint16, np.float32, 28), 2: (np.float32, np.float32, 12),
+           3: (np.float32, np.float32, 13), 4: (np.float32, np.int16, 21), 5: (np.int16, np.float32, 13),
+           6: (np.float32, np.float32, 12), 7: (np.float32, np.float32, 28), 8: (np.float32, np.uint8, 22),
+           9: (np.float32, np.uint16, 25)}
+
+
+def _space(s):
+    return SPACES[s] if isinstance(s, str) else int(s)
+
+
+def colour_table(which):
+    n = C.c_int()
+    lib().orc_colour_table.restype = C.c_void_p
+    p = lib().orc_colour_table(which, C.byref(n))
+    dt = np.int32 if which in (0, 2) else np.float32
+    return np.frombuffer((C.c_uint8 * (n.value * 4)).from_address(p), dtype=dt).copy()
+
+
+def colour_step(a, step, interpretation):
+    """One colour op (first three bands through the line function, extra bands
+    rescaled / cast / re-attached as vips_colour_build does)."""
+    a, h, w, b, f = _img(a)
+    step = STEPS[step] if isinstance(step, str) else step
+    out = np.empty((h, w, b), STEP_IO[step][1])
+    if lib().orc_colour_step(step, _p(a), w, h, b, f, _space(interpretation), _p(out)):
+        raise ValueError("colour_step")
+    return out
+
+
+def colourspace(a, space, source_space):
+    a, h, w, b, f = _img(a)
+    to, frm = _space(space), _space(source_space)
+    out = np.empty((h, w, b), DTYPE[lib().orc_colourspace_format(to)])
+    if lib().orc_colourspace(_p(a), w, h, b, f, frm, to, _p(out)):
+        raise ValueError("colourspace %s -> %s" % (source_space, space))
+    return out

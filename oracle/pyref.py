@@ -135,3 +135,26 @@ def thumbnail_image(a, width, height=None, size="both", tile=(0, 0)):
     if premul:
         im = im.unpremultiply(uchar=True)
     return im.numpy(tile)
+
+
+# ------------------------------------------------------------------ colour
+def colour_line(step, a):
+    """Run the reference's own *_line function over an (n, 3) array."""
+    step = pyoracle.STEPS[step] if isinstance(step, str) else step
+    a = np.ascontiguousarray(a).reshape(-1, 3)
+    assert a.dtype == pyoracle.STEP_IO[step][0], (a.dtype, step)
+    out = np.empty(a.shape, pyoracle.STEP_IO[step][1])
+    L = lib()
+    L.ref_colour_line.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    if L.ref_colour_line(step, a.ctypes.data, out.ctypes.data, a.shape[0]):
+        raise ValueError("ref_colour_line")
+    return out
+
+
+def colour_table(which):
+    L = lib()
+    L.ref_colour_table.restype = C.c_void_p
+    n = C.c_int()
+    p = L.ref_colour_table(which, C.byref(n))
+    dt = np.int32 if which in (0, 2) else np.float32
+    return np.frombuffer((C.c_uint8 * (n.value * 4)).from_address(p), dtype=dt).copy()

@@ -343,6 +343,39 @@ double vips_image_get_offset(const VipsImage *image);
 double vips_image_get_scale(const VipsImage *image);
 #define VIPS_MATRIX(I, X, Y) ((double *) VIPS_IMAGE_ADDR(I, X, Y))
 
+
+/* ---- bits the colour files touch */
+typedef struct { int done; } GOnce;
+#define G_ONCE_INIT { 0 }
+#define VIPS_ONCE(ONCE, FN, CLIENT) G_STMT_START { if (!(ONCE)->done) { (void) FN(CLIENT); (ONCE)->done = 1; } } G_STMT_END
+typedef struct _VipsArea { void *data; size_t length; int n; } VipsArea;
+typedef VipsArea VipsArrayDouble;
+typedef enum { VIPS_INTENT_PERCEPTUAL = 0, VIPS_INTENT_RELATIVE, VIPS_INTENT_SATURATION, VIPS_INTENT_ABSOLUTE, VIPS_INTENT_AUTO = 32 } VipsIntent;
+typedef enum { VIPS_PCS_LAB, VIPS_PCS_XYZ } VipsPCS;
+/* include/vips/colour.h:124-138 */
+typedef enum {
+	VIPS_CICP_COLOUR_PRIMARIES_BT709 = 1, VIPS_CICP_COLOUR_PRIMARIES_UNSPECIFIED = 2,
+	VIPS_CICP_COLOUR_PRIMARIES_BT470M = 4, VIPS_CICP_COLOUR_PRIMARIES_BT470BG = 5, VIPS_CICP_COLOUR_PRIMARIES_BT601 = 6,
+	VIPS_CICP_COLOUR_PRIMARIES_SMPTE240 = 7, VIPS_CICP_COLOUR_PRIMARIES_GENERIC_FILM = 8,
+	VIPS_CICP_COLOUR_PRIMARIES_BT2020 = 9, VIPS_CICP_COLOUR_PRIMARIES_SMPTE428 = 10,
+	VIPS_CICP_COLOUR_PRIMARIES_SMPTE431 = 11, VIPS_CICP_COLOUR_PRIMARIES_SMPTE432 = 12,
+	VIPS_CICP_COLOUR_PRIMARIES_EBU3213 = 22
+} VipsCICPColourPrimaries;
+int vips_check_vector_length(const char *domain, int n, int len);
+int vips_check_coding(const char *domain, VipsImage *im, VipsCoding coding);
+/* include/vips/colour.h: the sRGB <-> linear tables and helpers LabQ2sRGB.c defines */
+extern float vips_v2Y_8[256];
+extern float vips_v2Y_16[65536];
+void vips_col_make_tables_RGB_8(void);
+void vips_col_make_tables_RGB_16(void);
+int vips_col_sRGB2scRGB_8(int r, int g, int b, float *R, float *G, float *B);
+int vips_col_sRGB2scRGB_16(int r, int g, int b, float *R, float *G, float *B);
+int vips_col_scRGB2XYZ(float R, float G, float B, float *X, float *Y, float *Z);
+int vips_col_XYZ2scRGB(float X, float Y, float Z, float *R, float *G, float *B);
+int vips_col_scRGB2sRGB_8(float R, float G, float B, int *r, int *g, int *b, int *og);
+int vips_col_scRGB2sRGB_16(float R, float G, float B, int *r, int *g, int *b, int *og);
+typedef int (*VipsColourTransformFn)(VipsImage *in, VipsImage **out, ...);
+
 /* shim: the sink.  Evaluate a lazy image into packed memory with the tile
  * geometry vips_get_tile_size() would pick from its demand hint
  * (iofuncs/thread.c:288-325) or an explicit one.

@@ -1,0 +1,143 @@
+"""Colour path.  CPU: the oracle against the reference's own line functions
+(oracle/_ref) and the known answers in the reference's test_colour.py.  GPU:
+the fused route kernel against the oracle, bit for bit (the spec allows 1 ULP
+on float; we assert 0) through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from oracle import pyref
+
+SPACES = ["srgb", "scrgb", "xyz", "lab", "labs", "rgb16"]
+SPACE_DT = {"srgb": np.uint8, "rgb16": np.uint16, "labs": np.int16, "scrgb": np.float32, "xyz": np.float32,
+            "lab": np.float32}
+needs_ref = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built")
+
+
+def sample(space, rng, n=20000, wild=False):
+    if space == "srgb":
+        return rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    if space == "rgb16":
+        return rng.integers(0, 65536, (n, 3), dtype=np.uint16)
+    if space == "labs":
+        a = rng.integers(-32768, 32768, (n, 3), dtype=np.int64).astype(np.int16)
+        a[:, 0] = np.abs(a[:, 0])
+        return a
+    if wild:
+        a = (rng.standard_normal((n, 3)) * 150).astype(np.float32)
+        a[::97, 0] = np.nan
+        a[::89, 1] = np.inf
+        a[::83, 2] = -np.inf
+        return a
+    if space == "scrgb":
+        return rng.random((n, 3), dtype=np.float32) * 1.2 - 0.1
+    if space == "xyz":
+        return rng.random((n, 3), dtype=np.float32) * 110 - 5
+    lab = rng.random((n, 3), dtype=np.float32)
+    lab[:, 0] *= 100
+    lab[:, 1:] = lab[:, 1:] * 256 - 128
+    return lab
+
+
+STEP_SPACE = [("sRGB2scRGB", "srgb"), ("RGB162scRGB", "rgb16"), ("scRGB2XYZ", "scrgb"), ("XYZ2Lab", "xyz"),
+              ("Lab2LabS", "lab"), ("LabS2Lab", "labs"), ("Lab2XYZ", "lab"), ("XYZ2scRGB", "xyz"),
+              ("scRGB2sRGB", "scrgb"), ("scRGB2RGB16", "scrgb")]
+
+
+@needs_ref
+def test_tables_match_reference():
+    for which in range(5):
+        assert np.array_equal(orc.colour_table(which), pyref.colour_table(which))
+
+
+@needs_ref
+@pytest.mark.parametrize("step,space", STEP_SPACE)
+def test_oracle_step_matches_reference_line(step, space):
+    rng = np.random.default_rng(7)
+    for wild in (False, True):
+        a = sample(space, rng, wild=wild)
+        want = pyref.colour_line(step, a)
+        got = orc.colour_step(a.reshape(1, -1, 3), step, space).reshape(-1, 3)
+        assert np.array_equal(want, got, equal_nan=True), step
+
+
+def test_known_answer_lab_to_xyz():
+    """test_colour.py:53-57: Lab(50,0,0) -> XYZ = [17.5064, 18.4187, 20.0547] (Lindbloom)"""
+    xyz = orc.colourspace(np.array([[[50, 0, 0]]], np.float32), "xyz", "lab").ravel()
+    assert np.allclose(xyz, [17.5064, 18.4187, 20.0547], atol=1e-4)
+
+
+def test_oracle_all_pairs_round_trip():
+    """test_colour.py:9-51: every pair of spaces round-trips Lab(50,0,0) + alpha 42 within 0.1"""
+    start = np.array([[[50, 0, 0, 42]]], np.float32)
+    for a in SPACES:
+        x = orc.colourspace(start, a, "lab")
+        for b in SPACES:
+            y = orc.colourspace(x, b, a)
+            back = orc.colourspace(y, "lab", b).astype(np.float64).ravel()
+            tol = 0.5 if "srgb" in (a, b) else 0.1  # 8-bit quantisation
+            assert np.abs(back[:3] - [50, 0, 0]).max() < tol, (a, b, back)
+            assert abs(back[3] - 42) < 1.0, (a, b, back)
+
+
+def test_srgb_all_triples_round_trip_exact():
+    """sRGB -> Lab -> sRGB is the identity on 8-bit data (BASELINE config 4 property)"""
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (64, 4096, 3), dtype=np.uint8)
+    lab = orc.colourspace(a, "lab", "srgb")
+    assert lab.dtype == np.float32
+    assert np.array_equal(orc.colourspace(lab, "srgb", "lab"), a)
+
+
+# ---------------------------------------------------------------------- GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src", SPACES)
+@pytest.mark.parametrize("dst", SPACES)
+def test_gpu_routes(vb, src, dst):
+    rng = np.random.default_rng(11)
+    a = sample(src, rng, n=64 * 257).reshape(64, 257, 3)
+    got = vb.Image(a, src).colourspace(dst).numpy()
+    want = orc.colourspace(a, dst, src)
+    assert got.dtype == want.dtype == SPACE_DT[dst]
+    assert np.array_equal(got, want, equal_nan=True), (src, dst, np.nanmax(np.abs(got.astype(np.float64) - want)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src", ["scrgb", "xyz", "lab"])
+def test_gpu_wild_floats(vb, src):
+    """NaN / Inf / out-of-gamut inputs follow the reference's clipping"""
+    rng = np.random.default_rng(12)
+    a = sample(src, rng, n=40000, wild=True).reshape(100, 400, 3)
+    for dst in SPACES:
+        got = vb.Image(a, src).colourspace(dst).numpy()
+        want = orc.colourspace(a, dst, src)
+        assert np.array_equal(got, want, equal_nan=True), (src, dst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bands", [4, 5])
+def test_gpu_extra_bands(vb, bands):
+    """alpha rides along: rescaled by max_alpha ratio and cast per step (colour.c:252-291)"""
+    rng = np.random.default_rng(13)
+    for src in SPACES:
+        rgb = sample(src, rng, n=33 * 65)
+        extra = sample(src, rng, n=33 * 65)[:, :bands - 3]
+        a = np.concatenate([rgb, extra], axis=1).reshape(33, 65, bands)
+        for dst in SPACES:
+            got = vb.Image(a, src).colourspace(dst).numpy()
+            want = orc.colourspace(a, dst, src)
+            assert np.array_equal(got, want, equal_nan=True), (src, dst)
+
+
+@pytest.mark.gpu
+def test_gpu_srgb_lab_round_trip_full_gamut(vb):
+    """BASELINE config 4 at reduced size: all 2^24 sRGB triples -> Lab -> sRGB is exact,
+    and Lab equals the oracle's on a sample"""
+    g = np.arange(256, dtype=np.uint8)
+    a = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(4096, 4096, 3)
+    lab = vb.Image(a, "srgb").colourspace("lab")
+    back = lab.colourspace("srgb").numpy()
+    assert np.array_equal(back, a)
+    assert np.array_equal(lab.numpy()[:64], orc.colourspace(a[:64], "lab", "srgb"))
