@@ -186,6 +186,47 @@ int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int 
  */
 int vb200_colourspace(const VB200Image *in, VB200Image *out, int space);
 
+/* ------------------------------------------------------------- convolution
+ *
+ * A mask is what the reference passes as a VipsImage matrix: width x height
+ * doubles, row-major, plus the "scale" and "offset" metadata
+ * (reference: vips_check_matrix, vips_image_get_scale/offset).
+ */
+typedef struct {
+	int width;
+	int height;
+	const double *coeff;
+	double scale;
+	double offset;
+} VB200Mask;
+
+/* reference: vips_conv(), convolution/conv.c:60-121.  precision FLOAT ->
+ * vips_convf (double accumulate, float out); INTEGER -> vips_convi (exact
+ * int64 C path; see vb200_set_vector_convi).  APPROXIMATE (conva) returns -1.
+ */
+int vb200_conv(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int precision);
+/* reference: vips_convsep(), convolution/convsep.c:61-114 (mask is n x 1 or 1 x n) */
+int vb200_convsep(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int precision);
+/* reference: vips_gaussblur(), convolution/gaussblur.c:70-114.  min_ampl <= 0 = 0.2 */
+int vb200_gaussblur(const VB200Image *in, VB200Image *out, double sigma, double min_ampl, int precision);
+/* reference: vips_gaussmat(), create/gaussmat.c:93-170.  Allocates out->coeff
+ * (free with vb200_mask_free).
+ */
+int vb200_gaussmat(VB200Mask *out, double sigma, double min_ampl, int separable, int precision);
+void vb200_mask_free(VB200Mask *mask);
+/* reference: vips_sharpen(), convolution/sharpen.c:171-303
+ * (defaults sigma 0.5, x1 2, y2 10, y3 20, m1 0, m2 3)
+ */
+int vb200_sharpen(const VB200Image *in, VB200Image *out, double sigma, double x1, double y2, double y3, double m1,
+	double m2);
+/* 0 (default): uchar INTEGER convolutions use the exact C arithmetic
+ * (vips_convi_gen, what a --vips-novector / non-Highway build runs).
+ * 1: they use the Highway arithmetic (8-bit mantissa + shared exponent,
+ * convi.c:931-1119, convi_hwy.cpp:265-273) whenever vips_convi_intize accepts
+ * the mask, like a Highway build with vips_vector_isenabled().
+ */
+void vb200_set_vector_convi(int on);
+
 /* ------------------------------------------- resample: generate()-shaped ops
  *
  * reference: VipsGenerateFn, include/vips/image.h:151-154.  Fill out->valid

@@ -46,6 +46,11 @@ class CRegion(C.Structure):
     _fields_ = [("im", CImage), ("valid", CRect), ("data", C.c_void_p), ("bpl", C.c_int)]
 
 
+class CMask(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("coeff", C.POINTER(C.c_double)), ("scale", C.c_double),
+                ("offset", C.c_double)]
+
+
 class CReduceParams(C.Structure):
     _fields_ = [("n_point", C.c_int), ("kernel", C.c_int), ("residual_shrink", C.c_double),
                 ("offset", C.c_double)]
@@ -82,6 +87,13 @@ def lib():
         L.vb200_unpremultiply.argtypes = [IP, IP, C.c_double, C.c_int]
         L.vb200_thumbnail_image.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int, C.c_int]
         L.vb200_colourspace.argtypes = [IP, IP, C.c_int]
+        MP = C.POINTER(CMask)
+        L.vb200_conv.argtypes = [IP, IP, MP, C.c_int]
+        L.vb200_convsep.argtypes = [IP, IP, MP, C.c_int]
+        L.vb200_gaussblur.argtypes = [IP, IP, C.c_double, C.c_double, C.c_int]
+        L.vb200_sharpen.argtypes = [IP, IP] + [C.c_double] * 6
+        L.vb200_gaussmat.argtypes = [MP, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.vb200_mask_free.argtypes = [MP]
         L.vb200_image_free.argtypes = [IP]
         L.vb200_thumbnail_plan_new.restype = C.c_void_p
         L.vb200_thumbnail_plan_new.argtypes = [C.c_int] * 9
@@ -128,6 +140,20 @@ def set_stream(handle):
 
 def set_tile_geometry(tile_width=0, tile_height=0, fatstrip_height=0, thinstrip_height=0):
     lib().vb200_set_tile_geometry(tile_width, tile_height, fatstrip_height, thinstrip_height)
+
+
+def set_vector_convi(on):
+    lib().vb200_set_vector_convi(int(on))
+
+
+def gaussmat(sigma, min_ampl, separable=False, precision="integer"):
+    """vips_gaussmat: returns (coefficients, scale, offset)."""
+    m = CMask()
+    _check(lib().vb200_gaussmat(C.byref(m), float(sigma), float(min_ampl), int(separable), PRECISIONS[precision]))
+    a = np.ctypeslib.as_array(m.coeff, shape=(m.height, m.width)).copy()
+    scale, offset = m.scale, m.offset
+    lib().vb200_mask_free(C.byref(m))
+    return a, scale, offset
 
 
 def _k(kernel):
@@ -223,6 +249,28 @@ class Image:
 
     def thumbnail_image(self, width, height=None, size="both", linear=False):
         return self._call(lib().vb200_thumbnail_image, int(width), int(height or 0), SIZES[size], int(linear))
+
+    # ---- convolution
+    @staticmethod
+    def _mask(mask, scale, offset):
+        m = np.ascontiguousarray(mask, np.float64)
+        if m.ndim == 1:
+            m = m[None, :]
+        return m, CMask(m.shape[1], m.shape[0], m.ctypes.data_as(C.POINTER(C.c_double)), float(scale), float(offset))
+
+    def conv(self, mask, scale=1.0, offset=0.0, precision="float"):
+        m, cm = self._mask(mask, scale, offset)
+        return self._call(lib().vb200_conv, C.byref(cm), PRECISIONS[precision])
+
+    def convsep(self, mask, scale=1.0, offset=0.0, precision="float"):
+        m, cm = self._mask(mask, scale, offset)
+        return self._call(lib().vb200_convsep, C.byref(cm), PRECISIONS[precision])
+
+    def gaussblur(self, sigma, min_ampl=0.2, precision="integer"):
+        return self._call(lib().vb200_gaussblur, float(sigma), float(min_ampl), PRECISIONS[precision])
+
+    def sharpen(self, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+        return self._call(lib().vb200_sharpen, float(sigma), float(x1), float(y2), float(y3), float(m1), float(m2))
 
     # ---- colour
     def colourspace(self, space, source_space=None):

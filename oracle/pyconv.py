@@ -1,0 +1,134 @@
+"""Convolution bindings for the oracle and for oracle/_ref (the reference's own
+convf.c / convi.c / gaussmat.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+
+import numpy as np
+
+from . import pyoracle, pyref
+
+PREC = {"integer": 0, "float": 1, "approximate": 2}
+
+
+def _prec(p):
+    return PREC[p] if isinstance(p, str) else int(p)
+
+
+# ------------------------------------------------------------------ oracle
+def gaussmat(sigma, min_ampl, separable=False, precision="integer"):
+    L = pyoracle.lib()
+    L.orc_gaussmat_size.argtypes = [C.c_double, C.c_double]
+    L.orc_gaussmat.restype = C.c_double
+    L.orc_gaussmat.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    n = L.orc_gaussmat_size(sigma, min_ampl)
+    m = np.zeros((1 if separable else n, n), np.float64)
+    scale = L.orc_gaussmat(sigma, min_ampl, int(separable), int(_prec(precision) != 1), m.ctypes.data)
+    return m, scale, 0.0
+
+
+def _out_dtype(dt, precision):
+    if _prec(precision) == 1:
+        return np.float64 if dt == np.float64 else np.float32
+    return dt
+
+
+def conv(a, mask, scale=1.0, offset=0.0, precision="float", vector=False):
+    a, h, w, b, f = pyoracle._img(a)
+    mask = np.ascontiguousarray(mask, np.float64)
+    if mask.ndim == 1:
+        mask = mask[None, :]
+    out = np.empty((h, w, b), _out_dtype(a.dtype, precision))
+    L = pyoracle.lib()
+    L.orc_conv.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                           C.c_double, C.c_int, C.c_int, C.c_void_p]
+    if L.orc_conv(a.ctypes.data, w, h, b, f, mask.ctypes.data, mask.shape[1], mask.shape[0], scale, offset,
+                  _prec(precision), int(vector), out.ctypes.data):
+        raise ValueError("conv")
+    return out
+
+
+def convsep(a, mask, scale=1.0, offset=0.0, precision="float", vector=False):
+    a, h, w, b, f = pyoracle._img(a)
+    mask = np.ascontiguousarray(mask, np.float64).ravel()
+    out = np.empty((h, w, b), _out_dtype(a.dtype, precision))
+    L = pyoracle.lib()
+    L.orc_convsep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                              C.c_double, C.c_int, C.c_int, C.c_void_p]
+    if L.orc_convsep(a.ctypes.data, w, h, b, f, mask.ctypes.data, mask.size, scale, offset, _prec(precision),
+                     int(vector), out.ctypes.data):
+        raise ValueError("convsep")
+    return out
+
+
+def gaussblur(a, sigma, min_ampl=0.2, precision="integer", vector=False):
+    a, h, w, b, f = pyoracle._img(a)
+    out = np.empty((h, w, b), a.dtype if sigma < 0.2 else _out_dtype(a.dtype, precision))
+    L = pyoracle.lib()
+    L.orc_gaussblur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                C.c_int, C.c_void_p]
+    if L.orc_gaussblur(a.ctypes.data, w, h, b, f, sigma, min_ampl, _prec(precision), int(vector), out.ctypes.data):
+        raise ValueError("gaussblur")
+    return out
+
+
+def sharpen(a, interpretation, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+    a, h, w, b, f = pyoracle._img(a)
+    out = np.empty((h, w, b), a.dtype)
+    L = pyoracle.lib()
+    L.orc_sharpen.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_double] * 6 + [C.c_void_p]
+    if L.orc_sharpen(a.ctypes.data, w, h, b, f, pyoracle._space(interpretation), sigma, x1, y2, y3, m1, m2,
+                     out.ctypes.data):
+        raise ValueError("sharpen")
+    return out
+
+
+def convi_intize8(mask, scale):
+    mask = np.ascontiguousarray(mask, np.float64).ravel()
+    mant = np.zeros(mask.size, np.int16)
+    pos = np.zeros(mask.size, np.int32)
+    nnz, exp = C.c_int(), C.c_int()
+    L = pyoracle.lib()
+    L.orc_convi_intize8.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]
+    if L.orc_convi_intize8(mask.ctypes.data, mask.size, scale, mant.ctypes.data, pos.ctypes.data, C.byref(nnz),
+                           C.byref(exp)):
+        return None
+    return mant[:nnz.value], pos[:nnz.value], exp.value
+
+
+# --------------------------------------------------------------- reference
+def _rl():
+    L = pyref.lib()
+    L.ref_matrix.restype = C.c_void_p
+    L.ref_matrix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.ref_conv.restype = C.c_void_p
+    L.ref_conv.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.ref_gaussmat.restype = C.c_void_p
+    L.ref_gaussmat.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+    L.ref_matrix_scale.restype = C.c_double
+    L.ref_matrix_offset.restype = C.c_double
+    L.ref_matrix_scale.argtypes = [C.c_void_p]
+    L.ref_matrix_offset.argtypes = [C.c_void_p]
+    L.ref_matrix_data.restype = C.c_void_p
+    L.ref_matrix_data.argtypes = [C.c_void_p]
+    return L
+
+
+def ref_conv(a, mask, scale=1.0, offset=0.0, precision="float", vector=False, tile=(0, 0)):
+    L = _rl()
+    mask = np.ascontiguousarray(mask, np.float64)
+    if mask.ndim == 1:
+        mask = mask[None, :]
+    m = L.ref_matrix(mask.ctypes.data, mask.shape[1], mask.shape[0], scale, offset)
+    im = pyref.RefImage.from_array(a)
+    out = pyref.RefImage(L.ref_conv(im.h, m, _prec(precision), int(vector)), (im, mask))
+    return out.numpy(tile)
+
+
+def ref_gaussmat(sigma, min_ampl, separable=False, precision="integer"):
+    L = _rl()
+    m = L.ref_gaussmat(sigma, min_ampl, int(separable), _prec(precision))
+    if not m:
+        raise ValueError("ref gaussmat")
+    w, h = L.ref_image_width(m), L.ref_image_height(m)
+    data = np.frombuffer((C.c_uint8 * (w * h * 8)).from_address(L.ref_matrix_data(m)), dtype=np.float64)
+    return data.reshape(h, w).copy(), L.ref_matrix_scale(m), L.ref_matrix_offset(m)

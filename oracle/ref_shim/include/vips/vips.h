@@ -193,6 +193,9 @@ typedef struct _VipsImage {
 	int (*stop_fn)(void *seq, void *a, void *b);
 	void *client1;
 	void *client2;
+	/* shim: the "scale" / "offset" metadata of matrix images */
+	double mat_scale, mat_offset;
+	int mat_meta_set;
 } VipsImage;
 
 typedef struct _VipsRegion {
@@ -339,6 +342,12 @@ int vips_tilecache(VipsImage *in, VipsImage **out, ...);
 int vips_cast(VipsImage *in, VipsImage **out, VipsBandFormat format, ...);
 int vips_copy(VipsImage *in, VipsImage **out, ...);
 int vips_call_split(const char *operation_name, va_list optional, ...);
+void vips_image_set_double(VipsImage *image, const char *name, double d);
+void vips_image_init_fields(VipsImage *image, int xsize, int ysize, int bands, VipsBandFormat format, VipsCoding coding,
+	VipsInterpretation interpretation, double xres, double yres);
+int vips_image_write_prepare(VipsImage *image);
+VipsImage *vips_image_new_matrix(int width, int height);
+void g_object_set(void *object, const char *first, ...);
 double vips_image_get_offset(const VipsImage *image);
 double vips_image_get_scale(const VipsImage *image);
 #define VIPS_MATRIX(I, X, Y) ((double *) VIPS_IMAGE_ADDR(I, X, Y))

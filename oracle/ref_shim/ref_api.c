@@ -65,3 +65,41 @@ void *ref_unpremultiply(void *in, double max_alpha, int uchar_mode)
 						   : vips_unpremultiply((VipsImage *) in, &out, "uchar", uchar_mode, NULL);
 	return rc ? NULL : out;
 }
+
+/* ---------------------------------------------------------------- convolution */
+int vips_convf(VipsImage *in, VipsImage **out, VipsImage *mask, ...);
+int vips_convi(VipsImage *in, VipsImage **out, VipsImage *mask, ...);
+int ref_convi_vector(VipsImage *in, VipsImage **out, VipsImage *mask);
+int vips_gaussmat(VipsImage **out, double sigma, double min_ampl, ...);
+
+void *ref_matrix(const double *coeff, int w, int h, double scale, double offset)
+{
+	VipsImage *m = vips_image_new_matrix(w, h);
+	memcpy(m->data, coeff, sizeof(double) * w * h);
+	vips_image_set_double(m, "scale", scale);
+	vips_image_set_double(m, "offset", offset);
+	return m;
+}
+double ref_matrix_scale(void *m) { return vips_image_get_scale((VipsImage *) m); }
+double ref_matrix_offset(void *m) { return vips_image_get_offset((VipsImage *) m); }
+const double *ref_matrix_data(void *m) { return (const double *) ((VipsImage *) m)->data; }
+
+/* vips_conv's dispatch, conv.c:84-112; vector: 0 = C path, 1 = the Highway arithmetic */
+void *ref_conv(void *in, void *mask, int precision, int vector)
+{
+	VipsImage *out = NULL;
+	int rc;
+	if (precision == VIPS_PRECISION_FLOAT)
+		rc = vips_convf((VipsImage *) in, &out, (VipsImage *) mask, NULL);
+	else if (vector)
+		rc = ref_convi_vector((VipsImage *) in, &out, (VipsImage *) mask);
+	else
+		rc = vips_convi((VipsImage *) in, &out, (VipsImage *) mask, NULL);
+	return rc ? NULL : out;
+}
+
+void *ref_gaussmat(double sigma, double min_ampl, int separable, int precision)
+{
+	VipsImage *out = NULL;
+	return vips_gaussmat(&out, sigma, min_ampl, "separable", separable, "precision", precision, NULL) ? NULL : out;
+}

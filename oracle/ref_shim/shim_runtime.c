@@ -140,6 +140,68 @@ gboolean vips_object_argument_isset(VipsObject *object, const char *name)
 	return FALSE;
 }
 
+/* --------------------------------------------------------- matrix images */
+
+double vips_image_get_scale(const VipsImage *image) { return image->mat_meta_set & 1 ? image->mat_scale : 1.0; }
+double vips_image_get_offset(const VipsImage *image) { return image->mat_meta_set & 2 ? image->mat_offset : 0.0; }
+
+void vips_image_set_double(VipsImage *image, const char *name, double d)
+{
+	if (strcmp(name, "scale") == 0) {
+		image->mat_scale = d;
+		image->mat_meta_set |= 1;
+	}
+	else if (strcmp(name, "offset") == 0) {
+		image->mat_offset = d;
+		image->mat_meta_set |= 2;
+	}
+}
+
+void vips_image_init_fields(VipsImage *image, int xsize, int ysize, int bands, VipsBandFormat format, VipsCoding coding,
+	VipsInterpretation interpretation, double xres, double yres)
+{
+	image->Xsize = xsize;
+	image->Ysize = ysize;
+	image->Bands = bands;
+	image->BandFmt = format;
+	image->Coding = coding;
+	image->Type = interpretation;
+	image->Xres = xres;
+	image->Yres = yres;
+}
+
+int vips_image_write_prepare(VipsImage *image)
+{
+	image->data = (VipsPel *) calloc(1, VIPS_IMAGE_SIZEOF_LINE(image) * image->Ysize + 16);
+	return image->data ? 0 : -1;
+}
+
+VipsImage *vips_image_new_matrix(int width, int height)
+{
+	VipsImage *im = vips_image_new();
+	vips_image_init_fields(im, width, height, 1, VIPS_FORMAT_DOUBLE, VIPS_CODING_NONE, VIPS_INTERPRETATION_MULTIBAND, 1.0, 1.0);
+	vips_image_write_prepare(im);
+	return im;
+}
+
+/* vips_check_matrix, iofuncs/error.c: a 1-band double memory copy carrying scale/offset */
+int vips_check_matrix(const char *domain, VipsImage *im, VipsImage **out)
+{
+	VipsImage *t;
+	int i, n = im->Xsize * im->Ysize;
+	if (im->Bands != 1 || im->BandFmt != VIPS_FORMAT_DOUBLE || !im->data) {
+		vips_error(domain, "shim: matrix images must be 1-band double in memory");
+		return -1;
+	}
+	t = vips_image_new_matrix(im->Xsize, im->Ysize);
+	for (i = 0; i < n; i++)
+		((double *) t->data)[i] = ((double *) im->data)[i];
+	vips_image_set_double(t, "scale", vips_image_get_scale(im));
+	vips_image_set_double(t, "offset", vips_image_get_offset(im));
+	*out = t;
+	return 0;
+}
+
 /* ----------------------------------------------------------------- regions */
 
 VipsRegion *vips_region_new(VipsImage *image)
