@@ -45,7 +45,7 @@ namespace vb200 {
 namespace {
 
 constexpr int kChunkRows = 8; /* K */
-constexpr int kMaxThreads = 640; /* 2 CTAs per SM */
+constexpr int kMaxThreads = 576; /* 18 consumer warps (+1 producer in v2): 2 CTAs per SM at 48 registers */
 
 struct FusedParams {
 	/* input frame geometry */
@@ -70,6 +70,7 @@ struct FusedParams {
 	int NT;	 /* threads per CTA == pair-buffer column stride */
 	int NEmax; /* max embedded shrinkh columns per band (even) */
 	int slots;	/* pair slots per column */
+	int stage_pitch; /* v2: bytes between rows of a TMA stage (multiple of 16) */
 	/* tables */
 	const int2 *vrow;  /* [OH] {first pair (embedded rows >> 1), coefficient set} */
 	const int2 *hcol;  /* [OW] {first pair (embedded cols >> 1), coefficient set} */
@@ -375,6 +376,438 @@ thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__r
 	}
 }
 
+/* ======================================================================
+ * v2: the same chain with the input rows brought on chip by the TMA engine.
+ *
+ * A producer warp (one elected lane) streams the band's input rows into a
+ * shared-memory ring with cp.async.bulk (one bulk copy per row, completion
+ * counted on an mbarrier per stage); the consumer threads never form a global
+ * address: each pixel costs them one LDS.  A stage holds the 2 * VS input rows
+ * of one box-shrunk ROW PAIR.  full[] / empty[] mbarriers hand the stages back
+ * and forth; the consumers' block barrier is a named barrier that excludes the
+ * producer warp.  Arithmetic is identical to v1 (and to the reference).
+ * ====================================================================== */
+
+constexpr int kStages = 2;
+constexpr int kChunkRowsTma = 4;
+/* bytes between rows of a stage: a compile-time constant so the 2 * VS row
+ * reads of a pair are LDS with immediate offsets (band width <= kMaxThreads + 6 columns)
+ */
+constexpr int kStagePitch = (kMaxThreads + 8) * 4;
+
+__device__ __forceinline__ unsigned
+smem_addr(const void *p)
+{
+	return (unsigned) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(unsigned bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void
+mbar_wait(unsigned bar, unsigned parity)
+{
+	unsigned done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+					 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+					 "selp.u32 %0, 1, 0, p;\n\t}"
+					 : "=r"(done)
+					 : "r"(bar), "r"(parity)
+					 : "memory");
+	} while (!done);
+}
+
+__device__ __forceinline__ void
+mbar_arrive(unsigned bar)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+	asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+				 : "memory");
+}
+
+__device__ __forceinline__ void
+bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+				 "l"(src), "r"(bytes), "r"(bar)
+				 : "memory");
+}
+
+__device__ __forceinline__ unsigned
+lds32(unsigned addr)
+{
+	unsigned v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ void
+consumer_barrier(int n_threads)
+{
+	asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+/* one pixel: premultiply (max_alpha 255) and add into the 16-bit-lane accumulators */
+template <bool PREMUL>
+__device__ __forceinline__ void
+accumulate_pixel(unsigned x, unsigned &rb, unsigned &ga)
+{
+	if (PREMUL) {
+		/* out = (in * scale[alpha] + 128) >> 8 with scale[a] = (int) (256 * a / 255.0)
+		 * = a + (a == 255) = (a * 257 + 1) >> 8      premultiply.c:152-166, 253-259
+		 */
+		const unsigned a = x >> 24;
+		const unsigned s = (a * 257u + 1u) >> 8;
+		const unsigned trb = (x & 0x00ff00ffu) * s + 0x00800080u;
+		const unsigned tg = __byte_perm(x, 0, 0x4441) * s + 128u; /* bytes [lo, g', 0, 0] */
+		rb += __byte_perm(trb, 0, 0x4341);						  /* [r', 0, b', 0] */
+		ga += __byte_perm(tg, x, 0x3731);						  /* [g', 0, a, 0] */
+	}
+	else {
+		rb += x & 0x00ff00ffu;
+		ga += __byte_perm(x, 0, 0x4341);
+	}
+}
+
+/* box average of both rows of a pair + byte transposition: [A0 B0 A2 B2] */
+__device__ __forceinline__ unsigned
+average_pair(unsigned lanesA, unsigned lanesB, unsigned mul8, int shift)
+{
+	if (shift >= 0)
+		/* bytes 0 and 2 of (lanes >> shift) are exact: no masking needed */
+		return __byte_perm(lanesA >> shift, lanesB >> shift, 0x6240);
+	const unsigned a = __umulhi(lanesA & 0xffffu, mul8) | (__umulhi(lanesA >> 16, mul8) << 16);
+	const unsigned b = __umulhi(lanesB & 0xffffu, mul8) | (__umulhi(lanesB >> 16, mul8) << 16);
+	return __byte_perm(a, b, 0x6240);
+}
+
+__device__ __forceinline__ unsigned
+finalize_pack(int r, int g, int b, int a)
+{
+	/* unsigned_fixed_round + VIPS_CLIP(0, v, 255), reducev.cpp:461-471 */
+	r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+	g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+	b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+	a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+	return (unsigned) r + (unsigned) g * 256u + (unsigned) b * 65536u + (unsigned) a * 16777216u;
+}
+
+/* NP > 0: both axes use exactly NP coefficient pairs (unrolled, vertical
+ * coefficients in registers); NP == 0: run-time pair counts.
+ */
+template <int VS, int NP, bool PREMUL>
+__global__ void __launch_bounds__(kMaxThreads + 32, 2)
+thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
+	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+
+	constexpr int K = kChunkRowsTma;
+	constexpr int NPR = NP > 0 ? NP : 1;
+	const int NT = P.NT; /* consumer threads; the producer warp is threads NT..NT+31 */
+	const int t = threadIdx.x;
+	const int vs = VS > 0 ? VS : P.VS;
+	const int NPv = NP > 0 ? NP : P.NPv;
+	const int NPh = NP > 0 ? NP : P.NPh;
+	const int rows_per_stage = 2 * vs;
+	const unsigned stage_bytes = (unsigned) rows_per_stage * kStagePitch;
+
+	unsigned char *stages = smem_raw; /* [kStages][2 * vs][kStagePitch] */
+	uint64_t *bars = (uint64_t *) (smem_raw + kStages * stage_bytes);
+	uint2 *pairbuf = (uint2 *) (bars + 2 * kStages);			  /* [slots][NT] */
+	unsigned *rv = (unsigned *) (pairbuf + (size_t) P.slots * NT); /* [K][NT] */
+	uint2 *sh = (uint2 *) (rv + (size_t) K * NT);				  /* [K][NEmax / 2] */
+	int *vcoef = (int *) (sh + (size_t) K * (P.NEmax / 2));
+	int *hcoef = vcoef + P.nvsets * P.NPv;
+	int *uscale = hcoef + P.nhsets * P.NPh; /* [256] unpremultiply LUT */
+
+	const unsigned stages_s = smem_addr(stages);
+	const unsigned full_s = smem_addr(bars);		   /* full[i] at + 8 * i */
+	const unsigned empty_s = full_s + 8u * kStages; /* empty[i] at + 8 * i */
+
+	if (t == 0) {
+		for (int i = 0; i < kStages; i++) {
+			mbar_init(full_s + 8u * i, 1);
+			mbar_init(empty_s + 8u * i, NT / 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int i = t; i < P.nvsets * P.NPv; i += blockDim.x)
+		vcoef[i] = P.vcoef[i];
+	for (int i = t; i < P.nhsets * P.NPh; i += blockDim.x)
+		hcoef[i] = P.hcoef[i];
+	if (PREMUL)
+		for (int i = t; i < 256; i += blockDim.x)
+			/* unpremultiply.c:313-324 with max_alpha 255 (IEEE double, exact on device) */
+			uscale[i] = i == 0 ? 0 : (int) __ddiv_rn(__dmul_rn(256.0, 255.0), (double) i);
+
+	const int xa = blockIdx.x * P.TW;
+	const int xb = min(xa + P.TW, P.OW);
+	const int y_begin = blockIdx.y * P.RPC;
+	const int y_end = min(y_begin + P.RPC, P.OH);
+	const int frame = frame0 + blockIdx.z;
+	const uint8_t *fin = in + (size_t) frame * in_frame_stride;
+	uint8_t *fout = out + (size_t) frame * out_frame_stride;
+
+	const int pair_h0 = __ldg(&P.hcol[xa]).x;
+	const int E0 = 2 * pair_h0;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh) - E0;
+
+	/* input columns of the band: [c_lo, c_hi), 16-byte aligned for the bulk copies */
+	auto column_of = [&](int tt) {
+		const int e = E0 + tt / P.HS;
+		const int k = tt - (tt / P.HS) * P.HS;
+		const int sc = max(0, min(e - P.hembed, P.Ws - 1));
+		return min(sc * P.HS + k, P.W - 1);
+	};
+	const int c_lo = column_of(0) & ~3;
+	const int c_hi = min(P.W, (column_of(NE * P.HS - 1) + 4) & ~3);
+	const unsigned row_bytes = (unsigned) (c_hi - c_lo) * 4u;
+
+	__syncthreads();
+
+	if (t >= NT) {
+		/* ---------------- producer warp: one lane feeds the ring */
+		if (t == NT) {
+			const uint8_t *src0 = fin + (size_t) c_lo * 4;
+			int s = 0;
+			unsigned phase = 0;
+			int pdone = INT_MIN;
+			for (int ya = y_begin; ya < y_end; ya += K) {
+				const int yb = min(ya + K, y_end);
+				const int P0 = __ldg(&P.vrow[ya]).x;
+				const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+				for (int p = max(pdone, P0); p <= P1; p++) {
+					mbar_wait(empty_s + 8u * s, phase ^ 1u);
+					mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
+					const unsigned dst = stages_s + (unsigned) s * stage_bytes;
+					for (int j = 0; j < 2; j++) {
+						/* embedded reducev row -> box-shrunk row -> vs input rows, all EXTEND_COPY */
+						const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
+						for (int k = 0; k < vs; k++) {
+							const int row = min(sr * vs + k, P.H - 1);
+							bulk_copy_g2s(dst + (unsigned) (j * vs + k) * kStagePitch, src0 + (size_t) row * P.in_bpl, row_bytes,
+								full_s + 8u * s);
+						}
+					}
+					if (++s == kStages) {
+						s = 0;
+						phase ^= 1u;
+					}
+				}
+				pdone = P1 + 1;
+			}
+		}
+		return;
+	}
+
+	/* ---------------- consumers */
+	/* idle threads (beyond the band) shadow the last column */
+	const unsigned my_col = stages_s + (unsigned) (column_of(min(t, NE * P.HS - 1)) - c_lo) * 4u;
+	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
+	const bool lane0 = (t & 31) == 0;
+	const unsigned vmul8 = P.vmul8;
+	const int vshift = P.vshift;
+
+	int s = 0;
+	unsigned phase = 0;
+	int pdone = INT_MIN;
+	int P0_prev = 0;
+	int cset = -1;
+	unsigned cf[NPR];
+
+	for (int ya = y_begin; ya < y_end; ya += K) {
+		const int yb = min(ya + K, y_end);
+		const int P0 = __ldg(&P.vrow[ya]).x;
+		const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+
+		/* stage V.a: carry the window over */
+		int pfirst = P0;
+		if (pdone > P0) {
+			const int shift = P0 - P0_prev;
+			if (shift > 0) {
+				const int cnt = pdone - P0;
+				uint2 *dstp = pairbuf + t;
+				const uint2 *srcp = pairbuf + shift * NT + t;
+#pragma unroll 4
+				for (int i = 0; i < cnt; i++)
+					dstp[i * NT] = srcp[i * NT];
+			}
+			pfirst = pdone;
+		}
+
+		/* stage V.b: consume one ring stage per row pair */
+		uint2 *pdst = pairbuf + (pfirst - P0) * NT + t;
+		for (int p = pfirst; p <= P1; p++, pdst += NT) {
+			const unsigned src = my_col + (unsigned) s * stage_bytes;
+			unsigned rbA = amend2, gaA = amend2, rbB = amend2, gaB = amend2;
+			mbar_wait(full_s + 8u * s, phase);
+			if (VS > 0) {
+				unsigned pa[VS > 0 ? VS : 1], pb[VS > 0 ? VS : 1];
+#pragma unroll
+				for (int k = 0; k < VS; k++) {
+					pa[k] = lds32(src + (unsigned) k * kStagePitch);
+					pb[k] = lds32(src + (unsigned) (VS + k) * kStagePitch);
+				}
+				__syncwarp();
+				if (lane0)
+					mbar_arrive(empty_s + 8u * s);
+#pragma unroll
+				for (int k = 0; k < VS; k++) {
+					accumulate_pixel<PREMUL>(pa[k], rbA, gaA);
+					accumulate_pixel<PREMUL>(pb[k], rbB, gaB);
+				}
+			}
+			else {
+				for (int k = 0; k < vs; k++) {
+					accumulate_pixel<PREMUL>(lds32(src + (unsigned) k * kStagePitch), rbA, gaA);
+					accumulate_pixel<PREMUL>(lds32(src + (unsigned) (vs + k) * kStagePitch), rbB, gaB);
+				}
+				__syncwarp();
+				if (lane0)
+					mbar_arrive(empty_s + 8u * s);
+			}
+			if (++s == kStages) {
+				s = 0;
+				phase ^= 1u;
+			}
+			uint2 w;
+			w.x = average_pair(rbA, rbB, vmul8, vshift); /* [rA rB bA bB] */
+			w.y = average_pair(gaA, gaB, vmul8, vshift); /* [gA gB aA aB] */
+			*pdst = w;
+		}
+
+		/* stage V.c: reducev */
+		unsigned *rvp = rv + t;
+		for (int y = ya; y < yb; y++, rvp += NT) {
+			const int2 vr = __ldg(&P.vrow[y]);
+			const uint2 *win = pairbuf + (vr.x - P0) * NT + t;
+			int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+			if (NP > 0) {
+				if (vr.y != cset) {
+					cset = vr.y;
+#pragma unroll
+					for (int k = 0; k < NPR; k++)
+						cf[k] = (unsigned) vcoef[cset * NPR + k];
+				}
+#pragma unroll
+				for (int k = 0; k < NPR; k++) {
+					const uint2 w = win[k * NT];
+					r = dp2a_lo(cf[k], w.x, r);
+					b = dp2a_hi(cf[k], w.x, b);
+					g = dp2a_lo(cf[k], w.y, g);
+					a = dp2a_hi(cf[k], w.y, a);
+				}
+			}
+			else {
+				const int *cfp = vcoef + vr.y * NPv;
+				for (int k = 0; k < NPv; k++) {
+					const uint2 w = win[k * NT];
+					const unsigned c = (unsigned) cfp[k];
+					r = dp2a_lo(c, w.x, r);
+					b = dp2a_hi(c, w.x, b);
+					g = dp2a_lo(c, w.y, g);
+					a = dp2a_hi(c, w.y, a);
+				}
+			}
+			*rvp = finalize_pack(r, g, b, a);
+		}
+		pdone = P1 + 1;
+		P0_prev = P0;
+
+		consumer_barrier(NT);
+
+		/* stage H1: box-sum HS adjacent columns -> column pairs */
+		const int rows = yb - ya;
+		const int npairs = NE / 2;
+		const unsigned hamend2 = (unsigned) (P.HS / 2) * 0x00010001u;
+		for (int idx = t; idx < rows * npairs; idx += NT) {
+			const int k = idx / npairs;
+			const int j = idx - k * npairs;
+			const unsigned *src = rv + k * NT + (2 * j) * P.HS;
+			unsigned rbA = hamend2, gaA = hamend2, rbB = hamend2, gaB = hamend2;
+			if (P.HS == 4) {
+				const uint4 A = *(const uint4 *) src;
+				const uint4 B = *(const uint4 *) (src + 4);
+				rbA += (A.x & 0x00ff00ffu) + (A.y & 0x00ff00ffu) + (A.z & 0x00ff00ffu) + (A.w & 0x00ff00ffu);
+				gaA += __byte_perm(A.x, 0, 0x4341) + __byte_perm(A.y, 0, 0x4341) + __byte_perm(A.z, 0, 0x4341) +
+					__byte_perm(A.w, 0, 0x4341);
+				rbB += (B.x & 0x00ff00ffu) + (B.y & 0x00ff00ffu) + (B.z & 0x00ff00ffu) + (B.w & 0x00ff00ffu);
+				gaB += __byte_perm(B.x, 0, 0x4341) + __byte_perm(B.y, 0, 0x4341) + __byte_perm(B.z, 0, 0x4341) +
+					__byte_perm(B.w, 0, 0x4341);
+			}
+			else
+				for (int i = 0; i < P.HS; i++) {
+					const unsigned wA = src[i];
+					const unsigned wB = src[P.HS + i];
+					rbA += wA & 0x00ff00ffu;
+					gaA += __byte_perm(wA, 0, 0x4341);
+					rbB += wB & 0x00ff00ffu;
+					gaB += __byte_perm(wB, 0, 0x4341);
+				}
+			uint2 w;
+			w.x = average_pair(rbA, rbB, P.hmul8, P.hshift);
+			w.y = average_pair(gaA, gaB, P.hmul8, P.hshift);
+			sh[k * (P.NEmax / 2) + j] = w;
+		}
+
+		consumer_barrier(NT);
+
+		/* stage H2: reduceh + unpremultiply + store */
+		const int bw = xb - xa;
+		for (int idx = t; idx < rows * bw; idx += NT) {
+			const int k = idx / bw;
+			const int x = xa + (idx - k * bw);
+			const int2 hc = __ldg(&P.hcol[x]);
+			const uint2 *win = sh + k * (P.NEmax / 2) + (hc.x - pair_h0);
+			const int *cfp = hcoef + hc.y * NPh;
+			int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+			if (NP > 0) {
+#pragma unroll
+				for (int kk = 0; kk < NPR; kk++) {
+					const uint2 w = win[kk];
+					const unsigned c = (unsigned) cfp[kk];
+					r = dp2a_lo(c, w.x, r);
+					b = dp2a_hi(c, w.x, b);
+					g = dp2a_lo(c, w.y, g);
+					a = dp2a_hi(c, w.y, a);
+				}
+			}
+			else
+				for (int kk = 0; kk < NPh; kk++) {
+					const uint2 w = win[kk];
+					const unsigned c = (unsigned) cfp[kk];
+					r = dp2a_lo(c, w.x, r);
+					b = dp2a_hi(c, w.x, b);
+					g = dp2a_lo(c, w.y, g);
+					a = dp2a_hi(c, w.y, a);
+				}
+			r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+			g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+			b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+			a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+			if (PREMUL) {
+				/* unpremultiply.c:209-222: byte store without clip */
+				const int sc = uscale[a];
+				r = ((r * sc + 128) >> 8) & 0xff;
+				g = ((g * sc + 128) >> 8) & 0xff;
+				b = ((b * sc + 128) >> 8) & 0xff;
+			}
+			*(unsigned *) (fout + (size_t) (ya + k) * P.out_bpl + (size_t) x * 4) =
+				(unsigned) r | ((unsigned) g << 8) | ((unsigned) b << 16) | ((unsigned) a << 24);
+		}
+	}
+}
+
 /* Pack a 65 x n table of short coefficients into parity-aligned s16x2 pairs:
  * set (phase, parity) holds pairs k = 0..NP-1 = (c[2k - parity], c[2k + 1 - parity]).
  */
@@ -401,6 +834,29 @@ struct PairSets {
 		}
 		return id;
 	}
+
+	/* Drop trailing pairs that are zero in EVERY set in use (e.g. Lanczos3 at
+	 * shrink 2, phase 0: the 13th tap is 0, so 6 pairs carry the 12 live taps).
+	 * Zero taps contribute nothing to the integer sum, so results are unchanged.
+	 */
+	void
+	trim()
+	{
+		const int nsets = (int) ids.size();
+		int keep = 1;
+		for (int s = 0; s < nsets; s++)
+			for (int k = 0; k < NP; k++)
+				if (coef[(size_t) s * NP + k] != 0)
+					keep = std::max(keep, k + 1);
+		if (keep == NP)
+			return;
+		std::vector<int> packed;
+		for (int s = 0; s < nsets; s++)
+			for (int k = 0; k < keep; k++)
+				packed.push_back(coef[(size_t) s * NP + k]);
+		coef.swap(packed);
+		NP = keep;
+	}
 };
 
 } // namespace
@@ -423,6 +879,10 @@ struct ThumbnailPlanImpl {
 	void *tables = nullptr; /* one device block */
 	size_t smem = 0;
 	dim3 grid;
+	/* v2 (TMA-fed) variant of the same kernel: its own chunking and smem */
+	bool tma_ok = false;
+	int slots_tma = 0;
+	size_t smem_tma = 0;
 	/* host pump */
 	static constexpr int kStreams = 3;
 	cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
@@ -496,6 +956,65 @@ launch_fused_vs(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_
 	}
 }
 
+/* v2 launchers: same grid, one extra (producer) warp per CTA */
+template <int VS, int NP, bool PREMUL>
+int
+launch_tma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride,
+	void *out, size_t out_stride, int n, dim3 grid, cudaStream_t s)
+{
+	auto kern = thumbnail_fused_tma_kernel<VS, NP, PREMUL>;
+	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_tma));
+	for (int f0 = 0; f0 < n; f0 += 32768) {
+		grid.z = std::min(32768, n - f0);
+		kern<<<grid, fp.NT + 32, pl->smem_tma, s>>>(fp, (const uint8_t *) in, in_stride, (uint8_t *) out, out_stride, f0);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "thumbnail_fused_tma_kernel launch");
+		count_launch();
+	}
+	return 0;
+}
+
+template <int NP, bool PREMUL>
+int
+launch_tma_vs(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t is, void *out,
+	size_t os, int n, dim3 grid, cudaStream_t s)
+{
+	switch (fp.VS) {
+	case 1: return launch_tma_t<1, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	case 2: return launch_tma_t<2, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	case 3: return launch_tma_t<3, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	case 4: return launch_tma_t<4, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	case 8: return launch_tma_t<8, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	default: return launch_tma_t<0, NP, PREMUL>(domain, pl, fp, in, is, out, os, n, grid, s);
+	}
+}
+
+int
+launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
+	cudaStream_t s)
+{
+	FusedParams fp = pl->fp;
+	fp.slots = pl->slots_tma;
+	/* rows per CTA: whole height for big batches, split when there are few frames */
+	const int K = kChunkRowsTma;
+	const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
+	int rpc = ((pl->OH + K - 1) / K) * K;
+	while ((long long) bands_x * ((pl->OH + rpc - 1) / rpc) * n < 2 * 148 && rpc > 4 * K)
+		rpc = ((rpc / 2 + K - 1) / K) * K;
+	fp.RPC = rpc;
+	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+	const int np = fp.NPv == fp.NPh ? fp.NPv : 0;
+	if (np == 6)
+		return pl->premul ? launch_tma_vs<6, true>(domain, pl, fp, in, is, out, os, n, grid, s)
+						  : launch_tma_vs<6, false>(domain, pl, fp, in, is, out, os, n, grid, s);
+	if (np == 7)
+		return pl->premul ? launch_tma_vs<7, true>(domain, pl, fp, in, is, out, os, n, grid, s)
+						  : launch_tma_vs<7, false>(domain, pl, fp, in, is, out, os, n, grid, s);
+	return pl->premul ? launch_tma_vs<0, true>(domain, pl, fp, in, is, out, os, n, grid, s)
+					  : launch_tma_vs<0, false>(domain, pl, fp, in, is, out, os, n, grid, s);
+}
+
 int
 plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 {
@@ -529,6 +1048,8 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		hcol[x].x = th.first[x] >> 1;
 		hcol[x].y = shh.get(th, th.phase[x], th.first[x] & 1);
 	}
+	sv.trim();
+	shh.trim();
 
 	FusedParams &fp = pl->fp;
 	fp.W = pl->W;
@@ -575,7 +1096,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		return worst * fp.HS;
 	};
 	int nemax = 0;
-	while (TW > 4 && band_threads(TW, &nemax) > 640)
+	while (TW > 4 && band_threads(TW, &nemax) > kMaxThreads)
 		TW /= 2;
 	if (band_threads(TW, &nemax) > kMaxThreads)
 		return 1;
@@ -601,6 +1122,39 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 512) * 4;
 	if (pl->smem > 200 * 1024)
 		return 1;
+
+	/* v2: rows arrive by cp.async.bulk, which wants 16-byte aligned rows */
+	pl->tma_ok = false;
+	if ((fp.in_bpl % 16) == 0 && fp.VS <= 16) {
+		int slots2 = 0;
+		for (int ya = 0; ya < pl->OH; ya += kChunkRowsTma) {
+			const int yb = std::min(ya + kChunkRowsTma, pl->OH);
+			slots2 = std::max(slots2, vrow[yb - 1].x + fp.NPv - 1 - vrow[ya].x + 1);
+		}
+		/* widest band, in input columns rounded out to 4-pixel (16-byte) bounds */
+		auto column_of = [&](int E0, int tt) {
+			const int e = E0 + tt / fp.HS;
+			const int k = tt % fp.HS;
+			const int sc = std::max(0, std::min(e - fp.hembed, fp.Ws - 1));
+			return std::min(sc * fp.HS + k, fp.W - 1);
+		};
+		int max_cols = 0;
+		for (int xa = 0; xa < pl->OW; xa += TW) {
+			const int xb = std::min(xa + TW, pl->OW);
+			const int E0 = 2 * hcol[xa].x;
+			const int ne = 2 * (hcol[xb - 1].x + fp.NPh) - E0;
+			const int c_lo = column_of(E0, 0) & ~3;
+			const int c_hi = std::min(fp.W, (column_of(E0, ne * fp.HS - 1) + 4) & ~3);
+			max_cols = std::max(max_cols, c_hi - c_lo);
+		}
+		fp.stage_pitch = kStagePitch;
+		pl->slots_tma = slots2;
+		pl->smem_tma = (size_t) kStages * 2 * fp.VS * kStagePitch + 2 * kStages * 8 + (size_t) slots2 * fp.NT * 8 +
+			(size_t) kChunkRowsTma * fp.NT * 4 + (size_t) kChunkRowsTma * (nemax / 2) * 8 +
+			(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 256) * 4;
+		pl->tma_ok = max_cols * 4 <= kStagePitch && pl->smem_tma <= 110 * 1024 && fp.max_alpha == 255.0 &&
+			getenv("VB200_NO_TMA") == nullptr;
+	}
 
 	/* upload tables as one block */
 	const size_t n_vrow = vrow.size() * sizeof(int2), n_hcol = hcol.size() * sizeof(int2);
@@ -673,6 +1227,9 @@ thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void 
 	if (n <= 0)
 		return 0;
 	if (pl->fused) {
+		/* the TMA-fed kernel when rows, frames and the base pointer are 16-byte aligned */
+		if (pl->tma_ok && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0))
+			return launch_tma(domain, pl, in, in_stride, out, out_stride, n, s);
 		/* enough CTAs to fill the machine: split rows when the batch is small */
 		FusedParams &fp = pl->fp;
 		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
