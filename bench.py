@@ -209,10 +209,8 @@ def main():
         want = pyoracle.thumbnail_image(common, TARGET)
         assert np.array_equal(outs[0].cpu().numpy(), want), "GPU thumbnail differs from the oracle"
     if dist:
-        lo, hi = csum.clone(), csum.clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert int(lo) == int(hi), "ranks disagree on the shared frame"
+        from libvips_b200 import shard
+        assert shard.all_agree(dist, csum.reshape(1)), "ranks disagree on the shared frame"
 
     for _ in range(max(0, args.warmup - 1)):
         step()

@@ -71,6 +71,7 @@ struct FusedParams {
 	int NEmax; /* max embedded shrinkh columns per band (even) */
 	int slots;	/* pair slots per column */
 	int stage_pitch; /* v2: bytes between rows of a TMA stage (multiple of 16) */
+	int vgrid, hgrid; /* pair p covers embedded rows / columns 2p + grid, 2p + grid + 1 */
 	/* tables */
 	const int2 *vrow;  /* [OH] {first pair (embedded rows >> 1), coefficient set} */
 	const int2 *hcol;  /* [OW] {first pair (embedded cols >> 1), coefficient set} */
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2)
 thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
 	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
 
 	const int NT = P.NT;
 	const int t = threadIdx.x;
@@ -193,8 +194,8 @@ thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__r
 
 	/* embedded shrinkh columns of this band: [E0, E0 + NE), E0 even */
 	const int pair_h0 = __ldg(&P.hcol[xa]).x;
-	const int E0 = 2 * pair_h0;
-	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh) - E0;
+	const int E0 = 2 * pair_h0 + P.hgrid;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh - pair_h0);
 
 	/* this thread's input pixel column (clamped: the two EXTEND_COPY embeds of
 	 * reduceh.cpp:515-521 and shrinkh.c:383)
@@ -239,8 +240,8 @@ thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__r
 				 * embed of reducev.cpp:975-981) -> VS input rows each (the
 				 * round-up embed of shrinkv.c:501)
 				 */
-				const int sA = max(0, min(2 * p - P.vembed, P.Hs - 1));
-				const int sB = max(0, min(2 * p + 1 - P.vembed, P.Hs - 1));
+				const int sA = max(0, min(2 * p + P.vgrid - P.vembed, P.Hs - 1));
+				const int sB = max(0, min(2 * p + P.vgrid + 1 - P.vembed, P.Hs - 1));
 				if (VS > 0) {
 					unsigned pa[VS > 0 ? VS : 1], pb[VS > 0 ? VS : 1];
 #pragma unroll
@@ -388,7 +389,7 @@ thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__r
  * producer warp.  Arithmetic is identical to v1 (and to the reference).
  * ====================================================================== */
 
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr int kChunkRowsTma = 4;
 /* bytes between rows of a stage: a compile-time constant so the 2 * VS row
  * reads of a pair are LDS with immediate offsets (band width <= kMaxThreads + 6 columns)
@@ -559,8 +560,8 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	uint8_t *fout = out + (size_t) frame * out_frame_stride;
 
 	const int pair_h0 = __ldg(&P.hcol[xa]).x;
-	const int E0 = 2 * pair_h0;
-	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh) - E0;
+	const int E0 = 2 * pair_h0 + P.hgrid;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh - pair_h0);
 
 	/* input columns of the band: [c_lo, c_hi), 16-byte aligned for the bulk copies */
 	auto column_of = [&](int tt) {
@@ -592,7 +593,7 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 					const unsigned dst = stages_s + (unsigned) s * stage_bytes;
 					for (int j = 0; j < 2; j++) {
 						/* embedded reducev row -> box-shrunk row -> vs input rows, all EXTEND_COPY */
-						const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
+						const int sr = max(0, min(2 * p + P.vgrid + j - P.vembed, P.Hs - 1));
 						for (int k = 0; k < vs; k++) {
 							const int row = min(sr * vs + k, P.H - 1);
 							bulk_copy_g2s(dst + (unsigned) (j * vs + k) * kStagePitch, src0 + (size_t) row * P.in_bpl, row_bytes,
@@ -1036,20 +1037,43 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	build_axis_table(tv, pl->OH, pl->gv.residual, pl->gv.offset, pl->gv.n_point, VB200_KERNEL_LANCZOS3, rect_h);
 	build_axis_table(th, pl->OW, pl->gh.residual, pl->gh.offset, pl->gh.n_point, VB200_KERNEL_LANCZOS3, tile_w);
 
+	/* Pair grid: pair p covers embedded positions (2p + grid, 2p + grid + 1).  Pick
+	 * the grid phase (0 / 1) that needs fewer coefficient pairs once all-zero
+	 * trailing pairs are trimmed: at shrink 2 the first tap sits on an odd
+	 * position, so grid 1 packs the 12 live Lanczos3 taps into 6 pairs, not 7.
+	 */
+	auto build_sets = [](const AxisTable &t, int count, int grid, PairSets &sets, std::vector<int2> &idx) {
+		sets = PairSets();
+		sets.NP = (t.n_point + 2) / 2;
+		idx.resize(count);
+		for (int i = 0; i < count; i++) {
+			const int rel = t.first[i] - grid;
+			idx[i].x = rel >> 1; /* floor */
+			idx[i].y = sets.get(t, t.phase[i], rel & 1);
+		}
+		sets.trim();
+	};
 	PairSets sv, shh;
-	sv.NP = (pl->gv.n_point + 2) / 2;
-	shh.NP = (pl->gh.n_point + 2) / 2;
-	std::vector<int2> vrow(pl->OH), hcol(pl->OW);
-	for (int y = 0; y < pl->OH; y++) {
-		vrow[y].x = tv.first[y] >> 1;
-		vrow[y].y = sv.get(tv, tv.phase[y], tv.first[y] & 1);
+	std::vector<int2> vrow, hcol;
+	int vgrid = 0, hgrid = 0;
+	{
+		PairSets alt;
+		std::vector<int2> alt_idx;
+		build_sets(tv, pl->OH, 0, sv, vrow);
+		build_sets(tv, pl->OH, 1, alt, alt_idx);
+		if (alt.NP < sv.NP) {
+			sv = alt;
+			vrow = alt_idx;
+			vgrid = 1;
+		}
+		build_sets(th, pl->OW, 0, shh, hcol);
+		build_sets(th, pl->OW, 1, alt, alt_idx);
+		if (alt.NP < shh.NP) {
+			shh = alt;
+			hcol = alt_idx;
+			hgrid = 1;
+		}
 	}
-	for (int x = 0; x < pl->OW; x++) {
-		hcol[x].x = th.first[x] >> 1;
-		hcol[x].y = shh.get(th, th.phase[x], th.first[x] & 1);
-	}
-	sv.trim();
-	shh.trim();
 
 	FusedParams &fp = pl->fp;
 	fp.W = pl->W;
@@ -1059,6 +1083,8 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	fp.Hs = pl->gv.shrunk_size;
 	fp.vembed = tv.embed;
 	fp.NPv = sv.NP;
+	fp.vgrid = vgrid;
+	fp.hgrid = hgrid;
 	fp.vmul8 = (unsigned) (((1LL << 32) / (256LL * fp.VS)) << 8);
 	fp.vshift = -1;
 	for (int sft = 0; sft < 9; sft++)
@@ -1141,8 +1167,8 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		int max_cols = 0;
 		for (int xa = 0; xa < pl->OW; xa += TW) {
 			const int xb = std::min(xa + TW, pl->OW);
-			const int E0 = 2 * hcol[xa].x;
-			const int ne = 2 * (hcol[xb - 1].x + fp.NPh) - E0;
+			const int E0 = 2 * hcol[xa].x + hgrid;
+			const int ne = 2 * (hcol[xb - 1].x + fp.NPh - hcol[xa].x);
 			const int c_lo = column_of(E0, 0) & ~3;
 			const int c_hi = std::min(fp.W, (column_of(E0, ne * fp.HS - 1) + 4) & ~3);
 			max_cols = std::max(max_cols, c_hi - c_lo);
@@ -1152,7 +1178,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		pl->smem_tma = (size_t) kStages * 2 * fp.VS * kStagePitch + 2 * kStages * 8 + (size_t) slots2 * fp.NT * 8 +
 			(size_t) kChunkRowsTma * fp.NT * 4 + (size_t) kChunkRowsTma * (nemax / 2) * 8 +
 			(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 256) * 4;
-		pl->tma_ok = max_cols * 4 <= kStagePitch && pl->smem_tma <= 110 * 1024 && fp.max_alpha == 255.0 &&
+		pl->tma_ok = max_cols * 4 <= kStagePitch && pl->smem_tma <= 113 * 1024 && fp.max_alpha == 255.0 &&
 			getenv("VB200_NO_TMA") == nullptr;
 	}
 
