@@ -1472,8 +1472,50 @@ vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int heig
 	if (ensure_init(domain))
 		return -1;
 	if (linear) {
-		error(domain, "linear thumbnails are not on the device path yet");
-		return -1;
+		/* thumbnail.c:766-806, 848-902, 971-987 for an 8-bit sRGB image without ICC profile:
+		 * sRGB -> scRGB (float; alpha / 255), float premultiply (max_alpha 1.0), float
+		 * resize, float unpremultiply, scRGB -> sRGB.  Unfused chain of leaf kernels.
+		 */
+		if (in->BandFmt != VB200_FORMAT_UCHAR || in->Bands < 3) {
+			error(domain, "linear thumbnails on the device path need an 8-bit image with 3+ bands");
+			return -1;
+		}
+		const int th = height > 0 ? height : width;
+		double hs, vs;
+		thumbnail_shrink(in->Xsize, in->Ysize, width, th, size, &hs, &vs);
+		if (hs < 1.0 || vs < 1.0) {
+			error(domain, "upsizing is not on the device path yet");
+			return -1;
+		}
+		cudaStream_t s = current_stream();
+		DevImage din, lin, pre, res, unpre, fin;
+		if (to_device(domain, in, &din, s))
+			return -1;
+		const bool premul = (in->Bands == 4 || in->Bands > 4) && hs != 1.0 && vs != 1.0;
+		int rc = dev_colourspace(domain, din, &lin, VB200_INTERPRETATION_scRGB, VB200_INTERPRETATION_sRGB, s);
+		const DevImage *cur = &lin;
+		if (!rc && premul) {
+			rc = dev_premultiply(domain, lin, &pre, 0.0, 0, s); /* max_alpha from scRGB: 1.0 */
+			cur = &pre;
+		}
+		if (!rc)
+			rc = dev_resize(domain, *cur, &res, 1.0 / hs, 1.0 / vs, VB200_KERNEL_LANCZOS3, 2.0, s);
+		cur = &res;
+		if (!rc && premul) {
+			rc = dev_unpremultiply(domain, res, &unpre, 0.0, 0, s);
+			cur = &unpre;
+		}
+		if (!rc)
+			rc = dev_colourspace(domain, *cur, &fin, VB200_INTERPRETATION_sRGB, VB200_INTERPRETATION_scRGB, s);
+		if (!rc)
+			rc = deliver(domain, &fin, in, out, s);
+		dev_image_release(&din, s);
+		dev_image_release(&lin, s);
+		dev_image_release(&pre, s);
+		dev_image_release(&res, s);
+		dev_image_release(&unpre, s);
+		dev_image_release(&fin, s);
+		return rc;
 	}
 	/* vips_image_hasalpha(): 2 or 4 bands (iofuncs/header.c) for 8-bit sRGB / B_W */
 	const int has_alpha = in->Bands == 2 || in->Bands == 4;

@@ -1037,3 +1037,48 @@ orc_thumbnail_image_batch(const void *in, int n_frames, int w, int h, int bands,
 		t.join();
 	return rc;
 }
+
+/* vips_thumbnail_image(..., linear = TRUE) for an 8-bit sRGB image without ICC
+ * profile: thumbnail.c:766-806 (to scRGB), :848-902 (float premultiply / resize /
+ * unpremultiply + cast), :971-987 (back to sRGB).  bands >= 3.
+ */
+extern "C" int orc_colourspace(const void *in, int w, int h, int bands, int fmt, int from, int to, void *out);
+
+extern "C" int
+orc_thumbnail_image_linear(const void *in, int w, int h, int bands, int target_w, int target_h, int size_mode,
+	int has_alpha, int tile_w, int tile_h, void *out)
+{
+	double hs, vs;
+	int ow, oh;
+	if (bands < 3)
+		return -1; /* GREY16 route: not restated */
+	if (orc_thumbnail_size(w, h, target_w, target_h, size_mode, &hs, &vs, &ow, &oh))
+		return -1;
+	if (hs < 1.0 || vs < 1.0)
+		return -1;
+
+	const size_t n_in = (size_t) w * h * bands, n_out = (size_t) ow * oh * bands;
+	std::vector<float> lin(n_in), pre, res(n_out), unpre;
+	if (orc_colourspace(in, w, h, bands, ORC_FORMAT_UCHAR, 22 /*sRGB*/, 28 /*scRGB*/, lin.data()))
+		return -1;
+	const bool premul = has_alpha && hs != 1.0 && vs != 1.0;
+	const float *src = lin.data();
+	if (premul) {
+		pre.resize(n_in);
+		/* max_alpha = vips_interpretation_max_alpha(scRGB) = 1.0 */
+		if (orc_premultiply(lin.data(), w, h, bands, ORC_FORMAT_FLOAT, 1.0, 0, pre.data()))
+			return -1;
+		src = pre.data();
+	}
+	if (orc_resize(src, w, h, bands, ORC_FORMAT_FLOAT, 1.0 / hs, 1.0 / vs, ORC_KERNEL_LANCZOS3, 2.0, tile_w, tile_h,
+			res.data()))
+		return -1;
+	const float *last = res.data();
+	if (premul) {
+		unpre.resize(n_out);
+		if (orc_unpremultiply(res.data(), ow, oh, bands, ORC_FORMAT_FLOAT, 1.0, 0, unpre.data()))
+			return -1;
+		last = unpre.data(); /* vips_cast(float -> float) is the identity */
+	}
+	return orc_colourspace(last, ow, oh, bands, ORC_FORMAT_FLOAT, 28, 22, out);
+}

@@ -51,6 +51,17 @@ def main():
     np.savez_compressed(path, **out)
     print("wrote %s: %d cases, %d bytes" % (path, len(out), os.path.getsize(path)))
 
+    # the one stored-answer fixture the reference's test-suite has on this path
+    # (test/test-suite/test_resample.py:234-238): rgba.png -> thumbnail(64, linear=True)
+    # .flatten(255).avg() must be within 1 of rgba-correct.ppm.  Decoded here with PIL.
+    from PIL import Image
+    images = "/root/reference/test/test-suite/images"
+    rgba = np.array(Image.open(os.path.join(images, "rgba.png")))
+    correct = np.array(Image.open(os.path.join(images, "rgba-correct.ppm")))
+    path = os.path.join(HERE, "rgba_fixture.npz")
+    np.savez_compressed(path, rgba=rgba, correct_avg=np.float64(correct.mean()), correct_shape=np.array(correct.shape))
+    print("wrote %s: %d bytes" % (path, os.path.getsize(path)))
+
 
 if __name__ == "__main__":
     main()
