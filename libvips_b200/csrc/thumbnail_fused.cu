@@ -391,6 +391,7 @@ thumbnail_fused_kernel(const __grid_constant__ FusedParams P, const uint8_t *__r
 
 constexpr int kStages = 3;
 constexpr int kChunkRowsTma = 4;
+constexpr int kColsPerThread = 2;
 /* bytes between rows of a stage: a compile-time constant so the 2 * VS row
  * reads of a pair are LDS with immediate offsets (band width <= kMaxThreads + 6 columns)
  */
@@ -504,9 +505,12 @@ finalize_pack(int r, int g, int b, int a)
 
 /* NP > 0: both axes use exactly NP coefficient pairs (unrolled, vertical
  * coefficients in registers); NP == 0: run-time pair counts.
+ * CPT: adjacent input pixel columns per consumer thread.  Two columns halve
+ * every per-thread overhead (barrier waits, loop control, window addressing,
+ * coefficient loads) and turn the window traffic into 128-bit LDS / STS.
  */
-template <int VS, int NP, bool PREMUL>
-__global__ void __launch_bounds__(kMaxThreads + 32, 2)
+template <int VS, int NP, bool PREMUL, int CPT>
+__global__ void __launch_bounds__(kMaxThreads / CPT + 32, 2)
 thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
 	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
 {
@@ -514,7 +518,9 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 
 	constexpr int K = kChunkRowsTma;
 	constexpr int NPR = NP > 0 ? NP : 1;
-	const int NT = P.NT; /* consumer threads; the producer warp is threads NT..NT+31 */
+	constexpr int VSR = VS > 0 ? VS : 1;
+	const int NT = P.NT;	   /* consumer threads; the producer warp is threads NT..NT+31 */
+	const int NC = NT * CPT; /* columns: the stride of pairbuf / rv */
 	const int t = threadIdx.x;
 	const int vs = VS > 0 ? VS : P.VS;
 	const int NPv = NP > 0 ? NP : P.NPv;
@@ -524,9 +530,9 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 
 	unsigned char *stages = smem_raw; /* [kStages][2 * vs][kStagePitch] */
 	uint64_t *bars = (uint64_t *) (smem_raw + kStages * stage_bytes);
-	uint2 *pairbuf = (uint2 *) (bars + 2 * kStages);			  /* [slots][NT] */
-	unsigned *rv = (unsigned *) (pairbuf + (size_t) P.slots * NT); /* [K][NT] */
-	uint2 *sh = (uint2 *) (rv + (size_t) K * NT);				  /* [K][NEmax / 2] */
+	uint2 *pairbuf = (uint2 *) (bars + 2 * kStages);			  /* [slots][NC] */
+	unsigned *rv = (unsigned *) (pairbuf + (size_t) P.slots * NC); /* [K][NC] */
+	uint2 *sh = (uint2 *) (rv + (size_t) K * NC);				  /* [K][NEmax / 2] */
 	int *vcoef = (int *) (sh + (size_t) K * (P.NEmax / 2));
 	int *hcoef = vcoef + P.nvsets * P.NPv;
 	int *uscale = hcoef + P.nhsets * P.NPh; /* [256] unpremultiply LUT */
@@ -612,12 +618,16 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	}
 
 	/* ---------------- consumers */
-	/* idle threads (beyond the band) shadow the last column */
-	const unsigned my_col = stages_s + (unsigned) (column_of(min(t, NE * P.HS - 1)) - c_lo) * 4u;
+	/* columns beyond the band shadow the last one */
+	unsigned my_col[CPT];
+#pragma unroll
+	for (int i = 0; i < CPT; i++)
+		my_col[i] = stages_s + (unsigned) (column_of(min(t * CPT + i, NE * P.HS - 1)) - c_lo) * 4u;
 	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
 	const bool lane0 = (t & 31) == 0;
 	const unsigned vmul8 = P.vmul8;
 	const int vshift = P.vshift;
+	const int tc = t * CPT; /* first column of this thread */
 
 	int s = 0;
 	unsigned phase = 0;
@@ -637,42 +647,55 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 			const int shift = P0 - P0_prev;
 			if (shift > 0) {
 				const int cnt = pdone - P0;
-				uint2 *dstp = pairbuf + t;
-				const uint2 *srcp = pairbuf + shift * NT + t;
+				uint2 *dstp = pairbuf + tc;
+				const uint2 *srcp = pairbuf + shift * NC + tc;
 #pragma unroll 4
-				for (int i = 0; i < cnt; i++)
-					dstp[i * NT] = srcp[i * NT];
+				for (int i = 0; i < cnt; i++) {
+					if (CPT == 2)
+						*(uint4 *) (dstp + i * NC) = *(const uint4 *) (srcp + i * NC);
+					else
+						dstp[i * NC] = srcp[i * NC];
+				}
 			}
 			pfirst = pdone;
 		}
 
 		/* stage V.b: consume one ring stage per row pair */
-		uint2 *pdst = pairbuf + (pfirst - P0) * NT + t;
-		for (int p = pfirst; p <= P1; p++, pdst += NT) {
-			const unsigned src = my_col + (unsigned) s * stage_bytes;
-			unsigned rbA = amend2, gaA = amend2, rbB = amend2, gaB = amend2;
+		uint2 *pdst = pairbuf + (pfirst - P0) * NC + tc;
+		for (int p = pfirst; p <= P1; p++, pdst += NC) {
+			const unsigned soff = (unsigned) s * stage_bytes;
+			unsigned rbA[CPT], gaA[CPT], rbB[CPT], gaB[CPT];
+#pragma unroll
+			for (int i = 0; i < CPT; i++)
+				rbA[i] = gaA[i] = rbB[i] = gaB[i] = amend2;
 			mbar_wait(full_s + 8u * s, phase);
 			if (VS > 0) {
-				unsigned pa[VS > 0 ? VS : 1], pb[VS > 0 ? VS : 1];
+				unsigned pa[CPT][VSR], pb[CPT][VSR];
 #pragma unroll
-				for (int k = 0; k < VS; k++) {
-					pa[k] = lds32(src + (unsigned) k * kStagePitch);
-					pb[k] = lds32(src + (unsigned) (VS + k) * kStagePitch);
-				}
+				for (int i = 0; i < CPT; i++)
+#pragma unroll
+					for (int k = 0; k < VSR; k++) {
+						pa[i][k] = lds32(my_col[i] + soff + (unsigned) k * kStagePitch);
+						pb[i][k] = lds32(my_col[i] + soff + (unsigned) (VSR + k) * kStagePitch);
+					}
 				__syncwarp();
 				if (lane0)
 					mbar_arrive(empty_s + 8u * s);
 #pragma unroll
-				for (int k = 0; k < VS; k++) {
-					accumulate_pixel<PREMUL>(pa[k], rbA, gaA);
-					accumulate_pixel<PREMUL>(pb[k], rbB, gaB);
-				}
+				for (int i = 0; i < CPT; i++)
+#pragma unroll
+					for (int k = 0; k < VSR; k++) {
+						accumulate_pixel<PREMUL>(pa[i][k], rbA[i], gaA[i]);
+						accumulate_pixel<PREMUL>(pb[i][k], rbB[i], gaB[i]);
+					}
 			}
 			else {
-				for (int k = 0; k < vs; k++) {
-					accumulate_pixel<PREMUL>(lds32(src + (unsigned) k * kStagePitch), rbA, gaA);
-					accumulate_pixel<PREMUL>(lds32(src + (unsigned) (vs + k) * kStagePitch), rbB, gaB);
-				}
+				for (int k = 0; k < vs; k++)
+#pragma unroll
+					for (int i = 0; i < CPT; i++) {
+						accumulate_pixel<PREMUL>(lds32(my_col[i] + soff + (unsigned) k * kStagePitch), rbA[i], gaA[i]);
+						accumulate_pixel<PREMUL>(lds32(my_col[i] + soff + (unsigned) (vs + k) * kStagePitch), rbB[i], gaB[i]);
+					}
 				__syncwarp();
 				if (lane0)
 					mbar_arrive(empty_s + 8u * s);
@@ -681,18 +704,27 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 				s = 0;
 				phase ^= 1u;
 			}
-			uint2 w;
-			w.x = average_pair(rbA, rbB, vmul8, vshift); /* [rA rB bA bB] */
-			w.y = average_pair(gaA, gaB, vmul8, vshift); /* [gA gB aA aB] */
-			*pdst = w;
+			uint2 w[CPT];
+#pragma unroll
+			for (int i = 0; i < CPT; i++) {
+				w[i].x = average_pair(rbA[i], rbB[i], vmul8, vshift); /* [rA rB bA bB] */
+				w[i].y = average_pair(gaA[i], gaB[i], vmul8, vshift); /* [gA gB aA aB] */
+			}
+			if (CPT == 2)
+				*(uint4 *) pdst = make_uint4(w[0].x, w[0].y, w[CPT - 1].x, w[CPT - 1].y);
+			else
+				*pdst = w[0];
 		}
 
 		/* stage V.c: reducev */
-		unsigned *rvp = rv + t;
-		for (int y = ya; y < yb; y++, rvp += NT) {
+		unsigned *rvp = rv + tc;
+		for (int y = ya; y < yb; y++, rvp += NC) {
 			const int2 vr = __ldg(&P.vrow[y]);
-			const uint2 *win = pairbuf + (vr.x - P0) * NT + t;
-			int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+			const uint2 *win = pairbuf + (vr.x - P0) * NC + tc;
+			int acc[CPT][4];
+#pragma unroll
+			for (int i = 0; i < CPT; i++)
+				acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = VB200_INTERPOLATE_SCALE >> 1;
 			if (NP > 0) {
 				if (vr.y != cset) {
 					cset = vr.y;
@@ -702,25 +734,42 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 				}
 #pragma unroll
 				for (int k = 0; k < NPR; k++) {
-					const uint2 w = win[k * NT];
-					r = dp2a_lo(cf[k], w.x, r);
-					b = dp2a_hi(cf[k], w.x, b);
-					g = dp2a_lo(cf[k], w.y, g);
-					a = dp2a_hi(cf[k], w.y, a);
+					uint2 w[CPT];
+					if (CPT == 2) {
+						const uint4 q = *(const uint4 *) (win + k * NC);
+						w[0] = make_uint2(q.x, q.y);
+						w[CPT - 1] = make_uint2(q.z, q.w);
+					}
+					else
+						w[0] = win[k * NC];
+#pragma unroll
+					for (int i = 0; i < CPT; i++) {
+						acc[i][0] = dp2a_lo(cf[k], w[i].x, acc[i][0]);
+						acc[i][2] = dp2a_hi(cf[k], w[i].x, acc[i][2]);
+						acc[i][1] = dp2a_lo(cf[k], w[i].y, acc[i][1]);
+						acc[i][3] = dp2a_hi(cf[k], w[i].y, acc[i][3]);
+					}
 				}
 			}
 			else {
 				const int *cfp = vcoef + vr.y * NPv;
 				for (int k = 0; k < NPv; k++) {
-					const uint2 w = win[k * NT];
 					const unsigned c = (unsigned) cfp[k];
-					r = dp2a_lo(c, w.x, r);
-					b = dp2a_hi(c, w.x, b);
-					g = dp2a_lo(c, w.y, g);
-					a = dp2a_hi(c, w.y, a);
+#pragma unroll
+					for (int i = 0; i < CPT; i++) {
+						const uint2 w = win[k * NC + i];
+						acc[i][0] = dp2a_lo(c, w.x, acc[i][0]);
+						acc[i][2] = dp2a_hi(c, w.x, acc[i][2]);
+						acc[i][1] = dp2a_lo(c, w.y, acc[i][1]);
+						acc[i][3] = dp2a_hi(c, w.y, acc[i][3]);
+					}
 				}
 			}
-			*rvp = finalize_pack(r, g, b, a);
+			if (CPT == 2)
+				*(uint2 *) rvp = make_uint2(finalize_pack(acc[0][0], acc[0][1], acc[0][2], acc[0][3]),
+					finalize_pack(acc[CPT - 1][0], acc[CPT - 1][1], acc[CPT - 1][2], acc[CPT - 1][3]));
+			else
+				*rvp = finalize_pack(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
 		}
 		pdone = P1 + 1;
 		P0_prev = P0;
@@ -734,7 +783,7 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 		for (int idx = t; idx < rows * npairs; idx += NT) {
 			const int k = idx / npairs;
 			const int j = idx - k * npairs;
-			const unsigned *src = rv + k * NT + (2 * j) * P.HS;
+			const unsigned *src = rv + k * NC + (2 * j) * P.HS;
 			unsigned rbA = hamend2, gaA = hamend2, rbB = hamend2, gaB = hamend2;
 			if (P.HS == 4) {
 				const uint4 A = *(const uint4 *) src;
@@ -963,7 +1012,7 @@ int
 launch_tma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride,
 	void *out, size_t out_stride, int n, dim3 grid, cudaStream_t s)
 {
-	auto kern = thumbnail_fused_tma_kernel<VS, NP, PREMUL>;
+	auto kern = thumbnail_fused_tma_kernel<VS, NP, PREMUL, kColsPerThread>;
 	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_tma));
 	for (int f0 = 0; f0 < n; f0 += 32768) {
 		grid.z = std::min(32768, n - f0);
@@ -997,6 +1046,8 @@ launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 {
 	FusedParams fp = pl->fp;
 	fp.slots = pl->slots_tma;
+	/* consumer threads: kColsPerThread columns each (pl->fp.NT counts columns, rounded to 32) */
+	fp.NT = ((pl->fp.NT / kColsPerThread + 31) / 32) * 32;
 	/* rows per CTA: whole height for big batches, split when there are few frames */
 	const int K = kChunkRowsTma;
 	const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
@@ -1175,8 +1226,9 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		}
 		fp.stage_pitch = kStagePitch;
 		pl->slots_tma = slots2;
-		pl->smem_tma = (size_t) kStages * 2 * fp.VS * kStagePitch + 2 * kStages * 8 + (size_t) slots2 * fp.NT * 8 +
-			(size_t) kChunkRowsTma * fp.NT * 4 + (size_t) kChunkRowsTma * (nemax / 2) * 8 +
+		const int nc = ((fp.NT / kColsPerThread + 31) / 32) * 32 * kColsPerThread; /* buffer columns of the v2 kernel */
+		pl->smem_tma = (size_t) kStages * 2 * fp.VS * kStagePitch + 2 * kStages * 8 + (size_t) slots2 * nc * 8 +
+			(size_t) kChunkRowsTma * nc * 4 + (size_t) kChunkRowsTma * (nemax / 2) * 8 +
 			(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 256) * 4;
 		pl->tma_ok = max_cols * 4 <= kStagePitch && pl->smem_tma <= 113 * 1024 && fp.max_alpha == 255.0 &&
 			getenv("VB200_NO_TMA") == nullptr;
