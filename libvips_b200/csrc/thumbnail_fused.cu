@@ -452,6 +452,16 @@ lds32(unsigned addr)
 	return v;
 }
 
+/* idx / d for 0 <= idx < 4096 and 1 <= d: exact via a float reciprocal + one correction */
+__device__ __forceinline__ int
+fast_div(int idx, int d)
+{
+	int q = (int) (__int2float_rn(idx) * __frcp_rn(__int2float_rn(d)));
+	const int r = idx - q * d;
+	q += (r >= d) - (r < 0);
+	return q;
+}
+
 __device__ __forceinline__ void
 consumer_barrier(int n_threads)
 {
@@ -583,36 +593,36 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	__syncthreads();
 
 	if (t >= NT) {
-		/* ---------------- producer warp: one lane feeds the ring */
-		if (t == NT) {
-			const uint8_t *src0 = fin + (size_t) c_lo * 4;
-			int s = 0;
-			unsigned phase = 0;
-			int pdone = INT_MIN;
-			for (int ya = y_begin; ya < y_end; ya += K) {
-				const int yb = min(ya + K, y_end);
-				const int P0 = __ldg(&P.vrow[ya]).x;
-				const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
-				for (int p = max(pdone, P0); p <= P1; p++) {
-					mbar_wait(empty_s + 8u * s, phase ^ 1u);
+		/* ---------------- producer warp: lane L copies row L of each stage */
+		const int lane = t - NT;
+		const uint8_t *src0 = fin + (size_t) c_lo * 4;
+		const int j = lane / vs, k = lane - j * vs; /* lane -> (row of the pair, row of the box) */
+		const bool copier = lane < rows_per_stage;
+		int s = 0;
+		unsigned phase = 0;
+		int pdone = INT_MIN;
+		for (int ya = y_begin; ya < y_end; ya += K) {
+			const int yb = min(ya + K, y_end);
+			const int P0 = __ldg(&P.vrow[ya]).x;
+			const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+			for (int p = max(pdone, P0); p <= P1; p++) {
+				mbar_wait(empty_s + 8u * s, phase ^ 1u);
+				if (lane == 0)
 					mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
-					const unsigned dst = stages_s + (unsigned) s * stage_bytes;
-					for (int j = 0; j < 2; j++) {
-						/* embedded reducev row -> box-shrunk row -> vs input rows, all EXTEND_COPY */
-						const int sr = max(0, min(2 * p + P.vgrid + j - P.vembed, P.Hs - 1));
-						for (int k = 0; k < vs; k++) {
-							const int row = min(sr * vs + k, P.H - 1);
-							bulk_copy_g2s(dst + (unsigned) (j * vs + k) * kStagePitch, src0 + (size_t) row * P.in_bpl, row_bytes,
-								full_s + 8u * s);
-						}
-					}
-					if (++s == kStages) {
-						s = 0;
-						phase ^= 1u;
-					}
+				__syncwarp();
+				if (copier) {
+					/* embedded reducev row -> box-shrunk row -> input row, all EXTEND_COPY */
+					const int sr = max(0, min(2 * p + P.vgrid + j - P.vembed, P.Hs - 1));
+					const int row = min(sr * vs + k, P.H - 1);
+					bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * kStagePitch,
+						src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
 				}
-				pdone = P1 + 1;
+				if (++s == kStages) {
+					s = 0;
+					phase ^= 1u;
+				}
 			}
+			pdone = P1 + 1;
 		}
 		return;
 	}
@@ -626,7 +636,8 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
 	const bool lane0 = (t & 31) == 0;
 	const unsigned vmul8 = P.vmul8;
-	const int vshift = P.vshift;
+	/* box height a power of two: the average is a compile-time shift */
+	const int vshift = VS == 1 ? 0 : VS == 2 ? 1 : VS == 4 ? 2 : VS == 8 ? 3 : P.vshift;
 	const int tc = t * CPT; /* first column of this thread */
 
 	int s = 0;
@@ -781,7 +792,7 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 		const int npairs = NE / 2;
 		const unsigned hamend2 = (unsigned) (P.HS / 2) * 0x00010001u;
 		for (int idx = t; idx < rows * npairs; idx += NT) {
-			const int k = idx / npairs;
+			const int k = fast_div(idx, npairs);
 			const int j = idx - k * npairs;
 			const unsigned *src = rv + k * NC + (2 * j) * P.HS;
 			unsigned rbA = hamend2, gaA = hamend2, rbB = hamend2, gaB = hamend2;
@@ -815,7 +826,7 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 		/* stage H2: reduceh + unpremultiply + store */
 		const int bw = xb - xa;
 		for (int idx = t; idx < rows * bw; idx += NT) {
-			const int k = idx / bw;
+			const int k = fast_div(idx, bw);
 			const int x = xa + (idx - k * bw);
 			const int2 hc = __ldg(&P.hcol[x]);
 			const uint2 *win = sh + k * (P.NEmax / 2) + (hc.x - pair_h0);

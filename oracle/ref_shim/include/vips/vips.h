@@ -149,7 +149,10 @@ typedef struct _VipsRect { int left, top, width, height; } VipsRect;
 #define VIPS_RECT_BOTTOM(R) ((R)->top + (R)->height)
 
 /* ---- object model: plain structs, never instantiated through a type system */
-typedef struct _GObject { int kind; /* shim: 1 image, 2 region, 3 operation */ } GObject;
+typedef struct _GObject {
+	int kind;    /* shim: 1 image, 2 region, 3 anything made by vips__shim_object_new() */
+	void *klass; /* shim: the class struct (see vips__shim_type_register) */
+} GObject;
 typedef struct _GObjectClass {
 	void (*set_property)(void);
 	void (*get_property)(void);
@@ -238,32 +241,42 @@ typedef void *(*VipsStartFn)(VipsImage *out, void *a, void *b);
 typedef int (*VipsStopFn)(void *seq, void *a, void *b);
 
 /* ---- class plumbing: compiled, class_init never runs; build() does */
+/* A miniature type system: one heap class struct per type, made on first use by
+ * copying the parent's class struct and running the type's own class_init --
+ * exactly the part of GObject the reference's build()/dispatch code relies on.
+ */
+GType vips__shim_type_register(GType parent, size_t class_size, size_t instance_size, void (*class_init)(void *),
+	void (*instance_init)(void *), gpointer *parent_class_out);
+void *vips__shim_object_new(GType type);
+GType vips__shim_operation_get_type(void);
 #define G_DEFINE_TYPE(TN, t_n, T_P) \
 	static void t_n##_class_init(TN##Class *klass); \
 	static void t_n##_init(TN *self); \
-	static gpointer t_n##_parent_class = (gpointer) &vips__shim_parent_class; \
+	static gpointer t_n##_parent_class = 0; \
 	GType t_n##_get_type(void) \
 	{ \
-		(void) t_n##_class_init; (void) t_n##_init; (void) t_n##_parent_class; \
-		return 0; \
+		static GType type = 0; \
+		if (!type) \
+			type = vips__shim_type_register((GType) (T_P), sizeof(TN##Class), sizeof(TN), \
+				(void (*)(void *)) t_n##_class_init, (void (*)(void *)) t_n##_init, &t_n##_parent_class); \
+		return type; \
 	}
 #define G_DEFINE_ABSTRACT_TYPE(TN, t_n, T_P) G_DEFINE_TYPE(TN, t_n, T_P)
 #define G_TYPE_CHECK_INSTANCE_CAST(O, T, C) ((C *) (O))
 #define G_TYPE_CHECK_CLASS_CAST(K, T, C) ((C *) (K))
 #define G_TYPE_CHECK_INSTANCE_TYPE(O, T) (1)
 #define G_TYPE_CHECK_CLASS_TYPE(K, T) (1)
-#define G_TYPE_INSTANCE_GET_CLASS(O, T, C) ((C *) vips__shim_class)
-extern VipsOperationClass vips__shim_parent_class; /* build() returns 0 */
-#define vips__shim_class ((char *) &vips__shim_parent_class)
+#define G_TYPE_INSTANCE_GET_CLASS(O, T, C) ((C *) ((GObject *) (O))->klass)
 #define G_OBJECT(O) ((GObject *) (O))
 #define G_OBJECT_CLASS(K) ((GObjectClass *) (K))
 #define VIPS_OBJECT(O) ((VipsObject *) (O))
 #define VIPS_OBJECT_CLASS(K) ((VipsObjectClass *) (K))
-#define VIPS_OBJECT_GET_CLASS(O) ((VipsObjectClass *) vips__shim_class)
+#define VIPS_OBJECT_GET_CLASS(O) ((VipsObjectClass *) ((GObject *) (O))->klass)
 #define VIPS_OPERATION(O) ((VipsOperation *) (O))
 #define VIPS_OPERATION_CLASS(K) ((VipsOperationClass *) (K))
 #define VIPS_IMAGE(O) ((VipsImage *) (O))
-#define VIPS_TYPE_OPERATION 0
+#define VIPS_TYPE_OPERATION (vips__shim_operation_get_type())
+#define VIPS_TYPE_OBJECT (vips__shim_operation_get_type())
 #define VIPS_TYPE_IMAGE 0
 #define VIPS_TYPE_KERNEL 0
 #define VIPS_TYPE_PRECISION 0
@@ -384,6 +397,60 @@ int vips_col_XYZ2scRGB(float X, float Y, float Z, float *R, float *G, float *B);
 int vips_col_scRGB2sRGB_8(float R, float G, float B, int *r, int *g, int *b, int *og);
 int vips_col_scRGB2sRGB_16(float R, float G, float B, int *r, int *g, int *b, int *og);
 typedef int (*VipsColourTransformFn)(VipsImage *in, VipsImage **out, ...);
+
+
+/* ---- include/vips/interpolate.h, include/vips/transform.h */
+typedef struct _VipsInterpolate { VipsObject parent_object; } VipsInterpolate;
+typedef void (*VipsInterpolateMethod)(VipsInterpolate *interpolate, void *out, VipsRegion *in, double x, double y);
+typedef struct _VipsInterpolateClass {
+	VipsObjectClass parent_class;
+	VipsInterpolateMethod interpolate;
+	int (*get_window_size)(VipsInterpolate *interpolate);
+	int window_size;
+	int (*get_window_offset)(VipsInterpolate *interpolate);
+	int window_offset;
+} VipsInterpolateClass;
+#define VIPS_TYPE_INTERPOLATE (vips_interpolate_get_type())
+#define VIPS_INTERPOLATE(obj) ((VipsInterpolate *) (obj))
+#define VIPS_INTERPOLATE_CLASS(klass) ((VipsInterpolateClass *) (klass))
+#define VIPS_INTERPOLATE_GET_CLASS(obj) ((VipsInterpolateClass *) ((GObject *) (obj))->klass)
+GType vips_interpolate_get_type(void);
+void vips_interpolate(VipsInterpolate *interpolate, void *out, VipsRegion *in, double x, double y);
+VipsInterpolateMethod vips_interpolate_get_method(VipsInterpolate *interpolate);
+int vips_interpolate_get_window_size(VipsInterpolate *interpolate);
+int vips_interpolate_get_window_offset(VipsInterpolate *interpolate);
+VipsInterpolate *vips_interpolate_new(const char *nickname);
+VipsInterpolate *vips_interpolate_nearest_static(void);
+VipsInterpolate *vips_interpolate_bilinear_static(void);
+void vips__interpolate_init(void);
+typedef struct {
+	VipsRect iarea;
+	VipsRect oarea;
+	double a, b, c, d;
+	double idx, idy;
+	double odx, ody;
+	double ia, ib, ic, id;
+} VipsTransformation;
+void vips__transform_init(VipsTransformation *trn);
+int vips__transform_calc_inverse(VipsTransformation *trn);
+int vips__transform_isidentity(const VipsTransformation *trn);
+int vips__transform_add(const VipsTransformation *in1, const VipsTransformation *in2, VipsTransformation *out);
+void vips__transform_print(const VipsTransformation *trn);
+void vips__transform_forward_point(const VipsTransformation *trn, const double x, const double y, double *ox, double *oy);
+void vips__transform_invert_point(const VipsTransformation *trn, const double x, const double y, double *ox, double *oy);
+void vips__transform_forward_rect(const VipsTransformation *trn, const VipsRect *in, VipsRect *out);
+void vips__transform_invert_rect(const VipsTransformation *trn, const VipsRect *in, VipsRect *out);
+void vips__transform_set_area(VipsTransformation *);
+#define VIPS_ROUND_INT(R) ((int) ((R) > 0 ? ((R) + 0.5) : ((R) -0.5)))
+#define VIPS_AREA(X) ((VipsArea *) (X))
+void vips_rect_marginadjust(VipsRect *r, int n);
+void vips_rect_intersectrect(const VipsRect *r1, const VipsRect *r2, VipsRect *out);
+gboolean vips_rect_isempty(const VipsRect *r);
+void vips_region_paint_pel(VipsRegion *reg, const VipsRect *r, const VipsPel *ink);
+VipsPel *vips__vector_to_ink(const char *domain, VipsImage *im, double *real, double *imag, int n);
+void *g_object_ref(void *p);
+void vips_object_set_static(VipsObject *object, gboolean static_object);
+#define DBL_MIN_SHIM 2.2250738585072014e-308
 
 /* shim: the sink.  Evaluate a lazy image into packed memory with the tile
  * geometry vips_get_tile_size() would pick from its demand hint

@@ -11,7 +11,7 @@
 int
 vips_convf(VipsImage *in, VipsImage **out, VipsImage *mask, ...)
 {
-	VipsConvf *convf = (VipsConvf *) calloc(1, sizeof(VipsConvf));
+	VipsConvf *convf = (VipsConvf *) vips__shim_object_new(vips_convf_get_type());
 	VipsConvolution *convolution = (VipsConvolution *) convf;
 
 	convolution->in = in;
@@ -19,7 +19,6 @@ vips_convf(VipsImage *in, VipsImage **out, VipsImage *mask, ...)
 	/* vips_convolution_build, convolution.c:99-102 */
 	if (vips_check_matrix("convf", mask, &convolution->M))
 		return -1;
-	vips_convf_init(convf);
 	if (vips_convf_build((VipsObject *) convf))
 		return -1;
 	*out = convolution->out;

@@ -11,14 +11,13 @@
 int
 vips_convi(VipsImage *in, VipsImage **out, VipsImage *mask, ...)
 {
-	VipsConvi *convi = (VipsConvi *) calloc(1, sizeof(VipsConvi));
+	VipsConvi *convi = (VipsConvi *) vips__shim_object_new(vips_convi_get_type());
 	VipsConvolution *convolution = (VipsConvolution *) convi;
 
 	convolution->in = in;
 	convolution->mask = mask;
 	if (vips_check_matrix("convi", mask, &convolution->M))
 		return -1;
-	vips_convi_init(convi);
 	if (vips_convi_build((VipsObject *) convi))
 		return -1;
 	*out = convolution->out;

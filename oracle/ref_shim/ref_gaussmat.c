@@ -10,7 +10,7 @@ int
 vips_gaussmat(VipsImage **out, double sigma, double min_ampl, ...)
 {
 	static const char *set_precision[] = { "precision", NULL };
-	VipsGaussmat *g = (VipsGaussmat *) calloc(1, sizeof(VipsGaussmat));
+	VipsGaussmat *g = (VipsGaussmat *) vips__shim_object_new(vips_gaussmat_get_type());
 	VipsCreate *create = (VipsCreate *) g;
 	va_list ap;
 	const char *name;

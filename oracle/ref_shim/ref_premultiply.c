@@ -9,7 +9,7 @@ int
 vips_premultiply(VipsImage *in, VipsImage **out, ...)
 {
 	static const char *set_max_alpha[] = { "max_alpha", NULL };
-	VipsPremultiply *pre = (VipsPremultiply *) calloc(1, sizeof(VipsPremultiply));
+	VipsPremultiply *pre = (VipsPremultiply *) vips__shim_object_new(vips_premultiply_get_type());
 	VipsConversion *conversion = (VipsConversion *) pre;
 	va_list ap;
 	const char *name;

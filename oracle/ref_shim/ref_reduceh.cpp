@@ -9,7 +9,7 @@
 extern "C" int
 vips_reduceh(VipsImage *in, VipsImage **out, double hshrink, ...)
 {
-	VipsReduceh *reduceh = (VipsReduceh *) calloc(1, sizeof(VipsReduceh));
+	VipsReduceh *reduceh = (VipsReduceh *) vips__shim_object_new(vips_reduceh_get_type());
 	VipsResample *resample = (VipsResample *) reduceh;
 	va_list ap;
 	const char *name;

@@ -13,7 +13,7 @@
 extern "C" int
 vips_reducev(VipsImage *in, VipsImage **out, double vshrink, ...)
 {
-	VipsReducev *reducev = (VipsReducev *) calloc(1, sizeof(VipsReducev));
+	VipsReducev *reducev = (VipsReducev *) vips__shim_object_new(vips_reducev_get_type());
 	VipsResample *resample = (VipsResample *) reducev;
 	va_list ap;
 	const char *name;

@@ -17,7 +17,7 @@ int
 vips_resize(VipsImage *in, VipsImage **out, double scale, ...)
 {
 	static const char *set_vscale[] = { "vscale", NULL };
-	VipsResize *resize = (VipsResize *) calloc(1, sizeof(VipsResize));
+	VipsResize *resize = (VipsResize *) vips__shim_object_new(vips_resize_get_type());
 	VipsResample *resample = (VipsResample *) resize;
 	va_list ap;
 	const char *name;

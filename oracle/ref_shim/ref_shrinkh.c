@@ -8,7 +8,7 @@
 int
 vips_shrinkh(VipsImage *in, VipsImage **out, int hshrink, ...)
 {
-	VipsShrinkh *shrink = (VipsShrinkh *) calloc(1, sizeof(VipsShrinkh));
+	VipsShrinkh *shrink = (VipsShrinkh *) vips__shim_object_new(vips_shrinkh_get_type());
 	VipsResample *resample = (VipsResample *) shrink;
 	va_list ap;
 	const char *name;

@@ -8,7 +8,7 @@
 int
 vips_shrinkv(VipsImage *in, VipsImage **out, int vshrink, ...)
 {
-	VipsShrinkv *shrink = (VipsShrinkv *) calloc(1, sizeof(VipsShrinkv));
+	VipsShrinkv *shrink = (VipsShrinkv *) vips__shim_object_new(vips_shrinkv_get_type());
 	VipsResample *resample = (VipsResample *) shrink;
 	va_list ap;
 	const char *name;

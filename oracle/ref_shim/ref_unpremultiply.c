@@ -9,7 +9,7 @@ int
 vips_unpremultiply(VipsImage *in, VipsImage **out, ...)
 {
 	static const char *set_max_alpha[] = { "max_alpha", NULL };
-	VipsUnpremultiply *unpre = (VipsUnpremultiply *) calloc(1, sizeof(VipsUnpremultiply));
+	VipsUnpremultiply *unpre = (VipsUnpremultiply *) vips__shim_object_new(vips_unpremultiply_get_type());
 	VipsConversion *conversion = (VipsConversion *) unpre;
 	va_list ap;
 	const char *name;

@@ -15,8 +15,137 @@
 #include <stdarg.h>
 #include <vips/vips.h>
 
+/* --------------------------------------------------------------- type system */
+
+typedef struct _ShimType {
+	struct _ShimType *parent;
+	size_t class_size, instance_size;
+	void (*instance_init)(void *);
+	/* the class struct follows */
+} ShimType;
+
+#define SHIM_CLASS(T) ((void *) ((ShimType *) (T) + 1))
+#define SHIM_TYPE_OF_CLASS(K) ((ShimType *) (K) -1)
+
+GType vips__shim_type_register(GType parent, size_t class_size, size_t instance_size, void (*class_init)(void *),
+	void (*instance_init)(void *), gpointer *parent_class_out)
+{
+	ShimType *pt = parent ? SHIM_TYPE_OF_CLASS((void *) parent) : NULL;
+	ShimType *t;
+	if (pt && class_size < pt->class_size)
+		class_size = pt->class_size;
+	if (pt && instance_size < pt->instance_size)
+		instance_size = pt->instance_size;
+	t = (ShimType *) calloc(1, sizeof(ShimType) + class_size + 64);
+	t->parent = pt;
+	t->class_size = class_size;
+	t->instance_size = instance_size;
+	t->instance_init = instance_init;
+	if (pt)
+		memcpy(SHIM_CLASS(t), SHIM_CLASS(pt), pt->class_size);
+	if (parent_class_out)
+		*parent_class_out = pt ? SHIM_CLASS(pt) : NULL;
+	if (class_init)
+		class_init(SHIM_CLASS(t));
+	return (GType) SHIM_CLASS(t);
+}
+
+static void shim_init_chain(ShimType *t, void *obj)
+{
+	if (!t)
+		return;
+	shim_init_chain(t->parent, obj);
+	if (t->instance_init)
+		t->instance_init(obj);
+}
+
+void *vips__shim_object_new(GType type)
+{
+	ShimType *t = SHIM_TYPE_OF_CLASS((void *) type);
+	GObject *obj = (GObject *) calloc(1, t->instance_size + 64);
+	obj->kind = 3;
+	obj->klass = (void *) type;
+	shim_init_chain(t, obj);
+	return obj;
+}
+
 static int shim_build_ok(VipsObject *object) { return 0; }
-VipsOperationClass vips__shim_parent_class = { { { 0, 0, 0, 0 }, shim_build_ok, "shim", "shim" }, VIPS_OPERATION_NONE };
+static void shim_operation_class_init(void *klass)
+{
+	VipsObjectClass *oc = (VipsObjectClass *) klass;
+	oc->build = shim_build_ok;
+	oc->nickname = "operation";
+	oc->description = "shim root";
+}
+
+GType vips__shim_operation_get_type(void)
+{
+	static GType type = 0;
+	if (!type)
+		type = vips__shim_type_register(0, sizeof(VipsOperationClass) + 256, sizeof(VipsOperation), shim_operation_class_init, NULL, NULL);
+	return type;
+}
+
+/* parent classes whose own source files are not compiled: plain children of the root */
+#define SHIM_PLAIN_TYPE(fn) \
+	GType fn(void) \
+	{ \
+		static GType type = 0; \
+		if (!type) \
+			type = vips__shim_type_register(vips__shim_operation_get_type(), sizeof(VipsOperationClass) + 256, \
+				sizeof(VipsOperation) + 64, NULL, NULL, NULL); \
+		return type; \
+	}
+SHIM_PLAIN_TYPE(vips_resample_get_type)
+SHIM_PLAIN_TYPE(vips_conversion_get_type)
+SHIM_PLAIN_TYPE(vips_convolution_get_type)
+SHIM_PLAIN_TYPE(vips_create_get_type)
+
+void *g_object_ref(void *p) { return p; }
+void vips_object_set_static(VipsObject *object, gboolean static_object) {}
+
+/* ------------------------------------------------------------------- rects */
+
+void vips_rect_marginadjust(VipsRect *r, int n)
+{
+	r->left -= n;
+	r->top -= n;
+	r->width += 2 * n;
+	r->height += 2 * n;
+}
+
+void vips_rect_intersectrect(const VipsRect *r1, const VipsRect *r2, VipsRect *out)
+{
+	int left = VIPS_MAX(r1->left, r2->left);
+	int top = VIPS_MAX(r1->top, r2->top);
+	int right = VIPS_MIN(VIPS_RECT_RIGHT(r1), VIPS_RECT_RIGHT(r2));
+	int bottom = VIPS_MIN(VIPS_RECT_BOTTOM(r1), VIPS_RECT_BOTTOM(r2));
+	int width = VIPS_MAX(0, right - left);
+	int height = VIPS_MAX(0, bottom - top);
+	out->left = left;
+	out->top = top;
+	out->width = width;
+	out->height = height;
+}
+
+gboolean vips_rect_isempty(const VipsRect *r) { return r->width <= 0 || r->height <= 0; }
+
+void vips_region_paint_pel(VipsRegion *reg, const VipsRect *r, const VipsPel *ink)
+{
+	const size_t ps = VIPS_IMAGE_SIZEOF_PEL(reg->im);
+	int x, y;
+	for (y = 0; y < r->height; y++)
+		for (x = 0; x < r->width; x++)
+			memcpy(VIPS_REGION_ADDR(reg, r->left + x, r->top + y), ink, ps);
+}
+
+VipsPel *vips__vector_to_ink(const char *domain, VipsImage *im, double *real, double *imag, int n)
+{
+	/* background 0 only */
+	return (VipsPel *) calloc(1, VIPS_IMAGE_SIZEOF_PEL(im) + 16);
+}
+
+int vips_check_vector_length(const char *domain, int n, int len) { return n == len ? 0 : -1; }
 
 int vips__tile_width = 128, vips__tile_height = 128, vips__fatstrip_height = 16, vips__thinstrip_height = 1;
 
