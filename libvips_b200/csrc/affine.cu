@@ -1,0 +1,334 @@
+/* affine.cu -- the upsizing half of vips_resize: a scale-only vips_affine with the
+ * nearest / bilinear / bicubic interpolators.
+ *
+ * reference:
+ *   resample/resize.c:116-132,233-307   interpolator per kernel, idx/idy = 0.5 * (1 - 1 / scale), the affine calls
+ *   resample/affine.c:412-605           transform, oarea = ROUND_INT(forward rect), embed by window + 1, idx -= 1
+ *   resample/affine.c:227-410           vips_affine_gen: ix advanced by repeated addition of ddx along each rect row
+ *   resample/transform.c:48-70          inverse: tmp = 1 / det; ia = tmp * d; id = tmp * a
+ *   resample/interpolate.c:334-349      nearest;  :433-482 bilinear (12-bit fixed point for 8/16-bit ints, double else)
+ *   resample/bicubic.cpp:106-405,487-645, templates.h:150-305   bicubic (fixed point for 8-bit, double tables else)
+ *
+ * A scale-only affine (b = c = 0) separates: the column coordinate depends only
+ * on x (and on the rect it starts in: FATSTRIP rects are full width, so it is
+ * one sequence per row starting at x = 0) and the row coordinate only on y.
+ * The host builds both sequences with the reference's own double additions and
+ * uploads them; one thread interpolates one output pixel.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "vb200_internal.h"
+
+namespace vb200 {
+
+namespace {
+
+enum { INTERP_NEAREST = 0, INTERP_BILINEAR = 1, INTERP_BICUBIC = 2 };
+
+struct AffineDev {
+	const double *ixs; /* [OW] column coordinate in the embedded image */
+	const double *iys; /* [OH] */
+	const double *cf;  /* [65][4] bicubic, double */
+	const int *ci;	   /* [65][4] bicubic, 12-bit fixed point */
+	int w, h, bands, pad; /* source; pad = window_offset + 1 */
+	int OW, OH;
+	size_t in_bpl, out_bpl;
+	int ile, iri, ito, ibo; /* clip against iarea, affine.c:318-323 */
+	int interp;
+};
+
+template <typename T> struct Kind;
+template <> struct Kind<uint8_t> { static constexpr int k = 0; static constexpr double lo = 0, hi = 255; };
+template <> struct Kind<int8_t> { static constexpr int k = 1; static constexpr double lo = -128, hi = 127; };
+template <> struct Kind<uint16_t> { static constexpr int k = 2; static constexpr double lo = 0, hi = 65535; };
+template <> struct Kind<int16_t> { static constexpr int k = 2; static constexpr double lo = -32768, hi = 32767; };
+template <> struct Kind<uint32_t> { static constexpr int k = 3; static constexpr double lo = 0, hi = 2147483647.0; };
+template <> struct Kind<int32_t> { static constexpr int k = 3; static constexpr double lo = -2147483648.0, hi = 2147483647.0; };
+template <> struct Kind<float> { static constexpr int k = 4; static constexpr double lo = 0, hi = 0; };
+
+__device__ __forceinline__ int
+ufr(int v)
+{
+	return (v + (VB200_INTERPOLATE_SCALE >> 1)) >> VB200_INTERPOLATE_SHIFT;
+}
+
+__device__ __forceinline__ int
+sfr(int v)
+{
+	const int round_by = v >= 0 ? (VB200_INTERPOLATE_SCALE >> 1) : -(VB200_INTERPOLATE_SCALE >> 1);
+	return (v + round_by) >> VB200_INTERPOLATE_SHIFT;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_scale_kernel(const __grid_constant__ AffineDev P, const T *__restrict__ in, T *__restrict__ out)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= P.OW)
+		return;
+	const double ix = P.ixs[x];
+	const double iy = P.iys[y];
+	T *q = (T *) ((char *) out + (size_t) y * P.out_bpl) + (size_t) x * P.bands;
+	const int fx = (int) floor(ix);
+	const int fy = (int) floor(iy);
+	if (!(fx >= P.ile && fx <= P.iri && fy >= P.ito && fy <= P.ibo)) {
+		for (int z = 0; z < P.bands; z++)
+			q[z] = (T) 0;
+		return;
+	}
+
+	auto at = [&](int X, int Y, int z) -> T {
+		const int sx = max(0, min(X - P.pad, P.w - 1));
+		const int sy = max(0, min(Y - P.pad, P.h - 1));
+		return ((const T *) ((const char *) in + (size_t) sy * P.in_bpl))[(size_t) sx * P.bands + z];
+	};
+
+	const int xi = (int) ix, yi = (int) iy;
+	if (P.interp == INTERP_NEAREST) {
+		for (int z = 0; z < P.bands; z++)
+			q[z] = at(xi, yi, z);
+		return;
+	}
+	if (P.interp == INTERP_BILINEAR) {
+		if constexpr (Kind<T>::k <= 2) {
+			/* BILINEAR_INT */
+			const int X = (int) __dmul_rn(__dsub_rn(ix, (double) xi), (double) VB200_INTERPOLATE_SCALE);
+			const int Y = (int) __dmul_rn(__dsub_rn(iy, (double) yi), (double) VB200_INTERPOLATE_SCALE);
+			const int Yd = VB200_INTERPOLATE_SCALE - Y;
+			const int c4 = (Y * X) >> VB200_INTERPOLATE_SHIFT;
+			const int c2 = (Yd * X) >> VB200_INTERPOLATE_SHIFT;
+			const int c3 = Y - c4;
+			const int c1 = Yd - c2;
+			for (int z = 0; z < P.bands; z++)
+				q[z] = (T) ((c1 * (int) at(xi, yi, z) + c2 * (int) at(xi + 1, yi, z) + c3 * (int) at(xi, yi + 1, z) +
+								c4 * (int) at(xi + 1, yi + 1, z) + (1 << VB200_INTERPOLATE_SHIFT) / 2) >>
+					VB200_INTERPOLATE_SHIFT);
+		}
+		else {
+			/* BILINEAR_FLOAT: coefficients and sum in double, evaluation order as written */
+			const double X = __dsub_rn(ix, (double) xi);
+			const double Y = __dsub_rn(iy, (double) yi);
+			const double Yd = __dsub_rn(1.0, Y);
+			const double c4 = __dmul_rn(Y, X);
+			const double c2 = __dmul_rn(Yd, X);
+			const double c3 = __dsub_rn(Y, c4);
+			const double c1 = __dsub_rn(Yd, c2);
+			for (int z = 0; z < P.bands; z++) {
+				double v = __dmul_rn(c1, (double) at(xi, yi, z));
+				v = __dadd_rn(v, __dmul_rn(c2, (double) at(xi + 1, yi, z)));
+				v = __dadd_rn(v, __dmul_rn(c3, (double) at(xi, yi + 1, z)));
+				v = __dadd_rn(v, __dmul_rn(c4, (double) at(xi + 1, yi + 1, z)));
+				q[z] = (T) v;
+			}
+		}
+		return;
+	}
+
+	/* bicubic */
+	const int sx = (int) __dmul_rn(__dmul_rn(ix, (double) VB200_TRANSFORM_SCALE), 2.0);
+	const int sy = (int) __dmul_rn(__dmul_rn(iy, (double) VB200_TRANSFORM_SCALE), 2.0);
+	const int tx = ((sx & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+	const int ty = ((sy & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+	for (int z = 0; z < P.bands; z++) {
+		if constexpr (Kind<T>::k <= 1) {
+			const int *cx = P.ci + tx * 4, *cy = P.ci + ty * 4;
+			int r[4];
+			for (int j = 0; j < 4; j++) {
+				const int sum = cx[0] * (int) at(xi - 1, yi - 1 + j, z) + cx[1] * (int) at(xi, yi - 1 + j, z) +
+					cx[2] * (int) at(xi + 1, yi - 1 + j, z) + cx[3] * (int) at(xi + 2, yi - 1 + j, z);
+				r[j] = Kind<T>::k == 0 ? ufr(sum) : sfr(sum);
+			}
+			const int sum = cy[0] * r[0] + cy[1] * r[1] + cy[2] * r[2] + cy[3] * r[3];
+			int v = Kind<T>::k == 0 ? ufr(sum) : sfr(sum);
+			v = max((int) Kind<T>::lo, min(v, (int) Kind<T>::hi));
+			q[z] = (T) v;
+		}
+		else {
+			const double *cx = P.cf + tx * 4, *cy = P.cf + ty * 4;
+			double r[4];
+			for (int j = 0; j < 4; j++) {
+				double v = __dmul_rn(cx[0], (double) at(xi - 1, yi - 1 + j, z));
+				v = __dadd_rn(v, __dmul_rn(cx[1], (double) at(xi, yi - 1 + j, z)));
+				v = __dadd_rn(v, __dmul_rn(cx[2], (double) at(xi + 1, yi - 1 + j, z)));
+				v = __dadd_rn(v, __dmul_rn(cx[3], (double) at(xi + 2, yi - 1 + j, z)));
+				/* bicubic_float<float>: every cubic_float<T> returns T */
+				r[j] = Kind<T>::k == 4 ? (double) (float) v : v;
+			}
+			double v = __dmul_rn(cy[0], r[0]);
+			v = __dadd_rn(v, __dmul_rn(cy[1], r[1]));
+			v = __dadd_rn(v, __dmul_rn(cy[2], r[2]));
+			v = __dadd_rn(v, __dmul_rn(cy[3], r[3]));
+			if constexpr (Kind<T>::k == 4)
+				q[z] = (T) (float) v;
+			else {
+				/* VIPS_CLIP in double, then the C conversion */
+				const double m = Kind<T>::hi < v ? Kind<T>::hi : v;
+				v = Kind<T>::lo > m ? Kind<T>::lo : m;
+				q[z] = (T) v;
+			}
+		}
+	}
+}
+
+#define VB200_ROUND_INT(R) ((int) ((R) > 0 ? ((R) + 0.5) : ((R) -0.5)))
+
+} // namespace
+
+/* vips_affine(in, a, 0, 0, d, interpolate, idx, idy, extend COPY, premultiplied TRUE) */
+int
+dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a, double d, int interp, double idx,
+	double idy, cudaStream_t s)
+{
+	if (!format_is_supported(in.fmt)) {
+		error(domain, "band format %d not supported on the device path", in.fmt);
+		return -1;
+	}
+	/* vips__transform_calc_inverse */
+	const double det = a * d;
+	if (fabs(det) < 2.0 * 2.2250738585072014e-308) {
+		error(domain, "singular or near-singular matrix");
+		return -1;
+	}
+	const double tmp = 1.0 / det;
+	const double ia = tmp * d, id = tmp * a;
+	/* vips__transform_set_area: forward rect of (0, 0, w, h) with idx = idy = 0 */
+	const double xs[2] = {a * 0.0 + 0.0 * 0.0 + 0.0, a * in.w + 0.0 * 0.0 + 0.0};
+	const double ys[2] = {0.0 * 0.0 + d * 0.0 + 0.0, 0.0 * 0.0 + d * in.h + 0.0};
+	const double left = std::min(xs[0], xs[1]), right = std::max(xs[0], xs[1]);
+	const double top = std::min(ys[0], ys[1]), bottom = std::max(ys[0], ys[1]);
+	const int ol = VB200_ROUND_INT(left), ot = VB200_ROUND_INT(top);
+	const int OW = VB200_ROUND_INT(right - left), OH = VB200_ROUND_INT(bottom - top);
+	if (OW <= 0 || OH <= 0) {
+		error(domain, "image has shrunk to nothing");
+		return -1;
+	}
+	const int window_size = interp == INTERP_BICUBIC ? 4 : (interp == INTERP_BILINEAR ? 2 : 1);
+	const int window_offset = std::max(0, window_size / 2 - 1);
+	const double tidx = idx - 1, tidy = idy - 1; /* the embed's one-pixel border, affine.c:533-534 */
+
+	/* the coordinate sequences of vips_affine_gen (affine.c:325-400), ib = ic = 0, odx = ody = 0 */
+	std::vector<double> host((size_t) OW + OH + 65 * 4);
+	{
+		const double ox = 0 + ol - 0.0;
+		double ix = ia * ox + 0.0 * (0 + ot - 0.0);
+		ix -= tidx;
+		ix += window_offset;
+		for (int x = 0; x < OW; x++) {
+			host[x] = ix;
+			ix += ia; /* ddx */
+		}
+		for (int y = 0; y < OH; y++) {
+			const double oy = y + ot - 0.0;
+			double iy = 0.0 * ox + id * oy;
+			iy -= tidy;
+			iy += window_offset;
+			host[OW + y] = iy;
+		}
+	}
+	/* bicubic tables: calculate_coefficients_catmull (templates.h:281-305), bicubic.cpp:636-644 */
+	std::vector<int> ci(65 * 4);
+	for (int t = 0; t <= VB200_TRANSFORM_SCALE; t++) {
+		const double x = (float) t / VB200_TRANSFORM_SCALE;
+		const double cr1 = 1. - x;
+		const double cr2 = -.5 * x;
+		const double cr3 = cr1 * cr2;
+		const double cone = cr1 * cr3;
+		const double cfou = x * cr3;
+		const double cr4 = cfou - cone;
+		const double ctwo = cr1 - cone + cr4;
+		const double cthr = x - cfou - cr4;
+		double *c = &host[(size_t) OW + OH + t * 4];
+		c[0] = cone;
+		c[1] = ctwo;
+		c[2] = cthr;
+		c[3] = cfou;
+		for (int i = 0; i < 4; i++)
+			ci[t * 4 + i] = c[i] * VB200_INTERPOLATE_SCALE;
+	}
+
+	void *block = nullptr;
+	const size_t nd = host.size() * sizeof(double), ni = ci.size() * sizeof(int);
+	if (dev_alloc(domain, &block, nd + ni, s))
+		return -1;
+	VB200_CUDA(domain, cudaMemcpyAsync(block, host.data(), nd, cudaMemcpyHostToDevice, s));
+	VB200_CUDA(domain, cudaMemcpyAsync((char *) block + nd, ci.data(), ni, cudaMemcpyHostToDevice, s));
+
+	if (dev_image_new(domain, out, OW, OH, in.bands, in.fmt, in.type, s)) {
+		dev_free(block, s);
+		return -1;
+	}
+	AffineDev P;
+	P.ixs = (const double *) block;
+	P.iys = P.ixs + OW;
+	P.cf = P.iys + OH;
+	P.ci = (const int *) ((char *) block + nd);
+	P.w = in.w;
+	P.h = in.h;
+	P.bands = in.bands;
+	P.pad = window_offset + 1;
+	P.OW = OW;
+	P.OH = OH;
+	P.in_bpl = in.bpl;
+	P.out_bpl = out->bpl;
+	P.ile = 0 + window_offset;
+	P.ito = 0 + window_offset;
+	P.iri = P.ile + in.w;
+	P.ibo = P.ito + in.h;
+	P.interp = interp;
+	const dim3 grid((OW + 255) / 256, OH);
+#define AF(T) affine_scale_kernel<T><<<grid, 256, 0, s>>>(P, (const T *) in.data, (T *) out->data)
+	switch (in.fmt) {
+	case VB200_FORMAT_UCHAR: AF(uint8_t); break;
+	case VB200_FORMAT_CHAR: AF(int8_t); break;
+	case VB200_FORMAT_USHORT: AF(uint16_t); break;
+	case VB200_FORMAT_SHORT: AF(int16_t); break;
+	case VB200_FORMAT_UINT: AF(uint32_t); break;
+	case VB200_FORMAT_INT: AF(int32_t); break;
+	case VB200_FORMAT_FLOAT: AF(float); break;
+	}
+#undef AF
+	cudaError_t e = cudaGetLastError();
+	dev_free(block, s);
+	if (e != cudaSuccess)
+		return cuda_fail(domain, e, "affine kernel");
+	count_launch();
+	return 0;
+}
+
+/* the upsizing tail of vips_resize for a pure enlargement, resize.c:233-307 */
+int
+dev_resize_up(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,
+	cudaStream_t s)
+{
+	const int interp = kernel == VB200_KERNEL_NEAREST ? INTERP_NEAREST
+		: (kernel == VB200_KERNEL_LINEAR ? INTERP_BILINEAR : INTERP_BICUBIC);
+	if (kernel == VB200_KERNEL_NEAREST && hscale == floor(hscale) && vscale == floor(vscale)) {
+		/* the reference takes vips_zoom here (resize.c:263-271); pixel replication is
+		 * not the same code path as the nearest affine, and it is not restated yet
+		 */
+		error(domain, "integral nearest-neighbour enlargement (vips_zoom) is not on the device path");
+		return -1;
+	}
+	const double idx = kernel == VB200_KERNEL_NEAREST ? 0.0 : 0.5 * (1.0 - 1.0 / hscale);
+	const double idy = kernel == VB200_KERNEL_NEAREST ? 0.0 : 0.5 * (1.0 - 1.0 / vscale);
+	double a, d;
+	if (hscale > 1.0 && vscale > 1.0) {
+		a = hscale;
+		d = vscale;
+	}
+	else if (hscale > 1.0) {
+		a = hscale;
+		d = 1.0;
+	}
+	else {
+		a = 1.0;
+		d = vscale;
+	}
+	return dev_affine_scale(domain, in, out, a, d, interp, idx, idy, s);
+}
+
+} // namespace vb200

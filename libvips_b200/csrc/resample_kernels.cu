@@ -797,8 +797,14 @@ dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale,
 	hscale = std::max(hscale, 1.0 / in.w);
 	vscale = std::max(vscale, 1.0 / in.h);
 	if (hscale > 1.0 || vscale > 1.0) {
-		error(domain, "upsizing is not on the device path yet");
-		return -1;
+		if (hscale < 1.0 || vscale < 1.0) {
+			/* reduce on one axis feeding an affine on the other: the reduce pass would see
+			 * the rects the affine asks for, which the whole-image passes here do not model
+			 */
+			error(domain, "mixed up/down resize is not on the device path");
+			return -1;
+		}
+		return dev_resize_up(domain, in, out, hscale, vscale, kernel, s);
 	}
 	const double vs = vscale < 1.0 ? 1.0 / vscale : 1.0;
 	const double hs = hscale < 1.0 ? 1.0 / hscale : 1.0;

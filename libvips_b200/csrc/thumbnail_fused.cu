@@ -629,10 +629,13 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 
 	/* ---------------- consumers */
 	/* columns beyond the band shadow the last one */
-	unsigned my_col[CPT];
+	/* generic pointers into the ring: with the compile-time pitch the 2 * VS row
+	 * reads of a pair become LDS [reg + immediate]
+	 */
+	const unsigned char *my_col[CPT];
 #pragma unroll
 	for (int i = 0; i < CPT; i++)
-		my_col[i] = stages_s + (unsigned) (column_of(min(t * CPT + i, NE * P.HS - 1)) - c_lo) * 4u;
+		my_col[i] = stages + (size_t) (column_of(min(t * CPT + i, NE * P.HS - 1)) - c_lo) * 4u;
 	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
 	const bool lane0 = (t & 31) == 0;
 	const unsigned vmul8 = P.vmul8;
@@ -686,8 +689,8 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 				for (int i = 0; i < CPT; i++)
 #pragma unroll
 					for (int k = 0; k < VSR; k++) {
-						pa[i][k] = lds32(my_col[i] + soff + (unsigned) k * kStagePitch);
-						pb[i][k] = lds32(my_col[i] + soff + (unsigned) (VSR + k) * kStagePitch);
+						pa[i][k] = *(const unsigned *) (my_col[i] + soff + k * kStagePitch);
+						pb[i][k] = *(const unsigned *) (my_col[i] + soff + (VSR + k) * kStagePitch);
 					}
 				__syncwarp();
 				if (lane0)
@@ -704,8 +707,8 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 				for (int k = 0; k < vs; k++)
 #pragma unroll
 					for (int i = 0; i < CPT; i++) {
-						accumulate_pixel<PREMUL>(lds32(my_col[i] + soff + (unsigned) k * kStagePitch), rbA[i], gaA[i]);
-						accumulate_pixel<PREMUL>(lds32(my_col[i] + soff + (unsigned) (vs + k) * kStagePitch), rbB[i], gaB[i]);
+						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + k * kStagePitch), rbA[i], gaA[i]);
+						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + (vs + k) * kStagePitch), rbB[i], gaB[i]);
 					}
 				__syncwarp();
 				if (lane0)
@@ -869,6 +872,371 @@ thumbnail_fused_tma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	}
 }
 
+/* ======================================================================
+ * v3: v2 with the horizontal box done inside the warp and the reduceh pass on its
+ * own warp.  Two adjacent input columns per thread (CPT 2), HS in {2, 4, 8}: the
+ * HS columns of one box-shrunk pixel sit in HS / 2 adjacent lanes, so the box sum
+ * is a shuffle reduction and the column PAIR is one more shuffle; the lane that
+ * owns a pair stores it straight to sh[].  No rv[] round trip, no H1 stage and
+ * -- because sh[] is double buffered and handed over with mbarriers -- no
+ * block-wide barrier anywhere in the main loop:
+ *     warps 0 .. NT/32-1   V: premultiply, box, reducev, shrinkh    -> sh[buf]
+ *     warp  NT/32          H: reduceh, unpremultiply, store          <- sh[buf]
+ *     warp  NT/32 + 1      P: cp.async.bulk producer
+ * ====================================================================== */
+template <int VS, int NP, bool PREMUL, int HSQ>
+__global__ void __launch_bounds__(kMaxThreads / 2 + 64, 2)
+thumbnail_fused_tma3_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
+	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+
+	constexpr int K = kChunkRowsTma;
+	constexpr int CPT = 2;
+	constexpr int G = HSQ / CPT; /* lanes per box-shrunk column */
+	constexpr int HSHIFT = HSQ == 2 ? 1 : HSQ == 4 ? 2 : 3;
+	constexpr int NPR = NP > 0 ? NP : 1;
+	constexpr int VSR = VS > 0 ? VS : 1;
+	const int NT = P.NT;	   /* V threads */
+	const int NC = NT * CPT; /* columns: the stride of pairbuf */
+	const int t = threadIdx.x;
+	const int vs = VS > 0 ? VS : P.VS;
+	const int NPv = NP > 0 ? NP : P.NPv;
+	const int NPh = NP > 0 ? NP : P.NPh;
+	const int rows_per_stage = 2 * vs;
+	const unsigned stage_bytes = (unsigned) rows_per_stage * kStagePitch;
+	const int shs = P.NEmax / 2; /* pairs per sh row */
+
+	unsigned char *stages = smem_raw; /* [kStages][2 * vs][kStagePitch] */
+	uint64_t *bars = (uint64_t *) (smem_raw + kStages * stage_bytes); /* full[kStages] empty[kStages] shfull[2] shempty[2] */
+	uint2 *pairbuf = (uint2 *) (bars + 2 * kStages + 4);			  /* [slots][NC] */
+	uint2 *sh = pairbuf + (size_t) P.slots * NC;					  /* [2][K][shs] */
+	int *vcoef = (int *) (sh + (size_t) 2 * K * shs);
+	int *hcoef = vcoef + P.nvsets * P.NPv;
+	int *uscale = hcoef + P.nhsets * P.NPh; /* [256] unpremultiply LUT */
+
+	const unsigned stages_s = smem_addr(stages);
+	const unsigned full_s = smem_addr(bars);
+	const unsigned empty_s = full_s + 8u * kStages;
+	const unsigned shfull_s = empty_s + 8u * kStages;
+	const unsigned shempty_s = shfull_s + 16u;
+
+	if (t == 0) {
+		for (int i = 0; i < kStages; i++) {
+			mbar_init(full_s + 8u * i, 1);
+			mbar_init(empty_s + 8u * i, NT / 32);
+		}
+		for (int i = 0; i < 2; i++) {
+			mbar_init(shfull_s + 8u * i, NT / 32);
+			mbar_init(shempty_s + 8u * i, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int i = t; i < P.nvsets * P.NPv; i += blockDim.x)
+		vcoef[i] = P.vcoef[i];
+	for (int i = t; i < P.nhsets * P.NPh; i += blockDim.x)
+		hcoef[i] = P.hcoef[i];
+	if (PREMUL)
+		for (int i = t; i < 256; i += blockDim.x)
+			uscale[i] = i == 0 ? 0 : (int) __ddiv_rn(__dmul_rn(256.0, 255.0), (double) i);
+
+	const int xa = blockIdx.x * P.TW;
+	const int xb = min(xa + P.TW, P.OW);
+	const int y_begin = blockIdx.y * P.RPC;
+	const int y_end = min(y_begin + P.RPC, P.OH);
+	const int frame = frame0 + blockIdx.z;
+	const uint8_t *fin = in + (size_t) frame * in_frame_stride;
+	uint8_t *fout = out + (size_t) frame * out_frame_stride;
+
+	const int pair_h0 = __ldg(&P.hcol[xa]).x;
+	const int E0 = 2 * pair_h0 + P.hgrid;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh - pair_h0);
+	const int npairs = NE / 2;
+
+	auto column_of = [&](int tt) {
+		const int e = E0 + tt / HSQ;
+		const int k = tt - (tt / HSQ) * HSQ;
+		const int sc = max(0, min(e - P.hembed, P.Ws - 1));
+		return min(sc * HSQ + k, P.W - 1);
+	};
+	const int c_lo = column_of(0) & ~3;
+	const int c_hi = min(P.W, (column_of(NE * HSQ - 1) + 4) & ~3);
+	const unsigned row_bytes = (unsigned) (c_hi - c_lo) * 4u;
+
+	__syncthreads();
+
+	if (t >= NT + 32) {
+		/* ---------------- P: lane L copies row L of each stage */
+		const int lane = t - NT - 32;
+		const uint8_t *src0 = fin + (size_t) c_lo * 4;
+		const int j = lane / vs, k = lane - j * vs;
+		const bool copier = lane < rows_per_stage;
+		int s = 0;
+		unsigned phase = 0;
+		int pdone = INT_MIN;
+		for (int ya = y_begin; ya < y_end; ya += K) {
+			const int yb = min(ya + K, y_end);
+			const int P0 = __ldg(&P.vrow[ya]).x;
+			const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+			for (int p = max(pdone, P0); p <= P1; p++) {
+				mbar_wait(empty_s + 8u * s, phase ^ 1u);
+				if (lane == 0)
+					mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
+				__syncwarp();
+				if (copier) {
+					const int sr = max(0, min(2 * p + P.vgrid + j - P.vembed, P.Hs - 1));
+					const int row = min(sr * vs + k, P.H - 1);
+					bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * kStagePitch,
+						src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
+				}
+				if (++s == kStages) {
+					s = 0;
+					phase ^= 1u;
+				}
+			}
+			pdone = P1 + 1;
+		}
+		return;
+	}
+
+	if (t >= NT) {
+		/* ---------------- H: reduceh + unpremultiply + store, one warp */
+		const int lane = t - NT;
+		const int bw = xb - xa;
+		int chunk = 0;
+		for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
+			const int yb = min(ya + K, y_end);
+			const int rows = yb - ya;
+			const int buf = chunk & 1;
+			const uint2 *shb = sh + (size_t) buf * K * shs;
+			mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
+			for (int idx = lane; idx < rows * bw; idx += 32) {
+				const int k = fast_div(idx, bw);
+				const int x = xa + (idx - k * bw);
+				const int2 hc = __ldg(&P.hcol[x]);
+				const uint2 *win = shb + k * shs + (hc.x - pair_h0);
+				const int *cfp = hcoef + hc.y * NPh;
+				int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+				if (NP > 0) {
+#pragma unroll
+					for (int kk = 0; kk < NPR; kk++) {
+						const uint2 w = win[kk];
+						const unsigned c = (unsigned) cfp[kk];
+						r = dp2a_lo(c, w.x, r);
+						b = dp2a_hi(c, w.x, b);
+						g = dp2a_lo(c, w.y, g);
+						a = dp2a_hi(c, w.y, a);
+					}
+				}
+				else
+					for (int kk = 0; kk < NPh; kk++) {
+						const uint2 w = win[kk];
+						const unsigned c = (unsigned) cfp[kk];
+						r = dp2a_lo(c, w.x, r);
+						b = dp2a_hi(c, w.x, b);
+						g = dp2a_lo(c, w.y, g);
+						a = dp2a_hi(c, w.y, a);
+					}
+				r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+				g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+				b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+				a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+				if (PREMUL) {
+					const int sc = uscale[a];
+					r = ((r * sc + 128) >> 8) & 0xff;
+					g = ((g * sc + 128) >> 8) & 0xff;
+					b = ((b * sc + 128) >> 8) & 0xff;
+				}
+				*(unsigned *) (fout + (size_t) (ya + k) * P.out_bpl + (size_t) x * 4) =
+					(unsigned) r | ((unsigned) g << 8) | ((unsigned) b << 16) | ((unsigned) a << 24);
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(shempty_s + 8u * buf);
+		}
+		return;
+	}
+
+	/* ---------------- V warps */
+	const unsigned char *my_col[CPT];
+#pragma unroll
+	for (int i = 0; i < CPT; i++)
+		my_col[i] = stages + (size_t) (column_of(min(t * CPT + i, NE * HSQ - 1)) - c_lo) * 4u;
+	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
+	const unsigned hamend2 = (unsigned) (HSQ / 2) * 0x00010001u;
+	const bool lane0 = (t & 31) == 0;
+	const unsigned vmul8 = P.vmul8;
+	const int vshift = VS == 1 ? 0 : VS == 2 ? 1 : VS == 4 ? 2 : VS == 8 ? 3 : P.vshift;
+	const int tc = t * CPT;
+	/* this thread's column pair: lanes [2G m, 2G m + 2G) hold pair m; its first lane stores it */
+	const int my_pair = t / (2 * G);
+	const bool pair_writer = (t & (2 * G - 1)) == 0 && my_pair < npairs;
+	const bool is_B = (t & G) != 0; /* second column of the pair */
+
+	int s = 0;
+	unsigned phase = 0;
+	int pdone = INT_MIN;
+	int P0_prev = 0;
+	int cset = -1;
+	unsigned cf[NPR];
+	int chunk = 0;
+
+	for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
+		const int yb = min(ya + K, y_end);
+		const int P0 = __ldg(&P.vrow[ya]).x;
+		const int P1 = __ldg(&P.vrow[yb - 1]).x + P.NPv - 1;
+
+		int pfirst = P0;
+		if (pdone > P0) {
+			const int shift = P0 - P0_prev;
+			if (shift > 0) {
+				const int cnt = pdone - P0;
+				uint2 *dstp = pairbuf + tc;
+				const uint2 *srcp = pairbuf + shift * NC + tc;
+#pragma unroll 4
+				for (int i = 0; i < cnt; i++)
+					*(uint4 *) (dstp + i * NC) = *(const uint4 *) (srcp + i * NC);
+			}
+			pfirst = pdone;
+		}
+
+		uint2 *pdst = pairbuf + (pfirst - P0) * NC + tc;
+		for (int p = pfirst; p <= P1; p++, pdst += NC) {
+			const unsigned soff = (unsigned) s * stage_bytes;
+			unsigned rbA[CPT], gaA[CPT], rbB[CPT], gaB[CPT];
+#pragma unroll
+			for (int i = 0; i < CPT; i++)
+				rbA[i] = gaA[i] = rbB[i] = gaB[i] = amend2;
+			mbar_wait(full_s + 8u * s, phase);
+			if (VS > 0) {
+				unsigned pa[CPT][VSR], pb[CPT][VSR];
+#pragma unroll
+				for (int i = 0; i < CPT; i++)
+#pragma unroll
+					for (int k = 0; k < VSR; k++) {
+						pa[i][k] = *(const unsigned *) (my_col[i] + soff + k * kStagePitch);
+						pb[i][k] = *(const unsigned *) (my_col[i] + soff + (VSR + k) * kStagePitch);
+					}
+				__syncwarp();
+				if (lane0)
+					mbar_arrive(empty_s + 8u * s);
+#pragma unroll
+				for (int i = 0; i < CPT; i++)
+#pragma unroll
+					for (int k = 0; k < VSR; k++) {
+						accumulate_pixel<PREMUL>(pa[i][k], rbA[i], gaA[i]);
+						accumulate_pixel<PREMUL>(pb[i][k], rbB[i], gaB[i]);
+					}
+			}
+			else {
+				for (int k = 0; k < vs; k++)
+#pragma unroll
+					for (int i = 0; i < CPT; i++) {
+						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + k * kStagePitch), rbA[i], gaA[i]);
+						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + (vs + k) * kStagePitch), rbB[i], gaB[i]);
+					}
+				__syncwarp();
+				if (lane0)
+					mbar_arrive(empty_s + 8u * s);
+			}
+			if (++s == kStages) {
+				s = 0;
+				phase ^= 1u;
+			}
+			*(uint4 *) pdst = make_uint4(average_pair(rbA[0], rbB[0], vmul8, vshift), average_pair(gaA[0], gaB[0], vmul8, vshift),
+				average_pair(rbA[1], rbB[1], vmul8, vshift), average_pair(gaA[1], gaB[1], vmul8, vshift));
+		}
+
+		/* reducev + in-warp shrinkh; rows go to sh[buf] once the H warp has released it */
+		const int buf = chunk & 1;
+		uint2 *shb = sh + (size_t) buf * K * shs + my_pair;
+		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
+		for (int y = ya; y < yb; y++, shb += shs) {
+			const int2 vr = __ldg(&P.vrow[y]);
+			const uint2 *win = pairbuf + (vr.x - P0) * NC + tc;
+			int acc[CPT][4];
+#pragma unroll
+			for (int i = 0; i < CPT; i++)
+				acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = VB200_INTERPOLATE_SCALE >> 1;
+			if (NP > 0) {
+				if (vr.y != cset) {
+					cset = vr.y;
+#pragma unroll
+					for (int k = 0; k < NPR; k++)
+						cf[k] = (unsigned) vcoef[cset * NPR + k];
+				}
+#pragma unroll
+				for (int k = 0; k < NPR; k++) {
+					const uint4 q = *(const uint4 *) (win + k * NC);
+					acc[0][0] = dp2a_lo(cf[k], q.x, acc[0][0]);
+					acc[0][2] = dp2a_hi(cf[k], q.x, acc[0][2]);
+					acc[0][1] = dp2a_lo(cf[k], q.y, acc[0][1]);
+					acc[0][3] = dp2a_hi(cf[k], q.y, acc[0][3]);
+					acc[1][0] = dp2a_lo(cf[k], q.z, acc[1][0]);
+					acc[1][2] = dp2a_hi(cf[k], q.z, acc[1][2]);
+					acc[1][1] = dp2a_lo(cf[k], q.w, acc[1][1]);
+					acc[1][3] = dp2a_hi(cf[k], q.w, acc[1][3]);
+				}
+			}
+			else {
+				const int *cfp = vcoef + vr.y * NPv;
+				for (int k = 0; k < NPv; k++) {
+					const unsigned c = (unsigned) cfp[k];
+					const uint4 q = *(const uint4 *) (win + k * NC);
+					acc[0][0] = dp2a_lo(c, q.x, acc[0][0]);
+					acc[0][2] = dp2a_hi(c, q.x, acc[0][2]);
+					acc[0][1] = dp2a_lo(c, q.y, acc[0][1]);
+					acc[0][3] = dp2a_hi(c, q.y, acc[0][3]);
+					acc[1][0] = dp2a_lo(c, q.z, acc[1][0]);
+					acc[1][2] = dp2a_hi(c, q.z, acc[1][2]);
+					acc[1][1] = dp2a_lo(c, q.w, acc[1][1]);
+					acc[1][3] = dp2a_hi(c, q.w, acc[1][3]);
+				}
+			}
+			/* reducev results (clipped bytes) straight into the box-sum lanes:
+			 * rb = r | b << 16, ga = g | a << 16, this thread's two columns added
+			 */
+			unsigned rb = hamend2, ga = hamend2;
+#pragma unroll
+			for (int i = 0; i < CPT; i++) {
+				const int r = max(0, min(acc[i][0] >> VB200_INTERPOLATE_SHIFT, 255));
+				const int g = max(0, min(acc[i][1] >> VB200_INTERPOLATE_SHIFT, 255));
+				const int b = max(0, min(acc[i][2] >> VB200_INTERPOLATE_SHIFT, 255));
+				const int a = max(0, min(acc[i][3] >> VB200_INTERPOLATE_SHIFT, 255));
+				rb += (unsigned) r + (unsigned) b * 65536u;
+				ga += (unsigned) g + (unsigned) a * 65536u;
+			}
+			if (G > 1) {
+				/* the other lanes of this box-shrunk column; amend was added once per lane */
+#pragma unroll
+				for (int off = 1; off < G; off <<= 1) {
+					rb += __shfl_xor_sync(0xffffffffu, rb, off);
+					ga += __shfl_xor_sync(0xffffffffu, ga, off);
+				}
+				rb -= (unsigned) (G - 1) * hamend2;
+				ga -= (unsigned) (G - 1) * hamend2;
+			}
+			/* ((amend + sum) * multiplier) >> 24 with HS a power of two == >> log2(HS); bytes 0, 2 exact */
+			rb >>= HSHIFT;
+			ga >>= HSHIFT;
+			const unsigned orb = __shfl_xor_sync(0xffffffffu, rb, G);
+			const unsigned oga = __shfl_xor_sync(0xffffffffu, ga, G);
+			if (pair_writer) {
+				uint2 w;
+				w.x = __byte_perm(rb, orb, 0x6240); /* writer is the A column: [rA rB bA bB] */
+				w.y = __byte_perm(ga, oga, 0x6240);
+				*shb = w;
+			}
+			(void) is_B;
+		}
+		pdone = P1 + 1;
+		P0_prev = P0;
+		__syncwarp();
+		if (lane0)
+			mbar_arrive(shfull_s + 8u * buf);
+	}
+}
+
 /* Pack a 65 x n table of short coefficients into parity-aligned s16x2 pairs:
  * set (phase, parity) holds pairs k = 0..NP-1 = (c[2k - parity], c[2k + 1 - parity]).
  */
@@ -944,6 +1312,8 @@ struct ThumbnailPlanImpl {
 	bool tma_ok = false;
 	int slots_tma = 0;
 	size_t smem_tma = 0;
+	bool tma3_ok = false; /* v3: in-warp shrinkh + H warp (HS in {2,4,8}) */
+	size_t smem_tma3 = 0;
 	/* host pump */
 	static constexpr int kStreams = 3;
 	cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
@@ -1051,6 +1421,44 @@ launch_tma_vs(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, 
 	}
 }
 
+template <int VS, int NP, bool PREMUL, int HSQ>
+int
+launch_tma3_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride,
+	void *out, size_t out_stride, int n, dim3 grid, cudaStream_t s)
+{
+	auto kern = thumbnail_fused_tma3_kernel<VS, NP, PREMUL, HSQ>;
+	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_tma3));
+	for (int f0 = 0; f0 < n; f0 += 32768) {
+		grid.z = std::min(32768, n - f0);
+		kern<<<grid, fp.NT + 64, pl->smem_tma3, s>>>(fp, (const uint8_t *) in, in_stride, (uint8_t *) out, out_stride, f0);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "thumbnail_fused_tma3_kernel launch");
+		count_launch();
+	}
+	return 0;
+}
+
+/* the instantiated corner of v3: box 2 / 4 / 8 on both axes (what gap 2.0 gives for
+ * shrinks 4..20) with 6 or 7 coefficient pairs; everything else runs v2
+ */
+template <bool PREMUL>
+int
+launch_tma3(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t is, void *out,
+	size_t os, int n, dim3 grid, cudaStream_t s, bool *handled)
+{
+	*handled = true;
+	const int np = fp.NPv == fp.NPh ? fp.NPv : 0;
+#define V3(VS_, NP_, HS_) \
+	if (fp.VS == VS_ && np == NP_ && fp.HS == HS_) \
+		return launch_tma3_t<VS_, NP_, PREMUL, HS_>(domain, pl, fp, in, is, out, os, n, grid, s);
+	V3(2, 6, 2) V3(2, 7, 2) V3(4, 6, 4) V3(4, 7, 4) V3(8, 6, 8) V3(8, 7, 8)
+	V3(2, 0, 2) V3(4, 0, 4) V3(8, 0, 8) V3(3, 0, 4) V3(4, 0, 2) V3(2, 0, 4)
+#undef V3
+	*handled = false;
+	return 0;
+}
+
 int
 launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
 	cudaStream_t s)
@@ -1067,6 +1475,13 @@ launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 		rpc = ((rpc / 2 + K - 1) / K) * K;
 	fp.RPC = rpc;
 	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+	if (pl->tma3_ok) {
+		bool handled = false;
+		const int rc = pl->premul ? launch_tma3<true>(domain, pl, fp, in, is, out, os, n, grid, s, &handled)
+								  : launch_tma3<false>(domain, pl, fp, in, is, out, os, n, grid, s, &handled);
+		if (handled)
+			return rc;
+	}
 	const int np = fp.NPv == fp.NPh ? fp.NPv : 0;
 	if (np == 6)
 		return pl->premul ? launch_tma_vs<6, true>(domain, pl, fp, in, is, out, os, n, grid, s)
@@ -1241,6 +1656,11 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		pl->smem_tma = (size_t) kStages * 2 * fp.VS * kStagePitch + 2 * kStages * 8 + (size_t) slots2 * nc * 8 +
 			(size_t) kChunkRowsTma * nc * 4 + (size_t) kChunkRowsTma * (nemax / 2) * 8 +
 			(size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 256) * 4;
+		pl->smem_tma3 = (size_t) kStages * 2 * fp.VS * kStagePitch + (2 * kStages + 4) * 8 + (size_t) slots2 * nc * 8 +
+			(size_t) 2 * kChunkRowsTma * (nemax / 2) * 8 + (size_t) (fp.nvsets * fp.NPv + fp.nhsets * fp.NPh + 256) * 4;
+		pl->tma3_ok = (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) && max_cols * 4 <= kStagePitch &&
+			pl->smem_tma3 <= 113 * 1024 && fp.max_alpha == 255.0 && getenv("VB200_NO_TMA3") == nullptr &&
+			getenv("VB200_NO_TMA") == nullptr;
 		pl->tma_ok = max_cols * 4 <= kStagePitch && pl->smem_tma <= 113 * 1024 && fp.max_alpha == 255.0 &&
 			getenv("VB200_NO_TMA") == nullptr;
 	}
@@ -1280,8 +1700,20 @@ thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
 	}
 	thumbnail_shrink(pl->W, pl->H, pl->target_w, pl->target_h, pl->size, &pl->hshrink, &pl->vshrink);
 	if (pl->hshrink < 1.0 || pl->vshrink < 1.0) {
-		error(domain, "upsizing is not on the device path yet");
-		return -1;
+		/* enlarging thumbnail: premultiply / vips_resize (affine) / unpremultiply, unfused */
+		const double hscale = std::max(1.0 / pl->hshrink, 1.0 / pl->W);
+		const double vscale = std::max(1.0 / pl->vshrink, 1.0 / pl->H);
+		if (hscale < 1.0 || vscale < 1.0) {
+			error(domain, "mixed up/down resize is not on the device path");
+			return -1;
+		}
+		/* oarea of the scale-only affine, affine.c:466-481 */
+		const double rw = (hscale > 1.0 ? hscale : 1.0) * pl->W, rh = (vscale > 1.0 ? vscale : 1.0) * pl->H;
+		pl->OW = (int) (rw > 0 ? rw + 0.5 : rw - 0.5);
+		pl->OH = (int) (rh > 0 ? rh + 0.5 : rh - 0.5);
+		pl->premul = pl->has_alpha && pl->hshrink != 1.0 && pl->vshrink != 1.0;
+		pl->fused = false;
+		return 0;
 	}
 	/* vips_resize: scale = 1 / shrink, then reducev(1 / vscale) -- keep the double rounding */
 	double hscale = std::max(1.0 / pl->hshrink, 1.0 / pl->W);

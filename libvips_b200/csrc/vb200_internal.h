@@ -109,6 +109,10 @@ int dev_resize(const char *domain, const DevImage &in, DevImage *out, double hsc
 
 double interpretation_max_alpha(int type);
 
+/* affine.cu */
+int dev_resize_up(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,
+	cudaStream_t s);
+
 /* colour.cu */
 int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space,
 	cudaStream_t s);

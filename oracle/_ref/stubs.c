@@ -1,7 +1,5 @@
 #include <stdio.h>
 #include <stdlib.h>
-void vips_area_unref(void) { fputs("ref shim: vips_area_unref() is not available", stderr); abort(); }
-void vips_array_double_newv(void) { fputs("ref shim: vips_array_double_newv() is not available", stderr); abort(); }
 void vips_call_split(void) { fputs("ref shim: vips_call_split() is not available", stderr); abort(); }
 void vips_cast(void) { fputs("ref shim: vips_cast() is not available", stderr); abort(); }
 void vips_colour_code_get_type(void) { fputs("ref shim: vips_colour_code_get_type() is not available", stderr); abort(); }

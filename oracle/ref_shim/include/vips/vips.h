@@ -449,6 +449,8 @@ gboolean vips_rect_isempty(const VipsRect *r);
 void vips_region_paint_pel(VipsRegion *reg, const VipsRect *r, const VipsPel *ink);
 VipsPel *vips__vector_to_ink(const char *domain, VipsImage *im, double *real, double *imag, int n);
 void *g_object_ref(void *p);
+VipsArrayDouble *vips_array_double_newv(int n, ...);
+void vips_area_unref(VipsArea *area);
 void vips_object_set_static(VipsObject *object, gboolean static_object);
 #define DBL_MIN_SHIM 2.2250738585072014e-308
 

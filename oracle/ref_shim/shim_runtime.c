@@ -102,6 +102,22 @@ SHIM_PLAIN_TYPE(vips_convolution_get_type)
 SHIM_PLAIN_TYPE(vips_create_get_type)
 
 void *g_object_ref(void *p) { return p; }
+
+VipsArrayDouble *vips_array_double_newv(int n, ...)
+{
+	VipsArea *area = (VipsArea *) calloc(1, sizeof(VipsArea));
+	double *d = (double *) calloc(n > 0 ? n : 1, sizeof(double));
+	va_list ap;
+	int i;
+	va_start(ap, n);
+	for (i = 0; i < n; i++)
+		d[i] = va_arg(ap, double);
+	va_end(ap);
+	area->data = d;
+	area->n = n;
+	return (VipsArrayDouble *) area;
+}
+void vips_area_unref(VipsArea *area) {}
 void vips_object_set_static(VipsObject *object, gboolean static_object) {}
 
 /* ------------------------------------------------------------------- rects */

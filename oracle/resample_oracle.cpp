@@ -847,11 +847,38 @@ resize_shrinks(int w, int h, double hscale, double vscale, double *hshrink, doub
 	*hshrink = hscale < 1.0 ? 1.0 / hscale : 1.0;
 }
 
+extern "C" int orc_affine_size(int w, int h, double a, double b, double c, double d, int *ow, int *oh);
+extern "C" int orc_affine(const void *in, int w, int h, int bands, int fmt, double a, double b, double c, double d,
+	int interp, double idx, double idy, double odx, double ody, int tile_w, int tile_h, void *out);
+extern "C" int orc_resize_affine_args(double hscale, double vscale, int kernel, double *a, double *d, double *idx,
+	double *idy, int *interp);
+
+/* upsizing (resize.c:233-307): pure enlargements only; a mixed up/down resize
+ * chains reduce and affine with rect origins this whole-image oracle does not model
+ */
+static int
+resize_is_upsize(int w, int h, double hscale, double vscale, int *mixed)
+{
+	hscale = std::max(hscale, 1.0 / w);
+	vscale = std::max(vscale, 1.0 / h);
+	*mixed = (hscale > 1.0 && vscale < 1.0) || (hscale < 1.0 && vscale > 1.0);
+	return hscale > 1.0 || vscale > 1.0;
+}
+
 extern "C" int
 orc_resize_size(int w, int h, double hscale, double vscale, int kernel, double gap, int *ow, int *oh)
 {
 	double hs, vs;
 	OrcReduceGeom g;
+	int mixed;
+	if (resize_is_upsize(w, h, hscale, vscale, &mixed)) {
+		double a, d, idx, idy;
+		int interp;
+		if (mixed)
+			return -1;
+		orc_resize_affine_args(std::max(hscale, 1.0 / w), std::max(vscale, 1.0 / h), kernel, &a, &d, &idx, &idy, &interp);
+		return orc_affine_size(w, h, a, 0, 0, d, ow, oh);
+	}
 	resize_shrinks(w, h, hscale, vscale, &hs, &vs);
 	*oh = h;
 	*ow = w;
@@ -895,6 +922,22 @@ orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, doub
 	int tile_w, int tile_h, void *out)
 {
 	double hs, vs;
+	int mixed;
+	if (resize_is_upsize(w, h, hscale, vscale, &mixed)) {
+		double a, d, idx, idy;
+		int interp, ow, oh;
+		if (mixed)
+			return -1;
+		orc_resize_affine_args(std::max(hscale, 1.0 / w), std::max(vscale, 1.0 / h), kernel, &a, &d, &idx, &idy, &interp);
+		if (orc_affine_size(w, h, a, 0, 0, d, &ow, &oh))
+			return -1;
+		/* a scale-only affine asks FATSTRIP (affine.c:571-575): full-width x 16-row sink tiles */
+		if (tile_w <= 0 || tile_h <= 0) {
+			tile_w = ow;
+			tile_h = 16;
+		}
+		return orc_affine(in, w, h, bands, fmt, a, 0, 0, d, interp, idx, idy, 0, 0, tile_w, tile_h, out);
+	}
 	resize_shrinks(w, h, hscale, vscale, &hs, &vs);
 	const size_t es = orc_sizeof_format(fmt);
 
@@ -983,8 +1026,7 @@ orc_thumbnail_image(const void *in, int w, int h, int bands, int target_w, int t
 	int ow, oh;
 	if (orc_thumbnail_size(w, h, target_w, target_h, size_mode, &hs, &vs, &ow, &oh))
 		return -1;
-	if (hs < 1.0 || vs < 1.0)
-		return -1; /* upsizing goes through affine: see orc_affine */
+	/* enlarging thumbnails go through vips_resize's affine half (orc_resize handles it) */
 
 	const bool premul = has_alpha && hs != 1.0 && vs != 1.0; /* thumbnail.c:848-861 */
 	std::vector<uint8_t> pre, res;
