@@ -145,6 +145,94 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def side_workload(args):
+    """BASELINE.json configs 1, 3, 4 on one GPU, device-resident, CUDA events: not the
+    headline line, the rows of BASELINE.md's results table."""
+    import numpy as np
+    import torch
+
+    import libvips_b200 as vb
+    from libvips_b200 import CImage, CMask
+
+    vb.init(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream()
+    vb.set_stream(stream.cuda_stream)
+    L = vb.lib()
+    peak, peak_src = peaks()
+
+    def dimg(t, interp):
+        h, w, b = t.shape
+        fmt = {torch.uint8: 0, torch.float32: 6, torch.int16: 3}[t.dtype]
+        return CImage(w, h, b, fmt, interp, vb.DEVICE, C.c_void_p(t.data_ptr()), w * b * t.element_size())
+
+    def run(fn, alg_bytes, label, units, unit_name):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = vb.launch_count()
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        print(json.dumps({"metric": label, "value": units / (ms / 1e3), "unit": unit_name, "n_gpus": 1,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "dtype": "f32/f64 accumulate" if "conv" in label or "colour" in label else "u8",
+                          "data": "synthetic", "config": {"workload": label, "device_resident": True},
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                       "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                                       "algorithmic_bytes": alg_bytes},
+                          "gpu_launches": int(vb.launch_count() - n0)}))
+
+    if args.workload == "convsep":
+        n = 8192
+        a = torch.rand((n, n, 3), device=dev) * 255
+        out = torch.empty_like(a)
+        m, scale, off = vb.gaussmat(4.0, 0.2, True, "float")
+        cm = CMask(m.shape[1], m.shape[0], m.ctypes.data_as(C.POINTER(C.c_double)), scale, off)
+        cin = dimg(a, 22)
+
+        def fn():
+            cout = dimg(out, 22)
+            vb._check(L.vb200_convsep(C.byref(cin), C.byref(cout), C.byref(cm), 1))
+        run(fn, 2 * a.numel() * 4, "vips_convsep 15-tap Gaussian float on 8192x8192 RGB float32", n * n / 1e6, "Mpixels/s")
+    elif args.workload == "colour":
+        n = 16384
+        a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
+        lab = torch.empty((n, n, 3), dtype=torch.float32, device=dev)
+        back = torch.empty_like(a)
+        cin = dimg(a, 22)
+
+        def fn():
+            clab = dimg(lab, 13)
+            vb._check(L.vb200_colourspace(C.byref(cin), C.byref(clab), 13))
+            clab = dimg(lab, 13)
+            cback = dimg(back, 22)
+            vb._check(L.vb200_colourspace(C.byref(clab), C.byref(cback), 22))
+        fn()
+        torch.cuda.synchronize()
+        assert torch.equal(a, back), "sRGB -> Lab -> sRGB must be the identity on 8-bit data"
+        run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_colourspace sRGB->Lab->sRGB round trip on 16384x16384",
+            2 * n * n / 1e6, "Mpixels/s")
+    elif args.workload == "reduce49":
+        n = 4096
+        a = torch.randint(0, 256, (n, n, 4), dtype=torch.uint8, device=dev)
+        out = torch.empty((n // 8, n // 8, 4), dtype=torch.uint8, device=dev)
+        cin = dimg(a, 22)
+
+        def fn():
+            cout = dimg(out, 22)
+            vb._check(L.vb200_reduce(C.byref(cin), C.byref(cout), 8.0, 8.0, 5, 0.0))
+        run(fn, a.numel() + out.numel(), "vips_reduce(8, 8) Lanczos3 gap 0 (49 taps) on one 4096x4096 uchar RGBA",
+            n * n / 1e6, "Mpixels/s")
+    else:
+        raise SystemExit("unknown workload %s" % args.workload)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -155,10 +243,15 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
     ap.add_argument("--cpu-frames", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="thumbnail",
+                    help="thumbnail (the headline, default) | convsep | colour | reduce49: the other BASELINE.json "
+                         "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload != "thumbnail":
+        return side_workload(args)
 
     import numpy as np
     import torch

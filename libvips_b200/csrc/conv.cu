@@ -69,6 +69,58 @@ convf_kernel(const __grid_constant__ ConvDev P, const T *__restrict__ in, float 
 	((float *) ((char *) out + (size_t) y * P.out_bpl))[e] = (float) sum;
 }
 
+/* 1-D masks (the two passes of convsep / gaussblur): taps in shared memory, an
+ * interior fast path without clamping, unit-stride (coalesced) loads per tap.
+ * Same accumulation order and rounding as convf_kernel.
+ */
+template <typename T, bool VERT>
+__global__ void __launch_bounds__(256)
+convf_line_kernel(const __grid_constant__ ConvDev P, const T *__restrict__ in, float *__restrict__ out)
+{
+	__shared__ double sc[64];
+	__shared__ int sd[64];
+	if (threadIdx.x < P.nnz) {
+		sc[threadIdx.x] = P.fcoeff[threadIdx.x];
+		sd[threadIdx.x] = VERT ? P.taps[threadIdx.x].dy : P.taps[threadIdx.x].dx;
+	}
+	__syncthreads();
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (e >= P.w * P.bands)
+		return;
+	const int nnz = P.nnz;
+	double sum = P.offset;
+	if (VERT) {
+		const size_t stride = P.in_bpl;
+		const char *col = (const char *) in + (size_t) e * sizeof(T);
+		if (y + sd[0] >= 0 && y + sd[nnz - 1] < P.h) {
+			const char *p = col + (size_t) y * stride;
+			for (int i = 0; i < nnz; i++)
+				sum = __dadd_rn(sum, __dmul_rn(sc[i], (double) *(const T *) (p + (ptrdiff_t) sd[i] * (ptrdiff_t) stride)));
+		}
+		else
+			for (int i = 0; i < nnz; i++) {
+				const int sy = clampi(y + sd[i], 0, P.h - 1);
+				sum = __dadd_rn(sum, __dmul_rn(sc[i], (double) *(const T *) (col + (size_t) sy * stride)));
+			}
+	}
+	else {
+		const T *row = (const T *) ((const char *) in + (size_t) y * P.in_bpl);
+		const int x = e / P.bands;
+		if (x + sd[0] >= 0 && x + sd[nnz - 1] < P.w) {
+			const T *p = row + e;
+			for (int i = 0; i < nnz; i++)
+				sum = __dadd_rn(sum, __dmul_rn(sc[i], (double) p[sd[i] * P.bands]));
+		}
+		else {
+			const int b = e - x * P.bands;
+			for (int i = 0; i < nnz; i++)
+				sum = __dadd_rn(sum, __dmul_rn(sc[i], (double) row[clampi(x + sd[i], 0, P.w - 1) * P.bands + b]));
+		}
+	}
+	((float *) ((char *) out + (size_t) y * P.out_bpl))[e] = (float) sum;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 convi_kernel(const __grid_constant__ ConvDev P, const T *__restrict__ in, T *__restrict__ out, long long lo,
@@ -311,7 +363,17 @@ dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *ma
 		P.out_bpl = out->bpl;
 		if (upload_taps(domain, pos, mw, mh, &coeff, nullptr, &P, &u, s))
 			return -1;
-#define CF(T) convf_kernel<T><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data)
+		/* taps arrive sorted by mask position, so sd[0] / sd[nnz - 1] bound the stencil */
+		const bool line_h = mh == 1 && coeff.size() <= 64, line_v = mw == 1 && coeff.size() <= 64;
+#define CF(T) \
+	do { \
+		if (line_h) \
+			convf_line_kernel<T, false><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data); \
+		else if (line_v) \
+			convf_line_kernel<T, true><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data); \
+		else \
+			convf_kernel<T><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data); \
+	} while (0)
 		switch (in.fmt) {
 		case VB200_FORMAT_UCHAR: CF(uint8_t); break;
 		case VB200_FORMAT_CHAR: CF(int8_t); break;

@@ -58,6 +58,7 @@ struct FusedParams {
 	int NPv;	  /* coefficient pairs per vertical set */
 	unsigned vmul8; /* ((1 << 32) / (256 * VS)) << 8, for umulhi */
 	int vshift;	  /* log2(VS) if VS is a power of two, else -1 */
+	unsigned accmul; /* v3: 256 / VS when VS is a power of two (box sums kept pre-scaled), else 1 */
 	/* horizontal */
 	int HS, Ws, hembed, NPh;
 	unsigned hmul8;
@@ -415,7 +416,7 @@ mbar_wait(unsigned bar, unsigned parity)
 	unsigned done;
 	do {
 		asm volatile("{\n\t.reg .pred p;\n\t"
-					 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+					 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
 					 "selp.u32 %0, 1, 0, p;\n\t}"
 					 : "=r"(done)
 					 : "r"(bar), "r"(parity)
@@ -500,6 +501,43 @@ average_pair(unsigned lanesA, unsigned lanesB, unsigned mul8, int shift)
 	const unsigned a = __umulhi(lanesA & 0xffffu, mul8) | (__umulhi(lanesA >> 16, mul8) << 16);
 	const unsigned b = __umulhi(lanesB & 0xffffu, mul8) | (__umulhi(lanesB >> 16, mul8) << 16);
 	return __byte_perm(a, b, 0x6240);
+}
+
+/* v3 forms.  The integer pipes of an SM sub-partition are two half-rate units: IMAD
+ * (fma pipe) and everything else -- SHF, LOP3, PRMT, IADD3, IDP -- on the alu pipe,
+ * which is what bounds this kernel.  So the per-pixel work is phrased to put as
+ * much as possible on IMAD: the lane sums are accumulated by a multiply-add with a
+ * run-time multiplier m = 256 / VS, which also leaves the box average
+ * ((sum + VS / 2) * m) >> 8 sitting in bytes 1 and 3 (one PRMT, no shifts), and
+ * scale[alpha] comes from one LOP3 + one IMAD.HI.
+ */
+template <bool PREMUL>
+__device__ __forceinline__ void
+accumulate_pixel_m(unsigned x, unsigned m, unsigned k16, unsigned &rb, unsigned &ga)
+{
+	if (PREMUL) {
+		/* s = (a * 257 + 1) >> 8 = hi32((a << 24 | 1 << 16) * 257); k16 = 1 << 16 held in a
+		 * register so that the mask-and-or is ONE LOP3 (it encodes a single immediate)
+		 */
+		unsigned t0;
+		asm("lop3.b32 %0, %1, 0xff000000, %2, 0xea;" : "=r"(t0) : "r"(x), "r"(k16)); /* (x & 0xff000000) | k16 */
+		const unsigned s = __umulhi(t0, 257u);
+		const unsigned trb = (x & 0x00ff00ffu) * s + 0x00800080u; /* 16-bit lanes r * s + 128, b * s + 128 */
+		const unsigned tg = (x & 0x0000ff00u) * s + 0x00008000u;	  /* (g * s + 128) << 8: byte 2 = g', byte 3 = 0 */
+		rb = __byte_perm(trb, 0, 0x4341) * m + rb;				  /* [r', 0, b', 0] */
+		ga = __byte_perm(tg, x, 0x3732) * m + ga;				  /* [g', 0, a, 0] */
+	}
+	else {
+		rb = (x & 0x00ff00ffu) * m + rb;
+		ga = __byte_perm(x, 0, 0x4341) * m + ga;
+	}
+}
+
+/* lanes hold (sum + VS / 2) * 256 / VS: the averages are bytes 1 and 3 */
+__device__ __forceinline__ unsigned
+average_pair_m(unsigned lanesA, unsigned lanesB)
+{
+	return __byte_perm(lanesA, lanesB, 0x7351);
 }
 
 __device__ __forceinline__ unsigned
@@ -1058,11 +1096,12 @@ thumbnail_fused_tma3_kernel(const __grid_constant__ FusedParams P, const uint8_t
 	}
 
 	/* ---------------- V warps */
-	const unsigned char *my_col[CPT];
-#pragma unroll
-	for (int i = 0; i < CPT; i++)
-		my_col[i] = stages + (size_t) (column_of(min(t * CPT + i, NE * HSQ - 1)) - c_lo) * 4u;
-	const unsigned amend2 = (unsigned) (vs / 2) * 0x00010001u;
+	/* the thread's two columns are adjacent and start on an even column: one 64-bit LDS per row */
+	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - 2)) - c_lo) * 4u;
+	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
+	unsigned k16;
+	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
+	const unsigned amend2 = (unsigned) (vs / 2) * accm * 0x00010001u;
 	const unsigned hamend2 = (unsigned) (HSQ / 2) * 0x00010001u;
 	const bool lane0 = (t & 31) == 0;
 	const unsigned vmul8 = P.vmul8;
@@ -1109,32 +1148,32 @@ thumbnail_fused_tma3_kernel(const __grid_constant__ FusedParams P, const uint8_t
 				rbA[i] = gaA[i] = rbB[i] = gaB[i] = amend2;
 			mbar_wait(full_s + 8u * s, phase);
 			if (VS > 0) {
-				unsigned pa[CPT][VSR], pb[CPT][VSR];
+				uint2 pa[VSR], pb[VSR];
 #pragma unroll
-				for (int i = 0; i < CPT; i++)
-#pragma unroll
-					for (int k = 0; k < VSR; k++) {
-						pa[i][k] = *(const unsigned *) (my_col[i] + soff + k * kStagePitch);
-						pb[i][k] = *(const unsigned *) (my_col[i] + soff + (VSR + k) * kStagePitch);
-					}
+				for (int k = 0; k < VSR; k++) {
+					pa[k] = *(const uint2 *) (my_cols + soff + k * kStagePitch);
+					pb[k] = *(const uint2 *) (my_cols + soff + (VSR + k) * kStagePitch);
+				}
 				__syncwarp();
 				if (lane0)
 					mbar_arrive(empty_s + 8u * s);
 #pragma unroll
-				for (int i = 0; i < CPT; i++)
-#pragma unroll
-					for (int k = 0; k < VSR; k++) {
-						accumulate_pixel<PREMUL>(pa[i][k], rbA[i], gaA[i]);
-						accumulate_pixel<PREMUL>(pb[i][k], rbB[i], gaB[i]);
-					}
+				for (int k = 0; k < VSR; k++) {
+					accumulate_pixel_m<PREMUL>(pa[k].x, accm, k16, rbA[0], gaA[0]);
+					accumulate_pixel_m<PREMUL>(pa[k].y, accm, k16, rbA[1], gaA[1]);
+					accumulate_pixel_m<PREMUL>(pb[k].x, accm, k16, rbB[0], gaB[0]);
+					accumulate_pixel_m<PREMUL>(pb[k].y, accm, k16, rbB[1], gaB[1]);
+				}
 			}
 			else {
-				for (int k = 0; k < vs; k++)
-#pragma unroll
-					for (int i = 0; i < CPT; i++) {
-						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + k * kStagePitch), rbA[i], gaA[i]);
-						accumulate_pixel<PREMUL>(*(const unsigned *) (my_col[i] + soff + (vs + k) * kStagePitch), rbB[i], gaB[i]);
-					}
+				for (int k = 0; k < vs; k++) {
+					const uint2 qa = *(const uint2 *) (my_cols + soff + k * kStagePitch);
+					const uint2 qb = *(const uint2 *) (my_cols + soff + (vs + k) * kStagePitch);
+					accumulate_pixel_m<PREMUL>(qa.x, accm, k16, rbA[0], gaA[0]);
+					accumulate_pixel_m<PREMUL>(qa.y, accm, k16, rbA[1], gaA[1]);
+					accumulate_pixel_m<PREMUL>(qb.x, accm, k16, rbB[0], gaB[0]);
+					accumulate_pixel_m<PREMUL>(qb.y, accm, k16, rbB[1], gaB[1]);
+				}
 				__syncwarp();
 				if (lane0)
 					mbar_arrive(empty_s + 8u * s);
@@ -1143,8 +1182,12 @@ thumbnail_fused_tma3_kernel(const __grid_constant__ FusedParams P, const uint8_t
 				s = 0;
 				phase ^= 1u;
 			}
-			*(uint4 *) pdst = make_uint4(average_pair(rbA[0], rbB[0], vmul8, vshift), average_pair(gaA[0], gaB[0], vmul8, vshift),
-				average_pair(rbA[1], rbB[1], vmul8, vshift), average_pair(gaA[1], gaB[1], vmul8, vshift));
+			if (vshift >= 0)
+				*(uint4 *) pdst = make_uint4(average_pair_m(rbA[0], rbB[0]), average_pair_m(gaA[0], gaB[0]),
+					average_pair_m(rbA[1], rbB[1]), average_pair_m(gaA[1], gaB[1]));
+			else
+				*(uint4 *) pdst = make_uint4(average_pair(rbA[0], rbB[0], vmul8, -1), average_pair(gaA[0], gaB[0], vmul8, -1),
+					average_pair(rbA[1], rbB[1], vmul8, -1), average_pair(gaA[1], gaB[1], vmul8, -1));
 		}
 
 		/* reducev + in-warp shrinkh; rows go to sh[buf] once the H warp has released it */
@@ -1564,9 +1607,12 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	fp.hgrid = hgrid;
 	fp.vmul8 = (unsigned) (((1LL << 32) / (256LL * fp.VS)) << 8);
 	fp.vshift = -1;
+	fp.accmul = 1;
 	for (int sft = 0; sft < 9; sft++)
-		if ((1 << sft) == fp.VS)
+		if ((1 << sft) == fp.VS) {
 			fp.vshift = sft;
+			fp.accmul = 256u >> sft;
+		}
 	fp.HS = pl->gh.int_shrink;
 	fp.Ws = pl->gh.shrunk_size;
 	fp.hembed = th.embed;
