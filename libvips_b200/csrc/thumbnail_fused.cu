@@ -79,6 +79,9 @@ struct FusedParams {
 	const int *vcoef;  /* [nvsets][NPv] packed s16x2 */
 	const int *hcoef;  /* [nhsets][NPh] */
 	int nvsets, nhsets;
+	/* v4 (thumbnail_fused_mma.cuh) */
+	const int2 *vchunk;	 /* [ceil(OH / 8)] {first quad, last quad} of each 8-row chunk */
+	const uint4 *vbfrag; /* [chunks][32] B fragments {hi b0, hi b1, lo b0, lo b1} */
 	/* alpha */
 	int premul;		  /* 1: premultiply/unpremultiply with max_alpha */
 	double max_alpha; /* LUTs are derived from it in the prologue */
@@ -1280,6 +1283,8 @@ thumbnail_fused_tma3_kernel(const __grid_constant__ FusedParams P, const uint8_t
 	}
 }
 
+#include "thumbnail_fused_mma.cuh"
+
 /* Pack a 65 x n table of short coefficients into parity-aligned s16x2 pairs:
  * set (phase, parity) holds pairs k = 0..NP-1 = (c[2k - parity], c[2k + 1 - parity]).
  */
@@ -1357,6 +1362,11 @@ struct ThumbnailPlanImpl {
 	size_t smem_tma = 0;
 	bool tma3_ok = false; /* v3: in-warp shrinkh + H warp (HS in {2,4,8}) */
 	size_t smem_tma3 = 0;
+	/* v4: reducev on the integer tensor pipe */
+	bool mma_ok = false;
+	int mma_cols = 0, mma_tw = 0, mma_nt = 0, mma_nemax = 0;
+	size_t smem_mma = 0;
+	void *tables_mma = nullptr;
 	/* host pump */
 	static constexpr int kStreams = 3;
 	cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
@@ -1502,10 +1512,75 @@ launch_tma3(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, co
 	return 0;
 }
 
+template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS>
+int
+launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, dim3 grid, cudaStream_t s)
+{
+	auto kern = thumbnail_fused_mma_kernel<VS, NP, PREMUL, HSQ, WCOLS>;
+	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_mma));
+	for (int f0 = 0; f0 < n; f0 += 32768) {
+		grid.z = std::min(32768, n - f0);
+		kern<<<grid, fp.NT + 64, pl->smem_mma, s>>>(fp, (const uint8_t *) in, in_stride, (uint8_t *) out, out_stride, f0);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "thumbnail_fused_mma_kernel launch");
+		count_launch();
+	}
+	return 0;
+}
+
+/* the instantiated corner of v4: box 2 / 4 vertically, 2 / 4 / 8 horizontally */
+template <bool PREMUL, int WCOLS>
+int
+launch_mma_w(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t is, void *out,
+	size_t os, int n, dim3 grid, cudaStream_t s, bool *handled)
+{
+	*handled = true;
+	const int np = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
+#define V4(VS_, NP_, HS_) \
+	if (fp.VS == VS_ && np == NP_ && fp.HS == HS_) \
+		return launch_mma_t<VS_, NP_, PREMUL, HS_, WCOLS>(domain, pl, fp, in, is, out, os, n, grid, s);
+	V4(4, 6, 4) V4(4, 7, 4) V4(2, 6, 2) V4(2, 7, 2)
+	V4(4, 0, 4) V4(2, 0, 2) V4(4, 0, 2) V4(2, 0, 4) V4(4, 0, 8) V4(2, 0, 8)
+#undef V4
+	*handled = false;
+	return 0;
+}
+
+int
+launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
+	cudaStream_t s, bool *handled)
+{
+	FusedParams fp = pl->fp;
+	fp.TW = pl->mma_tw;
+	fp.NT = pl->mma_nt;
+	fp.NEmax = pl->mma_nemax;
+	const int K = kV4Rows;
+	const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
+	int rpc = ((pl->OH + K - 1) / K) * K;
+	const int ctas = pl->mma_cols > 448 ? 148 : 2 * 148;
+	while ((long long) bands_x * ((pl->OH + rpc - 1) / rpc) * n < ctas && rpc > 4 * K)
+		rpc = ((rpc / 2 + K - 1) / K) * K;
+	fp.RPC = rpc;
+	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+	if (pl->mma_cols > 448)
+		return pl->premul ? launch_mma_w<true, 768>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+						  : launch_mma_w<false, 768>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+	return pl->premul ? launch_mma_w<true, 384>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+					  : launch_mma_w<false, 384>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+}
+
 int
 launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
 	cudaStream_t s)
 {
+	if (pl->mma_ok) {
+		bool handled = false;
+		const int rc = launch_mma(domain, pl, in, is, out, os, n, s, &handled);
+		if (handled)
+			return rc;
+	}
 	FusedParams fp = pl->fp;
 	fp.slots = pl->slots_tma;
 	/* consumer threads: kColsPerThread columns each (pl->fp.NT counts columns, rounded to 32) */
@@ -1711,6 +1786,119 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			getenv("VB200_NO_TMA") == nullptr;
 	}
 
+	/* v4: reducev as u8 x s8 MMAs over a ring of 8 quads (32 box-shrunk rows) per 8 output rows */
+	pl->mma_ok = false;
+	if (pl->tma_ok && (fp.VS == 2 || fp.VS == 4) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
+		getenv("VB200_NO_MMA") == nullptr) {
+		const int K = kV4Rows;
+		const int chunks = (pl->OH + K - 1) / K;
+		const int np = tv.n_point;
+		std::vector<int2> vchunk(chunks);
+		std::vector<uint4> bfrag((size_t) chunks * 32);
+		bool ok = true;
+		for (int c = 0; c < chunks && ok; c++) {
+			int lo = INT_MAX, hi = INT_MIN;
+			for (int y = c * K; y < std::min(c * K + K, pl->OH); y++) {
+				const short *m = &tv.ms[(size_t) tv.phase[y] * np];
+				int a = 0, b = np - 1;
+				while (a < b && m[a] == 0)
+					a++;
+				while (b > a && m[b] == 0)
+					b--;
+				lo = std::min(lo, tv.first[y] + a);
+				hi = std::max(hi, tv.first[y] + b);
+			}
+			if (lo < 0) {
+				ok = false;
+				break;
+			}
+			int q0 = lo >> 2;
+			const int q1 = hi >> 2;
+			if (c > 0) {
+				/* quads are produced in order, without gaps */
+				q0 = std::min(q0, vchunk[c - 1].y + 1);
+				if (q1 < vchunk[c - 1].y)
+					ok = false;
+			}
+			if (q1 - q0 + 1 > kV4Quads)
+				ok = false;
+			vchunk[c] = make_int2(q0, q1);
+			for (int lane = 0; lane < 32 && ok; lane++) {
+				const int tig = lane & 3, g = lane >> 2;
+				const int y = c * K + g;
+				unsigned w[4] = {0, 0, 0, 0}; /* hi b0, hi b1, lo b0, lo b1 */
+				for (int half = 0; half < 2; half++) {
+					const int slot = tig + 4 * half;
+					int q = -1;
+					for (int qq = q0; qq <= q1; qq++)
+						if ((qq & (kV4Quads - 1)) == slot)
+							q = qq;
+					for (int i = 0; i < 4; i++) {
+						int coef = 0;
+						if (q >= 0 && y < pl->OH) {
+							const int tap = 4 * q + i - tv.first[y];
+							if (tap >= 0 && tap < np)
+								coef = tv.ms[(size_t) tv.phase[y] * np + tap];
+						}
+						w[half] |= (unsigned) ((coef >> 8) & 0xff) << (8 * i);
+						w[2 + half] |= (unsigned) (coef & 0xff) << (8 * i);
+					}
+				}
+				bfrag[(size_t) c * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
+			}
+		}
+		/* band width: the fewest bands whose widest one fits the column budget */
+		const char *ev = getenv("VB200_V4_COLS");
+		const int wcols = ev && atoi(ev) > 448 ? 768 : 384;
+		const int pitch = (wcols + 8) * 4;
+		auto column_of = [&](int E0, int tt) {
+			const int e = E0 + tt / fp.HS;
+			const int k = tt % fp.HS;
+			const int sc = std::max(0, std::min(e - fp.hembed, fp.Ws - 1));
+			return std::min(sc * fp.HS + k, fp.W - 1);
+		};
+		int tw4 = 0, nemax4 = 0;
+		for (int nb = 1; nb <= pl->OW && ok; nb++) {
+			const int tw = (pl->OW + nb - 1) / nb;
+			int worst = 0, max_cols = 0;
+			for (int xa = 0; xa < pl->OW; xa += tw) {
+				const int xb = std::min(xa + tw, pl->OW);
+				const int E0 = 2 * hcol[xa].x + hgrid;
+				const int ne = 2 * (hcol[xb - 1].x + fp.NPh - hcol[xa].x);
+				const int c_lo = column_of(E0, 0) & ~3;
+				const int c_hi = std::min(fp.W, (column_of(E0, ne * fp.HS - 1) + 4) & ~3);
+				worst = std::max(worst, ne);
+				max_cols = std::max(max_cols, c_hi - c_lo);
+			}
+			if (worst * fp.HS <= wcols && max_cols * 4 <= pitch) {
+				tw4 = tw;
+				nemax4 = worst;
+				break;
+			}
+			if (tw <= 4)
+				break;
+		}
+		if (ok && tw4 > 0) {
+			pl->mma_cols = wcols;
+			pl->mma_tw = tw4;
+			pl->mma_nemax = nemax4;
+			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / 2 + 31) / 32) * 32);
+			const int stages = fp.VS <= 2 ? 8 : 4;
+			pl->smem_mma = (size_t) stages * 2 * fp.VS * pitch + (2 * stages + 4) * 8 +
+				(size_t) kV4Quads * ((size_t) pl->mma_nt * 2 * 16 + 16) + (size_t) 2 * K * (nemax4 / 2) * 8 +
+				(size_t) (fp.nhsets * fp.NPh + 256) * 4;
+			const size_t n_ch = vchunk.size() * sizeof(int2), n_bf = bfrag.size() * sizeof(uint4);
+			if (pl->smem_mma <= (wcols > 448 ? 226 : 113) * 1024) {
+				VB200_CUDA(domain, cudaMalloc(&pl->tables_mma, n_bf + n_ch));
+				VB200_CUDA(domain, cudaMemcpy(pl->tables_mma, bfrag.data(), n_bf, cudaMemcpyHostToDevice));
+				VB200_CUDA(domain, cudaMemcpy((char *) pl->tables_mma + n_bf, vchunk.data(), n_ch, cudaMemcpyHostToDevice));
+				fp.vbfrag = (const uint4 *) pl->tables_mma;
+				fp.vchunk = (const int2 *) ((char *) pl->tables_mma + n_bf);
+				pl->mma_ok = true;
+			}
+		}
+	}
+
 	/* upload tables as one block */
 	const size_t n_vrow = vrow.size() * sizeof(int2), n_hcol = hcol.size() * sizeof(int2);
 	const size_t n_vc = sv.coef.size() * 4, n_hc = shh.coef.size() * 4;
@@ -1850,6 +2038,8 @@ thumbnail_plan_destroy(ThumbnailPlanImpl *pl)
 {
 	if (pl->tables)
 		cudaFree(pl->tables);
+	if (pl->tables_mma)
+		cudaFree(pl->tables_mma);
 	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
 		if (pl->stage_in[i])
 			cudaFree(pl->stage_in[i]);

@@ -1,0 +1,371 @@
+/* thumbnail_fused_mma.cuh -- v4 of the fused thumbnail kernel (included by
+ * thumbnail_fused.cu inside its anonymous namespace, after v3).
+ *
+ * v3 is bound by the alu pipe, and 45% of its alu work is the reducev pass:
+ * 48 IDP.2A per thread per output row.  v4 hands exactly that sum to the
+ * integer tensor-core path (legacy mma.sync m16n8k32, u8 x s8 -> s32, exact):
+ *
+ *     D[colchan][y] = sum_k  data[colchan][k] * coef[k][y]
+ *
+ *   M = 16 column-channels (4 pixel columns x RGBA), K = 32 box-shrunk rows (a ring
+ *   of 8 "quads" = 4 rows byte-transposed into one register), N = 8 output rows.
+ *   The 13-bit reducev coefficients are split c = hi * 256 + lo (hi s8, lo u8): two
+ *   MMAs, recombined in s32, so the result is the same integer sum the reference
+ *   forms (reducev.cpp:461-471), then (sum + 2048) >> 12 and the clip as before.
+ *
+ * This is not a GEMM reformulation for its own sake: the tensor pipe is ~3% busy; it is
+ * used as a wide dot-product unit to take 3 alu instructions per input pixel off the
+ * pipe that bounds the kernel.  Everything else (premultiply, box sums, shrinkh,
+ * reduceh on the H warp, unpremultiply) is v3's arithmetic.
+ *
+ * Warp roles as v3:  V warps (2 adjacent input columns per thread) | H warp | P warp.
+ * Each V warp owns 64 columns end to end -- it writes the quads of its columns and
+ * runs the MMAs over them -- so the only synchronisation inside the V side is
+ * __syncwarp().
+ *
+ * Shared memory:
+ *   stages  [S][2 VS][PITCH]      raw RGBA rows by cp.async.bulk (a stage = 2 shrunk rows)
+ *   bars    full[S] empty[S] shfull[2] shempty[2]
+ *   quadbuf [8][NC][4] u32 (+16 B per quad slot: conflict-free A-fragment loads)
+ *   sh      [2][8][NEmax / 2] uint2  reducev + shrinkh output, v3's pair layout
+ *   hcoef, uscale
+ */
+
+constexpr int kV4Rows = 8;	/* output rows per chunk: N of the MMA */
+constexpr int kV4Quads = 8; /* quad ring: K / 4 */
+
+template <int VS>
+struct V4Stages {
+	static constexpr int value = VS <= 2 ? 8 : 4;
+};
+
+__device__ __forceinline__ void
+mma_u8s8(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+				 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+				 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void
+mma_u8u8(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
+{
+	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+				 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+				 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+/* (hi * 256 + lo) >> 12 clipped to 0..255; lo already carries the + 2048 */
+__device__ __forceinline__ int
+v4_finish(int hi, int lo)
+{
+	const int v = (hi * 256 + lo) >> VB200_INTERPOLATE_SHIFT;
+	return max(0, min(v, 255));
+}
+
+template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS>
+__global__ void __launch_bounds__(WCOLS / 2 + 64, WCOLS <= 448 ? 2 : 1)
+thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
+	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+
+	constexpr int K = kV4Rows;
+	constexpr int CPT = 2;
+	constexpr int S = V4Stages<VS>::value;
+	constexpr int PITCH = (WCOLS + 8) * 4;
+	constexpr int NPR = NP > 0 ? NP : 1;
+	constexpr int HSHIFT = HSQ == 2 ? 1 : HSQ == 4 ? 2 : 3;
+	constexpr int rows_per_stage = 2 * VS;
+	constexpr unsigned stage_bytes = (unsigned) rows_per_stage * PITCH;
+
+	const int NT = P.NT;	 /* V threads */
+	const int NC = NT * CPT; /* columns */
+	const int t = threadIdx.x;
+	const int NPh = NP > 0 ? NP : P.NPh;
+	const int shs = P.NEmax / 2; /* pairs per sh row */
+	const unsigned QS = (unsigned) NC * 16u + 16u; /* bytes per quad slot */
+
+	unsigned char *stages = smem_raw;
+	uint64_t *bars = (uint64_t *) (smem_raw + S * stage_bytes);
+	unsigned char *quadbuf = (unsigned char *) (bars + 2 * S + 4);
+	uint2 *sh = (uint2 *) (quadbuf + (size_t) kV4Quads * QS);
+	int *hcoef = (int *) (sh + (size_t) 2 * K * shs);
+	int *uscale = hcoef + P.nhsets * P.NPh;
+
+	const unsigned stages_s = smem_addr(stages);
+	const unsigned full_s = smem_addr(bars);
+	const unsigned empty_s = full_s + 8u * S;
+	const unsigned shfull_s = empty_s + 8u * S;
+	const unsigned shempty_s = shfull_s + 16u;
+
+	if (t == 0) {
+		for (int i = 0; i < S; i++) {
+			mbar_init(full_s + 8u * i, 1);
+			mbar_init(empty_s + 8u * i, NT / 32);
+		}
+		for (int i = 0; i < 2; i++) {
+			mbar_init(shfull_s + 8u * i, NT / 32);
+			mbar_init(shempty_s + 8u * i, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	for (int i = t; i < P.nhsets * P.NPh; i += blockDim.x)
+		hcoef[i] = P.hcoef[i];
+	if (PREMUL)
+		for (int i = t; i < 256; i += blockDim.x)
+			uscale[i] = i == 0 ? 0 : (int) __ddiv_rn(__dmul_rn(256.0, 255.0), (double) i);
+
+	const int xa = blockIdx.x * P.TW;
+	const int xb = min(xa + P.TW, P.OW);
+	const int y_begin = blockIdx.y * P.RPC;
+	const int y_end = min(y_begin + P.RPC, P.OH);
+	const int frame = frame0 + blockIdx.z;
+	const uint8_t *fin = in + (size_t) frame * in_frame_stride;
+	uint8_t *fout = out + (size_t) frame * out_frame_stride;
+
+	const int pair_h0 = __ldg(&P.hcol[xa]).x;
+	const int E0 = 2 * pair_h0 + P.hgrid;
+	const int NE = 2 * (__ldg(&P.hcol[xb - 1]).x + P.NPh - pair_h0);
+
+	auto column_of = [&](int tt) {
+		const int e = E0 + tt / HSQ;
+		const int k = tt - (tt / HSQ) * HSQ;
+		const int sc = max(0, min(e - P.hembed, P.Ws - 1));
+		return min(sc * HSQ + k, P.W - 1);
+	};
+	const int c_lo = column_of(0) & ~3;
+	const int c_hi = min(P.W, (column_of(NE * HSQ - 1) + 4) & ~3);
+	const unsigned row_bytes = (unsigned) (c_hi - c_lo) * 4u;
+	const int q_first = __ldg(&P.vchunk[y_begin / K]).x;
+
+	__syncthreads();
+
+	if (t >= NT + 32) {
+		/* ---------------- P: lane L copies row L of each stage (stage p = shrunk rows 2p, 2p + 1) */
+		const int lane = t - NT - 32;
+		const uint8_t *src0 = fin + (size_t) c_lo * 4;
+		const int j = lane / VS, k = lane - j * VS;
+		const bool copier = lane < rows_per_stage;
+		int s = 0;
+		unsigned phase = 0;
+		int pdone = 2 * q_first;
+		for (int ya = y_begin; ya < y_end; ya += K) {
+			const int P1 = 2 * __ldg(&P.vchunk[ya / K]).y + 1; /* last pair of the chunk's last quad */
+			for (int p = pdone; p <= P1; p++) {
+				mbar_wait(empty_s + 8u * s, phase ^ 1u);
+				if (lane == 0)
+					mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
+				__syncwarp();
+				if (copier) {
+					const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
+					const int row = min(sr * VS + k, P.H - 1);
+					bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * PITCH,
+						src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
+				}
+				if (++s == S) {
+					s = 0;
+					phase ^= 1u;
+				}
+			}
+			pdone = max(pdone, P1 + 1);
+		}
+		return;
+	}
+
+	if (t >= NT) {
+		/* ---------------- H: reduceh + unpremultiply + store, one warp (v3's) */
+		const int lane = t - NT;
+		const int bw = xb - xa;
+		int chunk = 0;
+		for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
+			const int yb = min(ya + K, y_end);
+			const int rows = yb - ya;
+			const int buf = chunk & 1;
+			const uint2 *shb = sh + (size_t) buf * K * shs;
+			mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
+			for (int idx = lane; idx < rows * bw; idx += 32) {
+				const int k = fast_div(idx, bw);
+				const int x = xa + (idx - k * bw);
+				const int2 hc = __ldg(&P.hcol[x]);
+				const uint2 *win = shb + k * shs + (hc.x - pair_h0);
+				const int *cfp = hcoef + hc.y * NPh;
+				int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+				if (NP > 0) {
+#pragma unroll
+					for (int kk = 0; kk < NPR; kk++) {
+						const uint2 w = win[kk];
+						const unsigned c = (unsigned) cfp[kk];
+						r = dp2a_lo(c, w.x, r);
+						b = dp2a_hi(c, w.x, b);
+						g = dp2a_lo(c, w.y, g);
+						a = dp2a_hi(c, w.y, a);
+					}
+				}
+				else
+					for (int kk = 0; kk < NPh; kk++) {
+						const uint2 w = win[kk];
+						const unsigned c = (unsigned) cfp[kk];
+						r = dp2a_lo(c, w.x, r);
+						b = dp2a_hi(c, w.x, b);
+						g = dp2a_lo(c, w.y, g);
+						a = dp2a_hi(c, w.y, a);
+					}
+				r = max(0, min(r >> VB200_INTERPOLATE_SHIFT, 255));
+				g = max(0, min(g >> VB200_INTERPOLATE_SHIFT, 255));
+				b = max(0, min(b >> VB200_INTERPOLATE_SHIFT, 255));
+				a = max(0, min(a >> VB200_INTERPOLATE_SHIFT, 255));
+				if (PREMUL) {
+					const int sc = uscale[a];
+					r = ((r * sc + 128) >> 8) & 0xff;
+					g = ((g * sc + 128) >> 8) & 0xff;
+					b = ((b * sc + 128) >> 8) & 0xff;
+				}
+				*(unsigned *) (fout + (size_t) (ya + k) * P.out_bpl + (size_t) x * 4) =
+					(unsigned) r | ((unsigned) g << 8) | ((unsigned) b << 16) | ((unsigned) a << 24);
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(shempty_s + 8u * buf);
+		}
+		return;
+	}
+
+	/* ---------------- V warps */
+	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - 2)) - c_lo) * 4u;
+	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
+	unsigned k16;
+	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
+	const unsigned amend2 = (unsigned) (VS / 2) * accm * 0x00010001u;
+	const int lane = t & 31;
+	const bool lane0 = lane == 0;
+	/* MMA fragment coordinates */
+	const int tig = lane & 3, g = lane >> 2, ch = g & 3, jj = g >> 2;
+	const int warp_col0 = (t & ~31) * CPT;
+	/* A loads: quad slot tig (+4), column warp_col0 + 8 tp + 4 jj + 2 T + h, channel ch */
+	const unsigned char *a_base = quadbuf + (size_t) tig * QS + (size_t) (warp_col0 + 4 * jj) * 16u + (unsigned) ch * 4u;
+	unsigned char *q_store = quadbuf + (size_t) (t * CPT) * 16u;
+	/* sh store: v3's pair layout, [rA rB bA bB gA gB aA aB] per column pair */
+	const int ch_off = ch == 0 ? 0 : ch == 1 ? 4 : ch == 2 ? 2 : 6;
+	const int warp_sx0 = warp_col0 / HSQ;
+
+	int s = 0;
+	unsigned phase = 0;
+	int qdone = q_first;
+	int chunk = 0;
+
+	for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
+		const int q1 = __ldg(&P.vchunk[ya / K]).y;
+
+		for (int q = qdone; q <= q1; q++) {
+			unsigned rb[4][CPT], ga[4][CPT];
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+#pragma unroll
+				for (int i = 0; i < CPT; i++)
+					rb[r][i] = ga[r][i] = amend2;
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				const unsigned soff = (unsigned) s * stage_bytes;
+				uint2 pa[VS], pb[VS];
+				mbar_wait(full_s + 8u * s, phase);
+#pragma unroll
+				for (int k = 0; k < VS; k++) {
+					pa[k] = *(const uint2 *) (my_cols + soff + k * PITCH);
+					pb[k] = *(const uint2 *) (my_cols + soff + (VS + k) * PITCH);
+				}
+				__syncwarp();
+				if (lane0)
+					mbar_arrive(empty_s + 8u * s);
+#pragma unroll
+				for (int k = 0; k < VS; k++) {
+					accumulate_pixel_m<PREMUL>(pa[k].x, accm, k16, rb[2 * half][0], ga[2 * half][0]);
+					accumulate_pixel_m<PREMUL>(pa[k].y, accm, k16, rb[2 * half][1], ga[2 * half][1]);
+					accumulate_pixel_m<PREMUL>(pb[k].x, accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
+					accumulate_pixel_m<PREMUL>(pb[k].y, accm, k16, rb[2 * half + 1][1], ga[2 * half + 1][1]);
+				}
+				if (++s == S) {
+					s = 0;
+					phase ^= 1u;
+				}
+			}
+			/* box averages are bytes 1 and 3 of each lane word: transpose 4 rows into quads */
+#pragma unroll
+			for (int i = 0; i < CPT; i++) {
+				const unsigned rb01 = __byte_perm(rb[0][i], rb[1][i], 0x7351); /* [r0 r1 b0 b1] */
+				const unsigned rb23 = __byte_perm(rb[2][i], rb[3][i], 0x7351);
+				const unsigned ga01 = __byte_perm(ga[0][i], ga[1][i], 0x7351);
+				const unsigned ga23 = __byte_perm(ga[2][i], ga[3][i], 0x7351);
+				uint4 w;
+				w.x = __byte_perm(rb01, rb23, 0x5410); /* r rows 0..3 */
+				w.y = __byte_perm(ga01, ga23, 0x5410); /* g */
+				w.z = __byte_perm(rb01, rb23, 0x7632); /* b */
+				w.w = __byte_perm(ga01, ga23, 0x7632); /* a */
+				*(uint4 *) (q_store + (size_t) (q & (kV4Quads - 1)) * QS + i * 16) = w;
+			}
+		}
+		qdone = max(qdone, q1 + 1);
+		__syncwarp();
+
+		/* reducev on the tensor pipe + in-thread shrinkh; rows go to sh[buf] once the H warp has released it */
+		const int buf = chunk & 1;
+		const uint4 bf = __ldg(&P.vbfrag[(size_t) (ya / K) * 32 + lane]); /* {hi b0, hi b1, lo b0, lo b1} */
+		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
+		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * K * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
+#pragma unroll 2
+		for (int tp = 0; tp < 8; tp++) {
+			unsigned a[2][4];
+			int dh[2][4], dl[2][4];
+#pragma unroll
+			for (int T = 0; T < 2; T++) {
+				const unsigned char *ap = a_base + tp * 128 + T * 32;
+				a[T][0] = *(const unsigned *) (ap);
+				a[T][1] = *(const unsigned *) (ap + 16);
+				a[T][2] = *(const unsigned *) (ap + 4 * (size_t) QS);
+				a[T][3] = *(const unsigned *) (ap + 4 * (size_t) QS + 16);
+			}
+#pragma unroll
+			for (int T = 0; T < 2; T++) {
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					dh[T][i] = 0;
+					dl[T][i] = VB200_INTERPOLATE_SCALE >> 1;
+				}
+				mma_u8s8(dh[T], a[T], bf.x, bf.y);
+				mma_u8u8(dl[T], a[T], bf.z, bf.w);
+			}
+			/* d[T][r]: column h = 0, output row 2 tig + r;  d[T][2 + r]: column h = 1 */
+#pragma unroll
+			for (int r = 0; r < 2; r++) {
+				const int v00 = v4_finish(dh[0][r], dl[0][r]);
+				const int v01 = v4_finish(dh[0][2 + r], dl[0][2 + r]);
+				const int v10 = v4_finish(dh[1][r], dl[1][r]);
+				const int v11 = v4_finish(dh[1][2 + r], dl[1][2 + r]);
+				if (HSQ == 2) {
+					/* two complete boxes: columns (4 jj, 4 jj + 1) and (4 jj + 2, 4 jj + 3) */
+					const int sx = warp_sx0 + tp * 4 + 2 * jj;
+					if (sx < NE) {
+						unsigned char *d = shb + (size_t) r * shs * 8 + (sx >> 1) * 8;
+						d[0] = (unsigned char) ((v00 + v01 + 1) >> 1);
+						d[1] = (unsigned char) ((v10 + v11 + 1) >> 1);
+					}
+				}
+				else if (HSQ == 4) {
+					const int sx = warp_sx0 + tp * 2 + jj;
+					if (sx < NE)
+						shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((v00 + v01 + v10 + v11 + 2) >> 2);
+				}
+				else {
+					int sum = v00 + v01 + v10 + v11;
+					sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+					const int sx = warp_sx0 + tp;
+					if (jj == 0 && sx < NE)
+						shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((sum + 4) >> HSHIFT);
+				}
+			}
+		}
+		__syncwarp();
+		if (lane0)
+			mbar_arrive(shfull_s + 8u * buf);
+	}
+}
