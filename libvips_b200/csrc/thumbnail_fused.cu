@@ -38,6 +38,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h> /* CUtensorMap + the cuTensorMapEncodeTiled prototype; resolved at run time, libcuda is not linked */
+
 #include "vb200_internal.h"
 
 namespace vb200 {
@@ -425,6 +427,26 @@ mbar_wait(unsigned bar, unsigned parity)
 					 : "r"(bar), "r"(parity)
 					 : "memory");
 	} while (!done);
+}
+
+/* the same wait for a warp that expects to idle (producer, H warp): back off between
+ * polls so that the spin does not take issue slots from the warps doing the arithmetic
+ */
+__device__ __forceinline__ void
+mbar_wait_idle(unsigned bar, unsigned parity, unsigned ns)
+{
+	unsigned done;
+	for (;;) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+					 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+					 "selp.u32 %0, 1, 0, p;\n\t}"
+					 : "=r"(done)
+					 : "r"(bar), "r"(parity)
+					 : "memory");
+		if (done)
+			break;
+		__nanosleep(ns);
+	}
 }
 
 __device__ __forceinline__ void
@@ -1364,7 +1386,7 @@ struct ThumbnailPlanImpl {
 	size_t smem_tma3 = 0;
 	/* v4: reducev on the integer tensor pipe */
 	bool mma_ok = false;
-	int mma_cols = 0, mma_tw = 0, mma_nt = 0, mma_nemax = 0;
+	int mma_cols = 0, mma_cpt = 2, mma_tw = 0, mma_nt = 0, mma_nemax = 0;
 	size_t smem_mma = 0;
 	void *tables_mma = nullptr;
 	/* host pump */
@@ -1512,16 +1534,55 @@ launch_tma3(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, co
 	return 0;
 }
 
-template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS>
+/* A tiled tensor map over the batch: u64 elements (2 pixels), dims {W / 2, H, frames}, box
+ * {(WCOLS + 8) / 2, rows, 1}: one cp.async.bulk.tensor per TMA stage.  Returns false when
+ * the driver entry point or the geometry is not usable; the kernel then copies row by row.
+ */
+bool
+make_stage_tensor_map(CUtensorMap *tm, const void *in, int W, int H, size_t in_bpl, size_t frame_stride, int frames,
+	int box_cols, int box_rows)
+{
+	typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+		const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+		CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn encode = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+			qres == cudaDriverEntryPointSuccess)
+			encode = (encode_fn) fn;
+		cudaGetLastError();
+	}
+	if (!encode || getenv("VB200_NO_TENSORMAP"))
+		return false;
+	if ((W & 1) || (in_bpl % 16) || (frame_stride % 16) || ((uintptr_t) in % 16) || box_cols / 2 > 256 || box_rows > 256)
+		return false;
+	const cuuint64_t dims[3] = {(cuuint64_t) W / 2, (cuuint64_t) H, (cuuint64_t) frames};
+	const cuuint64_t strides[2] = {(cuuint64_t) in_bpl, (cuuint64_t) frame_stride};
+	const cuuint32_t box[3] = {(cuuint32_t) box_cols / 2, (cuuint32_t) box_rows, 1};
+	const cuuint32_t estr[3] = {1, 1, 1};
+	return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(in), dims, strides, box, estr,
+			   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+			   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT>
 int
 launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, dim3 grid, cudaStream_t s)
 {
-	auto kern = thumbnail_fused_mma_kernel<VS, NP, PREMUL, HSQ, WCOLS>;
+	auto kern = thumbnail_fused_mma_kernel<VS, NP, PREMUL, HSQ, WCOLS, CPT>;
 	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_mma));
+	CUtensorMap tm;
+	memset(&tm, 0, sizeof(tm));
+	const int use_tmap = make_stage_tensor_map(&tm, in, fp.W, fp.H, fp.in_bpl, in_stride, n, WCOLS + 8, 2 * VS) ? 1 : 0;
 	for (int f0 = 0; f0 < n; f0 += 32768) {
 		grid.z = std::min(32768, n - f0);
-		kern<<<grid, fp.NT + 64, pl->smem_mma, s>>>(fp, (const uint8_t *) in, in_stride, (uint8_t *) out, out_stride, f0);
+		kern<<<grid, fp.NT + 64, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
+			out_stride, f0);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
 			return cuda_fail(domain, e, "thumbnail_fused_mma_kernel launch");
@@ -1531,7 +1592,7 @@ launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 }
 
 /* the instantiated corner of v4: box 2 / 4 vertically, 2 / 4 / 8 horizontally */
-template <bool PREMUL, int WCOLS>
+template <bool PREMUL, int WCOLS, int CPT>
 int
 launch_mma_w(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t is, void *out,
 	size_t os, int n, dim3 grid, cudaStream_t s, bool *handled)
@@ -1540,7 +1601,7 @@ launch_mma_w(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 	const int np = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
 #define V4(VS_, NP_, HS_) \
 	if (fp.VS == VS_ && np == NP_ && fp.HS == HS_) \
-		return launch_mma_t<VS_, NP_, PREMUL, HS_, WCOLS>(domain, pl, fp, in, is, out, os, n, grid, s);
+		return launch_mma_t<VS_, NP_, PREMUL, HS_, WCOLS, CPT>(domain, pl, fp, in, is, out, os, n, grid, s);
 	V4(4, 6, 4) V4(4, 7, 4) V4(2, 6, 2) V4(2, 7, 2)
 	V4(4, 0, 4) V4(2, 0, 2) V4(4, 0, 2) V4(2, 0, 4) V4(4, 0, 8) V4(2, 0, 8)
 #undef V4
@@ -1564,11 +1625,11 @@ launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 		rpc = ((rpc / 2 + K - 1) / K) * K;
 	fp.RPC = rpc;
 	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
-	if (pl->mma_cols > 448)
-		return pl->premul ? launch_mma_w<true, 768>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
-						  : launch_mma_w<false, 768>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
-	return pl->premul ? launch_mma_w<true, 384>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
-					  : launch_mma_w<false, 384>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+	if (pl->mma_cpt == 1)
+		return pl->premul ? launch_mma_w<true, 384, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+						  : launch_mma_w<false, 384, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+	return pl->premul ? launch_mma_w<true, 384, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+					  : launch_mma_w<false, 384, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
 }
 
 int
@@ -1849,7 +1910,9 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		}
 		/* band width: the fewest bands whose widest one fits the column budget */
 		const char *ev = getenv("VB200_V4_COLS");
-		const int wcols = ev && atoi(ev) > 448 ? 768 : 384;
+		const int wcols = 384;
+		(void) ev;
+		pl->mma_cpt = getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 1 ? 1 : 2;
 		const int pitch = (wcols + 8) * 4;
 		auto column_of = [&](int E0, int tt) {
 			const int e = E0 + tt / fp.HS;
@@ -1882,10 +1945,11 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			pl->mma_cols = wcols;
 			pl->mma_tw = tw4;
 			pl->mma_nemax = nemax4;
-			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / 2 + 31) / 32) * 32);
+			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
 			const int stages = fp.VS <= 2 ? 8 : 4;
 			pl->smem_mma = (size_t) stages * 2 * fp.VS * pitch + (2 * stages + 4) * 8 +
-				(size_t) kV4Quads * ((size_t) pl->mma_nt * 2 * 16 + 16) + (size_t) 2 * K * (nemax4 / 2) * 8 +
+				(size_t) kV4Quads * ((size_t) pl->mma_nt * pl->mma_cpt * 16 + 16) +
+				(size_t) 2 * K * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +
 				(size_t) (fp.nhsets * fp.NPh + 256) * 4;
 			const size_t n_ch = vchunk.size() * sizeof(int2), n_bf = bfrag.size() * sizeof(uint4);
 			if (pl->smem_mma <= (wcols > 448 ? 226 : 113) * 1024) {

@@ -57,21 +57,23 @@ mma_u8u8(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1)
 
 /* (hi * 256 + lo) >> 12 clipped to 0..255; lo already carries the + 2048 */
 __device__ __forceinline__ int
-v4_finish(int hi, int lo)
+v4_finish(int hi, int lo, int k20)
 {
-	const int v = (hi * 256 + lo) >> VB200_INTERPOLATE_SHIFT;
+	/* >> 12 as mulhi by 1 << 20 (k20, held in a register so that it stays an IMAD.HI): the alu
+	 * pipe is the one that is short
+	 */
+	const int v = __mulhi(hi * 256 + lo, k20);
 	return max(0, min(v, 255));
 }
 
-template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS>
-__global__ void __launch_bounds__(WCOLS / 2 + 64, WCOLS <= 448 ? 2 : 1)
-thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t *__restrict__ in, size_t in_frame_stride,
-	uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
+template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT>
+__global__ void __launch_bounds__(WCOLS / CPT + 64, WCOLS <= 448 ? 2 : 1)
+thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, int use_tmap,
+	const uint8_t *__restrict__ in, size_t in_frame_stride, uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 
 	constexpr int K = kV4Rows;
-	constexpr int CPT = 2;
 	constexpr int S = V4Stages<VS>::value;
 	constexpr int PITCH = (WCOLS + 8) * 4;
 	constexpr int NPR = NP > 0 ? NP : 1;
@@ -83,7 +85,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	const int NC = NT * CPT; /* columns */
 	const int t = threadIdx.x;
 	const int NPh = NP > 0 ? NP : P.NPh;
-	const int shs = P.NEmax / 2; /* pairs per sh row */
+	const int shs = NC / HSQ / 2; /* pairs per sh row: every V thread has a slot, so the epilogue stores need no guard */
 	const unsigned QS = (unsigned) NC * 16u + 16u; /* bytes per quad slot */
 
 	unsigned char *stages = smem_raw;
@@ -154,14 +156,30 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 			const int P1 = 2 * __ldg(&P.vchunk[ya / K]).y + 1; /* last pair of the chunk's last quad */
 			for (int p = pdone; p <= P1; p++) {
 				mbar_wait(empty_s + 8u * s, phase ^ 1u);
-				if (lane == 0)
-					mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
-				__syncwarp();
-				if (copier) {
-					const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
-					const int row = min(sr * VS + k, P.H - 1);
-					bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * PITCH,
-						src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
+				/* interior stage: its 2 VS input rows are consecutive and none is an edge replica --
+				 * one tiled-TMA box {PITCH bytes, 2 VS rows} instead of 2 VS row copies
+				 */
+				const int sr0 = 2 * p - P.vembed;
+				const bool interior = use_tmap && sr0 >= 0 && sr0 + 1 <= P.Hs - 1 && (sr0 + 2) * VS <= P.H;
+				if (interior) {
+					if (lane == 0) {
+						mbar_expect_tx(full_s + 8u * s, stage_bytes);
+						asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+										 stages_s + (unsigned) s * stage_bytes),
+									 "l"(&tmap), "r"(c_lo >> 1), "r"(sr0 * VS), "r"(frame), "r"(full_s + 8u * s)
+									 : "memory");
+					}
+				}
+				else {
+					if (lane == 0)
+						mbar_expect_tx(full_s + 8u * s, (unsigned) rows_per_stage * row_bytes);
+					__syncwarp();
+					if (copier) {
+						const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
+						const int row = min(sr * VS + k, P.H - 1);
+						bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * PITCH,
+							src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
+					}
 				}
 				if (++s == S) {
 					s = 0;
@@ -232,10 +250,13 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 	}
 
 	/* ---------------- V warps */
-	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - 2)) - c_lo) * 4u;
+	/* CPT 2: the thread's two columns are adjacent and start on an even column (one 64-bit LDS per row) */
+	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - CPT)) - c_lo) * 4u;
 	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
 	unsigned k16;
 	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
+	int k20;
+	asm volatile("mov.u32 %0, 0x100000;" : "=r"(k20));
 	const unsigned amend2 = (unsigned) (VS / 2) * accm * 0x00010001u;
 	const int lane = t & 31;
 	const bool lane0 = lane == 0;
@@ -267,22 +288,40 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 #pragma unroll
 			for (int half = 0; half < 2; half++) {
 				const unsigned soff = (unsigned) s * stage_bytes;
-				uint2 pa[VS], pb[VS];
 				mbar_wait(full_s + 8u * s, phase);
+				if (CPT == 2) {
+					uint2 pa[VS], pb[VS];
 #pragma unroll
-				for (int k = 0; k < VS; k++) {
-					pa[k] = *(const uint2 *) (my_cols + soff + k * PITCH);
-					pb[k] = *(const uint2 *) (my_cols + soff + (VS + k) * PITCH);
+					for (int k = 0; k < VS; k++) {
+						pa[k] = *(const uint2 *) (my_cols + soff + k * PITCH);
+						pb[k] = *(const uint2 *) (my_cols + soff + (VS + k) * PITCH);
+					}
+					__syncwarp();
+					if (lane0)
+						mbar_arrive(empty_s + 8u * s);
+#pragma unroll
+					for (int k = 0; k < VS; k++) {
+						accumulate_pixel_m<PREMUL>(pa[k].x, accm, k16, rb[2 * half][0], ga[2 * half][0]);
+						accumulate_pixel_m<PREMUL>(pa[k].y, accm, k16, rb[2 * half][CPT - 1], ga[2 * half][CPT - 1]);
+						accumulate_pixel_m<PREMUL>(pb[k].x, accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
+						accumulate_pixel_m<PREMUL>(pb[k].y, accm, k16, rb[2 * half + 1][CPT - 1], ga[2 * half + 1][CPT - 1]);
+					}
 				}
-				__syncwarp();
-				if (lane0)
-					mbar_arrive(empty_s + 8u * s);
+				else {
+					unsigned pa[VS], pb[VS];
 #pragma unroll
-				for (int k = 0; k < VS; k++) {
-					accumulate_pixel_m<PREMUL>(pa[k].x, accm, k16, rb[2 * half][0], ga[2 * half][0]);
-					accumulate_pixel_m<PREMUL>(pa[k].y, accm, k16, rb[2 * half][1], ga[2 * half][1]);
-					accumulate_pixel_m<PREMUL>(pb[k].x, accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
-					accumulate_pixel_m<PREMUL>(pb[k].y, accm, k16, rb[2 * half + 1][1], ga[2 * half + 1][1]);
+					for (int k = 0; k < VS; k++) {
+						pa[k] = *(const unsigned *) (my_cols + soff + k * PITCH);
+						pb[k] = *(const unsigned *) (my_cols + soff + (VS + k) * PITCH);
+					}
+					__syncwarp();
+					if (lane0)
+						mbar_arrive(empty_s + 8u * s);
+#pragma unroll
+					for (int k = 0; k < VS; k++) {
+						accumulate_pixel_m<PREMUL>(pa[k], accm, k16, rb[2 * half][0], ga[2 * half][0]);
+						accumulate_pixel_m<PREMUL>(pb[k], accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
+					}
 				}
 				if (++s == S) {
 					s = 0;
@@ -313,7 +352,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
 		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * K * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
 #pragma unroll 2
-		for (int tp = 0; tp < 8; tp++) {
+		for (int tp = 0; tp < 4 * CPT; tp++) {
 			unsigned a[2][4];
 			int dh[2][4], dl[2][4];
 #pragma unroll
@@ -337,29 +376,26 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const uint8_t 
 			/* d[T][r]: column h = 0, output row 2 tig + r;  d[T][2 + r]: column h = 1 */
 #pragma unroll
 			for (int r = 0; r < 2; r++) {
-				const int v00 = v4_finish(dh[0][r], dl[0][r]);
-				const int v01 = v4_finish(dh[0][2 + r], dl[0][2 + r]);
-				const int v10 = v4_finish(dh[1][r], dl[1][r]);
-				const int v11 = v4_finish(dh[1][2 + r], dl[1][2 + r]);
+				const int v00 = v4_finish(dh[0][r], dl[0][r], k20);
+				const int v01 = v4_finish(dh[0][2 + r], dl[0][2 + r], k20);
+				const int v10 = v4_finish(dh[1][r], dl[1][r], k20);
+				const int v11 = v4_finish(dh[1][2 + r], dl[1][2 + r], k20);
 				if (HSQ == 2) {
 					/* two complete boxes: columns (4 jj, 4 jj + 1) and (4 jj + 2, 4 jj + 3) */
 					const int sx = warp_sx0 + tp * 4 + 2 * jj;
-					if (sx < NE) {
-						unsigned char *d = shb + (size_t) r * shs * 8 + (sx >> 1) * 8;
-						d[0] = (unsigned char) ((v00 + v01 + 1) >> 1);
-						d[1] = (unsigned char) ((v10 + v11 + 1) >> 1);
-					}
+					unsigned char *d = shb + (size_t) r * shs * 8 + (sx >> 1) * 8;
+					d[0] = (unsigned char) ((v00 + v01 + 1) >> 1);
+					d[1] = (unsigned char) ((v10 + v11 + 1) >> 1);
 				}
 				else if (HSQ == 4) {
 					const int sx = warp_sx0 + tp * 2 + jj;
-					if (sx < NE)
-						shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((v00 + v01 + v10 + v11 + 2) >> 2);
+					shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((v00 + v01 + v10 + v11 + 2) >> 2);
 				}
 				else {
 					int sum = v00 + v01 + v10 + v11;
 					sum += __shfl_xor_sync(0xffffffffu, sum, 16);
 					const int sx = warp_sx0 + tp;
-					if (jj == 0 && sx < NE)
+					if (jj == 0)
 						shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((sum + 4) >> HSHIFT);
 				}
 			}
