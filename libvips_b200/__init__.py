@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libvb200.so")
+_LIB_PATH = os.environ.get("VB200_LIB") or os.path.join(_HERE, "libvb200.so")  # VB200_LIB: tuning builds (tools/build_variant.sh)
 _lib = None
 
 HOST, DEVICE = 0, 1

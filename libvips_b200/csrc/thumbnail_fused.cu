@@ -558,6 +558,39 @@ accumulate_pixel_m(unsigned x, unsigned m, unsigned k16, unsigned &rb, unsigned 
 	}
 }
 
+/* The same sums on the half2 adder.  A 16-bit lane holding an integer below 1024 IS an fp16
+ * denormal (value n * 2^-24), denormals and the first normal binade share one spacing, so
+ * add.f16x2 (no .ftz) adds the lanes as integers, exactly, while a lane stays below 2048 --
+ * and a box of up to 8 bytes + its rounding amend does.  HADD2 keeps the accumulation off
+ * both the alu pipe and the IMAD half of the fma pipe.
+ */
+__device__ __forceinline__ unsigned
+hadd2_lanes(unsigned a, unsigned b)
+{
+	unsigned d;
+	asm("add.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+	return d;
+}
+
+template <bool PREMUL>
+__device__ __forceinline__ void
+accumulate_pixel_h(unsigned x, unsigned k16, unsigned &rb, unsigned &ga)
+{
+	if (PREMUL) {
+		unsigned t0;
+		asm("lop3.b32 %0, %1, 0xff000000, %2, 0xea;" : "=r"(t0) : "r"(x), "r"(k16));
+		const unsigned s = __umulhi(t0, 257u);
+		const unsigned trb = (x & 0x00ff00ffu) * s + 0x00800080u;
+		const unsigned tg = (x & 0x0000ff00u) * s + 0x00008000u;
+		rb = hadd2_lanes(rb, __byte_perm(trb, 0, 0x4341));
+		ga = hadd2_lanes(ga, __byte_perm(tg, x, 0x3732));
+	}
+	else {
+		rb = hadd2_lanes(rb, x & 0x00ff00ffu);
+		ga = hadd2_lanes(ga, __byte_perm(x, 0, 0x4341));
+	}
+}
+
 /* lanes hold (sum + VS / 2) * 256 / VS: the averages are bytes 1 and 3 */
 __device__ __forceinline__ unsigned
 average_pair_m(unsigned lanesA, unsigned lanesB)
@@ -1386,7 +1419,7 @@ struct ThumbnailPlanImpl {
 	size_t smem_tma3 = 0;
 	/* v4: reducev on the integer tensor pipe */
 	bool mma_ok = false;
-	int mma_cols = 0, mma_cpt = 2, mma_tw = 0, mma_nt = 0, mma_nemax = 0;
+	int mma_cols = 0, mma_cpt = 1, mma_tw = 0, mma_nt = 0, mma_nemax = 0;
 	size_t smem_mma = 0;
 	void *tables_mma = nullptr;
 	/* host pump */
@@ -1626,10 +1659,10 @@ launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 	fp.RPC = rpc;
 	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
 	if (pl->mma_cpt == 1)
-		return pl->premul ? launch_mma_w<true, 384, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
-						  : launch_mma_w<false, 384, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
-	return pl->premul ? launch_mma_w<true, 384, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
-					  : launch_mma_w<false, 384, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+		return pl->premul ? launch_mma_w<true, VB200_V4_COLS, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+						  : launch_mma_w<false, VB200_V4_COLS, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
+	return pl->premul ? launch_mma_w<true, VB200_V4_COLS, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+					  : launch_mma_w<false, VB200_V4_COLS, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
 }
 
 int
@@ -1910,9 +1943,9 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		}
 		/* band width: the fewest bands whose widest one fits the column budget */
 		const char *ev = getenv("VB200_V4_COLS");
-		const int wcols = 384;
+		const int wcols = VB200_V4_COLS;
 		(void) ev;
-		pl->mma_cpt = getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 1 ? 1 : 2;
+		pl->mma_cpt = getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 2 ? 2 : 1; /* columns per V thread */
 		const int pitch = (wcols + 8) * 4;
 		auto column_of = [&](int E0, int tt) {
 			const int e = E0 + tt / fp.HS;
@@ -1920,10 +1953,15 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			const int sc = std::max(0, std::min(e - fp.hembed, fp.Ws - 1));
 			return std::min(sc * fp.HS + k, fp.W - 1);
 		};
+		/* band width: the one that needs the fewest V warps over a frame row (warps past a band's last
+		 * column exit at once, so a narrow last band is cheap); ties go to the wider band
+		 */
 		int tw4 = 0, nemax4 = 0;
-		for (int nb = 1; nb <= pl->OW && ok; nb++) {
-			const int tw = (pl->OW + nb - 1) / nb;
+		long best_cost = LONG_MAX;
+		const int cols_per_warp = 32 * pl->mma_cpt;
+		for (int tw = std::min(pl->OW, 256); tw >= 2 && ok; tw--) {
 			int worst = 0, max_cols = 0;
+			long cost = 0;
 			for (int xa = 0; xa < pl->OW; xa += tw) {
 				const int xb = std::min(xa + tw, pl->OW);
 				const int E0 = 2 * hcol[xa].x + hgrid;
@@ -1932,21 +1970,20 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 				const int c_hi = std::min(fp.W, (column_of(E0, ne * fp.HS - 1) + 4) & ~3);
 				worst = std::max(worst, ne);
 				max_cols = std::max(max_cols, c_hi - c_lo);
+				cost += (ne * fp.HS + cols_per_warp - 1) / cols_per_warp + 1; /* + the H / P warps' share */
 			}
-			if (worst * fp.HS <= wcols && max_cols * 4 <= pitch) {
+			if (worst * fp.HS <= wcols && max_cols * 4 <= pitch && cost < best_cost) {
+				best_cost = cost;
 				tw4 = tw;
 				nemax4 = worst;
-				break;
 			}
-			if (tw <= 4)
-				break;
 		}
 		if (ok && tw4 > 0) {
 			pl->mma_cols = wcols;
 			pl->mma_tw = tw4;
 			pl->mma_nemax = nemax4;
 			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
-			const int stages = fp.VS <= 2 ? 8 : 4;
+			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
 			pl->smem_mma = (size_t) stages * 2 * fp.VS * pitch + (2 * stages + 4) * 8 +
 				(size_t) kV4Quads * ((size_t) pl->mma_nt * pl->mma_cpt * 16 + 16) +
 				(size_t) 2 * K * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +

@@ -34,9 +34,33 @@
 constexpr int kV4Rows = 8;	/* output rows per chunk: N of the MMA */
 constexpr int kV4Quads = 8; /* quad ring: K / 4 */
 
+/* tuning knobs (compile time): columns per CTA and TMA stages for the VS 4 case */
+#ifndef VB200_V4_COLS
+#define VB200_V4_COLS 384
+#endif
+#ifndef VB200_V4_STAGES
+#define VB200_V4_STAGES 4
+#endif
+
+/* timing experiment only: VB200_EXP_NOPREMUL drops the premultiply arithmetic (wrong pixels) */
+#ifndef VB200_V4_HADD2
+#define VB200_V4_HADD2 1 /* box sums on the half2 adder (hadd2_lanes) */
+#endif
+#ifdef VB200_EXP_NOPREMUL
+#define V4_ACC_PREMUL false
+#else
+#define V4_ACC_PREMUL PREMUL
+#endif
+
+#if VB200_V4_HADD2
+#define V4_ACC(x, rb, ga) accumulate_pixel_h<V4_ACC_PREMUL>(x, k16, rb, ga)
+#else
+#define V4_ACC(x, rb, ga) accumulate_pixel_m<V4_ACC_PREMUL>(x, accm, k16, rb, ga)
+#endif
+
 template <int VS>
 struct V4Stages {
-	static constexpr int value = VS <= 2 ? 8 : 4;
+	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
 };
 
 __device__ __forceinline__ void
@@ -101,17 +125,6 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	const unsigned shfull_s = empty_s + 8u * S;
 	const unsigned shempty_s = shfull_s + 16u;
 
-	if (t == 0) {
-		for (int i = 0; i < S; i++) {
-			mbar_init(full_s + 8u * i, 1);
-			mbar_init(empty_s + 8u * i, NT / 32);
-		}
-		for (int i = 0; i < 2; i++) {
-			mbar_init(shfull_s + 8u * i, NT / 32);
-			mbar_init(shempty_s + 8u * i, 1);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
 	for (int i = t; i < P.nhsets * P.NPh; i += blockDim.x)
 		hcoef[i] = P.hcoef[i];
 	if (PREMUL)
@@ -140,7 +153,20 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	const int c_hi = min(P.W, (column_of(NE * HSQ - 1) + 4) & ~3);
 	const unsigned row_bytes = (unsigned) (c_hi - c_lo) * 4u;
 	const int q_first = __ldg(&P.vchunk[y_begin / K]).x;
+	/* V warps whose columns all lie beyond this band's last column do not run at all */
+	const int NTa = min(NT, ((NE * HSQ + 32 * CPT - 1) / (32 * CPT)) * 32);
 
+	if (t == 0) {
+		for (int i = 0; i < S; i++) {
+			mbar_init(full_s + 8u * i, 1);
+			mbar_init(empty_s + 8u * i, NTa / 32);
+		}
+		for (int i = 0; i < 2; i++) {
+			mbar_init(shfull_s + 8u * i, NTa / 32);
+			mbar_init(shempty_s + 8u * i, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	__syncthreads();
 
 	if (t >= NT + 32) {
@@ -250,6 +276,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	}
 
 	/* ---------------- V warps */
+	if (t >= NTa)
+		return;
 	/* CPT 2: the thread's two columns are adjacent and start on an even column (one 64-bit LDS per row) */
 	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - CPT)) - c_lo) * 4u;
 	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
@@ -257,7 +285,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
 	int k20;
 	asm volatile("mov.u32 %0, 0x100000;" : "=r"(k20));
-	const unsigned amend2 = (unsigned) (VS / 2) * accm * 0x00010001u;
+	const unsigned amend2 = (unsigned) (VS / 2) * (VB200_V4_HADD2 ? 1u : accm) * 0x00010001u;
 	const int lane = t & 31;
 	const bool lane0 = lane == 0;
 	/* MMA fragment coordinates */
@@ -301,10 +329,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 						mbar_arrive(empty_s + 8u * s);
 #pragma unroll
 					for (int k = 0; k < VS; k++) {
-						accumulate_pixel_m<PREMUL>(pa[k].x, accm, k16, rb[2 * half][0], ga[2 * half][0]);
-						accumulate_pixel_m<PREMUL>(pa[k].y, accm, k16, rb[2 * half][CPT - 1], ga[2 * half][CPT - 1]);
-						accumulate_pixel_m<PREMUL>(pb[k].x, accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
-						accumulate_pixel_m<PREMUL>(pb[k].y, accm, k16, rb[2 * half + 1][CPT - 1], ga[2 * half + 1][CPT - 1]);
+						V4_ACC(pa[k].x, rb[2 * half][0], ga[2 * half][0]);
+						V4_ACC(pa[k].y, rb[2 * half][CPT - 1], ga[2 * half][CPT - 1]);
+						V4_ACC(pb[k].x, rb[2 * half + 1][0], ga[2 * half + 1][0]);
+						V4_ACC(pb[k].y, rb[2 * half + 1][CPT - 1], ga[2 * half + 1][CPT - 1]);
 					}
 				}
 				else {
@@ -319,8 +347,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 						mbar_arrive(empty_s + 8u * s);
 #pragma unroll
 					for (int k = 0; k < VS; k++) {
-						accumulate_pixel_m<PREMUL>(pa[k], accm, k16, rb[2 * half][0], ga[2 * half][0]);
-						accumulate_pixel_m<PREMUL>(pb[k], accm, k16, rb[2 * half + 1][0], ga[2 * half + 1][0]);
+						V4_ACC(pa[k], rb[2 * half][0], ga[2 * half][0]);
+						V4_ACC(pb[k], rb[2 * half + 1][0], ga[2 * half + 1][0]);
 					}
 				}
 				if (++s == S) {
@@ -331,6 +359,14 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 			/* box averages are bytes 1 and 3 of each lane word: transpose 4 rows into quads */
 #pragma unroll
 			for (int i = 0; i < CPT; i++) {
+				if (VB200_V4_HADD2) {
+					/* plain sums (HADD2): scale them here, one IMAD per word instead of one per pixel */
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						rb[r][i] *= accm;
+						ga[r][i] *= accm;
+					}
+				}
 				const unsigned rb01 = __byte_perm(rb[0][i], rb[1][i], 0x7351); /* [r0 r1 b0 b1] */
 				const unsigned rb23 = __byte_perm(rb[2][i], rb[3][i], 0x7351);
 				const unsigned ga01 = __byte_perm(ga[0][i], ga[1][i], 0x7351);
