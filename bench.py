@@ -29,6 +29,10 @@ BANDS = 4
 TARGET = 512
 MPIX_PER_FRAME = W * H / 1e6
 METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per 4096x4096 frame, from the
+# committed `ncu --set full` capture (a launch of 128 frames: 8.6373 GB read, 137.2 MB written)
+DRAM_BYTES_PER_FRAME = (8.637300e9 + 137.208320e6) / 128
+DRAM_SOURCE = "profiles/r1n_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
 WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
 
 
@@ -241,7 +245,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=1024, help="synthetic frames resident per GPU")
     ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
-    ap.add_argument("--cpu-frames", type=int, default=16)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0: one per host thread, at least 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | convsep | colour | reduce49: the other BASELINE.json "
@@ -377,6 +381,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = host_threads()
+        if args.cpu_frames <= 0:
+            args.cpu_frames = max(16, min(threads, 192))
         arm = CpuArm(args.cpu_frames, threads)
         arm.step()
         secs = min(arm.step() for _ in range(2))
@@ -394,8 +400,8 @@ def main():
                        "output": "512x512x4 u8", "l2": "inputs (%.1f GiB per GPU) larger than L2" % (F * plan.in_frame_bytes / 2**30),
                        "sharding": "independent frames per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "thumbnail_fused_kernel<4,true>",
-                         "bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
+                         "traffic": DRAM_BYTES_PER_FRAME * F, "traffic_source": DRAM_SOURCE, "peak_source": peak_src,
+                         "kernel": plan.kernel, "bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

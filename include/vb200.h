@@ -286,6 +286,11 @@ int vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t 
 int vb200_thumbnail_plan_is_fused(const VB200ThumbnailPlan *plan);
 /* Algorithmic HBM bytes one frame moves through the fused kernel. */
 size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
+/* Which kernel a batch call of this plan launches (for bench / profile labels): a
+ * static string such as "thumbnail_fused_mma_kernel<VS=4,NP=6,premul,HS=4,cols=384,cpt=1>",
+ * or "leaf kernels" for an unfused plan.
+ */
+const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
 
 /* pinned host memory for the pump (cudaHostAlloc / cudaFreeHost) */
 void *vb200_host_alloc(size_t bytes);

@@ -102,6 +102,8 @@ def lib():
         L.vb200_thumbnail_plan_bytes_per_frame.restype = C.c_size_t
         L.vb200_thumbnail_plan_bytes_per_frame.argtypes = [C.c_void_p]
         L.vb200_thumbnail_plan_is_fused.argtypes = [C.c_void_p]
+        L.vb200_thumbnail_plan_kernel.restype = C.c_char_p
+        L.vb200_thumbnail_plan_kernel.argtypes = [C.c_void_p]
         L.vb200_thumbnail_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                    C.c_int]
         L.vb200_thumbnail_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
@@ -297,6 +299,7 @@ class ThumbnailPlan:
         self.out_frame_bytes = self.out_width * self.out_height * bands
         self.bytes_per_frame = int(lib().vb200_thumbnail_plan_bytes_per_frame(self._p))
         self.fused = bool(lib().vb200_thumbnail_plan_is_fused(self._p))
+        self.kernel = lib().vb200_thumbnail_plan_kernel(self._p).decode()
 
     def close(self):
         if self._p:

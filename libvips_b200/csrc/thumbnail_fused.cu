@@ -2225,6 +2225,28 @@ vb200_thumbnail_plan_is_fused(const VB200ThumbnailPlan *plan)
 	return plan && plan->impl.fused;
 }
 
+extern "C" const char *
+vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan)
+{
+	static thread_local char name[160];
+	if (!plan || !plan->impl.fused)
+		return "leaf kernels";
+	const ThumbnailPlanImpl &pl = plan->impl;
+	const FusedParams &fp = pl.fp;
+	const int nph = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
+	const bool v4 = pl.mma_ok && (fp.VS == 2 || fp.VS == 4);
+	if (v4)
+		snprintf(name, sizeof(name), "thumbnail_fused_mma_kernel<VS=%d,NP=%d,%s,HS=%d,cols=%d,cpt=%d>", fp.VS, nph,
+			pl.premul ? "premul" : "plain", fp.HS, pl.mma_cols, pl.mma_cpt);
+	else if (pl.tma3_ok)
+		snprintf(name, sizeof(name), "thumbnail_fused_tma3_kernel<VS=%d,%s,HS=%d>", fp.VS, pl.premul ? "premul" : "plain", fp.HS);
+	else if (pl.tma_ok)
+		snprintf(name, sizeof(name), "thumbnail_fused_tma_kernel<VS=%d,%s>", fp.VS, pl.premul ? "premul" : "plain");
+	else
+		snprintf(name, sizeof(name), "thumbnail_fused_kernel<VS=%d,%s>", fp.VS, pl.premul ? "premul" : "plain");
+	return name;
+}
+
 extern "C" int
 vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
 	size_t out_frame_stride, int n_frames)

@@ -247,3 +247,37 @@ def test_tile_geometry_changes_phase_tables(vb, oracle):
             same(vb.Image(a).thumbnail_image(123).numpy(), oracle.thumbnail_image(a, 123, tile=(tw, th)))
     finally:
         vb.set_tile_geometry(128, 128, 16, 1)
+
+
+V4_CASES = [
+    # (W, H, target_w, target_h, size, has_alpha, frames, tensor-pipe kernel expected)
+    (2048, 2048, 256, None, "both", True, 3, True),     # VS 4, HS 4: the headline's shape at 1/2 scale
+    (1024, 1024, 256, None, "both", True, 2, True),     # 2, 2
+    (1600, 1200, 200, None, "both", True, 1, True),     # 4, 4, one frame: rows split over CTAs
+    (2048, 1024, 256, 256, "force", True, 2, True),     # V 2, H 4
+    (1024, 2048, 256, 256, "force", True, 2, True),     # V 4, H 2
+    (4096, 512, 256, 128, "force", True, 1, True),      # V 2, H 8
+    (1600, 1600, 200, None, "both", False, 2, True),    # 4, 4 without alpha: no premultiply
+    (4096, 4096, 512, None, "both", True, 2, True),     # the headline frame
+    # plans the tensor-pipe kernel declines (box 3 / box 8 / a 15-tap window that overflows the 32-row
+    # quad ring): they must land on the older fused kernels with the same pixels
+    (1200, 900, 150, None, "both", True, 1, False),
+    (2000, 1000, 420, None, "both", True, 2, False),
+    (1003, 2057, 120, None, "both", True, 2, False),
+]
+
+
+@pytest.mark.parametrize("case", V4_CASES, ids=lambda c: "%dx%d-%s" % (c[0], c[1], c[2]))
+def test_thumbnail_tensor_pipe_kernel(vb, oracle, case):
+    """The headline kernel (reducev as u8 x s8 MMAs, thumbnail_fused_mma.cuh) on every (VS, HS)
+    corner it is instantiated for, batches of 1..3 frames, bit-exact against the oracle."""
+    w, h, tw, th, size, alpha, n, mma = case
+    rng = np.random.default_rng(w * 31 + h)
+    frames = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+    frames[0, : h // 3, :, 3] = 255     # an opaque region and a transparent one
+    frames[0, -(h // 5):, :, 3] = 0
+    plan = vb.ThumbnailPlan(w, h, 4, tw, th, size=size, has_alpha=alpha)
+    assert plan.fused, plan.kernel
+    assert ("mma_kernel" in plan.kernel) == mma, plan.kernel
+    want = np.stack([oracle.thumbnail_image(f, tw, th, size, has_alpha=alpha) for f in frames])
+    same(plan.run_host(frames), want)
