@@ -121,6 +121,196 @@ convf_line_kernel(const __grid_constant__ ConvDev P, const T *__restrict__ in, f
 	((float *) ((char *) out + (size_t) y * P.out_bpl))[e] = (float) sum;
 }
 
+/* 1-D masks again, register-blocked: R outputs per thread along the mask axis, so each input
+ * is loaded and widened to double once per R outputs instead of once per tap, and the
+ * coefficients of an R x R block of multiply-adds sit in registers.  Every accumulator still
+ * takes its taps in ascending mask order with a separately rounded multiply and add
+ * (convf.c:175-199 compiled without contraction), and absent (zero) taps are skipped, not
+ * multiplied, exactly like the reference's squeezed tap list.
+ */
+struct LineMask {
+	double c[64];			   /* dense: c[i] for mask position i (0 where absent) */
+	unsigned long long present; /* bit i: position i is a tap */
+	int n;					   /* mask length */
+};
+
+template <typename T, bool VERT, int R>
+__global__ void __launch_bounds__(128)
+convf_block_kernel(const __grid_constant__ ConvDev P, const __grid_constant__ LineMask M, const T *__restrict__ in,
+	float *__restrict__ out)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n = M.n;
+	const int d0 = -(n / 2);
+	int e, y0, x0 = 0, b = 0;
+	if (VERT) {
+		e = idx;
+		if (e >= P.w * P.bands)
+			return;
+		y0 = blockIdx.y * R;
+	}
+	else {
+		const int groups = (P.w + R - 1) / R;
+		if (idx >= groups * P.bands)
+			return;
+		const int pg = idx / P.bands;
+		b = idx - pg * P.bands;
+		x0 = pg * R;
+		y0 = blockIdx.y;
+		e = 0;
+	}
+	double acc[R];
+#pragma unroll
+	for (int r = 0; r < R; r++)
+		acc[r] = P.offset;
+	const char *base = (const char *) in;
+	const T *row = (const T *) (base + (size_t) y0 * P.in_bpl); /* HORIZ */
+
+	for (int j0 = 0; j0 < n + R - 1; j0 += R) {
+		double cc[2 * R - 1];
+		unsigned vm = 0;
+#pragma unroll
+		for (int k = 0; k < 2 * R - 1; k++) {
+			const int i = j0 - (R - 1) + k;
+			const bool ok = (unsigned) i < (unsigned) n && ((M.present >> i) & 1ull);
+			cc[k] = ok ? M.c[i] : 0.0;
+			vm |= ok ? (1u << k) : 0u;
+		}
+#pragma unroll
+		for (int jj = 0; jj < R; jj++) {
+			const int j = j0 + jj;
+			if (j < n + R - 1) {
+				double v;
+				if (VERT) {
+					const int sy = clampi(y0 + d0 + j, 0, P.h - 1);
+					v = (double) ((const T *) (base + (size_t) sy * P.in_bpl))[e];
+				}
+				else {
+					const int sx = clampi(x0 + d0 + j, 0, P.w - 1);
+					v = (double) row[sx * P.bands + b];
+				}
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					const int k = jj - r + R - 1;
+					if (vm & (1u << k))
+						acc[r] = __dadd_rn(acc[r], __dmul_rn(cc[k], v));
+				}
+			}
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		if (VERT) {
+			if (y0 + r < P.h)
+				((float *) ((char *) out + (size_t) (y0 + r) * P.out_bpl))[e] = (float) acc[r];
+		}
+		else if (x0 + r < P.w)
+			((float *) ((char *) out + (size_t) y0 * P.out_bpl))[(x0 + r) * P.bands + b] = (float) acc[r];
+	}
+}
+
+/* The dense case of the above (every mask position is a tap, n >= R: Gaussians): the
+ * (row, output) pairs that exist form a head triangle, a band of full rows and a tail
+ * triangle, so nothing is predicated and no multiply-add is issued for a tap that does
+ * not exist.  Same arithmetic, same order.
+ */
+template <typename T, bool VERT, int R>
+__global__ void __launch_bounds__(128)
+convf_dense_kernel(const __grid_constant__ ConvDev P, const __grid_constant__ LineMask M, const T *__restrict__ in,
+	float *__restrict__ out)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n = M.n;
+	const int d0 = -(n / 2);
+	int e = 0, y0, x0 = 0, b = 0;
+	if (VERT) {
+		e = idx;
+		if (e >= P.w * P.bands)
+			return;
+		y0 = blockIdx.y * R;
+	}
+	else {
+		const int groups = (P.w + R - 1) / R;
+		if (idx >= groups * P.bands)
+			return;
+		const int pg = idx / P.bands;
+		b = idx - pg * P.bands;
+		x0 = pg * R;
+		y0 = blockIdx.y;
+	}
+	const char *base = (const char *) in;
+	const T *row = (const T *) (base + (size_t) y0 * P.in_bpl); /* HORIZ */
+	const bool interior = VERT ? (y0 + d0 >= 0 && y0 + d0 + n + R - 2 < P.h) : (x0 + d0 >= 0 && x0 + d0 + n + R - 2 < P.w);
+	const T *p0 = VERT ? (const T *) (base + (size_t) (y0 + d0) * P.in_bpl) + e : row + (size_t) (x0 + d0) * P.bands + b;
+	const size_t step = VERT ? P.in_bpl / sizeof(T) : (size_t) P.bands;
+	double acc[R];
+#pragma unroll
+	for (int r = 0; r < R; r++)
+		acc[r] = P.offset;
+
+	/* the body twice: interior tiles read through one pointer + a constant step, so the loads of a
+	 * group of rows can be issued together; edge tiles clamp every coordinate (VIPS_EXTEND_COPY)
+	 */
+	auto body = [&](auto load) {
+		/* head: rows 0 .. R - 2, outputs r <= row */
+#pragma unroll
+		for (int j = 0; j < R - 1; j++) {
+			const double v = load(j);
+#pragma unroll
+			for (int r = 0; r <= j; r++)
+				acc[r] = __dadd_rn(acc[r], __dmul_rn(M.c[j - r], v));
+		}
+		/* full rows R - 1 .. n - 1, R at a time with their 2R - 1 coefficients in registers */
+		int j = R - 1;
+		for (; j + R <= n; j += R) {
+			double cc[2 * R - 1];
+#pragma unroll
+			for (int k = 0; k < 2 * R - 1; k++)
+				cc[k] = M.c[j - (R - 1) + k];
+#pragma unroll
+			for (int jj = 0; jj < R; jj++) {
+				const double v = load(j + jj);
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					acc[r] = __dadd_rn(acc[r], __dmul_rn(cc[jj - r + R - 1], v));
+			}
+		}
+		for (; j < n; j++) {
+			const double v = load(j);
+#pragma unroll
+			for (int r = 0; r < R; r++)
+				acc[r] = __dadd_rn(acc[r], __dmul_rn(M.c[j - r], v));
+		}
+		/* tail: rows n .. n + R - 2, outputs r > row - n */
+		double ct[R - 1];
+#pragma unroll
+		for (int k = 0; k < R - 1; k++)
+			ct[k] = M.c[n - R + 1 + k];
+#pragma unroll
+		for (int jt = 0; jt < R - 1; jt++) {
+			const double v = load(n + jt);
+#pragma unroll
+			for (int r = jt + 1; r < R; r++)
+				acc[r] = __dadd_rn(acc[r], __dmul_rn(ct[jt - r + R - 1], v));
+		}
+	};
+	if (interior)
+		body([&](int j) -> double { return (double) p0[(size_t) j * step]; });
+	else if (VERT)
+		body([&](int j) -> double { return (double) ((const T *) (base + (size_t) clampi(y0 + d0 + j, 0, P.h - 1) * P.in_bpl))[e]; });
+	else
+		body([&](int j) -> double { return (double) row[clampi(x0 + d0 + j, 0, P.w - 1) * P.bands + b]; });
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		if (VERT) {
+			if (y0 + r < P.h)
+				((float *) ((char *) out + (size_t) (y0 + r) * P.out_bpl))[e] = (float) acc[r];
+		}
+		else if (x0 + r < P.w)
+			((float *) ((char *) out + (size_t) y0 * P.out_bpl))[(x0 + r) * P.bands + b] = (float) acc[r];
+	}
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 convi_kernel(const __grid_constant__ ConvDev P, const T *__restrict__ in, T *__restrict__ out, long long lo,
@@ -361,13 +551,44 @@ dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *ma
 		if (dev_image_new(domain, out, in.w, in.h, in.bands, VB200_FORMAT_FLOAT, in.type, s))
 			return -1;
 		P.out_bpl = out->bpl;
-		if (upload_taps(domain, pos, mw, mh, &coeff, nullptr, &P, &u, s))
-			return -1;
 		/* taps arrive sorted by mask position, so sd[0] / sd[nnz - 1] bound the stencil */
 		const bool line_h = mh == 1 && coeff.size() <= 64, line_v = mw == 1 && coeff.size() <= 64;
+		constexpr int RB = 8; /* outputs per thread of convf_block_kernel */
+		LineMask lm;
+		bool block_ok = (line_h || line_v) && n <= 64 && getenv("VB200_NO_CONV_BLOCK") == nullptr;
+		if (block_ok) {
+			memset(&lm, 0, sizeof(lm));
+			lm.n = n;
+			for (int i = 0; i < n; i++) {
+				const double c = mask[i] / scale;
+				if (c) {
+					lm.c[i] = c;
+					lm.present |= 1ull << i;
+				}
+			}
+		}
+		if (block_ok && lm.present == 0)
+			block_ok = false; /* the all-zero mask keeps one 0 * pixel term (convf.c:321-325): the generic kernels do that */
+		const bool dense_ok = block_ok && n >= RB && lm.present == (n == 64 ? ~0ull : (1ull << n) - 1) &&
+			getenv("VB200_NO_CONV_DENSE") == nullptr;
+		/* the 1-D kernels take their mask as a kernel parameter: no table upload (a pageable
+		 * cudaMemcpyAsync is a host-side stall as long as the kernel itself on a big image)
+		 */
+		if (!block_ok && upload_taps(domain, pos, mw, mh, &coeff, nullptr, &P, &u, s))
+			return -1;
+		const dim3 grid_h(((in.w + RB - 1) / RB * in.bands + 127) / 128, in.h);
+		const dim3 grid_v((in.w * in.bands + 127) / 128, (in.h + RB - 1) / RB);
 #define CF(T) \
 	do { \
-		if (line_h) \
+		if (dense_ok && line_h) \
+			convf_dense_kernel<T, false, RB><<<grid_h, 128, 0, s>>>(P, lm, (const T *) in.data, (float *) out->data); \
+		else if (dense_ok && line_v) \
+			convf_dense_kernel<T, true, RB><<<grid_v, 128, 0, s>>>(P, lm, (const T *) in.data, (float *) out->data); \
+		else if (block_ok && line_h) \
+			convf_block_kernel<T, false, RB><<<grid_h, 128, 0, s>>>(P, lm, (const T *) in.data, (float *) out->data); \
+		else if (block_ok && line_v) \
+			convf_block_kernel<T, true, RB><<<grid_v, 128, 0, s>>>(P, lm, (const T *) in.data, (float *) out->data); \
+		else if (line_h) \
 			convf_line_kernel<T, false><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data); \
 		else if (line_v) \
 			convf_line_kernel<T, true><<<grid, 256, 0, s>>>(P, (const T *) in.data, (float *) out->data); \
@@ -599,7 +820,7 @@ namespace {
 
 template <typename Op>
 int
-run_conv_op(const char *domain, const VB200Image *in, VB200Image *out, Op op)
+run_conv_op(const char *domain, const VB200Image *in, VB200Image *out, Op op, bool direct = false)
 {
 	if (!in || !out) {
 		error(domain, "null argument");
@@ -611,6 +832,8 @@ run_conv_op(const char *domain, const VB200Image *in, VB200Image *out, Op op)
 	DevImage din, dout;
 	if (to_device(domain, in, &din, s))
 		return -1;
+	if (direct)
+		preset_output(&dout, in, out);
 	int rc = op(din, &dout, s);
 	if (!rc) {
 		if (dout.data == din.data) {
@@ -640,7 +863,7 @@ vb200_conv(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int pre
 	}
 	return run_conv_op("conv", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
 		return dev_conv("conv", d, o, mask->coeff, mask->width, mask->height, mask->scale, mask->offset, precision, s);
-	});
+	}, true);
 }
 
 extern "C" int
@@ -658,7 +881,7 @@ vb200_convsep(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int 
 	const int n = mask->width * mask->height;
 	return run_conv_op("convsep", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
 		return dev_convsep("convsep", d, o, mask->coeff, n, mask->scale, mask->offset, precision, s);
-	});
+	}, true);
 }
 
 extern "C" int
@@ -668,7 +891,7 @@ vb200_gaussblur(const VB200Image *in, VB200Image *out, double sigma, double min_
 		min_ampl = 0.2; /* gaussblur.c class default */
 	return run_conv_op("gaussblur", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
 		return dev_gaussblur("gaussblur", d, o, sigma, min_ampl, precision, s);
-	});
+	}, true);
 }
 
 extern "C" int

@@ -1,3 +1,4 @@
+#include <algorithm>
 /* runtime.cu -- init, error buffer, stream and memory plumbing of libvb200.so.
  *
  * Mirrors the reference's conventions: 0 / -1 returns with a text buffer
@@ -151,9 +152,36 @@ dev_image_new(const char *domain, DevImage *d, int w, int h, int bands, int fmt,
 	d->bands = bands;
 	d->fmt = fmt;
 	d->type = type;
-	d->bpl = (size_t) w * bands * format_sizeof(fmt);
+	const size_t line = (size_t) w * bands * format_sizeof(fmt);
+	if (d->preset && d->data) {
+		/* the caller's buffer (preset_output): sized by contract for this op's result */
+		d->preset = false;
+		d->owned = false;
+		if (d->bpl < line)
+			d->bpl = line;
+		return 0;
+	}
+	d->bpl = line;
 	d->owned = true;
 	return dev_alloc(domain, &d->data, d->bpl * h, s);
+}
+
+void
+preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out)
+{
+	if (in->where != VB200_DEVICE || !out->data || !in->data)
+		return;
+	const size_t in_bytes = (in->bpl ? in->bpl : (size_t) in->Xsize * in->Bands * format_sizeof(in->BandFmt)) * in->Ysize;
+	const char *a = (const char *) in->data, *o = (const char *) out->data;
+	/* no aliasing: the result must lie wholly before or after the input.  Its extent is not known
+	 * yet; no device op produces wider than 4-byte elements, and none changes the pixel count.
+	 */
+	const size_t out_line = std::max((size_t) out->bpl, (size_t) in->Xsize * in->Bands * 4);
+	if (o >= a + in_bytes || o + out_line * in->Ysize <= a) {
+		dout->data = out->data;
+		dout->bpl = out->bpl;
+		dout->preset = true;
+	}
 }
 
 void
@@ -224,6 +252,11 @@ deliver(const char *domain, DevImage *d, const VB200Image *like, VB200Image *out
 			out->data = d->data;
 			out->bpl = d->bpl;
 			d->owned = false;
+			return 0;
+		}
+		if (dst && dst == d->data) {
+			/* the op wrote into the caller's buffer (preset_output) */
+			out->bpl = d->bpl;
 			return 0;
 		}
 		if (!dst) {

@@ -50,6 +50,7 @@ struct DevImage {
 	void *data = nullptr;
 	size_t bpl = 0;
 	bool owned = false; /* free with dev_free on destruction of the holder */
+	bool preset = false; /* data / bpl name the caller's output buffer: dev_image_new() adopts it instead of allocating */
 };
 
 size_t format_sizeof(int fmt);
@@ -61,6 +62,10 @@ int to_device(const char *domain, const VB200Image *in, DevImage *d, cudaStream_
 int deliver(const char *domain, DevImage *d, const VB200Image *like, VB200Image *out, cudaStream_t s);
 /* Allocate an owned packed device image. */
 int dev_image_new(const char *domain, DevImage *d, int w, int h, int bands, int fmt, int type, cudaStream_t s);
+/* Let the op write straight into a device buffer the caller supplied (no device-to-device copy in
+ * deliver()), when it cannot alias the input.
+ */
+void preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out);
 void dev_image_release(DevImage *d, cudaStream_t s);
 
 /* ------------------------------------------------------------ resample host */
