@@ -41,6 +41,7 @@ struct ColourTables {
 	const float *v2Y_16; /* [65536] */
 	const int *Y2v_16;	 /* [65537] */
 	const float *cbrt;	 /* [100000] */
+	const float2 *cbrt2; /* [kQuant] (cbrt[i], cbrt[i + 1]) */
 };
 
 struct StepInfo {
@@ -110,7 +111,13 @@ get_tables(const char *domain, ColourTables *out)
 		else
 			cb[i] = cbrtf(Y);
 	}
-	const size_t bytes = (y8.size() + v8.size() + y16.size() + v16.size() + cb.size()) * 4;
+	/* the same table as (t[i], t[i + 1]) pairs: one aligned 8-byte gather per lookup */
+	std::vector<float> cb2(2 * (size_t) kQuant);
+	for (int i = 0; i < kQuant; i++) {
+		cb2[2 * i] = cb[i];
+		cb2[2 * i + 1] = cb[std::min(i + 1, kQuant - 1)];
+	}
+	const size_t bytes = (y8.size() + v8.size() + y16.size() + v16.size() + cb.size() + cb2.size()) * 4 + 16;
 	char *block = nullptr;
 	VB200_CUDA(domain, cudaMalloc(&block, bytes));
 	char *p = block;
@@ -126,6 +133,8 @@ get_tables(const char *domain, ColourTables *out)
 	t.v2Y_16 = (const float *) put(v16.data(), v16.size() * 4);
 	t.Y2v_16 = (const int *) put(y16.data(), y16.size() * 4);
 	t.cbrt = (const float *) put(cb.data(), cb.size() * 4);
+	p = (char *) (((uintptr_t) p + 15) & ~(uintptr_t) 15);
+	t.cbrt2 = (const float2 *) put(cb2.data(), cb2.size() * 4);
 	VB200_CUDA(domain, cudaDeviceSynchronize());
 	if (dev < 16) {
 		g_tables[dev] = t;
@@ -421,6 +430,89 @@ colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restric
 	}
 }
 
+/* The two hot routes (BASELINE config 4), 3-band packed rows, four pixels per thread: sRGB bytes come
+ * in as three 32-bit words and leave as three, Lab floats as three float4; the route is
+ * compiled in (no per-step switch) and the cbrt table is read as aligned (t[i], t[i + 1]) pairs.
+ * Same steps, same roundings as colour_route_kernel.
+ */
+__device__ __forceinline__ float
+cbrt_lookup2(const float2 *__restrict__ table, float nX)
+{
+	int i = x86_float_to_int(nX);
+	i = max(0, min(kQuant - 2, i));
+	const float f = __fsub_rn(nX, (float) i);
+	const float2 t = __ldg(table + i);
+	return __fadd_rn(t.x, __fmul_rn(f, __fsub_rn(t.y, t.x)));
+}
+
+__global__ void __launch_bounds__(256)
+colour_srgb2lab_x4_kernel(const __grid_constant__ RouteParams P, const uint8_t *__restrict__ in, float *__restrict__ out)
+{
+	__shared__ float s_v2Y_8[256];
+	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+		s_v2Y_8[i] = P.t.v2Y_8[i];
+	__syncthreads();
+	const int q = blockIdx.x * blockDim.x + threadIdx.x; /* group of 4 pixels */
+	if (q * 4 >= P.w)
+		return;
+	const uint32_t *pin = (const uint32_t *) (in + (size_t) blockIdx.y * P.in_bpl) + (size_t) q * 3;
+	float4 *pout = (float4 *) ((char *) out + (size_t) blockIdx.y * P.out_bpl) + (size_t) q * 3;
+	const uint32_t w0 = __ldg(pin), w1 = __ldg(pin + 1), w2 = __ldg(pin + 2);
+	const uint32_t bytes[12] = {w0 & 255, (w0 >> 8) & 255, (w0 >> 16) & 255, w0 >> 24, w1 & 255, (w1 >> 8) & 255,
+		(w1 >> 16) & 255, w1 >> 24, w2 & 255, (w2 >> 8) & 255, (w2 >> 16) & 255, w2 >> 24};
+	float r[12];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		float a = s_v2Y_8[bytes[3 * k]], b = s_v2Y_8[bytes[3 * k + 1]], c = s_v2Y_8[bytes[3 * k + 2]];
+		step_scRGB2XYZ(a, b, c);
+		const float nX = (float) DIVC((double) __fmul_rn(100000.0f, a), 95.0470);
+		const float nY = (float) DIVC((double) __fmul_rn(100000.0f, b), 100.0);
+		const float nZ = (float) DIVC((double) __fmul_rn(100000.0f, c), 108.8827);
+		const float cbx = cbrt_lookup2(P.t.cbrt2, nX);
+		const float cby = cbrt_lookup2(P.t.cbrt2, nY);
+		const float cbz = cbrt_lookup2(P.t.cbrt2, nZ);
+		r[3 * k] = __fsub_rn(__fmul_rn(116.0F, cby), 16.0F);
+		r[3 * k + 1] = __fmul_rn(500.0F, __fsub_rn(cbx, cby));
+		r[3 * k + 2] = __fmul_rn(200.0F, __fsub_rn(cby, cbz));
+	}
+	pout[0] = make_float4(r[0], r[1], r[2], r[3]);
+	pout[1] = make_float4(r[4], r[5], r[6], r[7]);
+	pout[2] = make_float4(r[8], r[9], r[10], r[11]);
+}
+
+__global__ void __launch_bounds__(256)
+colour_lab2srgb_x4_kernel(const __grid_constant__ RouteParams P, const float *__restrict__ in, uint8_t *__restrict__ out)
+{
+	__shared__ int s_Y2v_8[257];
+	for (int i = threadIdx.x; i < 257; i += blockDim.x)
+		s_Y2v_8[i] = P.t.Y2v_8[i];
+	__syncthreads();
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q * 4 >= P.w)
+		return;
+	const float4 *pin = (const float4 *) ((const char *) in + (size_t) blockIdx.y * P.in_bpl) + (size_t) q * 3;
+	uint32_t *pout = (uint32_t *) (out + (size_t) blockIdx.y * P.out_bpl) + (size_t) q * 3;
+	const float4 v0 = __ldg(pin), v1 = __ldg(pin + 1), v2 = __ldg(pin + 2);
+	const float f[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+	uint32_t o[12];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		float a = f[3 * k], b = f[3 * k + 1], c = f[3 * k + 2];
+		step_Lab2XYZ(a, b, c);
+		step_XYZ2scRGB(a, b, c);
+		if (isnan(a) || isnan(b) || isnan(c))
+			o[3 * k] = o[3 * k + 1] = o[3 * k + 2] = 0;
+		else {
+			o[3 * k] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, a) & 255u;
+			o[3 * k + 1] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, b) & 255u;
+			o[3 * k + 2] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, c) & 255u;
+		}
+	}
+	pout[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+	pout[1] = o[4] | (o[5] << 8) | (o[6] << 16) | (o[7] << 24);
+	pout[2] = o[8] | (o[9] << 8) | (o[10] << 16) | (o[11] << 24);
+}
+
 /* identity routes: a cast to the space's format (colourspace.c rows X -> X) */
 __global__ void __launch_bounds__(256)
 cast_kernel(const void *__restrict__ in, size_t in_bpl, int in_fmt, void *__restrict__ out, size_t out_bpl, int out_fmt,
@@ -582,7 +674,15 @@ dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space
 		return -1;
 	P.in_bpl = in.bpl;
 	P.out_bpl = out->bpl;
-	colour_route_kernel<<<dim3((in.w + 255) / 256, in.h), block, 0, s>>>(P, in.data, out->data);
+	const bool x4 = in.bands == 3 && (in.w & 3) == 0 && ((uintptr_t) in.data & 15) == 0 && ((uintptr_t) out->data & 15) == 0 &&
+		(in.bpl & 15) == 0 && (out->bpl & 15) == 0 && getenv("VB200_NO_COLOUR_X4") == nullptr;
+	const dim3 grid4((in.w / 4 + 255) / 256, in.h);
+	if (x4 && n == 3 && steps[0] == S_sRGB2scRGB && steps[1] == S_scRGB2XYZ && steps[2] == S_XYZ2Lab)
+		colour_srgb2lab_x4_kernel<<<grid4, block, 0, s>>>(P, (const uint8_t *) in.data, (float *) out->data);
+	else if (x4 && n == 3 && steps[0] == S_Lab2XYZ && steps[1] == S_XYZ2scRGB && steps[2] == S_scRGB2sRGB)
+		colour_lab2srgb_x4_kernel<<<grid4, block, 0, s>>>(P, (const float *) in.data, (uint8_t *) out->data);
+	else
+		colour_route_kernel<<<dim3((in.w + 255) / 256, in.h), block, 0, s>>>(P, in.data, out->data);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess)
 		return cuda_fail(domain, e, "colour_route_kernel");
