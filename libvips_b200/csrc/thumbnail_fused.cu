@@ -1614,7 +1614,7 @@ launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 	const int use_tmap = make_stage_tensor_map(&tm, in, fp.W, fp.H, fp.in_bpl, in_stride, n, WCOLS + 8, 2 * VS) ? 1 : 0;
 	for (int f0 = 0; f0 < n; f0 += 32768) {
 		grid.z = std::min(32768, n - f0);
-		kern<<<grid, fp.NT + 64, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
+		kern<<<grid, fp.NT + 32 * V4HWarps<CPT>::value + 32, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
 			out_stride, f0);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)

@@ -58,6 +58,14 @@ constexpr int kV4Quads = 8; /* quad ring: K / 4 */
 #define V4_ACC(x, rb, ga) accumulate_pixel_m<V4_ACC_PREMUL>(x, accm, k16, rb, ga)
 #endif
 
+/* H warps per CTA: the reduceh work of a chunk is ~2/3 of a V warp's; one H warp overloads its SM
+ * sub-partition (the V warps there set the pace for all), so it is spread over several
+ */
+template <int CPT>
+struct V4HWarps {
+	static constexpr int value = CPT == 1 ? 3 : 2;
+};
+
 template <int VS>
 struct V4Stages {
 	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
@@ -91,7 +99,7 @@ v4_finish(int hi, int lo, int k20)
 }
 
 template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT>
-__global__ void __launch_bounds__(WCOLS / CPT + 64, WCOLS <= 448 ? 2 : 1)
+__global__ void __launch_bounds__(WCOLS / CPT + 32 * V4HWarps<CPT>::value + 32, WCOLS <= 448 ? 2 : 1)
 thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, int use_tmap,
 	const uint8_t *__restrict__ in, size_t in_frame_stride, uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
 {
@@ -99,6 +107,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 
 	constexpr int K = kV4Rows;
 	constexpr int S = V4Stages<VS>::value;
+	constexpr int NH = V4HWarps<CPT>::value;
 	constexpr int PITCH = (WCOLS + 8) * 4;
 	constexpr int NPR = NP > 0 ? NP : 1;
 	constexpr int HSHIFT = HSQ == 2 ? 1 : HSQ == 4 ? 2 : 3;
@@ -163,15 +172,15 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		}
 		for (int i = 0; i < 2; i++) {
 			mbar_init(shfull_s + 8u * i, NTa / 32);
-			mbar_init(shempty_s + 8u * i, 1);
+			mbar_init(shempty_s + 8u * i, NH);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	if (t >= NT + 32) {
+	if (t >= NT + 32 * NH) {
 		/* ---------------- P: lane L copies row L of each stage (stage p = shrunk rows 2p, 2p + 1) */
-		const int lane = t - NT - 32;
+		const int lane = t - NT - 32 * NH;
 		const uint8_t *src0 = fin + (size_t) c_lo * 4;
 		const int j = lane / VS, k = lane - j * VS;
 		const bool copier = lane < rows_per_stage;
@@ -219,7 +228,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 
 	if (t >= NT) {
 		/* ---------------- H: reduceh + unpremultiply + store, one warp (v3's) */
-		const int lane = t - NT;
+		const int ht = t - NT; /* 0 .. 32 NH - 1 */
+		const int lane = ht & 31;
 		const int bw = xb - xa;
 		int chunk = 0;
 		for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
@@ -228,7 +238,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 			const int buf = chunk & 1;
 			const uint2 *shb = sh + (size_t) buf * K * shs;
 			mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
-			for (int idx = lane; idx < rows * bw; idx += 32) {
+			for (int idx = ht; idx < rows * bw; idx += 32 * NH) {
 				const int k = fast_div(idx, bw);
 				const int x = xa + (idx - k * bw);
 				const int2 hc = __ldg(&P.hcol[x]);
