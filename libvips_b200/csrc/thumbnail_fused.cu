@@ -1611,10 +1611,10 @@ launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_mma));
 	CUtensorMap tm;
 	memset(&tm, 0, sizeof(tm));
-	const int use_tmap = make_stage_tensor_map(&tm, in, fp.W, fp.H, fp.in_bpl, in_stride, n, WCOLS + 8, 2 * VS) ? 1 : 0;
+	const int use_tmap = make_stage_tensor_map(&tm, in, fp.W, fp.H, fp.in_bpl, in_stride, n, (WCOLS + 8) / (WCOLS + 8 > 512 ? 2 : 1), 2 * VS) ? 1 : 0;
 	for (int f0 = 0; f0 < n; f0 += 32768) {
 		grid.z = std::min(32768, n - f0);
-		kern<<<grid, fp.NT + 32 * V4HWarps<CPT>::value + 32, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
+		kern<<<grid, fp.NT + 32 * V4HWarpsW<WCOLS, CPT>::value + 32, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
 			out_stride, f0);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
@@ -1658,6 +1658,9 @@ launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 		rpc = ((rpc / 2 + K - 1) / K) * K;
 	fp.RPC = rpc;
 	const dim3 grid(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+	if (pl->mma_cols > 448)
+		return pl->premul ? launch_mma_w<true, 768, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
+						  : launch_mma_w<false, 768, 2>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
 	if (pl->mma_cpt == 1)
 		return pl->premul ? launch_mma_w<true, VB200_V4_COLS, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled)
 						  : launch_mma_w<false, VB200_V4_COLS, 1>(domain, pl, fp, in, is, out, os, n, grid, s, handled);
@@ -1943,9 +1946,8 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		}
 		/* band width: the fewest bands whose widest one fits the column budget */
 		const char *ev = getenv("VB200_V4_COLS");
-		const int wcols = VB200_V4_COLS;
-		(void) ev;
-		pl->mma_cpt = getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 2 ? 2 : 1; /* columns per V thread */
+		const int wcols = ev && atoi(ev) <= 448 ? VB200_V4_COLS : 768; /* 768 (default): one CTA per SM, two columns per thread */
+		pl->mma_cpt = wcols > 448 || (getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 2) ? 2 : 1; /* columns per V thread */
 		const int pitch = (wcols + 8) * 4;
 		auto column_of = [&](int E0, int tt) {
 			const int e = E0 + tt / fp.HS;
@@ -1984,7 +1986,9 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			pl->mma_nemax = nemax4;
 			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
 			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
-			pl->smem_mma = (size_t) stages * 2 * fp.VS * pitch + (2 * stages + 4) * 8 +
+			const int nbox = wcols + 8 > 512 ? 2 : 1;
+			const size_t box_bytes = ((size_t) 2 * fp.VS * (pitch / nbox) + 127) & ~(size_t) 127;
+			pl->smem_mma = (size_t) stages * nbox * box_bytes + (2 * stages + 4) * 8 +
 				(size_t) kV4Quads * ((size_t) pl->mma_nt * pl->mma_cpt * 16 + 16) +
 				(size_t) 2 * K * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +
 				(size_t) (fp.nhsets * fp.NPh + 256) * 4;

@@ -65,6 +65,10 @@ template <int CPT>
 struct V4HWarps {
 	static constexpr int value = CPT == 1 ? 3 : 2;
 };
+template <int WCOLS, int CPT>
+struct V4HWarpsW {
+	static constexpr int value = WCOLS > 448 ? 4 : V4HWarps<CPT>::value;
+};
 
 template <int VS>
 struct V4Stages {
@@ -99,7 +103,7 @@ v4_finish(int hi, int lo, int k20)
 }
 
 template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT>
-__global__ void __launch_bounds__(WCOLS / CPT + 32 * V4HWarps<CPT>::value + 32, WCOLS <= 448 ? 2 : 1)
+__global__ void __launch_bounds__(WCOLS / CPT + 32 * V4HWarpsW<WCOLS, CPT>::value + 32, WCOLS <= 448 ? 2 : 1)
 thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap, int use_tmap,
 	const uint8_t *__restrict__ in, size_t in_frame_stride, uint8_t *__restrict__ out, size_t out_frame_stride, int frame0)
 {
@@ -107,12 +111,16 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 
 	constexpr int K = kV4Rows;
 	constexpr int S = V4Stages<VS>::value;
-	constexpr int NH = V4HWarps<CPT>::value;
-	constexpr int PITCH = (WCOLS + 8) * 4;
+	constexpr int NH = V4HWarpsW<WCOLS, CPT>::value;
+	/* a stage row is held as NBOX column boxes (a tiled-TMA box is at most 256 elements = 512 pixels wide) */
+	constexpr int NBOX = WCOLS + 8 > 512 ? 2 : 1;
+	constexpr int BOXW = (WCOLS + 8) / NBOX; /* pixels; even, a multiple of 4 */
+	constexpr int PITCH = BOXW * 4;			 /* bytes between rows of a box */
 	constexpr int NPR = NP > 0 ? NP : 1;
 	constexpr int HSHIFT = HSQ == 2 ? 1 : HSQ == 4 ? 2 : 3;
 	constexpr int rows_per_stage = 2 * VS;
-	constexpr unsigned stage_bytes = (unsigned) rows_per_stage * PITCH;
+	constexpr unsigned box_bytes = ((unsigned) rows_per_stage * PITCH + 127u) & ~127u; /* a tiled-TMA destination is 128-byte aligned */
+	constexpr unsigned stage_bytes = NBOX * box_bytes;
 
 	const int NT = P.NT;	 /* V threads */
 	const int NC = NT * CPT; /* columns */
@@ -198,11 +206,13 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 				const bool interior = use_tmap && sr0 >= 0 && sr0 + 1 <= P.Hs - 1 && (sr0 + 2) * VS <= P.H;
 				if (interior) {
 					if (lane == 0) {
-						mbar_expect_tx(full_s + 8u * s, stage_bytes);
-						asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-										 stages_s + (unsigned) s * stage_bytes),
-									 "l"(&tmap), "r"(c_lo >> 1), "r"(sr0 * VS), "r"(frame), "r"(full_s + 8u * s)
-									 : "memory");
+						mbar_expect_tx(full_s + 8u * s, (unsigned) NBOX * rows_per_stage * PITCH); /* the boxes' bytes, not their padded slots */
+#pragma unroll
+						for (int h = 0; h < NBOX; h++)
+							asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+											 stages_s + (unsigned) s * stage_bytes + (unsigned) h * box_bytes),
+										 "l"(&tmap), "r"((c_lo + h * BOXW) >> 1), "r"(sr0 * VS), "r"(frame), "r"(full_s + 8u * s)
+										 : "memory");
 					}
 				}
 				else {
@@ -212,8 +222,13 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 					if (copier) {
 						const int sr = max(0, min(2 * p + j - P.vembed, P.Hs - 1));
 						const int row = min(sr * VS + k, P.H - 1);
-						bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) lane * PITCH,
-							src0 + (size_t) row * P.in_bpl, row_bytes, full_s + 8u * s);
+#pragma unroll
+						for (int h = 0; h < NBOX; h++) {
+							const int nb = min((int) row_bytes - h * PITCH, PITCH);
+							if (nb > 0)
+								bulk_copy_g2s(stages_s + (unsigned) s * stage_bytes + (unsigned) h * box_bytes + (unsigned) lane * PITCH,
+									src0 + (size_t) row * P.in_bpl + (size_t) h * PITCH, (unsigned) nb, full_s + 8u * s);
+						}
 					}
 				}
 				if (++s == S) {
@@ -289,7 +304,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	if (t >= NTa)
 		return;
 	/* CPT 2: the thread's two columns are adjacent and start on an even column (one 64-bit LDS per row) */
-	const unsigned char *my_cols = stages + (size_t) (column_of(min(t * CPT, NE * HSQ - CPT)) - c_lo) * 4u;
+	const int my_c = column_of(min(t * CPT, NE * HSQ - CPT)) - c_lo;
+	const unsigned char *my_cols = stages + (size_t) (my_c / BOXW) * box_bytes + (size_t) (my_c % BOXW) * 4u;
 	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
 	unsigned k16;
 	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
