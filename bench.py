@@ -30,9 +30,9 @@ TARGET = 512
 MPIX_PER_FRAME = W * H / 1e6
 METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per 4096x4096 frame, from the
-# committed `ncu --set full` capture (a launch of 128 frames: 8.6373 GB read, 137.2 MB written)
-DRAM_BYTES_PER_FRAME = (8.637300e9 + 137.208320e6) / 128
-DRAM_SOURCE = "profiles/r1n_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
+# committed `ncu --set full` capture (a launch of 148 frames: 10.1243 GB read, 159.4 MB written)
+DRAM_BYTES_PER_FRAME = (10.124292e9 + 159.375872e6) / 148
+DRAM_SOURCE = "profiles/r1p_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
 WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
 
 
