@@ -245,6 +245,14 @@ int vb200_reducev_gen(const VB200Region *out, const VB200Region *in, const VB200
 int vb200_reduceh_gen(const VB200Region *out, const VB200Region *in, const VB200ReduceParams *params);
 int vb200_shrinkv_gen(const VB200Region *out, const VB200Region *in, int vshrink);
 int vb200_shrinkh_gen(const VB200Region *out, const VB200Region *in, int hshrink);
+/* convolution and colour in the same shape.  conv: regions are on the EMBEDDED image and `in`
+ * covers {left, top, width + mask->width - 1, height + mask->height - 1} of out->valid
+ * (replaces vips_convf_gen convf.c:185-282 / vips_convi_gen convi.c:752-852; the arithmetic is
+ * vb200_conv's).  colour: `in` covers out->valid, in->im.Type is the source space (replaces
+ * vips_colour_gen colour.c:119-156 over the route of vips_colourspace_build colourspace.c:551-617).
+ */
+int vb200_conv_gen(const VB200Region *out, const VB200Region *in, const VB200Mask *mask, int precision);
+int vb200_colour_gen(const VB200Region *out, const VB200Region *in, int space);
 
 /* -------------------------------------------- resample: scanline kernel seam
  *

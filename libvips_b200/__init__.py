@@ -113,6 +113,8 @@ def lib():
         L.vb200_reduceh_gen.argtypes = [RP, RP, C.POINTER(CReduceParams)]
         L.vb200_shrinkv_gen.argtypes = [RP, RP, C.c_int]
         L.vb200_shrinkh_gen.argtypes = [RP, RP, C.c_int]
+        L.vb200_conv_gen.argtypes = [RP, RP, C.POINTER(CMask), C.c_int]
+        L.vb200_colour_gen.argtypes = [RP, RP, C.c_int]
         _lib = L
     return _lib
 

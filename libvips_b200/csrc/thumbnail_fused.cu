@@ -429,26 +429,6 @@ mbar_wait(unsigned bar, unsigned parity)
 	} while (!done);
 }
 
-/* the same wait for a warp that expects to idle (producer, H warp): back off between
- * polls so that the spin does not take issue slots from the warps doing the arithmetic
- */
-__device__ __forceinline__ void
-mbar_wait_idle(unsigned bar, unsigned parity, unsigned ns)
-{
-	unsigned done;
-	for (;;) {
-		asm volatile("{\n\t.reg .pred p;\n\t"
-					 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-					 "selp.u32 %0, 1, 0, p;\n\t}"
-					 : "=r"(done)
-					 : "r"(bar), "r"(parity)
-					 : "memory");
-		if (done)
-			break;
-		__nanosleep(ns);
-	}
-}
-
 __device__ __forceinline__ void
 mbar_arrive(unsigned bar)
 {
@@ -468,14 +448,6 @@ bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
 				 "l"(src), "r"(bytes), "r"(bar)
 				 : "memory");
-}
-
-__device__ __forceinline__ unsigned
-lds32(unsigned addr)
-{
-	unsigned v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-	return v;
 }
 
 /* idx / d for 0 <= idx < 4096 and 1 <= d: exact via a float reciprocal + one correction */

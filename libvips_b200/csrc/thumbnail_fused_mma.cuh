@@ -18,16 +18,18 @@
  * pipe that bounds the kernel.  Everything else (premultiply, box sums, shrinkh,
  * reduceh on the H warp, unpremultiply) is v3's arithmetic.
  *
- * Warp roles as v3:  V warps (2 adjacent input columns per thread) | H warp | P warp.
- * Each V warp owns 64 columns end to end -- it writes the quads of its columns and
- * runs the MMAs over them -- so the only synchronisation inside the V side is
- * __syncwarp().
+ * Warp roles:  12 V warps (COLS / (32 CPT); CPT = columns per thread) | NH H warps | 1 producer warp.
+ * Each V warp owns 32 CPT columns end to end -- it writes the quads of its columns and runs the
+ * MMAs over them -- so the only synchronisation inside the V side is __syncwarp().  NH (3 or 4) is
+ * chosen so that each SM sub-partition (warp slot % 4) carries the same number of V warps and the
+ * same share of the reduceh work: a TMA stage is refilled only when every V warp has read it, so
+ * the V warp on the most loaded sub-partition sets the pace of the CTA.
  *
  * Shared memory:
- *   stages  [S][2 VS][PITCH]      raw RGBA rows by cp.async.bulk (a stage = 2 shrunk rows)
+ *   stages  [S][NBOX][2 VS][PITCH]  raw RGBA rows as NBOX tiled-TMA boxes (a stage = 2 shrunk rows)
  *   bars    full[S] empty[S] shfull[2] shempty[2]
  *   quadbuf [8][NC][4] u32 (+16 B per quad slot: conflict-free A-fragment loads)
- *   sh      [2][8][NEmax / 2] uint2  reducev + shrinkh output, v3's pair layout
+ *   sh      [2][8][NC / HS / 2] uint2  reducev + shrinkh output, v3's pair layout
  *   hcoef, uscale
  */
 
