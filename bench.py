@@ -170,7 +170,17 @@ def side_workload(args):
         fmt = {torch.uint8: 0, torch.float32: 6, torch.int16: 3}[t.dtype]
         return CImage(w, h, b, fmt, interp, vb.DEVICE, C.c_void_p(t.data_ptr()), w * b * t.element_size())
 
-    def run(fn, alg_bytes, label, units, unit_name):
+    def cpu_side(cpu_fn, units, sample):
+        """the oracle port of the same op on a bounded sample, one host thread (it is a scalar port)"""
+        if args.no_cpu or cpu_fn is None:
+            return None
+        cpu_fn()
+        t = time.perf_counter()
+        cpu_fn()
+        dt = time.perf_counter() - t
+        return {"value": units / dt, "unit": "Mpixels/s", "cores": 1, "kind": "port", "sample": "%s, %.1f s" % (sample, dt)}
+
+    def run(fn, alg_bytes, label, units, unit_name, cpu=None):
         for _ in range(args.warmup):
             fn()
         torch.cuda.synchronize()
@@ -190,7 +200,7 @@ def side_workload(args):
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                                        "algorithmic_bytes": alg_bytes},
-                          "gpu_launches": int(vb.launch_count() - n0)}))
+                          "cpu_baseline": cpu, "gpu_launches": int(vb.launch_count() - n0)}))
 
     if args.workload == "convsep":
         n = 8192
@@ -203,7 +213,10 @@ def side_workload(args):
         def fn():
             cout = dimg(out, 22)
             vb._check(L.vb200_convsep(C.byref(cin), C.byref(cout), C.byref(cm), 1))
-        run(fn, 2 * a.numel() * 4, "vips_convsep 15-tap Gaussian float on 8192x8192 RGB float32", n * n / 1e6, "Mpixels/s")
+        from oracle import pyconv
+        ca = (np.random.default_rng(1234).random((2048, 2048, 3), dtype=np.float32) * 255)
+        cpu = cpu_side(lambda: pyconv.convsep(ca, m, scale, off, "float"), 2048 * 2048 / 1e6, "2048x2048x3 float32")
+        run(fn, 2 * a.numel() * 4, "vips_convsep 15-tap Gaussian float on 8192x8192 RGB float32", n * n / 1e6, "Mpixels/s", cpu)
     elif args.workload == "colour":
         n = 16384
         a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
@@ -220,8 +233,12 @@ def side_workload(args):
         fn()
         torch.cuda.synchronize()
         assert torch.equal(a, back), "sRGB -> Lab -> sRGB must be the identity on 8-bit data"
+        from oracle import pyoracle
+        ca = np.random.default_rng(1234).integers(0, 256, (2048, 2048, 3), dtype=np.uint8)
+        cpu = cpu_side(lambda: pyoracle.colourspace(pyoracle.colourspace(ca, "lab", "srgb"), "srgb", "lab"),
+                       2 * 2048 * 2048 / 1e6, "2048x2048x3 uint8, both directions")
         run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_colourspace sRGB->Lab->sRGB round trip on 16384x16384",
-            2 * n * n / 1e6, "Mpixels/s")
+            2 * n * n / 1e6, "Mpixels/s", cpu)
     elif args.workload == "reduce49":
         n = 4096
         a = torch.randint(0, 256, (n, n, 4), dtype=torch.uint8, device=dev)
@@ -231,8 +248,41 @@ def side_workload(args):
         def fn():
             cout = dimg(out, 22)
             vb._check(L.vb200_reduce(C.byref(cin), C.byref(cout), 8.0, 8.0, 5, 0.0))
+        from oracle import pyoracle
+        ca = np.random.default_rng(1234).integers(0, 256, (n, n, 4), dtype=np.uint8)
+        cpu = cpu_side(lambda: pyoracle.reduceh(pyoracle.reducev(ca, 8.0, "lanczos3", 0.0), 8.0, "lanczos3", 0.0),
+                       n * n / 1e6, "one 4096x4096 RGBA frame")
         run(fn, a.numel() + out.numel(), "vips_reduce(8, 8) Lanczos3 gap 0 (49 taps) on one 4096x4096 uchar RGBA",
-            n * n / 1e6, "Mpixels/s")
+            n * n / 1e6, "Mpixels/s", cpu)
+    elif args.workload == "upsize":
+        # vips_resize x2 = vips_affine + bicubic (resize.c:235-305)
+        n = 4096
+        a = torch.randint(0, 256, (n, n, 4), dtype=torch.uint8, device=dev)
+        out = torch.empty((2 * n, 2 * n, 4), dtype=torch.uint8, device=dev)
+        cin = dimg(a, 22)
+
+        def fn():
+            cout = dimg(out, 22)
+            vb._check(L.vb200_resize(C.byref(cin), C.byref(cout), 2.0, 2.0, 5, 2.0))
+        from oracle import pyoracle
+        ca = np.random.default_rng(1234).integers(0, 256, (1024, 1024, 4), dtype=np.uint8)
+        cpu = cpu_side(lambda: pyoracle.resize(ca, 2.0), 4 * 1024 * 1024 / 1e6, "1024x1024 RGBA -> 2048x2048")
+        run(fn, a.numel() + out.numel(), "vips_resize x2 (affine + bicubic) 4096x4096 uchar RGBA -> 8192x8192",
+            4 * n * n / 1e6, "output Mpixels/s", cpu)
+    elif args.workload == "sharpen":
+        # vips_sharpen defaults on an sRGB image (sRGB -> LabS, L blur + LUT, LabS -> sRGB)
+        n = 4096
+        a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
+        out = torch.empty_like(a)
+        cin = dimg(a, 22)
+
+        def fn():
+            cout = dimg(out, 22)
+            vb._check(L.vb200_sharpen(C.byref(cin), C.byref(cout), 0.5, 2.0, 10.0, 20.0, 0.0, 3.0))
+        from oracle import pyconv
+        ca = np.random.default_rng(1234).integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+        cpu = cpu_side(lambda: pyconv.sharpen(ca, "srgb"), 1024 * 1024 / 1e6, "1024x1024 RGB")
+        run(fn, 2 * a.numel(), "vips_sharpen defaults on 4096x4096 sRGB uchar", n * n / 1e6, "Mpixels/s", cpu)
     else:
         raise SystemExit("unknown workload %s" % args.workload)
 
@@ -248,7 +298,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0: one per host thread, at least 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="thumbnail",
-                    help="thumbnail (the headline, default) | convsep | colour | reduce49: the other BASELINE.json "
+                    help="thumbnail (the headline, default) | convsep | colour | reduce49 | upsize | sharpen: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
