@@ -17,6 +17,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -60,6 +61,82 @@ sfr(int v)
 {
 	const int round_by = v >= 0 ? (VB200_INTERPOLATE_SCALE >> 1) : -(VB200_INTERPOLATE_SCALE >> 1);
 	return (v + round_by) >> VB200_INTERPOLATE_SHIFT;
+}
+
+/* The common upsize: uchar, 4 bands, bicubic.  One thread per output pixel, all four channels at
+ * once: the 4 x 4 window is 16 32-bit loads through 4 clamped column offsets and 4 clamped row
+ * pointers, pixels are byte-transposed pairwise (PRMT) so that dp2a does two taps of one channel
+ * per instruction.  Same two-stage fixed-point sums as bicubic_unsigned_int_tab (bicubic.cpp:106-166).
+ */
+__device__ __forceinline__ int
+dp2a_lo_s(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
+__device__ __forceinline__ int
+dp2a_hi_s(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
+
+__global__ void __launch_bounds__(256)
+affine_bicubic_u8x4_kernel(const __grid_constant__ AffineDev P, const uint8_t *__restrict__ in, uint8_t *__restrict__ out)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= P.OW)
+		return;
+	const double ix = P.ixs[x];
+	const double iy = P.iys[y];
+	unsigned *q = (unsigned *) ((char *) out + (size_t) y * P.out_bpl) + x;
+	const int fx = (int) floor(ix);
+	const int fy = (int) floor(iy);
+	if (!(fx >= P.ile && fx <= P.iri && fy >= P.ito && fy <= P.ibo)) {
+		*q = 0;
+		return;
+	}
+	const int xi = (int) ix, yi = (int) iy;
+	const int sx = (int) __dmul_rn(__dmul_rn(ix, (double) VB200_TRANSFORM_SCALE), 2.0);
+	const int sy = (int) __dmul_rn(__dmul_rn(iy, (double) VB200_TRANSFORM_SCALE), 2.0);
+	const int tx = ((sx & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+	const int ty = ((sy & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+	const int4 cx = __ldg((const int4 *) (P.ci + tx * 4));
+	const int4 cy = __ldg((const int4 *) (P.ci + ty * 4));
+	const unsigned cx01 = ((unsigned) cx.y << 16) | ((unsigned) cx.x & 0xffffu);
+	const unsigned cx23 = ((unsigned) cx.w << 16) | ((unsigned) cx.z & 0xffffu);
+	int col[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		col[i] = max(0, min(xi - 1 + i - P.pad, P.w - 1));
+	const int cyv[4] = {cy.x, cy.y, cy.z, cy.w};
+	int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const int sy2 = max(0, min(yi - 1 + j - P.pad, P.h - 1));
+		const unsigned *row = (const unsigned *) (in + (size_t) sy2 * P.in_bpl);
+		const unsigned p0 = __ldg(row + col[0]), p1 = __ldg(row + col[1]), p2 = __ldg(row + col[2]), p3 = __ldg(row + col[3]);
+		const unsigned a01 = __byte_perm(p0, p1, 0x5140); /* [p0.c0 p1.c0 p0.c1 p1.c1] */
+		const unsigned b01 = __byte_perm(p0, p1, 0x7362); /* [p0.c2 p1.c2 p0.c3 p1.c3] */
+		const unsigned a23 = __byte_perm(p2, p3, 0x5140);
+		const unsigned b23 = __byte_perm(p2, p3, 0x7362);
+		const int r0 = ufr(dp2a_lo_s(cx23, a23, dp2a_lo_s(cx01, a01, 0)));
+		const int r1 = ufr(dp2a_hi_s(cx23, a23, dp2a_hi_s(cx01, a01, 0)));
+		const int r2 = ufr(dp2a_lo_s(cx23, b23, dp2a_lo_s(cx01, b01, 0)));
+		const int r3 = ufr(dp2a_hi_s(cx23, b23, dp2a_hi_s(cx01, b01, 0)));
+		acc[0] += cyv[j] * r0;
+		acc[1] += cyv[j] * r1;
+		acc[2] += cyv[j] * r2;
+		acc[3] += cyv[j] * r3;
+	}
+	unsigned v = 0;
+#pragma unroll
+	for (int c = 0; c < 4; c++)
+		v |= (unsigned) max(0, min(ufr(acc[c]), 255)) << (8 * c);
+	*q = v;
 }
 
 template <typename T>
@@ -211,7 +288,7 @@ dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a
 	const double tidx = idx - 1, tidy = idy - 1; /* the embed's one-pixel border, affine.c:533-534 */
 
 	/* the coordinate sequences of vips_affine_gen (affine.c:325-400), ib = ic = 0, odx = ody = 0 */
-	std::vector<double> host((size_t) OW + OH + 65 * 4);
+	std::vector<double> host((((size_t) OW + OH + 65 * 4) + 1) & ~(size_t) 1); /* even: the int table after it stays 16-byte aligned */
 	{
 		const double ox = 0 + ol - 0.0;
 		double ix = ia * ox + 0.0 * (0 + ot - 0.0);
@@ -281,6 +358,11 @@ dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a
 	P.interp = interp;
 	const dim3 grid((OW + 255) / 256, OH);
 #define AF(T) affine_scale_kernel<T><<<grid, 256, 0, s>>>(P, (const T *) in.data, (T *) out->data)
+	const bool u8x4 = in.fmt == VB200_FORMAT_UCHAR && in.bands == 4 && interp == INTERP_BICUBIC && (in.bpl & 3) == 0 &&
+		((uintptr_t) in.data & 3) == 0 && getenv("VB200_NO_AFFINE_X4") == nullptr;
+	if (u8x4)
+		affine_bicubic_u8x4_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *) in.data, (uint8_t *) out->data);
+	else
 	switch (in.fmt) {
 	case VB200_FORMAT_UCHAR: AF(uint8_t); break;
 	case VB200_FORMAT_CHAR: AF(int8_t); break;

@@ -26,14 +26,16 @@ def test_shrink_gens(vb):
     # rows 8..23 of shrinkv(a, 3) need input rows 24..71
     want = orc.shrinkv(a, 3)[8:24]
     out = np.zeros_like(want)
-    rin = region(vb, np.ascontiguousarray(a[24:72]), 0, 24)
+    src = np.ascontiguousarray(a[24:72])  # the CRegion holds a raw pointer: keep the array alive
+    rin = region(vb, src, 0, 24)
     rout = region(vb, out, 0, 8)
     vb._check(L.vb200_shrinkv_gen(C.byref(rout), C.byref(rin), 3))
     assert np.array_equal(out, want)
     # columns 5..24 of shrinkh(a, 4) need input columns 20..99
     want = np.ascontiguousarray(orc.shrinkh(a, 4)[:, 5:25])
     out = np.zeros_like(want)
-    rin = region(vb, np.ascontiguousarray(a[:, 20:100]), 20, 0)
+    src = np.ascontiguousarray(a[:, 20:100])
+    rin = region(vb, src, 20, 0)
     rout = region(vb, out, 5, 0)
     vb._check(L.vb200_shrinkh_gen(C.byref(rout), C.byref(rin), 4))
     assert np.array_equal(out, want)
@@ -63,7 +65,8 @@ def test_colour_gen(vb):
     a = rng.integers(0, 256, (40, 64, 3), dtype=np.uint8)
     want = np.ascontiguousarray(orc.colourspace(a, "lab", "srgb")[8:24, 16:48])
     out = np.zeros_like(want)
-    rin = region(vb, np.ascontiguousarray(a[4:30, 10:60]), 10, 4, interp=22)
+    src = np.ascontiguousarray(a[4:30, 10:60])
+    rin = region(vb, src, 10, 4, interp=22)
     rout = region(vb, out, 16, 8, interp=13)
     vb._check(vb.lib().vb200_colour_gen(C.byref(rout), C.byref(rin), 13))
     assert np.array_equal(out, want)
