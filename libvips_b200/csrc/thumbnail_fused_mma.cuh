@@ -43,6 +43,12 @@ constexpr int kV4Quads = 8; /* quad ring: K / 4 */
 #ifndef VB200_V4_STAGES
 #define VB200_V4_STAGES 4
 #endif
+#ifndef VB200_V4_NH768
+#define VB200_V4_NH768 3 /* H warps of the 768-column configuration (3: 74.3%, 4: 73.2% of HBM at 296 frames) */
+#endif
+#ifndef VB200_V4_MMA_UNROLL
+#define VB200_V4_MMA_UNROLL 2
+#endif
 
 /* timing experiment only: VB200_EXP_NOPREMUL drops the premultiply arithmetic (wrong pixels) */
 #ifndef VB200_V4_HADD2
@@ -69,7 +75,7 @@ struct V4HWarps {
 };
 template <int WCOLS, int CPT>
 struct V4HWarpsW {
-	static constexpr int value = WCOLS > 448 ? 4 : V4HWarps<CPT>::value;
+	static constexpr int value = WCOLS > 448 ? VB200_V4_NH768 : V4HWarps<CPT>::value;
 };
 
 template <int VS>
@@ -114,6 +120,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	constexpr int K = kV4Rows;
 	constexpr int S = V4Stages<VS>::value;
 	constexpr int NH = V4HWarpsW<WCOLS, CPT>::value;
+	constexpr int kMmaUnroll = VB200_V4_MMA_UNROLL;
 	/* a stage row is held as NBOX column boxes (a tiled-TMA box is at most 256 elements = 512 pixels wide) */
 	constexpr int NBOX = WCOLS + 8 > 512 ? 2 : 1;
 	constexpr int BOXW = (WCOLS + 8) / NBOX; /* pixels; even, a multiple of 4 */
@@ -415,7 +422,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		const uint4 bf = __ldg(&P.vbfrag[(size_t) (ya / K) * 32 + lane]); /* {hi b0, hi b1, lo b0, lo b1} */
 		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
 		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * K * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
-#pragma unroll 2
+#pragma unroll kMmaUnroll
 		for (int tp = 0; tp < 4 * CPT; tp++) {
 			unsigned a[2][4];
 			int dh[2][4], dl[2][4];
