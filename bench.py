@@ -30,9 +30,9 @@ TARGET = 512
 MPIX_PER_FRAME = W * H / 1e6
 METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per 4096x4096 frame, from the
-# committed `ncu --set full` capture (a launch of 148 frames: 10.1243 GB read, 159.4 MB written)
-DRAM_BYTES_PER_FRAME = (10.124292e9 + 159.375872e6) / 148
-DRAM_SOURCE = "profiles/r1p_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
+# committed `ncu --set full` capture (a launch of 148 frames: 10.1220 GB read, 159.4 MB written)
+DRAM_BYTES_PER_FRAME = (10.122020e9 + 159.401728e6) / 148
+DRAM_SOURCE = "profiles/r1q_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
 WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
 
 
