@@ -254,4 +254,103 @@ build_axis_table(AxisTable &t, int out_size, double residual, double offset, int
 	}
 }
 
+bool
+build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag)
+{
+	const int K = 8, QUADS = 8;
+	const int chunks = (out_size + K - 1) / K;
+	const int np = t.n_point;
+	vchunk.assign((size_t) chunks * 2, 0);
+	bfrag.assign((size_t) chunks * 32 * 4, 0);
+	for (int c = 0; c < chunks; c++) {
+		/* the rows this chunk's live taps touch (all-zero end taps do not count) */
+		int lo = INT_MAX, hi = INT_MIN;
+		for (int y = c * K; y < std::min(c * K + K, out_size); y++) {
+			const short *m = &t.ms[(size_t) t.phase[y] * np];
+			int a = 0, b = np - 1;
+			while (a < b && m[a] == 0)
+				a++;
+			while (b > a && m[b] == 0)
+				b--;
+			lo = std::min(lo, t.first[y] + a);
+			hi = std::max(hi, t.first[y] + b);
+		}
+		if (lo < 0)
+			return false;
+		int q0 = lo >> 2;
+		const int q1 = hi >> 2;
+		if (c > 0) {
+			/* quads are produced in order, without gaps */
+			q0 = std::min(q0, vchunk[(c - 1) * 2 + 1] + 1);
+			if (q1 < vchunk[(c - 1) * 2 + 1])
+				return false;
+		}
+		if (q1 - q0 + 1 > QUADS)
+			return false;
+		vchunk[c * 2] = q0;
+		vchunk[c * 2 + 1] = q1;
+		for (int lane = 0; lane < 32; lane++) {
+			const int tig = lane & 3, g = lane >> 2;
+			const int y = c * K + g;
+			unsigned w[4] = {0, 0, 0, 0}; /* hi b0, hi b1, lo b0, lo b1 */
+			for (int half = 0; half < 2; half++) {
+				const int slot = tig + 4 * half;
+				int q = -1;
+				for (int qq = q0; qq <= q1; qq++)
+					if ((qq & (QUADS - 1)) == slot)
+						q = qq;
+				for (int i = 0; i < 4; i++) {
+					int coef = 0;
+					if (q >= 0 && y < out_size) {
+						const int tap = 4 * q + i - t.first[y];
+						if (tap >= 0 && tap < np)
+							coef = t.ms[(size_t) t.phase[y] * np + tap];
+					}
+					w[half] |= (unsigned) ((coef >> 8) & 0xff) << (8 * i);
+					w[2 + half] |= (unsigned) (coef & 0xff) << (8 * i);
+				}
+			}
+			for (int k = 0; k < 4; k++)
+				bfrag[((size_t) c * 32 + lane) * 4 + k] = w[k];
+		}
+	}
+	return true;
+}
+
 } // namespace vb200
+
+/* Test hook (tests/test_mma_tables.py, CPU): the reducev geometry, sampling table and tensor-pipe
+ * tables of a vertical thumbnail shrink, exactly as the plan builds them.  Arrays are caller-sized:
+ * first/phase [*out_size], vchunk [2 * chunks], bfrag [128 * chunks], mask65 [65 * *n_point] shorts.
+ * Returns 0, 1 when the window does not fit the quad ring, -1 on bad arguments.
+ */
+extern "C" int
+vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_shrink, int *shrunk_size, int *out_size,
+	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows)
+{
+	using namespace vb200;
+	ReduceGeom g;
+	if (reduce_geometry("debug", in_size, shrink, VB200_KERNEL_LANCZOS3, 2.0, &g))
+		return -1;
+	if (g.out_size > cap_rows)
+		return -1;
+	AxisTable t;
+	build_axis_table(t, g.out_size, g.residual, g.offset, g.n_point, VB200_KERNEL_LANCZOS3, rect_size);
+	*int_shrink = g.int_shrink;
+	*shrunk_size = g.shrunk_size;
+	*out_size = g.out_size;
+	*n_point = g.n_point;
+	*embed = t.embed;
+	for (int i = 0; i < g.out_size; i++) {
+		first[i] = t.first[i];
+		phase[i] = t.phase[i];
+	}
+	memcpy(mask65, t.ms.data(), t.ms.size() * sizeof(short));
+	std::vector<int> vc;
+	std::vector<unsigned> bf;
+	if (!build_mma_tables(t, g.out_size, vc, bf))
+		return 1;
+	memcpy(vchunk, vc.data(), vc.size() * sizeof(int));
+	memcpy(bfrag, bf.data(), bf.size() * sizeof(unsigned));
+	return 0;
+}

@@ -1860,61 +1860,15 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	if (pl->tma_ok && (fp.VS == 2 || fp.VS == 4) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
 		getenv("VB200_NO_MMA") == nullptr) {
 		const int K = kV4Rows;
+		std::vector<int> vchunk_flat;
+		std::vector<unsigned> bfrag_flat;
+		bool ok = build_mma_tables(tv, pl->OH, vchunk_flat, bfrag_flat);
 		const int chunks = (pl->OH + K - 1) / K;
-		const int np = tv.n_point;
 		std::vector<int2> vchunk(chunks);
 		std::vector<uint4> bfrag((size_t) chunks * 32);
-		bool ok = true;
-		for (int c = 0; c < chunks && ok; c++) {
-			int lo = INT_MAX, hi = INT_MIN;
-			for (int y = c * K; y < std::min(c * K + K, pl->OH); y++) {
-				const short *m = &tv.ms[(size_t) tv.phase[y] * np];
-				int a = 0, b = np - 1;
-				while (a < b && m[a] == 0)
-					a++;
-				while (b > a && m[b] == 0)
-					b--;
-				lo = std::min(lo, tv.first[y] + a);
-				hi = std::max(hi, tv.first[y] + b);
-			}
-			if (lo < 0) {
-				ok = false;
-				break;
-			}
-			int q0 = lo >> 2;
-			const int q1 = hi >> 2;
-			if (c > 0) {
-				/* quads are produced in order, without gaps */
-				q0 = std::min(q0, vchunk[c - 1].y + 1);
-				if (q1 < vchunk[c - 1].y)
-					ok = false;
-			}
-			if (q1 - q0 + 1 > kV4Quads)
-				ok = false;
-			vchunk[c] = make_int2(q0, q1);
-			for (int lane = 0; lane < 32 && ok; lane++) {
-				const int tig = lane & 3, g = lane >> 2;
-				const int y = c * K + g;
-				unsigned w[4] = {0, 0, 0, 0}; /* hi b0, hi b1, lo b0, lo b1 */
-				for (int half = 0; half < 2; half++) {
-					const int slot = tig + 4 * half;
-					int q = -1;
-					for (int qq = q0; qq <= q1; qq++)
-						if ((qq & (kV4Quads - 1)) == slot)
-							q = qq;
-					for (int i = 0; i < 4; i++) {
-						int coef = 0;
-						if (q >= 0 && y < pl->OH) {
-							const int tap = 4 * q + i - tv.first[y];
-							if (tap >= 0 && tap < np)
-								coef = tv.ms[(size_t) tv.phase[y] * np + tap];
-						}
-						w[half] |= (unsigned) ((coef >> 8) & 0xff) << (8 * i);
-						w[2 + half] |= (unsigned) (coef & 0xff) << (8 * i);
-					}
-				}
-				bfrag[(size_t) c * 32 + lane] = make_uint4(w[0], w[1], w[2], w[3]);
-			}
+		if (ok) {
+			memcpy(vchunk.data(), vchunk_flat.data(), vchunk.size() * sizeof(int2));
+			memcpy(bfrag.data(), bfrag_flat.data(), bfrag.size() * sizeof(uint4));
 		}
 		/* band width: the fewest bands whose widest one fits the column budget */
 		const char *ev = getenv("VB200_V4_COLS");

@@ -93,6 +93,14 @@ struct AxisTable {
 void build_axis_table(AxisTable &t, int out_size, double residual, double offset, int n_point, int kernel,
 	int rect_size, int rect_origin = 0, int count = -1);
 
+/* Tables of the tensor-pipe reducev (thumbnail_fused_mma.cuh): per chunk of 8 output rows the
+ * {first, last} quad (4 box-shrunk rows) of its window in a ring of 8, and the 32 B fragments
+ * {hi b0, hi b1, lo b0, lo b1} of mma.m16n8k32 with the coefficients placed by ring slot.
+ * false when a chunk's window does not fit the ring (the plan then uses the dp2a kernels).
+ * Pure host code: tests/test_mma_tables.py replays the MMA arithmetic over these tables on the CPU.
+ */
+bool build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag);
+
 /* ------------------------------------------------------- resample device ops */
 
 int dev_shrinkv(const char *domain, const DevImage &in, DevImage *out, int vshrink, int ceil_mode, cudaStream_t s);

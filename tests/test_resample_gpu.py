@@ -7,6 +7,8 @@ max |diff| == 0, which is stricter than the 1 ULP the spec allows.
 Structure follows the reference's test/test-suite/test_resample.py: every
 format x kernel x factor, constant images, geometry/rounding, thumbnails.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -281,3 +283,29 @@ def test_thumbnail_tensor_pipe_kernel(vb, oracle, case):
     assert ("mma_kernel" in plan.kernel) == mma, plan.kernel
     want = np.stack([oracle.thumbnail_image(f, tw, th, size, has_alpha=alpha) for f in frames])
     same(plan.run_host(frames), want)
+
+
+@pytest.mark.parametrize("pad,shift", [(0, 0), (4096, 0), (48, 0), (20, 0), (0, 4)])
+def test_batch_device_strides_and_alignment(vb, oracle, pad, shift):
+    """Frame strides with padding (multiples of 16 keep the TMA kernels, others fall back to the
+    ld.global kernel) and a base pointer off the 16-byte grid: same pixels on every path."""
+    import torch
+    rng = np.random.default_rng(77)
+    n, h, w = 3, 512, 1024
+    frame_bytes = h * w * 4
+    stride = frame_bytes + pad
+    raw = torch.zeros(shift + n * stride + 64, dtype=torch.uint8, device="cuda")
+    frames = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+    for i in range(n):
+        raw[shift + i * stride: shift + i * stride + frame_bytes] = torch.from_numpy(frames[i].reshape(-1)).cuda()
+    plan = vb.ThumbnailPlan(w, h, 4, 128)
+    out = torch.zeros((n, plan.out_height, plan.out_width, 4), dtype=torch.uint8, device="cuda")
+    vb.set_stream(torch.cuda.current_stream().cuda_stream)
+    L = vb.lib()
+    L.vb200_thumbnail_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    vb._check(L.vb200_thumbnail_batch_device(plan._p, raw.data_ptr() + shift, stride, out.data_ptr(),
+                                             plan.out_frame_bytes, n))
+    torch.cuda.synchronize()
+    vb.set_stream(0)
+    want = np.stack([oracle.thumbnail_image(f, 128) for f in frames])
+    same(out.cpu().numpy(), want)
