@@ -43,6 +43,7 @@ typedef enum {
 typedef enum {
 	VB200_INTERPRETATION_MULTIBAND = 0,
 	VB200_INTERPRETATION_B_W = 1,
+	VB200_INTERPRETATION_CMYK = 15,
 	VB200_INTERPRETATION_XYZ = 12,
 	VB200_INTERPRETATION_LAB = 13,
 	VB200_INTERPRETATION_LABS = 21,
@@ -299,6 +300,29 @@ size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
  * or "leaf kernels" for an unfused plan.
  */
 const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
+
+/* ------------------------------------------------------------------ ICC
+ * vips_icc_import / vips_icc_export / vips_icc_transform (colour/icc_transform.c:813-945, :995-1117,
+ * :1166-1220) with the profile passed as a memory blob (what vips_icc_load_profile_blob hands lcms2).
+ * The reference's arithmetic is lcms2's; this is a from-specification ICC evaluator whose parity is
+ * pinned to lcms2 2.18 within a tolerance (tests/test_icc.py), not bit for bit.  Supported: RGB
+ * matrix/TRC, grey TRC and lut8 / lut16 (e.g. CMYK) profiles; intent VB200_INTENT_RELATIVE (the
+ * reference's default); depth 8 or 16;
+ * images whose band count equals the profile's channel count.  Everything else (the other intents,
+ * black point compensation, v4 lutAtoB tags, extra bands) returns -1: keep the host path.
+ */
+enum { VB200_INTENT_PERCEPTUAL = 0, VB200_INTENT_RELATIVE = 1, VB200_INTENT_SATURATION = 2, VB200_INTENT_ABSOLUTE = 3 };
+enum { VB200_PCS_LAB = 0, VB200_PCS_XYZ = 1 };
+int vb200_icc_import(const VB200Image *in, VB200Image *out, const void *profile, size_t profile_len, int intent, int pcs);
+int vb200_icc_export(const VB200Image *in, VB200Image *out, const void *profile, size_t profile_len, int intent, int depth,
+	int pcs);
+int vb200_icc_transform(const VB200Image *in, VB200Image *out, const void *in_profile, size_t in_len,
+	const void *out_profile, size_t out_len, int intent, int depth);
+/* Test hook, host only: the evaluator's per-pixel code on the CPU over n packed pixels
+ * (mode 0 import, 1 export, 2 transform; pa / pb = the profile(s)); returns the output band count.
+ */
+int vb200_debug_icc_eval(int mode, const void *in, int in_fmt, int in_bands, void *out, int n, const void *pa, size_t la,
+	const void *pb, size_t lb, int intent, int depth, int pcs);
 
 /* Test hook, host only (no GPU, no CUDA call): the reducev geometry, sampling table and
  * tensor-pipe tables of a vertical thumbnail shrink exactly as a plan builds them, so that the CPU

@@ -25,7 +25,9 @@ KERNELS = {"nearest": 0, "linear": 1, "cubic": 2, "mitchell": 3, "lanczos2": 4, 
            "mks2013": 6, "mks2021": 7}
 SIZES = {"both": 0, "up": 1, "down": 2, "force": 3}
 PRECISIONS = {"integer": 0, "float": 1, "approximate": 2}
-INTERPRETATIONS = {"multiband": 0, "b-w": 1, "xyz": 12, "lab": 13, "labs": 21, "srgb": 22, "rgb16": 25,
+INTENTS = {"perceptual": 0, "relative": 1, "saturation": 2, "absolute": 3}
+PCS = {"lab": 0, "xyz": 1}
+INTERPRETATIONS = {"multiband": 0, "b-w": 1, "cmyk": 15, "xyz": 12, "lab": 13, "labs": 21, "srgb": 22, "rgb16": 25,
                    "grey16": 26, "scrgb": 28}
 
 
@@ -114,6 +116,11 @@ def lib():
         L.vb200_shrinkv_gen.argtypes = [RP, RP, C.c_int]
         L.vb200_shrinkh_gen.argtypes = [RP, RP, C.c_int]
         L.vb200_conv_gen.argtypes = [RP, RP, C.POINTER(CMask), C.c_int]
+        L.vb200_icc_import.argtypes = [IP, IP, C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.vb200_icc_export.argtypes = [IP, IP, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
+        L.vb200_icc_transform.argtypes = [IP, IP, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int]
+        L.vb200_debug_icc_eval.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t,
+                                           C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
         L.vb200_colour_gen.argtypes = [RP, RP, C.c_int]
         _lib = L
     return _lib
@@ -280,6 +287,17 @@ class Image:
     def colourspace(self, space, source_space=None):
         src = self if source_space is None else Image(self.array, source_space)
         return src._call(lib().vb200_colourspace, _interp(space))
+
+    # ---- ICC (profiles are bytes: what vips_profile_load hands on)
+    def icc_import(self, profile, intent="relative", pcs="lab"):
+        return self._call(lib().vb200_icc_import, profile, len(profile), INTENTS[intent], PCS[pcs])
+
+    def icc_export(self, profile, intent="relative", depth=8, pcs="lab"):
+        return self._call(lib().vb200_icc_export, profile, len(profile), INTENTS[intent], int(depth), PCS[pcs])
+
+    def icc_transform(self, output_profile, input_profile, intent="relative", depth=8):
+        return self._call(lib().vb200_icc_transform, input_profile, len(input_profile), output_profile, len(output_profile),
+                          INTENTS[intent], int(depth))
 
 
 class ThumbnailPlan:
