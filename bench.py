@@ -283,6 +283,35 @@ def side_workload(args):
         ca = np.random.default_rng(1234).integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
         cpu = cpu_side(lambda: pyconv.sharpen(ca, "srgb"), 1024 * 1024 / 1e6, "1024x1024 RGB")
         run(fn, 2 * a.numel(), "vips_sharpen defaults on 4096x4096 sRGB uchar", n * n / 1e6, "Mpixels/s", cpu)
+    elif args.workload == "icc":
+        # vips_icc_import then vips_icc_export through an sRGB-like v4 matrix/TRC profile
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import icc_fixtures
+        prof = icc_fixtures.rgb_profile("srgb")
+        n = 8192
+        a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
+        lab = torch.empty((n, n, 3), dtype=torch.float32, device=dev)
+        back = torch.empty_like(a)
+        cin = dimg(a, 22)
+
+        def fn():
+            clab = dimg(lab, 13)
+            vb._check(L.vb200_icc_import(C.byref(cin), C.byref(clab), prof, len(prof), 1, 0))
+            clab = dimg(lab, 13)
+            cback = dimg(back, 22)
+            vb._check(L.vb200_icc_export(C.byref(clab), C.byref(cback), prof, len(prof), 1, 8, 0))
+        fn()
+        torch.cuda.synchronize()
+        assert (a.to(torch.int16) - back.to(torch.int16)).abs().max().item() <= 1, "import then export is the identity to 1 LSB"
+        cpu = None
+        from oracle import pylcms
+        if pylcms.available() and not args.no_cpu:
+            ca = np.random.default_rng(1234).integers(0, 256, (2048, 2048, 3), dtype=np.uint8)
+            cpu = cpu_side(lambda: pylcms.icc_export(pylcms.icc_import(ca, prof), prof), 2 * 2048 * 2048 / 1e6,
+                           "2048x2048x3 uint8 through lcms2 2.18 itself, both directions")
+            cpu["kind"] = "reference"
+        run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_icc_import + vips_icc_export (sRGB-like v4 profile) on 8192x8192",
+            2 * n * n / 1e6, "Mpixels/s", cpu)
     else:
         raise SystemExit("unknown workload %s" % args.workload)
 
@@ -298,7 +327,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0: one per host thread, at least 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="thumbnail",
-                    help="thumbnail (the headline, default) | convsep | colour | reduce49 | upsize | sharpen: the other BASELINE.json "
+                    help="thumbnail (the headline, default) | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
