@@ -23,6 +23,7 @@
  * per thread and vb200_debug_icc_eval calls it on the CPU, so the CPU test-suite exercises the same code.
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -606,6 +607,12 @@ struct IccJob {
 	int mode;		 /* 0 import, 1 export, 2 transform */
 	int pcs_xyz;	 /* import / export: the vips PCS is XYZ (D65, Y = 100), else Lab */
 	int in_fmt, depth;
+	/* integer input / output through a matrix or grey profile: the TRCs tabulated once on the host
+	 * (pool offsets, -1 = evaluate the curves per pixel): in_tab[c][code] = curve(code / max), and
+	 * out_thr[c][k] = curve((k - 0.5) / max), so that the output code is the number of thresholds
+	 * <= the linear value -- the same code floor(inverse(lin) * max + 0.5) gives, without a pow()
+	 */
+	int in_tab, in_tab_n, out_thr, out_thr_n;
 };
 
 /* one pixel; pin / pout point at the pixel's first element */
@@ -614,9 +621,26 @@ icc_pixel(const IccJob &J, const void *pin, void *pout)
 {
 	double dev[4] = {0, 0, 0, 0}, xyz[3] = {0, 0, 0};
 	if (J.mode == 0 || J.mode == 2) {
-		for (int i = 0; i < J.in.bands; i++)
-			dev[i] = load_dev(pin, J.in_fmt, i);
-		side_to_xyz(J.in, dev, xyz);
+		if (J.in_tab >= 0) {
+			double lin[3] = {0, 0, 0};
+			for (int i = 0; i < J.in.bands; i++) {
+				const int code = J.in_fmt == VB200_FORMAT_UCHAR ? ((const uint8_t *) pin)[i] : ((const uint16_t *) pin)[i];
+				lin[i] = J.in.pool[J.in_tab + i * J.in_tab_n + code];
+			}
+			if (J.in.model == MODEL_MATRIX)
+				for (int r = 0; r < 3; r++)
+					xyz[r] = J.in.m[r * 3] * lin[0] + J.in.m[r * 3 + 1] * lin[1] + J.in.m[r * 3 + 2] * lin[2];
+			else {
+				xyz[0] = lin[0] * D50X;
+				xyz[1] = lin[0] * D50Y;
+				xyz[2] = lin[0] * D50Z;
+			}
+		}
+		else {
+			for (int i = 0; i < J.in.bands; i++)
+				dev[i] = load_dev(pin, J.in_fmt, i);
+			side_to_xyz(J.in, dev, xyz);
+		}
 	}
 	if (J.mode == 0) {
 		float *q = (float *) pout;
@@ -652,6 +676,28 @@ icc_pixel(const IccJob &J, const void *pin, void *pout)
 			xyz[1] = 0.029582F * X + 0.990484F * Y + -0.017079F * Z;
 			xyz[2] = -0.009252F * X + 0.015073F * Y + 0.751678F * Z;
 		}
+	}
+	if (J.out_thr >= 0) {
+		for (int r = 0; r < J.out.bands; r++) {
+			const float lin = (float) (J.out.model == MODEL_MATRIX
+					? J.out.m[r * 3] * xyz[0] + J.out.m[r * 3 + 1] * xyz[1] + J.out.m[r * 3 + 2] * xyz[2]
+					: xyz[1] / D50Y);
+			/* thresholds 1 .. n - 1 ascend: count those <= lin */
+			const float *thr = J.out.pool + J.out_thr + r * J.out_thr_n;
+			int lo = 0, hi = J.out_thr_n - 1; /* the answer lies in [lo, hi] */
+			while (lo < hi) {
+				const int mid = (lo + hi + 1) >> 1;
+				if (thr[mid] <= lin)
+					lo = mid;
+				else
+					hi = mid - 1;
+			}
+			if (J.depth == 8)
+				((uint8_t *) pout)[r] = (uint8_t) lo;
+			else
+				((uint16_t *) pout)[r] = (uint16_t) lo;
+		}
+		return;
 	}
 	side_from_xyz(J.out, xyz, dev);
 	for (int i = 0; i < J.out.bands; i++)
@@ -724,6 +770,38 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, IccJo
 		*out_type = J->out.bands == 1 ? (sp.depth == 8 ? VB200_INTERPRETATION_B_W : VB200_INTERPRETATION_GREY16)
 			: J->out.bands == 3		  ? (sp.depth == 8 ? VB200_INTERPRETATION_sRGB : VB200_INTERPRETATION_RGB16)
 									  : VB200_INTERPRETATION_CMYK;
+	}
+	/* tabulate the TRCs for integer codes (the curves read `pool` themselves: evaluate against the host copy) */
+	J->in_tab = J->out_thr = -1;
+	const bool tabulate = getenv("VB200_NO_ICC_TABLES") == nullptr;
+	if (tabulate && (sp.mode == 0 || sp.mode == 2) && J->in.model != MODEL_LUT &&
+		(in_fmt == VB200_FORMAT_UCHAR || in_fmt == VB200_FORMAT_USHORT)) {
+		const int n = in_fmt == VB200_FORMAT_UCHAR ? 256 : 65536;
+		std::vector<float> tab((size_t) J->in.bands * n);
+		for (int c = 0; c < J->in.bands; c++)
+			for (int i = 0; i < n; i++)
+				tab[(size_t) c * n + i] = (float) curve_fwd(J->in.curve[c], pool.data(), (double) i / (n - 1));
+		J->in_tab = (int) pool.size();
+		J->in_tab_n = n;
+		pool.insert(pool.end(), tab.begin(), tab.end());
+	}
+	if (tabulate && (sp.mode == 1 || sp.mode == 2) && J->out.model != MODEL_LUT) {
+		const int n = sp.depth == 8 ? 256 : 65536;
+		std::vector<float> thr((size_t) J->out.bands * n);
+		bool monotone = true;
+		for (int c = 0; c < J->out.bands; c++) {
+			thr[(size_t) c * n] = -3.0e38f; /* code 0 is always reached */
+			for (int k = 1; k < n; k++) {
+				thr[(size_t) c * n + k] = (float) curve_fwd(J->out.curve[c], pool.data(), (k - 0.5) / (n - 1));
+				if (thr[(size_t) c * n + k] < thr[(size_t) c * n + k - 1])
+					monotone = false;
+			}
+		}
+		if (monotone) {
+			J->out_thr = (int) pool.size();
+			J->out_thr_n = n;
+			pool.insert(pool.end(), thr.begin(), thr.end());
+		}
 	}
 	return 0;
 }
