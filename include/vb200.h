@@ -308,8 +308,8 @@ const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
  * pinned to lcms2 2.18 within a tolerance (tests/test_icc.py), not bit for bit.  Supported: RGB
  * matrix/TRC, grey TRC and lut8 / lut16 (e.g. CMYK) profiles; intent VB200_INTENT_RELATIVE (the
  * reference's default); depth 8 or 16;
- * images whose band count equals the profile's channel count.  Everything else (the other intents,
- * black point compensation, v4 lutAtoB tags, extra bands) returns -1: keep the host path.
+ * bands after the profile's channels ride along as in vips_colour_build.  Everything else (the other
+ * intents, black point compensation, v4 lutAtoB tags) returns -1: keep the host path.
  */
 enum { VB200_INTENT_PERCEPTUAL = 0, VB200_INTENT_RELATIVE = 1, VB200_INTENT_SATURATION = 2, VB200_INTENT_ABSOLUTE = 3 };
 enum { VB200_PCS_LAB = 0, VB200_PCS_XYZ = 1 };

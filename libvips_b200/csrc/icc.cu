@@ -613,11 +613,16 @@ struct IccJob {
 	 * <= the linear value -- the same code floor(inverse(lin) * max + 0.5) gives, without a pow()
 	 */
 	int in_tab, in_tab_n, out_thr, out_thr_n;
+	/* bands after the colour channels ride along (vips_colour_build, colour.c:196-291): rescaled by the ratio
+	 * of the interpretations' alpha ranges in float, then cast to the output format with a clip
+	 */
+	int extra, out_fmt, alpha_rescale;
+	float alpha_a;
 };
 
 /* one pixel; pin / pout point at the pixel's first element */
 HD void
-icc_pixel(const IccJob &J, const void *pin, void *pout)
+icc_colour(const IccJob &J, const void *pin, void *pout)
 {
 	double dev[4] = {0, 0, 0, 0}, xyz[3] = {0, 0, 0};
 	if (J.mode == 0 || J.mode == 2) {
@@ -704,6 +709,33 @@ icc_pixel(const IccJob &J, const void *pin, void *pout)
 		store_dev(pout, J.depth, i, dev[i]);
 }
 
+HD void
+icc_pixel(const IccJob &J, const void *pin, void *pout)
+{
+	icc_colour(J, pin, pout);
+	const int in_bands = J.mode == 1 ? 3 : J.in.bands;
+	const int out_bands = J.mode == 0 ? 3 : J.out.bands;
+	for (int e = 0; e < J.extra; e++) {
+		double v = J.in_fmt == VB200_FORMAT_UCHAR ? (double) ((const uint8_t *) pin)[in_bands + e]
+			: J.in_fmt == VB200_FORMAT_USHORT	  ? (double) ((const uint16_t *) pin)[in_bands + e]
+												  : (double) ((const float *) pin)[in_bands + e];
+		if (J.alpha_rescale) {
+			const float scaled = J.alpha_a * (float) v + 0.0f;
+			v = (double) scaled;
+		}
+		if (J.out_fmt == VB200_FORMAT_UCHAR) {
+			const double m = 255.0 < v ? 255.0 : v; /* VIPS_CLIP with C's ?: (NaN -> 0) */
+			((uint8_t *) pout)[out_bands + e] = (uint8_t) (0.0 > m ? 0.0 : m);
+		}
+		else if (J.out_fmt == VB200_FORMAT_USHORT) {
+			const double m = 65535.0 < v ? 65535.0 : v;
+			((uint16_t *) pout)[out_bands + e] = (uint16_t) (0.0 > m ? 0.0 : m);
+		}
+		else
+			((float *) pout)[out_bands + e] = (float) v;
+	}
+}
+
 __global__ void __launch_bounds__(256)
 icc_kernel(const __grid_constant__ IccJob J, const char *__restrict__ in, size_t in_bpl, size_t in_ps, char *__restrict__ out,
 	size_t out_bpl, size_t out_ps, int w)
@@ -723,8 +755,8 @@ struct JobSpec {
 };
 
 int
-build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, IccJob *J, std::vector<float> &pool, int *out_bands,
-	int *out_fmt, int *out_type)
+build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, int in_type, IccJob *J, std::vector<float> &pool,
+	int *out_bands, int *out_fmt, int *out_type)
 {
 	memset((void *) J, 0, sizeof(*J));
 	J->mode = sp.mode;
@@ -742,11 +774,11 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, IccJo
 			error(domain, "band format %d not supported on the device path", in_fmt);
 			return -1;
 		}
-		if (in_bands != J->in.bands) {
-			error(domain, "image has %d bands, the input profile wants %d (extra bands are not handled on the device path)",
-				in_bands, J->in.bands);
+		if (in_bands < J->in.bands) {
+			error(domain, "image has %d bands, the input profile wants %d", in_bands, J->in.bands);
 			return -1;
 		}
+		J->extra = in_bands - J->in.bands;
 	}
 	if (sp.mode == 1 || sp.mode == 2) {
 		const void *p = sp.mode == 1 ? sp.pa : sp.pb;
@@ -754,9 +786,12 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, IccJo
 		if (parse_side(domain, p, l, sp.intent, false, &J->out, pool))
 			return -1;
 	}
-	if (sp.mode == 1 && (in_fmt != VB200_FORMAT_FLOAT || in_bands != 3)) {
-		error(domain, "export wants a 3-band float PCS image");
-		return -1;
+	if (sp.mode == 1) {
+		if (in_fmt != VB200_FORMAT_FLOAT || in_bands < 3) {
+			error(domain, "export wants a float PCS image of 3 bands (+ extra bands)");
+			return -1;
+		}
+		J->extra = in_bands - 3;
 	}
 	if (sp.mode == 0) {
 		*out_bands = 3;
@@ -770,6 +805,14 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, IccJo
 		*out_type = J->out.bands == 1 ? (sp.depth == 8 ? VB200_INTERPRETATION_B_W : VB200_INTERPRETATION_GREY16)
 			: J->out.bands == 3		  ? (sp.depth == 8 ? VB200_INTERPRETATION_sRGB : VB200_INTERPRETATION_RGB16)
 									  : VB200_INTERPRETATION_CMYK;
+	}
+	{
+		/* the extra bands: colour.c:252-291 */
+		const double before = interpretation_max_alpha(in_type), after = interpretation_max_alpha(*out_type);
+		J->alpha_rescale = before != after;
+		J->alpha_a = (float) (after / before);
+		J->out_fmt = *out_fmt;
+		*out_bands += J->extra;
 	}
 	/* tabulate the TRCs for integer codes (the curves read `pool` themselves: evaluate against the host copy) */
 	J->in_tab = J->out_thr = -1;
@@ -819,7 +862,7 @@ run_icc(const char *domain, const VB200Image *in, VB200Image *out, const JobSpec
 	IccJob J;
 	std::vector<float> pool;
 	int ob, of, ot;
-	if (build_job(domain, sp, in->BandFmt, in->Bands, &J, pool, &ob, &of, &ot))
+	if (build_job(domain, sp, in->BandFmt, in->Bands, in->Type, &J, pool, &ob, &of, &ot))
 		return -1;
 	DevImage din, dout;
 	if (to_device(domain, in, &din, s))
@@ -892,7 +935,9 @@ vb200_debug_icc_eval(int mode, const void *in, int in_fmt, int in_bands, void *o
 	IccJob J;
 	std::vector<float> pool;
 	int ob, of, ot;
-	if (build_job("icc_eval", sp, in_fmt, in_bands, &J, pool, &ob, &of, &ot))
+	const int in_type = mode == 1 ? (pcs == VB200_PCS_XYZ ? VB200_INTERPRETATION_XYZ : VB200_INTERPRETATION_LAB)
+		: in_fmt == VB200_FORMAT_USHORT ? VB200_INTERPRETATION_RGB16 : VB200_INTERPRETATION_sRGB;
+	if (build_job("icc_eval", sp, in_fmt, in_bands, in_type, &J, pool, &ob, &of, &ot))
 		return -1;
 	J.in.pool = J.out.pool = pool.data();
 	const size_t ips = format_sizeof(in_fmt) * in_bands, ops = format_sizeof(of) * ob;

@@ -30,7 +30,7 @@ def host_eval(mode, a, pa, pb=None, depth=8, pcs=0, intent=1):
     L.vb200_error_buffer.restype = C.c_char_p
     a = np.ascontiguousarray(a)
     n = a.size // a.shape[-1]
-    out = np.zeros((n, 4), np.float32 if mode == 0 else (np.uint8 if depth == 8 else np.uint16))
+    out = np.zeros((n, 8), np.float32 if mode == 0 else (np.uint8 if depth == 8 else np.uint16))
     ob = L.vb200_debug_icc_eval(mode, a.ctypes.data, FMT[a.dtype], a.shape[-1], out.ctypes.data, n, pa, len(pa), pb,
                                 len(pb) if pb else 0, intent, depth, pcs)
     if ob < 0:
@@ -140,9 +140,24 @@ def test_known_answers_and_refusals():
     with pytest.raises(vb.Error, match="intent"):
         host_eval(0, np.zeros((1, 3), np.uint8), prof, intent=0)
     with pytest.raises(vb.Error, match="bands"):
-        host_eval(0, np.zeros((1, 4), np.uint8), prof)
+        host_eval(0, np.zeros((1, 2), np.uint8), prof)
     with pytest.raises(vb.Error, match="ICC"):
         host_eval(0, np.zeros((1, 3), np.uint8), b"not a profile" * 20)
+
+
+def test_extra_bands_ride_along():
+    """vips_colour_build detaches the bands after the colour channels and re-attaches them cast to the output
+    format, rescaled when the interpretations' alpha ranges differ (colour.c:196-291)"""
+    prof = F.rgb_profile()
+    a = np.random.default_rng(9).integers(0, 256, (500, 5), dtype=np.uint8)
+    lab = host_eval(0, a, prof)
+    assert lab.shape == (500, 5)
+    assert np.array_equal(lab[:, :3], host_eval(0, np.ascontiguousarray(a[:, :3]), prof))
+    assert np.array_equal(lab[:, 3:], a[:, 3:].astype(np.float32))              # sRGB -> Lab: both 0..255
+    back = host_eval(1, lab, prof)
+    assert np.array_equal(back[:, 3:], a[:, 3:]) and np.abs(back[:, :3].astype(int) - a[:, :3]).max() <= 1
+    wide = host_eval(2, a, prof, F.rgb_profile("gamma"), depth=16)               # sRGB -> RGB16: alpha x 257
+    assert np.array_equal(wide[:, 3:], a[:, 3:].astype(np.uint16) * 257)
 
 
 @pytest.mark.gpu
@@ -165,6 +180,9 @@ def test_gpu_matches_host_evaluation(vb):
     c = rng.integers(0, 65536, (32, 48, 4), dtype=np.uint16)
     got = vb.Image(c, "cmyk").icc_import(ink, pcs="xyz").numpy()
     assert np.abs(got.reshape(-1, 3) - host_eval(0, c.reshape(-1, 4), ink, pcs=1)).max() < 2e-3
+    rgba = rng.integers(0, 256, (24, 40, 4), dtype=np.uint8)
+    got = vb.Image(rgba, "srgb").icc_transform(rgb, rgb, depth=16).numpy()
+    assert got.shape == (24, 40, 4) and np.array_equal(got[..., 3], rgba[..., 3].astype(np.uint16) * 257)
     g = rng.integers(0, 256, (16, 40, 1), dtype=np.uint8)
     got = vb.Image(g, "b-w").icc_transform(rgb, grey, depth=16).numpy()
     want = host_eval(2, g.reshape(-1, 1), grey, rgb, depth=16).reshape(16, 40, 3)
