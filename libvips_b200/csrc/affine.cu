@@ -68,6 +68,19 @@ sfr(int v)
  * pointers, pixels are byte-transposed pairwise (PRMT) so that dp2a does two taps of one channel
  * per instruction.  Same two-stage fixed-point sums as bicubic_unsigned_int_tab (bicubic.cpp:106-166).
  */
+/* vips_zoom: out(x, y) = in(x / xfac, y / yfac), pixels of ps bytes */
+__global__ void __launch_bounds__(256)
+zoom_kernel(const char *__restrict__ in, size_t in_bpl, char *__restrict__ out, size_t out_bpl, int ow, int ps, int xf, int yf)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= ow)
+		return;
+	const char *p = in + (size_t) (blockIdx.y / yf) * in_bpl + (size_t) (x / xf) * ps;
+	char *q = out + (size_t) blockIdx.y * out_bpl + (size_t) x * ps;
+	for (int i = 0; i < ps; i++)
+		q[i] = p[i];
+}
+
 __device__ __forceinline__ int
 dp2a_lo_s(unsigned coef, unsigned bytes, int acc)
 {
@@ -389,11 +402,25 @@ dev_resize_up(const char *domain, const DevImage &in, DevImage *out, double hsca
 	const int interp = kernel == VB200_KERNEL_NEAREST ? INTERP_NEAREST
 		: (kernel == VB200_KERNEL_LINEAR ? INTERP_BILINEAR : INTERP_BICUBIC);
 	if (kernel == VB200_KERNEL_NEAREST && hscale == floor(hscale) && vscale == floor(vscale)) {
-		/* the reference takes vips_zoom here (resize.c:263-271); pixel replication is
-		 * not the same code path as the nearest affine, and it is not restated yet
+		/* vips_zoom (resize.c:263-271, conversion/zoom.c:95-227): every input pixel becomes an
+		 * xfac x yfac block -- exact replication, not the nearest affine (whose coordinate is
+		 * built by repeated addition of 1 / scale and can land one pixel low for scales like 3)
 		 */
-		error(domain, "integral nearest-neighbour enlargement (vips_zoom) is not on the device path");
-		return -1;
+		const int xf = (int) floor(hscale), yf = (int) floor(vscale);
+		if ((long long) in.w * xf > 100000000LL || (long long) in.h * yf > 100000000LL) {
+			error(domain, "zoom factors too large");
+			return -1;
+		}
+		if (dev_image_new(domain, out, in.w * xf, in.h * yf, in.bands, in.fmt, in.type, s))
+			return -1;
+		const int ps = (int) (format_sizeof(in.fmt) * in.bands);
+		const dim3 grid((out->w + 255) / 256, out->h);
+		zoom_kernel<<<grid, 256, 0, s>>>((const char *) in.data, in.bpl, (char *) out->data, out->bpl, out->w, ps, xf, yf);
+		const cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "zoom_kernel");
+		count_launch();
+		return 0;
 	}
 	const double idx = kernel == VB200_KERNEL_NEAREST ? 0.0 : 0.5 * (1.0 - 1.0 / hscale);
 	const double idy = kernel == VB200_KERNEL_NEAREST ? 0.0 : 0.5 * (1.0 - 1.0 / vscale);

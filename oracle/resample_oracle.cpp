@@ -928,6 +928,18 @@ orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, doub
 		int interp, ow, oh;
 		if (mixed)
 			return -1;
+		const double ch = std::max(hscale, 1.0 / w), cv = std::max(vscale, 1.0 / h);
+		if (kernel == ORC_KERNEL_NEAREST && ch == floor(ch) && cv == floor(cv)) {
+			/* vips_zoom (resize.c:263-271; conversion/zoom.c:95-227 paints each input pixel as an
+			 * xfac x yfac block): out(x, y) = in(x / xfac, y / yfac), any format
+			 */
+			const int xf = (int) floor(ch), yf = (int) floor(cv);
+			const size_t ps = orc_sizeof_format(fmt) * bands;
+			for (int y = 0; y < h * yf; y++)
+				for (int x = 0; x < w * xf; x++)
+					memcpy((char *) out + ((size_t) y * w * xf + x) * ps, (const char *) in + ((size_t) (y / yf) * w + x / xf) * ps, ps);
+			return 0;
+		}
 		orc_resize_affine_args(std::max(hscale, 1.0 / w), std::max(vscale, 1.0 / h), kernel, &a, &d, &idx, &idy, &interp);
 		if (orc_affine_size(w, h, a, 0, 0, d, &ow, &oh))
 			return -1;

@@ -73,5 +73,18 @@ def test_gpu_mixed_and_zoom_fail_loudly(vb):
     a = np.zeros((20, 20, 1), np.uint8)
     with pytest.raises(vb.Error):
         vb.Image(a).resize(2.0, 0.5)
-    with pytest.raises(vb.Error):
-        vb.Image(a).resize(2.0, kernel="nearest")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.float32])
+def test_gpu_zoom(vb, dt):
+    """integral nearest enlargement is vips_zoom (resize.c:263-271): exact replication, also for factors
+    like 3 and 7 where a coordinate built by repeated addition of 1 / scale would drift"""
+    rng = np.random.default_rng(21)
+    a = (rng.random((37, 53, 3)) * 200).astype(dt)
+    for hs, vs in ((2.0, 2.0), (3.0, 7.0), (5.0, 1.0)):
+        got = vb.Image(a).resize(hs, vs, kernel="nearest").numpy()
+        want = np.repeat(np.repeat(a, int(vs), axis=0), int(hs), axis=1)
+        assert np.array_equal(got, want)
+        if vs > 1.0 or hs > 1.0:
+            assert np.array_equal(orc.resize(a, hs, vs, kernel="nearest"), want)
