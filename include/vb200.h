@@ -328,10 +328,11 @@ int vb200_debug_icc_eval(int mode, const void *in, int in_fmt, int in_bands, voi
  * tensor-pipe tables of a vertical thumbnail shrink exactly as a plan builds them, so that the CPU
  * test suite can replay the MMA arithmetic over them (tests/test_mma_tables.py).  Caller-sized arrays:
  * first / phase [cap_rows], mask65 [65 * n_point] shorts, vchunk [2 * chunks], bfrag [128 * chunks]
- * with chunks = ceil(out_size / 8).  0 = ok, 1 = window does not fit the quad ring, -1 = bad arguments.
+ * with chunks = ceil(out_size / *rows_per_chunk) (the largest of 8 .. 4 rows whose windows fit).  0 = ok, 1 = window does not fit the quad ring, -1 = bad arguments.
  */
 int vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_shrink, int *shrunk_size, int *out_size,
-	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows);
+	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows,
+	int *rows_per_chunk);
 
 /* pinned host memory for the pump (cudaHostAlloc / cudaFreeHost) */
 void *vb200_host_alloc(size_t bytes);

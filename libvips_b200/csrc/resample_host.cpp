@@ -255,9 +255,11 @@ build_axis_table(AxisTable &t, int out_size, double residual, double offset, int
 }
 
 bool
-build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag)
+build_mma_tables(const AxisTable &t, int out_size, int rows, std::vector<int> &vchunk, std::vector<unsigned> &bfrag)
 {
-	const int K = 8, QUADS = 8;
+	const int K = rows, QUADS = 8; /* rows: output rows per chunk, <= 8 (the N of the MMA; columns past it are zero) */
+	if (K < 1 || K > 8)
+		return false;
 	const int chunks = (out_size + K - 1) / K;
 	const int np = t.n_point;
 	vchunk.assign((size_t) chunks * 2, 0);
@@ -291,7 +293,7 @@ build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std
 		vchunk[c * 2 + 1] = q1;
 		for (int lane = 0; lane < 32; lane++) {
 			const int tig = lane & 3, g = lane >> 2;
-			const int y = c * K + g;
+			const int y = g < K ? c * K + g : out_size; /* fragment columns past the chunk's rows stay zero */
 			unsigned w[4] = {0, 0, 0, 0}; /* hi b0, hi b1, lo b0, lo b1 */
 			for (int half = 0; half < 2; half++) {
 				const int slot = tig + 4 * half;
@@ -317,16 +319,28 @@ build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std
 	return true;
 }
 
+int
+pick_mma_rows(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag)
+{
+	/* most output rows per chunk first: fewer MMAs per row */
+	for (int rows = 8; rows >= 4; rows--)
+		if (build_mma_tables(t, out_size, rows, vchunk, bfrag))
+			return rows;
+	return 0;
+}
+
 } // namespace vb200
 
 /* Test hook (tests/test_mma_tables.py, CPU): the reducev geometry, sampling table and tensor-pipe
  * tables of a vertical thumbnail shrink, exactly as the plan builds them.  Arrays are caller-sized:
- * first/phase [*out_size], vchunk [2 * chunks], bfrag [128 * chunks], mask65 [65 * *n_point] shorts.
+ * first/phase [*out_size], vchunk [2 * chunks], bfrag [128 * chunks] with chunks = ceil(out_size / rows_per_chunk),
+ * mask65 [65 * *n_point] shorts.
  * Returns 0, 1 when the window does not fit the quad ring, -1 on bad arguments.
  */
 extern "C" int
 vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_shrink, int *shrunk_size, int *out_size,
-	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows)
+	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows,
+	int *rows_per_chunk)
 {
 	using namespace vb200;
 	ReduceGeom g;
@@ -348,8 +362,10 @@ vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_shrin
 	memcpy(mask65, t.ms.data(), t.ms.size() * sizeof(short));
 	std::vector<int> vc;
 	std::vector<unsigned> bf;
-	if (!build_mma_tables(t, g.out_size, vc, bf))
+	const int rows = pick_mma_rows(t, g.out_size, vc, bf);
+	if (!rows)
 		return 1;
+	*rows_per_chunk = rows;
 	memcpy(vchunk, vc.data(), vc.size() * sizeof(int));
 	memcpy(bfrag, bf.data(), bf.size() * sizeof(unsigned));
 	return 0;

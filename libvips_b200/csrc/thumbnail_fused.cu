@@ -84,6 +84,7 @@ struct FusedParams {
 	/* v4 (thumbnail_fused_mma.cuh) */
 	const int2 *vchunk;	 /* [ceil(OH / 8)] {first quad, last quad} of each 8-row chunk */
 	const uint4 *vbfrag; /* [chunks][32] B fragments {hi b0, hi b1, lo b0, lo b1} */
+	int mma_rows;		 /* output rows per chunk (4 .. 8) */
 	/* alpha */
 	int premul;		  /* 1: premultiply/unpremultiply with max_alpha */
 	double max_alpha; /* LUTs are derived from it in the prologue */
@@ -1622,7 +1623,7 @@ launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 	fp.TW = pl->mma_tw;
 	fp.NT = pl->mma_nt;
 	fp.NEmax = pl->mma_nemax;
-	const int K = kV4Rows;
+	const int K = fp.mma_rows;
 	const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
 	int rpc = ((pl->OH + K - 1) / K) * K;
 	const int ctas = pl->mma_cols > 448 ? 148 : 2 * 148;
@@ -1859,11 +1860,12 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	pl->mma_ok = false;
 	if (pl->tma_ok && (fp.VS == 2 || fp.VS == 4) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
 		getenv("VB200_NO_MMA") == nullptr) {
-		const int K = kV4Rows;
 		std::vector<int> vchunk_flat;
 		std::vector<unsigned> bfrag_flat;
-		bool ok = build_mma_tables(tv, pl->OH, vchunk_flat, bfrag_flat);
-		const int chunks = (pl->OH + K - 1) / K;
+		const int K = pick_mma_rows(tv, pl->OH, vchunk_flat, bfrag_flat); /* 0: no chunking fits the ring */
+		bool ok = K > 0;
+		fp.mma_rows = K;
+		const int chunks = ok ? (pl->OH + K - 1) / K : 0;
 		std::vector<int2> vchunk(chunks);
 		std::vector<uint4> bfrag((size_t) chunks * 32);
 		if (ok) {
@@ -1916,7 +1918,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			const size_t box_bytes = ((size_t) 2 * fp.VS * (pitch / nbox) + 127) & ~(size_t) 127;
 			pl->smem_mma = (size_t) stages * nbox * box_bytes + (2 * stages + 4) * 8 +
 				(size_t) kV4Quads * ((size_t) pl->mma_nt * pl->mma_cpt * 16 + 16) +
-				(size_t) 2 * K * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +
+				(size_t) 2 * kV4Rows * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +
 				(size_t) (fp.nhsets * fp.NPh + 256) * 4;
 			const size_t n_ch = vchunk.size() * sizeof(int2), n_bf = bfrag.size() * sizeof(uint4);
 			if (pl->smem_mma <= (wcols > 448 ? 226 : 113) * 1024) {

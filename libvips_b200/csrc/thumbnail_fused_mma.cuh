@@ -117,7 +117,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 
-	constexpr int K = kV4Rows;
+	constexpr int KM = kV4Rows; /* rows the sh buffers hold */
+	const int K = P.mma_rows;   /* output rows per chunk, 4 .. 8: as many as keep every chunk's tap window inside the 32-row ring */
 	constexpr int S = V4Stages<VS>::value;
 	constexpr int NH = V4HWarpsW<WCOLS, CPT>::value;
 	constexpr int kMmaUnroll = VB200_V4_MMA_UNROLL;
@@ -142,7 +143,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	uint64_t *bars = (uint64_t *) (smem_raw + S * stage_bytes);
 	unsigned char *quadbuf = (unsigned char *) (bars + 2 * S + 4);
 	uint2 *sh = (uint2 *) (quadbuf + (size_t) kV4Quads * QS);
-	int *hcoef = (int *) (sh + (size_t) 2 * K * shs);
+	int *hcoef = (int *) (sh + (size_t) 2 * KM * shs);
 	int *uscale = hcoef + P.nhsets * P.NPh;
 
 	const unsigned stages_s = smem_addr(stages);
@@ -178,7 +179,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	const int c_lo = column_of(0) & ~3;
 	const int c_hi = min(P.W, (column_of(NE * HSQ - 1) + 4) & ~3);
 	const unsigned row_bytes = (unsigned) (c_hi - c_lo) * 4u;
-	const int q_first = __ldg(&P.vchunk[y_begin / K]).x;
+	const int chunk0 = y_begin / K; /* RPC is a multiple of K: chunk c of this CTA is table entry chunk0 + c */
+	const int q_first = __ldg(&P.vchunk[chunk0]).x;
 	/* V warps whose columns all lie beyond this band's last column do not run at all */
 	const int NTa = min(NT, ((NE * HSQ + 32 * CPT - 1) / (32 * CPT)) * 32);
 
@@ -204,8 +206,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		int s = 0;
 		unsigned phase = 0;
 		int pdone = 2 * q_first;
-		for (int ya = y_begin; ya < y_end; ya += K) {
-			const int P1 = 2 * __ldg(&P.vchunk[ya / K]).y + 1; /* last pair of the chunk's last quad */
+		for (int ya = y_begin, cc = chunk0; ya < y_end; ya += K, cc++) {
+			const int P1 = 2 * __ldg(&P.vchunk[cc]).y + 1; /* last pair of the chunk's last quad */
 			for (int p = pdone; p <= P1; p++) {
 				mbar_wait(empty_s + 8u * s, phase ^ 1u);
 				/* interior stage: its 2 VS input rows are consecutive and none is an edge replica --
@@ -260,7 +262,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 			const int yb = min(ya + K, y_end);
 			const int rows = yb - ya;
 			const int buf = chunk & 1;
-			const uint2 *shb = sh + (size_t) buf * K * shs;
+			const uint2 *shb = sh + (size_t) buf * KM * shs;
 			mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
 			for (int idx = ht; idx < rows * bw; idx += 32 * NH) {
 				const int k = fast_div(idx, bw);
@@ -339,7 +341,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	int chunk = 0;
 
 	for (int ya = y_begin; ya < y_end; ya += K, chunk++) {
-		const int q1 = __ldg(&P.vchunk[ya / K]).y;
+		const int q1 = __ldg(&P.vchunk[chunk0 + chunk]).y;
 
 		for (int q = qdone; q <= q1; q++) {
 			unsigned rb[4][CPT], ga[4][CPT];
@@ -419,9 +421,9 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 
 		/* reducev on the tensor pipe + in-thread shrinkh; rows go to sh[buf] once the H warp has released it */
 		const int buf = chunk & 1;
-		const uint4 bf = __ldg(&P.vbfrag[(size_t) (ya / K) * 32 + lane]); /* {hi b0, hi b1, lo b0, lo b1} */
+		const uint4 bf = __ldg(&P.vbfrag[(size_t) (chunk0 + chunk) * 32 + lane]); /* {hi b0, hi b1, lo b0, lo b1} */
 		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
-		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * K * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
+		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * KM * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
 #pragma unroll kMmaUnroll
 		for (int tp = 0; tp < 4 * CPT; tp++) {
 			unsigned a[2][4];

@@ -99,7 +99,9 @@ void build_axis_table(AxisTable &t, int out_size, double residual, double offset
  * false when a chunk's window does not fit the ring (the plan then uses the dp2a kernels).
  * Pure host code: tests/test_mma_tables.py replays the MMA arithmetic over these tables on the CPU.
  */
-bool build_mma_tables(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag);
+bool build_mma_tables(const AxisTable &t, int out_size, int rows, std::vector<int> &vchunk, std::vector<unsigned> &bfrag);
+/* the largest rows-per-chunk in 8 .. 4 for which every chunk fits (0: none), with its tables */
+int pick_mma_rows(const AxisTable &t, int out_size, std::vector<int> &vchunk, std::vector<unsigned> &bfrag);
 
 /* ------------------------------------------------------- resample device ops */
 

@@ -17,24 +17,28 @@ def tables(in_size, shrink, rect=16):
     L = C.CDLL(vb.library_path())
     cap = 4096
     ints = [C.c_int() for _ in range(5)]
+    rows = C.c_int(0)
     first = (C.c_int * cap)()
     phase = (C.c_int * cap)()
     mask = (C.c_short * (65 * 64))()
     vchunk = (C.c_int * (2 * cap // 8 + 2))()
     bfrag = (C.c_uint * (128 * (cap // 8 + 1)))()
     L.vb200_debug_mma_tables.argtypes = [C.c_int, C.c_double, C.c_int] + [C.POINTER(C.c_int)] * 7 + \
-        [C.POINTER(C.c_short), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.c_int]
-    rc = L.vb200_debug_mma_tables(in_size, shrink, rect, *[C.byref(i) for i in ints], first, phase, mask, vchunk, bfrag, cap)
+        [C.POINTER(C.c_short), C.POINTER(C.c_int), C.POINTER(C.c_uint), C.c_int, C.POINTER(C.c_int)]
+    rc = L.vb200_debug_mma_tables(in_size, shrink, rect, *[C.byref(i) for i in ints], first, phase, mask, vchunk, bfrag, cap, C.byref(rows))
     vs, hs, oh, npnt, embed = [i.value for i in ints]
-    return rc, dict(VS=vs, Hs=hs, OH=oh, n_point=npnt, embed=embed, first=np.array(first[:oh]), phase=np.array(phase[:oh]),
-                    vchunk=np.array(vchunk[:2 * ((oh + 7) // 8)]).reshape(-1, 2),
-                    bfrag=np.array(bfrag[:128 * ((oh + 7) // 8)], dtype=np.uint32).reshape(-1, 32, 4))
+    R = max(rows.value, 1)
+    nch = (oh + R - 1) // R
+    return rc, dict(VS=vs, Hs=hs, OH=oh, n_point=npnt, embed=embed, rows=R, first=np.array(first[:oh]), phase=np.array(phase[:oh]),
+                    vchunk=np.array(vchunk[:2 * nch]).reshape(-1, 2),
+                    bfrag=np.array(bfrag[:128 * nch], dtype=np.uint32).reshape(-1, 32, 4))
 
 
-@pytest.mark.parametrize("in_size,shrink", [(4096, 8.0), (2048, 8.0), (1024, 4.0), (1600, 8.0), (1000, 4.0), (4096, 8.7)])
+@pytest.mark.parametrize("in_size,shrink", [(4096, 8.0), (2048, 8.0), (1024, 4.0), (1600, 8.0), (1000, 4.0), (4096, 8.7),
+                                            (2000, 4.76), (3000, 5.9), (4096, 9.9)])
 def test_mma_tables_reproduce_reducev(in_size, shrink):
     rc, t = tables(in_size, shrink)
-    assert rc == 0, "window must fit the 8-quad ring for shrinks of 4..9"
+    assert rc == 0, "some chunking of 4..8 rows must fit the 8-quad ring for shrinks of 4..10"
     assert t["VS"] in (2, 4)
     rng = np.random.default_rng(in_size)
     col = rng.integers(0, 256, (in_size, 3, 1), dtype=np.uint8)       # a 3-pixel-wide, 1-band image
@@ -54,8 +58,9 @@ def test_mma_tables_reproduce_reducev(in_size, shrink):
         produced = max(produced, q1)
         for lane in range(32):                                           # the MMA: lane (g, tig) holds B[k][n = g]
             tig, g = lane & 3, lane >> 2
-            y = c * 8 + g
-            if y >= t["OH"]:
+            y = c * t["rows"] + g
+            if g >= t["rows"] or y >= t["OH"]:
+                assert not t["bfrag"][c, lane].any() or y < t["OH"]
                 continue
             w = t["bfrag"][c, lane]
             acc = np.full(3, 2048, np.int64)
@@ -75,7 +80,8 @@ def test_mma_tables_reproduce_reducev(in_size, shrink):
     assert np.array_equal(got, want)
 
 
-def test_mma_tables_decline_wide_windows():
-    """residual shrink 2.4 needs 15+ taps over 8 rows at stride 2.4: more than 32 rows"""
-    rc, _ = tables(2000, 4.76)
-    assert rc == 1
+def test_mma_tables_rows_per_chunk():
+    """exact factors keep 8 rows per chunk; a residual shrink of 2.4 (17 taps at stride 2.4) needs fewer"""
+    assert tables(4096, 8.0)[1]["rows"] == 8
+    rc, t = tables(2000, 4.76)
+    assert rc == 0 and 4 <= t["rows"] < 8

@@ -261,10 +261,12 @@ V4_CASES = [
     (4096, 512, 256, 128, "force", True, 1, True),      # V 2, H 8
     (1600, 1600, 200, None, "both", False, 2, True),    # 4, 4 without alpha: no premultiply
     (4096, 4096, 512, None, "both", True, 2, True),     # the headline frame
-    # plans the tensor-pipe kernel declines (box 3 / box 8 / a 15-tap window that overflows the 32-row
-    # quad ring): they must land on the older fused kernels with the same pixels
+    (2000, 1000, 420, None, "both", True, 2, True),     # residual 2.38, 15 taps: 5 output rows per chunk
+    (3000, 2000, 640, None, "both", True, 1, True),     # shrink 4.69
+    (4000, 3000, 410, None, "both", True, 1, True),     # shrink 9.76: box 4, residual 2.44
+    # plans the tensor-pipe kernel declines (box 3 / box 8): they must land on the older fused kernels with
+    # the same pixels
     (1200, 900, 150, None, "both", True, 1, False),
-    (2000, 1000, 420, None, "both", True, 2, False),
     (1003, 2057, 120, None, "both", True, 2, False),
 ]
 
