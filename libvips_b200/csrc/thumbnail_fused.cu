@@ -1610,6 +1610,7 @@ launch_mma_w(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 		return launch_mma_t<VS_, NP_, PREMUL, HS_, WCOLS, CPT>(domain, pl, fp, in, is, out, os, n, grid, s);
 	V4(4, 6, 4) V4(4, 7, 4) V4(2, 6, 2) V4(2, 7, 2)
 	V4(4, 0, 4) V4(2, 0, 2) V4(4, 0, 2) V4(2, 0, 4) V4(4, 0, 8) V4(2, 0, 8)
+	V4(8, 6, 8) V4(8, 7, 8) V4(8, 0, 8) V4(8, 0, 4)
 #undef V4
 	*handled = false;
 	return 0;
@@ -1643,13 +1644,18 @@ launch_mma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 
 int
 launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is, void *out, size_t os, int n,
-	cudaStream_t s)
+	cudaStream_t s, bool *done)
 {
+	*done = true;
 	if (pl->mma_ok) {
 		bool handled = false;
 		const int rc = launch_mma(domain, pl, in, is, out, os, n, s, &handled);
 		if (handled)
 			return rc;
+	}
+	if (!pl->tma_ok) {
+		*done = false; /* the caller falls through to the ld.global kernel */
+		return 0;
 	}
 	FusedParams fp = pl->fp;
 	fp.slots = pl->slots_tma;
@@ -1858,7 +1864,9 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 
 	/* v4: reducev as u8 x s8 MMAs over a ring of 8 quads (32 box-shrunk rows) per 8 output rows */
 	pl->mma_ok = false;
-	if (pl->tma_ok && (fp.VS == 2 || fp.VS == 4) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
+	/* (not gated on tma_ok: the older TMA kernels' shared-memory bound fails for box 8, this kernel's does not) */
+	if ((fp.in_bpl % 16) == 0 && fp.max_alpha == 255.0 && getenv("VB200_NO_TMA") == nullptr &&
+		(fp.VS == 2 || fp.VS == 4 || fp.VS == 8) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
 		getenv("VB200_NO_MMA") == nullptr) {
 		std::vector<int> vchunk_flat;
 		std::vector<unsigned> bfrag_flat;
@@ -1913,7 +1921,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			pl->mma_tw = tw4;
 			pl->mma_nemax = nemax4;
 			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
-			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
+			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES : (fp.VS >= 8 ? VB200_V4_STAGES / 2 : VB200_V4_STAGES);
 			const int nbox = wcols + 8 > 512 ? 2 : 1;
 			const size_t box_bytes = ((size_t) 2 * fp.VS * (pitch / nbox) + 127) & ~(size_t) 127;
 			pl->smem_mma = (size_t) stages * nbox * box_bytes + (2 * stages + 4) * 8 +
@@ -2016,8 +2024,12 @@ thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void 
 		return 0;
 	if (pl->fused) {
 		/* the TMA-fed kernel when rows, frames and the base pointer are 16-byte aligned */
-		if (pl->tma_ok && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0))
-			return launch_tma(domain, pl, in, in_stride, out, out_stride, n, s);
+		if ((pl->tma_ok || pl->mma_ok) && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0)) {
+			bool handled = true;
+			const int rc = launch_tma(domain, pl, in, in_stride, out, out_stride, n, s, &handled);
+			if (handled)
+				return rc;
+		}
 		/* enough CTAs to fill the machine: split rows when the batch is small */
 		FusedParams &fp = pl->fp;
 		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
@@ -2166,7 +2178,7 @@ vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan)
 	const ThumbnailPlanImpl &pl = plan->impl;
 	const FusedParams &fp = pl.fp;
 	const int nph = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
-	const bool v4 = pl.mma_ok && (fp.VS == 2 || fp.VS == 4);
+	const bool v4 = pl.mma_ok && (fp.VS == 2 || fp.VS == 4 || fp.VS == 8);
 	if (v4)
 		snprintf(name, sizeof(name), "thumbnail_fused_mma_kernel<VS=%d,NP=%d,%s,HS=%d,cols=%d,cpt=%d>", fp.VS, nph,
 			pl.premul ? "premul" : "plain", fp.HS, pl.mma_cols, pl.mma_cpt);

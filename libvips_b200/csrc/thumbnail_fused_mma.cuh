@@ -80,7 +80,8 @@ struct V4HWarpsW {
 
 template <int VS>
 struct V4Stages {
-	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES : VB200_V4_STAGES;
+	/* a stage is 2 VS input rows: 8 stages of 4 rows, 4 of 8, 2 of 16 keep the ring near 100 KB */
+	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES : (VS >= 8 ? VB200_V4_STAGES / 2 : VB200_V4_STAGES);
 };
 
 __device__ __forceinline__ void

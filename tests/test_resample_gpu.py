@@ -264,6 +264,8 @@ V4_CASES = [
     (2000, 1000, 420, None, "both", True, 2, True),     # residual 2.38, 15 taps: 5 output rows per chunk
     (3000, 2000, 640, None, "both", True, 1, True),     # shrink 4.69
     (4000, 3000, 410, None, "both", True, 1, True),     # shrink 9.76: box 4, residual 2.44
+    (4096, 4096, 256, None, "both", True, 2, True),     # shrink 16: box 8 on both axes
+    (3840, 2160, 225, None, "both", True, 1, True),     # shrink 17.07: box 8, residual 2.13
     # plans the tensor-pipe kernel declines (box 3 / box 8): they must land on the older fused kernels with
     # the same pixels
     (1200, 900, 150, None, "both", True, 1, False),
