@@ -306,10 +306,10 @@ const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
  * :1166-1220) with the profile passed as a memory blob (what vips_icc_load_profile_blob hands lcms2).
  * The reference's arithmetic is lcms2's; this is a from-specification ICC evaluator whose parity is
  * pinned to lcms2 2.18 within a tolerance (tests/test_icc.py), not bit for bit.  Supported: RGB
- * matrix/TRC, grey TRC and lut8 / lut16 (e.g. CMYK) profiles; intent VB200_INTENT_RELATIVE (the
+ * matrix/TRC, grey TRC, lut8 / lut16 (e.g. CMYK) and v4 lutAtoB / lutBtoA profiles; intent VB200_INTENT_RELATIVE (the
  * reference's default); depth 8 or 16;
  * bands after the profile's channels ride along as in vips_colour_build.  Everything else (the other
- * intents, black point compensation, v4 lutAtoB tags) returns -1: keep the host path.
+ * intents, black point compensation) returns -1: keep the host path.
  */
 enum { VB200_INTENT_PERCEPTUAL = 0, VB200_INTENT_RELATIVE = 1, VB200_INTENT_SATURATION = 2, VB200_INTENT_ABSOLUTE = 3 };
 enum { VB200_PCS_LAB = 0, VB200_PCS_XYZ = 1 };

@@ -9,9 +9,9 @@
  * The arithmetic of the reference lives inside lcms2 (not under /root/reference, no version pinned by
  * meson.build:444-447).  This is a from-specification ICC evaluator (ICC.1:2010 / ICC.1:2001-04):
  *   - RGB matrix/TRC profiles (rXYZ gXYZ bXYZ + curv / para TRCs), grey TRC profiles,
- *   - lut16 / lut8 (mft2 / mft1) A2Bn / B2An profiles with XYZ or Lab PCS (e.g. CMYK),
+ *   - lut16 / lut8 (mft2 / mft1) and v4 lutAtoB / lutBtoA (mAB / mBA) A2Bn / B2An profiles, XYZ or Lab PCS,
  *   - relative colorimetric (the reference's default intent) only.
- * Perceptual / saturation / absolute intents, black point compensation, v4 lutAtoB/lutBtoA (mAB / mBA) tags, device-link and
+ * Perceptual / saturation / absolute intents, black point compensation, device-link and
  * named-colour profiles return -1 ("keep the host path").
  *
  * PARITY: pinned to lcms2 2.18 (oracle/pylcms.py makes the reference's exact lcms2 calls) within a
@@ -33,7 +33,7 @@ namespace vb200 {
 
 namespace {
 
-enum { MODEL_MATRIX = 1, MODEL_GREY = 2, MODEL_LUT = 3 };
+enum { MODEL_MATRIX = 1, MODEL_GREY = 2, MODEL_LUT = 3, MODEL_MAB = 4 };
 enum { CURVE_IDENTITY = 0, CURVE_TABLE = 1, CURVE_PARA = 2 };
 
 struct IccCurve {
@@ -52,6 +52,20 @@ struct IccLut {
 	double m[9];
 };
 
+/* lutAtoBType / lutBtoAType (ICC.1:2010 10.10, 10.11): optional stages around a CLUT whose grid may
+ * differ per dimension.  A2B runs A curves -> CLUT -> M curves -> matrix -> B curves, B2A runs
+ * B curves -> matrix -> M curves -> CLUT -> A curves; values are the tags' 0..1 encodings.
+ */
+struct IccMab {
+	int in_ch = 0, out_ch = 0;
+	int has_a = 0, has_clut = 0, has_m = 0, has_matrix = 0;
+	int trilinear = 0; /* B2A of a Lab-PCS profile: lcms2 interpolates it multilinearly (cmsio1.c) */
+	int grid[4] = {0, 0, 0, 0};
+	int clut_off = 0;
+	IccCurve a[4], m[3], b[4];
+	double mat[12]; /* 3 x 3 then the three offsets */
+};
+
 struct IccSide {
 	int model = 0;
 	int bands = 0;		 /* device channels */
@@ -59,6 +73,8 @@ struct IccSide {
 	IccCurve curve[3];
 	double m[9];		 /* device-linear -> XYZ D50 (import) or its inverse (export) */
 	IccLut lut;
+	IccMab mab;
+	int to_pcs = 0; /* direction of this side (MODEL_MAB needs it) */
 	const float *pool = nullptr; /* device or host pointer, set at use */
 };
 
@@ -135,6 +151,120 @@ parse_curve(const Blob &b, const char *sig, IccCurve *c, std::vector<float> &poo
 		return true;
 	}
 	return false;
+}
+
+/* a curveType / parametricCurveType element inside another tag; *used = its length padded to 4 */
+bool
+parse_curve_at(const Blob &b, size_t off, IccCurve *c, std::vector<float> &pool, size_t *used)
+{
+	if (!b.ok(off, 12))
+		return false;
+	if (memcmp(b.d + off, "curv", 4) == 0) {
+		const unsigned n = b.u32(off + 8);
+		if (!b.ok(off + 12, 2 * (size_t) n))
+			return false;
+		*used = (12 + 2 * (size_t) n + 3) & ~(size_t) 3;
+		if (n == 0)
+			c->kind = CURVE_IDENTITY;
+		else if (n == 1) {
+			c->kind = CURVE_PARA;
+			c->ptype = 0;
+			c->p[0] = b.u16(off + 12) / 256.0;
+		}
+		else {
+			c->kind = CURVE_TABLE;
+			c->n = (int) n;
+			c->table_off = (int) pool.size();
+			for (unsigned i = 0; i < n; i++)
+				pool.push_back((float) (b.u16(off + 12 + 2 * i) / 65535.0));
+		}
+		return true;
+	}
+	if (memcmp(b.d + off, "para", 4) == 0) {
+		const int t = (int) b.u16(off + 8);
+		static const int count[5] = {1, 3, 4, 5, 7};
+		if (t < 0 || t > 4 || !b.ok(off + 12, 4 * (size_t) count[t]))
+			return false;
+		c->kind = CURVE_PARA;
+		c->ptype = t;
+		for (int i = 0; i < count[t]; i++)
+			c->p[i] = b.s15f16(off + 12 + 4 * i);
+		*used = 12 + 4 * (size_t) count[t];
+		return true;
+	}
+	return false;
+}
+
+bool
+parse_mab(const Blob &b, const char *sig, bool to_pcs, IccMab *m, std::vector<float> &pool)
+{
+	size_t off, len;
+	if (!find_tag(b, sig, &off, &len) || len < 32)
+		return false;
+	if (memcmp(b.d + off, to_pcs ? "mAB " : "mBA ", 4) != 0)
+		return false;
+	m->in_ch = b.d[off + 8];
+	m->out_ch = b.d[off + 9];
+	if (m->in_ch < 1 || m->in_ch > 4 || m->out_ch < 1 || m->out_ch > 4)
+		return false;
+	const size_t ob = b.u32(off + 12), omat = b.u32(off + 16), om = b.u32(off + 20), oc = b.u32(off + 24), oa = b.u32(off + 28);
+	/* B curves are on the PCS side, A curves on the device side */
+	const int nb = to_pcs ? m->out_ch : m->in_ch, na = to_pcs ? m->in_ch : m->out_ch;
+	if (!ob)
+		return false;
+	auto curves = [&](size_t o, int n, IccCurve *c) {
+		size_t p = off + o;
+		for (int i = 0; i < n; i++) {
+			size_t used = 0;
+			if (!parse_curve_at(b, p, &c[i], pool, &used))
+				return false;
+			p += used;
+		}
+		return true;
+	};
+	if (!curves(ob, nb, m->b))
+		return false;
+	if (omat) {
+		if (nb != 3 || !b.ok(off + omat, 48))
+			return false;
+		for (int i = 0; i < 12; i++)
+			m->mat[i] = b.s15f16(off + omat + 4 * i);
+		m->has_matrix = 1;
+	}
+	if (om) {
+		if (nb != 3 || !curves(om, 3, m->m))
+			return false;
+		m->has_m = 1;
+	}
+	if (oa) {
+		if (!curves(oa, na, m->a))
+			return false;
+		m->has_a = 1;
+	}
+	if (oc) {
+		if (!b.ok(off + oc, 20))
+			return false;
+		size_t nodes = 1;
+		for (int i = 0; i < m->in_ch; i++) {
+			m->grid[i] = b.d[off + oc + i];
+			if (m->grid[i] < 2)
+				return false;
+			nodes *= (size_t) m->grid[i];
+		}
+		const int prec = b.d[off + oc + 16];
+		if (prec != 1 && prec != 2)
+			return false;
+		const size_t count = nodes * m->out_ch;
+		if (!b.ok(off + oc + 20, count * prec))
+			return false;
+		m->clut_off = (int) pool.size();
+		for (size_t i = 0; i < count; i++)
+			pool.push_back(prec == 2 ? (float) (b.u16(off + oc + 20 + 2 * i) / 65535.0) : (float) (b.d[off + oc + 20 + i] / 255.0));
+		m->has_clut = 1;
+	}
+	else if (m->in_ch != m->out_ch)
+		return false;
+	return true;
 }
 
 bool
@@ -253,9 +383,23 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 	const char *const *tags = to_pcs ? a2b : b2a;
 	size_t off, tl;
 	const char *want = find_tag(b, tags[intent], &off, &tl) ? tags[intent] : (find_tag(b, tags[0], &off, &tl) ? tags[0] : nullptr);
+	s->to_pcs = to_pcs;
+	if (want && memcmp(b.d + off, to_pcs ? "mAB " : "mBA ", 4) == 0) {
+		if (!parse_mab(b, want, to_pcs, &s->mab, pool)) {
+			error(domain, "malformed %s tag", want);
+			return -1;
+		}
+		if ((to_pcs ? s->mab.in_ch : s->mab.out_ch) != s->bands || (to_pcs ? s->mab.out_ch : s->mab.in_ch) != 3) {
+			error(domain, "lut channel counts do not match the profile header");
+			return -1;
+		}
+		s->mab.trilinear = !to_pcs && s->pcs_lab;
+		s->model = MODEL_MAB;
+		return 0;
+	}
 	if (want) {
 		if (!parse_lut(b, want, &s->lut, pool)) {
-			error(domain, "%s is not a lut8 / lut16 tag (v4 lutAtoB / lutBtoA are not supported on the device path)", want);
+			error(domain, "%s is neither lut8 / lut16 nor lutAtoB / lutBtoA", want);
 			return -1;
 		}
 		if ((to_pcs ? s->lut.in_ch : s->lut.out_ch) != s->bands || (to_pcs ? s->lut.out_ch : s->lut.in_ch) != 3) {
@@ -530,6 +674,147 @@ pcs_to_lut(const IccSide &s, const double *xyz, double *v)
 			v[i] = clamp01(xyz[i] * 32768.0 / 65535.0);
 }
 
+/* n-dimensional CLUT with per-dimension grids: tetrahedral over the last three inputs, linear over a
+ * fourth in front of them (as clut_tetra3 / lut_eval above), multilinear for 1 or 2 inputs
+ */
+HD void
+mab_clut(const IccMab &m, const float *pool, const double *x, double *out)
+{
+	int base[4];
+	double frac[4];
+	for (int c = 0; c < m.in_ch; c++) {
+		const double p = clamp01(x[c]) * (m.grid[c] - 1);
+		int i = (int) p;
+		if (i > m.grid[c] - 2)
+			i = m.grid[c] - 2;
+		base[c] = i;
+		frac[c] = p - i;
+	}
+	/* strides in nodes, first input slowest */
+	size_t stride[4];
+	size_t acc_s = 1;
+	for (int c = m.in_ch - 1; c >= 0; c--) {
+		stride[c] = acc_s;
+		acc_s *= (size_t) m.grid[c];
+	}
+	auto node = [&](size_t idx) { return pool + m.clut_off + idx * m.out_ch; };
+	auto tetra = [&](size_t o, const int first, double *res) {
+		const size_t sx = stride[first], sy = stride[first + 1], sz = stride[first + 2];
+		const double rx = frac[first], ry = frac[first + 1], rz = frac[first + 2];
+		size_t p1, p2;
+		double w1, w2, w3;
+		if (rx >= ry && ry >= rz) { p1 = sx; p2 = sx + sy; w1 = rx; w2 = ry; w3 = rz; }
+		else if (rx >= rz && rz >= ry) { p1 = sx; p2 = sx + sz; w1 = rx; w2 = rz; w3 = ry; }
+		else if (rz >= rx && rx >= ry) { p1 = sz; p2 = sz + sx; w1 = rz; w2 = rx; w3 = ry; }
+		else if (ry >= rx && rx >= rz) { p1 = sy; p2 = sy + sx; w1 = ry; w2 = rx; w3 = rz; }
+		else if (ry >= rz && rz >= rx) { p1 = sy; p2 = sy + sz; w1 = ry; w2 = rz; w3 = rx; }
+		else { p1 = sz; p2 = sz + sy; w1 = rz; w2 = ry; w3 = rx; }
+		const float *n0 = node(o), *n1 = node(o + p1), *n2 = node(o + p2), *n3 = node(o + sx + sy + sz);
+		for (int c = 0; c < m.out_ch; c++)
+			res[c] = n0[c] + ((double) n1[c] - n0[c]) * w1 + ((double) n2[c] - n1[c]) * w2 + ((double) n3[c] - n2[c]) * w3;
+	};
+	size_t o = 0;
+	for (int c = 0; c < m.in_ch; c++)
+		o += (size_t) base[c] * stride[c];
+	if (m.in_ch == 3 && !m.trilinear)
+		tetra(o, 0, out);
+	else if (m.in_ch == 4 && !m.trilinear) {
+		double lo[4], hi[4];
+		tetra(o, 1, lo);
+		tetra(o + stride[0], 1, hi);
+		for (int c = 0; c < m.out_ch; c++)
+			out[c] = lo[c] + (hi[c] - lo[c]) * frac[0];
+	}
+	else {
+		for (int c = 0; c < m.out_ch; c++)
+			out[c] = 0.0;
+		for (int k = 0; k < (1 << m.in_ch); k++) {
+			double w = 1.0;
+			size_t idx = o;
+			for (int c = 0; c < m.in_ch; c++) {
+				const int bit = (k >> c) & 1;
+				w *= bit ? frac[c] : 1.0 - frac[c];
+				idx += bit ? stride[c] : 0;
+			}
+			const float *n = node(idx);
+			for (int c = 0; c < m.out_ch; c++)
+				out[c] += w * n[c];
+		}
+	}
+}
+
+HD void
+mab_matrix(const IccMab &m, double *v)
+{
+	const double x = v[0], y = v[1], z = v[2];
+	for (int r = 0; r < 3; r++)
+		v[r] = m.mat[r * 3] * x + m.mat[r * 3 + 1] * y + m.mat[r * 3 + 2] * z + m.mat[9 + r];
+}
+
+/* v4 PCS encodings as 0..1: XYZ u1.15 of 16 bits (1.0 -> 32768 / 65535), Lab L / 100, (a, b + 128) / 255 */
+HD void
+mab_to_xyz(const IccSide &s, const double *dev, double *xyz)
+{
+	const IccMab &m = s.mab;
+	double v[4] = {dev[0], dev[1], dev[2], dev[3]}, w[4];
+	if (m.has_a)
+		for (int c = 0; c < m.in_ch; c++)
+			v[c] = curve_fwd(m.a[c], s.pool, v[c]);
+	if (m.has_clut) {
+		mab_clut(m, s.pool, v, w);
+		for (int c = 0; c < m.out_ch; c++)
+			v[c] = w[c];
+	}
+	if (m.has_m)
+		for (int c = 0; c < 3; c++)
+			v[c] = curve_fwd(m.m[c], s.pool, v[c]);
+	if (m.has_matrix)
+		mab_matrix(m, v);
+	for (int c = 0; c < 3; c++)
+		v[c] = curve_fwd(m.b[c], s.pool, v[c]);
+	if (s.pcs_lab) {
+		const double lab[3] = {v[0] * 100.0, v[1] * 255.0 - 128.0, v[2] * 255.0 - 128.0};
+		lab2xyz(lab, xyz);
+	}
+	else
+		for (int i = 0; i < 3; i++)
+			xyz[i] = v[i] * 65535.0 / 32768.0;
+}
+
+HD void
+mab_from_xyz(const IccSide &s, const double *xyz, double *dev)
+{
+	const IccMab &m = s.mab;
+	double v[4] = {0, 0, 0, 0}, w[4];
+	if (s.pcs_lab) {
+		double lab[3];
+		xyz2lab(xyz, lab);
+		v[0] = lab[0] / 100.0;
+		v[1] = (lab[1] + 128.0) / 255.0;
+		v[2] = (lab[2] + 128.0) / 255.0;
+	}
+	else
+		for (int i = 0; i < 3; i++)
+			v[i] = xyz[i] * 32768.0 / 65535.0;
+	for (int c = 0; c < 3; c++)
+		v[c] = curve_fwd(m.b[c], s.pool, v[c]);
+	if (m.has_matrix)
+		mab_matrix(m, v);
+	if (m.has_m)
+		for (int c = 0; c < 3; c++)
+			v[c] = curve_fwd(m.m[c], s.pool, v[c]);
+	if (m.has_clut) {
+		mab_clut(m, s.pool, v, w);
+		for (int c = 0; c < m.out_ch; c++)
+			v[c] = w[c];
+	}
+	if (m.has_a)
+		for (int c = 0; c < m.out_ch; c++)
+			v[c] = curve_fwd(m.a[c], s.pool, v[c]);
+	for (int c = 0; c < m.out_ch; c++)
+		dev[c] = clamp01(v[c]);
+}
+
 /* device values (0..1) -> PCS XYZ (D50, Y = 1) */
 HD void
 side_to_xyz(const IccSide &s, const double *dev, double *xyz)
@@ -547,6 +832,8 @@ side_to_xyz(const IccSide &s, const double *dev, double *xyz)
 		xyz[1] = y * D50Y;
 		xyz[2] = y * D50Z;
 	}
+	else if (s.model == MODEL_MAB)
+		mab_to_xyz(s, dev, xyz);
 	else {
 		double v[4];
 		lut_eval(s.lut, s.pool, dev, v);
@@ -566,6 +853,8 @@ side_from_xyz(const IccSide &s, const double *xyz, double *dev)
 	}
 	else if (s.model == MODEL_GREY)
 		dev[0] = clamp01(curve_inv(s.curve[0], s.pool, xyz[1] / D50Y));
+	else if (s.model == MODEL_MAB)
+		mab_from_xyz(s, xyz, dev);
 	else {
 		double v[3];
 		pcs_to_lut(s, xyz, v);
@@ -736,6 +1025,8 @@ icc_pixel(const IccJob &J, const void *pin, void *pout)
 	}
 }
 
+static_assert(sizeof(IccJob) <= 4096, "IccJob travels as a kernel parameter");
+
 __global__ void __launch_bounds__(256)
 icc_kernel(const __grid_constant__ IccJob J, const char *__restrict__ in, size_t in_bpl, size_t in_ps, char *__restrict__ out,
 	size_t out_bpl, size_t out_ps, int w)
@@ -817,7 +1108,7 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, int i
 	/* tabulate the TRCs for integer codes (the curves read `pool` themselves: evaluate against the host copy) */
 	J->in_tab = J->out_thr = -1;
 	const bool tabulate = getenv("VB200_NO_ICC_TABLES") == nullptr;
-	if (tabulate && (sp.mode == 0 || sp.mode == 2) && J->in.model != MODEL_LUT &&
+	if (tabulate && (sp.mode == 0 || sp.mode == 2) && (J->in.model == MODEL_MATRIX || J->in.model == MODEL_GREY) &&
 		(in_fmt == VB200_FORMAT_UCHAR || in_fmt == VB200_FORMAT_USHORT)) {
 		const int n = in_fmt == VB200_FORMAT_UCHAR ? 256 : 65536;
 		std::vector<float> tab((size_t) J->in.bands * n);
@@ -828,7 +1119,7 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, int i
 		J->in_tab_n = n;
 		pool.insert(pool.end(), tab.begin(), tab.end());
 	}
-	if (tabulate && (sp.mode == 1 || sp.mode == 2) && J->out.model != MODEL_LUT) {
+	if (tabulate && (sp.mode == 1 || sp.mode == 2) && (J->out.model == MODEL_MATRIX || J->out.model == MODEL_GREY)) {
 		const int n = sp.depth == 8 ? 256 : 65536;
 		std::vector<float> thr((size_t) J->out.bands * n);
 		bool monotone = true;

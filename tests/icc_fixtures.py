@@ -130,3 +130,64 @@ def ink_profile(grid_a2b=9, grid_b2a=17):
     tags = [("desc", _text("desc", "vb200 test inks")), ("cprt", _text("cprt", "none")), ("wtpt", _xyz_tag(0.9642, 1.0, 0.8249)),
             ("A2B0", a2b), ("A2B1", a2b), ("B2A0", b2a), ("B2A1", b2a)]
     return _profile(0x02200000, "prtr", "CMYK", "Lab ", tags)
+
+
+def _mab(sig, in_ch, out_ch, b_curves, matrix=None, m_curves=None, clut=None, a_curves=None):
+    """lutAtoBType ('mAB ') / lutBtoAType ('mBA '), ICC.1:2010 10.10 / 10.11.  clut = (grid tuple, array[..., out] 0..1)."""
+    def pad(x):
+        return x + b"\0" * ((-len(x)) % 4)
+    parts, off = {}, 32
+    body = b""
+    def put(name, data):
+        nonlocal body, off
+        parts[name] = off
+        body += pad(data)
+        off = 32 + len(body)
+    put("b", b"".join(pad(c) for c in b_curves))
+    if matrix is not None:
+        put("mat", b"".join(_s15(v) for v in matrix))
+    if m_curves is not None:
+        put("m", b"".join(pad(c) for c in m_curves))
+    if clut is not None:
+        grid, arr = clut
+        g = bytes(list(grid) + [0] * (16 - len(grid)))
+        put("clut", g + bytes([2, 0, 0, 0]) + np.ascontiguousarray(np.rint(np.clip(arr, 0, 1) * 65535), dtype=">u2").tobytes())
+    if a_curves is not None:
+        put("a", b"".join(pad(c) for c in a_curves))
+    hdr = sig + b"\0" * 4 + bytes([in_ch, out_ch, 0, 0])
+    hdr += struct.pack(">5I", parts["b"], parts.get("mat", 0), parts.get("m", 0), parts.get("clut", 0), parts.get("a", 0))
+    return hdr + body
+
+
+def lut_v4_rgb_profile(pcs="XYZ "):
+    """A v4 RGB profile whose transforms are lutAtoB / lutBtoA tags: gamma-2 A curves, a gently bent CLUT on a
+    non-uniform grid, identity M curves, the sRGB matrix (in the tag's encoded PCS units) and identity B curves."""
+    ident = _curv([])
+    grid = (9, 7, 8)
+    axes = [np.linspace(0, 1, g) for g in grid]
+    R, G, B = np.meshgrid(*axes, indexing="ij")
+    lin = np.stack([R + 0.04 * np.sin(np.pi * R) * G, G + 0.03 * np.sin(np.pi * G) * B, B - 0.03 * np.sin(np.pi * B) * R], -1)
+    if pcs == "XYZ ":
+        enc = 32768.0 / 65535.0
+        mat = list((_M * enc).reshape(-1)) + [0.0, 0.0, 0.0]
+        a2b = _mab(b"mAB ", 3, 3, [ident] * 3, matrix=mat, m_curves=[ident] * 3, clut=(grid, lin), a_curves=[_para(0, [2.0])] * 3)
+        inv = list((np.linalg.inv(_M) / enc).reshape(-1)) + [0.0, 0.0, 0.0]
+        g2 = (11, 11, 11)
+        ax = np.linspace(0, 1, 11)
+        X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+        ident_clut = np.stack([X, Y, Z], -1)
+        b2a = _mab(b"mBA ", 3, 3, [ident] * 3, matrix=inv, m_curves=[ident] * 3, clut=(g2, ident_clut), a_curves=[_para(0, [0.5])] * 3)
+    else:
+        # Lab PCS: the CLUT holds encoded Lab directly (no matrix), B curves identity
+        lab = _xyz_to_lab(np.clip(lin, 0, 1) @ _M.T)
+        enc_lab = np.stack([lab[..., 0] / 100.0, (lab[..., 1] + 128.0) / 255.0, (lab[..., 2] + 128.0) / 255.0], -1)
+        a2b = _mab(b"mAB ", 3, 3, [ident] * 3, clut=(grid, enc_lab), a_curves=[_para(0, [2.0])] * 3)
+        g2 = (13, 13, 13)
+        ax = np.linspace(0, 1, 13)
+        Le, ae, be = np.meshgrid(ax, ax, ax, indexing="ij")
+        labg = np.stack([Le * 100.0, ae * 255.0 - 128.0, be * 255.0 - 128.0], -1)
+        linb = np.clip(_lab_to_xyz(labg) @ np.linalg.inv(_M).T, 0, 1)
+        b2a = _mab(b"mBA ", 3, 3, [ident] * 3, clut=(g2, linb), a_curves=[_para(0, [0.5])] * 3)
+    tags = [("desc", _text("desc", "vb200 test lut v4")), ("cprt", _text("cprt", "none")), ("wtpt", _xyz_tag(0.9642, 1.0, 0.8249)),
+            ("A2B0", a2b), ("A2B1", a2b), ("B2A0", b2a), ("B2A1", b2a)]
+    return _profile(0x04200000, "mntr", "RGB ", pcs, tags)

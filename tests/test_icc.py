@@ -108,6 +108,25 @@ def test_lut_profile_against_lcms2():
 
 
 @needs_lcms
+@pytest.mark.parametrize("pcs", ["XYZ ", "Lab "])
+def test_v4_lut_profile_against_lcms2(pcs):
+    """lutAtoB / lutBtoA tags (A curves, CLUT on a non-uniform grid, M curves, matrix, B curves)"""
+    prof, rgb = F.lut_v4_rgb_profile(pcs), F.rgb_profile()
+    rng = np.random.default_rng(12)
+    a = rng.integers(0, 256, (30000, 3), dtype=np.uint8)
+    af = rng.random((30000, 3), dtype=np.float32)
+    assert de(host_eval(0, a, prof), pylcms.icc_import(a, prof)).max() < 1.6
+    assert np.abs(host_eval(0, af, prof) - pylcms.icc_import(af, prof)).max() < 0.04
+    lab = pylcms.icc_import(a, rgb)
+    d = np.abs(host_eval(1, lab, prof).astype(int) - pylcms.icc_export(lab, prof).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    d = np.abs(host_eval(2, a, prof, rgb).astype(int) - pylcms.icc_transform(a, prof, rgb).astype(int))
+    assert d.max() <= 5 and d.mean() < 0.2
+    d = np.abs(host_eval(2, a, rgb, prof).astype(int) - pylcms.icc_transform(a, rgb, prof).astype(int))
+    assert d.max() <= 10 and d.mean() < 0.3
+
+
+@needs_lcms
 @pytest.mark.skipif(not os.path.isdir(REF_PROFILES), reason="reference profiles not on this machine")
 def test_reference_profiles_against_lcms2():
     P = lambda n: open(os.path.join(REF_PROFILES, n), "rb").read()
@@ -183,6 +202,10 @@ def test_gpu_matches_host_evaluation(vb):
     rgba = rng.integers(0, 256, (24, 40, 4), dtype=np.uint8)
     got = vb.Image(rgba, "srgb").icc_transform(rgb, rgb, depth=16).numpy()
     assert got.shape == (24, 40, 4) and np.array_equal(got[..., 3], rgba[..., 3].astype(np.uint16) * 257)
+    v4 = F.lut_v4_rgb_profile("Lab ")
+    got = vb.Image(a, "srgb").icc_transform(v4, v4).numpy()                  # lutAtoB then lutBtoA
+    want = host_eval(2, a.reshape(-1, 3), v4, v4).reshape(a.shape)
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
     g = rng.integers(0, 256, (16, 40, 1), dtype=np.uint8)
     got = vb.Image(g, "b-w").icc_transform(rgb, grey, depth=16).numpy()
     want = host_eval(2, g.reshape(-1, 1), grey, rgb, depth=16).reshape(16, 40, 3)
