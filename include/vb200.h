@@ -307,7 +307,8 @@ const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
  * The reference's arithmetic is lcms2's; this is a from-specification ICC evaluator whose parity is
  * pinned to lcms2 2.18 within a tolerance (tests/test_icc.py), not bit for bit.  Supported: RGB
  * matrix/TRC, grey TRC, lut8 / lut16 (e.g. CMYK) and v4 lutAtoB / lutBtoA profiles; intent VB200_INTENT_RELATIVE (the
- * reference's default); depth 8 or 16;
+ * reference's default), and PERCEPTUAL / SATURATION for matrix / grey profiles with a zero black point (where
+ * lcms2's black point compensation is the identity); depth 8 or 16;
  * bands after the profile's channels ride along as in vips_colour_build.  Everything else (the other
  * intents, black point compensation) returns -1: keep the host path.
  */

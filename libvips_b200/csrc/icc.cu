@@ -10,8 +10,9 @@
  * meson.build:444-447).  This is a from-specification ICC evaluator (ICC.1:2010 / ICC.1:2001-04):
  *   - RGB matrix/TRC profiles (rXYZ gXYZ bXYZ + curv / para TRCs), grey TRC profiles,
  *   - lut16 / lut8 (mft2 / mft1) and v4 lutAtoB / lutBtoA (mAB / mBA) A2Bn / B2An profiles, XYZ or Lab PCS,
- *   - relative colorimetric (the reference's default intent) only.
- * Perceptual / saturation / absolute intents, black point compensation, device-link and
+ *   - relative colorimetric (the reference's default intent); perceptual / saturation where lcms2's
+ *     black point compensation is the identity (matrix / grey profiles whose TRCs map 0 to 0).
+ * Absolute colorimetric, black point compensation proper, device-link and
  * named-colour profiles return -1 ("keep the host path").
  *
  * PARITY: pinned to lcms2 2.18 (oracle/pylcms.py makes the reference's exact lcms2 calls) within a
@@ -346,6 +347,8 @@ invert3(const double *m, double *inv)
 	return true;
 }
 
+int black_is_zero(const char *domain, const IccSide *s, const std::vector<float> &pool, int intent);
+
 /* One direction of one profile: to_pcs (A2B / forward matrix) or from_pcs (B2A / inverse matrix). */
 int
 parse_side(const char *domain, const void *data, size_t len, int intent, bool to_pcs, IccSide *s, std::vector<float> &pool)
@@ -355,11 +358,9 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 		error(domain, "not an ICC profile");
 		return -1;
 	}
-	if (intent != 1) {
-		/* perceptual / saturation against the v4 Lab / XYZ PCS profiles make lcms2 turn black point compensation
-		 * on (cmscnvrt.c), absolute needs the media white points: only relative colorimetric is evaluated here
-		 */
-		error(domain, "rendering intent %d not supported on the device path (relative colorimetric only)", intent);
+	if (intent < 0 || intent > 2) {
+		/* absolute colorimetric needs the media white points: not evaluated here */
+		error(domain, "rendering intent %d not supported on the device path", intent);
 		return -1;
 	}
 	const unsigned char *cs = b.d + 16, *pcs = b.d + 20;
@@ -384,6 +385,13 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 	size_t off, tl;
 	const char *want = find_tag(b, tags[intent], &off, &tl) ? tags[intent] : (find_tag(b, tags[0], &off, &tl) ? tags[0] : nullptr);
 	s->to_pcs = to_pcs;
+	if (want && intent != 1) {
+		/* perceptual / saturation against the v4 Lab / XYZ PCS profiles make lcms2 turn black point compensation
+		 * on (cmscnvrt.c); for a lut profile that needs its black point, which is not evaluated here
+		 */
+		error(domain, "rendering intent %d of a lut-based profile is not supported on the device path", intent);
+		return -1;
+	}
 	if (want && memcmp(b.d + off, to_pcs ? "mAB " : "mBA ", 4) == 0) {
 		if (!parse_mab(b, want, to_pcs, &s->mab, pool)) {
 			error(domain, "malformed %s tag", want);
@@ -410,11 +418,6 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 		s->model = MODEL_LUT;
 		return 0;
 	}
-	if (intent != 1 && b.u32(8) >= 0x04000000u) {
-		/* lcms2 forces black point compensation on v4 perceptual / saturation */
-		error(domain, "perceptual / saturation intents of v4 matrix profiles are not supported on the device path");
-		return -1;
-	}
 	if (s->pcs_lab) {
 		error(domain, "matrix/TRC profile with a Lab PCS");
 		return -1;
@@ -425,7 +428,7 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 			return -1;
 		}
 		s->model = MODEL_GREY;
-		return 0;
+		return black_is_zero(domain, s, pool, intent);
 	}
 	if (s->bands == 3) {
 		double col[3][3];
@@ -446,7 +449,7 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 			return -1;
 		}
 		s->model = MODEL_MATRIX;
-		return 0;
+		return black_is_zero(domain, s, pool, intent);
 	}
 	error(domain, "profile has neither lut nor matrix/TRC tags usable on the device path");
 	return -1;
@@ -521,6 +524,25 @@ curve_inv(const IccCurve &c, const float *pool, double y)
 		return y >= brk ? (pow(y - e, 1.0 / g) - b) / a : (cc != 0 ? (y - f) / cc : 0.0);
 	}
 	}
+}
+
+/* Perceptual and saturation intents of a matrix / grey profile: lcms2 applies black point compensation
+ * between the profile's black and the PCS profile's (zero); when the TRCs map 0 to 0 the profile's black
+ * is XYZ 0 too, the compensation is the identity, and the transform equals the relative colorimetric
+ * one bit for bit (checked against lcms2 in tests/test_icc.py).  Anything else is declined.
+ */
+int
+black_is_zero(const char *domain, const IccSide *s, const std::vector<float> &pool, int intent)
+{
+	if (intent == 1)
+		return 0;
+	const int n = s->model == MODEL_GREY ? 1 : 3;
+	for (int i = 0; i < n; i++)
+		if (curve_fwd(s->curve[i], pool.data(), 0.0) != 0.0) {
+			error(domain, "rendering intent %d with a non-zero black point is not supported on the device path", intent);
+			return -1;
+		}
+	return 0;
 }
 
 /* ICC PCS Lab <-> XYZ, D50, Y = 1 */

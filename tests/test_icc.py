@@ -69,6 +69,22 @@ def test_matrix_profiles_against_lcms2(trc):
 
 
 @needs_lcms
+@pytest.mark.parametrize("intent", ["perceptual", "saturation"])
+def test_matrix_profiles_other_intents(intent):
+    """lcms2 turns black point compensation on for these intents against the v4 PCS profiles; for a matrix or grey
+    profile whose black is XYZ 0 that is the identity, and lcms2's own output is bit-identical to its relative one"""
+    prof, code = F.rgb_profile("srgb"), {"perceptual": 0, "saturation": 2}[intent]
+    a = np.random.default_rng(13).integers(0, 256, (20000, 3), dtype=np.uint8)
+    assert np.array_equal(pylcms.icc_import(a, prof, intent), pylcms.icc_import(a, prof, "relative"))
+    assert np.array_equal(host_eval(0, a, prof, intent=code), host_eval(0, a, prof))
+    lab = pylcms.icc_import(a, prof)
+    assert np.array_equal(pylcms.icc_export(lab, prof, intent), pylcms.icc_export(lab, prof, "relative"))
+    assert np.array_equal(host_eval(1, lab, prof, intent=code), host_eval(1, lab, prof))
+    g = np.arange(256, dtype=np.uint8).reshape(-1, 1)
+    assert np.array_equal(pylcms.icc_import(g, F.grey_profile(), intent), pylcms.icc_import(g, F.grey_profile(), "relative"))
+
+
+@needs_lcms
 def test_rgb_to_rgb_transform_against_lcms2():
     pa, pb = F.rgb_profile("srgb"), F.rgb_profile("gamma")
     a = np.random.default_rng(4).integers(0, 256, (40000, 3), dtype=np.uint8)
@@ -157,7 +173,9 @@ def test_known_answers_and_refusals():
     assert np.abs(lab - [[100, 0, 0], [0, 0, 0]]).max() < 0.02
     assert np.array_equal(host_eval(1, lab, prof), [[255, 255, 255], [0, 0, 0]])
     with pytest.raises(vb.Error, match="intent"):
-        host_eval(0, np.zeros((1, 3), np.uint8), prof, intent=0)
+        host_eval(0, np.zeros((1, 3), np.uint8), prof, intent=3)                       # absolute colorimetric
+    with pytest.raises(vb.Error, match="lut-based"):
+        host_eval(0, np.zeros((1, 4), np.uint8), F.ink_profile(), intent=0)            # needs black point compensation
     with pytest.raises(vb.Error, match="bands"):
         host_eval(0, np.zeros((1, 2), np.uint8), prof)
     with pytest.raises(vb.Error, match="ICC"):
