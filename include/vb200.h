@@ -335,9 +335,13 @@ int vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_s
 	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows,
 	int *rows_per_chunk);
 
-/* pinned host memory for the pump (cudaHostAlloc / cudaFreeHost) */
+/* Pinned host memory for the pump: page-locked and, on a multi-socket machine, placed on the NUMA
+ * node the current device hangs off (falls back to cudaHostAlloc).  vb200_device_numa_node():
+ * that node, or -1 (unknown / single node).
+ */
 void *vb200_host_alloc(size_t bytes);
 void vb200_host_free(void *p);
+int vb200_device_numa_node(void);
 
 #ifdef __cplusplus
 }

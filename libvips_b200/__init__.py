@@ -306,7 +306,8 @@ class ThumbnailPlan:
     def __init__(self, width, height, bands=4, target_width=512, target_height=None, size="both",
                  has_alpha=None, linear=False):
         if has_alpha is None:
-            has_alpha = bands in (2, 4)
+            # vips_image_hasalpha for the interpretation Image() guesses: B_W below 3 bands, sRGB from 3
+            has_alpha = bands == 2 or bands >= 4
         self.width, self.height, self.bands = width, height, bands
         self._p = lib().vb200_thumbnail_plan_new(width, height, bands, 0, int(has_alpha), target_width,
                                                  target_height or 0, SIZES[size], int(linear))

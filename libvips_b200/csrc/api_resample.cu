@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "vb200_internal.h"
+#include "vb200_vips_abi.h"
 
 using namespace vb200;
 
@@ -90,9 +91,15 @@ vb200_reduceh(const VB200Image *in, VB200Image *out, double hshrink, int kernel,
 extern "C" int
 vb200_reduce(const VB200Image *in, VB200Image *out, double hshrink, double vshrink, int kernel, double gap)
 {
-	/* reduce.c:97-119: reducev then reduceh */
+	/* reduce.c:97-119: reducev(vshrink) then reduceh(hshrink), the caller's doubles untouched;
+	 * a factor < 1 fails in reduce_geometry with the reference's "reduce factor should be >= 1.0"
+	 */
 	return run_op("reduce", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
-		return dev_resize("reduce", d, o, 1.0 / hshrink, 1.0 / vshrink, kernel, gap, s);
+		if (hshrink < 1.0 || vshrink < 1.0) {
+			error("reduce", "reduce factor should be >= 1.0");
+			return -1;
+		}
+		return dev_reduce_chain("reduce", d, o, hshrink, vshrink, kernel, gap, s);
 	});
 }
 
@@ -385,12 +392,19 @@ vips_reduceh_uchar_hwy(uint8_t *pout, uint8_t *pin, int n, int width, int bands,
 		t.phase[x] = (six + 1) >> 1;
 		pos += hshrink;
 	}
-	const int in_w = t.first[width - 1] + n; /* pixels read from pin */
+	/* pin is a VIRTUAL origin: the caller passes VIPS_REGION_ADDR(ir, ir->valid.left, y) - ir->valid.left * ps
+	 * with X in absolute image coordinates (reduceh.cpp:379-386), so only pixels first[0] .. first[w - 1] + n - 1
+	 * are inside the region.  Copy exactly those and rebase the table.
+	 */
+	const int x0 = t.first[0];
+	const int in_w = t.first[width - 1] + n - x0;
+	for (auto &f : t.first)
+		f -= x0;
 	cudaStream_t s = current_stream();
 	void *din = nullptr, *dout = nullptr;
 	if (dev_alloc(domain, &din, (size_t) in_w * bands, s) || dev_alloc(domain, &dout, (size_t) width * bands, s))
 		return;
-	cudaMemcpyAsync(din, pin, (size_t) in_w * bands, cudaMemcpyHostToDevice, s);
+	cudaMemcpyAsync(din, pin + (ptrdiff_t) x0 * bands, (size_t) in_w * bands, cudaMemcpyHostToDevice, s);
 	if (!launch_reduceh(domain, din, (size_t) in_w * bands, in_w, dout, (size_t) width * bands, bands, width, 1,
 			VB200_FORMAT_UCHAR, t, s)) {
 		cudaMemcpyAsync(pout, dout, (size_t) width * bands, cudaMemcpyDeviceToHost, s);
@@ -479,4 +493,90 @@ vips_shrinkv_write_line_uchar_hwy(uint8_t *pout, int ne, int vshrink, unsigned i
 	cudaStreamSynchronize(s);
 	dev_free(dout, s);
 	dev_free(dsum, s);
+}
+
+/* ------------------------------------------------------ vips_convi_uchar_hwy
+ * reference: convolution/pconvolution.h:74-76, convi_hwy.cpp:93-276 (scalar statement :265-273).
+ */
+namespace {
+
+__global__ void __launch_bounds__(256)
+convi_hwy_kernel(const uint8_t *__restrict__ p0, int in_bpl, uint8_t *__restrict__ q0, int out_bpl, int ne, int nnz,
+	const int *__restrict__ offsets, const short *__restrict__ mant, int exp, int offset)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= ne)
+		return;
+	const uint8_t *p = p0 + (size_t) blockIdx.y * in_bpl + x;
+	int sum = 1 << (exp - 1);
+	for (int i = 0; i < nnz; i++)
+		sum += (int) p[__ldg(offsets + i)] * (int) __ldg(mant + i);
+	q0[(size_t) blockIdx.y * out_bpl + x] = (uint8_t) max(0, min((sum >> exp) + offset, 255));
+}
+
+} // namespace
+
+extern "C" int
+vb200_convi_uchar_vector(uint8_t *q0, int out_bpl, const uint8_t *p0, int in_bpl, int in_line_bytes, int in_rows, int ne,
+	int rows, int nnz, int offset, const int32_t *offsets, const int16_t *mant, int exp)
+{
+	const char *domain = "vips_convi_uchar_hwy";
+	if (!q0 || !p0 || !offsets || !mant || ne <= 0 || rows <= 0 || nnz <= 0 || exp < 1 || exp > 31) {
+		error(domain, "bad argument");
+		return -1;
+	}
+	/* every read must stay inside the prepared input */
+	for (int i = 0; i < nnz; i++) {
+		const long last = (long) (rows - 1) * in_bpl + (ne - 1) + offsets[i];
+		if (offsets[i] < 0 || last / in_bpl >= in_rows || (offsets[i] % in_bpl) + ne > in_line_bytes) {
+			error(domain, "tap %d (offset %d) reads outside the input region", i, offsets[i]);
+			return -1;
+		}
+	}
+	if (ensure_init(domain))
+		return -1;
+	cudaStream_t s = current_stream();
+	void *din = nullptr, *dout = nullptr, *dtab = nullptr;
+	const size_t tab = (size_t) nnz * (sizeof(int) + sizeof(short));
+	int rc = dev_alloc(domain, &din, (size_t) in_bpl * in_rows, s) || dev_alloc(domain, &dout, (size_t) ne * rows, s) ||
+		dev_alloc(domain, &dtab, tab, s);
+	if (!rc) {
+		std::vector<char> host(tab);
+		memcpy(host.data(), offsets, (size_t) nnz * sizeof(int));
+		memcpy(host.data() + (size_t) nnz * sizeof(int), mant, (size_t) nnz * sizeof(short));
+		/* same pitch on the device: the caller's element offsets stay valid */
+		cudaMemcpy2DAsync(din, in_bpl, p0, in_bpl, in_line_bytes, in_rows, cudaMemcpyHostToDevice, s);
+		cudaMemcpyAsync(dtab, host.data(), tab, cudaMemcpyHostToDevice, s);
+		cudaStreamSynchronize(s); /* host staging vector dies with this scope */
+		convi_hwy_kernel<<<dim3((ne + 255) / 256, rows), 256, 0, s>>>((const uint8_t *) din, in_bpl, (uint8_t *) dout, ne, ne, nnz,
+			(const int *) dtab, (const short *) ((char *) dtab + (size_t) nnz * sizeof(int)), exp, offset);
+		count_launch();
+		cudaError_t e = cudaGetLastError();
+		if (e == cudaSuccess)
+			e = cudaMemcpy2DAsync(q0, out_bpl, dout, ne, ne, rows, cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess)
+			rc = cuda_fail(domain, e, "convi_hwy_kernel");
+	}
+	dev_free(din, s);
+	dev_free(dout, s);
+	dev_free(dtab, s);
+	return rc ? -1 : 0;
+}
+
+extern "C" void
+vips_convi_uchar_hwy(VB200VipsRegionHead *out_region, VB200VipsRegionHead *ir, VB200Rect *r, int32_t ne, int32_t nnz,
+	int32_t offset, const int32_t *offsets, const int16_t *mant, int32_t exp)
+{
+	if (!out_region || !ir || !r || !ir->im || !out_region->im)
+		return;
+	/* VIPS_REGION_ADDR, include/vips/region.h:230-233 (uchar: sizeof pel = Bands) */
+	const int ips = ir->im->Bands, ops = out_region->im->Bands;
+	const uint8_t *p0 = ir->data + (size_t) (r->top - ir->valid.top) * ir->bpl + (size_t) (r->left - ir->valid.left) * ips;
+	uint8_t *q0 = out_region->data + (size_t) (r->top - out_region->valid.top) * out_region->bpl +
+		(size_t) (r->left - out_region->valid.left) * ops;
+	const int in_rows = ir->valid.top + ir->valid.height - r->top;
+	const int in_line = (ir->valid.left + ir->valid.width - r->left) * ips;
+	vb200_convi_uchar_vector(q0, out_region->bpl, p0, ir->bpl, in_line, in_rows, ne, r->height, nnz, offset, offsets, mant, exp);
 }

@@ -711,7 +711,8 @@ vb200_colourspace(const VB200Image *in, VB200Image *out, int space)
 	DevImage din, dout;
 	if (to_device(domain, in, &din, s))
 		return -1;
-	preset_output(&dout, in, out);
+	/* colour ops keep the geometry and band count; no output element is wider than a float */
+	preset_output(&dout, in, out, (size_t) in->Xsize * in->Bands * 4, in->Ysize);
 	int rc = dev_colourspace(domain, din, &dout, space, in->Type, s);
 	if (!rc)
 		rc = deliver(domain, &dout, in, out, s);

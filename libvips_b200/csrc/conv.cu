@@ -14,6 +14,7 @@
  * The vips_embed(EXTEND_COPY) in front of every conv (convf.c:335-341) is clamp addressing.
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -24,7 +25,7 @@ namespace vb200 {
 
 namespace {
 
-static bool g_vector_convi = false;
+static std::atomic<bool> g_vector_convi{false};
 
 struct Tap {
 	int dx, dy; /* relative to the output pixel, already minus M / 2 */
@@ -512,7 +513,7 @@ upload_taps(const char *domain, const std::vector<int> &pos, int mw, int mh, con
 
 int
 dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, double scale,
-	double offset, int precision, cudaStream_t s)
+	double offset, int precision, cudaStream_t s, bool allow_vector)
 {
 	if (!format_is_supported(in.fmt)) {
 		error(domain, "band format %d not supported on the device path", in.fmt);
@@ -612,7 +613,7 @@ dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *ma
 		P.out_bpl = out->bpl;
 		std::vector<int> mant, pos;
 		int exp = 0;
-		if (g_vector_convi && in.fmt == VB200_FORMAT_UCHAR && intize8(mask, n, scale, mant, pos, &exp)) {
+		if (allow_vector && g_vector_convi.load() && in.fmt == VB200_FORMAT_UCHAR && intize8(mask, n, scale, mant, pos, &exp)) {
 			/* the Highway arithmetic (convi.c:1152-1160 picks it for uchar when intize succeeds) */
 			P.exp = exp;
 			P.ioffset = rint(offset);
@@ -668,17 +669,41 @@ dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *ma
 	return 0;
 }
 
-/* vips_convsep, convsep.c:61-114: conv(M) then conv(rot90(M)) with offset 0 and the same scale */
+/* 0 = done, -1 = error, 1 = this mask / image is not eligible (defined below) */
+int dev_convsep_fused(const char *domain, const DevImage &in, DevImage *out, const double *first, const double *second, int mw,
+	int mh, double scale, double offset, cudaStream_t s);
+
+/* vips_convsep, convsep.c:61-114: conv(M) as given, with its offset, then conv(rot90(M)) with offset 0
+ * and the same scale.  vips_rot90 (conversion/rot.c:100-156) maps out(x, y) = in(y, Ysize - 1 - x): an
+ * n x 1 mask becomes the 1 x n column in the same order; a 1 x n mask becomes the n x 1 row REVERSED.
+ */
 int
-dev_convsep(const char *domain, const DevImage &in, DevImage *out, const double *mask, int n, double scale,
-	double offset, int precision, cudaStream_t s)
+dev_convsep(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, double scale,
+	double offset, int precision, cudaStream_t s, bool allow_vector)
 {
+	const int n = mw * mh;
+	std::vector<double> rot(mask, mask + n);
+	if (mw == 1)
+		std::reverse(rot.begin(), rot.end());
+	/* the dense float pair as ONE kernel: the intermediate never leaves shared memory */
+	if (precision == VB200_PRECISION_FLOAT) {
+		const int fused = dev_convsep_fused(domain, in, out, mask, rot.data(), mw, mh, scale, offset, s);
+		if (fused <= 0)
+			return fused; /* 0 done, -1 failed; 1 = not eligible */
+	}
 	DevImage mid;
-	if (dev_conv(domain, in, &mid, mask, n, 1, scale, offset, precision, s))
+	if (dev_conv(domain, in, &mid, mask, mw, mh, scale, offset, precision, s, allow_vector))
 		return -1;
-	int r = dev_conv(domain, mid, out, mask, 1, n, scale, 0.0, precision, s);
+	int r = dev_conv(domain, mid, out, rot.data(), mh, mw, scale, 0.0, precision, s, allow_vector);
 	dev_image_release(&mid, s);
 	return r;
+}
+
+int
+dev_convsep_fused(const char *domain, const DevImage &in, DevImage *out, const double *first, const double *second, int mw,
+	int mh, double scale, double offset, cudaStream_t s)
+{
+	return 1;
 }
 
 /* vips_gaussmat, create/gaussmat.c:93-170 */
@@ -730,7 +755,7 @@ dev_gaussblur(const char *domain, const DevImage &in, DevImage *out, double sigm
 	int w, h;
 	double scale;
 	host_gaussmat(sigma, min_ampl, true, precision != VB200_PRECISION_FLOAT, m, &w, &h, &scale);
-	return dev_convsep(domain, in, out, m.data(), w, scale, 0.0, precision, s);
+	return dev_convsep(domain, in, out, m.data(), w, h, scale, 0.0, precision, s, true);
 }
 
 /* vips_sharpen, sharpen.c:171-303 */
@@ -790,10 +815,7 @@ dev_sharpen(const char *domain, const DevImage &in, DevImage *out, double sigma,
 			L.bpl, labs.w);
 		count_launch();
 		/* short input: always the exact C path, never the vector one */
-		const bool saved = g_vector_convi;
-		g_vector_convi = false;
-		rc = dev_convsep(domain, L, &blur, m.data(), mw, scale, 0.0, VB200_PRECISION_INTEGER, s);
-		g_vector_convi = saved;
+		rc = dev_convsep(domain, L, &blur, m.data(), mw, mh, scale, 0.0, VB200_PRECISION_INTEGER, s, false);
 	}
 	if (!rc) {
 		sharpen_kernel<<<grid, 256, 0, s>>>((short *) labs.data, labs.bpl, labs.bands, (const short *) blur.data, blur.bpl,
@@ -833,7 +855,8 @@ run_conv_op(const char *domain, const VB200Image *in, VB200Image *out, Op op, bo
 	if (to_device(domain, in, &din, s))
 		return -1;
 	if (direct)
-		preset_output(&dout, in, out);
+		/* convolutions keep the geometry; convf widens to float */
+		preset_output(&dout, in, out, (size_t) in->Xsize * in->Bands * std::max<size_t>(4, format_sizeof(in->BandFmt)), in->Ysize);
 	int rc = op(din, &dout, s);
 	if (!rc) {
 		if (dout.data == din.data) {
@@ -862,7 +885,7 @@ vb200_conv(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int pre
 		return -1;
 	}
 	return run_conv_op("conv", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
-		return dev_conv("conv", d, o, mask->coeff, mask->width, mask->height, mask->scale, mask->offset, precision, s);
+		return dev_conv("conv", d, o, mask->coeff, mask->width, mask->height, mask->scale, mask->offset, precision, s, true);
 	}, true);
 }
 
@@ -878,9 +901,9 @@ vb200_convsep(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int 
 		error("convsep", "mask must be 1xn or nx1 elements");
 		return -1;
 	}
-	const int n = mask->width * mask->height;
 	return run_conv_op("convsep", in, out, [&](const DevImage &d, DevImage *o, cudaStream_t s) {
-		return dev_convsep("convsep", d, o, mask->coeff, n, mask->scale, mask->offset, precision, s);
+		return dev_convsep("convsep", d, o, mask->coeff, mask->width, mask->height, mask->scale, mask->offset, precision, s,
+			true);
 	}, true);
 }
 

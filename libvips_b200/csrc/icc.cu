@@ -124,6 +124,8 @@ parse_curve(const Blob &b, const char *sig, IccCurve *c, std::vector<float> &poo
 			return true;
 		}
 		if (n == 1) {
+			if (!b.ok(off + 12, 2))
+				return false; /* truncated 'curv' tag */
 			c->kind = CURVE_PARA;
 			c->ptype = 0;
 			c->p[0] = b.u16(off + 12) / 256.0;
@@ -301,6 +303,8 @@ parse_lut(const Blob &b, const char *sig, IccLut *l, std::vector<float> &pool)
 	}
 	size_t p = off + 48;
 	if (is16) {
+		if (!b.ok(p, 4))
+			return false; /* truncated 'mft2' tag */
 		l->n_in = (int) b.u16(p);
 		l->n_out = (int) b.u16(p + 2);
 		p += 4;
@@ -1188,7 +1192,7 @@ run_icc(const char *domain, const VB200Image *in, VB200Image *out, const JobSpec
 			rc = -1;
 	}
 	J.in.pool = J.out.pool = dpool;
-	preset_output(&dout, in, out);
+	preset_output(&dout, in, out, (size_t) din.w * ob * format_sizeof(of), din.h); /* the exact result extent (grey -> Lab widens 1 band to 3 floats) */
 	if (!rc)
 		rc = dev_image_new(domain, &dout, din.w, din.h, ob, of, ot, s);
 	if (!rc) {

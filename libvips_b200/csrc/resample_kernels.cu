@@ -808,13 +808,23 @@ dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale,
 	}
 	const double vs = vscale < 1.0 ? 1.0 / vscale : 1.0;
 	const double hs = hscale < 1.0 ? 1.0 / hscale : 1.0;
+	return dev_reduce_chain(domain, in, out, hs, vs, kernel, gap, s);
+}
 
+/* reducev(vshrink) then reduceh(hshrink) with the caller's doubles: the downsizing half of
+ * vips_resize (resize.c:215-231) and the whole of vips_reduce (reduce.c:106-114).  A factor of
+ * exactly 1.0 skips its pass, as both builds do.
+ */
+int
+dev_reduce_chain(const char *domain, const DevImage &in, DevImage *out, double hs, double vs, int kernel, double gap,
+	cudaStream_t s)
+{
 	ReduceGeom gv, gh;
 	gv.int_shrink = gh.int_shrink = 1;
 	gh.out_size = in.w;
-	if (vs > 1.0 && reduce_geometry(domain, in.h, vs, kernel, gap, &gv))
+	if (vs != 1.0 && reduce_geometry(domain, in.h, vs, kernel, gap, &gv))
 		return -1;
-	if (hs > 1.0 && reduce_geometry(domain, in.w, hs, kernel, gap, &gh))
+	if (hs != 1.0 && reduce_geometry(domain, in.w, hs, kernel, gap, &gh))
 		return -1;
 
 	/* Sink tile geometry from the pipeline's demand hint: the minimum over
@@ -841,9 +851,9 @@ dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale,
 
 	DevImage mid = in;
 	mid.owned = false;
-	if (vs > 1.0 && dev_reducev(domain, in, &mid, vs, kernel, gap, rect_h, s))
+	if (vs != 1.0 && dev_reducev(domain, in, &mid, vs, kernel, gap, rect_h, s))
 		return -1;
-	if (hs > 1.0) {
+	if (hs != 1.0) {
 		int r = dev_reduceh(domain, mid, out, hs, kernel, gap, tile_w, s);
 		dev_image_release(&mid, s);
 		return r;

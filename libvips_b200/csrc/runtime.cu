@@ -7,10 +7,16 @@
  * VIPS_NOVECTOR), and tile-geometry globals (iofuncs/thread.c:74-77).
  */
 #include <atomic>
+#include <cctype>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "vb200_internal.h"
 
@@ -25,6 +31,11 @@ static std::mutex g_init_lock;
  * include/vips/private.h:147-153
  */
 static TileGeometry g_tiles = {128, 128, 16, 1};
+static std::mutex g_tiles_lock;
+/* the device this thread's CUDA runtime is bound to: generate() callbacks arrive on worker threads
+ * the library has never seen (iofuncs/region.c:1600-1626), and a fresh thread defaults to device 0
+ */
+static thread_local int t_bound_device = -1;
 
 void
 error(const char *domain, const char *fmt, ...)
@@ -62,15 +73,26 @@ count_launch(int n)
 TileGeometry
 tile_geometry()
 {
+	std::lock_guard<std::mutex> lock(g_tiles_lock);
 	return g_tiles;
 }
 
 int
 ensure_init(const char *domain)
 {
-	if (g_device.load() >= 0)
-		return 0;
-	return vb200_init(0) ? (error(domain, "libvb200 is not initialised and no CUDA device is usable"), -1) : 0;
+	int dev = g_device.load();
+	if (dev < 0) {
+		if (vb200_init(0)) {
+			error(domain, "libvb200 is not initialised and no CUDA device is usable");
+			return -1;
+		}
+		dev = g_device.load();
+	}
+	if (t_bound_device != dev) {
+		VB200_CUDA(domain, cudaSetDevice(dev));
+		t_bound_device = dev;
+	}
+	return 0;
 }
 
 int
@@ -129,6 +151,41 @@ format_is_supported(int fmt)
 	return false;
 }
 
+int
+interpretation_bands(int type)
+{
+	/* reference: vips_interpretation_bands, iofuncs/header.c:217-249 (the interpretations this ABI names) */
+	switch (type) {
+	case VB200_INTERPRETATION_B_W:
+	case VB200_INTERPRETATION_GREY16:
+		return 1;
+	case VB200_INTERPRETATION_XYZ:
+	case VB200_INTERPRETATION_LAB:
+	case VB200_INTERPRETATION_LABS:
+	case VB200_INTERPRETATION_sRGB:
+	case VB200_INTERPRETATION_RGB16:
+	case VB200_INTERPRETATION_scRGB:
+	case 17: /* RGB */
+	case 18: /* CMC */
+	case 19: /* LCH */
+	case 23: /* YXY */
+	case 29: /* HSV */
+		return 3;
+	case VB200_INTERPRETATION_CMYK:
+		return 4;
+	default:
+		return 0;
+	}
+}
+
+bool
+image_hasalpha(int type, int bands)
+{
+	/* reference: vips_image_hasalpha, iofuncs/image.c:3113-3119 */
+	const int real = interpretation_bands(type);
+	return real > 0 && bands > real;
+}
+
 double
 interpretation_max_alpha(int type)
 {
@@ -167,17 +224,17 @@ dev_image_new(const char *domain, DevImage *d, int w, int h, int bands, int fmt,
 }
 
 void
-preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out)
+preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out, size_t out_line_bytes, int out_rows)
 {
 	if (in->where != VB200_DEVICE || !out->data || !in->data)
 		return;
 	const size_t in_bytes = (in->bpl ? in->bpl : (size_t) in->Xsize * in->Bands * format_sizeof(in->BandFmt)) * in->Ysize;
 	const char *a = (const char *) in->data, *o = (const char *) out->data;
-	/* no aliasing: the result must lie wholly before or after the input.  Its extent is not known
-	 * yet; no device op produces wider than 4-byte elements, and none changes the pixel count.
+	/* no aliasing: the result (out_rows lines of out_line_bytes, at the caller's stride if that is
+	 * larger) must lie wholly before or after the input
 	 */
-	const size_t out_line = std::max((size_t) out->bpl, (size_t) in->Xsize * in->Bands * 4);
-	if (o >= a + in_bytes || o + out_line * in->Ysize <= a) {
+	const size_t out_line = std::max((size_t) out->bpl, out_line_bytes);
+	if (o >= a + in_bytes || o + out_line * (size_t) out_rows <= a) {
 		dout->data = out->data;
 		dout->bpl = out->bpl;
 		dout->preset = true;
@@ -319,6 +376,7 @@ vb200_init(int device)
 		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
 	}
 	g_device.store(device);
+	t_bound_device = device;
 	return 0;
 }
 
@@ -368,6 +426,7 @@ vb200_get_stream(void)
 extern "C" void
 vb200_set_tile_geometry(int tile_width, int tile_height, int fatstrip_height, int thinstrip_height)
 {
+	std::lock_guard<std::mutex> lock(g_tiles_lock);
 	if (tile_width > 0)
 		g_tiles.tile_width = tile_width;
 	if (tile_height > 0)
@@ -402,11 +461,96 @@ vb200_format_sizeof(int band_format)
 	return format_sizeof(band_format);
 }
 
+/* ---------------------------------------------------------------- pinned host memory
+ * The pump's host buffers: page-locked, and placed on the NUMA node the GPU hangs off (on the 8-GPU
+ * boxes GPUs 4-7 sit on node 1; a plain cudaHostAlloc from a process that runs on node 0 makes every
+ * H2D copy of those ranks cross the socket interconnect).  mmap + mbind(MPOL_PREFERRED) + first touch
+ * + cudaHostRegister; any failure falls back to cudaHostAlloc.
+ */
+namespace {
+
+std::mutex g_host_lock;
+std::map<void *, size_t> g_host_registered; /* mmap'ed + registered blocks */
+
+int
+gpu_numa_node(int device)
+{
+	char bus[64];
+	if (device < 0 || cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+		cudaGetLastError();
+		return -1;
+	}
+	for (char *c = bus; *c; c++)
+		*c = (char) tolower(*c);
+	char path[160];
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+	FILE *f = fopen(path, "r");
+	if (!f)
+		return -1;
+	int node = -1;
+	if (fscanf(f, "%d", &node) != 1)
+		node = -1;
+	fclose(f);
+	if (node < 0)
+		return -1;
+	/* only worth it on a machine with more than one node */
+	if (access("/sys/devices/system/node/node1", F_OK) != 0)
+		return -1;
+	return node;
+}
+
+void *
+numa_pinned_alloc(size_t bytes, int node)
+{
+	const size_t huge = (size_t) 2 << 20;
+	const size_t len = (bytes + huge - 1) & ~(huge - 1);
+	void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+	if (p == MAP_FAILED)
+		return nullptr;
+#ifdef SYS_mbind
+	unsigned long mask[16];
+	memset(mask, 0, sizeof(mask));
+	mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+	/* MPOL_PREFERRED = 1: pages come from `node` while it has memory, never an OOM kill */
+	if (syscall(SYS_mbind, p, len, 1, mask, (unsigned long) (8 * sizeof(mask) + 1), 0) != 0) {
+		munmap(p, len);
+		return nullptr; /* no policy, no point: let cudaHostAlloc do it */
+	}
+#else
+	munmap(p, len);
+	return nullptr;
+#endif
+	memset(p, 0, len); /* first touch under the policy */
+	if (cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+		cudaGetLastError();
+		munmap(p, len);
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lock(g_host_lock);
+	g_host_registered[p] = len;
+	return p;
+}
+
+} // namespace
+
 extern "C" void *
 vb200_host_alloc(size_t bytes)
 {
+	if (ensure_init("host_alloc"))
+		return nullptr;
+	if (bytes == 0)
+		bytes = 1;
+	const char *off = getenv("VB200_NO_NUMA");
+	if (!(off && *off && strcmp(off, "0") != 0)) {
+		const int node = gpu_numa_node(g_device.load());
+		if (node >= 0) {
+			void *p = numa_pinned_alloc(bytes, node);
+			if (p)
+				return p;
+		}
+	}
 	void *p = nullptr;
-	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess)
 		return nullptr;
 	return p;
 }
@@ -414,6 +558,30 @@ vb200_host_alloc(size_t bytes)
 extern "C" void
 vb200_host_free(void *p)
 {
-	if (p)
+	if (!p)
+		return;
+	size_t len = 0;
+	{
+		std::lock_guard<std::mutex> lock(g_host_lock);
+		auto it = g_host_registered.find(p);
+		if (it != g_host_registered.end()) {
+			len = it->second;
+			g_host_registered.erase(it);
+		}
+	}
+	if (len) {
+		cudaHostUnregister(p);
+		munmap(p, len);
+	}
+	else
 		cudaFreeHost(p);
+}
+
+/* the NUMA node of the current device (-1: unknown or a single-node machine); the host binding
+ * may want to run its feeder threads there (bench.py does)
+ */
+extern "C" int
+vb200_device_numa_node(void)
+{
+	return gpu_numa_node(g_device.load());
 }

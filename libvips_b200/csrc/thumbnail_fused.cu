@@ -1400,7 +1400,10 @@ struct ThumbnailPlanImpl {
 	cudaStream_t streams[kStreams] = {nullptr, nullptr, nullptr};
 	void *stage_in[kStreams] = {nullptr, nullptr, nullptr};
 	void *stage_out[kStreams] = {nullptr, nullptr, nullptr};
+	cudaEvent_t drained[kStreams] = {nullptr, nullptr, nullptr};
 	int stage_frames = 0;
+	std::mutex pump_lock;
+	std::mutex launch_lock;
 };
 
 namespace {
@@ -2030,7 +2033,10 @@ thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void 
 			if (handled)
 				return rc;
 		}
-		/* enough CTAs to fill the machine: split rows when the batch is small */
+		/* enough CTAs to fill the machine: split rows when the batch is small.  This (fallback) path
+		 * writes the per-launch geometry into the plan: serialise concurrent callers of one plan
+		 */
+		std::lock_guard<std::mutex> launch_lock(pl->launch_lock);
 		FusedParams &fp = pl->fp;
 		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
 		int rpc = ((pl->OH + kChunkRows - 1) / kChunkRows) * kChunkRows;
@@ -2090,6 +2096,8 @@ thumbnail_plan_destroy(ThumbnailPlanImpl *pl)
 			cudaFree(pl->stage_in[i]);
 		if (pl->stage_out[i])
 			cudaFree(pl->stage_out[i]);
+		if (pl->drained[i])
+			cudaEventDestroy(pl->drained[i]);
 		if (pl->streams[i])
 			cudaStreamDestroy(pl->streams[i]);
 	}
@@ -2200,6 +2208,8 @@ vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in
 		error(domain, "null argument");
 		return -1;
 	}
+	if (ensure_init(domain))
+		return -1;
 	return thumbnail_plan_run_device(domain, &plan->impl, in, in_frame_stride, out, out_frame_stride, n_frames,
 		current_stream());
 }
@@ -2219,13 +2229,21 @@ vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t in_f
 		error(domain, "null argument");
 		return -1;
 	}
+	if (ensure_init(domain))
+		return -1;
 	ThumbnailPlanImpl &pl = plan->impl;
+	std::lock_guard<std::mutex> lock(pl.pump_lock); /* one pump per plan at a time: the staging ring is the plan's */
 	const size_t in_frame = (size_t) pl.W * pl.H * pl.bands;
 	const size_t out_frame = (size_t) pl.OW * pl.OH * pl.bands;
-	/* slice size: ~64 MiB of input per slot */
+	/* Slice size: ~64 MiB of input per slot (one 4K RGBA frame).  The pump is bound by the H2D copy
+	 * (one such frame is 1.2 ms of PCIe against 14 us of kernel), so small slices cost nothing and
+	 * shorten the pipeline fill; small frames are batched up to the same byte budget.
+	 */
 	const int per_slice = (int) std::max<size_t>(1, std::min<size_t>(n_frames, (64u << 20) / in_frame));
 	if (pl.stage_frames < per_slice) {
 		for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
+			if (pl.streams[i])
+				cudaStreamSynchronize(pl.streams[i]);
 			if (pl.stage_in[i])
 				cudaFree(pl.stage_in[i]);
 			if (pl.stage_out[i])
@@ -2235,26 +2253,34 @@ vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t in_f
 			VB200_CUDA(domain, cudaMalloc(&pl.stage_out[i], out_frame * per_slice));
 			if (!pl.streams[i])
 				VB200_CUDA(domain, cudaStreamCreateWithFlags(&pl.streams[i], cudaStreamNonBlocking));
+			if (!pl.drained[i])
+				VB200_CUDA(domain, cudaEventCreateWithFlags(&pl.drained[i], cudaEventDisableTiming | cudaEventBlockingSync));
 		}
 		pl.stage_frames = per_slice;
 	}
 
+	bool used[ThumbnailPlanImpl::kStreams] = {false, false, false};
 	int slot = 0;
 	for (int f = 0; f < n_frames; f += per_slice, slot = (slot + 1) % ThumbnailPlanImpl::kStreams) {
 		const int n = std::min(per_slice, n_frames - f);
 		cudaStream_t s = pl.streams[slot];
-		/* the slot's previous slice must have drained before we overwrite it */
-		VB200_CUDA(domain, cudaStreamSynchronize(s));
+		/* the slot's previous slice must have drained (its D2H recorded the event) before its staging
+		 * buffers are overwritten; the host sleeps on the event instead of spinning on the stream
+		 */
+		if (used[slot])
+			VB200_CUDA(domain, cudaEventSynchronize(pl.drained[slot]));
 		VB200_CUDA(domain, cudaMemcpy2DAsync(pl.stage_in[slot], in_frame, (const char *) in + (size_t) f * in_frame_stride,
 							   in_frame_stride, in_frame, n, cudaMemcpyHostToDevice, s));
 		if (thumbnail_plan_run_device(domain, &pl, pl.stage_in[slot], in_frame, pl.stage_out[slot], out_frame, n, s))
 			return -1;
 		VB200_CUDA(domain, cudaMemcpy2DAsync((char *) out + (size_t) f * out_frame_stride, out_frame_stride,
 							   pl.stage_out[slot], out_frame, out_frame, n, cudaMemcpyDeviceToHost, s));
+		VB200_CUDA(domain, cudaEventRecord(pl.drained[slot], s));
+		used[slot] = true;
 	}
 	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++)
-		if (pl.streams[i])
-			VB200_CUDA(domain, cudaStreamSynchronize(pl.streams[i]));
+		if (used[i])
+			VB200_CUDA(domain, cudaEventSynchronize(pl.drained[i]));
 	return 0;
 }
 
@@ -2289,7 +2315,7 @@ vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int heig
 		DevImage din, lin, pre, res, unpre, fin;
 		if (to_device(domain, in, &din, s))
 			return -1;
-		const bool premul = (in->Bands == 4 || in->Bands > 4) && hs != 1.0 && vs != 1.0;
+		const bool premul = image_hasalpha(in->Type, in->Bands) && hs != 1.0 && vs != 1.0;
 		int rc = dev_colourspace(domain, din, &lin, VB200_INTERPRETATION_scRGB, VB200_INTERPRETATION_sRGB, s);
 		const DevImage *cur = &lin;
 		if (!rc && premul) {
@@ -2315,8 +2341,8 @@ vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int heig
 		dev_image_release(&fin, s);
 		return rc;
 	}
-	/* vips_image_hasalpha(): 2 or 4 bands (iofuncs/header.c) for 8-bit sRGB / B_W */
-	const int has_alpha = in->Bands == 2 || in->Bands == 4;
+	/* vips_image_hasalpha(): more bands than the interpretation implies (iofuncs/image.c:3113-3119) */
+	const int has_alpha = image_hasalpha(in->Type, in->Bands);
 	VB200ThumbnailPlan *plan = vb200_thumbnail_plan_new(in->Xsize, in->Ysize, in->Bands, in->BandFmt, has_alpha, width,
 		height, size, 0);
 	if (!plan)

@@ -65,7 +65,7 @@ int dev_image_new(const char *domain, DevImage *d, int w, int h, int bands, int 
 /* Let the op write straight into a device buffer the caller supplied (no device-to-device copy in
  * deliver()), when it cannot alias the input.
  */
-void preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out);
+void preset_output(DevImage *dout, const VB200Image *in, const VB200Image *out, size_t out_line_bytes, int out_rows);
 void dev_image_release(DevImage *d, cudaStream_t s);
 
 /* ------------------------------------------------------------ resample host */
@@ -122,7 +122,13 @@ int dev_unpremultiply(const char *domain, const DevImage &in, DevImage *out, dou
 int dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,
 	double gap, cudaStream_t s);
 
+int dev_reduce_chain(const char *domain, const DevImage &in, DevImage *out, double hshrink, double vshrink, int kernel,
+	double gap, cudaStream_t s);
+
 double interpretation_max_alpha(int type);
+/* vips_interpretation_bands / vips_image_hasalpha, iofuncs/header.c:217-249, image.c:3113-3119 */
+int interpretation_bands(int type);
+bool image_hasalpha(int type, int bands);
 
 /* affine.cu */
 int dev_resize_up(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,

@@ -4,6 +4,8 @@ void vips_call_split(void) { fputs("ref shim: vips_call_split() is not available
 void vips_cast(void) { fputs("ref shim: vips_cast() is not available", stderr); abort(); }
 void vips_colour_code_get_type(void) { fputs("ref shim: vips_colour_code_get_type() is not available", stderr); abort(); }
 void vips_colour_transform_get_type(void) { fputs("ref shim: vips_colour_transform_get_type() is not available", stderr); abort(); }
+void vips_conva(void) { fputs("ref shim: vips_conva() is not available", stderr); abort(); }
+void vips_convasep(void) { fputs("ref shim: vips_convasep() is not available", stderr); abort(); }
 void vips_interpolate_lbb_get_type(void) { fputs("ref shim: vips_interpolate_lbb_get_type() is not available", stderr); abort(); }
 void vips_interpolate_nohalo_get_type(void) { fputs("ref shim: vips_interpolate_nohalo_get_type() is not available", stderr); abort(); }
 void vips_interpolate_vsqbs_get_type(void) { fputs("ref shim: vips_interpolate_vsqbs_get_type() is not available", stderr); abort(); }

@@ -353,18 +353,33 @@ orc_conv(const void *in, int w, int h, int bands, int fmt, const double *mask, i
 	return 0;
 }
 
-/* vips_convsep, convsep.c:61-114: conv(M) then conv(rot90(M), offset 0), same scale.
- * mask is a 1-D mask of n elements (n x 1).
+/* vips_convsep, convsep.c:61-114: conv(M) as given, then conv(rot90(M)) with offset 0, same scale.
+ * vips_rot90 (conversion/rot.c:100-156): out(x, y) = in(y, Ysize - 1 - x), so an n x 1 row becomes
+ * the 1 x n column in the same order and a 1 x n column becomes the n x 1 row reversed.
  */
+extern "C" int
+orc_convsep2(const void *in, int w, int h, int bands, int fmt, const double *mask, int mw, int mh, double scale,
+	double offset, int precision, int vector, void *out)
+{
+	if (mw != 1 && mh != 1)
+		return -1; /* vips_check_separable */
+	const int n = mw * mh;
+	std::vector<double> rot(mask, mask + n);
+	if (mw == 1)
+		std::reverse(rot.begin(), rot.end());
+	const int mid_fmt = orc_conv_out_format(fmt, precision);
+	std::vector<uint8_t> mid((size_t) w * h * bands * orc_sizeof_format(mid_fmt));
+	if (orc_conv(in, w, h, bands, fmt, mask, mw, mh, scale, offset, precision, vector, mid.data()))
+		return -1;
+	return orc_conv(mid.data(), w, h, bands, mid_fmt, rot.data(), mh, mw, scale, 0.0, precision, vector, out);
+}
+
+/* the n x 1 (horizontal first) case under its old name */
 extern "C" int
 orc_convsep(const void *in, int w, int h, int bands, int fmt, const double *mask, int n, double scale, double offset,
 	int precision, int vector, void *out)
 {
-	const int mid_fmt = orc_conv_out_format(fmt, precision);
-	std::vector<uint8_t> mid((size_t) w * h * bands * orc_sizeof_format(mid_fmt));
-	if (orc_conv(in, w, h, bands, fmt, mask, n, 1, scale, offset, precision, vector, mid.data()))
-		return -1;
-	return orc_conv(mid.data(), w, h, bands, mid_fmt, mask, 1, n, scale, 0.0, precision, vector, out);
+	return orc_convsep2(in, w, h, bands, fmt, mask, n, 1, scale, offset, precision, vector, out);
 }
 
 /* vips_gaussblur, gaussblur.c:70-114 */
@@ -380,6 +395,27 @@ orc_gaussblur(const void *in, int w, int h, int bands, int fmt, double sigma, do
 	std::vector<double> m(n);
 	const double scale = orc_gaussmat(sigma, min_ampl, 1, precision != 1, m.data());
 	return orc_convsep(in, w, h, bands, fmt, m.data(), n, scale, 0.0, precision, vector, out);
+}
+
+/* the LUT of vips_sharpen_build, sharpen.c:227-257: index = signed L difference + 32768 */
+extern "C" void
+orc_sharpen_lut(double x1, double y2, double y3, double m1, double m2, int *lut)
+{
+	for (int i = 0; i < 65536; i++) {
+		double v = (i - 32767) / 327.67;
+		double y;
+		if (v < -x1)
+			y = (v + x1) * m2 + -x1 * m1;
+		else if (v < x1)
+			y = v * m1;
+		else
+			y = (v - x1) * m2 + x1 * m1;
+		if (y < -y3)
+			y = -y3;
+		if (y > y2)
+			y = y2;
+		lut[i] = rint(y * 327.67);
+	}
 }
 
 /* vips_sharpen on an image of interpretation `type` whose format is the
@@ -399,21 +435,7 @@ orc_sharpen(const void *in, int w, int h, int bands, int fmt, int type, double s
 	const double scale = orc_gaussmat(sigma, 0.1, 1, 1, m.data());
 
 	std::vector<int> lut(65536);
-	for (int i = 0; i < 65536; i++) {
-		double v = (i - 32767) / 327.67;
-		double y;
-		if (v < -x1)
-			y = (v + x1) * m2 + -x1 * m1;
-		else if (v < x1)
-			y = v * m1;
-		else
-			y = (v - x1) * m2 + x1 * m1;
-		if (y < -y3)
-			y = -y3;
-		if (y > y2)
-			y = y2;
-		lut[i] = rint(y * 327.67);
-	}
+	orc_sharpen_lut(x1, y2, y3, m1, m2, lut.data());
 
 	std::vector<int16_t> L(n), blur(n);
 	for (size_t i = 0; i < n; i++)

@@ -47,14 +47,18 @@ def conv(a, mask, scale=1.0, offset=0.0, precision="float", vector=False):
 
 
 def convsep(a, mask, scale=1.0, offset=0.0, precision="float", vector=False):
+    """mask: 1-D (taken as n x 1, horizontal pass first) or 2-D with one dimension 1 (a column
+    runs the vertical pass first, then the reversed row: vips_rot90)."""
     a, h, w, b, f = pyoracle._img(a)
-    mask = np.ascontiguousarray(mask, np.float64).ravel()
+    mask = np.ascontiguousarray(mask, np.float64)
+    if mask.ndim == 1:
+        mask = mask[None, :]
     out = np.empty((h, w, b), _out_dtype(a.dtype, precision))
     L = pyoracle.lib()
-    L.orc_convsep.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
-                              C.c_double, C.c_int, C.c_int, C.c_void_p]
-    if L.orc_convsep(a.ctypes.data, w, h, b, f, mask.ctypes.data, mask.size, scale, offset, _prec(precision),
-                     int(vector), out.ctypes.data):
+    L.orc_convsep2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                               C.c_double, C.c_int, C.c_int, C.c_void_p]
+    if L.orc_convsep2(a.ctypes.data, w, h, b, f, mask.ctypes.data, mask.shape[1], mask.shape[0], scale, offset,
+                      _prec(precision), int(vector), out.ctypes.data):
         raise ValueError("convsep")
     return out
 
@@ -132,3 +136,42 @@ def ref_gaussmat(sigma, min_ampl, separable=False, precision="integer"):
     w, h = L.ref_image_width(m), L.ref_image_height(m)
     data = np.frombuffer((C.c_uint8 * (w * h * 8)).from_address(L.ref_matrix_data(m)), dtype=np.float64)
     return data.reshape(h, w).copy(), L.ref_matrix_scale(m), L.ref_matrix_offset(m)
+
+
+def ref_convsep(a, mask, scale=1.0, offset=0.0, precision="float", tile=(0, 0)):
+    """vips_convsep through the reference's own convsep.c / conv.c / rot.c / convf.c / convi.c"""
+    L = _rl()
+    L.ref_convsep.restype = C.c_void_p
+    L.ref_convsep.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    mask = np.ascontiguousarray(mask, np.float64)
+    if mask.ndim == 1:
+        mask = mask[None, :]
+    m = L.ref_matrix(mask.ctypes.data, mask.shape[1], mask.shape[0], scale, offset)
+    im = pyref.RefImage.from_array(a)
+    return pyref.RefImage(L.ref_convsep(im.h, m, _prec(precision)), (im, mask)).numpy(tile)
+
+
+def ref_sharpen(a, interpretation, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0, tile=(0, 0)):
+    """vips_sharpen through the reference's own sharpen.c (build + generate), 3-band images"""
+    L = _rl()
+    L.ref_sharpen.restype = C.c_void_p
+    L.ref_sharpen.argtypes = [C.c_void_p] + [C.c_double] * 6
+    im = pyref.RefImage.from_array(a, pyoracle._space(interpretation))
+    return pyref.RefImage(L.ref_sharpen(im.h, sigma, x1, y2, y3, m1, m2), (im,)).numpy(tile)
+
+
+def ref_sharpen_lut(sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+    L = _rl()
+    L.ref_sharpen_lut.argtypes = [C.c_double] * 6 + [C.c_void_p]
+    lut = np.zeros(65536, np.int32)
+    if L.ref_sharpen_lut(sigma, x1, y2, y3, m1, m2, lut.ctypes.data):
+        raise ValueError("ref sharpen lut")
+    return lut
+
+
+def sharpen_lut(x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+    L = pyoracle.lib()
+    L.orc_sharpen_lut.argtypes = [C.c_double] * 5 + [C.c_void_p]
+    lut = np.zeros(65536, np.int32)
+    L.orc_sharpen_lut(x1, y2, y3, m1, m2, lut.ctypes.data)
+    return lut

@@ -170,7 +170,7 @@ def thumbnail_image(a, width, height=None, size="both", has_alpha=None, tile=(0,
     a, h, w, b, f = _img(a)
     assert a.dtype == np.uint8
     if has_alpha is None:
-        has_alpha = b in (2, 4)
+        has_alpha = b == 2 or b >= 4  # vips_image_hasalpha for B_W (< 3 bands) / sRGB (3+), image.c:3113-3119
     height = width if height is None else height
     _, _, ow, oh = thumbnail_size(w, h, width, height, size)
     out = np.empty((oh, ow, b), np.uint8)

@@ -128,7 +128,7 @@ def thumbnail_image(a, width, height=None, size="both", tile=(0, 0)):
     h, w, b = a.shape
     hs, vs, _, _ = pyoracle.thumbnail_size(w, h, width, height, size)
     im = RefImage.from_array(a)
-    premul = b in (2, 4) and hs != 1.0 and vs != 1.0
+    premul = (b == 2 or b >= 4) and hs != 1.0 and vs != 1.0
     if premul:
         im = im.premultiply(uchar=True)
     im = im.resize(1.0 / hs, 1.0 / vs)

@@ -103,3 +103,11 @@ void *ref_gaussmat(double sigma, double min_ampl, int separable, int precision)
 	VipsImage *out = NULL;
 	return vips_gaussmat(&out, sigma, min_ampl, "separable", separable, "precision", precision, NULL) ? NULL : out;
 }
+
+int vips_convsep(VipsImage *in, VipsImage **out, VipsImage *mask, ...);
+/* vips_convsep through the reference's own convsep.c + conv.c + rot.c (C-path convi / convf) */
+void *ref_convsep(void *in, void *mask, int precision)
+{
+	VipsImage *out = NULL;
+	return vips_convsep((VipsImage *) in, &out, (VipsImage *) mask, "precision", precision, NULL) ? NULL : out;
+}

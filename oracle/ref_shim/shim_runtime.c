@@ -245,6 +245,10 @@ int vips_image_pipelinev(VipsImage *image, VipsDemandStyle hint, ...)
 			image->Type = in->Type;
 			image->Xres = in->Xres;
 			image->Yres = in->Yres;
+			/* ... and its metadata: the only items this shim models are a matrix's scale / offset */
+			image->mat_scale = in->mat_scale;
+			image->mat_offset = in->mat_offset;
+			image->mat_meta_set = in->mat_meta_set;
 			first = 0;
 		}
 		if ((int) in->dhint < (int) set_hint)

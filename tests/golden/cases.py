@@ -50,3 +50,16 @@ def resample_cases():
     add(op="thumbnail", dtype="u8", shape=(256, 384, 4), width=48, height=100, size="force")
     add(op="thumbnail", dtype="u8", shape=(300, 300, 1), width=75)
     return cases
+
+
+def seam_cases():
+    """Tiled evaluations for the generate()-shaped / scanline seams (tests/test_seams_gpu.py): the same
+    image pulled through the reference's generate() with explicit sink tiles, so that the rects --
+    and with a non-representable factor such as 1.7 the per-rect coordinate stepping -- are pinned."""
+    out = []
+    for op, shape in (("reducev", (333, 300, 4)), ("reduceh", (150, 420, 4)), ("reducev", (260, 150, 3)),
+                      ("reduceh", (70, 311, 3))):
+        for tname, tile in (("smalltile", (128, 128)), ("fatstrip", (0, 16))):
+            out.append({"op": op, "dtype": "u8", "shape": shape, "f": 1.7, "tile": tile, "seed": 4242 + len(out),
+                        "name": "seam%02d_%s_%s_%dband" % (len(out), op, tname, shape[2])})
+    return out

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, HERE)
 
-from cases import resample_cases, make_input  # noqa: E402
+from cases import resample_cases, seam_cases, make_input  # noqa: E402
 from oracle import pyref  # noqa: E402
 
 
@@ -48,6 +48,17 @@ def main():
     for case in resample_cases():
         out[case["name"]] = run_ref(case)
     path = os.path.join(HERE, "resample_ref.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s: %d cases, %d bytes" % (path, len(out), os.path.getsize(path)))
+
+    # tiled evaluations for the seam tests: the reference's generate() called with explicit sink tiles
+    out = {}
+    for case in seam_cases():
+        r = pyref.RefImage.from_array(make_input(case))
+        r = r.reducev(case["f"]) if case["op"] == "reducev" else r.reduceh(case["f"])
+        tw, th = case["tile"]
+        out[case["name"]] = r.numpy(tile=(tw if tw else r.shape[1], th))
+    path = os.path.join(HERE, "seams_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d cases, %d bytes" % (path, len(out), os.path.getsize(path)))
 

@@ -108,6 +108,46 @@ def test_sharpen_identity_when_m1_m2_zero():
     assert np.abs(back - lab).max() < 0.01
 
 
+def test_convsep_mask_orientation_against_reference():
+    """convsep.c:92-107 through the reference's own convsep.c / rot.c: an n x 1 mask runs the horizontal
+    pass first; a 1 x n mask runs the vertical pass first and then the REVERSED row (vips_rot90), with
+    the offset applied in the first pass only.  Asymmetric masks, integer rounding / clipping per pass."""
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(21)
+    row = np.array([[1.0, 4.0, 9.0, 2.0, -3.0]])
+    for dt in (np.uint8, np.int16, np.float32):
+        a = rnd(rng, dt, (40, 52, 3))
+        for mask in (row, row.T.copy()):
+            for pr in ("float", "integer"):
+                got = pyconv.convsep(a, mask, 13.0, 7.0, pr)
+                want = pyconv.ref_convsep(a, mask, 13.0, 7.0, pr)
+                assert got.dtype == want.dtype and np.array_equal(got, want), (dt, mask.shape, pr)
+    # and the orientation matters for these masks: the two orders differ
+    assert not np.array_equal(pyconv.convsep(a, row, 13.0, 7.0, "integer"), pyconv.convsep(a, row.T.copy(), 13.0, 7.0, "integer"))
+
+
+def test_sharpen_against_reference_sharpen_c():
+    """The reference's own sharpen.c (build: integer gaussmat at min_ampl 0.1, the LUT, L extraction,
+    convsep; generate: sharpen.c:116-168) compiled into oracle/_ref: the oracle must equal it bit for
+    bit -- LUT and pixels, several parameter sets, sRGB and LabS inputs, SMALLTILE and FATSTRIP sinks."""
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    for kw in ({}, {"sigma": 1.5, "m2": 5.0, "y2": 20.0}, {"sigma": 0.8, "x1": 1.0, "m1": 0.5, "y3": 5.0}):
+        lut_kw = {k: v for k, v in kw.items() if k != "sigma"}
+        assert np.array_equal(pyconv.sharpen_lut(**lut_kw), pyconv.ref_sharpen_lut(**kw)), kw
+    rng = np.random.default_rng(22)
+    a = rnd(rng, np.uint8, (150, 170, 3))
+    smooth = np.clip(np.add.outer(np.arange(150), np.arange(170))[:, :, None] * 0.7 + rng.integers(0, 12, (150, 170, 3)), 0, 255).astype(np.uint8)
+    for img in (a, smooth):
+        for kw in ({}, {"sigma": 1.5, "m2": 5.0, "y2": 20.0}, {"sigma": 0.8, "x1": 1.0, "m1": 0.5, "y3": 5.0}):
+            want = pyconv.ref_sharpen(img, "srgb", **kw)
+            assert np.array_equal(pyconv.sharpen(img, "srgb", **kw), want), kw
+            assert np.array_equal(pyconv.ref_sharpen(img, "srgb", tile=(128, 128), **kw), want)  # tile-invariant
+    labs = orc.colourspace(a, "labs", "srgb")
+    assert np.array_equal(pyconv.sharpen(labs, "labs"), pyconv.ref_sharpen(labs, "labs"))
+
+
 # ------------------------------------------------------------------- GPU
 
 @pytest.mark.gpu
@@ -170,3 +210,14 @@ def test_gpu_sharpen(vb):
     assert np.array_equal(vb.Image(a, "srgb").sharpen(m1=0, m2=0).numpy(), a)
     lab = orc.colourspace(a, "lab", "srgb")
     same(vb.Image(lab, "lab").sharpen().numpy(), pyconv.sharpen(lab, "lab"))
+
+
+@pytest.mark.gpu
+def test_gpu_convsep_mask_orientation(vb):
+    rng = np.random.default_rng(23)
+    row = np.array([[1.0, 4.0, 9.0, 2.0, -3.0]])
+    for dt in (np.uint8, np.int16, np.float32):
+        a = rnd(rng, dt, (40, 52, 3))
+        for mask in (row, row.T.copy()):
+            for pr in ("float", "integer"):
+                same(vb.Image(a).convsep(mask, 13.0, 7.0, pr).numpy(), pyconv.convsep(a, mask, 13.0, 7.0, pr))
