@@ -220,6 +220,13 @@ void vb200_mask_free(VB200Mask *mask);
  */
 int vb200_sharpen(const VB200Image *in, VB200Image *out, double sigma, double x1, double y2, double y3, double m1,
 	double m2);
+/* vips_sharpen over a batch of same-shaped packed 8-bit sRGB frames (3 or 4 bands) resident on the
+ * device, as ONE fused kernel (sRGB -> LabS, separable integer blur of L, the sharpen LUT, LabS -> sRGB;
+ * nothing but the input and the output touches HBM): the second stage of the thumbnail + sharpen stream.
+ * Frame i at in + i * in_frame_stride; in and out must not overlap.  Queued on the caller's stream.
+ */
+int vb200_sharpen_batch_device(const void *in, size_t in_frame_stride, void *out, size_t out_frame_stride, int n_frames, int width,
+	int height, int bands, double sigma, double x1, double y2, double y3, double m1, double m2);
 /* 0 (default): uchar INTEGER convolutions use the exact C arithmetic
  * (vips_convi_gen, what a --vips-novector / non-Highway build runs).
  * 1: they use the Highway arithmetic (8-bit mantissa + shared exponent,
@@ -289,6 +296,12 @@ int vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_
  */
 int vb200_thumbnail_batch_host(VB200ThumbnailPlan *plan, const void *in, size_t in_frame_stride, void *out,
 	size_t out_frame_stride, int n_frames);
+/* Append vips_sharpen (convolution/sharpen.c:171-303) to every batch call of the plan: the fused
+ * thumbnail kernel writes into a device scratch batch, vb200_sharpen_batch_device's kernel reads it and
+ * writes the caller's output -- BASELINE config 5's "thumbnail + sharpen + sRGB" stream, two kernels per
+ * batch.  sigma <= 0 switches it off again.  Needs 3- or 4-band frames.
+ */
+int vb200_thumbnail_plan_set_sharpen(VB200ThumbnailPlan *plan, double sigma, double x1, double y2, double y3, double m1, double m2);
 /* 1 if the plan runs the single fused kernel, 0 if it chains the leaf kernels
  * (other band counts, one-axis shrinks, or a window that does not fit on chip).
  */

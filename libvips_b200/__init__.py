@@ -122,6 +122,9 @@ def lib():
         L.vb200_debug_icc_eval.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t,
                                            C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int]
         L.vb200_colour_gen.argtypes = [RP, RP, C.c_int]
+        L.vb200_sharpen_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.c_int] * 4 + [C.c_double] * 6
+        L.vb200_thumbnail_plan_set_sharpen.argtypes = [C.c_void_p] + [C.c_double] * 6
+        L.vb200_device_numa_node.restype = C.c_int
         _lib = L
     return _lib
 
@@ -321,6 +324,11 @@ class ThumbnailPlan:
         self.bytes_per_frame = int(lib().vb200_thumbnail_plan_bytes_per_frame(self._p))
         self.fused = bool(lib().vb200_thumbnail_plan_is_fused(self._p))
         self.kernel = lib().vb200_thumbnail_plan_kernel(self._p).decode()
+
+    def set_sharpen(self, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+        """vips_sharpen appended to every batch of this plan (sigma <= 0: off); BASELINE config 5"""
+        _check(lib().vb200_thumbnail_plan_set_sharpen(self._p, float(sigma), float(x1), float(y2), float(y3), float(m1),
+                                                      float(m2)))
 
     def close(self):
         if self._p:

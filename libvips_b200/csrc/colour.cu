@@ -23,42 +23,11 @@
 #include <math_constants.h>
 
 #include "vb200_internal.h"
+#include "colour_steps.cuh"
 
 namespace vb200 {
 
 namespace {
-
-constexpr int kQuant = 100000; /* QUANT_ELEMENTS, XYZ2Lab.c:66 */
-
-enum Step {
-	S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
-	S_scRGB2RGB16, S_RGB162scRGB
-};
-
-struct ColourTables {
-	const float *v2Y_8;	 /* [256] */
-	const int *Y2v_8;	 /* [257] */
-	const float *v2Y_16; /* [65536] */
-	const int *Y2v_16;	 /* [65537] */
-	const float *cbrt;	 /* [100000] */
-	const float2 *cbrt2; /* [kQuant] (cbrt[i], cbrt[i + 1]) */
-};
-
-struct StepInfo {
-	int step;
-	int out_fmt;   /* format of the step's output image */
-	float alpha_a; /* max_alpha_after / max_alpha_before, as float (vips_linear1 a1) */
-	int rescale;   /* alpha scale changes on this step */
-};
-
-struct RouteParams {
-	int n_steps;
-	StepInfo steps[6];
-	ColourTables t;
-	int w, bands;
-	size_t in_bpl, out_bpl;
-	int in_fmt, out_fmt;
-};
 
 std::mutex g_tables_lock;
 ColourTables g_tables[16];
@@ -88,6 +57,8 @@ host_rgb_tables(int range, std::vector<int> &Y2v, std::vector<float> &v2Y)
 			v2Y[i] = powf((f + 0.055F) / (1 + 0.055F), 2.4F);
 	}
 }
+
+} // namespace
 
 int
 get_tables(const char *domain, ColourTables *out)
@@ -144,175 +115,7 @@ get_tables(const char *domain, ColourTables *out)
 	return 0;
 }
 
-/* ------------------------------------------------------------ device steps */
-
-/* x86 cvttss2si: out-of-range and NaN give INT_MIN (what "(int) nX" does in
- * the reference build); CUDA's cast would saturate instead.
- */
-__device__ __forceinline__ int
-x86_float_to_int(float v)
-{
-	if (!(v > -2147483904.0f && v < 2147483648.0f))
-		return INT_MIN;
-	return (int) v;
-}
-
-/* x / D for a compile-time constant D, correctly rounded, in 3 FP64 instructions instead of the
- * ~25 of __ddiv_rn: q0 = RN(x * RN(1 / D)), the exact remainder by FMA, one corrected
- * rounding (Markstein).  tests/test_div_const.py checks it against the hardware quotient for
- * every float mantissa (and float * 100000 products, and 2 * 10^7 random doubles) per constant
- * used here; zero remainders and infinities return q0 so that signed zeros and Inf survive.
- */
-__device__ __forceinline__ double
-div_const(double x, double d, double r)
-{
-	const double q0 = __dmul_rn(x, r);
-	const double rem = __fma_rn(-q0, d, x);
-	if (rem == 0.0 || !(fabs(q0) < CUDART_INF))
-		return q0;
-	return __fma_rn(rem, r, q0);
-}
-#define DIVC(x, D) div_const((x), (D), 1.0 / (D))
-
-__device__ __forceinline__ float
-cbrt_lookup(const float *__restrict__ table, float nX)
-{
-	int i = x86_float_to_int(nX);
-	i = max(0, min(kQuant - 2, i));
-	const float f = __fsub_rn(nX, (float) i);
-	const float t0 = __ldg(table + i), t1 = __ldg(table + i + 1);
-	return __fadd_rn(t0, __fmul_rn(f, __fsub_rn(t1, t0)));
-}
-
-__device__ __forceinline__ void
-step_scRGB2XYZ(float &a, float &b, float &c)
-{
-	/* p * VIPS_D65_Y0 is a double product rounded to float */
-	const float R = (float) __dmul_rn((double) a, 100.0);
-	const float G = (float) __dmul_rn((double) b, 100.0);
-	const float B = (float) __dmul_rn((double) c, 100.0);
-	a = __fadd_rn(__fadd_rn(__fmul_rn(0.4124F, R), __fmul_rn(0.3576F, G)), __fmul_rn(0.1805F, B));
-	b = __fadd_rn(__fadd_rn(__fmul_rn(0.2126F, R), __fmul_rn(0.7152F, G)), __fmul_rn(0.0722F, B));
-	c = __fadd_rn(__fadd_rn(__fmul_rn(0.0193F, R), __fmul_rn(0.1192F, G)), __fmul_rn(0.9505F, B));
-}
-
-__device__ __forceinline__ void
-step_XYZ2scRGB(float &a, float &b, float &c)
-{
-	const float X = (float) DIVC((double) a, 100.0);
-	const float Y = (float) DIVC((double) b, 100.0);
-	const float Z = (float) DIVC((double) c, 100.0);
-	a = __fadd_rn(__fadd_rn(__fmul_rn(3.240625F, X), __fmul_rn(-1.537208F, Y)), __fmul_rn(-0.498629F, Z));
-	b = __fadd_rn(__fadd_rn(__fmul_rn(-0.968931F, X), __fmul_rn(1.875756F, Y)), __fmul_rn(0.041518F, Z));
-	c = __fadd_rn(__fadd_rn(__fmul_rn(0.055710F, X), __fmul_rn(-0.204021F, Y)), __fmul_rn(1.056996F, Z));
-}
-
-__device__ __forceinline__ void
-step_XYZ2Lab(const float *__restrict__ table, float &a, float &b, float &c)
-{
-	/* nX = QUANT_ELEMENTS * X / X0: float product, double quotient, float store */
-	const float nX = (float) DIVC((double) __fmul_rn(100000.0f, a), 95.0470);
-	const float nY = (float) DIVC((double) __fmul_rn(100000.0f, b), 100.0);
-	const float nZ = (float) DIVC((double) __fmul_rn(100000.0f, c), 108.8827);
-	const float cbx = cbrt_lookup(table, nX);
-	const float cby = cbrt_lookup(table, nY);
-	const float cbz = cbrt_lookup(table, nZ);
-	a = __fsub_rn(__fmul_rn(116.0F, cby), 16.0F);
-	b = __fmul_rn(500.0F, __fsub_rn(cbx, cby));
-	c = __fmul_rn(200.0F, __fsub_rn(cby, cbz));
-}
-
-__device__ __forceinline__ void
-step_Lab2XYZ(float &a, float &b, float &c)
-{
-	const double X0 = 95.0470, Y0 = 100.0, Z0 = 108.8827;
-	const float L = a, A = b, B = c;
-	double cby, tmp;
-	float X, Y, Z;
-
-	if ((double) L < 8.0) {
-		Y = (float) DIVC(__dmul_rn((double) L, Y0), 903.3);
-		cby = __dadd_rn(__dmul_rn(7.787, DIVC((double) Y, Y0)), 16.0 / 116.0);
-	}
-	else {
-		cby = DIVC(__dadd_rn((double) L, 16.0), 116.0);
-		Y = (float) __dmul_rn(__dmul_rn(__dmul_rn(Y0, cby), cby), cby);
-	}
-	tmp = __dadd_rn(DIVC((double) A, 500.0), cby);
-	if (tmp < 0.2069)
-		X = (float) DIVC(__dmul_rn(X0, __dsub_rn(tmp, 0.13793)), 7.787);
-	else
-		X = (float) __dmul_rn(__dmul_rn(__dmul_rn(X0, tmp), tmp), tmp);
-	tmp = __dsub_rn(cby, DIVC((double) B, 200.0));
-	if (tmp < 0.2069)
-		Z = (float) DIVC(__dmul_rn(Z0, __dsub_rn(tmp, 0.13793)), 7.787);
-	else
-		Z = (float) __dmul_rn(__dmul_rn(__dmul_rn(Z0, tmp), tmp), tmp);
-	a = X;
-	b = Y;
-	c = Z;
-}
-
-/* vips_col_scRGB2sRGB for one channel, LabQ2sRGB.c:323-353 */
-__device__ __forceinline__ int
-scRGB2sRGB_channel(const int *lut, int maxval, float R)
-{
-	float Yf = __fmul_rn(R, (float) maxval);
-	if (Yf < 0)
-		Yf = 0;
-	else if (Yf > maxval)
-		Yf = maxval;
-	const int Yi = (int) Yf;
-	const int l0 = lut[Yi], l1 = lut[Yi + 1];
-	const float v = __fadd_rn((float) l0, __fmul_rn((float) (l1 - l0), __fsub_rn(Yf, (float) Yi)));
-	return (int) rintf(v);
-}
-
-__device__ __forceinline__ double
-clipd(double lo, double v, double hi)
-{
-	/* VIPS_CLIP(A, V, B) = MAX(A, MIN(B, V)) with C's ?: on doubles */
-	const double m = hi < v ? hi : v;
-	return lo > m ? lo : m;
-}
-
-__device__ __forceinline__ double
-load_elem(const void *p, int fmt, int idx)
-{
-	switch (fmt) {
-	case VB200_FORMAT_UCHAR: return ((const uint8_t *) p)[idx];
-	case VB200_FORMAT_CHAR: return ((const int8_t *) p)[idx];
-	case VB200_FORMAT_USHORT: return ((const uint16_t *) p)[idx];
-	case VB200_FORMAT_SHORT: return ((const int16_t *) p)[idx];
-	case VB200_FORMAT_UINT: return ((const uint32_t *) p)[idx];
-	case VB200_FORMAT_INT: return ((const int32_t *) p)[idx];
-	default: return ((const float *) p)[idx];
-	}
-}
-
-/* vips_cast of a value (conversion/cast.c:123-265): clip in double, truncate */
-__device__ __forceinline__ double
-cast_value(double v, int fmt)
-{
-	switch (fmt) {
-	case VB200_FORMAT_UCHAR: return (double) (uint8_t) clipd(0, v, 255);
-	case VB200_FORMAT_USHORT: return (double) (uint16_t) clipd(0, v, 65535);
-	case VB200_FORMAT_SHORT: return (double) (int16_t) clipd(-32768, v, 32767);
-	case VB200_FORMAT_FLOAT: return (double) (float) v;
-	default: return v;
-	}
-}
-
-__device__ __forceinline__ void
-store_elem(void *p, int fmt, int idx, double v)
-{
-	switch (fmt) {
-	case VB200_FORMAT_UCHAR: ((uint8_t *) p)[idx] = (uint8_t) v; break;
-	case VB200_FORMAT_USHORT: ((uint16_t *) p)[idx] = (uint16_t) v; break;
-	case VB200_FORMAT_SHORT: ((int16_t *) p)[idx] = (int16_t) v; break;
-	default: ((float *) p)[idx] = (float) v; break;
-	}
-}
+namespace {
 
 __global__ void __launch_bounds__(256)
 colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restrict__ in, void *__restrict__ out)
@@ -420,13 +223,7 @@ colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restric
 
 	/* extra bands: colour.c:252-291 per step */
 	for (int e = 3; e < P.bands; e++) {
-		double v = load_elem(pin, P.in_fmt, base + e);
-		for (int s = 0; s < P.n_steps; s++) {
-			if (P.steps[s].rescale)
-				v = (double) __fadd_rn(__fmul_rn(P.steps[s].alpha_a, (float) v), 0.0f);
-			v = cast_value(v, P.steps[s].out_fmt);
-		}
-		store_elem(pout, P.out_fmt, base + e, v);
+		store_elem(pout, P.out_fmt, base + e, carry_extra_band(load_elem(pin, P.in_fmt, base + e), P.steps, P.n_steps));
 	}
 }
 
@@ -435,16 +232,6 @@ colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restric
  * compiled in (no per-step switch) and the cbrt table is read as aligned (t[i], t[i + 1]) pairs.
  * Same steps, same roundings as colour_route_kernel.
  */
-__device__ __forceinline__ float
-cbrt_lookup2(const float2 *__restrict__ table, float nX)
-{
-	int i = x86_float_to_int(nX);
-	i = max(0, min(kQuant - 2, i));
-	const float f = __fsub_rn(nX, (float) i);
-	const float2 t = __ldg(table + i);
-	return __fadd_rn(t.x, __fmul_rn(f, __fsub_rn(t.y, t.x)));
-}
-
 __global__ void __launch_bounds__(256)
 colour_srgb2lab_x4_kernel(const __grid_constant__ RouteParams P, const uint8_t *__restrict__ in, float *__restrict__ out)
 {
@@ -617,6 +404,33 @@ step_io(int step, int *in_fmt, int *out_fmt, int *out_type)
 } // namespace
 
 int
+colour_route_params(const char *domain, int source_space, int space, RouteParams *P)
+{
+	int steps[8];
+	const int n = build_route(source_space, space, steps);
+	if (n < 0) {
+		error(domain, "no known route from %d to %d on the device path", source_space, space);
+		return -1;
+	}
+	memset(P, 0, sizeof(*P));
+	if (get_tables(domain, &P->t))
+		return -1;
+	P->n_steps = n;
+	int type = source_space;
+	for (int i = 0; i < n; i++) {
+		int ifmt, ofmt, otype;
+		step_io(steps[i], &ifmt, &ofmt, &otype);
+		const double before = interpretation_max_alpha(type), after = interpretation_max_alpha(otype);
+		P->steps[i].step = steps[i];
+		P->steps[i].out_fmt = ofmt;
+		P->steps[i].rescale = before != after;
+		P->steps[i].alpha_a = (float) (after / before);
+		type = otype;
+	}
+	return 0;
+}
+
+int
 dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space, cudaStream_t s)
 {
 	int steps[8];
@@ -651,21 +465,8 @@ dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space
 		return -1;
 	}
 	RouteParams P;
-	memset(&P, 0, sizeof(P));
-	if (get_tables(domain, &P.t))
+	if (colour_route_params(domain, source_space, space, &P))
 		return -1;
-	P.n_steps = n;
-	int type = source_space;
-	for (int i = 0; i < n; i++) {
-		int ifmt, ofmt, otype;
-		step_io(steps[i], &ifmt, &ofmt, &otype);
-		const double before = interpretation_max_alpha(type), after = interpretation_max_alpha(otype);
-		P.steps[i].step = steps[i];
-		P.steps[i].out_fmt = ofmt;
-		P.steps[i].rescale = before != after;
-		P.steps[i].alpha_a = (float) (after / before);
-		type = otype;
-	}
 	P.w = in.w;
 	P.bands = in.bands;
 	P.in_fmt = in.fmt;

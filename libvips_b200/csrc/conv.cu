@@ -758,11 +758,31 @@ dev_gaussblur(const char *domain, const DevImage &in, DevImage *out, double sigm
 	return dev_convsep(domain, in, out, m.data(), w, h, scale, 0.0, precision, s, true);
 }
 
+/* sharpen_fused.cu */
+int dev_sharpen_fused(const char *domain, const void *in, size_t in_bpl, size_t in_frame_stride, void *out, size_t out_bpl,
+	size_t out_frame_stride, int n_frames, int w, int h, int bands, double sigma, double x1, double y2, double y3, double m1,
+	double m2, cudaStream_t s);
+
 /* vips_sharpen, sharpen.c:171-303 */
 int
 dev_sharpen(const char *domain, const DevImage &in, DevImage *out, double sigma, double x1, double y2, double y3,
 	double m1, double m2, cudaStream_t s)
 {
+	/* 8-bit sRGB, 3 or 4 bands: the whole graph as one kernel (sharpen_fused.cu) */
+	if (in.fmt == VB200_FORMAT_UCHAR && in.type == VB200_INTERPRETATION_sRGB && (in.bands == 3 || in.bands == 4)) {
+		DevImage res;
+		if (dev_image_new(domain, &res, in.w, in.h, in.bands, in.fmt, in.type, s))
+			return -1;
+		const int rc = dev_sharpen_fused(domain, in.data, in.bpl, 0, res.data, res.bpl, 0, 1, in.w, in.h, in.bands, sigma, x1, y2,
+			y3, m1, m2, s);
+		if (rc == 0) {
+			*out = res;
+			return 0;
+		}
+		dev_image_release(&res, s);
+		if (rc < 0)
+			return -1;
+	}
 	DevImage labs;
 	if (dev_colourspace(domain, in, &labs, VB200_INTERPRETATION_LABS, in.type, s))
 		return -1;

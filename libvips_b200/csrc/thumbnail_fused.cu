@@ -1404,7 +1404,15 @@ struct ThumbnailPlanImpl {
 	int stage_frames = 0;
 	std::mutex pump_lock;
 	std::mutex launch_lock;
+	/* vips_sharpen appended to every batch (vb200_thumbnail_plan_set_sharpen) */
+	bool sharpen = false;
+	double sh_sigma = 0.5, sh_x1 = 2.0, sh_y2 = 10.0, sh_y3 = 20.0, sh_m1 = 0.0, sh_m2 = 3.0;
 };
+
+/* sharpen_fused.cu */
+int dev_sharpen_fused(const char *domain, const void *in, size_t in_bpl, size_t in_frame_stride, void *out, size_t out_bpl,
+	size_t out_frame_stride, int n_frames, int w, int h, int bands, double sigma, double x1, double y2, double y3, double m1,
+	double m2, cudaStream_t s);
 
 namespace {
 
@@ -2019,8 +2027,37 @@ thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
 	return 0;
 }
 
+static int thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s);
+
 int
 thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s)
+{
+	if (n <= 0)
+		return 0;
+	if (!pl->sharpen)
+		return thumbnail_plan_run_thumbnail(domain, pl, in, in_stride, out, out_stride, n, s);
+	/* thumbnail -> scratch batch (stream-ordered pool) -> sharpen -> out */
+	const size_t frame = (size_t) pl->OW * pl->OH * pl->bands;
+	void *mid = nullptr;
+	if (dev_alloc(domain, &mid, frame * n, s))
+		return -1;
+	int rc = thumbnail_plan_run_thumbnail(domain, pl, in, in_stride, mid, frame, n, s);
+	if (!rc) {
+		rc = dev_sharpen_fused(domain, mid, (size_t) pl->OW * pl->bands, frame, out, (size_t) pl->OW * pl->bands, out_stride, n,
+			pl->OW, pl->OH, pl->bands, pl->sh_sigma, pl->sh_x1, pl->sh_y2, pl->sh_y3, pl->sh_m1, pl->sh_m2, s);
+		if (rc == 1) {
+			error(domain, "sharpen parameters are not on the fused path (mask too wide)");
+			rc = -1;
+		}
+	}
+	dev_free(mid, s);
+	return rc;
+}
+
+static int
+thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, cudaStream_t s)
 {
 	if (n <= 0)
@@ -2169,6 +2206,37 @@ vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan)
 {
 	const ThumbnailPlanImpl &pl = plan->impl;
 	return (size_t) pl.W * pl.H * pl.bands + (size_t) pl.OW * pl.OH * pl.bands;
+}
+
+extern "C" int
+vb200_thumbnail_plan_set_sharpen(VB200ThumbnailPlan *plan, double sigma, double x1, double y2, double y3, double m1, double m2)
+{
+	const char *domain = "thumbnail_plan_set_sharpen";
+	if (!plan) {
+		error(domain, "null plan");
+		return -1;
+	}
+	ThumbnailPlanImpl &pl = plan->impl;
+	if (sigma <= 0) {
+		pl.sharpen = false;
+		return 0;
+	}
+	if ((pl.bands != 3 && pl.bands != 4) || pl.fmt != VB200_FORMAT_UCHAR) {
+		error(domain, "the sharpen stage needs 3- or 4-band 8-bit frames");
+		return -1;
+	}
+	if (sigma < 0.000001 || sigma > 10.0) { /* sharpen.c: the "sigma" argument's range */
+		error(domain, "parameter sigma out of range [0.000001, 10]");
+		return -1;
+	}
+	pl.sh_sigma = sigma;
+	pl.sh_x1 = x1;
+	pl.sh_y2 = y2;
+	pl.sh_y3 = y3;
+	pl.sh_m1 = m1;
+	pl.sh_m2 = m2;
+	pl.sharpen = true;
+	return 0;
 }
 
 extern "C" int
