@@ -29,11 +29,15 @@ BANDS = 4
 TARGET = 512
 MPIX_PER_FRAME = W * H / 1e6
 METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
+METRIC_PIPELINE = "Mpixels/s for thumbnail(4K->512,lanczos3) + sharpen + sRGB (BASELINE config 5 stream)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per 4096x4096 frame, from the
 # committed `ncu --set full` capture (a launch of 148 frames: 10.1220 GB read, 159.4 MB written)
 DRAM_BYTES_PER_FRAME = (10.122020e9 + 159.401728e6) / 148
 DRAM_SOURCE = "profiles/r1q_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
 WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
+WORKLOAD_PIPELINE = ("vips_thumbnail 4K->512 uchar RGBA then vips_sharpen (sRGB->LabS, 3-tap integer blur of L, LUT, LabS->sRGB) on the 512x512 "
+                     "result, synthetic frames, device-resident")
+PIPELINE = False  # set by --workload pipeline: the CPU arm and the GPU arm both append the sharpen stage
 
 
 def peaks():
@@ -96,7 +100,14 @@ class ClockSampler:
 def _ref_worker(i):
     """one frame through the reference's own C sources (oracle/_ref), in a worker process"""
     from oracle import pyref
-    return int(pyref.thumbnail_image(_REF_FRAMES[i], TARGET)[0, 0, 0])
+    t = pyref.thumbnail_image(_REF_FRAMES[i], TARGET)
+    if PIPELINE:
+        # sharpen.c runs under oracle/_ref for 3-band images only (the shim's colourspace stand-in has no alpha
+        # re-attach): the 512x512 RGBA result -- 1.5% of the frame's pixels -- goes through the oracle port, which
+        # tests/test_convolution.py pins bit for bit to the reference's sharpen.c
+        from oracle import pyconv
+        t = pyconv.sharpen(t, "srgb")
+    return int(t[0, 0, 0])
 
 
 _REF_FRAMES = None
@@ -139,10 +150,11 @@ class CpuArm:
             self.out = np.empty((n_frames, TARGET, TARGET, BANDS), np.uint8)
 
     def describe(self):
+        tail = "; then vips_sharpen on the 512x512 result through the oracle port (pinned to the reference's sharpen.c)" if PIPELINE else ""
         if self.kind == "reference":
             return ("the reference's own sources (oracle/_ref: premultiply, shrinkv, reducev, shrinkh, reduceh, unpremultiply; "
-                    "scalar C paths, no Highway) under the shim region engine, one frame per process")
-        return "oracle port of the reference chain (liboracle_fast.so), one frame per thread"
+                    "scalar C paths, no Highway) under the shim region engine, one frame per process" + tail)
+        return "oracle port of the reference chain (liboracle_fast.so), one frame per thread" + tail
 
     def step(self):
         t = time.perf_counter()
@@ -152,6 +164,11 @@ class CpuArm:
             rc = self.L.orc_thumbnail_image_batch(C.c_void_p(self.a.ctypes.data), self.n, W, H, BANDS, TARGET, TARGET,
                                                   0, 1, C.c_void_p(self.out.ctypes.data), TARGET, TARGET, self.threads)
             assert rc == 0
+            if PIPELINE:
+                from concurrent.futures import ThreadPoolExecutor
+                from oracle import pyconv
+                with ThreadPoolExecutor(self.threads) as ex:  # ctypes releases the GIL
+                    list(ex.map(lambda f: pyconv.sharpen(f, "srgb"), self.out))
         return time.perf_counter() - t
 
     def close(self):
@@ -184,6 +201,18 @@ def host_threads():
     return n
 
 
+def numa_cpus(node):
+    """CPUs of a NUMA node (sysfs cpulist), or None"""
+    try:
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus or None
+    except (OSError, ValueError):
+        return None
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -208,10 +237,11 @@ def reference_arm(args):
         also = {"kind": "port", "value": frames * MPIX_PER_FRAME / min(port.step() for _ in range(2)), "unit": "Mpixels/s",
                 "sample": port.describe()}
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_PIPELINE if PIPELINE else METRIC, "value": v, "unit": "Mpixels/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD.replace("device-resident", "host RAM"), "frames_per_step": frames},
+        "config": {"workload": (WORKLOAD_PIPELINE if PIPELINE else WORKLOAD).replace("device-resident", "host RAM"),
+                   "frames_per_step": frames},
         "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": arm.kind,
                          "sample": "%d 4096x4096 RGBA frames per step: %s" % (frames, arm.describe()), "also": also},
         "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -394,16 +424,18 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=1024, help="synthetic frames resident per GPU")
     ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
-    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0: one per host thread, at least 16)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="thumbnail",
-                    help="thumbnail (the headline, default) | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
+                    help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
+                         "--gpus N like the headline) | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
+    global PIPELINE
+    PIPELINE = args.workload == "pipeline"
     if args.impl == "reference":
         return reference_arm(args)
-    if args.workload != "thumbnail":
+    if args.workload not in ("thumbnail", "pipeline"):
         return side_workload(args)
 
     import numpy as np
@@ -442,19 +474,38 @@ def main():
     common = np.random.default_rng(1234).integers(0, 256, (H, W, BANDS), dtype=np.uint8)
     frames[0].copy_(torch.from_numpy(common))
     outs = torch.empty((F, TARGET, TARGET, BANDS), dtype=torch.uint8, device=dev)
+    SHARPEN = (0.5, 2.0, 10.0, 20.0, 0.0, 3.0)  # vips_sharpen's defaults
+    Lc = vb.lib()
+    mid = torch.empty_like(outs) if PIPELINE else None
+    ev_mid = []
 
     def step():
-        plan.run_device(frames.data_ptr(), outs.data_ptr(), F)
+        if PIPELINE:
+            # the two stages of the stream through their public batch entry points, so that an event can sit
+            # between the kernels (a plan with set_sharpen() launches the same two kernels: tests/test_pipeline.py)
+            plan.run_device(frames.data_ptr(), mid.data_ptr(), F)
+            if ev_mid:
+                ev_mid[0].record(stream)
+            vb._check(Lc.vb200_sharpen_batch_device(mid.data_ptr(), plan.out_frame_bytes, outs.data_ptr(), plan.out_frame_bytes, F,
+                                                    TARGET, TARGET, BANDS, *SHARPEN))
+        else:
+            plan.run_device(frames.data_ptr(), outs.data_ptr(), F)
 
-    # correctness gate before timing: frame 0 against the oracle (rank 0), same checksum on all ranks
+    # correctness gate before timing: frame 0 against the oracle (rank 0), same checksum on all ranks.  Always run:
+    # a tuning build (VB200_LIB, tools/build_variant.sh) that computes wrong pixels is reported as such, never as the metric
     step()
     torch.cuda.synchronize()
     csum = outs[0].to(torch.int64).sum()
+    parity = "ok"
     if rank == 0:
         from oracle import pyoracle
         want = pyoracle.thumbnail_image(common, TARGET)
-        if os.environ.get("VB200_LIB") is None:  # a tuning build (tools/build_variant.sh) may compute wrong pixels on purpose
-            assert np.array_equal(outs[0].cpu().numpy(), want), "GPU thumbnail differs from the oracle"
+        if PIPELINE:
+            from oracle import pyconv
+            want = pyconv.sharpen(want, "srgb", *SHARPEN)
+        if not np.array_equal(outs[0].cpu().numpy(), want):
+            parity = "failed"
+            assert os.environ.get("VB200_LIB") is not None, "GPU result differs from the oracle"
     if dist:
         from libvips_b200 import shard
         assert shard.all_agree(dist, csum.reshape(1)), "ranks disagree on the shared frame"
@@ -471,13 +522,16 @@ def main():
     if rank == 0:
         sampler.start()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     launches0 = vb.launch_count()
     barrier()
     evs[0].record(stream)
     for i in range(args.steps):
+        ev_mid[:] = [mids[i]]
         step()
         evs[i + 1].record(stream)
     barrier()
+    ev_mid[:] = []
     launches = vb.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = evs[0].elapsed_time(evs[-1])
@@ -493,14 +547,34 @@ def main():
     peak, peak_src = peaks()
     kern_ms = sum(per_step) / len(per_step)
     bytes_per_launch = plan.bytes_per_frame * F
+    kernels = None
+    if PIPELINE:
+        # dominant kernel = the fused thumbnail (start -> mid event); the sharpen kernel (mid -> end) beside it
+        thumb_ms = sum(evs[i].elapsed_time(mids[i]) for i in range(args.steps)) / args.steps
+        sharp_ms = sum(mids[i].elapsed_time(evs[i + 1]) for i in range(args.steps)) / args.steps
+        sharp_bytes = 2 * plan.out_frame_bytes * F
+        kernels = [{"kernel": plan.kernel, "ms": thumb_ms, "algorithmic_bytes": bytes_per_launch,
+                    "frac": bytes_per_launch / (thumb_ms / 1e3) / 1e9 / peak},
+                   {"kernel": "sharpen_fused_kernel<4>", "ms": sharp_ms, "algorithmic_bytes": sharp_bytes,
+                    "frac": sharp_bytes / (sharp_ms / 1e3) / 1e9 / peak}]
+        kern_ms = thumb_ms
     achieved = bytes_per_launch / (kern_ms / 1e3) / 1e9
 
     # end to end through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H inside the timed region
     e2e = None
     E = args.e2e_frames
     L = vb.lib()
+    # the feeder runs on the GPU's NUMA node, its pinned buffers live there (vb200_host_alloc places them):
+    # on the 8-GPU boxes GPUs 4-7 hang off node 1
+    node = L.vb200_device_numa_node()
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    local_cpus = numa_cpus(node) if node >= 0 else None
+    if affinity0 and local_cpus and (local_cpus & affinity0):
+        os.sched_setaffinity(0, local_cpus & affinity0)
     hin = L.vb200_host_alloc(E * plan.in_frame_bytes)
     hout = L.vb200_host_alloc(E * plan.out_frame_bytes)
+    if PIPELINE:
+        plan.set_sharpen(*SHARPEN)
     if hin and hout:
         src = np.frombuffer((C.c_uint8 * (E * plan.in_frame_bytes)).from_address(hin), dtype=np.uint8)
         one = np.random.default_rng(99 + rank).integers(0, 256, plan.in_frame_bytes, dtype=np.uint8)
@@ -521,7 +595,10 @@ def main():
         e2e = {"value": world * E * n_e2e * MPIX_PER_FRAME / float(te.item()), "unit": "Mpixels/s",
                "h2d_bytes_per_step": E * plan.in_frame_bytes, "d2h_bytes_per_step": E * plan.out_frame_bytes,
                "frames_per_step": E, "steps": n_e2e, "host_memory": "pinned (vb200_host_alloc)",
-               "api": "vb200_thumbnail_batch_host"}
+               "api": "vb200_thumbnail_batch_host" + (" (plan with vb200_thumbnail_plan_set_sharpen)" if PIPELINE else ""),
+               "numa_node": node}
+    if affinity0:
+        os.sched_setaffinity(0, affinity0)  # the CPU baseline below gets every core back
     if hin:
         L.vb200_host_free(hin)
     if hout:
@@ -531,23 +608,25 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         # in a child process: the reference arm forks workers, which a process that holds a CUDA context should not
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                               capture_output=True, text=True, timeout=900)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                                "--workload", args.workload], capture_output=True, text=True, timeout=900)
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
             cpu = {"value": None, "unit": "Mpixels/s", "cores": host_threads(), "kind": "port", "sample": "failed: %r" % (e,)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "metric": ("" if parity == "ok" else "UNVERIFIED (pixels differ from the oracle) ") + (METRIC_PIPELINE if PIPELINE else METRIC),
+            "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu": F, "frame": "4096x4096x4 u8",
+            "parity": parity, "lib": vb.library_path(),
+            "config": {"workload": WORKLOAD_PIPELINE if PIPELINE else WORKLOAD, "frames_per_gpu": F, "frame": "4096x4096x4 u8",
                        "output": "512x512x4 u8", "l2": "inputs (%.1f GiB per GPU) larger than L2" % (F * plan.in_frame_bytes / 2**30),
                        "sharding": "independent frames per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": DRAM_BYTES_PER_FRAME * F, "traffic_source": DRAM_SOURCE, "peak_source": peak_src,
-                         "kernel": plan.kernel, "bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms},
+                         "kernel": plan.kernel, "bytes_per_launch": bytes_per_launch, "kernel_ms": kern_ms, "kernels": kernels},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

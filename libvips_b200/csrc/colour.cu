@@ -121,11 +121,11 @@ __global__ void __launch_bounds__(256)
 colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restrict__ in, void *__restrict__ out)
 {
 	__shared__ float s_v2Y_8[256];
-	__shared__ int s_Y2v_8[257];
+	__shared__ float s_Y2v_8[257]; /* integers <= 255 held as floats: scRGB2sRGB_channel_f */
 	for (int i = threadIdx.x; i < 257; i += blockDim.x) {
 		if (i < 256)
 			s_v2Y_8[i] = P.t.v2Y_8[i];
-		s_Y2v_8[i] = P.t.Y2v_8[i];
+		s_Y2v_8[i] = (float) P.t.Y2v_8[i];
 	}
 	__syncthreads();
 
@@ -181,9 +181,9 @@ colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restric
 			if (isnan(a) || isnan(b) || isnan(c))
 				ia = ib = ic = 0;
 			else {
-				ia = scRGB2sRGB_channel(s_Y2v_8, 255, a);
-				ib = scRGB2sRGB_channel(s_Y2v_8, 255, b);
-				ic = scRGB2sRGB_channel(s_Y2v_8, 255, c);
+				ia = scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, a);
+				ib = scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, b);
+				ic = scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, c);
 			}
 			break;
 		case S_scRGB2RGB16:
@@ -270,9 +270,9 @@ colour_srgb2lab_x4_kernel(const __grid_constant__ RouteParams P, const uint8_t *
 __global__ void __launch_bounds__(256)
 colour_lab2srgb_x4_kernel(const __grid_constant__ RouteParams P, const float *__restrict__ in, uint8_t *__restrict__ out)
 {
-	__shared__ int s_Y2v_8[257];
+	__shared__ float s_Y2v_8[257];
 	for (int i = threadIdx.x; i < 257; i += blockDim.x)
-		s_Y2v_8[i] = P.t.Y2v_8[i];
+		s_Y2v_8[i] = (float) P.t.Y2v_8[i];
 	__syncthreads();
 	const int q = blockIdx.x * blockDim.x + threadIdx.x;
 	if (q * 4 >= P.w)
@@ -290,9 +290,9 @@ colour_lab2srgb_x4_kernel(const __grid_constant__ RouteParams P, const float *__
 		if (isnan(a) || isnan(b) || isnan(c))
 			o[3 * k] = o[3 * k + 1] = o[3 * k + 2] = 0;
 		else {
-			o[3 * k] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, a) & 255u;
-			o[3 * k + 1] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, b) & 255u;
-			o[3 * k + 2] = (uint32_t) scRGB2sRGB_channel(s_Y2v_8, 255, c) & 255u;
+			o[3 * k] = (uint32_t) scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, a) & 255u;
+			o[3 * k + 1] = (uint32_t) scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, b) & 255u;
+			o[3 * k + 2] = (uint32_t) scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, c) & 255u;
 		}
 	}
 	pout[0] = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);

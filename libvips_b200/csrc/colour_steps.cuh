@@ -88,12 +88,30 @@ div_const(double x, double d, double r)
 }
 #define DIVC(x, D) div_const((x), (D), 1.0 / (D))
 
+/* i = clip((int) nX, 0, QUANT_ELEMENTS - 2) and (float) i, XYZ2Lab.c:121-123.  For 0 <= nX < 2^23 the
+ * truncation is an add with round-toward-zero against 2^23 (the integer lands in the significand, and
+ * subtracting 2^23 again is exact): the fma pipe instead of two trips through the conversion unit.
+ */
+__device__ __forceinline__ int
+cbrt_index(float nX, float *fi)
+{
+	if (nX >= 0.0f && nX < 8388608.0f) {
+		const float t = __fadd_rz(nX, 8388608.0f);
+		*fi = fminf(__fsub_rn(t, 8388608.0f), (float) (kQuant - 2));
+		return min(__float_as_int(t) - 0x4B000000, kQuant - 2);
+	}
+	int i = x86_float_to_int(nX);
+	i = max(0, min(kQuant - 2, i));
+	*fi = (float) i;
+	return i;
+}
+
 __device__ __forceinline__ float
 cbrt_lookup(const float *__restrict__ table, float nX)
 {
-	int i = x86_float_to_int(nX);
-	i = max(0, min(kQuant - 2, i));
-	const float f = __fsub_rn(nX, (float) i);
+	float fi;
+	const int i = cbrt_index(nX, &fi);
+	const float f = __fsub_rn(nX, fi);
 	const float t0 = __ldg(table + i), t1 = __ldg(table + i + 1);
 	return __fadd_rn(t0, __fmul_rn(f, __fsub_rn(t1, t0)));
 }
@@ -101,10 +119,13 @@ cbrt_lookup(const float *__restrict__ table, float nX)
 __device__ __forceinline__ void
 step_scRGB2XYZ(float &a, float &b, float &c)
 {
-	/* p * VIPS_D65_Y0 is a double product rounded to float */
-	const float R = (float) __dmul_rn((double) a, 100.0);
-	const float G = (float) __dmul_rn((double) b, 100.0);
-	const float B = (float) __dmul_rn((double) c, 100.0);
+	/* p * VIPS_D65_Y0 is a double product rounded to float.  A 24-bit significand times 100 (7 bits) is
+	 * exact in double, so that is ONE rounding of the exact product -- which is what the float multiply
+	 * does (denormals, overflow and NaN included): no trip through the 64-bit conversion unit.
+	 */
+	const float R = __fmul_rn(a, 100.0F);
+	const float G = __fmul_rn(b, 100.0F);
+	const float B = __fmul_rn(c, 100.0F);
 	a = __fadd_rn(__fadd_rn(__fmul_rn(0.4124F, R), __fmul_rn(0.3576F, G)), __fmul_rn(0.1805F, B));
 	b = __fadd_rn(__fadd_rn(__fmul_rn(0.2126F, R), __fmul_rn(0.7152F, G)), __fmul_rn(0.0722F, B));
 	c = __fadd_rn(__fadd_rn(__fmul_rn(0.0193F, R), __fmul_rn(0.1192F, G)), __fmul_rn(0.9505F, B));
@@ -165,6 +186,27 @@ step_Lab2XYZ(float &a, float &b, float &c)
 	a = X;
 	b = Y;
 	c = Z;
+}
+
+/* vips_col_scRGB2sRGB for one channel (LabQ2sRGB.c:323-353) with the table held as floats (its entries
+ * are integers <= 65535, exact) and the three conversions done on the fma pipe: Yf is in [0, maxval], so
+ * (int) Yf is a round-toward-zero add against 2^23, (float) (l1 - l0) is the exact float difference, and
+ * rintf() of a value in [0, 65535] is the add / subtract of 1.5 * 2^23 in round-to-nearest-even.
+ */
+__device__ __forceinline__ int
+scRGB2sRGB_channel_f(const float *lutf, float maxval, float R)
+{
+	float Yf = __fmul_rn(R, maxval);
+	if (Yf < 0)
+		Yf = 0;
+	else if (Yf > maxval)
+		Yf = maxval;
+	const float t = __fadd_rz(Yf, 8388608.0f);
+	const int Yi = __float_as_int(t) - 0x4B000000;
+	const float fYi = __fsub_rn(t, 8388608.0f);
+	const float l0 = lutf[Yi], l1 = lutf[Yi + 1];
+	const float v = __fadd_rn(l0, __fmul_rn(__fsub_rn(l1, l0), __fsub_rn(Yf, fYi)));
+	return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
 }
 
 /* vips_col_scRGB2sRGB for one channel, LabQ2sRGB.c:323-353 */
@@ -231,9 +273,9 @@ store_elem(void *p, int fmt, int idx, double v)
 __device__ __forceinline__ float
 cbrt_lookup2(const float2 *__restrict__ table, float nX)
 {
-	int i = x86_float_to_int(nX);
-	i = max(0, min(kQuant - 2, i));
-	const float f = __fsub_rn(nX, (float) i);
+	float fi;
+	const int i = cbrt_index(nX, &fi);
+	const float f = __fsub_rn(nX, fi);
 	const float2 t = __ldg(table + i);
 	return __fadd_rn(t.x, __fmul_rn(f, __fsub_rn(t.y, t.x)));
 }

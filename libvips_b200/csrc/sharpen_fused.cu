@@ -50,6 +50,11 @@ struct SharpenParams {
 	int n;				/* taps, odd */
 	int coef[kMaxTaps]; /* rint(mask), vips__image_intize */
 	int scale, rounding;
+	/* magic = ceil(2^shift / scale), shift = 31 + bit length of scale: (n * magic) >> shift == n / scale
+	 * for every 0 <= n < 2^31 (the error term magic * scale - 2^shift is < scale < 2^(shift - 31))
+	 */
+	unsigned long long magic;
+	int shift;
 };
 
 __device__ __forceinline__ int
@@ -58,13 +63,23 @@ clip_short(int v)
 	return max(-32768, min(v, 32767));
 }
 
+/* (sum + rounding) / scale with C's truncation toward zero (convi.c:711), without the integer divide
+ * (a reciprocal on the conversion unit plus fix-up): one 32 x 32 -> 64 multiply by the host's magic number
+ */
+__device__ __forceinline__ int
+div_scale(int n, const SharpenParams &P)
+{
+	const unsigned q = (unsigned) (((unsigned long long) (unsigned) abs(n) * P.magic) >> P.shift);
+	return n < 0 ? -(int) q : (int) q;
+}
+
 /* L of one sRGB pixel in LabS, and optionally a / b: sRGB2scRGB, scRGB2XYZ, XYZ2Lab, Lab2LabS */
 template <bool WANT_AB>
 __device__ __forceinline__ void
 srgb_to_labs(const float *s_v2Y, const float2 *__restrict__ cbrt2, int r8, int g8, int b8, int &L, int &A, int &B)
 {
 	float a = s_v2Y[r8], b = s_v2Y[g8], c = s_v2Y[b8];
-	step_scRGB2XYZ(a, b, c);
+	step_scRGB2XYZ(a, b, c); /* (the halo needs Y only: the compiler drops X and Z there) */
 	const float nY = (float) DIVC((double) __fmul_rn(100000.0f, b), 100.0);
 	const float cby = cbrt_lookup2(cbrt2, nY);
 	const float fL = __fsub_rn(__fmul_rn(116.0F, cby), 16.0F);
@@ -92,13 +107,14 @@ sharpen_fused_kernel(const __grid_constant__ SharpenParams P, const uint8_t *__r
 	short *sH = sL + ((HH * HW + 1) & ~1);				   /* [HH][kTile] after the horizontal pass */
 	short2 *sAB = (short2 *) (sH + HH * kTile);			   /* [kTile][kTile] */
 	float *s_v2Y = (float *) (sAB + kTile * kTile);		   /* [256] */
-	int *s_Y2v = (int *) (s_v2Y + 256);					   /* [257] */
+	float *s_Y2v = s_v2Y + 256;							   /* [257], integers held as floats */
 
 	const int t = threadIdx.x;
+	const int lx = t & 31, ly = t >> 5; /* 32 x 8 threads over the tile: no index divisions */
 	for (int i = t; i < 257; i += 256) {
 		if (i < 256)
 			s_v2Y[i] = P.t.v2Y_8[i];
-		s_Y2v[i] = P.t.Y2v_8[i];
+		s_Y2v[i] = (float) P.t.Y2v_8[i];
 	}
 	__syncthreads();
 
@@ -108,8 +124,9 @@ sharpen_fused_kernel(const __grid_constant__ SharpenParams P, const uint8_t *__r
 	uint8_t *fout = out + (size_t) frame * P.out_frame_stride;
 
 	/* ---- 1: tile + halo to LabS (a / b only inside the tile) */
-	for (int i = t; i < HH * HW; i += 256) {
-		const int hy = i / HW, hx = i - hy * HW;
+	for (int hy = ly; hy < HH; hy += 8)
+	for (int hx = lx; hx < HW; hx += 32) {
+		const int i = hy * HW + hx;
 		const int gy = max(0, min(y0 + hy - r, P.h - 1)), gx = max(0, min(x0 + hx - r, P.w - 1));
 		const uint8_t *p = fin + (size_t) gy * P.in_bpl + (size_t) gx * BANDS;
 		int r8, g8, b8;
@@ -137,26 +154,25 @@ sharpen_fused_kernel(const __grid_constant__ SharpenParams P, const uint8_t *__r
 	__syncthreads();
 
 	/* ---- 2: the n x 1 pass (convi.c:698-717 on shorts: int sum, (sum + scale / 2) / scale truncating, clip) */
-	for (int i = t; i < HH * kTile; i += 256) {
-		const int hy = i / kTile, x = i - hy * kTile;
-		const short *row = sL + hy * HW + x;
+	for (int hy = ly; hy < HH; hy += 8) {
+		const short *row = sL + hy * HW + lx;
 		int sum = 0;
 		for (int k = 0; k < P.n; k++)
 			sum += P.coef[k] * (int) row[k];
-		sH[i] = (short) clip_short((sum + P.rounding) / P.scale);
+		sH[hy * kTile + lx] = (short) clip_short(div_scale(sum + P.rounding, P));
 	}
 	__syncthreads();
 
 	/* ---- 3: the 1 x n pass, the LUT, and back to sRGB */
-	for (int i = t; i < kTile * kTile; i += 256) {
-		const int ty = i / kTile, tx = i - ty * kTile;
+	for (int ty = ly; ty < kTile; ty += 8) {
+		const int tx = lx, i = ty * kTile + lx;
 		const int gx = x0 + tx, gy = y0 + ty;
 		if (gx >= P.w || gy >= P.h)
 			continue;
 		int sum = 0;
 		for (int k = 0; k < P.n; k++)
 			sum += P.coef[k] * (int) sH[(ty + k) * kTile + tx];
-		const int v2 = clip_short((sum + P.rounding) / P.scale);
+		const int v2 = clip_short(div_scale(sum + P.rounding, P));
 		const int v1 = sL[(ty + r) * HW + tx + r];
 		/* sharpen.c:139-160 */
 		const int diff = (v1 & 0x7fff) - (v2 & 0x7fff);
@@ -171,9 +187,9 @@ sharpen_fused_kernel(const __grid_constant__ SharpenParams P, const uint8_t *__r
 		step_XYZ2scRGB(a, b, c);
 		unsigned R = 0, G = 0, Bb = 0;
 		if (!(isnan(a) || isnan(b) || isnan(c))) {
-			R = (unsigned) scRGB2sRGB_channel(s_Y2v, 255, a) & 255u;
-			G = (unsigned) scRGB2sRGB_channel(s_Y2v, 255, b) & 255u;
-			Bb = (unsigned) scRGB2sRGB_channel(s_Y2v, 255, c) & 255u;
+			R = (unsigned) scRGB2sRGB_channel_f(s_Y2v, 255.0f, a) & 255u;
+			G = (unsigned) scRGB2sRGB_channel_f(s_Y2v, 255.0f, b) & 255u;
+			Bb = (unsigned) scRGB2sRGB_channel_f(s_Y2v, 255.0f, c) & 255u;
 		}
 		uint8_t *q = fout + (size_t) gy * P.out_bpl + (size_t) gx * BANDS;
 		if (BANDS == 4) {
@@ -287,6 +303,13 @@ dev_sharpen_fused(const char *domain, const void *in, size_t in_bpl, size_t in_f
 	}
 	P.scale = (int) rint(scale); /* convi.c:760-763 */
 	P.rounding = P.scale / 2;
+	if (P.scale <= 0)
+		return 1; /* a negative scale: leave it to the general path */
+	int bits = 0;
+	while ((P.scale >> bits) != 0)
+		bits++;
+	P.shift = 31 + bits;
+	P.magic = (unsigned long long) ((((unsigned __int128) 1 << P.shift) + P.scale - 1) / P.scale);
 	if (P.scale == 0 || abs_sum * 32768 >= (1L << 31))
 		return 1; /* the reference divides by it / sums in int64: keep the general path */
 
