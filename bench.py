@@ -295,7 +295,7 @@ def side_workload(args):
         ach = alg_bytes / (ms / 1e3) / 1e9
         print(json.dumps({"metric": label, "value": units / (ms / 1e3), "unit": unit_name, "n_gpus": 1,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                          "dtype": "f32/f64 accumulate" if "conv" in label or "colour" in label else "u8",
+                          "dtype": "f32/f64 accumulate" if "conv" in label or "colour" in label or "linear" in label else "u8",
                           "data": "synthetic", "config": {"workload": label, "device_resident": True},
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                                        "frac": ach / peak, "traffic": None, "peak_source": peak_src,
@@ -383,6 +383,29 @@ def side_workload(args):
         ca = np.random.default_rng(1234).integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
         cpu = cpu_side(lambda: pyconv.sharpen(ca, "srgb"), 1024 * 1024 / 1e6, "1024x1024 RGB")
         run(fn, 2 * a.numel(), "vips_sharpen defaults on 4096x4096 sRGB uchar", n * n / 1e6, "Mpixels/s", cpu)
+    elif args.workload == "thumbnail_linear":
+        # north_star's "fused Lanczos3-reduce -> sRGB -> linear" path: vips_thumbnail_image(linear=TRUE), SURVEY 3.1b
+        F = max(1, min(args.frames, 128))
+        plan = vb.ThumbnailPlan(W, H, BANDS, TARGET, linear=True)
+        assert plan.fused, "the two-kernel linear path must be the one under measurement"
+        g = torch.Generator(device=dev)
+        g.manual_seed(4321)
+        frames = torch.randint(0, 256, (F, H, W, BANDS), dtype=torch.uint8, device=dev, generator=g)
+        common = np.random.default_rng(1234).integers(0, 256, (H, W, BANDS), dtype=np.uint8)
+        frames[0].copy_(torch.from_numpy(common))
+        outs = torch.empty((F, TARGET, TARGET, BANDS), dtype=torch.uint8, device=dev)
+
+        def fn():
+            plan.run_device(frames.data_ptr(), outs.data_ptr(), F)
+        fn()
+        torch.cuda.synchronize()
+        from oracle import pyoracle
+        want = pyoracle.thumbnail_image(common, TARGET, linear=True)
+        assert np.array_equal(outs[0].cpu().numpy(), want), "GPU linear thumbnail differs from the oracle"
+        ca = np.random.default_rng(7).integers(0, 256, (H, W, BANDS), dtype=np.uint8)
+        cpu = cpu_side(lambda: pyoracle.thumbnail_image(ca, TARGET, linear=True), W * H / 1e6, "one 4096x4096 RGBA frame")
+        run(fn, plan.bytes_per_frame * F, "vips_thumbnail_image(linear=TRUE) 4K->512 uchar RGBA, %d frames (%s)" % (F, plan.kernel),
+            F * W * H / 1e6, "Mpixels/s", cpu)
     elif args.workload == "icc":
         # vips_icc_import then vips_icc_export through an sRGB-like v4 matrix/TRC profile
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -427,7 +450,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
-                         "--gpus N like the headline) | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
+                         "--gpus N like the headline) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 

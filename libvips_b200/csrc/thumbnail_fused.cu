@@ -430,6 +430,30 @@ mbar_wait(unsigned bar, unsigned parity)
 	} while (!done);
 }
 
+/* The same wait for a warp that will wait LONG (the H warps on a chunk of reducev output, the producer on a
+ * stage's release).  try_wait parks the warp on NANOSLEEP.SYNCS, which the hardware ends at EVERY mbarrier
+ * event of the CTA -- the r1q capture has the three H warps re-checking 222 times per wait (one TMA
+ * transaction or V-warp arrival at a time), 6% of all issued instructions, on the sub-partitions whose
+ * issue slots bound the kernel.  Here the warp polls test_wait on a plain timer instead: a handful of
+ * instructions per wait, at the price of up to `ns` of latency the double-buffered hand-offs absorb.
+ */
+__device__ __forceinline__ void
+mbar_wait_poll(unsigned bar, unsigned parity, unsigned ns)
+{
+	for (;;) {
+		unsigned done;
+		asm volatile("{\n\t.reg .pred p;\n\t"
+					 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+					 "selp.u32 %0, 1, 0, p;\n\t}"
+					 : "=r"(done)
+					 : "r"(bar), "r"(parity)
+					 : "memory");
+		if (done)
+			return;
+		asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+	}
+}
+
 __device__ __forceinline__ void
 mbar_arrive(unsigned bar)
 {
@@ -1368,6 +1392,14 @@ struct PairSets {
 
 /* ------------------------------------------------------------------ plan */
 
+/* thumbnail_linear.cu */
+struct LinearThumb;
+int linear_thumb_new(const char *domain, int W, int H, int bands, bool premul, const ReduceGeom &gv, const ReduceGeom &gh,
+	const AxisTable &tv, const AxisTable &th, LinearThumb **out);
+int linear_thumb_run(const char *domain, LinearThumb *lt, const void *in, size_t in_stride, void *out, size_t out_stride, int n,
+	cudaStream_t s);
+void linear_thumb_free(LinearThumb *lt);
+
 struct ThumbnailPlanImpl {
 	/* request */
 	int W = 0, H = 0, bands = 0, fmt = 0, has_alpha = 0;
@@ -1404,6 +1436,8 @@ struct ThumbnailPlanImpl {
 	int stage_frames = 0;
 	std::mutex pump_lock;
 	std::mutex launch_lock;
+	/* linear = TRUE: the two-kernel linear-light path (thumbnail_linear.cu), or null = the leaf chain */
+	LinearThumb *lin = nullptr;
 	/* vips_sharpen appended to every batch (vb200_thumbnail_plan_set_sharpen) */
 	bool sharpen = false;
 	double sh_sigma = 0.5, sh_x1 = 2.0, sh_y2 = 10.0, sh_y3 = 20.0, sh_m1 = 0.0, sh_m2 = 3.0;
@@ -1698,8 +1732,12 @@ launch_tma(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t is,
 					  : launch_tma_vs<0, false>(domain, pl, fp, in, is, out, os, n, grid, s);
 }
 
-int
-plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
+/* The per-row / per-column sampling tables of the plan's vips_resize, stepped per rect exactly as the
+ * reference's sink would call reducev / reduceh (demand hints: shrinkv forces SMALLTILE, shrinkh chunks
+ * into fatstrip-height strips; see dev_reduce_chain).
+ */
+void
+plan_axis_tables(const ThumbnailPlanImpl *pl, AxisTable &tv, AxisTable &th)
 {
 	const TileGeometry tg = tile_geometry();
 	int tile_w, tile_h;
@@ -1714,10 +1752,15 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	int rect_h = tile_h;
 	if (pl->gh.int_shrink > 1)
 		rect_h = std::min(rect_h, tg.fatstrip_height);
-
-	AxisTable tv, th;
 	build_axis_table(tv, pl->OH, pl->gv.residual, pl->gv.offset, pl->gv.n_point, VB200_KERNEL_LANCZOS3, rect_h);
 	build_axis_table(th, pl->OW, pl->gh.residual, pl->gh.offset, pl->gh.n_point, VB200_KERNEL_LANCZOS3, tile_w);
+}
+
+int
+plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
+{
+	AxisTable tv, th;
+	plan_axis_tables(pl, tv, th);
 
 	/* Pair grid: pair p covers embedded positions (2p + grid, 2p + grid + 1).  Pick
 	 * the grid phase (0 / 1) that needs fewer coefficient pairs once all-zero
@@ -1980,11 +2023,12 @@ thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
 		error(domain, "only uchar frames are on the batched device path");
 		return -1;
 	}
-	if (pl->linear) {
-		error(domain, "linear thumbnails run through vb200_thumbnail_image()");
+	thumbnail_shrink(pl->W, pl->H, pl->target_w, pl->target_h, pl->size, &pl->hshrink, &pl->vshrink);
+	if (pl->linear && (pl->bands < 3 || pl->hshrink < 1.0 || pl->vshrink < 1.0)) {
+		error(domain, pl->bands < 3 ? "linear thumbnails on the device path need an 8-bit image with 3+ bands"
+									: "upsizing is not on the device path yet");
 		return -1;
 	}
-	thumbnail_shrink(pl->W, pl->H, pl->target_w, pl->target_h, pl->size, &pl->hshrink, &pl->vshrink);
 	if (pl->hshrink < 1.0 || pl->vshrink < 1.0) {
 		/* enlarging thumbnail: premultiply / vips_resize (affine) / unpremultiply, unfused */
 		const double hscale = std::max(1.0 / pl->hshrink, 1.0 / pl->W);
@@ -2018,6 +2062,17 @@ thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
 	pl->premul = pl->has_alpha && pl->hshrink != 1.0 && pl->vshrink != 1.0;
 
 	pl->fused = false;
+	if (pl->linear) {
+		/* thumbnail.c:766-806: sRGB -> scRGB first; the float chain as two kernels where the geometry allows */
+		AxisTable tv, th;
+		if (pl->gv.n_point > 0 && pl->gh.n_point > 0) {
+			plan_axis_tables(pl, tv, th);
+			if (linear_thumb_new(domain, pl->W, pl->H, pl->bands, pl->premul, pl->gv, pl->gh, tv, th, &pl->lin) < 0)
+				return -1;
+		}
+		pl->fused = pl->lin != nullptr;
+		return 0;
+	}
 	if (pl->bands == 4 && pl->gv.n_point > 0 && pl->gh.n_point > 0) {
 		int r = plan_build_fused(domain, pl);
 		if (r < 0)
@@ -2056,12 +2111,63 @@ thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void 
 	return rc;
 }
 
+/* thumbnail.c:766-806, 848-902, 971-987 for an 8-bit sRGB image without ICC profile, as the chain of leaf
+ * kernels (geometries the two-kernel path declines): sRGB -> scRGB (float; alpha / 255), float premultiply
+ * (max_alpha 1.0), float resize, float unpremultiply, scRGB -> sRGB.
+ */
+static int
+thumbnail_linear_chain(const char *domain, ThumbnailPlanImpl *pl, const void *in, void *out, cudaStream_t s)
+{
+	DevImage din, lin, pre, res, unpre, fin;
+	din.w = pl->W;
+	din.h = pl->H;
+	din.bands = pl->bands;
+	din.fmt = VB200_FORMAT_UCHAR;
+	din.type = VB200_INTERPRETATION_sRGB;
+	din.bpl = (size_t) pl->W * pl->bands;
+	din.data = const_cast<void *>(in);
+	int rc = dev_colourspace(domain, din, &lin, VB200_INTERPRETATION_scRGB, VB200_INTERPRETATION_sRGB, s);
+	const DevImage *cur = &lin;
+	if (!rc && pl->premul) {
+		rc = dev_premultiply(domain, lin, &pre, 0.0, 0, s); /* max_alpha from scRGB: 1.0 */
+		cur = &pre;
+	}
+	if (!rc)
+		rc = dev_resize(domain, *cur, &res, 1.0 / pl->hshrink, 1.0 / pl->vshrink, VB200_KERNEL_LANCZOS3, 2.0, s);
+	cur = &res;
+	if (!rc && pl->premul) {
+		rc = dev_unpremultiply(domain, res, &unpre, 0.0, 0, s);
+		cur = &unpre;
+	}
+	if (!rc)
+		rc = dev_colourspace(domain, *cur, &fin, VB200_INTERPRETATION_sRGB, VB200_INTERPRETATION_scRGB, s);
+	if (!rc) {
+		const size_t line = (size_t) fin.w * fin.bands;
+		if (cudaMemcpy2DAsync(out, line, fin.data, fin.bpl, line, fin.h, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+			rc = cuda_fail(domain, cudaGetLastError(), "linear thumbnail copy");
+	}
+	dev_image_release(&lin, s);
+	dev_image_release(&pre, s);
+	dev_image_release(&res, s);
+	dev_image_release(&unpre, s);
+	dev_image_release(&fin, s);
+	return rc;
+}
+
 static int
 thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, cudaStream_t s)
 {
 	if (n <= 0)
 		return 0;
+	if (pl->linear) {
+		if (pl->lin)
+			return linear_thumb_run(domain, pl->lin, in, in_stride, out, out_stride, n, s);
+		for (int i = 0; i < n; i++)
+			if (thumbnail_linear_chain(domain, pl, (const char *) in + (size_t) i * in_stride, (char *) out + (size_t) i * out_stride, s))
+				return -1;
+		return 0;
+	}
 	if (pl->fused) {
 		/* the TMA-fed kernel when rows, frames and the base pointer are 16-byte aligned */
 		if ((pl->tma_ok || pl->mma_ok) && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0)) {
@@ -2128,6 +2234,9 @@ thumbnail_plan_destroy(ThumbnailPlanImpl *pl)
 		cudaFree(pl->tables);
 	if (pl->tables_mma)
 		cudaFree(pl->tables_mma);
+	if (pl->lin)
+		linear_thumb_free(pl->lin);
+	pl->lin = nullptr;
 	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
 		if (pl->stage_in[i])
 			cudaFree(pl->stage_in[i]);
@@ -2252,6 +2361,8 @@ vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan)
 	if (!plan || !plan->impl.fused)
 		return "leaf kernels";
 	const ThumbnailPlanImpl &pl = plan->impl;
+	if (pl.linear)
+		return "linear_v_kernel + linear_h_kernel";
 	const FusedParams &fp = pl.fp;
 	const int nph = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
 	const bool v4 = pl.mma_ok && (fp.VS == 2 || fp.VS == 4 || fp.VS == 8);
@@ -2363,56 +2474,14 @@ vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int heig
 	}
 	if (ensure_init(domain))
 		return -1;
-	if (linear) {
-		/* thumbnail.c:766-806, 848-902, 971-987 for an 8-bit sRGB image without ICC profile:
-		 * sRGB -> scRGB (float; alpha / 255), float premultiply (max_alpha 1.0), float
-		 * resize, float unpremultiply, scRGB -> sRGB.  Unfused chain of leaf kernels.
-		 */
-		if (in->BandFmt != VB200_FORMAT_UCHAR || in->Bands < 3) {
-			error(domain, "linear thumbnails on the device path need an 8-bit image with 3+ bands");
-			return -1;
-		}
-		const int th = height > 0 ? height : width;
-		double hs, vs;
-		thumbnail_shrink(in->Xsize, in->Ysize, width, th, size, &hs, &vs);
-		if (hs < 1.0 || vs < 1.0) {
-			error(domain, "upsizing is not on the device path yet");
-			return -1;
-		}
-		cudaStream_t s = current_stream();
-		DevImage din, lin, pre, res, unpre, fin;
-		if (to_device(domain, in, &din, s))
-			return -1;
-		const bool premul = image_hasalpha(in->Type, in->Bands) && hs != 1.0 && vs != 1.0;
-		int rc = dev_colourspace(domain, din, &lin, VB200_INTERPRETATION_scRGB, VB200_INTERPRETATION_sRGB, s);
-		const DevImage *cur = &lin;
-		if (!rc && premul) {
-			rc = dev_premultiply(domain, lin, &pre, 0.0, 0, s); /* max_alpha from scRGB: 1.0 */
-			cur = &pre;
-		}
-		if (!rc)
-			rc = dev_resize(domain, *cur, &res, 1.0 / hs, 1.0 / vs, VB200_KERNEL_LANCZOS3, 2.0, s);
-		cur = &res;
-		if (!rc && premul) {
-			rc = dev_unpremultiply(domain, res, &unpre, 0.0, 0, s);
-			cur = &unpre;
-		}
-		if (!rc)
-			rc = dev_colourspace(domain, *cur, &fin, VB200_INTERPRETATION_sRGB, VB200_INTERPRETATION_scRGB, s);
-		if (!rc)
-			rc = deliver(domain, &fin, in, out, s);
-		dev_image_release(&din, s);
-		dev_image_release(&lin, s);
-		dev_image_release(&pre, s);
-		dev_image_release(&res, s);
-		dev_image_release(&unpre, s);
-		dev_image_release(&fin, s);
-		return rc;
+	if (linear && (in->BandFmt != VB200_FORMAT_UCHAR || in->Bands < 3)) {
+		error(domain, "linear thumbnails on the device path need an 8-bit image with 3+ bands");
+		return -1;
 	}
 	/* vips_image_hasalpha(): more bands than the interpretation implies (iofuncs/image.c:3113-3119) */
 	const int has_alpha = image_hasalpha(in->Type, in->Bands);
 	VB200ThumbnailPlan *plan = vb200_thumbnail_plan_new(in->Xsize, in->Ysize, in->Bands, in->BandFmt, has_alpha, width,
-		height, size, 0);
+		height, size, linear);
 	if (!plan)
 		return -1;
 	cudaStream_t s = current_stream();

@@ -49,6 +49,19 @@ constexpr int kV4Quads = 8; /* quad ring: K / 4 */
 #ifndef VB200_V4_MMA_UNROLL
 #define VB200_V4_MMA_UNROLL 2
 #endif
+/* long waits poll on a timer instead of parking on the barrier unit (mbar_wait_poll): 0 = try_wait */
+#ifndef VB200_V4_HPOLL_NS
+#define VB200_V4_HPOLL_NS 0 /* the H warps' wait for a chunk of reducev output */
+#endif
+#ifndef VB200_V4_PPOLL_NS
+#define VB200_V4_PPOLL_NS 0 /* the producer's wait for a stage to be released */
+#endif
+#ifndef VB200_V4_VPOLL_NS
+#define VB200_V4_VPOLL_NS 0 /* the V warps' wait for a TMA stage (latency-critical) */
+#endif
+#ifndef VB200_V4_EPOLL_NS
+#define VB200_V4_EPOLL_NS 0 /* the V warps' wait for the H warps to release an sh buffer */
+#endif
 
 /* timing experiment only: VB200_EXP_NOPREMUL drops the premultiply arithmetic (wrong pixels) */
 #ifndef VB200_V4_HADD2
@@ -210,7 +223,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		for (int ya = y_begin, cc = chunk0; ya < y_end; ya += K, cc++) {
 			const int P1 = 2 * __ldg(&P.vchunk[cc]).y + 1; /* last pair of the chunk's last quad */
 			for (int p = pdone; p <= P1; p++) {
-				mbar_wait(empty_s + 8u * s, phase ^ 1u);
+				if (VB200_V4_PPOLL_NS)
+					mbar_wait_poll(empty_s + 8u * s, phase ^ 1u, VB200_V4_PPOLL_NS);
+				else
+					mbar_wait(empty_s + 8u * s, phase ^ 1u);
 				/* interior stage: its 2 VS input rows are consecutive and none is an edge replica --
 				 * one tiled-TMA box {PITCH bytes, 2 VS rows} instead of 2 VS row copies
 				 */
@@ -264,7 +280,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 			const int rows = yb - ya;
 			const int buf = chunk & 1;
 			const uint2 *shb = sh + (size_t) buf * KM * shs;
-			mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
+			if (VB200_V4_HPOLL_NS)
+				mbar_wait_poll(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u, VB200_V4_HPOLL_NS);
+			else
+				mbar_wait(shfull_s + 8u * buf, (unsigned) (chunk >> 1) & 1u);
 			for (int idx = ht; idx < rows * bw; idx += 32 * NH) {
 				const int k = fast_div(idx, bw);
 				const int x = xa + (idx - k * bw);
@@ -354,7 +373,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 #pragma unroll
 			for (int half = 0; half < 2; half++) {
 				const unsigned soff = (unsigned) s * stage_bytes;
-				mbar_wait(full_s + 8u * s, phase);
+				if (VB200_V4_VPOLL_NS)
+					mbar_wait_poll(full_s + 8u * s, phase, VB200_V4_VPOLL_NS);
+				else
+					mbar_wait(full_s + 8u * s, phase);
 				if (CPT == 2) {
 					uint2 pa[VS], pb[VS];
 #pragma unroll
@@ -423,7 +445,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		/* reducev on the tensor pipe + in-thread shrinkh; rows go to sh[buf] once the H warp has released it */
 		const int buf = chunk & 1;
 		const uint4 bf = __ldg(&P.vbfrag[(size_t) (chunk0 + chunk) * 32 + lane]); /* {hi b0, hi b1, lo b0, lo b1} */
-		mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
+		if (VB200_V4_EPOLL_NS)
+			mbar_wait_poll(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u, VB200_V4_EPOLL_NS);
+		else
+			mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
 		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * KM * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
 #pragma unroll kMmaUnroll
 		for (int tp = 0; tp < 4 * CPT; tp++) {

@@ -228,3 +228,68 @@ def test_gpu_matches_host_evaluation(vb):
     got = vb.Image(g, "b-w").icc_transform(rgb, grey, depth=16).numpy()
     want = host_eval(2, g.reshape(-1, 1), grey, rgb, depth=16).reshape(16, 40, 3)
     assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
+
+
+@pytest.mark.gpu
+def test_gpu_against_lcms2_fixtures(vb):
+    """the CUDA kernel against lcms2's OWN outputs (tests/golden/icc_lcms.npz, made by make_icc_golden.py through
+    oracle/pylcms.py), at the tolerances the CPU tests state for the host compile of the same evaluator -- so a
+    logic error the kernel and its host twin share cannot hide behind test_gpu_matches_host_evaluation"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_icc_golden import inputs
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icc_lcms.npz"))
+    I = inputs()
+    rgb, gamma, table, grey, ink = F.rgb_profile("srgb"), F.rgb_profile("gamma"), F.rgb_profile("table"), F.grey_profile(), F.ink_profile()
+    v4 = F.lut_v4_rgb_profile("Lab ")
+
+    def img(a, interp):
+        return vb.Image(a.reshape(1, a.shape[0], a.shape[1]), interp)
+
+    def flat(im):
+        return im.numpy().reshape(-1, im.numpy().shape[-1])
+
+    # import, 8-bit and float device values, Lab and XYZ PCS
+    got = flat(img(I["rgb8"], "srgb").icc_import(rgb))
+    assert de(got, G["import_rgb8_lab"]).max() < 0.8 and de(got, G["import_rgb8_lab"]).mean() < 0.05
+    assert np.abs(flat(img(I["rgbf"], "srgb").icc_import(rgb)) - G["import_rgbf_lab"]).max() < 0.03
+    assert np.abs(flat(img(I["rgb8"], "srgb").icc_import(rgb, pcs="xyz")) - G["import_rgb8_xyz"]).max() < 0.08
+    assert de(flat(img(I["rgb8"], "srgb").icc_import(table)), G["import_table8_lab"]).max() < 1.6
+    # export from lcms2's own Lab
+    lab = img(G["import_rgb8_lab"], "lab")
+    d = np.abs(flat(lab.icc_export(rgb)).astype(int) - G["export_lab_rgb8"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.004
+    d = np.abs(flat(lab.icc_export(rgb, depth=16)).astype(int) - G["export_lab_rgb16"].astype(int))
+    assert d.max() <= 128 and d.mean() < 2
+    d = np.abs(flat(lab.icc_export(gamma)).astype(int) - G["export_lab_gamma8"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.004
+    # device to device
+    d = np.abs(flat(img(I["rgb8"], "srgb").icc_transform(gamma, rgb)).astype(int) - G["transform_rgb8_gamma8"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.03
+    d = np.abs(flat(img(I["rgb16"], "rgb16").icc_transform(gamma, rgb, depth=16)).astype(int) - G["transform_rgb16_gamma16"].astype(int))
+    assert d.max() <= 256 and d.mean() < 6
+    # grey, CMYK (lut16), v4 lutAtoB / lutBtoA
+    assert de(flat(img(I["grey8"], "b-w").icc_import(grey)), G["import_grey8_lab"]).max() < 0.3
+    assert np.array_equal(flat(img(G["import_grey8_lab"], "lab").icc_export(grey)), G["export_lab_grey8"])
+    assert de(flat(img(I["cmyk8"], "cmyk").icc_import(ink)), G["import_cmyk8_lab"]).max() < 1.5
+    d = np.abs(flat(lab.icc_export(ink)).astype(int) - G["export_lab_cmyk8"].astype(int))
+    assert d.max() <= 2 and d.mean() < 0.05
+    assert de(flat(img(I["rgb8"], "srgb").icc_import(v4)), G["import_v4_rgb8_lab"]).max() < 1.6
+    d = np.abs(flat(lab.icc_export(v4)).astype(int) - G["export_lab_v4_rgb8"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+
+
+@needs_lcms
+def test_lcms2_fixtures_are_current():
+    """CPU: the stored fixtures are what lcms2 gives today for the same inputs (regenerate with make_icc_golden.py)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_icc_golden import inputs
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "icc_lcms.npz"))
+    I = inputs()
+    assert np.array_equal(pylcms.icc_import(I["rgb8"], F.rgb_profile("srgb")), G["import_rgb8_lab"])
+    assert np.array_equal(pylcms.icc_export(G["import_rgb8_lab"], F.ink_profile()), G["export_lab_cmyk8"])
+    # and the host twin of the kernel meets the same bars against them
+    assert de(host_eval(0, I["rgb8"], F.rgb_profile("srgb")), G["import_rgb8_lab"]).max() < 0.8
+    d = np.abs(host_eval(1, G["import_rgb8_lab"], F.rgb_profile("srgb")).astype(int) - G["export_lab_rgb8"].astype(int))
+    assert d.max() <= 1

@@ -1,7 +1,8 @@
-bash tools/gpu_side_profiles.sh r2b "sharpen"
-python bench.py --workload pipeline --steps 10 --warmup 3 --frames 512 > gpurun_out/r2b_pipeline.json 2> gpurun_out/r2b_pipeline.err; echo "pipeline rc=$?"; cut -c1-1500 gpurun_out/r2b_pipeline.json; tail -5 gpurun_out/r2b_pipeline.err
-python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench rc=$?"; cut -c1-1200 gpurun_out/r2b_bench.json; tail -5 gpurun_out/r2b_bench.err
-timeout 600 ncu --set full --clock-control none -k "regex:sharpen" -c 1 -f -o /tmp/r2b_pipe python bench.py --workload pipeline --steps 1 --warmup 0 --no-cpu --frames 148 > gpurun_out/r2b_ncu_pipe.log 2>&1
-ncu -i /tmp/r2b_pipe.ncu-rep --page raw --csv > gpurun_out/r2b_pipe_sharpen.raw.csv
-cp /tmp/r2b_pipe.ncu-rep gpurun_out/r2b_pipe_sharpen.ncu-rep
+bash tools/gpu_side_profiles.sh r2d "sharpen thumbnail_linear"
+for v in base h500 h1000p200 h500p100 h500p100v32 h500p100e200 h2000p400; do
+  if [ $v = base ]; then unset VB200_LIB; else export VB200_LIB=$PWD/libvips_b200/variants/libvb200_$v.so; fi
+  python bench.py --steps 10 --warmup 3 --no-cpu --frames 592 > gpurun_out/r2d_var_$v.json 2> gpurun_out/r2d_var_$v.err
+  echo "$v rc=$? $(python -c "import json;d=json.load(open('gpurun_out/r2d_var_$v.json'));print(d['ms_per_step'], d['roofline']['frac'], d['parity'], d['e2e']['value'])")"
+done
+unset VB200_LIB
 du -sh gpurun_out

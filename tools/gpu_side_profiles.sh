@@ -13,7 +13,7 @@ tail -15 $out/${tag}_pytest.log
 for w in $workloads; do
 	timeout 300 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $out/${tag}_side_$w.json 2> $out/${tag}_side_$w.err
 	echo "$w bench rc=$?"; cut -c1-300 $out/${tag}_side_$w.json; tail -3 $out/${tag}_side_$w.err
-	timeout 600 ncu --set full --clock-control none -k "regex:colour|conv|affine|sharpen|extract|icc|reduce|shrink|thumbnail" -c 4 -f -o /tmp/${tag}_$w \
+	timeout 600 ncu --set full --clock-control none -k "regex:colour|conv|affine|sharpen|extract|icc|reduce|shrink|thumbnail|linear" -c 4 -f -o /tmp/${tag}_$w \
 		python bench.py --workload $w --steps 1 --warmup 0 --no-cpu > $out/${tag}_ncu_$w.log 2>&1
 	echo "$w ncu rc=$?"
 	ncu -i /tmp/${tag}_$w.ncu-rep --page raw --csv > $out/${tag}_$w.raw.csv 2>/dev/null
