@@ -46,8 +46,10 @@ typedef enum {
 	VB200_INTERPRETATION_CMYK = 15,
 	VB200_INTERPRETATION_XYZ = 12,
 	VB200_INTERPRETATION_LAB = 13,
+	VB200_INTERPRETATION_LCH = 19,
 	VB200_INTERPRETATION_LABS = 21,
 	VB200_INTERPRETATION_sRGB = 22,
+	VB200_INTERPRETATION_YXY = 23,
 	VB200_INTERPRETATION_RGB16 = 25,
 	VB200_INTERPRETATION_GREY16 = 26,
 	VB200_INTERPRETATION_scRGB = 28
@@ -180,9 +182,10 @@ int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int 
  *
  * reference: vips_colourspace(), colour/colourspace.c:551-617.  The source
  * space is in->Type.  Routes among sRGB (uchar), RGB16 (ushort), scRGB, XYZ,
- * LAB (float) and LABS (short) run as ONE fused kernel; every reference step
+ * LAB, LCH, YXY (float) and LABS (short) run as ONE fused kernel; every reference step
  * (sRGB2scRGB, scRGB2XYZ, XYZ2Lab, Lab2LabS, LabS2Lab, Lab2XYZ, XYZ2scRGB,
- * scRGB2sRGB) keeps its own arithmetic.  Bands beyond the third are carried
+ * scRGB2sRGB, Lab2LCh, LCh2Lab, XYZ2Yxy, Yxy2XYZ) keeps its own arithmetic (the two LCh steps call
+ * atan / cosf / sinf: float results within 1 ULP of the reference's glibc; everything else is exact).  Bands beyond the third are carried
  * as vips_colour_build does (colour.c:196-291).
  */
 int vb200_colourspace(const VB200Image *in, VB200Image *out, int space);
@@ -313,6 +316,38 @@ size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
  * or "leaf kernels" for an unfused plan.
  */
 const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
+
+/* ------------------------------------------------------------ morphology
+ * reference: vips_morph(), morphology/morph.c:1030-1042 (generate functions :657-826; the Highway kernels
+ * morph_hwy.cpp give the same bytes).  mask elements 0 / 128 (do not care) / 255; uchar images.
+ */
+enum { VB200_MORPHOLOGY_ERODE = 0, VB200_MORPHOLOGY_DILATE = 1 };
+int vb200_morph(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int morph);
+
+/* ------------------------------------------------- unfused graphs: the chain pump
+ *
+ * What vips_sink_memory + vips_threadpool_run (iofuncs/sinkmemory.c:324, threadpool.c:625) do for an
+ * arbitrary graph of operations: a VB200Chain is a list of the operations above; vb200_chain_run_host
+ * runs it over a batch of host images with upload / compute / download of consecutive images overlapped on
+ * three streams, every intermediate staying on the device.  Each step is the stand-alone entry point's own
+ * device function: same pixels as calling vb200_resize(), vb200_conv() ... one by one, without their
+ * per-call host round trips.  in[i] / out[i] are arrays of n_images; out[i].data == NULL -> allocated
+ * (vb200_image_free).  Pinned host memory (vb200_host_alloc) lets the phases overlap.
+ */
+typedef struct VB200Chain VB200Chain;
+VB200Chain *vb200_chain_new(void);
+void vb200_chain_free(VB200Chain *chain);
+int vb200_chain_add_resize(VB200Chain *chain, double scale, double vscale, int kernel, double gap);
+int vb200_chain_add_reduce(VB200Chain *chain, double hshrink, double vshrink, int kernel, double gap);
+int vb200_chain_add_colourspace(VB200Chain *chain, int space);
+int vb200_chain_add_conv(VB200Chain *chain, const VB200Mask *mask, int precision);
+int vb200_chain_add_convsep(VB200Chain *chain, const VB200Mask *mask, int precision);
+int vb200_chain_add_gaussblur(VB200Chain *chain, double sigma, double min_ampl, int precision);
+int vb200_chain_add_sharpen(VB200Chain *chain, double sigma, double x1, double y2, double y3, double m1, double m2);
+int vb200_chain_add_premultiply(VB200Chain *chain, double max_alpha, int uchar_mode);
+int vb200_chain_add_unpremultiply(VB200Chain *chain, double max_alpha, int uchar_mode);
+int vb200_chain_add_morph(VB200Chain *chain, const VB200Mask *mask, int morph);
+int vb200_chain_run_host(VB200Chain *chain, const VB200Image *in, VB200Image *out, int n_images);
 
 /* ------------------------------------------------------------------ ICC
  * vips_icc_import / vips_icc_export / vips_icc_transform (colour/icc_transform.c:813-945, :995-1117,

@@ -27,8 +27,8 @@ SIZES = {"both": 0, "up": 1, "down": 2, "force": 3}
 PRECISIONS = {"integer": 0, "float": 1, "approximate": 2}
 INTENTS = {"perceptual": 0, "relative": 1, "saturation": 2, "absolute": 3}
 PCS = {"lab": 0, "xyz": 1}
-INTERPRETATIONS = {"multiband": 0, "b-w": 1, "cmyk": 15, "xyz": 12, "lab": 13, "labs": 21, "srgb": 22, "rgb16": 25,
-                   "grey16": 26, "scrgb": 28}
+INTERPRETATIONS = {"multiband": 0, "b-w": 1, "cmyk": 15, "xyz": 12, "lab": 13, "lch": 19, "labs": 21, "srgb": 22,
+                   "yxy": 23, "rgb16": 25, "grey16": 26, "scrgb": 28}
 
 
 class Error(Exception):
@@ -125,6 +125,20 @@ def lib():
         L.vb200_sharpen_batch_device.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t] + [C.c_int] * 4 + [C.c_double] * 6
         L.vb200_thumbnail_plan_set_sharpen.argtypes = [C.c_void_p] + [C.c_double] * 6
         L.vb200_device_numa_node.restype = C.c_int
+        L.vb200_morph.argtypes = [IP, IP, MP, C.c_int]
+        L.vb200_chain_add_morph.argtypes = [C.c_void_p, MP, C.c_int]
+        L.vb200_chain_new.restype = C.c_void_p
+        L.vb200_chain_free.argtypes = [C.c_void_p]
+        L.vb200_chain_add_resize.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.vb200_chain_add_reduce.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
+        L.vb200_chain_add_colourspace.argtypes = [C.c_void_p, C.c_int]
+        L.vb200_chain_add_conv.argtypes = [C.c_void_p, MP, C.c_int]
+        L.vb200_chain_add_convsep.argtypes = [C.c_void_p, MP, C.c_int]
+        L.vb200_chain_add_gaussblur.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
+        L.vb200_chain_add_sharpen.argtypes = [C.c_void_p] + [C.c_double] * 6
+        L.vb200_chain_add_premultiply.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.vb200_chain_add_unpremultiply.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.vb200_chain_run_host.argtypes = [C.c_void_p, IP, IP, C.c_int]
         _lib = L
     return _lib
 
@@ -286,6 +300,18 @@ class Image:
     def sharpen(self, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
         return self._call(lib().vb200_sharpen, float(sigma), float(x1), float(y2), float(y3), float(m1), float(m2))
 
+    # ---- morphology
+    def morph(self, mask, morph):
+        """vips_morph: mask elements 0 / 128 / 255; morph "erode" or "dilate" """
+        m, cm = self._mask(mask, 1.0, 0.0)
+        return self._call(lib().vb200_morph, C.byref(cm), {"erode": 0, "dilate": 1}.get(morph, morph))
+
+    def erode(self, mask):
+        return self.morph(mask, "erode")
+
+    def dilate(self, mask):
+        return self.morph(mask, "dilate")
+
     # ---- colour
     def colourspace(self, space, source_space=None):
         src = self if source_space is None else Image(self.array, source_space)
@@ -358,3 +384,82 @@ class ThumbnailPlan:
         out = np.empty((frames.shape[0], self.out_height, self.out_width, self.bands), np.uint8)
         self.run_host_ptr(frames.ctypes.data, out.ctypes.data, frames.shape[0])
         return out
+
+
+class Chain:
+    """An unfused operation graph pumped over a batch of host images (vb200_chain_* in include/vb200.h):
+    the methods mirror Image's; run() takes a list of arrays (sizes may differ) and returns Images."""
+
+    def __init__(self):
+        self._p = lib().vb200_chain_new()
+        if not self._p:
+            _check(-1)
+        self._keep = []
+
+    def close(self):
+        if self._p:
+            lib().vb200_chain_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def resize(self, scale, vscale=None, kernel="lanczos3", gap=2.0):
+        _check(lib().vb200_chain_add_resize(self._p, float(scale), float(scale if vscale is None else vscale), _k(kernel), float(gap)))
+        return self
+
+    def reduce(self, hshrink, vshrink, kernel="lanczos3", gap=0.0):
+        _check(lib().vb200_chain_add_reduce(self._p, float(hshrink), float(vshrink), _k(kernel), float(gap)))
+        return self
+
+    def colourspace(self, space):
+        _check(lib().vb200_chain_add_colourspace(self._p, _interp(space)))
+        return self
+
+    def conv(self, mask, scale=1.0, offset=0.0, precision="float"):
+        m, cm = Image._mask(mask, scale, offset)
+        _check(lib().vb200_chain_add_conv(self._p, C.byref(cm), PRECISIONS[precision]))
+        return self
+
+    def convsep(self, mask, scale=1.0, offset=0.0, precision="float"):
+        m, cm = Image._mask(mask, scale, offset)
+        _check(lib().vb200_chain_add_convsep(self._p, C.byref(cm), PRECISIONS[precision]))
+        return self
+
+    def morph(self, mask, morph):
+        m, cm = Image._mask(mask, 1.0, 0.0)
+        _check(lib().vb200_chain_add_morph(self._p, C.byref(cm), {"erode": 0, "dilate": 1}.get(morph, morph)))
+        return self
+
+    def gaussblur(self, sigma, min_ampl=0.2, precision="integer"):
+        _check(lib().vb200_chain_add_gaussblur(self._p, float(sigma), float(min_ampl), PRECISIONS[precision]))
+        return self
+
+    def sharpen(self, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
+        _check(lib().vb200_chain_add_sharpen(self._p, float(sigma), float(x1), float(y2), float(y3), float(m1), float(m2)))
+        return self
+
+    def premultiply(self, max_alpha=0.0, uchar=False):
+        _check(lib().vb200_chain_add_premultiply(self._p, float(max_alpha), int(uchar)))
+        return self
+
+    def unpremultiply(self, max_alpha=0.0, uchar=False):
+        _check(lib().vb200_chain_add_unpremultiply(self._p, float(max_alpha), int(uchar)))
+        return self
+
+    def run(self, images):
+        ims = [im if isinstance(im, Image) else Image(im) for im in images]
+        n = len(ims)
+        cin = (CImage * n)(*[im._c() for im in ims])
+        cout = (CImage * n)()
+        _check(lib().vb200_chain_run_host(self._p, cin, cout, n))
+        res = []
+        for o in cout:
+            buf = (C.c_uint8 * (o.Ysize * o.bpl)).from_address(o.data)
+            arr = np.frombuffer(buf, dtype=DTYPES[o.BandFmt]).reshape(o.Ysize, o.Xsize, o.Bands).copy()
+            lib().vb200_image_free(C.byref(o))
+            res.append(Image(arr, o.Type))
+        return res

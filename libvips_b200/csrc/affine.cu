@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "vb200_internal.h"
@@ -152,6 +153,93 @@ affine_bicubic_u8x4_kernel(const __grid_constant__ AffineDev P, const uint8_t *_
 	*q = v;
 }
 
+/* The same pixels, separably.  vips_interpolate_bicubic's integer path is two-stage -- four horizontal sums
+ * rounded to integers, then the vertical sum of those (bicubic_unsigned_int_tab, bicubic.cpp:106-166) -- so
+ * the horizontal stage of an input row is shared by every output row that samples it (two of them at x2).
+ * One CTA owns a 64 x 32 output tile: it runs the horizontal stage once per input row the tile touches
+ * (at most 32 + 3 when the vertical scale is >= 1) into shared memory as short4, then each output pixel
+ * is four 64-bit shared loads and sixteen multiply-adds.  ~65 instead of ~225 instructions per output pixel.
+ */
+constexpr int kSepTW = 64, kSepTH = 32, kSepRows = kSepTH + 4;
+
+__global__ void __launch_bounds__(256)
+affine_bicubic_u8x4_sep_kernel(const __grid_constant__ AffineDev P, const uint8_t *__restrict__ in, uint8_t *__restrict__ out)
+{
+	__shared__ short4 sh[kSepRows][kSepTW];
+	const int t = threadIdx.x;
+	const int lx = t & (kSepTW - 1), ly = t >> 6; /* 64 columns x 4 row phases */
+	const int x0 = blockIdx.x * kSepTW, y0 = blockIdx.y * kSepTH;
+	const int x = min(x0 + lx, P.OW - 1);
+	const int y_last = min(y0 + kSepTH, P.OH) - 1;
+
+	/* this thread's column: the horizontal coordinates never change down the tile */
+	const double ix = P.ixs[x];
+	const int fx = (int) floor(ix);
+	const bool x_in = fx >= P.ile && fx <= P.iri;
+	const int xi = (int) ix;
+	const int sx = (int) __dmul_rn(__dmul_rn(ix, (double) VB200_TRANSFORM_SCALE), 2.0);
+	const int tx = ((sx & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+	const int4 cx = __ldg((const int4 *) (P.ci + tx * 4));
+	const unsigned cx01 = ((unsigned) cx.y << 16) | ((unsigned) cx.x & 0xffffu);
+	const unsigned cx23 = ((unsigned) cx.w << 16) | ((unsigned) cx.z & 0xffffu);
+	int col[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		col[i] = max(0, min(xi - 1 + i - P.pad, P.w - 1));
+
+	/* the input rows this tile samples */
+	const int r_lo = (int) P.iys[y0] - 1;
+	const int nrows = min((int) P.iys[y_last] + 2 - r_lo + 1, kSepRows);
+	for (int rr = ly; rr < nrows; rr += 4) {
+		const int sy2 = max(0, min(r_lo + rr - P.pad, P.h - 1));
+		const unsigned *row = (const unsigned *) (in + (size_t) sy2 * P.in_bpl);
+		const unsigned p0 = __ldg(row + col[0]), p1 = __ldg(row + col[1]), p2 = __ldg(row + col[2]), p3 = __ldg(row + col[3]);
+		const unsigned a01 = __byte_perm(p0, p1, 0x5140); /* [p0.c0 p1.c0 p0.c1 p1.c1] */
+		const unsigned b01 = __byte_perm(p0, p1, 0x7362); /* [p0.c2 p1.c2 p0.c3 p1.c3] */
+		const unsigned a23 = __byte_perm(p2, p3, 0x5140);
+		const unsigned b23 = __byte_perm(p2, p3, 0x7362);
+		short4 r;
+		r.x = (short) ufr(dp2a_lo_s(cx23, a23, dp2a_lo_s(cx01, a01, 0)));
+		r.y = (short) ufr(dp2a_hi_s(cx23, a23, dp2a_hi_s(cx01, a01, 0)));
+		r.z = (short) ufr(dp2a_lo_s(cx23, b23, dp2a_lo_s(cx01, b01, 0)));
+		r.w = (short) ufr(dp2a_hi_s(cx23, b23, dp2a_hi_s(cx01, b01, 0)));
+		sh[rr][lx] = r;
+	}
+	__syncthreads();
+
+	if (x0 + lx >= P.OW)
+		return;
+	for (int y = y0 + ly; y <= y_last; y += 4) {
+		unsigned *q = (unsigned *) ((char *) out + (size_t) y * P.out_bpl) + x;
+		const double iy = P.iys[y];
+		const int fy = (int) floor(iy);
+		if (!(x_in && fy >= P.ito && fy <= P.ibo)) {
+			*q = 0;
+			continue;
+		}
+		const int yi = (int) iy;
+		const int sy = (int) __dmul_rn(__dmul_rn(iy, (double) VB200_TRANSFORM_SCALE), 2.0);
+		const int ty = ((sy & (VB200_TRANSFORM_SCALE * 2 - 1)) + 1) >> 1;
+		const int4 cy = __ldg((const int4 *) (P.ci + ty * 4));
+		const int cyv[4] = {cy.x, cy.y, cy.z, cy.w};
+		const int base = yi - 1 - r_lo;
+		int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const short4 r = sh[base + j][lx];
+			acc[0] += cyv[j] * r.x;
+			acc[1] += cyv[j] * r.y;
+			acc[2] += cyv[j] * r.z;
+			acc[3] += cyv[j] * r.w;
+		}
+		unsigned v = 0;
+#pragma unroll
+		for (int c = 0; c < 4; c++)
+			v |= (unsigned) max(0, min(ufr(acc[c]), 255)) << (8 * c);
+		*q = v;
+	}
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 affine_scale_kernel(const __grid_constant__ AffineDev P, const T *__restrict__ in, T *__restrict__ out)
@@ -266,6 +354,20 @@ affine_scale_kernel(const __grid_constant__ AffineDev P, const T *__restrict__ i
 
 #define VB200_ROUND_INT(R) ((int) ((R) > 0 ? ((R) + 0.5) : ((R) -0.5)))
 
+struct AffineKey {
+	int dev, OW, OH, ol, ot, window_offset;
+	double ia, id, tidx, tidy;
+};
+struct AffineEntry {
+	AffineKey key;
+	void *block;
+	size_t nd;
+	unsigned long long stamp;
+};
+std::mutex g_affine_lock;
+std::vector<AffineEntry> g_affine_cache;
+unsigned long long g_affine_clock = 0;
+
 } // namespace
 
 /* vips_affine(in, a, 0, 0, d, interpolate, idx, idy, extend COPY, premultiplied TRUE) */
@@ -300,57 +402,91 @@ dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a
 	const int window_offset = std::max(0, window_size / 2 - 1);
 	const double tidx = idx - 1, tidy = idy - 1; /* the embed's one-pixel border, affine.c:533-534 */
 
-	/* the coordinate sequences of vips_affine_gen (affine.c:325-400), ib = ic = 0, odx = ody = 0 */
-	std::vector<double> host((((size_t) OW + OH + 65 * 4) + 1) & ~(size_t) 1); /* even: the int table after it stays 16-byte aligned */
-	{
-		const double ox = 0 + ol - 0.0;
-		double ix = ia * ox + 0.0 * (0 + ot - 0.0);
-		ix -= tidx;
-		ix += window_offset;
-		for (int x = 0; x < OW; x++) {
-			host[x] = ix;
-			ix += ia; /* ddx */
-		}
-		for (int y = 0; y < OH; y++) {
-			const double oy = y + ot - 0.0;
-			double iy = 0.0 * ox + id * oy;
-			iy -= tidy;
-			iy += window_offset;
-			host[OW + y] = iy;
-		}
-	}
-	/* bicubic tables: calculate_coefficients_catmull (templates.h:281-305), bicubic.cpp:636-644 */
-	std::vector<int> ci(65 * 4);
-	for (int t = 0; t <= VB200_TRANSFORM_SCALE; t++) {
-		const double x = (float) t / VB200_TRANSFORM_SCALE;
-		const double cr1 = 1. - x;
-		const double cr2 = -.5 * x;
-		const double cr3 = cr1 * cr2;
-		const double cone = cr1 * cr3;
-		const double cfou = x * cr3;
-		const double cr4 = cfou - cone;
-		const double ctwo = cr1 - cone + cr4;
-		const double cthr = x - cfou - cr4;
-		double *c = &host[(size_t) OW + OH + t * 4];
-		c[0] = cone;
-		c[1] = ctwo;
-		c[2] = cthr;
-		c[3] = cfou;
-		for (int i = 0; i < 4; i++)
-			ci[t * 4 + i] = c[i] * VB200_INTERPOLATE_SCALE;
-	}
-
+	/* The coordinate and coefficient tables depend on the geometry only: a server resizing same-shaped frames
+	 * builds and uploads them once (host loops + a pageable copy were as long as the kernel itself at 4K x2).
+	 */
 	void *block = nullptr;
-	const size_t nd = host.size() * sizeof(double), ni = ci.size() * sizeof(int);
-	if (dev_alloc(domain, &block, nd + ni, s))
-		return -1;
-	VB200_CUDA(domain, cudaMemcpyAsync(block, host.data(), nd, cudaMemcpyHostToDevice, s));
-	VB200_CUDA(domain, cudaMemcpyAsync((char *) block + nd, ci.data(), ni, cudaMemcpyHostToDevice, s));
+	size_t nd = 0;
+	{
+		int dev = 0;
+		VB200_CUDA(domain, cudaGetDevice(&dev));
+		const AffineKey key{dev, OW, OH, ol, ot, window_offset, ia, id, tidx, tidy};
+		std::lock_guard<std::mutex> lock(g_affine_lock);
+		for (auto &e : g_affine_cache)
+			if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+				block = e.block;
+				nd = e.nd;
+				e.stamp = ++g_affine_clock;
+			}
+		if (!block) {
+		/* the coordinate sequences of vips_affine_gen (affine.c:325-400), ib = ic = 0, odx = ody = 0 */
+		std::vector<double> host((((size_t) OW + OH + 65 * 4) + 1) & ~(size_t) 1); /* even: the int table after it stays 16-byte aligned */
+		{
+			const double ox = 0 + ol - 0.0;
+			double ix = ia * ox + 0.0 * (0 + ot - 0.0);
+			ix -= tidx;
+			ix += window_offset;
+			for (int x = 0; x < OW; x++) {
+				host[x] = ix;
+				ix += ia; /* ddx */
+			}
+			for (int y = 0; y < OH; y++) {
+				const double oy = y + ot - 0.0;
+				double iy = 0.0 * ox + id * oy;
+				iy -= tidy;
+				iy += window_offset;
+				host[OW + y] = iy;
+			}
+		}
+		/* bicubic tables: calculate_coefficients_catmull (templates.h:281-305), bicubic.cpp:636-644 */
+		std::vector<int> ci(65 * 4);
+		for (int t = 0; t <= VB200_TRANSFORM_SCALE; t++) {
+			const double x = (float) t / VB200_TRANSFORM_SCALE;
+			const double cr1 = 1. - x;
+			const double cr2 = -.5 * x;
+			const double cr3 = cr1 * cr2;
+			const double cone = cr1 * cr3;
+			const double cfou = x * cr3;
+			const double cr4 = cfou - cone;
+			const double ctwo = cr1 - cone + cr4;
+			const double cthr = x - cfou - cr4;
+			double *c = &host[(size_t) OW + OH + t * 4];
+			c[0] = cone;
+			c[1] = ctwo;
+			c[2] = cthr;
+			c[3] = cfou;
+			for (int i = 0; i < 4; i++)
+				ci[t * 4 + i] = c[i] * VB200_INTERPOLATE_SCALE;
+		}
 
-	if (dev_image_new(domain, out, OW, OH, in.bands, in.fmt, in.type, s)) {
-		dev_free(block, s);
-		return -1;
+		nd = host.size() * sizeof(double);
+		const size_t ni = ci.size() * sizeof(int);
+		VB200_CUDA(domain, cudaMalloc(&block, nd + ni));
+		/* synchronous copies: the entry may be used from any stream afterwards */
+		VB200_CUDA(domain, cudaMemcpy(block, host.data(), nd, cudaMemcpyHostToDevice));
+		VB200_CUDA(domain, cudaMemcpy((char *) block + nd, ci.data(), ni, cudaMemcpyHostToDevice));
+		if (g_affine_cache.size() >= 16) {
+			/* evict the least recently used (cudaFree waits for kernels still reading it) */
+			size_t victim = 0;
+			for (size_t i = 1; i < g_affine_cache.size(); i++)
+				if (g_affine_cache[i].stamp < g_affine_cache[victim].stamp)
+					victim = i;
+			cudaFree(g_affine_cache[victim].block);
+			g_affine_cache.erase(g_affine_cache.begin() + victim);
+		}
+		AffineEntry e;
+		memset(&e.key, 0, sizeof(e.key));
+		e.key = key;
+		e.block = block;
+		e.nd = nd;
+		e.stamp = ++g_affine_clock;
+		g_affine_cache.push_back(e);
+		}
 	}
+
+
+	if (dev_image_new(domain, out, OW, OH, in.bands, in.fmt, in.type, s))
+		return -1;
 	AffineDev P;
 	P.ixs = (const double *) block;
 	P.iys = P.ixs + OW;
@@ -373,7 +509,12 @@ dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a
 #define AF(T) affine_scale_kernel<T><<<grid, 256, 0, s>>>(P, (const T *) in.data, (T *) out->data)
 	const bool u8x4 = in.fmt == VB200_FORMAT_UCHAR && in.bands == 4 && interp == INTERP_BICUBIC && (in.bpl & 3) == 0 &&
 		((uintptr_t) in.data & 3) == 0 && getenv("VB200_NO_AFFINE_X4") == nullptr;
-	if (u8x4)
+	/* vertical scale >= 1: a tile of 32 output rows touches at most 35 input rows (the separable kernel's budget) */
+	const bool sep = u8x4 && id <= 1.0 && getenv("VB200_NO_AFFINE_SEP") == nullptr;
+	if (sep)
+		affine_bicubic_u8x4_sep_kernel<<<dim3((OW + kSepTW - 1) / kSepTW, (OH + kSepTH - 1) / kSepTH), 256, 0, s>>>(P,
+			(const uint8_t *) in.data, (uint8_t *) out->data);
+	else if (u8x4)
 		affine_bicubic_u8x4_kernel<<<grid, 256, 0, s>>>(P, (const uint8_t *) in.data, (uint8_t *) out->data);
 	else
 	switch (in.fmt) {
@@ -387,7 +528,6 @@ dev_affine_scale(const char *domain, const DevImage &in, DevImage *out, double a
 	}
 #undef AF
 	cudaError_t e = cudaGetLastError();
-	dev_free(block, s);
 	if (e != cudaSuccess)
 		return cuda_fail(domain, e, "affine kernel");
 	count_launch();

@@ -186,6 +186,18 @@ colour_route_kernel(const __grid_constant__ RouteParams P, const void *__restric
 				ic = scRGB2sRGB_channel_f(s_Y2v_8, 255.0f, c);
 			}
 			break;
+		case S_Lab2LCh:
+			step_Lab2LCh(a, b, c);
+			break;
+		case S_LCh2Lab:
+			step_LCh2Lab(a, b, c);
+			break;
+		case S_XYZ2Yxy:
+			step_XYZ2Yxy(a, b, c);
+			break;
+		case S_Yxy2XYZ:
+			step_Yxy2XYZ(a, b, c);
+			break;
 		case S_scRGB2RGB16:
 			if (isnan(a) || isnan(b) || isnan(c))
 				ia = ib = ic = 0;
@@ -332,13 +344,39 @@ build_route(int from, int to, int *steps)
 {
 	const int XYZ = VB200_INTERPRETATION_XYZ, LAB = VB200_INTERPRETATION_LAB, LABS = VB200_INTERPRETATION_LABS;
 	const int sRGB = VB200_INTERPRETATION_sRGB, RGB16 = VB200_INTERPRETATION_RGB16, scRGB = VB200_INTERPRETATION_scRGB;
+	const int LCH = VB200_INTERPRETATION_LCH, YXY = VB200_INTERPRETATION_YXY;
 	int n = 0;
-	bool known_from = from == XYZ || from == LAB || from == LABS || from == sRGB || from == RGB16 || from == scRGB;
-	bool known_to = to == XYZ || to == LAB || to == LABS || to == sRGB || to == RGB16 || to == scRGB;
+	bool known_from = from == XYZ || from == LAB || from == LABS || from == sRGB || from == RGB16 || from == scRGB ||
+		from == LCH || from == YXY;
+	bool known_to = to == XYZ || to == LAB || to == LABS || to == sRGB || to == RGB16 || to == scRGB || to == LCH || to == YXY;
 	if (!known_from || !known_to)
 		return -1;
 	if (from == to)
 		return 0;
+	/* LCH hangs off LAB and YXY off XYZ in every row of the table (colourspace.c:226, 236, 242, 252, 275-290):
+	 * route to the hub, then one more step
+	 */
+	if (to == LCH || to == YXY) {
+		const int hub = to == LCH ? LAB : XYZ;
+		int m = 0;
+		if (from != hub) {
+			m = build_route(from, hub, steps);
+			if (m < 0)
+				return -1;
+		}
+		steps[m++] = to == LCH ? S_Lab2LCh : S_XYZ2Yxy;
+		return m;
+	}
+	if (from == LCH) {
+		steps[n++] = S_LCh2Lab;
+		from = LAB;
+	}
+	else if (from == YXY) {
+		steps[n++] = S_Yxy2XYZ;
+		from = XYZ;
+	}
+	if (from == to)
+		return n;
 	if (from == sRGB) {
 		steps[n++] = S_sRGB2scRGB;
 		from = scRGB;
@@ -397,6 +435,10 @@ step_io(int step, int *in_fmt, int *out_fmt, int *out_type)
 	case S_Lab2XYZ: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_XYZ; break;
 	case S_XYZ2scRGB: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_scRGB; break;
 	case S_scRGB2sRGB: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_UCHAR; *out_type = VB200_INTERPRETATION_sRGB; break;
+	case S_Lab2LCh: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_LCH; break;
+	case S_LCh2Lab: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_LAB; break;
+	case S_XYZ2Yxy: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_YXY; break;
+	case S_Yxy2XYZ: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_FLOAT; *out_type = VB200_INTERPRETATION_XYZ; break;
 	default: *in_fmt = VB200_FORMAT_FLOAT; *out_fmt = VB200_FORMAT_USHORT; *out_type = VB200_INTERPRETATION_RGB16; break;
 	}
 }

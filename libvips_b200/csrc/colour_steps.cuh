@@ -21,7 +21,7 @@ constexpr int kQuant = 100000; /* QUANT_ELEMENTS, XYZ2Lab.c:66 */
 
 enum Step {
 	S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
-	S_scRGB2RGB16, S_RGB162scRGB
+	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ
 };
 
 struct ColourTables {
@@ -278,6 +278,93 @@ cbrt_lookup2(const float2 *__restrict__ table, float nX)
 	const float f = __fsub_rn(nX, fi);
 	const float2 t = __ldg(table + i);
 	return __fadd_rn(t.x, __fmul_rn(f, __fsub_rn(t.y, t.x)));
+}
+
+/* ---- Lab <-> LCh, XYZ <-> Yxy */
+
+/* vips_Lab2LCh_line + vips_col_ab2h, Lab2LCh.c:61-124.  C is exact (float multiplies / add, IEEE sqrtf); the hue
+ * goes through the double atan(), where CUDA's libm and glibc may differ by an ulp of the DOUBLE result -- after
+ * the rounding to float that is the same float except in rare halfway cases: float results within 1 ULP.
+ */
+__device__ __forceinline__ void
+step_Lab2LCh(float &a, float &b, float &c)
+{
+	const float A = b, B = c;
+	const float C = __fsqrt_rn(__fadd_rn(__fmul_rn(A, A), __fmul_rn(B, B)));
+	const double PI = 3.14159265358979323846;
+	const double da = (double) A, db = (double) B;
+	double h;
+	if (da == 0) {
+		if (db < 0.0)
+			h = 270;
+		else if (db == 0.0)
+			h = 0;
+		else
+			h = 90;
+	}
+	else {
+		const double t = atan(__ddiv_rn(db, da));
+		if (da > 0.0)
+			if (db < 0.0)
+				h = __dmul_rn(__ddiv_rn(__dadd_rn(t, __dmul_rn(PI, 2.0)), __dmul_rn(2.0, PI)), 360.0);
+			else
+				h = __dmul_rn(__ddiv_rn(t, __dmul_rn(2.0, PI)), 360.0);
+		else
+			h = __dmul_rn(__ddiv_rn(__dadd_rn(t, PI), __dmul_rn(2.0, PI)), 360.0);
+	}
+	b = C;
+	c = (float) h;
+}
+
+/* vips_LCh2Lab_line + vips_col_Ch2ab, LCh2Lab.c:70-103: cosf / sinf of (float) VIPS_RAD(h); within 1-2 ULP of glibc's */
+__device__ __forceinline__ void
+step_LCh2Lab(float &a, float &b, float &c)
+{
+	const double PI = 3.14159265358979323846;
+	const float C = b, h = c;
+	const float rad = (float) __dmul_rn(__dmul_rn(__ddiv_rn((double) h, 360.0), 2.0), PI);
+	b = __fmul_rn(C, cosf(rad));
+	c = __fmul_rn(C, sinf(rad));
+}
+
+/* vips_XYZ2Yxy_line, XYZ2Yxy.c:57-88: float sum, double quotients -- exact */
+__device__ __forceinline__ void
+step_XYZ2Yxy(float &a, float &b, float &c)
+{
+	const float X = a, Y = b, Z = c;
+	const double total = (double) __fadd_rn(__fadd_rn(X, Y), Z);
+	float x, y;
+	if (total == 0.0) {
+		x = 0;
+		y = 0;
+	}
+	else {
+		x = (float) __ddiv_rn((double) X, total);
+		y = (float) __ddiv_rn((double) Y, total);
+	}
+	a = Y;
+	b = x;
+	c = y;
+}
+
+/* vips_Yxy2XYZ_line, Yxy2XYZ.c:59-93: float arithmetic as written -- exact */
+__device__ __forceinline__ void
+step_Yxy2XYZ(float &a, float &b, float &c)
+{
+	const float Y = a, x = b, y = c;
+	float X, Z;
+	if (x == 0.0f || y == 0.0f) {
+		X = 0.0F;
+		Z = 0.0F;
+	}
+	else {
+		const float total = __fdiv_rn(Y, y);
+		X = __fmul_rn(x, total);
+		Z = __fdiv_rn(__fsub_rn(__fsub_rn(X, __fmul_rn(x, X)), __fmul_rn(x, Y)), x);
+	}
+	a = X;
+	b = Y;
+	c = Z;
 }
 
 /* a band beyond the third through a route, as vips_colour_build re-attaches it per step

@@ -59,6 +59,9 @@ struct LinVParams {
 	StepInfo fwd[2];
 	int n_fwd;
 	const float *v2Y_8;
+	/* the residual-2.0 schedule (linear_v2_kernel): first[y] = f0 + 2 y, one phase, 13 taps */
+	int f0;
+	double c2[13];
 };
 
 struct LinHParams {
@@ -236,14 +239,158 @@ linear_v_kernel(const __grid_constant__ LinVParams P, const uint8_t *__restrict_
 	}
 }
 
+
+/* Kernel V for the commonest geometry: a total shrink that is an even integer (4096 -> 512, 3840 -> 640 ...)
+ * leaves vips_resize a residual of exactly 2.0 after the box, so every output row has the same 13
+ * coefficients and its window starts two box-shrunk rows after its predecessor's.  The schedule is then
+ * static: per iteration one output row starts (tap 0), seven rows receive an even tap from shrunk row A
+ * (the oldest completes with tap 12 and is stored), six receive an odd tap from row B.  The seven
+ * accumulators rotate through registers by unrolling seven iterations; coefficients are kernel-parameter
+ * constants.  Same sums in the same order as the general kernel -- 42 instead of 93 instructions per pixel.
+ */
+template <bool PREMUL, int VST>
+__global__ void __launch_bounds__(kVThreads, 2)
+linear_v2_kernel(const __grid_constant__ LinVParams P, const uint8_t *__restrict__ in, int frame0)
+{
+	constexpr int NCH = 4;
+	constexpr int ROWS = 2 * VST;						   /* input rows per iteration */
+	constexpr int CAP = (kDepth + 1) * kMaxBox;			   /* ring capacity in rows */
+	constexpr int NST = CAP / ROWS < 7 ? CAP / ROWS : 7;   /* ring stages */
+	constexpr int D2 = NST - 1;							   /* iterations in flight */
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	double *s_vc = (double *) smem_raw; /* unused here; keeps the layout of linear_v_kernel */
+	float *s_lin = (float *) (s_vc + 65 * P.nv);
+	/* alpha byte -> (premultiply factor, scRGB alpha): one 64-bit lookup.  (Holding the alpha as a double to
+	 * save its conversion was measured: the 8-byte random gather costs more shared-memory wavefronts than the
+	 * conversion it saves -- 57.7 vs 45.4 us per frame.)
+	 */
+	float2 *s_aln = (float2 *) (s_lin + 256);
+	unsigned *s_ring = (unsigned *) (s_lin + 4 * 256);
+
+	const int t = threadIdx.x;
+	for (int i = t; i < 256; i += kVThreads) {
+		s_lin[i] = P.v2Y_8[i];
+		const float A = (float) carry_extra_band((double) i, P.fwd, P.n_fwd);
+		const float clip_alpha = (float) fmax(0.0, fmin(1.0, (double) A));
+		s_aln[i] = make_float2((float) __ddiv_rn((double) clip_alpha, 1.0), A);
+	}
+	__syncthreads();
+
+	const int xi = blockIdx.x * kVThreads + t;
+	const bool live = xi < P.W;
+	const int x = min(xi, P.W - 1);
+	const int y_begin = blockIdx.y * P.RPC, y_end = min(y_begin + P.RPC, P.OH);
+	const int frame = frame0 + blockIdx.z;
+	const uint8_t *col = in + (size_t) frame * P.in_frame_stride + (size_t) x * NCH;
+	float *mcol = P.mid + (size_t) frame * P.mid_frame_stride + (size_t) x * NCH;
+	const int m_end = y_end + 6; /* iterations: output row mm starts at iteration mm, completes at mm + 6 */
+
+	/* iteration mm reads box-shrunk rows e = f0 + 2 mm (A) and e + 1 (B) */
+	/* ring stage of iteration mm: (mm - y_begin) mod NST -- the unrolled loop below passes it as a constant
+	 * when NST is 7 (the loop advances seven iterations at a time)
+	 */
+	auto prefetch = [&](int mm, int stage) {
+		if (mm < m_end) {
+			unsigned *dst = s_ring + stage * (ROWS * kVThreads) + t;
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				const int sr = max(0, min(P.f0 + 2 * mm + h - P.vembed, P.Hs - 1));
+#pragma unroll
+				for (int k = 0; k < VST; k++) {
+					const int row = min(sr * VST + k, P.H - 1);
+					const unsigned d = (unsigned) __cvta_generic_to_shared(dst + (h * VST + k) * kVThreads);
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(col + (size_t) row * P.in_bpl) : "memory");
+				}
+			}
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+#pragma unroll
+	for (int d = 0; d < D2; d++)
+		prefetch(y_begin + d, d % NST);
+
+	double a[7][NCH];
+#pragma unroll
+	for (int J = 0; J < 7; J++)
+#pragma unroll
+		for (int c = 0; c < NCH; c++)
+			a[J][c] = 0.0;
+
+	for (int m = y_begin; m < m_end; m += 7) {
+#pragma unroll
+		for (int u = 0; u < 7; u++) {
+			const int mm = m + u;
+			if (mm < m_end) {
+				const int stage = NST == 7 ? u : (mm - y_begin) % NST;
+				prefetch(mm + D2, NST == 7 ? (u + D2) % NST : (mm + D2 - y_begin) % NST);
+				asm volatile("cp.async.wait_group %0;" ::"n"(D2) : "memory");
+				const unsigned *mine = s_ring + stage * (ROWS * kVThreads) + t;
+				double sv[2][NCH];
+#pragma unroll
+				for (int h = 0; h < 2; h++) {
+					double sum[NCH];
+#pragma unroll
+					for (int c = 0; c < NCH; c++)
+						sum[c] = 0.0;
+#pragma unroll
+					for (int k = 0; k < VST; k++) {
+						const unsigned px = mine[(h * VST + k) * kVThreads];
+						const float r = s_lin[px & 255], g = s_lin[(px >> 8) & 255], b = s_lin[(px >> 16) & 255];
+						const float2 an = s_aln[px >> 24];
+						float q0 = r, q1 = g, q2 = b;
+						if (PREMUL) {
+							q0 = __fmul_rn(r, an.x);
+							q1 = __fmul_rn(g, an.x);
+							q2 = __fmul_rn(b, an.x);
+						}
+						sum[0] = __dadd_rn(sum[0], (double) q0);
+						sum[1] = __dadd_rn(sum[1], (double) q1);
+						sum[2] = __dadd_rn(sum[2], (double) q2);
+						sum[3] = __dadd_rn(sum[3], (double) an.y);
+					}
+#pragma unroll
+					for (int c = 0; c < NCH; c++)
+						sv[h][c] = (double) (float) __dmul_rn(sum[c], P.inv_v);
+				}
+				/* row A: even taps.  Output row mm - j sits in slot (u - j) mod 7; slot u starts here */
+#pragma unroll
+				for (int c = 0; c < NCH; c++)
+					a[u][c] = 0.0;
+#pragma unroll
+				for (int j = 0; j < 7; j++) {
+					const int sl = (u - j + 7) % 7;
+#pragma unroll
+					for (int c = 0; c < NCH; c++)
+						a[sl][c] = __dadd_rn(a[sl][c], __dmul_rn(P.c2[2 * j], sv[0][c]));
+				}
+				{
+					const int y = mm - 6, sl = (u + 1) % 7;
+					if (live && y >= y_begin)
+						*(float4 *) (mcol + (size_t) y * P.W * NCH) =
+							make_float4((float) a[sl][0], (float) a[sl][1], (float) a[sl][2], (float) a[sl][3]);
+				}
+				/* row B: odd taps */
+#pragma unroll
+				for (int j = 0; j < 6; j++) {
+					const int sl = (u - j + 7) % 7;
+#pragma unroll
+					for (int c = 0; c < NCH; c++)
+						a[sl][c] = __dadd_rn(a[sl][c], __dmul_rn(P.c2[2 * j + 1], sv[1][c]));
+				}
+			}
+		}
+	}
+}
+
 template <int NCH, bool PREMUL>
 __global__ void __launch_bounds__(256)
 linear_h_kernel(const __grid_constant__ LinHParams P, uint8_t *__restrict__ out, int frame0)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	double *s_hc = (double *) smem_raw;			   /* [65 * nh] */
-	float *s_Y2v = (float *) (s_hc + 65 * P.nh);   /* [257], integers as floats (+ 3 pad) */
-	float *s_shr = s_Y2v + 260;					   /* [Wse][NCH] the box-shrunk, embedded row */
+	float *s_row = (float *) smem_raw;								 /* [OW][NCH] the reduceh result */
+	float *s_shr = s_row + ((P.OW * NCH + 3) & ~3);					 /* [Wse][NCH] the box-shrunk, embedded row */
+	double *s_hc = (double *) (s_shr + ((P.Wse * NCH + 3) & ~3));	 /* [65 * nh] */
+	float *s_Y2v = (float *) (s_hc + 65 * P.nh);					 /* [257], integers as floats */
 
 	const int t = threadIdx.x;
 	for (int i = t; i < 65 * P.nh; i += 256)
@@ -255,47 +402,41 @@ linear_h_kernel(const __grid_constant__ LinHParams P, uint8_t *__restrict__ out,
 	const int frame = frame0 + blockIdx.y;
 	const float *row = P.mid + (size_t) frame * P.mid_frame_stride + (size_t) y * P.W * NCH;
 
-	/* ---- shrinkh (FSHRINK, shrinkh.c:134-152) over the embedded row: vips_embed(EXTEND_COPY) = clamp */
-	for (int j = t; j < P.Wse; j += 256) {
+	/* ---- shrinkh (FSHRINK, shrinkh.c:134-152) over the embedded row: vips_embed(EXTEND_COPY) = clamp.
+	 * One (column, band) per thread straight from the intermediate image: the NCH lanes of a column read
+	 * NCH consecutive floats, a warp covers 32 / NCH boxes, and over the HS steps of the box every sector is
+	 * used in full -- no staging of the 64 KB row, so many CTAs fit an SM and hide the loads' latency.
+	 */
+	__syncthreads();
+	for (int i = t; i < P.Wse * NCH; i += 256) {
+		const int j = NCH == 4 ? i >> 2 : i / NCH, c = i - j * NCH;
 		const int sc = max(0, min(j - P.hembed, P.Ws - 1));
-		double sum[NCH];
-#pragma unroll
-		for (int c = 0; c < NCH; c++)
-			sum[c] = 0.0;
-		for (int k = 0; k < P.HS; k++) {
-			const int colx = min(sc * P.HS + k, P.W - 1);
-			if (NCH == 4) {
-				const float4 v = __ldg((const float4 *) row + colx);
-				sum[0] = __dadd_rn(sum[0], (double) v.x);
-				sum[1] = __dadd_rn(sum[1], (double) v.y);
-				sum[2] = __dadd_rn(sum[2], (double) v.z);
-				sum[NCH - 1] = __dadd_rn(sum[NCH - 1], (double) v.w);
-			}
-			else {
-#pragma unroll
-				for (int c = 0; c < NCH; c++)
-					sum[c] = __dadd_rn(sum[c], (double) __ldg(row + (size_t) colx * NCH + c));
-			}
-		}
-#pragma unroll
-		for (int c = 0; c < NCH; c++)
-			s_shr[j * NCH + c] = (float) __dmul_rn(sum[c], P.inv_h);
+		double sum = 0.0;
+		for (int k = 0; k < P.HS; k++)
+			sum = __dadd_rn(sum, (double) __ldg(row + (size_t) min(sc * P.HS + k, P.W - 1) * NCH + c));
+		s_shr[i] = (float) __dmul_rn(sum, P.inv_h);
 	}
 	__syncthreads();
 
-	/* ---- reduceh, unpremultiply, scRGB -> sRGB */
+	/* ---- reduceh (reduceh.cpp:182-193): one (pixel, band) per thread */
+	for (int i = t; i < P.OW * NCH; i += 256) {
+		const int x = NCH == 4 ? i >> 2 : i / NCH, c = i - x * NCH;
+		const float *win = s_shr + __ldg(P.hfirst + x) * NCH + c;
+		const double *cf = s_hc + __ldg(P.hphase + x) * P.nh;
+		double sum = 0.0;
+		for (int k = 0; k < P.nh; k++)
+			sum = __dadd_rn(sum, __dmul_rn(cf[k], (double) win[k * NCH]));
+		s_row[i] = (float) sum;
+	}
+	__syncthreads();
+
+	/* ---- unpremultiply, scRGB -> sRGB: one pixel per thread */
 	uint8_t *orow = out + (size_t) frame * P.out_frame_stride + (size_t) y * P.out_bpl;
 	for (int x = t; x < P.OW; x += 256) {
-		const int first = __ldg(P.hfirst + x);
-		const double *cf = s_hc + __ldg(P.hphase + x) * P.nh;
 		float v[NCH];
 #pragma unroll
-		for (int c = 0; c < NCH; c++) {
-			double sum = 0.0;
-			for (int i = 0; i < P.nh; i++)
-				sum = __dadd_rn(sum, __dmul_rn(cf[i], (double) s_shr[(first + i) * NCH + c]));
-			v[c] = (float) sum;
-		}
+		for (int c = 0; c < NCH; c++)
+			v[c] = s_row[x * NCH + c];
 		if (PREMUL) {
 			/* FUNPRE_RGBA with max_alpha 1.0, unpremultiply.c:160-176 */
 			const float alpha = v[NCH - 1];
@@ -333,6 +474,7 @@ struct LinearThumb {
 	void *tables = nullptr;
 	size_t smem_v = 0, smem_h = 0;
 	int vst = 0;
+	bool static2 = false; /* linear_v2_kernel: residual exactly 2.0, 13 taps, one phase */
 };
 
 /* 0 = ready, 1 = this geometry is not on the two-kernel path (the caller chains the leaf kernels), -1 = error */
@@ -360,8 +502,9 @@ linear_thumb_new(const char *domain, int W, int H, int bands, bool premul, const
 	int wse = 0;
 	for (int x = 0; x < OW; x++)
 		wse = std::max(wse, th.first[x] + gh.n_point);
-	const size_t smem_v = (size_t) 65 * gv.n_point * 8 + 3 * 256 * 4 + (size_t) (kDepth + 1) * kMaxBox * kVThreads * 4;
-	const size_t smem_h = (size_t) 65 * gh.n_point * 8 + 260 * 4 + (size_t) wse * bands * 4;
+	const size_t smem_v = (size_t) 65 * gv.n_point * 8 + 4 * 256 * 4 + (size_t) (kDepth + 1) * kMaxBox * kVThreads * 4;
+	const size_t smem_h = (size_t) 65 * gh.n_point * 8 + 260 * 4 + (size_t) ((wse * bands + 3) & ~3) * 4 +
+		(size_t) ((OW * bands + 3) & ~3) * 4;
 	if (smem_v > 100 * 1024 || smem_h > 200 * 1024)
 		return 1;
 
@@ -419,6 +562,16 @@ linear_thumb_new(const char *domain, int W, int H, int bands, bool premul, const
 	memcpy(v.fwd, fwd.steps, sizeof(v.fwd));
 	v.n_fwd = fwd.n_steps;
 	v.v2Y_8 = fwd.t.v2Y_8;
+	/* the static schedule: every window two box-shrunk rows after the last, one set of 13 coefficients */
+	lt->static2 = bands == 4 && lt->vst != 0 && gv.n_point == 13 && getenv("VB200_NO_LINEAR_STATIC") == nullptr;
+	for (int y = 0; y < OH && lt->static2; y++)
+		if (tv.first[y] != tv.first[0] + 2 * y || tv.phase[y] != tv.phase[0])
+			lt->static2 = false;
+	if (lt->static2) {
+		v.f0 = tv.first[0];
+		for (int i = 0; i < 13; i++)
+			v.c2[i] = tv.mf[(size_t) tv.phase[0] * 13 + i];
+	}
 
 	LinHParams &h = lt->h;
 	h.W = W;
@@ -473,6 +626,33 @@ launch_v(const char *domain, const LinearThumb *lt, const LinVParams &v, const v
 	return 0;
 }
 
+int
+launch_v2(const char *domain, const LinearThumb *lt, const LinVParams &v, const void *in, dim3 grid, cudaStream_t s)
+{
+#define LV2(PM_, VST_) \
+	do { \
+		auto kern = linear_v2_kernel<PM_, VST_>; \
+		VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt->smem_v)); \
+		kern<<<grid, kVThreads, lt->smem_v, s>>>(v, (const uint8_t *) in, 0); \
+	} while (0)
+	if (lt->premul) {
+		switch (lt->vst) {
+		case 2: LV2(true, 2); break;
+		case 4: LV2(true, 4); break;
+		default: LV2(true, 8); break;
+		}
+	}
+	else {
+		switch (lt->vst) {
+		case 2: LV2(false, 2); break;
+		case 4: LV2(false, 4); break;
+		default: LV2(false, 8); break;
+		}
+	}
+#undef LV2
+	return 0;
+}
+
 } // namespace
 
 /* frames: packed uchar, `bands` per pixel; queued on s.  The float intermediate ([OH][W][bands] per frame)
@@ -489,8 +669,8 @@ linear_thumb_run(const char *domain, LinearThumb *lt, const void *in, size_t in_
 		return -1;
 	}
 	const size_t mid_frame = (size_t) lt->OH * lt->W * lt->bands; /* floats */
-	/* sub-batches keep the scratch near 1 GiB (33.5 MB per 4K frame) and, at small sizes, inside L2 */
-	const int sub = (int) std::max<size_t>(1, std::min<size_t>((size_t) n, ((size_t) 1 << 30) / (mid_frame * 4)));
+	/* sub-batches keep the scratch near 2 GiB (33.5 MB per 4K frame) and, at small sizes, inside L2 */
+	const int sub = (int) std::max<size_t>(1, std::min<size_t>((size_t) n, ((size_t) 2 << 30) / (mid_frame * 4)));
 	float *mid = nullptr;
 	if (dev_alloc(domain, (void **) &mid, mid_frame * 4 * sub, s))
 		return -1;
@@ -509,7 +689,9 @@ linear_thumb_run(const char *domain, LinearThumb *lt, const void *in, size_t in_
 		v.RPC = (lt->OH + splits - 1) / splits;
 		const dim3 gv(col_blocks, (lt->OH + v.RPC - 1) / v.RPC, nf);
 		const char *fin = (const char *) in + (size_t) f0 * in_stride;
-		if (lt->bands == 4)
+		if (lt->static2)
+			rc = launch_v2(domain, lt, v, fin, gv, s);
+		else if (lt->bands == 4)
 			rc = lt->premul ? launch_v<4, true>(domain, lt, v, fin, gv, 0, s) : launch_v<4, false>(domain, lt, v, fin, gv, 0, s);
 		else
 			rc = launch_v<3, false>(domain, lt, v, fin, gv, 0, s);

@@ -134,6 +134,19 @@ bool image_hasalpha(int type, int bands);
 int dev_resize_up(const char *domain, const DevImage &in, DevImage *out, double hscale, double vscale, int kernel,
 	cudaStream_t s);
 
+/* conv.cu */
+int dev_conv(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, double scale,
+	double offset, int precision, cudaStream_t s, bool allow_vector);
+int dev_convsep(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, double scale,
+	double offset, int precision, cudaStream_t s, bool allow_vector);
+int dev_gaussblur(const char *domain, const DevImage &in, DevImage *out, double sigma, double min_ampl, int precision,
+	cudaStream_t s);
+int dev_sharpen(const char *domain, const DevImage &in, DevImage *out, double sigma, double x1, double y2, double y3,
+	double m1, double m2, cudaStream_t s);
+
+/* morph.cu */
+int dev_morph(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, int op, cudaStream_t s);
+
 /* colour.cu */
 int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space,
 	cudaStream_t s);

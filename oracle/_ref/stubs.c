@@ -1,7 +1,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 void vips_call_split(void) { fputs("ref shim: vips_call_split() is not available", stderr); abort(); }
-void vips_cast(void) { fputs("ref shim: vips_cast() is not available", stderr); abort(); }
 void vips_colour_code_get_type(void) { fputs("ref shim: vips_colour_code_get_type() is not available", stderr); abort(); }
 void vips_colour_transform_get_type(void) { fputs("ref shim: vips_colour_transform_get_type() is not available", stderr); abort(); }
 void vips_conva(void) { fputs("ref shim: vips_conva() is not available", stderr); abort(); }

@@ -311,7 +311,117 @@ LabS2Lab_line(const int16_t *p, float *q, size_t n)
 /* ----------------------------------------------------------------- steps */
 
 enum { S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
-	S_scRGB2RGB16, S_RGB162scRGB };
+	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ };
+
+/* ---- the next VipsColour converters: Lab <-> LCh, XYZ <-> Yxy */
+
+/* vips_col_ab2h, Lab2LCh.c:61-89 */
+static double
+col_ab2h(double a, double b)
+{
+	const double PI = 3.14159265358979323846;
+	double h;
+	if (a == 0) {
+		if (b < 0.0)
+			h = 270;
+		else if (b == 0.0)
+			h = 0;
+		else
+			h = 90;
+	}
+	else {
+		double t = atan(b / a);
+		if (a > 0.0)
+			if (b < 0.0)
+				h = ((t + PI * 2.0) / (2.0 * PI)) * 360.0;
+			else
+				h = (t / (2.0 * PI)) * 360.0;
+		else
+			h = ((t + PI) / (2.0 * PI)) * 360.0;
+	}
+	return h;
+}
+
+/* vips_Lab2LCh_line, Lab2LCh.c:98-124 */
+static void
+Lab2LCh_line(const float *p, float *q, size_t n)
+{
+	for (size_t x = 0; x < n; x++) {
+		float L = p[0], a = p[1], b = p[2];
+		float C = sqrtf(a * a + b * b);
+		float h = col_ab2h(a, b);
+		q[0] = L;
+		q[1] = C;
+		q[2] = h;
+		p += 3;
+		q += 3;
+	}
+}
+
+/* vips_LCh2Lab_line + vips_col_Ch2ab, LCh2Lab.c:70-103 */
+static void
+LCh2Lab_line(const float *p, float *q, size_t n)
+{
+	const double PI = 3.14159265358979323846;
+	for (size_t x = 0; x < n; x++) {
+		float L = p[0], C = p[1], h = p[2];
+		float a = C * cosf(((h) / 360.0) * 2.0 * PI);
+		float b = C * sinf(((h) / 360.0) * 2.0 * PI);
+		q[0] = L;
+		q[1] = a;
+		q[2] = b;
+		p += 3;
+		q += 3;
+	}
+}
+
+/* vips_XYZ2Yxy_line, XYZ2Yxy.c:57-88 */
+static void
+XYZ2Yxy_line(const float *p, float *q, size_t n)
+{
+	for (size_t i = 0; i < n; i++) {
+		float X = p[0], Y = p[1], Z = p[2];
+		double total = X + Y + Z;
+		float x, y;
+		if (total == 0.0) {
+			x = 0;
+			y = 0;
+		}
+		else {
+			x = X / total;
+			y = Y / total;
+		}
+		q[0] = Y;
+		q[1] = x;
+		q[2] = y;
+		p += 3;
+		q += 3;
+	}
+}
+
+/* vips_Yxy2XYZ_line, Yxy2XYZ.c:59-93 */
+static void
+Yxy2XYZ_line(const float *p, float *q, size_t n)
+{
+	for (size_t i = 0; i < n; i++) {
+		float Y = p[0], x = p[1], y = p[2];
+		float X, Z;
+		if (x == 0.0 || y == 0.0) {
+			X = 0.0F;
+			Z = 0.0F;
+		}
+		else {
+			float total = Y / y;
+			X = x * total;
+			Z = (X - x * X - x * Y) / x;
+		}
+		q[0] = X;
+		q[1] = Y;
+		q[2] = Z;
+		p += 3;
+		q += 3;
+	}
+}
 
 struct Img {
 	int w = 0, h = 0, bands = 0, fmt = 0, type = 0;
@@ -384,6 +494,10 @@ run_step(int step, const Img &in, Img &out)
 	case S_XYZ2scRGB: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 28; break;
 	case S_scRGB2sRGB: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_UCHAR; out_type = 22; break;
 	case S_scRGB2RGB16: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_USHORT; out_type = 25; break;
+	case S_Lab2LCh: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 19; break;
+	case S_LCh2Lab: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 13; break;
+	case S_XYZ2Yxy: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 23; break;
+	case S_Yxy2XYZ: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 12; break;
 	default: return -1;
 	}
 	if (in.bands < 3)
@@ -425,6 +539,10 @@ run_step(int step, const Img &in, Img &out)
 	case S_XYZ2scRGB: XYZ2scRGB_line((const float *) rgb.data(), (float *) res.data(), n); break;
 	case S_scRGB2sRGB: scRGB2sRGB_line((const float *) rgb.data(), res.data(), 8, n); break;
 	case S_scRGB2RGB16: scRGB2sRGB_line((const float *) rgb.data(), res.data(), 16, n); break;
+	case S_Lab2LCh: Lab2LCh_line((const float *) rgb.data(), (float *) res.data(), n); break;
+	case S_LCh2Lab: LCh2Lab_line((const float *) rgb.data(), (float *) res.data(), n); break;
+	case S_XYZ2Yxy: XYZ2Yxy_line((const float *) rgb.data(), (float *) res.data(), n); break;
+	case S_Yxy2XYZ: Yxy2XYZ_line((const float *) rgb.data(), (float *) res.data(), n); break;
 	}
 
 	out.w = in.w;
@@ -465,12 +583,30 @@ run_step(int step, const Img &in, Img &out)
 static int
 route_for(int from, int to, int steps[8])
 {
-	enum { XYZ = 12, LAB = 13, LABS = 21, sRGB = 22, RGB16 = 25, scRGB = 28 };
+	enum { XYZ = 12, LAB = 13, LCH = 19, LABS = 21, sRGB = 22, YXY = 23, RGB16 = 25, scRGB = 28 };
 	int n = 0;
 	auto push = [&](std::initializer_list<int> l) { for (int s : l) steps[n++] = s; };
 	if (from == to)
 		return 0;
+	/* LCH hangs off LAB and YXY off XYZ in every row of the table (colourspace.c:226, 236, 242, 252, 275-290 ...):
+	 * route to the hub, then one more step
+	 */
+	if (to == LCH || to == YXY) {
+		const int hub = to == LCH ? LAB : XYZ;
+		int m = 0;
+		if (from != hub) {
+			m = route_for(from, hub, steps);
+			if (m < 0)
+				return -1;
+		}
+		steps[m++] = to == LCH ? S_Lab2LCh : S_XYZ2Yxy;
+		return m;
+	}
 	/* everything goes up to a hub and down again, exactly as the table rows spell out */
+	switch (from) {
+	case LCH: push({ S_LCh2Lab }); from = LAB; break;
+	case YXY: push({ S_Yxy2XYZ }); from = XYZ; break;
+	}
 	switch (from) {
 	case sRGB: push({ S_sRGB2scRGB }); from = scRGB; break;
 	case RGB16: push({ S_RGB162scRGB }); from = scRGB; break;

@@ -175,3 +175,29 @@ def sharpen_lut(x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
     lut = np.zeros(65536, np.int32)
     L.orc_sharpen_lut(x1, y2, y3, m1, m2, lut.ctypes.data)
     return lut
+
+
+# ------------------------------------------------------------------ morphology
+def morph(a, mask, op):
+    """vips_morph, oracle restatement (uchar images; op "erode" / "dilate")"""
+    a, h, w, b, f = pyoracle._img(a)
+    assert a.dtype == np.uint8
+    mask = np.ascontiguousarray(mask, np.float64)
+    out = np.empty_like(a)
+    L = pyoracle.lib()
+    L.orc_morph.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    if L.orc_morph(a.ctypes.data, w, h, b, mask.ctypes.data, mask.shape[1], mask.shape[0], {"erode": 0, "dilate": 1}[op],
+                   out.ctypes.data):
+        raise ValueError("morph: bad mask element")
+    return out
+
+
+def ref_morph(a, mask, op, tile=(0, 0)):
+    """vips_morph through the reference's own morph.c (C generate functions)"""
+    L = _rl()
+    L.ref_morph.restype = C.c_void_p
+    L.ref_morph.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    mask = np.ascontiguousarray(mask, np.float64)
+    m = L.ref_matrix(mask.ctypes.data, mask.shape[1], mask.shape[0], 1.0, 0.0)
+    im = pyref.RefImage.from_array(a)
+    return pyref.RefImage(L.ref_morph(im.h, m, {"erode": 0, "dilate": 1}[op]), (im, mask)).numpy(tile)

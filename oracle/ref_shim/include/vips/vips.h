@@ -33,6 +33,8 @@ typedef char gchar;
 typedef int gint;
 typedef unsigned int guint;
 typedef unsigned char guchar;
+typedef unsigned char guint8;
+typedef signed char gint8;
 typedef long long gint64;
 typedef unsigned long long guint64;
 typedef int gint32;
@@ -84,6 +86,8 @@ typedef unsigned char VipsPel;
 #define VIPS_RINT(V) rint(V)
 #define VIPS_FLOOR(V) floor(V)
 #define VIPS_CEIL(V) ceil(V)
+#define VIPS_RAD(R) (((R) / 360.0) * 2.0 * VIPS_PI) /* include/vips/util.h:50-51 */
+#define VIPS_DEG(A) (((A) / (2.0 * VIPS_PI)) * 360.0)
 #define VIPS_ROUND_UINT(R) ((int) ((R) + 0.5))
 #define VIPS_ROUND_DOWN(N, P) ((N) - ((N) % (P)))
 #define VIPS_ROUND_UP(N, P) (VIPS_ROUND_DOWN((N) + (P) -1, (P)))

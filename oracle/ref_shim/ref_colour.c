@@ -10,6 +10,10 @@
 #include "scRGB2sRGB.c"
 #include "Lab2LabS.c"
 #include "LabS2Lab.c"
+#include "Lab2LCh.c"
+#include "LCh2Lab.c"
+#include "XYZ2Yxy.c"
+#include "Yxy2XYZ.c"
 
 /* step numbers as in oracle/colour_oracle.cpp */
 int
@@ -77,6 +81,30 @@ ref_colour_line(int step, const void *in, void *out, int n)
 		memset(&obj, 0, sizeof(obj));
 		obj.depth = step == 8 ? 8 : 16;
 		vips_scRGB2sRGB_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 11: {
+		VipsLab2LCh obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_Lab2LCh_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 12: {
+		VipsLCh2Lab obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_LCh2Lab_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 13: {
+		VipsXYZ2Yxy obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_XYZ2Yxy_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 14: {
+		VipsYxy2XYZ obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_Yxy2XYZ_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
 		return 0;
 	}
 	}

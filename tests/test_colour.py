@@ -141,3 +141,92 @@ def test_gpu_srgb_lab_round_trip_full_gamut(vb):
     back = lab.colourspace("srgb").numpy()
     assert np.array_equal(back, a)
     assert np.array_equal(lab.numpy()[:64], orc.colourspace(a[:64], "lab", "srgb"))
+
+
+# ------------------------------------------------------------------ Lab <-> LCh, XYZ <-> Yxy
+NEW_STEPS = [("Lab2LCh", "lab"), ("LCh2Lab", "lch"), ("XYZ2Yxy", "xyz"), ("Yxy2XYZ", "yxy")]
+
+
+def sample_new(space, rng, n=20000):
+    if space == "lch":
+        a = rng.random((n, 3), dtype=np.float32)
+        a[:, 0] *= 100
+        a[:, 1] *= 130
+        a[:, 2] *= 360
+        return a
+    if space == "yxy":
+        a = rng.random((n, 3), dtype=np.float32)
+        a[:, 0] *= 100
+        a[::50, 1] = 0
+        a[::70, 2] = 0
+        return a
+    a = sample(space, rng, n)
+    if space == "lab":
+        a[::40, 1] = 0          # the hue's quadrant cases (Lab2LCh.c:68-75)
+        a[::80, 2] = 0
+    if space == "xyz":
+        a[::60] = 0             # total == 0 (XYZ2Yxy.c:74-77)
+    return a
+
+
+@needs_ref
+@pytest.mark.parametrize("step,space", NEW_STEPS)
+def test_oracle_new_converters_match_reference_lines(step, space):
+    """the reference's own Lab2LCh.c / LCh2Lab.c / XYZ2Yxy.c / Yxy2XYZ.c under oracle/_ref (same glibc: bit for bit)"""
+    a = sample_new(space, np.random.default_rng(17))
+    want = pyref.colour_line(step, a)
+    got = orc.colour_step(a.reshape(1, -1, 3), step, space).reshape(-1, 3)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_new_spaces_routes_follow_the_table():
+    """colourspace.c:226, 236, 242, 252, 275-290: LCH hangs off LAB, YXY off XYZ"""
+    L = orc.lib()
+    import ctypes as C
+    steps = (C.c_int * 8)()
+    name = {v: k for k, v in orc.STEPS.items()}
+    rows = {("srgb", "lch"): ["sRGB2scRGB", "scRGB2XYZ", "XYZ2Lab", "Lab2LCh"], ("lch", "srgb"): ["LCh2Lab", "Lab2XYZ", "XYZ2scRGB", "scRGB2sRGB"],
+            ("lab", "yxy"): ["Lab2XYZ", "XYZ2Yxy"], ("yxy", "lch"): ["Yxy2XYZ", "XYZ2Lab", "Lab2LCh"], ("labs", "lch"): ["LabS2Lab", "Lab2LCh"],
+            ("lch", "labs"): ["LCh2Lab", "Lab2LabS"], ("xyz", "lch"): ["XYZ2Lab", "Lab2LCh"], ("lch", "yxy"): ["LCh2Lab", "Lab2XYZ", "XYZ2Yxy"]}
+    for (a, b), want in rows.items():
+        n = L.orc_colourspace_route(orc.SPACES[a], orc.SPACES[b], steps)
+        assert [name[steps[i]] for i in range(n)] == want, (a, b)
+
+
+def ulp_diff(a, b):
+    """distance in float32 ULPs (both finite, same sign or zero)"""
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7fffffff), ia)
+    ib = np.where(ib < 0, -(ib & 0x7fffffff), ib)
+    return np.abs(ia - ib)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src,dst", [("xyz", "yxy"), ("yxy", "xyz"), ("srgb", "yxy"), ("yxy", "srgb"), ("yxy", "lab"), ("rgb16", "yxy")])
+def test_gpu_yxy_routes_exact(vb, src, dst):
+    rng = np.random.default_rng(21)
+    a = (sample_new(src, rng, 64 * 129) if src in ("yxy", "xyz") else sample(src, rng, 64 * 129)).reshape(64, 129, 3)
+    got = vb.Image(a, src).colourspace(dst).numpy()
+    want = orc.colourspace(a, dst, src)
+    assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (src, dst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src,dst", [("lab", "lch"), ("lch", "lab"), ("srgb", "lch"), ("lch", "srgb"), ("lch", "yxy"), ("labs", "lch")])
+def test_gpu_lch_routes_within_one_ulp(vb, src, dst):
+    """atan / cosf / sinf: CUDA's libm against the reference's glibc -- float results within 1 ULP (cos / sin: 2), the
+    tolerance north_star sets for the float colour path; integer outputs within 1 code"""
+    rng = np.random.default_rng(22)
+    a = (sample_new(src, rng, 64 * 129) if src in ("lch", "lab") else sample(src, rng, 64 * 129)).reshape(64, 129, 3)
+    got = vb.Image(a, src).colourspace(dst).numpy()
+    want = orc.colourspace(a, dst, src)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if want.dtype == np.float32:
+        # an angle near 0 / 360 or a cosine near 0 makes "ULP" meaningless: compare with an absolute floor
+        d = np.abs(got.astype(np.float64) - want)
+        ok = (ulp_diff(got, want) <= (2 if src == "lch" else 1)) | (d < 2e-5)
+        assert ok.all(), (src, dst, d.max())
+        assert (got == want).mean() > 0.99
+    else:
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= 1

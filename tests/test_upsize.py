@@ -88,3 +88,14 @@ def test_gpu_zoom(vb, dt):
         assert np.array_equal(got, want)
         if vs > 1.0 or hs > 1.0:
             assert np.array_equal(orc.resize(a, hs, vs, kernel="nearest"), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sc,vs", [(2.0, None), (3.7, 1.2), (1.0, 2.0), (1.25, 1.01), (4.0, 4.0)])
+def test_gpu_separable_bicubic_rgba(vb, sc, vs):
+    """the shared-memory separable form of the uchar RGBA bicubic upsize over many 64 x 32 tiles, ragged edges"""
+    rng = np.random.default_rng(31)
+    a = rnd(rng, np.uint8, (203, 317, 4))
+    got = vb.Image(a).resize(sc, vs, kernel="cubic").numpy()
+    want = orc.resize(a, sc, vs, kernel="cubic")
+    assert got.shape == want.shape and np.array_equal(got, want)
