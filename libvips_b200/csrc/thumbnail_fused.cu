@@ -1436,6 +1436,8 @@ struct ThumbnailPlanImpl {
 	int stage_frames = 0;
 	std::mutex pump_lock;
 	std::mutex launch_lock;
+	/* 3-band frames (what a JPEG decodes to) on the fused RGBA kernels: expanded to RGBX on the device */
+	bool rgb_expand = false;
 	/* linear = TRUE: the two-kernel linear-light path (thumbnail_linear.cu), or null = the leaf chain */
 	LinearThumb *lin = nullptr;
 	/* vips_sharpen appended to every batch (vb200_thumbnail_plan_set_sharpen) */
@@ -1656,6 +1658,14 @@ launch_mma_w(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, c
 	V4(4, 6, 4) V4(4, 7, 4) V4(2, 6, 2) V4(2, 7, 2)
 	V4(4, 0, 4) V4(2, 0, 2) V4(4, 0, 2) V4(2, 0, 4) V4(4, 0, 8) V4(2, 0, 8)
 	V4(8, 6, 8) V4(8, 7, 8) V4(8, 0, 8) V4(8, 0, 4)
+	/* boxes that are not powers of two: the pairs a uniform shrink produces (the two axes' boxes differ by at
+	 * most one), run-time tap counts, two columns per thread
+	 */
+	if constexpr (CPT == 2 && WCOLS > 448) {
+		V4(3, 0, 3) V4(5, 0, 5) V4(6, 0, 6) V4(7, 0, 7)
+		V4(2, 0, 3) V4(3, 0, 2) V4(3, 0, 4) V4(4, 0, 3) V4(4, 0, 5) V4(5, 0, 4) V4(5, 0, 6) V4(6, 0, 5)
+		V4(6, 0, 7) V4(7, 0, 6) V4(7, 0, 8) V4(8, 0, 7)
+	}
 #undef V4
 	*handled = false;
 	return 0;
@@ -1919,8 +1929,13 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	/* v4: reducev as u8 x s8 MMAs over a ring of 8 quads (32 box-shrunk rows) per 8 output rows */
 	pl->mma_ok = false;
 	/* (not gated on tma_ok: the older TMA kernels' shared-memory bound fails for box 8, this kernel's does not) */
-	if ((fp.in_bpl % 16) == 0 && fp.max_alpha == 255.0 && getenv("VB200_NO_TMA") == nullptr &&
-		(fp.VS == 2 || fp.VS == 4 || fp.VS == 8) && (fp.HS == 2 || fp.HS == 4 || fp.HS == 8) &&
+	const bool vpow2 = fp.VS == 2 || fp.VS == 4 || fp.VS == 8, hpow2 = fp.HS == 2 || fp.HS == 4 || fp.HS == 8;
+	/* the (VS, HS) corners launch_mma_w instantiates: powers of two freely mixed; otherwise boxes 2 .. 8 that
+	 * differ by at most one (what a uniform shrink gives)
+	 */
+	const bool mma_pair = (vpow2 && hpow2) ||
+		(fp.VS >= 2 && fp.VS <= 8 && fp.HS >= 2 && fp.HS <= 8 && abs(fp.VS - fp.HS) <= 1 && getenv("VB200_NO_MMA_NPOT") == nullptr);
+	if ((fp.in_bpl % 16) == 0 && fp.max_alpha == 255.0 && getenv("VB200_NO_TMA") == nullptr && mma_pair &&
 		getenv("VB200_NO_MMA") == nullptr) {
 		std::vector<int> vchunk_flat;
 		std::vector<unsigned> bfrag_flat;
@@ -1936,7 +1951,11 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		}
 		/* band width: the fewest bands whose widest one fits the column budget */
 		const char *ev = getenv("VB200_V4_COLS");
-		const int wcols = ev && atoi(ev) <= 448 ? VB200_V4_COLS : 768; /* 768 (default): one CTA per SM, two columns per thread */
+		const int wcols = ev && atoi(ev) <= 448 && vpow2 && hpow2 ? VB200_V4_COLS : 768; /* 768 (default): one CTA per SM, two columns per thread */
+		/* logical columns a V warp covers: 64, or 2 * floor(32 / HS) * HS when the horizontal box is not a
+		 * power of two (V4Group in thumbnail_fused_mma.cuh)
+		 */
+		const int warp_cols = hpow2 ? 0 : 2 * (32 / fp.HS) * fp.HS;
 		pl->mma_cpt = wcols > 448 || (getenv("VB200_V4_CPT") && atoi(getenv("VB200_V4_CPT")) == 2) ? 2 : 1; /* columns per V thread */
 		const int pitch = (wcols + 8) * 4;
 		auto column_of = [&](int E0, int tt) {
@@ -1950,7 +1969,8 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 		 */
 		int tw4 = 0, nemax4 = 0;
 		long best_cost = LONG_MAX;
-		const int cols_per_warp = 32 * pl->mma_cpt;
+		const int cols_per_warp = warp_cols ? warp_cols : 32 * pl->mma_cpt;
+		const int col_budget = warp_cols ? (wcols / 64) * warp_cols : wcols;
 		for (int tw = std::min(pl->OW, 256); tw >= 2 && ok; tw--) {
 			int worst = 0, max_cols = 0;
 			long cost = 0;
@@ -1964,7 +1984,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 				max_cols = std::max(max_cols, c_hi - c_lo);
 				cost += (ne * fp.HS + cols_per_warp - 1) / cols_per_warp + 1; /* + the H / P warps' share */
 			}
-			if (worst * fp.HS <= wcols && max_cols * 4 <= pitch && cost < best_cost) {
+			if (worst * fp.HS <= col_budget && max_cols * 4 <= pitch && cost < best_cost) {
 				best_cost = cost;
 				tw4 = tw;
 				nemax4 = worst;
@@ -1974,13 +1994,16 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 			pl->mma_cols = wcols;
 			pl->mma_tw = tw4;
 			pl->mma_nemax = nemax4;
-			pl->mma_nt = std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
-			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES : (fp.VS >= 8 ? VB200_V4_STAGES / 2 : VB200_V4_STAGES);
+			pl->mma_nt = warp_cols ? std::max(64, ((nemax4 * fp.HS + warp_cols - 1) / warp_cols) * 32)
+								   : std::max(64, ((nemax4 * fp.HS / pl->mma_cpt + 31) / 32) * 32);
+			const int stages = fp.VS <= 2 ? 2 * VB200_V4_STAGES
+				: (fp.VS >= 7 ? VB200_V4_STAGES / 2 : (fp.VS >= 5 ? (3 * VB200_V4_STAGES) / 4 : VB200_V4_STAGES));
+			const int logical_cols = warp_cols ? (pl->mma_nt / 32) * warp_cols : pl->mma_nt * pl->mma_cpt;
 			const int nbox = wcols + 8 > 512 ? 2 : 1;
 			const size_t box_bytes = ((size_t) 2 * fp.VS * (pitch / nbox) + 127) & ~(size_t) 127;
 			pl->smem_mma = (size_t) stages * nbox * box_bytes + (2 * stages + 4) * 8 +
 				(size_t) kV4Quads * ((size_t) pl->mma_nt * pl->mma_cpt * 16 + 16) +
-				(size_t) 2 * kV4Rows * (pl->mma_nt * pl->mma_cpt / fp.HS / 2) * 8 +
+				(size_t) 2 * kV4Rows * ((logical_cols / fp.HS + 1) / 2) * 8 +
 				(size_t) (fp.nhsets * fp.NPh + 256) * 4;
 			const size_t n_ch = vchunk.size() * sizeof(int2), n_bf = bfrag.size() * sizeof(uint4);
 			if (pl->smem_mma <= (wcols > 448 ? 226 : 113) * 1024) {
@@ -2012,6 +2035,40 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 
 	pl->grid = dim3((pl->OW + TW - 1) / TW, (pl->OH + fp.RPC - 1) / fp.RPC, 1);
 	return 0;
+}
+
+} // namespace
+
+namespace {
+
+/* packed RGB -> RGBX (X = 255) and back: four pixels (three words <-> four words) per thread */
+__global__ void __launch_bounds__(256)
+rgb_expand_kernel(const uint8_t *__restrict__ in, size_t in_stride, uint8_t *__restrict__ out, size_t out_stride, size_t quads)
+{
+	const size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= quads)
+		return;
+	const unsigned *p = (const unsigned *) (in + (size_t) blockIdx.y * in_stride) + q * 3;
+	const unsigned w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+	uint4 o;
+	o.x = (w0 & 0x00ffffffu) | 0xff000000u;
+	o.y = (w0 >> 24) | ((w1 & 0xffffu) << 8) | 0xff000000u;
+	o.z = (w1 >> 16) | ((w2 & 0xffu) << 16) | 0xff000000u;
+	o.w = (w2 >> 8) | 0xff000000u;
+	((uint4 *) (out + (size_t) blockIdx.y * out_stride))[q] = o;
+}
+
+__global__ void __launch_bounds__(256)
+rgbx_compact_kernel(const uint8_t *__restrict__ in, size_t in_stride, uint8_t *__restrict__ out, size_t out_stride, size_t pixels)
+{
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= pixels)
+		return;
+	const unsigned px = __ldg((const unsigned *) (in + (size_t) blockIdx.y * in_stride) + i);
+	uint8_t *q = out + (size_t) blockIdx.y * out_stride + i * 3;
+	q[0] = (uint8_t) px;
+	q[1] = (uint8_t) (px >> 8);
+	q[2] = (uint8_t) (px >> 16);
 }
 
 } // namespace
@@ -2073,16 +2130,25 @@ thumbnail_plan_init(const char *domain, ThumbnailPlanImpl *pl)
 		pl->fused = pl->lin != nullptr;
 		return 0;
 	}
-	if (pl->bands == 4 && pl->gv.n_point > 0 && pl->gh.n_point > 0) {
+	/* 3-band 8-bit frames: the channels of the uchar chain never mix without a premultiply, so RGB through the RGBA
+	 * kernels (X = 255, no premultiply) gives the reference's RGB bytes; needs frames whose pixel count is a
+	 * multiple of four (word-wise expansion)
+	 */
+	pl->rgb_expand = pl->bands == 3 && ((size_t) pl->W * pl->H) % 4 == 0 && getenv("VB200_NO_RGB_EXPAND") == nullptr;
+	if ((pl->bands == 4 || pl->rgb_expand) && pl->gv.n_point > 0 && pl->gh.n_point > 0) {
 		int r = plan_build_fused(domain, pl);
 		if (r < 0)
 			return -1;
 		pl->fused = r == 0;
 	}
+	if (!pl->fused)
+		pl->rgb_expand = false;
 	return 0;
 }
 
 static int thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s);
+static int thumbnail_plan_run_fused(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, cudaStream_t s);
 
 int
@@ -2168,28 +2234,40 @@ thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const vo
 				return -1;
 		return 0;
 	}
-	if (pl->fused) {
-		/* the TMA-fed kernel when rows, frames and the base pointer are 16-byte aligned */
-		if ((pl->tma_ok || pl->mma_ok) && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0)) {
-			bool handled = true;
-			const int rc = launch_tma(domain, pl, in, in_stride, out, out_stride, n, s, &handled);
-			if (handled)
-				return rc;
+	if (pl->fused && pl->rgb_expand && pl->bands == 3) {
+		/* sub-batches of RGBX scratch (~1 GiB): expand, fused kernel, compact */
+		if ((((uintptr_t) in) | in_stride) & 3) {
+			error(domain, "RGB frames must be 4-byte aligned for the fused path");
+			return -1;
 		}
-		/* enough CTAs to fill the machine: split rows when the batch is small.  This (fallback) path
-		 * writes the per-launch geometry into the plan: serialise concurrent callers of one plan
-		 */
-		std::lock_guard<std::mutex> launch_lock(pl->launch_lock);
-		FusedParams &fp = pl->fp;
-		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
-		int rpc = ((pl->OH + kChunkRows - 1) / kChunkRows) * kChunkRows;
-		while ((long long) bands_x * ((pl->OH + rpc - 1) / rpc) * n < 2 * 148 && rpc > 2 * kChunkRows)
-			rpc = ((rpc / 2 + kChunkRows - 1) / kChunkRows) * kChunkRows;
-		fp.RPC = rpc;
-		pl->grid = dim3(bands_x, (pl->OH + rpc - 1) / rpc, 1);
-		return pl->premul ? launch_fused_vs<true>(domain, pl, in, in_stride, out, out_stride, n, s)
-						  : launch_fused_vs<false>(domain, pl, in, in_stride, out, out_stride, n, s);
+		const size_t px_in = (size_t) pl->W * pl->H, px_out = (size_t) pl->OW * pl->OH;
+		const int sub = (int) std::max<size_t>(1, std::min<size_t>((size_t) n, ((size_t) 1 << 30) / (px_in * 4)));
+		void *xin = nullptr, *xout = nullptr;
+		if (dev_alloc(domain, &xin, px_in * 4 * sub, s) || dev_alloc(domain, &xout, px_out * 4 * sub, s)) {
+			dev_free(xin, s);
+			return -1;
+		}
+		int rc = 0;
+		for (int f0 = 0; f0 < n && !rc; f0 += sub) {
+			const int nf = std::min(sub, n - f0);
+			rgb_expand_kernel<<<dim3((unsigned) ((px_in / 4 + 255) / 256), nf), 256, 0, s>>>(
+				(const uint8_t *) in + (size_t) f0 * in_stride, in_stride, (uint8_t *) xin, px_in * 4, px_in / 4);
+			count_launch();
+			rc = thumbnail_plan_run_fused(domain, pl, xin, px_in * 4, xout, px_out * 4, nf, s);
+			if (!rc) {
+				rgbx_compact_kernel<<<dim3((unsigned) ((px_out + 255) / 256), nf), 256, 0, s>>>((const uint8_t *) xout, px_out * 4,
+					(uint8_t *) out + (size_t) f0 * out_stride, out_stride, px_out);
+				count_launch();
+				if (cudaGetLastError() != cudaSuccess)
+					rc = cuda_fail(domain, cudaGetLastError(), "rgb expand / compact");
+			}
+		}
+		dev_free(xin, s);
+		dev_free(xout, s);
+		return rc;
 	}
+	if (pl->fused)
+		return thumbnail_plan_run_fused(domain, pl, in, in_stride, out, out_stride, n, s);
 
 	/* unfused chain of leaf kernels, frame by frame */
 	for (int i = 0; i < n; i++) {
@@ -2225,6 +2303,35 @@ thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *pl, const vo
 		dev_image_release(&res, s);
 	}
 	return 0;
+}
+
+/* the fused kernels over RGBA frames */
+static int
+thumbnail_plan_run_fused(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
+	size_t out_stride, int n, cudaStream_t s)
+{
+	{
+		/* the TMA-fed kernel when rows, frames and the base pointer are 16-byte aligned */
+		if ((pl->tma_ok || pl->mma_ok) && (((uintptr_t) in) & 15) == 0 && (n == 1 || (in_stride & 15) == 0)) {
+			bool handled = true;
+			const int rc = launch_tma(domain, pl, in, in_stride, out, out_stride, n, s, &handled);
+			if (handled)
+				return rc;
+		}
+		/* enough CTAs to fill the machine: split rows when the batch is small.  This (fallback) path
+		 * writes the per-launch geometry into the plan: serialise concurrent callers of one plan
+		 */
+		std::lock_guard<std::mutex> launch_lock(pl->launch_lock);
+		FusedParams &fp = pl->fp;
+		const int bands_x = (pl->OW + fp.TW - 1) / fp.TW;
+		int rpc = ((pl->OH + kChunkRows - 1) / kChunkRows) * kChunkRows;
+		while ((long long) bands_x * ((pl->OH + rpc - 1) / rpc) * n < 2 * 148 && rpc > 2 * kChunkRows)
+			rpc = ((rpc / 2 + kChunkRows - 1) / kChunkRows) * kChunkRows;
+		fp.RPC = rpc;
+		pl->grid = dim3(bands_x, (pl->OH + rpc - 1) / rpc, 1);
+		return pl->premul ? launch_fused_vs<true>(domain, pl, in, in_stride, out, out_stride, n, s)
+						  : launch_fused_vs<false>(domain, pl, in, in_stride, out, out_stride, n, s);
+	}
 }
 
 void
@@ -2365,7 +2472,7 @@ vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan)
 		return "linear_v_kernel + linear_h_kernel";
 	const FusedParams &fp = pl.fp;
 	const int nph = fp.NPh == 6 || fp.NPh == 7 ? fp.NPh : 0;
-	const bool v4 = pl.mma_ok && (fp.VS == 2 || fp.VS == 4 || fp.VS == 8);
+	const bool v4 = pl.mma_ok;
 	if (v4)
 		snprintf(name, sizeof(name), "thumbnail_fused_mma_kernel<VS=%d,NP=%d,%s,HS=%d,cols=%d,cpt=%d>", fp.VS, nph,
 			pl.premul ? "premul" : "plain", fp.HS, pl.mma_cols, pl.mma_cpt);

@@ -93,8 +93,23 @@ struct V4HWarpsW {
 
 template <int VS>
 struct V4Stages {
-	/* a stage is 2 VS input rows: 8 stages of 4 rows, 4 of 8, 2 of 16 keep the ring near 100 KB */
-	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES : (VS >= 8 ? VB200_V4_STAGES / 2 : VB200_V4_STAGES);
+	/* a stage is 2 VS input rows: 8 stages of 4 rows, 4 of 6 / 8, 3 of 10 / 12, 2 of 14 / 16 keep the ring near 100 KB */
+	static constexpr int value = VS <= 2 ? 2 * VB200_V4_STAGES
+		: (VS >= 7 ? VB200_V4_STAGES / 2 : (VS >= 5 ? (3 * VB200_V4_STAGES) / 4 : VB200_V4_STAGES));
+};
+
+/* Boxes that are not a power of two (3, 5, 6, 7: thumbnail shrinks 6-8 and 10-16, i.e. most real thumbnails).
+ * The average is the reference's multiplier form ((sum + box / 2) * ((1 << 32) / (256 * box))) >> 24
+ * (shrinkv.c:218-227, shrinkh.c:78-93) -- not a division, and not the byte pick of the power-of-two case.
+ * Horizontally the MMA fragment's column slots are re-mapped: each half-warp group (jj) owns a RUN of
+ * G = floor(32 / HS) * HS consecutive columns instead of interleaved blocks of four, so that every box lies
+ * inside one thread's sequence of 32 slots and is summed in registers as the values come out of the
+ * epilogue; the 32 - G slots left over idle (6% of the tensor work at HS 3, 5, 6; 12% at 7).
+ */
+template <int HSQ>
+struct V4Group {
+	static constexpr bool pow2 = (HSQ & (HSQ - 1)) == 0;
+	static constexpr int value = pow2 ? 32 : (32 / HSQ) * HSQ; /* columns per jj group (CPT 2) */
 };
 
 __device__ __forceinline__ void
@@ -142,6 +157,10 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	constexpr int PITCH = BOXW * 4;			 /* bytes between rows of a box */
 	constexpr int NPR = NP > 0 ? NP : 1;
 	constexpr int HSHIFT = HSQ == 2 ? 1 : HSQ == 4 ? 2 : 3;
+	constexpr bool VPOW2 = (VS & (VS - 1)) == 0;
+	constexpr bool HPOW2 = V4Group<HSQ>::pow2;
+	constexpr int G = V4Group<HSQ>::value; /* logical columns per jj group; 2 G per warp */
+	static_assert(HPOW2 || CPT == 2, "non-power-of-two horizontal boxes are built for two columns per thread");
 	constexpr int rows_per_stage = 2 * VS;
 	constexpr unsigned box_bytes = ((unsigned) rows_per_stage * PITCH + 127u) & ~127u; /* a tiled-TMA destination is 128-byte aligned */
 	constexpr unsigned stage_bytes = NBOX * box_bytes;
@@ -150,7 +169,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	const int NC = NT * CPT; /* columns */
 	const int t = threadIdx.x;
 	const int NPh = NP > 0 ? NP : P.NPh;
-	const int shs = NC / HSQ / 2; /* pairs per sh row: every V thread has a slot, so the epilogue stores need no guard */
+	const int LC = HPOW2 ? NC : (NT / 32) * 2 * G; /* logical (band) columns the V warps cover */
+	const int shs = (LC / HSQ + 1) / 2; /* pairs per sh row: every V thread has a slot, so the epilogue stores need no guard */
 	const unsigned QS = (unsigned) NC * 16u + 16u; /* bytes per quad slot */
 
 	unsigned char *stages = smem_raw;
@@ -196,7 +216,7 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	const int chunk0 = y_begin / K; /* RPC is a multiple of K: chunk c of this CTA is table entry chunk0 + c */
 	const int q_first = __ldg(&P.vchunk[chunk0]).x;
 	/* V warps whose columns all lie beyond this band's last column do not run at all */
-	const int NTa = min(NT, ((NE * HSQ + 32 * CPT - 1) / (32 * CPT)) * 32);
+	const int NTa = HPOW2 ? min(NT, ((NE * HSQ + 32 * CPT - 1) / (32 * CPT)) * 32) : min(NT, ((NE * HSQ + 2 * G - 1) / (2 * G)) * 32);
 
 	if (t == 0) {
 		for (int i = 0; i < S; i++) {
@@ -334,26 +354,39 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 	/* ---------------- V warps */
 	if (t >= NTa)
 		return;
-	/* CPT 2: the thread's two columns are adjacent and start on an even column (one 64-bit LDS per row) */
-	const int my_c = column_of(min(t * CPT, NE * HSQ - CPT)) - c_lo;
+	/* CPT 2: the thread's two columns are adjacent and start on an even column (one 64-bit LDS per row) when the
+	 * horizontal box is even; with an odd box a pair can straddle two boxes (or a replicated edge box) and the
+	 * two columns are addressed separately.  Logical column tt of the band: with G < 32 the last 32 - G slots of
+	 * each half-warp group idle (they repeat the group's last column).
+	 */
+	const int lane_ = t & 31;
+	const int tt0 = HPOW2 ? t * CPT
+						  : (t >> 5) * 2 * G + (lane_ >> 4) * G + min((lane_ & 15) * 2, G - 2);
+	const int my_c = column_of(min(tt0, NE * HSQ - CPT)) - c_lo;
 	const unsigned char *my_cols = stages + (size_t) (my_c / BOXW) * box_bytes + (size_t) (my_c % BOXW) * 4u;
+	constexpr bool PAIR64 = (HSQ & 1) == 0;
+	const int my_c1 = column_of(min(tt0 + 1, NE * HSQ - 1)) - c_lo;
+	const unsigned char *my_cols1 = stages + (size_t) (my_c1 / BOXW) * box_bytes + (size_t) (my_c1 % BOXW) * 4u;
 	const unsigned accm = P.accmul; /* run-time on purpose: keeps the accumulation on IMAD */
 	unsigned k16;
 	asm volatile("mov.u32 %0, 0x10000;" : "=r"(k16));
 	int k20;
 	asm volatile("mov.u32 %0, 0x100000;" : "=r"(k20));
-	const unsigned amend2 = (unsigned) (VS / 2) * (VB200_V4_HADD2 ? 1u : accm) * 0x00010001u;
+	const unsigned amend2 = (unsigned) (VS / 2) * (VB200_V4_HADD2 || !VPOW2 ? 1u : accm) * 0x00010001u;
+	const unsigned vmul8 = P.vmul8, hmul8 = P.hmul8; /* ((1 << 32) / (256 * box)) << 8: umulhi gives ((sum) * mult) >> 24 */
 	const int lane = t & 31;
 	const bool lane0 = lane == 0;
 	/* MMA fragment coordinates */
 	const int tig = lane & 3, g = lane >> 2, ch = g & 3, jj = g >> 2;
 	const int warp_col0 = (t & ~31) * CPT;
-	/* A loads: quad slot tig (+4), column warp_col0 + 8 tp + 4 jj + 2 T + h, channel ch */
-	const unsigned char *a_base = quadbuf + (size_t) tig * QS + (size_t) (warp_col0 + 4 * jj) * 16u + (unsigned) ch * 4u;
+	/* A loads: quad slot tig (+4), column warp_col0 + 8 tp + 4 jj + 2 T + h, channel ch.  Non-power-of-two boxes:
+	 * column warp_col0 + 32 jj + 4 tp + 2 T + h -- group jj's slots are a run of consecutive columns.
+	 */
+	const unsigned char *a_base = quadbuf + (size_t) tig * QS + (size_t) (warp_col0 + (HPOW2 ? 4 : 32) * jj) * 16u + (unsigned) ch * 4u;
 	unsigned char *q_store = quadbuf + (size_t) (t * CPT) * 16u;
 	/* sh store: v3's pair layout, [rA rB bA bB gA gB aA aB] per column pair */
 	const int ch_off = ch == 0 ? 0 : ch == 1 ? 4 : ch == 2 ? 2 : 6;
-	const int warp_sx0 = warp_col0 / HSQ;
+	const int warp_sx0 = HPOW2 ? warp_col0 / HSQ : (t >> 5) * (2 * G / HSQ) + jj * (G / HSQ);
 
 	int s = 0;
 	unsigned phase = 0;
@@ -381,8 +414,16 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 					uint2 pa[VS], pb[VS];
 #pragma unroll
 					for (int k = 0; k < VS; k++) {
-						pa[k] = *(const uint2 *) (my_cols + soff + k * PITCH);
-						pb[k] = *(const uint2 *) (my_cols + soff + (VS + k) * PITCH);
+						if (PAIR64) {
+							pa[k] = *(const uint2 *) (my_cols + soff + k * PITCH);
+							pb[k] = *(const uint2 *) (my_cols + soff + (VS + k) * PITCH);
+						}
+						else {
+							pa[k].x = *(const unsigned *) (my_cols + soff + k * PITCH);
+							pa[k].y = *(const unsigned *) (my_cols1 + soff + k * PITCH);
+							pb[k].x = *(const unsigned *) (my_cols + soff + (VS + k) * PITCH);
+							pb[k].y = *(const unsigned *) (my_cols1 + soff + (VS + k) * PITCH);
+						}
 					}
 					__syncwarp();
 					if (lane0)
@@ -419,6 +460,26 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 			/* box averages are bytes 1 and 3 of each lane word: transpose 4 rows into quads */
 #pragma unroll
 			for (int i = 0; i < CPT; i++) {
+				if (!VPOW2) {
+					/* ((sum + VS / 2) * multiplier) >> 24 per 16-bit lane (shrinkv.c:218-227), then the four rows
+					 * of a channel into one quad word
+					 */
+					unsigned av[4][4]; /* [row][r b g a] */
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						av[r][0] = __umulhi(rb[r][i] & 0xffffu, vmul8);
+						av[r][1] = __umulhi(rb[r][i] >> 16, vmul8);
+						av[r][2] = __umulhi(ga[r][i] & 0xffffu, vmul8);
+						av[r][3] = __umulhi(ga[r][i] >> 16, vmul8);
+					}
+					uint4 w;
+					w.x = __byte_perm(__byte_perm(av[0][0], av[1][0], 0x0040), __byte_perm(av[2][0], av[3][0], 0x0040), 0x5410);
+					w.y = __byte_perm(__byte_perm(av[0][2], av[1][2], 0x0040), __byte_perm(av[2][2], av[3][2], 0x0040), 0x5410);
+					w.z = __byte_perm(__byte_perm(av[0][1], av[1][1], 0x0040), __byte_perm(av[2][1], av[3][1], 0x0040), 0x5410);
+					w.w = __byte_perm(__byte_perm(av[0][3], av[1][3], 0x0040), __byte_perm(av[2][3], av[3][3], 0x0040), 0x5410);
+					*(uint4 *) (q_store + (size_t) (q & (kV4Quads - 1)) * QS + i * 16) = w;
+					continue;
+				}
 				if (VB200_V4_HADD2) {
 					/* plain sums (HADD2): scale them here, one IMAD per word instead of one per pixel */
 #pragma unroll
@@ -450,13 +511,15 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 		else
 			mbar_wait(shempty_s + 8u * buf, ((unsigned) (chunk >> 1) & 1u) ^ 1u);
 		unsigned char *shb = (unsigned char *) (sh + (size_t) buf * KM * shs) + (size_t) (2 * tig) * shs * 8 + ch_off;
+		int bsum[2] = {0, 0}; /* non-power-of-two boxes: running sums of the box in progress, output rows r = 0, 1 */
+		int bcnt = 0, bidx = 0;
 #pragma unroll kMmaUnroll
 		for (int tp = 0; tp < 4 * CPT; tp++) {
 			unsigned a[2][4];
 			int dh[2][4], dl[2][4];
 #pragma unroll
 			for (int T = 0; T < 2; T++) {
-				const unsigned char *ap = a_base + tp * 128 + T * 32;
+				const unsigned char *ap = a_base + tp * (HPOW2 ? 128 : 64) + T * 32;
 				a[T][0] = *(const unsigned *) (ap);
 				a[T][1] = *(const unsigned *) (ap + 16);
 				a[T][2] = *(const unsigned *) (ap + 4 * (size_t) QS);
@@ -479,6 +542,8 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 				const int v01 = v4_finish(dh[0][2 + r], dl[0][2 + r], k20);
 				const int v10 = v4_finish(dh[1][r], dl[1][r], k20);
 				const int v11 = v4_finish(dh[1][2 + r], dl[1][2 + r], k20);
+				if (!HPOW2)
+					continue; /* handled below, slot by slot */
 				if (HSQ == 2) {
 					/* two complete boxes: columns (4 jj, 4 jj + 1) and (4 jj + 2, 4 jj + 3) */
 					const int sx = warp_sx0 + tp * 4 + 2 * jj;
@@ -496,6 +561,28 @@ thumbnail_fused_mma_kernel(const __grid_constant__ FusedParams P, const __grid_c
 					const int sx = warp_sx0 + tp;
 					if (jj == 0)
 						shb[(size_t) r * shs * 8 + (sx >> 1) * 8 + (sx & 1)] = (unsigned char) ((sum + 4) >> HSHIFT);
+				}
+			}
+			if (!HPOW2) {
+				/* this thread's slots 4 tp .. 4 tp + 3 are consecutive columns of its group: close a box every HSQ
+				 * of them with the reference's multiplier form (shrinkh.c:78-93).  Slots past G idle.
+				 */
+#pragma unroll
+				for (int sl = 0; sl < 4; sl++) {
+					const int T = sl >> 1, h = sl & 1;
+					if (4 * tp + sl < G) {
+						bsum[0] += v4_finish(dh[T][2 * h], dl[T][2 * h], k20);
+						bsum[1] += v4_finish(dh[T][2 * h + 1], dl[T][2 * h + 1], k20);
+						if (++bcnt == HSQ) {
+							const int sx = warp_sx0 + bidx;
+							unsigned char *d = shb + (sx >> 1) * 8 + (sx & 1);
+							d[0] = (unsigned char) __umulhi((unsigned) (bsum[0] + HSQ / 2), hmul8);
+							d[(size_t) shs * 8] = (unsigned char) __umulhi((unsigned) (bsum[1] + HSQ / 2), hmul8);
+							bsum[0] = bsum[1] = 0;
+							bcnt = 0;
+							bidx++;
+						}
+					}
 				}
 			}
 		}

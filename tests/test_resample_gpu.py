@@ -266,10 +266,20 @@ V4_CASES = [
     (4000, 3000, 410, None, "both", True, 1, True),     # shrink 9.76: box 4, residual 2.44
     (4096, 4096, 256, None, "both", True, 2, True),     # shrink 16: box 8 on both axes
     (3840, 2160, 225, None, "both", True, 1, True),     # shrink 17.07: box 8, residual 2.13
-    # plans the tensor-pipe kernel declines (box 3 / box 8): they must land on the older fused kernels with
-    # the same pixels
-    (1200, 900, 150, None, "both", True, 1, False),
+    # boxes that are not powers of two (multiplier-form averages, re-mapped fragment columns)
+    (1200, 900, 150, None, "both", True, 1, True),      # V 3, H 4
+    (3000, 2000, 428, None, "both", True, 2, True),     # 3, 3: shrink 7.01
+    (2400, 1800, 340, None, "both", False, 1, True),    # 3, 3 without alpha
+    (4000, 3000, 364, None, "both", True, 1, True),     # 5, 5: shrink 10.99
+    (4096, 4096, 320, None, "both", True, 1, True),     # 6, 6: shrink 12.8
+    (4096, 4096, 280, None, "both", True, 1, True),     # 7, 7: shrink 14.6
+    (1920, 1080, 274, None, "both", True, 3, True),     # 3, 3 on a 16:9 frame, three frames
+    (2048, 1536, 256, 256, "force", True, 1, True),     # V 3, H 4 in force mode
+    (4096, 2048, 500, None, "both", True, 1, True),     # 4, 4 ... (shrink 8.19: box 4, residual 2.05)
+    # plans the tensor-pipe kernel declines: rows not 16-byte aligned; boxes that differ by two.  They must land on
+    # the older fused kernels with the same pixels
     (1003, 2057, 120, None, "both", True, 2, False),
+    (2560, 1280, 256, 183, "force", True, 1, False),
 ]
 
 
@@ -313,3 +323,22 @@ def test_batch_device_strides_and_alignment(vb, oracle, pad, shift):
     vb.set_stream(0)
     want = np.stack([oracle.thumbnail_image(f, 128) for f in frames])
     same(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape,target", [((1024, 1024), 128), ((1200, 900), 150), ((600, 404), 99), ((2048, 1536), 256)])
+def test_rgb_frames_ride_the_fused_rgba_kernels(vb, oracle, shape, target):
+    """3-band 8-bit frames (what a JPEG decodes to): expanded to RGBX on the device, the fused RGBA kernel without
+    premultiply, compacted -- the channels of the uchar chain never mix, so the bytes are the reference's"""
+    from oracle import pyconv
+    rng = np.random.default_rng(shape[0])
+    h, w = shape
+    frames = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    plan = vb.ThumbnailPlan(w, h, 3, target)
+    assert plan.fused, plan.kernel
+    got = plan.run_host(frames)
+    for i in range(3):
+        assert np.array_equal(got[i], oracle.thumbnail_image(frames[i], target)), i
+    assert np.array_equal(vb.Image(frames[0]).thumbnail_image(target).numpy(), got[0])
+    plan.set_sharpen()
+    got = plan.run_host(frames[:1])
+    assert np.array_equal(got[0], pyconv.sharpen(oracle.thumbnail_image(frames[0], target), "srgb"))
