@@ -448,6 +448,9 @@ def main():
     ap.add_argument("--frames", type=int, default=1024, help="synthetic frames resident per GPU")
     ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--alpha", default="random", choices=["random", "opaque"],
+                    help="alpha band of the synthetic frames: random (the headline) | opaque (255 everywhere, what a PNG without "
+                         "transparency decodes to: the kernel's opaque-stage fast path; a second line, never the headline)")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
                          "--gpus N like the headline) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
@@ -495,6 +498,9 @@ def main():
         n = min(16, F - i)
         frames[i:i + n] = torch.randint(0, 256, (n, H, W, BANDS), dtype=torch.uint8, device=dev, generator=g)
     common = np.random.default_rng(1234).integers(0, 256, (H, W, BANDS), dtype=np.uint8)
+    if args.alpha == "opaque":
+        frames[..., BANDS - 1] = 255
+        common[..., BANDS - 1] = 255
     frames[0].copy_(torch.from_numpy(common))
     outs = torch.empty((F, TARGET, TARGET, BANDS), dtype=torch.uint8, device=dev)
     SHARPEN = (0.5, 2.0, 10.0, 20.0, 0.0, 3.0)  # vips_sharpen's defaults
@@ -601,6 +607,8 @@ def main():
     if hin and hout:
         src = np.frombuffer((C.c_uint8 * (E * plan.in_frame_bytes)).from_address(hin), dtype=np.uint8)
         one = np.random.default_rng(99 + rank).integers(0, 256, plan.in_frame_bytes, dtype=np.uint8)
+        if args.alpha == "opaque":
+            one[BANDS - 1::BANDS] = 255
         for i in range(E):
             src[i * plan.in_frame_bytes:(i + 1) * plan.in_frame_bytes] = np.roll(one, 4 * i)
         for _ in range(2):
@@ -644,7 +652,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "parity": parity, "lib": vb.library_path(),
-            "config": {"workload": WORKLOAD_PIPELINE if PIPELINE else WORKLOAD, "frames_per_gpu": F, "frame": "4096x4096x4 u8",
+            "config": {"workload": (WORKLOAD_PIPELINE if PIPELINE else WORKLOAD) + ("" if args.alpha == "random" else ", alpha band 255 everywhere"),
+                       "alpha": args.alpha, "frames_per_gpu": F, "frame": "4096x4096x4 u8",
                        "output": "512x512x4 u8", "l2": "inputs (%.1f GiB per GPU) larger than L2" % (F * plan.in_frame_bytes / 2**30),
                        "sharding": "independent frames per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

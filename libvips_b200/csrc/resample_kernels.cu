@@ -20,6 +20,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "vb200_internal.h"
 
@@ -202,9 +206,27 @@ struct AxisDev {
 	const int *phase;
 	const short *ms;
 	const double *mf;
+	const unsigned *mp; /* [65][npairs] s16 x 2: taps (2k, 2k + 1) of each phase, the odd tail paired with 0 (dp2a kernels) */
 	int n_point;
 	int embed;
+	int npairs; /* (n_point + 1) / 2 */
 };
+
+__device__ __forceinline__ int
+dp2a_lo_(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
+
+__device__ __forceinline__ int
+dp2a_hi_(unsigned coef, unsigned bytes, int acc)
+{
+	int d;
+	asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(coef), "r"(bytes), "r"(acc));
+	return d;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -287,6 +309,143 @@ reducev_u8x4_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uin
 	const unsigned int b0 = clampi(s0 >> 12, 0, 255), b1 = clampi(s1 >> 12, 0, 255);
 	const unsigned int b2 = clampi(s2 >> 12, 0, 255), b3 = clampi(s3 >> 12, 0, 255);
 	((unsigned int *) (out + (size_t) y * out_bpl))[x] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+}
+
+/* uchar, register-blocked: one thread owns a 4-byte column of kRvRows consecutive output rows and walks the
+ * union of their tap windows ONCE, two input rows at a time.  The two words are interleaved by PRMT into
+ * [b0 b0' b1 b1'] / [b2 b2' b3 b3'] and each output row takes them with four IDP.2A against its coefficient pair
+ * (c[u], c[u + 1]) for that pair of rows -- zero where a row lies outside the output row's window.  The pair table
+ * of the block's rows is built in shared memory from the phase masks (the rows of a block may have any first tap
+ * and any phase: the per-rect stepping of build_axis_table is kept).  Same integer sum as reducev_u8x4_kernel
+ * (reducev.cpp:461-471), 12 instead of ~60 instructions per input word: config 1's 49-tap pass went 93 -> us.
+ */
+constexpr int kRvRows = 4;
+constexpr int kRvThreads = 128;
+
+__global__ void __launch_bounds__(kRvThreads)
+reducev_u8_dp2a_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uint8_t *__restrict__ out,
+	size_t out_bpl, int nwords, int out_rows, AxisDev t)
+{
+	extern __shared__ __align__(16) unsigned s_c2[]; /* [pairs][kRvRows] */
+	const int n = t.n_point;
+	const int y0 = blockIdx.y * kRvRows;
+	int u0 = 0x7fffffff, u1 = -0x7fffffff;
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++) {
+		const int py = __ldg(t.first + min(y0 + j, out_rows - 1)) - t.embed;
+		u0 = min(u0, py);
+		u1 = max(u1, py + n - 1);
+	}
+	const int npairs = (u1 - u0 + 2) >> 1;
+	for (int idx = threadIdx.x; idx < npairs * kRvRows; idx += kRvThreads) {
+		const int k = idx / kRvRows, j = idx - k * kRvRows;
+		const int yj = min(y0 + j, out_rows - 1);
+		const short *c = t.ms + (size_t) __ldg(t.phase + yj) * n;
+		const int i0 = u0 + 2 * k - (__ldg(t.first + yj) - t.embed);
+		const unsigned lo = i0 >= 0 && i0 < n ? (unsigned short) c[i0] : 0u;
+		const unsigned hi = i0 + 1 >= 0 && i0 + 1 < n ? (unsigned short) c[i0 + 1] : 0u;
+		s_c2[idx] = lo | (hi << 16);
+	}
+	__syncthreads();
+	const int x = blockIdx.x * kRvThreads + threadIdx.x;
+	if (x >= nwords)
+		return;
+	int acc[kRvRows][4];
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++)
+#pragma unroll
+		for (int c = 0; c < 4; c++)
+			acc[j][c] = VB200_INTERPOLATE_SCALE >> 1;
+#pragma unroll 4
+	for (int k = 0; k < npairs; k++) {
+		const int ra = clampi(u0 + 2 * k, 0, in_h - 1), rb = clampi(u0 + 2 * k + 1, 0, in_h - 1);
+		const unsigned va = __ldg((const unsigned *) (in + (size_t) ra * in_bpl) + x);
+		const unsigned vb = __ldg((const unsigned *) (in + (size_t) rb * in_bpl) + x);
+		const unsigned w0 = __byte_perm(va, vb, 0x5140), w1 = __byte_perm(va, vb, 0x7362);
+		const uint4 c4 = *(const uint4 *) (s_c2 + k * kRvRows);
+		const unsigned cj[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+		for (int j = 0; j < kRvRows; j++) {
+			acc[j][0] = dp2a_lo_(cj[j], w0, acc[j][0]);
+			acc[j][1] = dp2a_hi_(cj[j], w0, acc[j][1]);
+			acc[j][2] = dp2a_lo_(cj[j], w1, acc[j][2]);
+			acc[j][3] = dp2a_hi_(cj[j], w1, acc[j][3]);
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++)
+		if (y0 + j < out_rows) {
+			const unsigned b0 = clampi(acc[j][0] >> VB200_INTERPOLATE_SHIFT, 0, 255), b1 = clampi(acc[j][1] >> VB200_INTERPOLATE_SHIFT, 0, 255);
+			const unsigned b2 = clampi(acc[j][2] >> VB200_INTERPOLATE_SHIFT, 0, 255), b3 = clampi(acc[j][3] >> VB200_INTERPOLATE_SHIFT, 0, 255);
+			((unsigned *) (out + (size_t) (y0 + j) * out_bpl))[x] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+		}
+}
+
+/* uchar RGBA rows: a CTA stages the span of input pixels its kRhThreads output pixels read (clamp addressing =
+ * the reference's EXTEND_COPY embed) into shared memory, padded one word in eight so that the stride-shrink reads
+ * of a warp spread over the banks, then every thread runs its taps two pixels at a time: PRMT to [r r' g g'] /
+ * [b b' a a'], four IDP.2A against the phase's coefficient pair (t.mp, built on the host).  reduceh.cpp:145-160.
+ */
+constexpr int kRhThreads = 128;
+
+__device__ __forceinline__ int
+rh_pad(int i)
+{
+	return i + (i >> 3);
+}
+
+__global__ void __launch_bounds__(kRhThreads)
+reduceh_u8x4_dp2a_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_w, uint8_t *__restrict__ out,
+	size_t out_bpl, int out_w, AxisDev t)
+{
+	extern __shared__ __align__(16) unsigned s_px[];
+	__shared__ int s_lo, s_hi;
+	const int n = t.n_point;
+	const int x = blockIdx.x * kRhThreads + threadIdx.x;
+	const int y = blockIdx.y;
+	const bool live = x < out_w;
+	const int ix = __ldg(t.first + min(x, out_w - 1)) - t.embed;
+	if (threadIdx.x == 0) {
+		s_lo = 0x7fffffff;
+		s_hi = -0x7fffffff;
+	}
+	__syncthreads();
+	{
+		int lo = ix, hi = ix;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+			hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+		}
+		if ((threadIdx.x & 31) == 0) {
+			atomicMin(&s_lo, lo);
+			atomicMax(&s_hi, hi);
+		}
+	}
+	__syncthreads();
+	const int p0 = s_lo, span = s_hi - s_lo + 2 * t.npairs; /* an odd tap count reads one word past its window (coefficient 0) */
+	const unsigned *row = (const unsigned *) (in + (size_t) y * in_bpl);
+	for (int i = threadIdx.x; i < span; i += kRhThreads)
+		s_px[rh_pad(i)] = __ldg(row + clampi(p0 + i, 0, in_w - 1));
+	__syncthreads();
+	if (!live)
+		return;
+	const unsigned *cp = t.mp + (size_t) __ldg(t.phase + x) * t.npairs;
+	const int rel = ix - p0;
+	int r = VB200_INTERPOLATE_SCALE >> 1, g = r, b = r, a = r;
+#pragma unroll 5
+	for (int k = 0; k < t.npairs; k++) {
+		const unsigned pa = s_px[rh_pad(rel + 2 * k)], pb = s_px[rh_pad(rel + 2 * k + 1)];
+		const unsigned w0 = __byte_perm(pa, pb, 0x5140), w1 = __byte_perm(pa, pb, 0x7362);
+		const unsigned c = __ldg(cp + k);
+		r = dp2a_lo_(c, w0, r);
+		g = dp2a_hi_(c, w0, g);
+		b = dp2a_lo_(c, w1, b);
+		a = dp2a_hi_(c, w1, a);
+	}
+	const unsigned b0 = clampi(r >> VB200_INTERPOLATE_SHIFT, 0, 255), b1 = clampi(g >> VB200_INTERPOLATE_SHIFT, 0, 255);
+	const unsigned b2 = clampi(b >> VB200_INTERPOLATE_SHIFT, 0, 255), b3 = clampi(a >> VB200_INTERPOLATE_SHIFT, 0, 255);
+	((unsigned *) (out + (size_t) y * out_bpl))[x] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
 }
 
 /* ------------------------------------------------------------------ reduceh */
@@ -446,36 +605,66 @@ aligned4(const void *p, size_t bpl)
 	return (((uintptr_t) p) & 3) == 0 && (bpl & 3) == 0;
 }
 
-/* Upload an AxisTable as one packed block; the AxisDev points into it. */
-int
-upload_axis(const char *domain, const AxisTable &t, AxisDev *d, void **block, cudaStream_t s)
+/* An AxisTable packed into one block: the AxisDev points into it (host image `host`, `total` bytes). */
+void
+pack_axis(const AxisTable &t, std::vector<char> &host, AxisDev *d)
 {
+	const int npairs = (t.n_point + 1) / 2;
+	std::vector<unsigned> mp((size_t) 65 * npairs);
+	for (int ph = 0; ph < 65 && t.ms.size() >= (size_t) 65 * t.n_point; ph++)
+		for (int k = 0; k < npairs; k++) {
+			const unsigned lo = (unsigned short) t.ms[(size_t) ph * t.n_point + 2 * k];
+			const unsigned hi = 2 * k + 1 < t.n_point ? (unsigned short) t.ms[(size_t) ph * t.n_point + 2 * k + 1] : 0u;
+			mp[(size_t) ph * npairs + k] = lo | (hi << 16);
+		}
 	const size_t n_first = t.first.size() * sizeof(int);
 	const size_t n_ms = t.ms.size() * sizeof(short);
 	const size_t n_mf = t.mf.size() * sizeof(double);
+	const size_t n_mp = mp.size() * sizeof(unsigned);
 	const size_t off_mf = 0;
 	const size_t off_first = off_mf + n_mf;
 	const size_t off_phase = off_first + n_first;
-	const size_t off_ms = off_phase + n_first;
-	const size_t total = off_ms + n_ms;
-
-	std::vector<char> host(total);
+	const size_t off_mp = off_phase + n_first;
+	const size_t off_ms = off_mp + n_mp;
+	host.resize(off_ms + n_ms);
 	memcpy(&host[off_mf], t.mf.data(), n_mf);
 	memcpy(&host[off_first], t.first.data(), n_first);
 	memcpy(&host[off_phase], t.phase.data(), n_first);
+	memcpy(&host[off_mp], mp.data(), n_mp);
 	memcpy(&host[off_ms], t.ms.data(), n_ms);
-
-	if (dev_alloc(domain, block, total, s))
-		return -1;
-	VB200_CUDA(domain, cudaMemcpyAsync(*block, host.data(), total, cudaMemcpyHostToDevice, s));
-	/* pageable source: the copy has been staged when the call returns */
-	char *b = (char *) *block;
-	d->mf = (const double *) (b + off_mf);
-	d->first = (const int *) (b + off_first);
-	d->phase = (const int *) (b + off_phase);
-	d->ms = (const short *) (b + off_ms);
+	/* offsets; rebased onto the device block by the caller */
+	d->mf = (const double *) off_mf;
+	d->first = (const int *) off_first;
+	d->phase = (const int *) off_phase;
+	d->mp = (const unsigned *) off_mp;
+	d->ms = (const short *) off_ms;
 	d->n_point = t.n_point;
 	d->embed = t.embed;
+	d->npairs = npairs;
+}
+
+void
+rebase_axis(AxisDev *d, const void *block)
+{
+	const char *b = (const char *) block;
+	d->mf = (const double *) (b + (size_t) d->mf);
+	d->first = (const int *) (b + (size_t) d->first);
+	d->phase = (const int *) (b + (size_t) d->phase);
+	d->mp = (const unsigned *) (b + (size_t) d->mp);
+	d->ms = (const short *) (b + (size_t) d->ms);
+}
+
+/* Upload an AxisTable as one packed block from the stream-ordered pool; the AxisDev points into it. */
+int
+upload_axis(const char *domain, const AxisTable &t, AxisDev *d, void **block, cudaStream_t s)
+{
+	std::vector<char> host;
+	pack_axis(t, host, d);
+	if (dev_alloc(domain, block, host.size(), s))
+		return -1;
+	VB200_CUDA(domain, cudaMemcpyAsync(*block, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+	/* pageable source: the copy has been staged when the call returns */
+	rebase_axis(d, *block);
 	return 0;
 }
 
@@ -489,7 +678,175 @@ check_launch(const char *domain, const char *what)
 	return 0;
 }
 
+/* shared memory the dp2a kernels need for this table (0: not usable) */
+size_t
+reducev_dp2a_smem(const AxisTable &t, int out_rows)
+{
+	int pairs = 0;
+	for (int y0 = 0; y0 < out_rows; y0 += kRvRows) {
+		int u0 = 0x7fffffff, u1 = -0x7fffffff;
+		for (int j = 0; j < kRvRows; j++) {
+			const int py = t.first[std::min(y0 + j, out_rows - 1)];
+			u0 = std::min(u0, py);
+			u1 = std::max(u1, py + t.n_point - 1);
+		}
+		pairs = std::max(pairs, (u1 - u0 + 2) >> 1);
+	}
+	return (size_t) pairs * kRvRows * sizeof(unsigned);
+}
+
+size_t
+reduceh_dp2a_smem(const AxisTable &t, int out_cols)
+{
+	int span = 0;
+	for (int x0 = 0; x0 < out_cols; x0 += kRhThreads) {
+		int lo = 0x7fffffff, hi = -0x7fffffff;
+		for (int x = x0; x < std::min(x0 + kRhThreads, out_cols); x++) {
+			lo = std::min(lo, t.first[x]);
+			hi = std::max(hi, t.first[x]);
+		}
+		span = std::max(span, hi - lo + 2 * ((t.n_point + 1) / 2));
+	}
+	return (size_t) (span + (span >> 3) + 2) * sizeof(unsigned);
+}
+
+int
+run_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne, int out_rows,
+	int fmt, const AxisDev &d, size_t dp2a_smem, cudaStream_t s)
+{
+#define RV(T) reducev_kernel<T><<<row_grid(ne, out_rows), 256, 0, s>>>((const T *) in, in_bpl, in_h, (T *) out, out_bpl, ne, d)
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR:
+		if ((ne & 3) == 0 && aligned4(in, in_bpl) && aligned4(out, out_bpl)) {
+			if (dp2a_smem > 0 && dp2a_smem <= 40 * 1024 && out_rows >= 1)
+				reducev_u8_dp2a_kernel<<<dim3((ne / 4 + kRvThreads - 1) / kRvThreads, (out_rows + kRvRows - 1) / kRvRows), kRvThreads,
+					dp2a_smem, s>>>((const uint8_t *) in, in_bpl, in_h, (uint8_t *) out, out_bpl, ne / 4, out_rows, d);
+			else
+				reducev_u8x4_kernel<<<row_grid(ne / 4, out_rows), 256, 0, s>>>((const uint8_t *) in, in_bpl, in_h,
+					(uint8_t *) out, out_bpl, ne / 4, d);
+		}
+		else
+			RV(uint8_t);
+		break;
+	case VB200_FORMAT_CHAR: RV(int8_t); break;
+	case VB200_FORMAT_USHORT: RV(uint16_t); break;
+	case VB200_FORMAT_SHORT: RV(int16_t); break;
+	case VB200_FORMAT_UINT: RV(uint32_t); break;
+	case VB200_FORMAT_INT: RV(int32_t); break;
+	case VB200_FORMAT_FLOAT: RV(float); break;
+	default:
+		error(domain, "band format %d not supported on the device path", fmt);
+		return -1;
+	}
+#undef RV
+	return check_launch(domain, "reducev kernel");
+}
+
+int
+run_reduceh(const char *domain, const void *in, size_t in_bpl, int in_w, void *out, size_t out_bpl, int bands, int out_cols,
+	int rows, int fmt, const AxisDev &d, size_t dp2a_smem, cudaStream_t s)
+{
+#define RH(T) reduceh_kernel<T><<<row_grid(out_cols * bands, rows), 256, 0, s>>>((const T *) in, in_bpl, in_w, (T *) out, out_bpl, out_cols, bands, d)
+	switch (fmt) {
+	case VB200_FORMAT_UCHAR:
+		if (bands == 4 && aligned4(in, in_bpl) && aligned4(out, out_bpl) && dp2a_smem > 0 && dp2a_smem <= 40 * 1024)
+			reduceh_u8x4_dp2a_kernel<<<dim3((out_cols + kRhThreads - 1) / kRhThreads, rows), kRhThreads, dp2a_smem, s>>>(
+				(const uint8_t *) in, in_bpl, in_w, (uint8_t *) out, out_bpl, out_cols, d);
+		else
+			RH(uint8_t);
+		break;
+	case VB200_FORMAT_CHAR: RH(int8_t); break;
+	case VB200_FORMAT_USHORT: RH(uint16_t); break;
+	case VB200_FORMAT_SHORT: RH(int16_t); break;
+	case VB200_FORMAT_UINT: RH(uint32_t); break;
+	case VB200_FORMAT_INT: RH(int32_t); break;
+	case VB200_FORMAT_FLOAT: RH(float); break;
+	default:
+		error(domain, "band format %d not supported on the device path", fmt);
+		return -1;
+	}
+#undef RH
+	return check_launch(domain, "reduceh kernel");
+}
+
+/* Tables of whole-image passes, cached: building one costs 65 x n sin() evaluations plus the per-rect stepping, and
+ * uploading it a staged copy -- together several times the kernel on a single 4096 x 4096 frame (config 1).  The key
+ * is everything build_axis_table() reads; the device block lives until the entry is evicted (cudaFree waits for the
+ * device, so a kernel still reading it is safe).
+ */
+struct AxisPlan {
+	AxisTable t;
+	AxisDev d;
+	void *block = nullptr;
+	size_t v_smem = 0, h_smem = 0;
+	~AxisPlan()
+	{
+		if (block)
+			cudaFree(block);
+	}
+};
+
+struct AxisKey {
+	int out_size, n_point, kernel, rect;
+	double residual, offset;
+	bool
+	operator==(const AxisKey &o) const
+	{
+		return out_size == o.out_size && n_point == o.n_point && kernel == o.kernel && rect == o.rect &&
+			memcmp(&residual, &o.residual, sizeof(double)) == 0 && memcmp(&offset, &o.offset, sizeof(double)) == 0;
+	}
+};
+
+std::mutex g_axis_lock;
+std::vector<std::pair<AxisKey, std::shared_ptr<AxisPlan>>> g_axis_cache; /* most recent last */
+constexpr size_t kAxisCacheEntries = 24;
+
+std::shared_ptr<AxisPlan>
+axis_plan(const char *domain, const ReduceGeom &g, int kernel, int rect, bool vertical)
+{
+	const AxisKey key = {g.out_size, g.n_point, kernel, rect, g.residual, g.offset};
+	{
+		std::lock_guard<std::mutex> lock(g_axis_lock);
+		for (size_t i = 0; i < g_axis_cache.size(); i++)
+			if (g_axis_cache[i].first == key) {
+				auto hit = g_axis_cache[i];
+				g_axis_cache.erase(g_axis_cache.begin() + i);
+				g_axis_cache.push_back(hit);
+				return hit.second;
+			}
+	}
+	auto pl = std::make_shared<AxisPlan>();
+	build_axis_table(pl->t, g.out_size, g.residual, g.offset, g.n_point, kernel, rect);
+	std::vector<char> host;
+	pack_axis(pl->t, host, &pl->d);
+	if (cudaMalloc(&pl->block, host.size()) != cudaSuccess) {
+		pl->block = nullptr;
+		cuda_fail(domain, cudaGetLastError(), "cudaMalloc (axis tables)");
+		return nullptr;
+	}
+	if (cudaMemcpy(pl->block, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+		cuda_fail(domain, cudaGetLastError(), "cudaMemcpy (axis tables)");
+		return nullptr;
+	}
+	rebase_axis(&pl->d, pl->block);
+	pl->v_smem = reducev_dp2a_smem(pl->t, g.out_size);
+	pl->h_smem = reduceh_dp2a_smem(pl->t, g.out_size);
+	(void) vertical;
+	std::lock_guard<std::mutex> lock(g_axis_lock);
+	if (g_axis_cache.size() >= kAxisCacheEntries)
+		g_axis_cache.erase(g_axis_cache.begin());
+	g_axis_cache.push_back(std::make_pair(key, pl));
+	return pl;
+}
+
 } // namespace
+
+void
+resample_cache_clear()
+{
+	std::lock_guard<std::mutex> lock(g_axis_lock);
+	g_axis_cache.clear();
+}
 
 /* ------------------------------------------------------------- launchers */
 
@@ -501,29 +858,8 @@ launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void
 	void *block = nullptr;
 	if (upload_axis(domain, t, &d, &block, s))
 		return -1;
-
-#define RV(T) reducev_kernel<T><<<row_grid(ne, out_rows), 256, 0, s>>>((const T *) in, in_bpl, in_h, (T *) out, out_bpl, ne, d)
-	switch (fmt) {
-	case VB200_FORMAT_UCHAR:
-		if ((ne & 3) == 0 && aligned4(in, in_bpl) && aligned4(out, out_bpl))
-			reducev_u8x4_kernel<<<row_grid(ne / 4, out_rows), 256, 0, s>>>((const uint8_t *) in, in_bpl, in_h,
-				(uint8_t *) out, out_bpl, ne / 4, d);
-		else
-			RV(uint8_t);
-		break;
-	case VB200_FORMAT_CHAR: RV(int8_t); break;
-	case VB200_FORMAT_USHORT: RV(uint16_t); break;
-	case VB200_FORMAT_SHORT: RV(int16_t); break;
-	case VB200_FORMAT_UINT: RV(uint32_t); break;
-	case VB200_FORMAT_INT: RV(int32_t); break;
-	case VB200_FORMAT_FLOAT: RV(float); break;
-	default:
-		dev_free(block, s);
-		error(domain, "band format %d not supported on the device path", fmt);
-		return -1;
-	}
-#undef RV
-	int r = check_launch(domain, "reducev kernel");
+	const int r = run_reducev(domain, in, in_bpl, in_h, out, out_bpl, ne, out_rows, fmt, d,
+		fmt == VB200_FORMAT_UCHAR ? reducev_dp2a_smem(t, out_rows) : 0, s);
 	dev_free(block, s);
 	return r;
 }
@@ -536,23 +872,8 @@ launch_reduceh(const char *domain, const void *in, size_t in_bpl, int in_w, void
 	void *block = nullptr;
 	if (upload_axis(domain, t, &d, &block, s))
 		return -1;
-
-#define RH(T) reduceh_kernel<T><<<row_grid(out_cols * bands, rows), 256, 0, s>>>((const T *) in, in_bpl, in_w, (T *) out, out_bpl, out_cols, bands, d)
-	switch (fmt) {
-	case VB200_FORMAT_UCHAR: RH(uint8_t); break;
-	case VB200_FORMAT_CHAR: RH(int8_t); break;
-	case VB200_FORMAT_USHORT: RH(uint16_t); break;
-	case VB200_FORMAT_SHORT: RH(int16_t); break;
-	case VB200_FORMAT_UINT: RH(uint32_t); break;
-	case VB200_FORMAT_INT: RH(int32_t); break;
-	case VB200_FORMAT_FLOAT: RH(float); break;
-	default:
-		dev_free(block, s);
-		error(domain, "band format %d not supported on the device path", fmt);
-		return -1;
-	}
-#undef RH
-	int r = check_launch(domain, "reduceh kernel");
+	const int r = run_reduceh(domain, in, in_bpl, in_w, out, out_bpl, bands, out_cols, rows, fmt, d,
+		fmt == VB200_FORMAT_UCHAR && bands == 4 ? reduceh_dp2a_smem(t, out_cols) : 0, s);
 	dev_free(block, s);
 	return r;
 }
@@ -650,22 +971,24 @@ int
 dev_reducev_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel, int rect_h,
 	cudaStream_t s)
 {
-	AxisTable t;
-	build_axis_table(t, g.out_size, g.residual, g.offset, g.n_point, kernel, rect_h);
+	const std::shared_ptr<AxisPlan> ap = axis_plan(domain, g, kernel, rect_h, true);
+	if (!ap)
+		return -1;
 	if (dev_image_new(domain, out, in.w, g.out_size, in.bands, in.fmt, in.type, s))
 		return -1;
-	return launch_reducev(domain, in.data, in.bpl, in.h, out->data, out->bpl, in.w * in.bands, g.out_size, in.fmt, t, s);
+	return run_reducev(domain, in.data, in.bpl, in.h, out->data, out->bpl, in.w * in.bands, g.out_size, in.fmt, ap->d, ap->v_smem, s);
 }
 
 int
 dev_reduceh_pass(const char *domain, const DevImage &in, DevImage *out, const ReduceGeom &g, int kernel, int rect_w,
 	cudaStream_t s)
 {
-	AxisTable t;
-	build_axis_table(t, g.out_size, g.residual, g.offset, g.n_point, kernel, rect_w);
+	const std::shared_ptr<AxisPlan> ap = axis_plan(domain, g, kernel, rect_w, false);
+	if (!ap)
+		return -1;
 	if (dev_image_new(domain, out, g.out_size, in.h, in.bands, in.fmt, in.type, s))
 		return -1;
-	return launch_reduceh(domain, in.data, in.bpl, in.w, out->data, out->bpl, in.bands, g.out_size, in.h, in.fmt, t, s);
+	return run_reduceh(domain, in.data, in.bpl, in.w, out->data, out->bpl, in.bands, g.out_size, in.h, in.fmt, ap->d, ap->h_smem, s);
 }
 
 int

@@ -384,8 +384,10 @@ extern "C" void
 vb200_shutdown(void)
 {
 	std::lock_guard<std::mutex> lock(g_init_lock);
-	if (g_device.load() >= 0)
+	if (g_device.load() >= 0) {
 		cudaDeviceSynchronize();
+		resample_cache_clear();
+	}
 	g_device.store(-1);
 }
 

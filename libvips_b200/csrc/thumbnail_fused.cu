@@ -87,6 +87,7 @@ struct FusedParams {
 	int mma_rows;		 /* output rows per chunk (4 .. 8) */
 	/* alpha */
 	int premul;		  /* 1: premultiply/unpremultiply with max_alpha */
+	const unsigned char *opaque_hint; /* v4: [frames of the launch] 1 = arm the V warps' opaque-stage vote for this frame; nullptr = never */
 	double max_alpha; /* LUTs are derived from it in the prologue */
 };
 
@@ -1436,6 +1437,17 @@ struct ThumbnailPlanImpl {
 	int stage_frames = 0;
 	std::mutex pump_lock;
 	std::mutex launch_lock;
+	/* the opaque-stage vote of the tensor-pipe kernel (thumbnail_fused_mma.cuh): per-launch counts of hinted frames
+	 * come back through pinned memory, a few launches late; opaque_mode picks the instantiation of the NEXT launch
+	 */
+	static constexpr int kHintSlots = 4;
+	std::mutex hint_lock;
+	int *hint_counts = nullptr; /* pinned [kHintSlots] */
+	cudaEvent_t hint_done[kHintSlots] = {nullptr, nullptr, nullptr, nullptr};
+	bool hint_pending[kHintSlots] = {false, false, false, false};
+	unsigned hint_slot_seq[kHintSlots] = {0, 0, 0, 0};
+	unsigned hint_seq = 0, hint_seen = 0;
+	bool opaque_mode = false;
 	/* 3-band frames (what a JPEG decodes to) on the fused RGBA kernels: expanded to RGBX on the device */
 	bool rgb_expand = false;
 	/* linear = TRUE: the two-kernel linear-light path (thumbnail_linear.cu), or null = the leaf chain */
@@ -1622,24 +1634,159 @@ make_stage_tensor_map(CUtensorMap *tm, const void *in, int W, int H, size_t in_b
 			   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+/* Arms the tensor-pipe kernel's opaque-stage vote per frame: 128 threads sample 2 pixels each, spread over the
+ * frame by a multiplicative hash; the hint is set where at least a quarter of the samples have alpha 255, and
+ * *count receives the number of hinted frames.  A hint, not a promise: the V warps still vote on every stage they
+ * skip the premultiply for.
+ */
+constexpr int kHintThreads = 128, kHintSamples = 2;
+
+__global__ void __launch_bounds__(kHintThreads)
+alpha_hint_kernel(const uint8_t *__restrict__ in, size_t in_frame_stride, size_t in_bpl, int W, int H, unsigned char *__restrict__ hint,
+	int *__restrict__ count)
+{
+	const uint8_t *f = in + (size_t) blockIdx.x * in_frame_stride;
+	const unsigned npix = (unsigned) W * (unsigned) H;
+	int opaque = 0;
+#pragma unroll
+	for (int i = 0; i < kHintSamples; i++) {
+		const unsigned k = (unsigned) (threadIdx.x * kHintSamples + i);
+		const unsigned p = (unsigned) (((unsigned long long) (k * 2654435761u) * npix) >> 32); /* 0 .. npix - 1 */
+		const unsigned y = p / (unsigned) W, x = p - y * (unsigned) W;
+		opaque += f[(size_t) y * in_bpl + (size_t) x * 4 + 3] == 255;
+	}
+	__shared__ int s_sum;
+	if (threadIdx.x == 0)
+		s_sum = 0;
+	__syncthreads();
+	opaque = __reduce_add_sync(0xffffffffu, opaque);
+	if ((threadIdx.x & 31) == 0)
+		atomicAdd(&s_sum, opaque);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int h = s_sum * 4 >= kHintThreads * kHintSamples ? 1 : 0;
+		hint[blockIdx.x] = (unsigned char) h;
+		if (h)
+			atomicAdd(count, 1);
+	}
+}
+
+/* Before a launch: harvest the counts of earlier launches that have completed (never waits), decide the
+ * instantiation, and run the hint kernel for this launch's frames.  *hint = nullptr when the vote is off.
+ */
+int
+opaque_hint_begin(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride, int n,
+	cudaStream_t s, void **hint, bool *use_opq)
+{
+	*hint = nullptr;
+	*use_opq = false;
+	const char *probe_env = getenv("VB200_OPAQUE_PROBE"); /* 0: never (A/B timing); 2: always use the voting instantiation */
+	if (!VB200_V4_OPAQUE || !pl->premul || (probe_env && probe_env[0] == '0'))
+		return 0;
+	{
+		std::lock_guard<std::mutex> lock(pl->hint_lock);
+		if (!pl->hint_counts) {
+			if (cudaHostAlloc((void **) &pl->hint_counts, sizeof(int) * ThumbnailPlanImpl::kHintSlots, cudaHostAllocDefault) != cudaSuccess) {
+				cudaGetLastError();
+				pl->hint_counts = nullptr;
+				return 0; /* no vote, same pixels */
+			}
+			for (int i = 0; i < ThumbnailPlanImpl::kHintSlots; i++)
+				cudaEventCreateWithFlags(&pl->hint_done[i], cudaEventDisableTiming);
+		}
+		for (int i = 0; i < ThumbnailPlanImpl::kHintSlots; i++)
+			if (pl->hint_pending[i] && cudaEventQuery(pl->hint_done[i]) == cudaSuccess) {
+				pl->hint_pending[i] = false;
+				if (pl->hint_slot_seq[i] + 1 > pl->hint_seen) {
+					pl->hint_seen = pl->hint_slot_seq[i] + 1;
+					pl->opaque_mode = pl->hint_counts[i] > 0;
+				}
+			}
+		cudaGetLastError(); /* cudaErrorNotReady from the queries */
+		*use_opq = pl->opaque_mode || (probe_env && probe_env[0] == '2');
+	}
+	const size_t count_off = ((size_t) n + 3) & ~(size_t) 3;
+	if (dev_alloc(domain, hint, count_off + sizeof(int), s))
+		return -1;
+	int *count = (int *) ((char *) *hint + count_off);
+	VB200_CUDA(domain, cudaMemsetAsync(count, 0, sizeof(int), s));
+	alpha_hint_kernel<<<n, kHintThreads, 0, s>>>((const uint8_t *) in, in_stride, fp.in_bpl, fp.W, fp.H, (unsigned char *) *hint, count);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		dev_free(*hint, s);
+		*hint = nullptr;
+		return cuda_fail(domain, e, "alpha_hint_kernel launch");
+	}
+	count_launch();
+	return 0;
+}
+
+/* After the launch: send this launch's count home and release the hint buffer (stream-ordered). */
+void
+opaque_hint_end(ThumbnailPlanImpl *pl, void *hint, int n, cudaStream_t s)
+{
+	if (!hint)
+		return;
+	{
+		std::lock_guard<std::mutex> lock(pl->hint_lock);
+		const int slot = (int) (pl->hint_seq % ThumbnailPlanImpl::kHintSlots);
+		if (!pl->hint_pending[slot]) {
+			const int *count = (const int *) ((const char *) hint + (((size_t) n + 3) & ~(size_t) 3));
+			if (cudaMemcpyAsync(&pl->hint_counts[slot], count, sizeof(int), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+				cudaEventRecord(pl->hint_done[slot], s) == cudaSuccess) {
+				pl->hint_pending[slot] = true;
+				pl->hint_slot_seq[slot] = pl->hint_seq;
+			}
+			cudaGetLastError();
+		}
+		pl->hint_seq++;
+	}
+	dev_free(hint, s);
+}
+
+template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT, bool OPQ>
+int
+launch_mma_k(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const CUtensorMap &tm, int use_tmap, const void *in,
+	size_t in_stride, void *out, size_t out_stride, int f0, dim3 grid, cudaStream_t s)
+{
+	auto kern = thumbnail_fused_mma_kernel<VS, NP, PREMUL, HSQ, WCOLS, CPT, OPQ>;
+	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_mma));
+	kern<<<grid, fp.NT + 32 * V4HWarpsW<WCOLS, CPT>::value + 32, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride,
+		(uint8_t *) out, out_stride, f0);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return cuda_fail(domain, e, "thumbnail_fused_mma_kernel launch");
+	count_launch();
+	return 0;
+}
+
 template <int VS, int NP, bool PREMUL, int HSQ, int WCOLS, int CPT>
 int
 launch_mma_t(const char *domain, ThumbnailPlanImpl *pl, const FusedParams &fp, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, dim3 grid, cudaStream_t s)
 {
-	auto kern = thumbnail_fused_mma_kernel<VS, NP, PREMUL, HSQ, WCOLS, CPT>;
-	VB200_CUDA(domain, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pl->smem_mma));
 	CUtensorMap tm;
 	memset(&tm, 0, sizeof(tm));
 	const int use_tmap = make_stage_tensor_map(&tm, in, fp.W, fp.H, fp.in_bpl, in_stride, n, (WCOLS + 8) / (WCOLS + 8 > 512 ? 2 : 1), 2 * VS) ? 1 : 0;
+	/* the opaque-stage vote exists for the configuration real batches run: premultiplied, 768-column bands */
+	constexpr bool CAN_OPQ = PREMUL && CPT == 2 && WCOLS > 448;
 	for (int f0 = 0; f0 < n; f0 += 32768) {
 		grid.z = std::min(32768, n - f0);
-		kern<<<grid, fp.NT + 32 * V4HWarpsW<WCOLS, CPT>::value + 32, pl->smem_mma, s>>>(fp, tm, use_tmap, (const uint8_t *) in, in_stride, (uint8_t *) out,
-			out_stride, f0);
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess)
-			return cuda_fail(domain, e, "thumbnail_fused_mma_kernel launch");
-		count_launch();
+		FusedParams fpl = fp;
+		void *hint = nullptr;
+		bool use_opq = false;
+		if (CAN_OPQ && opaque_hint_begin(domain, pl, fp, (const uint8_t *) in + (size_t) f0 * in_stride, in_stride, (int) grid.z, s, &hint, &use_opq))
+			return -1;
+		fpl.opaque_hint = (const unsigned char *) hint;
+		int rc;
+		if constexpr (CAN_OPQ)
+			rc = use_opq ? launch_mma_k<VS, NP, PREMUL, HSQ, WCOLS, CPT, true>(domain, pl, fpl, tm, use_tmap, in, in_stride, out, out_stride, f0, grid, s)
+						 : launch_mma_k<VS, NP, PREMUL, HSQ, WCOLS, CPT, false>(domain, pl, fpl, tm, use_tmap, in, in_stride, out, out_stride, f0, grid, s);
+		else
+			rc = launch_mma_k<VS, NP, PREMUL, HSQ, WCOLS, CPT, false>(domain, pl, fpl, tm, use_tmap, in, in_stride, out, out_stride, f0, grid, s);
+		opaque_hint_end(pl, hint, (int) grid.z, s);
+		if (rc)
+			return rc;
 	}
 	return 0;
 }
@@ -1842,6 +1989,7 @@ plan_build_fused(const char *domain, ThumbnailPlanImpl *pl)
 	fp.out_bpl = (size_t) pl->OW * 4;
 	fp.premul = pl->premul;
 	fp.max_alpha = 255.0;
+	fp.opaque_hint = nullptr; /* set per launch (launch_mma_t) */
 	fp.nvsets = (int) sv.ids.size();
 	fp.nhsets = (int) shh.ids.size();
 	if (fp.VS > 256 || fp.HS > 256)
@@ -2344,6 +2492,13 @@ thumbnail_plan_destroy(ThumbnailPlanImpl *pl)
 	if (pl->lin)
 		linear_thumb_free(pl->lin);
 	pl->lin = nullptr;
+	for (int i = 0; i < ThumbnailPlanImpl::kHintSlots; i++)
+		if (pl->hint_done[i]) {
+			cudaEventSynchronize(pl->hint_done[i]);
+			cudaEventDestroy(pl->hint_done[i]);
+		}
+	if (pl->hint_counts)
+		cudaFreeHost(pl->hint_counts);
 	for (int i = 0; i < ThumbnailPlanImpl::kStreams; i++) {
 		if (pl->stage_in[i])
 			cudaFree(pl->stage_in[i]);

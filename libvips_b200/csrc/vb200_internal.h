@@ -154,6 +154,7 @@ int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int s
 /* Launchers of the row/column-table kernels on raw device pointers (used by
  * the generate()-shaped and scanline seams too).
  */
+void resample_cache_clear(); /* cached axis tables (resample_kernels.cu); vb200_shutdown */
 int launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne,
 	int out_rows, int fmt, const AxisTable &t, cudaStream_t s);
 int launch_reduceh(const char *domain, const void *in, size_t in_bpl, int in_w, void *out, size_t out_bpl, int bands,

@@ -227,9 +227,19 @@ def test_gpu_lch_routes_within_one_ulp(vb, src, dst):
         d = np.abs(got.astype(np.float64) - want)
         ok = (ulp_diff(got, want) <= (2 if src == "lch" else 1)) | (d < 2e-5)
         if (src, dst) == ("lch", "yxy"):
-            # two more steps after the trigonometric one (Lab2XYZ cubes its input): the last-place difference of
-            # cosf / sinf grows to a few ULP of XYZ -- still 1e-5 relative
-            ok |= d <= 1e-5 * np.maximum(np.abs(want), 1.0)
+            # two more steps after the trigonometric one.  Lab2XYZ cubes its input: the last-place difference of
+            # cosf / sinf grows to a few ULP of XYZ -- still 1e-5 relative.  XYZ2Yxy then divides by X + Y + Z, which the
+            # wild samples bring arbitrarily close to zero, so a bound on x / y themselves would be a bound on luck:
+            # hold XYZ to the tolerance, and Yxy to the (exact, test_gpu_yxy_routes_exact) last step applied to the
+            # device's own XYZ -- the fused route keeps float intermediates exactly like the reference's float images
+            got_xyz = vb.Image(a, src).colourspace("xyz").numpy()
+            want_xyz = orc.colourspace(a, "xyz", src)
+            dx = np.abs(got_xyz.astype(np.float64) - want_xyz)
+            okx = (ulp_diff(got_xyz, want_xyz) <= 8) | (dx <= 1e-5 * np.maximum(np.abs(want_xyz), 1.0))
+            assert okx.all(), (src, "xyz", dx.max())
+            assert np.array_equal(got, orc.colourspace(got_xyz, "yxy", "xyz"), equal_nan=True)
+            assert (got == want).mean() > 0.8
+            return
         assert ok.all(), (src, dst, d.max())
         # cosf / sinf differ from glibc's in the last place on ~1 value in 9; the double atan() path on < 1 in 100
         assert (got == want).mean() > (0.8 if src == "lch" else 0.99)

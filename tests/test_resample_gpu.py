@@ -8,6 +8,7 @@ Structure follows the reference's test/test-suite/test_resample.py: every
 format x kernel x factor, constant images, geometry/rounding, thumbnails.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -84,6 +85,30 @@ def test_reduce_49_tap(vb, oracle):
     v = vb.Image(a).reducev(8.0).numpy()
     same(v, oracle.reducev(a, 8.0, "lanczos3", 0.0, rect_h=16))
     same(vb.Image(v).reduceh(8.0).numpy(), oracle.reduceh(v, 8.0, "lanczos3", 0.0, rect_w=0))
+
+
+@pytest.mark.parametrize("kernel", ["lanczos3", "lanczos2", "cubic", "linear", "nearest", "mks2021"])
+def test_reduce_uchar_dp2a_kernels(vb, oracle, kernel):
+    """The register-blocked IDP.2A leaf kernels (reducev_u8_dp2a_kernel: any band count with 4-byte rows,
+    reduceh_u8x4_dp2a_kernel: RGBA): even / odd tap counts, factors whose per-rect stepping changes phase from
+    tile to tile, windows hanging over both edges, images smaller than a row block / a CTA's span, row counts that
+    are not a multiple of the block, and a tap count too large for their shared memory (falls back)."""
+    rng = np.random.default_rng(11)
+    for (h, w, b) in ((301, 260, 4), (67, 36, 4), (130, 512, 3), (5, 8, 4), (97, 1031, 4)):
+        a = rand_image(rng, h, w, b, np.uint8)
+        for fac in (1.0, 1.7, 2.0, 2.37, 3.3, 8.0, 13.0):
+            if fac > min(h, w):
+                continue
+            same(vb.Image(a).reducev(fac, kernel=kernel).numpy(), oracle.reducev(a, fac, kernel, 0.0, rect_h=16))
+            same(vb.Image(a).reduceh(fac, kernel=kernel).numpy(), oracle.reduceh(a, fac, kernel, 0.0, rect_w=0))
+    a = rand_image(rng, 2100, 64, 4, np.uint8)
+    same(vb.Image(a).reducev(49.0, kernel=kernel).numpy(), oracle.reducev(a, 49.0, kernel, 0.0, rect_h=16))
+    a = rand_image(rng, 16, 2100, 4, np.uint8)
+    same(vb.Image(a).reduceh(49.0, kernel=kernel).numpy(), oracle.reduceh(a, 49.0, kernel, 0.0, rect_w=0))
+    # extremes that would overflow anything narrower than the reference's int sums
+    for const in (0, 255):
+        a = np.full((64, 64, 4), const, np.uint8)
+        same(vb.Image(a).reduce(8.0, 8.0, kernel=kernel).numpy(), oracle.reduceh(oracle.reducev(a, 8.0, kernel, 0.0, rect_h=16), 8.0, kernel, 0.0, rect_w=0))
 
 
 @pytest.mark.parametrize("dt", [np.uint8, np.uint16, np.int16, np.float32])
@@ -297,6 +322,40 @@ def test_thumbnail_tensor_pipe_kernel(vb, oracle, case):
     assert ("mma_kernel" in plan.kernel) == mma, plan.kernel
     want = np.stack([oracle.thumbnail_image(f, tw, th, size, has_alpha=alpha) for f in frames])
     same(plan.run_host(frames), want)
+
+
+@pytest.mark.parametrize("shape", [(2048, 2048, 256), (1200, 900, 150), (4096, 4096, 256)], ids=lambda c: "%dx%d-%d" % c)
+def test_thumbnail_opaque_stage_vote(vb, oracle, shape):
+    """The tensor-pipe kernel's opaque fast path (a warp whose stage holds only alpha 255 skips the premultiply
+    arithmetic; a warp that met live alpha probes every 8th stage): opaque frames, one stray pixel, alpha 254,
+    opaque / live blocks finer and coarser than a warp's columns and a stage's rows, and the probe turned off."""
+    w, h, tw = shape
+    rng = np.random.default_rng(w + h)
+    frames = rng.integers(0, 256, (6, h, w, 4), dtype=np.uint8)
+    frames[0, :, :, 3] = 255                                 # opaque
+    frames[1, :, :, 3] = 255
+    frames[1, h // 2 + 3, w // 3 + 1, 3] = 17                # one live pixel in an opaque frame
+    frames[2, :, :, 3] = 254                                 # nearly
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames[3, :, :, 3] = np.where(((yy // 8) + (xx // 64)) % 2 == 0, 255, frames[3, :, :, 3])    # stage x warp checkerboard
+    frames[4, :, :, 3] = np.where((yy // 97) % 3 != 1, 255, frames[4, :, :, 3])                  # long opaque / live runs of rows
+    frames[5, :, :, 3] = np.where((xx // 5) % 7 == 0, frames[5, :, :, 3], 255)                   # live columns inside every warp
+    plan = vb.ThumbnailPlan(w, h, 4, tw)
+    assert "mma_kernel" in plan.kernel, plan.kernel
+    want = np.stack([oracle.thumbnail_image(f, tw) for f in frames])
+    # VB200_OPAQUE_PROBE: 2 = the voting instantiation from the first launch on, 0 = never, unset = a plan
+    # switches to it once the hints of its earlier batches (read back asynchronously) found opaque frames
+    for mode in ("2", "0", None):
+        if mode is None:
+            os.environ.pop("VB200_OPAQUE_PROBE", None)
+        else:
+            os.environ["VB200_OPAQUE_PROBE"] = mode
+        try:
+            for _ in range(3 if mode is None else 1):
+                same(plan.run_host(frames), want)
+                same(plan.run_host(frames[2:3]), want[2:3])     # a batch without a hinted frame in between
+        finally:
+            os.environ.pop("VB200_OPAQUE_PROBE", None)
 
 
 @pytest.mark.parametrize("pad,shift", [(0, 0), (4096, 0), (48, 0), (20, 0), (0, 4)])
