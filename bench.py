@@ -249,6 +249,22 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+_JPEG_CPU = None
+
+
+def _jpeg_cpu_worker(i):
+    """one frame the reference's way on the host: libjpeg-turbo shrink-on-load, then the thumbnail chain"""
+    import io
+    import numpy as np
+    from PIL import Image
+    from oracle import pyoracle
+    distinct, shrink = _JPEG_CPU
+    im = Image.open(io.BytesIO(distinct[i % len(distinct)]))
+    im.draft("RGB", (W // shrink, H // shrink))
+    a = np.asarray(im)[: H // shrink, : W // shrink]
+    return int(pyoracle.thumbnail_image(a, TARGET)[0, 0, 0])
+
+
 def side_workload(args):
     """BASELINE.json configs 1, 3, 4 on one GPU, device-resident, CUDA events: not the
     headline line, the rows of BASELINE.md's results table."""
@@ -435,6 +451,83 @@ def side_workload(args):
             cpu["kind"] = "reference"
         run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_icc_import + vips_icc_export (sRGB-like v4 profile) on 8192x8192",
             2 * n * n / 1e6, "Mpixels/s", cpu)
+    elif args.workload in ("thumbnail_jpeg", "thumbnail_jpeg_norestart"):
+        # vips_thumbnail_buffer() of JPEG streams.  Host memory holds only the COMPRESSED frames; the
+        # shrink-on-load decode (thumbnail.c:489-517 picks 1/4 for 4K -> 512) and the thumbnail run on the device.
+        # End to end by construction: every step uploads its streams.  The CPU side is the reference's own recipe:
+        # libjpeg-turbo (the one inside Pillow) at scale 1/4, then the thumbnail chain (oracle port), one frame per process.
+        import io
+        from PIL import Image
+        restart = args.workload == "thumbnail_jpeg"
+        F = max(1, min(args.frames, 256 if restart else 1024))
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+        distinct = []
+        for i in range(8):
+            rng = np.random.default_rng(100 + i)
+            img = np.stack([128 + 100 * np.sin(xx / (37.0 + i) + yy / 91.0), 128 + 90 * np.cos(xx / 53.0 - yy / (29.0 + i)),
+                            np.mod(xx * 3 + yy * 5, 256)], -1) + rng.normal(0, 10, (H, W, 3)).astype(np.float32)
+            b = io.BytesIO()
+            Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(b, "JPEG", quality=85, subsampling=2,
+                                                                     **({"restart_marker_rows": 1} if restart else {}))
+            distinct.append(b.getvalue())
+        del yy, xx
+        streams = [distinct[i % len(distinct)] for i in range(F)]
+        batch = vb.JpegBatch(streams)
+        shrink = vb.thumbnail_jpegshrink(W, H, TARGET)
+        dw, dh, db = vb.jpeg_geometry(batch, shrink)
+        plan = vb.ThumbnailPlan(dw, dh, db, TARGET)
+        outs = torch.empty((F, plan.out_height, plan.out_width, db), dtype=torch.uint8, device=dev)
+
+        def turbo(data):
+            im = Image.open(io.BytesIO(data))
+            im.draft("RGB", (W // shrink, H // shrink))
+            return np.asarray(im)[: H // shrink, : W // shrink]
+
+        def fn():
+            plan.run_jpeg(batch, shrink, out_ptr=outs.data_ptr())
+        fn()
+        from oracle import pyoracle
+        want = pyoracle.thumbnail_image(turbo(streams[0]), TARGET)
+        assert np.array_equal(outs[0].cpu().numpy(), want), "GPU JPEG thumbnail differs from libjpeg-turbo + the oracle"
+        for _ in range(max(0, args.warmup - 1)):
+            fn()
+        os.environ["VB200_JPEG_TIMING"] = "1"
+        fn()
+        hm, im = C.c_float(), C.c_float()
+        L.vb200_debug_jpeg_times(C.byref(hm), C.byref(im))
+        del os.environ["VB200_JPEG_TIMING"]
+        torch.cuda.synchronize()
+        n0 = vb.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        cpu = None
+        if not args.no_cpu:
+            import multiprocessing as mp
+            threads = host_threads()
+            global _JPEG_CPU
+            _JPEG_CPU = (distinct, shrink)
+            with mp.get_context("fork").Pool(threads) as pool:
+                pool.map(_jpeg_cpu_worker, range(threads))
+                t1 = time.perf_counter()
+                pool.map(_jpeg_cpu_worker, range(2 * threads))
+                ct = time.perf_counter() - t1
+            cpu = {"value": 2 * threads * MPIX_PER_FRAME / ct, "unit": "Mpixels/s", "cores": threads, "kind": "reference + port",
+                   "sample": "%d frames: libjpeg-turbo (Pillow's) decode at scale 1/%d, then the oracle port of the thumbnail chain, "
+                             "one frame per process" % (2 * threads, shrink)}
+        label = ("vips_thumbnail_buffer: 4096x4096 4:2:0 JPEG streams (q85, %s) -> shrink-on-load 1/%d on the device -> 512x512, %d frames per step"
+                 % ("one restart interval per MCU row" if restart else "no restart markers", shrink, F))
+        print(json.dumps({"metric": label, "value": F * MPIX_PER_FRAME / dt, "unit": "Mpixels/s (input pixels)", "n_gpus": 1,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "dtype": "u8",
+                          "data": "synthetic", "config": {"workload": label, "device_resident": False, "frames_per_second": F / dt,
+                                                          "compressed_bytes_per_frame": batch.nbytes / F},
+                          "kernels": {"jpeg_huffman_kernel_ms": hm.value, "jpeg_idct_kernel_ms": im.value,
+                                      "note": "CUDA events over one step (chunks serialised for the measurement)"},
+                          "e2e": {"value": F * MPIX_PER_FRAME / dt, "unit": "Mpixels/s", "h2d_bytes_per_step": batch.nbytes,
+                                  "d2h_bytes_per_step": 0, "api": "vb200_thumbnail_plan_run_jpeg"},
+                          "cpu_baseline": cpu, "gpu_launches": int(vb.launch_count() - n0)}))
     else:
         raise SystemExit("unknown workload %s" % args.workload)
 
@@ -453,7 +546,7 @@ def main():
                          "transparency decodes to: the kernel's opaque-stage fast path; a second line, never the headline)")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
-                         "--gpus N like the headline) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
+                         "--gpus N like the headline) | thumbnail_jpeg | thumbnail_jpeg_norestart (decode staging, SURVEY 8f) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 

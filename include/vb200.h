@@ -383,6 +383,35 @@ int vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_s
 	int *n_point, int *embed, int *first, int *phase, short *mask65, int *vchunk, unsigned *bfrag, int cap_rows,
 	int *rows_per_chunk);
 
+/* ------------------------------------------------------------------ JPEG decode staging
+ * vips_jpegload_buffer(buf, len, &out, "shrink", shrink) (foreign/jpeg2vips.c:532-538, 631-640: scale_num = 1,
+ * scale_denom = shrink, output cropped to floor(size / shrink)) with the decoder on the device: the compressed
+ * bytes are all that crosses PCIe.  libjpeg(-turbo) itself is a third-party dependency outside the reference
+ * tree; its algorithm for the reference's configuration (JDCT_ISLOW, 8-bit Huffman baseline / extended
+ * sequential) is restated in csrc/jpeg.cu and pinned bit for bit to the libjpeg-turbo inside this image's Pillow
+ * (tests/test_jpeg.py).  Decoded: greyscale, 4:4:4 at shrink 1 / 2 / 4 / 8, 4:2:0, 4:2:2 and 4:4:0 at the shrinks
+ * where libjpeg's upsampler is the identity (4:2:0: 2, 4, 8 -- what vips_thumbnail asks for).  Progressive,
+ * arithmetic, 12-bit, CMYK / RGB-coded streams and full-size subsampled decodes return -1 (host loader).
+ *
+ * vb200_jpeg_decode_batch: n streams of ONE output geometry -> out[n][height][width][bands] uchar (bands 1 or 3),
+ *   out in host or device memory (out_location VB200_HOST / VB200_DEVICE); out = NULL only reports the geometry.
+ * vb200_jpegload_buffer: one stream into a VB200Image (allocate-or-fill like every op).
+ * vb200_thumbnail_jpegshrink: the load-time shrink vips_thumbnail picks (resample/thumbnail.c:489-517).
+ * vb200_thumbnail_plan_run_jpeg: decode at `shrink` + the plan's thumbnail chain, frames never leave the device;
+ *   the plan must have been made for the decoded geometry (3 bands).
+ * vb200_debug_jpeg_decode: test hook, host only -- the same per-block code on the CPU.
+ */
+int vb200_jpeg_decode_batch(const void *const *bufs, const size_t *lens, int n, int shrink, void *out, int out_location,
+	size_t out_bpl, size_t out_frame_stride, int *width, int *height, int *bands);
+int vb200_jpegload_buffer(const void *buf, size_t len, int shrink, VB200Image *out);
+int vb200_thumbnail_jpegshrink(int width, int height, int target_width, int target_height, int size);
+int vb200_thumbnail_plan_run_jpeg(VB200ThumbnailPlan *plan, const void *const *bufs, const size_t *lens, int n, int shrink,
+	void *out, int out_location, size_t out_frame_stride);
+int vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height,
+	int *bands);
+/* with env VB200_JPEG_TIMING: CUDA-event times of jpeg_huffman_kernel / jpeg_idct_kernel over the calling thread's last decode */
+void vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms);
+
 /* Pinned host memory for the pump: page-locked and, on a multi-socket machine, placed on the NUMA
  * node the current device hangs off (falls back to cudaHostAlloc).  vb200_device_numa_node():
  * that node, or -1 (unknown / single node).

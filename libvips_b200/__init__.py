@@ -99,6 +99,13 @@ def lib():
         L.vb200_image_free.argtypes = [IP]
         L.vb200_thumbnail_plan_new.restype = C.c_void_p
         L.vb200_thumbnail_plan_new.argtypes = [C.c_int] * 9
+        PI = C.POINTER(C.c_int)
+        L.vb200_jpeg_decode_batch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                              C.c_size_t, C.c_size_t, PI, PI, PI]
+        L.vb200_debug_jpeg_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, PI, PI, PI]
+        L.vb200_thumbnail_jpegshrink.argtypes = [C.c_int] * 5
+        L.vb200_thumbnail_plan_run_jpeg.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int,
+                                                    C.c_void_p, C.c_int, C.c_size_t]
         L.vb200_thumbnail_plan_free.argtypes = [C.c_void_p]
         L.vb200_thumbnail_plan_output.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.vb200_thumbnail_plan_bytes_per_frame.restype = C.c_size_t
@@ -329,6 +336,58 @@ class Image:
                           INTENTS[intent], int(depth))
 
 
+class JpegBatch:
+    """n JPEG streams (bytes objects) as the pointer / length arrays the C ABI takes; keeps them alive."""
+
+    def __init__(self, streams):
+        self.streams = [bytes(s) for s in streams]
+        self.n = len(self.streams)
+        self._bufs = [C.create_string_buffer(s, len(s)) for s in self.streams]
+        self.ptrs = (C.c_void_p * self.n)(*[C.cast(b, C.c_void_p) for b in self._bufs])
+        self.lens = (C.c_size_t * self.n)(*[len(s) for s in self.streams])
+        self.nbytes = sum(len(s) for s in self.streams)
+
+
+def jpeg_geometry(streams, shrink=1):
+    """(width, height, bands) the streams decode to at `shrink` (they must agree); no GPU needed"""
+    b = streams if isinstance(streams, JpegBatch) else JpegBatch(streams)
+    w, h, bands = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().vb200_jpeg_decode_batch(b.ptrs, b.lens, b.n, int(shrink), None, HOST, 0, 0, C.byref(w), C.byref(h), C.byref(bands)))
+    return w.value, h.value, bands.value
+
+
+def jpeg_decode_batch(streams, shrink=1, out_ptr=None):
+    """vips_jpegload_buffer(..., shrink=shrink) of every stream on the device -> uint8 [n, h, w, bands] (host),
+    or into the device pointer out_ptr (packed frames)"""
+    b = streams if isinstance(streams, JpegBatch) else JpegBatch(streams)
+    w, h, bands = jpeg_geometry(b, shrink)
+    ww, hh, bb = C.c_int(), C.c_int(), C.c_int()
+    if out_ptr is not None:
+        _check(lib().vb200_jpeg_decode_batch(b.ptrs, b.lens, b.n, int(shrink), C.c_void_p(out_ptr), DEVICE, w * bands, w * h * bands,
+                                             C.byref(ww), C.byref(hh), C.byref(bb)))
+        return w, h, bands
+    out = np.empty((b.n, h, w, bands), np.uint8)
+    _check(lib().vb200_jpeg_decode_batch(b.ptrs, b.lens, b.n, int(shrink), out.ctypes.data_as(C.c_void_p), HOST, w * bands,
+                                         w * h * bands, C.byref(ww), C.byref(hh), C.byref(bb)))
+    return out
+
+
+def jpeg_decode_host_twin(stream, shrink=1):
+    """the decoder's per-block code compiled for the host (vb200_debug_jpeg_decode): what the CPU tests pin to libjpeg-turbo"""
+    stream = bytes(stream)
+    w, h, bands = C.c_int(), C.c_int(), C.c_int()
+    _check(lib().vb200_debug_jpeg_decode(stream, len(stream), int(shrink), None, 0, C.byref(w), C.byref(h), C.byref(bands)))
+    out = np.empty((h.value, w.value, bands.value), np.uint8)
+    _check(lib().vb200_debug_jpeg_decode(stream, len(stream), int(shrink), out.ctypes.data_as(C.c_void_p), w.value * bands.value,
+                                         C.byref(w), C.byref(h), C.byref(bands)))
+    return out
+
+
+def thumbnail_jpegshrink(width, height, target_width, target_height=None, size="both"):
+    """vips_thumbnail_find_jpegshrink (thumbnail.c:489-517)"""
+    return int(lib().vb200_thumbnail_jpegshrink(width, height, target_width, target_height or 0, SIZES[size]))
+
+
 class ThumbnailPlan:
     """The batched tile pump (vb200_thumbnail_plan_* in include/vb200.h)."""
 
@@ -376,6 +435,19 @@ class ThumbnailPlan:
     def run_host_ptr(self, in_ptr, out_ptr, n_frames):
         _check(lib().vb200_thumbnail_batch_host(self._p, C.c_void_p(in_ptr), self.in_frame_bytes,
                                                 C.c_void_p(out_ptr), self.out_frame_bytes, n_frames))
+
+    def run_jpeg(self, streams, shrink, out_ptr=None):
+        """JPEG streams decoded at `shrink` on the device and thumbnailed by this plan (made for the decoded
+        geometry): -> uint8 [n, OH, OW, bands] on the host, or into the device pointer out_ptr"""
+        b = streams if isinstance(streams, JpegBatch) else JpegBatch(streams)
+        if out_ptr is not None:
+            _check(lib().vb200_thumbnail_plan_run_jpeg(self._p, b.ptrs, b.lens, b.n, int(shrink), C.c_void_p(out_ptr), DEVICE,
+                                                       self.out_frame_bytes))
+            return None
+        out = np.empty((b.n, self.out_height, self.out_width, self.bands), np.uint8)
+        _check(lib().vb200_thumbnail_plan_run_jpeg(self._p, b.ptrs, b.lens, b.n, int(shrink), out.ctypes.data_as(C.c_void_p), HOST,
+                                                   self.out_frame_bytes))
+        return out
 
     def run_host(self, frames):
         """frames: uint8 array [n, H, W, bands] in host memory -> [n, OH, OW, bands]."""

@@ -29,10 +29,18 @@
  * that the CPU test-suite pins it against libjpeg-turbo without a GPU.
  */
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
+#include "../../include/vb200.h"
 #include "vb200_internal.h"
 
 namespace vb200 {
@@ -89,11 +97,13 @@ struct JpegFrameDev {
 	int huff_base;				   /* index of this frame's 8 HuffDev (dc 0..3, ac 0..3) */
 	unsigned short qt[kMaxComp][64];
 	int out_w, out_h, tile_w, tile_h; /* cropped output, and the MCU's footprint in output pixels */
+	int blocks_per_mcu;				  /* T.81 A.2.3: component by component, rows of blocks, left to right */
+	unsigned char blk_comp[12], blk_dx[12], blk_dy[12];
 };
 
 const unsigned char kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14,
 	21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-__constant__ unsigned char d_zigzag[64];
+__device__ unsigned char d_zigzag[64]; /* global, not __constant__: the lanes of a warp index it divergently */
 
 /* ------------------------------------------------------------------ host: marker parsing (T.81 B.2) */
 
@@ -350,11 +360,6 @@ plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp
 			return -1;
 		}
 	}
-	if (H.ncomp == 1 && (H.comp[0].h != 1 || H.comp[0].v != 1)) {
-		/* a single-component scan is never interleaved: its MCU is one block whatever the sampling factors say */
-		error(domain, "greyscale JPEG with sampling factors other than 1x1 is not supported on the device path");
-		return -1;
-	}
 	return 0;
 }
 
@@ -383,34 +388,65 @@ build_huff(const unsigned char count[16], const unsigned char *sym, HuffDev *t)
 /* ------------------------------------------------------------------ entropy decoding (host + device) */
 
 struct BitReader {
-	const unsigned char *p, *end;
-	unsigned long long acc; /* bits are consumed from the top */
+	const unsigned char *base; /* 4-byte aligned start of the frame's bytes (readable 8 bytes past any interval's end) */
+	unsigned pos, end;			/* byte offsets from base */
+	unsigned long long acc;		/* bits are consumed from the top */
 	int n;
 };
 
 HD void
-br_init(BitReader &b, const unsigned char *p, const unsigned char *end)
+br_init(BitReader &b, const unsigned char *base, unsigned pos, unsigned end)
 {
-	b.p = p;
+	b.base = base;
+	b.pos = pos;
 	b.end = end;
 	b.acc = 0;
 	b.n = 0;
 }
 
-/* at least 32 valid bits (zeros past the end of the interval, as jdhuff.c feeds on a premature end) */
+/* bytes pos .. pos + 3 as one big-endian word, from two aligned loads */
+HD unsigned
+br_load_be32(const unsigned char *base, unsigned pos)
+{
+	const unsigned *w = (const unsigned *) base + (pos >> 2);
+	const unsigned w0 = w[0], w1 = w[1];
+#ifdef __CUDA_ARCH__
+	return __byte_perm(w0, w1, 0x0123u + 0x1111u * (pos & 3u));
+#else
+	const unsigned long long both = (unsigned long long) w0 | ((unsigned long long) w1 << 32);
+	const unsigned le = (unsigned) (both >> (8 * (pos & 3u)));
+	return (le >> 24) | ((le >> 8) & 0xff00u) | ((le << 8) & 0xff0000u) | (le << 24);
+#endif
+}
+
+/* at least 32 valid bits (zeros past the end of the interval, as jdhuff.c feeds on a premature end).  Four bytes at
+ * a time while none of them is 0xFF (one in ~256 is); the byte path handles FF00 (a stuffed FF) and markers.
+ */
 HD void
 br_fill(BitReader &b)
 {
+	if (b.n > 32)
+		return;
+	if (b.pos + 4 <= b.end) {
+		const unsigned w = br_load_be32(b.base, b.pos);
+		const unsigned x = ~w;
+		if (((x - 0x01010101u) & ~x & 0x80808080u) == 0) { /* no 0xFF byte */
+			b.acc |= (unsigned long long) w << (32 - b.n);
+			b.n += 32;
+			b.pos += 4;
+			return;
+		}
+	}
 	while (b.n <= 56) {
 		unsigned v = 0;
-		if (b.p < b.end) {
-			v = *b.p++;
+		if (b.pos < b.end) {
+			v = b.base[b.pos++];
 			if (v == 0xFF) {
 				/* FF00 is a stuffed FF; anything else is a marker: the interval is over, feed zeros */
-				if (b.p < b.end && *b.p == 0x00)
-					b.p++;
+				if (b.pos < b.end && b.base[b.pos] == 0x00)
+					b.pos++;
 				else {
-					b.p = b.end;
+					b.pos = b.end;
 					v = 0;
 				}
 			}
@@ -465,52 +501,77 @@ br_receive_extend(BitReader &b, int s)
 }
 
 /* Decode the MCUs [mcu0, mcu1) of a frame from one restart interval's bytes into the coefficient planes.
+ * ONE loop, one symbol per trip, for DC and AC alike: the threads of a warp decode different intervals, and with
+ * the textbook nest (blocks / coefficients) a thread that ends its block early idles at the loop's reconvergence
+ * point until the slowest lane has ended its own; here every lane is always in the same few instructions.
  * Returns 0, or -1 on a bad code (the remaining blocks of the interval stay zero).
  */
 HD int
-decode_interval(const JpegFrameDev &F, const HuffDev *huff, const unsigned char *zz, const unsigned char *p, const unsigned char *end,
+decode_interval(const JpegFrameDev &F, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned pos, unsigned end,
 	int mcu0, int mcu1, short *coef_pool)
 {
+	if (mcu0 >= mcu1)
+		return 0;
 	BitReader b;
-	br_init(b, p, end);
-	int pred[kMaxComp] = {0, 0, 0};
-	for (int mcu = mcu0; mcu < mcu1; mcu++) {
-		const int my = mcu / F.mcus_x, mx = mcu - my * F.mcus_x;
-		for (int c = 0; c < F.ncomp; c++) {
-			const HuffDev *dc = huff + F.td[c], *ac = huff + 4 + F.ta[c];
-			for (int by = 0; by < F.v[c]; by++)
-				for (int bx = 0; bx < F.h[c]; bx++) {
-					short *blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + by) * F.blocks_x[c] + (size_t) (mx * F.h[c] + bx)) * 64;
-					br_fill(b);
-					int s = huff_decode(b, dc);
-					if (s < 0 || s > 11)
-						return -1;
-					pred[c] += br_receive_extend(b, s);
-					blk[0] = (short) pred[c];
-					for (int k = 1; k < 64;) {
-						br_fill(b);
-						const int rs = huff_decode(b, ac);
-						if (rs < 0)
-							return -1;
-						const int r = rs >> 4;
-						s = rs & 15;
-						if (s == 0) {
-							if (r != 15)
-								break; /* EOB */
-							k += 16;
-							continue;
-						}
-						k += r;
-						const int v = br_receive_extend(b, s);
-						if (k > 63)
-							return -1;
-						blk[zz[k]] = (short) v;
-						k++;
-					}
+	br_init(b, base, pos, end);
+	int pred0 = 0, pred1 = 0, pred2 = 0;
+	int mcu = mcu0, bi = 0, k = 0;
+	int my = mcu / F.mcus_x, mx = mcu - my * F.mcus_x;
+	int c = F.blk_comp[0];
+	const HuffDev *dc = huff + F.td[c], *ac = huff + 4 + F.ta[c];
+	short *blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + F.blk_dy[0]) * F.blocks_x[c] + (size_t) (mx * F.h[c] + F.blk_dx[0])) * 64;
+	for (;;) {
+		br_fill(b);
+		const bool isdc = k == 0;
+		const int sym = huff_decode(b, isdc ? dc : ac);
+		if (sym < 0)
+			return -1;
+		if (isdc) {
+			if (sym > 11)
+				return -1;
+			const int diff = br_receive_extend(b, sym);
+			int pr = c == 0 ? pred0 : (c == 1 ? pred1 : pred2);
+			pr += diff;
+			if (c == 0)
+				pred0 = pr;
+			else if (c == 1)
+				pred1 = pr;
+			else
+				pred2 = pr;
+			blk[0] = (short) pr;
+			k = 1;
+		}
+		else {
+			const int r = sym >> 4, sz = sym & 15;
+			if (sz == 0)
+				k = r == 15 ? k + 16 : 64; /* ZRL / EOB */
+			else {
+				k += r;
+				const int v = br_receive_extend(b, sz);
+				if (k > 63)
+					return -1;
+				blk[zz[k]] = (short) v;
+				k++;
+			}
+		}
+		if (k >= 64) {
+			/* next block of the MCU, or the next MCU */
+			k = 0;
+			if (++bi == F.blocks_per_mcu) {
+				bi = 0;
+				if (++mcu >= mcu1)
+					return 0;
+				if (++mx == F.mcus_x) {
+					mx = 0;
+					my++;
 				}
+			}
+			c = F.blk_comp[bi];
+			dc = huff + F.td[c];
+			ac = huff + 4 + F.ta[c];
+			blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + F.blk_dy[bi]) * F.blocks_x[c] + (size_t) (mx * F.h[c] + F.blk_dx[bi])) * 64;
 		}
 	}
-	return 0;
 }
 
 /* ------------------------------------------------------------------ inverse DCTs (jidctint.c, jidctred.c) */
@@ -807,7 +868,9 @@ reconstruct_mcu(const JpegFrameDev &F, const short *coef_pool, int mx, int my, u
 /* ------------------------------------------------------------------ kernels */
 
 /* one thread per restart interval of one frame; blockIdx.y = frame of the batch */
-__global__ void __launch_bounds__(64)
+constexpr int kHuffThreads = 32;
+
+__global__ void __launch_bounds__(kHuffThreads)
 jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__restrict__ huff, const unsigned char *__restrict__ bytes,
 	const unsigned *__restrict__ offsets, short *__restrict__ coef, int *__restrict__ status)
 {
@@ -820,7 +883,7 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 	const int total = F.mcus_x * F.mcus_y;
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
 	const int mcu0 = i * per, mcu1 = min(total, mcu0 + per);
-	if (decode_interval(F, huff + F.huff_base, d_zigzag, base + off[i], base + off[i + 1], mcu0, mcu1, coef))
+	if (decode_interval(F, huff + F.huff_base, d_zigzag, base, off[i], off[i + 1], mcu0, mcu1, coef))
 		atomicOr(status + blockIdx.y, 1);
 }
 
@@ -839,21 +902,21 @@ jpeg_idct_kernel(const JpegFrameDev *__restrict__ frames, const short *__restric
 	reconstruct_mcu(F, coef, mx, my, out + (size_t) blockIdx.y * out_frame_stride, out_bpl);
 }
 
-/* ------------------------------------------------------------------ host: batch preparation */
+/* ------------------------------------------------------------------ host: frame preparation and the pump */
 
-struct JpegBatch {
-	std::vector<JpegFrameDev> frames;
-	std::vector<HuffDev> huff;
-	std::vector<unsigned> offsets;
-	std::vector<const unsigned char *> src; /* per frame: its entropy-coded bytes (host) */
-	std::vector<size_t> src_len;
-	size_t bytes_total = 0, coef_total = 0;
-	int out_w = 0, out_h = 0, bands = 0;
-	int max_intervals = 0, max_mcus = 0;
+/* one stream, parsed: everything relative to the frame (pool offsets are assigned when a chunk is assembled) */
+struct FramePrep {
+	JpegFrameDev F;
+	HuffDev huff[8];
+	std::vector<unsigned> offsets; /* n_intervals + 1, relative to the entropy-coded segment */
+	const unsigned char *src = nullptr;
+	size_t src_len = 0, coef_count = 0;
+	int bands = 0;
+	std::string err;
 };
 
 int
-batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, int shrink)
+frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, FramePrep *P)
 {
 	JpegHeader H;
 	memset(H.qt, 0, sizeof(H.qt));
@@ -861,6 +924,16 @@ batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, 
 	memset(H.hsym, 0, sizeof(H.hsym));
 	if (parse_jpeg(domain, d, len, &H))
 		return -1;
+	if (H.ncomp == 1) {
+		/* a single-component scan is never interleaved: its MCU is one block whatever the sampling factors say
+		 * (T.81 A.2.2), and jdmaster.c scales the lone component as if they were 1 x 1
+		 */
+		if (H.comp[0].h < 1 || H.comp[0].v < 1) {
+			error(domain, "JPEG component 0: bad sampling factors");
+			return -1;
+		}
+		H.comp[0].h = H.comp[0].v = 1;
+	}
 	for (int c = 0; c < H.ncomp; c++) {
 		H.max_h = std::max(H.max_h, H.comp[c].h);
 		H.max_v = std::max(H.max_v, H.comp[c].v);
@@ -868,7 +941,7 @@ batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, 
 	int dct[kMaxComp] = {8, 8, 8};
 	if (plan_frame(domain, H, shrink, dct))
 		return -1;
-	JpegFrameDev F;
+	JpegFrameDev &F = P->F;
 	memset(&F, 0, sizeof(F));
 	F.width = H.width;
 	F.height = H.height;
@@ -885,17 +958,8 @@ batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, 
 		error(domain, "image has shrunk to nothing");
 		return -1;
 	}
-	const int bands = H.ncomp == 3 ? 3 : 1;
-	if (B.frames.empty()) {
-		B.out_w = F.out_w;
-		B.out_h = F.out_h;
-		B.bands = bands;
-	}
-	else if (B.out_w != F.out_w || B.out_h != F.out_h || B.bands != bands) {
-		error(domain, "frames of a batch must decode to one geometry (%d x %d x %d, got %d x %d x %d)", B.out_w, B.out_h, B.bands,
-			F.out_w, F.out_h, bands);
-		return -1;
-	}
+	P->bands = H.ncomp == 3 ? 3 : 1;
+	P->coef_count = 0;
 	for (int c = 0; c < H.ncomp; c++) {
 		F.h[c] = H.comp[c].h;
 		F.v[c] = H.comp[c].v;
@@ -904,39 +968,47 @@ batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, 
 		F.ta[c] = H.comp[c].ta;
 		F.blocks_x[c] = F.mcus_x * F.h[c];
 		F.blocks_y[c] = F.mcus_y * F.v[c];
-		F.coef_off[c] = B.coef_total;
-		B.coef_total += (size_t) F.blocks_x[c] * F.blocks_y[c] * 64;
+		F.coef_off[c] = P->coef_count;
+		P->coef_count += (size_t) F.blocks_x[c] * F.blocks_y[c] * 64;
 		memcpy(F.qt[c], H.qt[H.comp[c].tq], sizeof(F.qt[c]));
 	}
-	F.huff_base = (int) B.huff.size();
-	B.huff.resize(B.huff.size() + 8);
+	F.blocks_per_mcu = 0;
+	for (int c = 0; c < H.ncomp; c++)
+		for (int by = 0; by < F.v[c]; by++)
+			for (int bx = 0; bx < F.h[c]; bx++) {
+				F.blk_comp[F.blocks_per_mcu] = (unsigned char) c;
+				F.blk_dx[F.blocks_per_mcu] = (unsigned char) bx;
+				F.blk_dy[F.blocks_per_mcu] = (unsigned char) by;
+				F.blocks_per_mcu++;
+			}
+	memset(P->huff, 0, sizeof(P->huff));
 	for (int tc = 0; tc < 2; tc++)
 		for (int th = 0; th < 4; th++)
 			if (H.hset[tc][th])
-				build_huff(H.hcount[tc][th], H.hsym[tc][th], &B.huff[F.huff_base + 4 * tc + th]);
+				build_huff(H.hcount[tc][th], H.hsym[tc][th], &P->huff[4 * tc + th]);
 	/* restart intervals: RSTn markers are byte-aligned FFD0..FFD7 inside the entropy-coded segment */
 	const int total = F.mcus_x * F.mcus_y;
 	F.restart_interval = H.restart_interval;
-	F.interval_off = B.offsets.size();
 	const size_t seg = H.scan_end - H.scan_off;
 	if (seg >= 0xffffff00u) {
 		error(domain, "entropy-coded segment too large");
 		return -1;
 	}
-	B.offsets.push_back(0);
+	P->offsets.clear();
+	P->offsets.push_back(0);
 	int n_int = 1;
 	if (H.restart_interval > 0) {
 		const int want = (total + H.restart_interval - 1) / H.restart_interval;
-		const unsigned char *s = d + H.scan_off;
+		const unsigned char *sp = d + H.scan_off;
 		size_t e = 0;
 		while (n_int < want && e + 1 < seg) {
-			const unsigned char *q = (const unsigned char *) memchr(s + e, 0xFF, seg - 1 - e);
+			const unsigned char *q = (const unsigned char *) memchr(sp + e, 0xFF, seg - 1 - e);
 			if (!q)
 				break;
-			e = q - s;
-			const int nx = s[e + 1];
+			e = q - sp;
+			const int nx = sp[e + 1];
 			if (nx >= 0xD0 && nx <= 0xD7) {
-				B.offsets.push_back((unsigned) (e + 2));
+				P->offsets.push_back((unsigned) (e + 2));
 				n_int++;
 			}
 			e += 2;
@@ -946,23 +1018,105 @@ batch_add(const char *domain, JpegBatch &B, const unsigned char *d, size_t len, 
 			return -1;
 		}
 	}
-	B.offsets.push_back((unsigned) seg);
+	P->offsets.push_back((unsigned) seg);
 	F.n_intervals = n_int;
-	F.data_off = B.bytes_total;
-	B.bytes_total += (seg + 15) & ~(size_t) 15;
-	B.src.push_back(d + H.scan_off);
-	B.src_len.push_back(seg);
-	B.frames.push_back(F);
-	B.max_intervals = std::max(B.max_intervals, n_int);
-	B.max_mcus = std::max(B.max_mcus, total);
+	P->src = d + H.scan_off;
+	P->src_len = seg;
 	return 0;
 }
 
+/* run fn(i) for i in [0, n) on up to `threads` host threads */
+template <typename Fn>
+void
+parallel_for(int n, int threads, Fn fn)
+{
+	threads = std::max(1, std::min(threads, n));
+	if (threads == 1) {
+		for (int i = 0; i < n; i++)
+			fn(i);
+		return;
+	}
+	std::atomic<int> next(0);
+	std::vector<std::thread> pool;
+	for (int t = 0; t < threads; t++)
+		pool.emplace_back([&] {
+			for (;;) {
+				const int i = next.fetch_add(1);
+				if (i >= n)
+					return;
+				fn(i);
+			}
+		});
+	for (auto &t : pool)
+		t.join();
+}
+
+int
+host_workers()
+{
+	static const int n = [] {
+		const char *e = getenv("VB200_JPEG_THREADS");
+		int v = e ? atoi(e) : 0;
+		if (v <= 0) {
+			v = (int) std::thread::hardware_concurrency();
+#ifdef __linux__
+			cpu_set_t set;
+			if (sched_getaffinity(0, sizeof(set), &set) == 0)
+				v = std::min(v > 0 ? v : 1, CPU_COUNT(&set));
+#endif
+			v = std::min(v, 16);
+		}
+		return std::max(1, v);
+	}();
+	return n;
+}
+
+/* the pump's slots: pinned staging + a stream each, kept per host thread (grow-only) */
+struct JpegSlot {
+	void *pinned = nullptr;
+	size_t cap = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t done = nullptr;
+	bool busy = false;
+};
+constexpr int kJpegSlots = 3;
+struct JpegPump {
+	JpegSlot slot[kJpegSlots];
+	cudaEvent_t fork = nullptr;
+	float huff_ms = 0, idct_ms = 0; /* VB200_JPEG_TIMING: the last call's kernel times */
+	~JpegPump()
+	{
+		for (auto &sl : slot) {
+			if (sl.pinned)
+				cudaFreeHost(sl.pinned);
+			if (sl.done)
+				cudaEventDestroy(sl.done);
+			if (sl.stream)
+				cudaStreamDestroy(sl.stream);
+		}
+		if (fork)
+			cudaEventDestroy(fork);
+	}
+};
+thread_local JpegPump g_pump;
+
 } // namespace
 
+static void
+jpeg_last_kernel_times(float *huff_ms, float *idct_ms)
+{
+	*huff_ms = g_pump.huff_ms;
+	*idct_ms = g_pump.idct_ms;
+}
+
 /* Decode n JPEG streams (host memory) that share one output geometry into out[n][out_h][out_w][bands] on the
- * device (out = nullptr: only report the geometry).  Everything after the upload of the compressed bytes runs on
- * the device, stream-ordered on s.
+ * device (out = nullptr: only report the geometry).
+ *
+ * The pump: headers are parsed and restart markers located on the host workers; the frames go up in chunks, each
+ * chunk = one pinned staging block (frame records, Huffman tables, interval offsets, compressed bytes) copied to the
+ * device and decoded on one of three internal streams, so that staging chunk k + 1 overlaps copy and kernels of
+ * chunk k (and the Huffman kernels of consecutive chunks share the machine).  The internal streams start after everything queued on s and s continues after them; the call returns when
+ * the frames are decoded (a corrupt stream is an error, as jpeg2vips.c makes it one by default).
  */
 int
 dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t *lens, int n, int shrink, void *out, size_t out_bpl,
@@ -972,93 +1126,212 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		error(domain, "no frames");
 		return -1;
 	}
-	JpegBatch B;
+	std::vector<FramePrep> prep(n);
+	std::atomic<int> failed(-1);
+	parallel_for(n, host_workers(), [&](int i) {
+		if (frame_prep(domain, (const unsigned char *) bufs[i], lens[i], shrink, &prep[i])) {
+			prep[i].err = vb200_error_buffer(); /* the worker's thread-local text */
+			int none = -1;
+			failed.compare_exchange_strong(none, i);
+		}
+	});
 	for (int i = 0; i < n; i++)
-		if (batch_add(domain, B, (const unsigned char *) bufs[i], lens[i], shrink))
+		if (!prep[i].err.empty()) {
+			error(domain, "frame %d: %s", i, prep[i].err.c_str());
 			return -1;
+		}
+	const int W = prep[0].F.out_w, Hh = prep[0].F.out_h, B = prep[0].bands;
+	for (int i = 1; i < n; i++)
+		if (prep[i].F.out_w != W || prep[i].F.out_h != Hh || prep[i].bands != B) {
+			error(domain, "frames of a batch must decode to one geometry (%d x %d x %d, frame %d: %d x %d x %d)", W, Hh, B, i,
+				prep[i].F.out_w, prep[i].F.out_h, prep[i].bands);
+			return -1;
+		}
 	if (out_w)
-		*out_w = B.out_w;
+		*out_w = W;
 	if (out_h)
-		*out_h = B.out_h;
+		*out_h = Hh;
 	if (bands)
-		*bands = B.bands;
+		*bands = B;
 	if (!out)
 		return 0;
-	if (out_bpl < (size_t) B.out_w * B.bands || (n > 1 && out_frame_stride < out_bpl * B.out_h)) {
-		error(domain, "output strides too small for %d x %d x %d", B.out_w, B.out_h, B.bands);
+	if (out_bpl < (size_t) W * B || (n > 1 && out_frame_stride < out_bpl * Hh)) {
+		error(domain, "output strides too small for %d x %d x %d", W, Hh, B);
 		return -1;
 	}
-	static bool zz_done = false;
-	if (!zz_done) {
-		VB200_CUDA(domain, cudaMemcpyToSymbol(d_zigzag, kZigzag, 64));
-		zz_done = true;
+	static std::once_flag zz_once;
+	std::call_once(zz_once, [] { cudaMemcpyToSymbol(d_zigzag, kZigzag, 64); });
+
+	JpegPump &P = g_pump;
+	for (auto &sl : P.slot)
+		if (!sl.stream) {
+			VB200_CUDA(domain, cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+			VB200_CUDA(domain, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+		}
+	if (!P.fork)
+		VB200_CUDA(domain, cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
+	const bool timing = getenv("VB200_JPEG_TIMING") != nullptr;
+	P.huff_ms = P.idct_ms = 0;
+
+	/* chunks: frames with many restart intervals fill the machine with few frames; a stream without them is one
+	 * thread per frame, so everything goes up at once.  Bounded by the coefficient pool (128 bytes per block).
+	 */
+	int max_int = 1;
+	size_t max_coef = 0;
+	for (int i = 0; i < n; i++) {
+		max_int = std::max(max_int, prep[i].F.n_intervals);
+		max_coef = std::max(max_coef, prep[i].coef_count);
 	}
-	/* one pinned staging block: frame records, Huffman tables, interval offsets, compressed bytes */
-	const size_t sz_f = B.frames.size() * sizeof(JpegFrameDev), sz_h = B.huff.size() * sizeof(HuffDev);
-	const size_t sz_o = (B.offsets.size() * sizeof(unsigned) + 15) & ~(size_t) 15;
-	const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_o = off_h + ((sz_h + 15) & ~(size_t) 15), off_b = off_o + sz_o;
-	const size_t total = off_b + B.bytes_total + 16;
-	void *hst = nullptr, *dev = nullptr, *coef = nullptr, *status = nullptr;
-	if (cudaMallocHost(&hst, total) != cudaSuccess)
-		return cuda_fail(domain, cudaGetLastError(), "cudaMallocHost (jpeg staging)");
-	memcpy(hst, B.frames.data(), sz_f);
-	memcpy((char *) hst + off_h, B.huff.data(), sz_h);
-	memcpy((char *) hst + off_o, B.offsets.data(), B.offsets.size() * sizeof(unsigned));
-	for (int i = 0; i < n; i++)
-		memcpy((char *) hst + off_b + B.frames[i].data_off, B.src[i], B.src_len[i]);
-	int rc = -1;
-	do {
-		if (dev_alloc(domain, &dev, total, s) || dev_alloc(domain, &coef, B.coef_total * sizeof(short), s) ||
-			dev_alloc(domain, &status, (size_t) n * sizeof(int), s))
-			break;
-		if (cudaMemcpyAsync(dev, hst, total, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-			cudaMemsetAsync(coef, 0, B.coef_total * sizeof(short), s) != cudaSuccess ||
-			cudaMemsetAsync(status, 0, (size_t) n * sizeof(int), s) != cudaSuccess) {
-			cuda_fail(domain, cudaGetLastError(), "jpeg staging copy");
-			break;
+	size_t free_b = 0, total_b = 0;
+	cudaMemGetInfo(&free_b, &total_b);
+	const size_t coef_budget = std::max<size_t>(free_b / 4, (size_t) 1 << 30);
+	int chunk = max_int >= 32 ? 64 : n;
+	chunk = (int) std::max<size_t>(1, std::min<size_t>(chunk, coef_budget / std::max<size_t>(1, max_coef * sizeof(short))));
+	chunk = std::min(chunk, n);
+
+	int *status = nullptr;
+	if (dev_alloc(domain, (void **) &status, (size_t) n * sizeof(int), s))
+		return -1;
+	int rc = 0;
+	if (cudaMemsetAsync(status, 0, (size_t) n * sizeof(int), s) != cudaSuccess || cudaEventRecord(P.fork, s) != cudaSuccess)
+		rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode setup");
+	for (int c0 = 0, k = 0; c0 < n && !rc; c0 += chunk, k++) {
+		const int cn = std::min(chunk, n - c0);
+		JpegSlot &sl = P.slot[k % kJpegSlots];
+		/* layout of the chunk's block */
+		std::vector<size_t> data_off(cn), int_off(cn), coef_off(cn);
+		size_t bytes_total = 0, ints_total = 0, coef_total = 0;
+		int max_intervals = 0, max_mcus = 0;
+		for (int i = 0; i < cn; i++) {
+			const FramePrep &fp = prep[c0 + i];
+			data_off[i] = bytes_total;
+			bytes_total += (fp.src_len + 15) & ~(size_t) 15;
+			int_off[i] = ints_total;
+			ints_total += fp.offsets.size();
+			coef_off[i] = coef_total;
+			coef_total += fp.coef_count;
+			max_intervals = std::max(max_intervals, fp.F.n_intervals);
+			max_mcus = std::max(max_mcus, fp.F.mcus_x * fp.F.mcus_y);
 		}
-		const JpegFrameDev *dF = (const JpegFrameDev *) dev;
-		const HuffDev *dH = (const HuffDev *) ((char *) dev + off_h);
-		const unsigned *dO = (const unsigned *) ((char *) dev + off_o);
-		const unsigned char *dB = (const unsigned char *) dev + off_b;
-		jpeg_huffman_kernel<<<dim3((B.max_intervals + 63) / 64, n), 64, 0, s>>>(dF, dH, dB, dO, (short *) coef, (int *) status);
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) {
-			cuda_fail(domain, e, "jpeg_huffman_kernel launch");
-			break;
-		}
-		count_launch();
-		jpeg_idct_kernel<<<dim3((B.max_mcus + 127) / 128, n), 128, 0, s>>>(dF, (const short *) coef, (unsigned char *) out, out_bpl,
-			out_frame_stride);
-		e = cudaGetLastError();
-		if (e != cudaSuccess) {
-			cuda_fail(domain, e, "jpeg_idct_kernel launch");
-			break;
-		}
-		count_launch();
-		/* a corrupt stream is an error, as jpeg2vips.c makes it one by default (fail_on): wait for the verdict */
-		std::vector<int> st(n);
-		if (cudaMemcpyAsync(st.data(), status, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-			cudaStreamSynchronize(s) != cudaSuccess) {
-			cuda_fail(domain, cudaGetLastError(), "jpeg decode");
-			break;
-		}
-		rc = 0;
-		for (int i = 0; i < n; i++)
-			if (st[i]) {
-				error(domain, "frame %d: corrupt JPEG data: bad Huffman code", i);
-				rc = -1;
+		const size_t sz_f = (size_t) cn * sizeof(JpegFrameDev), sz_h = (size_t) cn * 8 * sizeof(HuffDev);
+		const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_o = off_h + ((sz_h + 15) & ~(size_t) 15);
+		const size_t off_b = off_o + ((ints_total * sizeof(unsigned) + 15) & ~(size_t) 15);
+		const size_t total = off_b + bytes_total + 16;
+		if (sl.busy) {
+			if (cudaEventSynchronize(sl.done) != cudaSuccess) {
+				rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
 				break;
 			}
-	} while (0);
-	if (dev)
-		dev_free(dev, s);
-	if (coef)
-		dev_free(coef, s);
-	if (status)
-		dev_free(status, s);
-	cudaStreamSynchronize(s);
-	cudaFreeHost(hst);
+			sl.busy = false;
+		}
+		if (sl.cap < total) {
+			if (sl.pinned)
+				cudaFreeHost(sl.pinned);
+			sl.pinned = nullptr;
+			sl.cap = 0;
+			const size_t want = total + total / 4;
+			if (cudaMallocHost(&sl.pinned, want) != cudaSuccess) {
+				rc = cuda_fail(domain, cudaGetLastError(), "cudaMallocHost (jpeg staging)");
+				break;
+			}
+			sl.cap = want;
+		}
+		char *hst = (char *) sl.pinned;
+		parallel_for(cn, host_workers(), [&](int i) {
+			const FramePrep &fp = prep[c0 + i];
+			JpegFrameDev F = fp.F;
+			F.data_off = data_off[i];
+			F.interval_off = int_off[i];
+			for (int c = 0; c < F.ncomp; c++)
+				F.coef_off[c] += coef_off[i];
+			F.huff_base = 8 * i;
+			memcpy(hst + (size_t) i * sizeof(JpegFrameDev), &F, sizeof(F));
+			memcpy(hst + off_h + (size_t) i * 8 * sizeof(HuffDev), fp.huff, 8 * sizeof(HuffDev));
+			memcpy(hst + off_o + int_off[i] * sizeof(unsigned), fp.offsets.data(), fp.offsets.size() * sizeof(unsigned));
+			memcpy(hst + off_b + data_off[i], fp.src, fp.src_len);
+		});
+		void *dev = nullptr, *coef = nullptr;
+		cudaStream_t st = sl.stream;
+		if (k < kJpegSlots && cudaStreamWaitEvent(st, P.fork, 0) != cudaSuccess) {
+			rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
+			break;
+		}
+		if (dev_alloc(domain, &dev, total, st) || dev_alloc(domain, &coef, coef_total * sizeof(short), st)) {
+			if (dev)
+				dev_free(dev, st);
+			rc = -1;
+			break;
+		}
+		cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+		do {
+			if (cudaMemcpyAsync(dev, hst, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+				cudaMemsetAsync(coef, 0, coef_total * sizeof(short), st) != cudaSuccess) {
+				rc = cuda_fail(domain, cudaGetLastError(), "jpeg staging copy");
+				break;
+			}
+			const JpegFrameDev *dF = (const JpegFrameDev *) dev;
+			const HuffDev *dH = (const HuffDev *) ((char *) dev + off_h);
+			const unsigned *dO = (const unsigned *) ((char *) dev + off_o);
+			const unsigned char *dB = (const unsigned char *) dev + off_b;
+			if (timing) {
+				for (auto &e : ev)
+					cudaEventCreate(&e);
+				cudaEventRecord(ev[0], st);
+			}
+			jpeg_huffman_kernel<<<dim3((max_intervals + kHuffThreads - 1) / kHuffThreads, cn), kHuffThreads, 0, st>>>(dF, dH, dB, dO,
+				(short *) coef, status + c0);
+			cudaError_t e = cudaGetLastError();
+			if (e != cudaSuccess) {
+				rc = cuda_fail(domain, e, "jpeg_huffman_kernel launch");
+				break;
+			}
+			count_launch();
+			if (timing)
+				cudaEventRecord(ev[1], st);
+			jpeg_idct_kernel<<<dim3((max_mcus + 127) / 128, cn), 128, 0, st>>>(dF, (const short *) coef,
+				(unsigned char *) out + (size_t) c0 * out_frame_stride, out_bpl, out_frame_stride);
+			e = cudaGetLastError();
+			if (e != cudaSuccess) {
+				rc = cuda_fail(domain, e, "jpeg_idct_kernel launch");
+				break;
+			}
+			count_launch();
+			if (timing) {
+				cudaEventRecord(ev[2], st);
+				cudaEventSynchronize(ev[2]);
+				float a = 0, b = 0;
+				cudaEventElapsedTime(&a, ev[0], ev[1]);
+				cudaEventElapsedTime(&b, ev[1], ev[2]);
+				P.huff_ms += a;
+				P.idct_ms += b;
+			}
+		} while (0);
+		for (auto &e : ev)
+			if (e)
+				cudaEventDestroy(e);
+		dev_free(dev, st);
+		dev_free(coef, st);
+		if (!rc && cudaEventRecord(sl.done, st) == cudaSuccess)
+			sl.busy = true;
+	}
+	/* join: s continues after both internal streams; then wait for the verdict */
+	for (auto &sl : P.slot)
+		if (sl.busy) {
+			cudaStreamWaitEvent(s, sl.done, 0);
+			sl.busy = false;
+		}
+	std::vector<int> st(n, 0);
+	if (!rc && (cudaMemcpyAsync(st.data(), status, (size_t) n * sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+				   cudaStreamSynchronize(s) != cudaSuccess))
+		rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
+	if (rc)
+		cudaDeviceSynchronize();
+	dev_free(status, s);
+	for (int i = 0; i < n && !rc; i++)
+		if (st[i]) {
+			error(domain, "frame %d: corrupt JPEG data: bad Huffman code", i);
+			rc = -1;
+		}
 	return rc;
 }
 
@@ -1067,24 +1340,28 @@ int
 host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, unsigned char *out, size_t out_bpl, int *out_w, int *out_h,
 	int *bands)
 {
-	JpegBatch B;
-	if (batch_add(domain, B, (const unsigned char *) buf, len, shrink))
+	FramePrep P;
+	if (frame_prep(domain, (const unsigned char *) buf, len, shrink, &P))
 		return -1;
 	if (out_w)
-		*out_w = B.out_w;
+		*out_w = P.F.out_w;
 	if (out_h)
-		*out_h = B.out_h;
+		*out_h = P.F.out_h;
 	if (bands)
-		*bands = B.bands;
+		*bands = P.bands;
 	if (!out)
 		return 0;
-	const JpegFrameDev &F = B.frames[0];
-	std::vector<short> coef(B.coef_total, 0);
+	const JpegFrameDev &F = P.F;
+	std::vector<short> coef(P.coef_count, 0);
+	/* the reader loads aligned words up to 8 bytes past an interval's end: an aligned, padded copy, as the pump stages it */
+	std::vector<unsigned> padded_w((P.src_len + 16) / 4 + 1, 0);
+	memcpy(padded_w.data(), P.src, P.src_len);
+	const unsigned char *padded = (const unsigned char *) padded_w.data();
 	const int total = F.mcus_x * F.mcus_y;
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
 	for (int i = 0; i < F.n_intervals; i++)
-		if (decode_interval(F, B.huff.data() + F.huff_base, kZigzag, B.src[0] + B.offsets[i], B.src[0] + B.offsets[i + 1], i * per,
-				std::min(total, (i + 1) * per), coef.data())) {
+		if (decode_interval(F, P.huff, kZigzag, padded, P.offsets[i], P.offsets[i + 1], i * per, std::min(total, (i + 1) * per),
+				coef.data())) {
 			error(domain, "corrupt JPEG data: bad Huffman code");
 			return -1;
 		}
@@ -1096,3 +1373,125 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 }
 
 } // namespace vb200
+
+/* ------------------------------------------------------------------ C ABI */
+
+using namespace vb200;
+
+extern "C" int
+vb200_jpeg_decode_batch(const void *const *bufs, const size_t *lens, int n, int shrink, void *out, int out_location, size_t out_bpl,
+	size_t out_frame_stride, int *width, int *height, int *bands)
+{
+	const char *domain = "jpeg_decode_batch";
+	int w = 0, h = 0, b = 0;
+	if (!out) {
+		/* geometry only: no device needed */
+		if (n < 1 || !bufs || !lens) {
+			error(domain, "no frames");
+			return -1;
+		}
+		for (int i = 0; i < n; i++) {
+			int wi, hi, bi;
+			if (host_jpeg_decode(domain, bufs[i], lens[i], shrink, nullptr, 0, &wi, &hi, &bi))
+				return -1;
+			if (i && (wi != w || hi != h || bi != b)) {
+				error(domain, "frames of a batch must decode to one geometry");
+				return -1;
+			}
+			w = wi, h = hi, b = bi;
+		}
+	}
+	else {
+		if (ensure_init(domain))
+			return -1;
+		cudaStream_t s = current_stream();
+		if (out_location == VB200_DEVICE) {
+			if (dev_jpeg_decode_batch(domain, bufs, lens, n, shrink, out, out_bpl, out_frame_stride, &w, &h, &b, s))
+				return -1;
+		}
+		else {
+			if (dev_jpeg_decode_batch(domain, bufs, lens, n, shrink, nullptr, 0, 0, &w, &h, &b, s))
+				return -1;
+			const size_t line = (size_t) w * b;
+			if (out_bpl < line || (n > 1 && out_frame_stride < out_bpl * h)) {
+				error(domain, "output strides too small for %d x %d x %d", w, h, b);
+				return -1;
+			}
+			void *dev = nullptr;
+			if (dev_alloc(domain, &dev, line * h * n, s))
+				return -1;
+			int rc = dev_jpeg_decode_batch(domain, bufs, lens, n, shrink, dev, line, line * h, nullptr, nullptr, nullptr, s);
+			for (int i = 0; i < n && !rc; i++)
+				if (cudaMemcpy2DAsync((char *) out + (size_t) i * out_frame_stride, out_bpl, (char *) dev + (size_t) i * line * h, line, line, h,
+						cudaMemcpyDeviceToHost, s) != cudaSuccess)
+					rc = cuda_fail(domain, cudaGetLastError(), "copy to host");
+			if (!rc && cudaStreamSynchronize(s) != cudaSuccess)
+				rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
+			dev_free(dev, s);
+			if (rc)
+				return -1;
+		}
+	}
+	if (width)
+		*width = w;
+	if (height)
+		*height = h;
+	if (bands)
+		*bands = b;
+	return 0;
+}
+
+/* reference: vips_jpegload_buffer(buf, len, &out, "shrink", shrink, NULL), foreign/jpegload.c + jpeg2vips.c */
+extern "C" int
+vb200_jpegload_buffer(const void *buf, size_t len, int shrink, VB200Image *out)
+{
+	const char *domain = "jpegload_buffer";
+	if (!buf || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	cudaStream_t s = current_stream();
+	int w, h, b;
+	if (dev_jpeg_decode_batch(domain, &buf, &len, 1, shrink, nullptr, 0, 0, &w, &h, &b, s))
+		return -1;
+	DevImage d;
+	if (dev_image_new(domain, &d, w, h, b, VB200_FORMAT_UCHAR, b == 1 ? VB200_INTERPRETATION_B_W : VB200_INTERPRETATION_sRGB, s))
+		return -1;
+	if (dev_jpeg_decode_batch(domain, &buf, &len, 1, shrink, d.data, d.bpl, d.bpl * h, nullptr, nullptr, nullptr, s)) {
+		dev_image_release(&d, s);
+		return -1;
+	}
+	VB200Image like = *out;
+	return deliver(domain, &d, &like, out, s);
+}
+
+/* reference: vips_thumbnail_find_jpegshrink, resample/thumbnail.c:489-517 (linear = FALSE) */
+extern "C" int
+vb200_thumbnail_jpegshrink(int width, int height, int target_width, int target_height, int size)
+{
+	if (width < 1 || height < 1 || target_width < 1)
+		return 1;
+	const double shrink = thumbnail_common_shrink(width, height, target_width, target_height > 0 ? target_height : target_width, size);
+	return shrink >= 16 ? 8 : (shrink >= 8 ? 4 : (shrink >= 4 ? 2 : 1));
+}
+
+/* with VB200_JPEG_TIMING set: CUDA-event times of the two kernels over the calling thread's last decode */
+extern "C" void
+vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms)
+{
+	float a = 0, b = 0;
+	jpeg_last_kernel_times(&a, &b);
+	if (huffman_ms)
+		*huffman_ms = a;
+	if (idct_ms)
+		*idct_ms = b;
+}
+
+extern "C" int
+vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height, int *bands)
+{
+	return host_jpeg_decode("jpeg_decode (host twin)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands);
+}
+

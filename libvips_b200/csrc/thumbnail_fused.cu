@@ -2299,6 +2299,14 @@ static int thumbnail_plan_run_thumbnail(const char *domain, ThumbnailPlanImpl *p
 static int thumbnail_plan_run_fused(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, cudaStream_t s);
 
+double
+thumbnail_common_shrink(int w, int h, int tw, int th, int size)
+{
+	double hs, vs;
+	thumbnail_shrink(w, h, tw, th, size, &hs, &vs);
+	return std::min(hs, vs);
+}
+
 int
 thumbnail_plan_run_device(const char *domain, ThumbnailPlanImpl *pl, const void *in, size_t in_stride, void *out,
 	size_t out_stride, int n, cudaStream_t s)
@@ -2653,6 +2661,59 @@ vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in
 		return -1;
 	return thumbnail_plan_run_device(domain, &plan->impl, in, in_frame_stride, out, out_frame_stride, n_frames,
 		current_stream());
+}
+
+/* Decode staging feeding the plan: compressed JPEG bytes up, decoded at `shrink` on the device
+ * (jpeg.cu), thumbnailed by the plan's kernels -- the decoded frames never exist in host memory.  What
+ * vips_thumbnail_buffer() does with jpeg2vips + vips_thumbnail_image (thumbnail.c:583-613, 848-902).
+ */
+extern "C" int
+vb200_thumbnail_plan_run_jpeg(VB200ThumbnailPlan *plan, const void *const *bufs, const size_t *lens, int n, int shrink, void *out,
+	int out_location, size_t out_frame_stride)
+{
+	const char *domain = "thumbnail_plan_run_jpeg";
+	if (!plan || !bufs || !lens || !out || n < 1) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	ThumbnailPlanImpl &pl = plan->impl;
+	cudaStream_t s = current_stream();
+	const size_t in_frame = (size_t) pl.W * pl.H * pl.bands, out_frame = (size_t) pl.OW * pl.OH * pl.bands;
+	if (out_frame_stride == 0)
+		out_frame_stride = out_frame;
+	void *dec = nullptr, *res = nullptr;
+	if (dev_alloc(domain, &dec, in_frame * n, s))
+		return -1;
+	int rc = -1;
+	do {
+		int w, h, b;
+		if (dev_jpeg_decode_batch(domain, bufs, lens, n, shrink, dec, (size_t) pl.W * pl.bands, in_frame, &w, &h, &b, s))
+			break;
+		if (w != pl.W || h != pl.H || b != pl.bands) {
+			error(domain, "the plan is for %d x %d x %d frames, the streams decode to %d x %d x %d", pl.W, pl.H, pl.bands, w, h, b);
+			break;
+		}
+		if (out_location == VB200_DEVICE) {
+			rc = thumbnail_plan_run_device(domain, &pl, dec, in_frame, out, out_frame_stride, n, s);
+			break;
+		}
+		if (dev_alloc(domain, &res, out_frame * n, s))
+			break;
+		if (thumbnail_plan_run_device(domain, &pl, dec, in_frame, res, out_frame, n, s))
+			break;
+		if (cudaMemcpy2DAsync(out, out_frame_stride, res, out_frame, out_frame, n, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+			cudaStreamSynchronize(s) != cudaSuccess) {
+			cuda_fail(domain, cudaGetLastError(), "copy to host");
+			break;
+		}
+		rc = 0;
+	} while (0);
+	dev_free(dec, s);
+	if (res)
+		dev_free(res, s);
+	return rc;
 }
 
 /* The tile pump: a ring of kStreams device staging slots; for each slice of

@@ -154,6 +154,13 @@ int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int s
 /* Launchers of the row/column-table kernels on raw device pointers (used by
  * the generate()-shaped and scanline seams too).
  */
+/* jpeg.cu: n JPEG streams of one output geometry -> out[n][h][w][bands] on the device (out = nullptr: geometry only) */
+int dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t *lens, int n, int shrink, void *out, size_t out_bpl,
+	size_t out_frame_stride, int *out_w, int *out_h, int *bands, cudaStream_t s);
+int host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, unsigned char *out, size_t out_bpl, int *out_w,
+	int *out_h, int *bands);
+/* min(hshrink, vshrink) of vips_thumbnail_calculate_shrink, thumbnail.c:413-487 */
+double thumbnail_common_shrink(int w, int h, int tw, int th, int size);
 void resample_cache_clear(); /* cached axis tables (resample_kernels.cu); vb200_shutdown */
 int launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne,
 	int out_rows, int fmt, const AxisTable &t, cudaStream_t s);

@@ -1,0 +1,193 @@
+"""JPEG decode staging with shrink-on-load (csrc/jpeg.cu).
+
+The reference loads JPEGs through libjpeg (foreign/jpeg2vips.c), a third-party dependency that is not under
+/root/reference.  The oracle for this row is therefore libjpeg-turbo ITSELF, as shipped inside this image's Pillow:
+PIL decodes with the library's defaults (JDCT_ISLOW, fancy upsampling -- what jpeg2vips.c uses) and its draft mode
+sets scale_denom exactly as jpeg2vips.c:537-538 does.  Bit for bit, no tolerance.
+
+CPU tests run the decoder's per-block code compiled for the host (vb200_debug_jpeg_decode); the -m gpu tests run the
+kernels through the C ABI, and the thumbnail feed against the oracle thumbnail of libjpeg-turbo's decode.
+"""
+import io
+
+import numpy as np
+import pytest
+
+PIL = pytest.importorskip("PIL.Image")
+
+
+def synth(h, w, seed=0, grey=False):
+    """smooth structure + noise: compresses like a photograph, exercises every coefficient position"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = np.stack([128 + 100 * np.sin(xx / 37.0 + yy / 91.0), 128 + 90 * np.cos(xx / 53.0 - yy / 29.0), (xx * 3 + yy * 5) % 256], -1)
+    base = base + rng.normal(0, 12, base.shape)
+    a = np.clip(base, 0, 255).astype(np.uint8)
+    return a[..., 0] if grey else a
+
+
+def encode(a, quality=85, subsampling=2, **kw):
+    b = io.BytesIO()
+    PIL.fromarray(a).save(b, "JPEG", quality=quality, subsampling=subsampling, **kw)
+    return b.getvalue()
+
+
+def turbo_decode(data, shrink):
+    """libjpeg-turbo with scale_num / scale_denom = 1 / shrink, cropped as jpeg2vips.c:639-640 crops it"""
+    im = PIL.open(io.BytesIO(data))
+    w, h = im.size
+    if shrink > 1:
+        im.draft(im.mode, (max(1, w // shrink), max(1, h // shrink)))
+        assert im.size == ((w + shrink - 1) // shrink, (h + shrink - 1) // shrink), "draft() picked another scale"
+    a = np.asarray(im)[: h // shrink, : w // shrink]
+    return a[..., None] if a.ndim == 2 else a
+
+
+@pytest.fixture(scope="module")
+def vbl():
+    import libvips_b200 as vb
+    vb.lib()
+    return vb
+
+
+CASES = [(64, 64), (67, 93), (256, 200), (17, 300), (129, 31)]
+
+
+@pytest.mark.parametrize("size", CASES, ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("sub", [2, 0], ids=["420", "444"])
+def test_host_twin_matches_libjpeg_turbo(vbl, size, sub):
+    h, w = size
+    a = synth(h, w, seed=h * 7 + w)
+    for quality in (30, 85, 100):
+        d = encode(a, quality, sub)
+        for shrink in (8, 4, 2, 1):
+            if sub == 2 and shrink == 1:
+                continue  # full-size 4:2:0 needs libjpeg's fancy upsampler: declined, tested below
+            if min(h, w) // shrink < 1:
+                continue
+            got = vbl.jpeg_decode_host_twin(d, shrink)
+            want = turbo_decode(d, shrink)
+            assert got.shape == want.shape and np.array_equal(got, want), (size, sub, quality, shrink)
+
+
+def test_greyscale_restart_markers_and_optimised_tables(vbl):
+    g = synth(150, 203, seed=3, grey=True)
+    d = encode(g, 90)
+    for shrink in (1, 2, 4, 8):
+        assert np.array_equal(vbl.jpeg_decode_host_twin(d, shrink), turbo_decode(d, shrink))
+    a = synth(200, 312, seed=4)
+    for kw in ({"restart_marker_rows": 1}, {"restart_marker_blocks": 3}, {"optimize": True}, {"optimize": True, "restart_marker_rows": 2}):
+        for sub in (2, 0):
+            d = encode(a, 80, sub, **kw)
+            for shrink in (2, 4, 8):
+                assert np.array_equal(vbl.jpeg_decode_host_twin(d, shrink), turbo_decode(d, shrink)), (kw, sub, shrink)
+
+
+def test_extreme_coefficients(vbl):
+    """noise at quality 100 and saturated checkerboards: the range-limit table's clamps and the widest Huffman codes"""
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:96, 0:128]
+    check = np.repeat((((yy + xx) % 2) * 255).astype(np.uint8)[..., None], 3, -1)
+    for a in (noise, check):
+        for q in (100, 5):
+            for sub in (2, 0):
+                d = encode(a, q, sub)
+                for shrink in (2, 4, 8) + ((1,) if sub == 0 else ()):
+                    assert np.array_equal(vbl.jpeg_decode_host_twin(d, shrink), turbo_decode(d, shrink)), (q, sub, shrink)
+
+
+def test_declined_streams(vbl):
+    a = synth(64, 64)
+    with pytest.raises(vbl.Error, match="progressive"):
+        vbl.jpeg_decode_host_twin(encode(a, progressive=True), 2)
+    with pytest.raises(vbl.Error, match="upsampler"):
+        vbl.jpeg_decode_host_twin(encode(a, subsampling=2), 1)      # 4:2:0 at full size
+    with pytest.raises(vbl.Error, match="upsampler"):
+        vbl.jpeg_decode_host_twin(encode(a, subsampling=1), 2)      # 4:2:2
+    with pytest.raises(vbl.Error, match="shrink"):
+        vbl.jpeg_decode_host_twin(encode(a), 3)
+    with pytest.raises(vbl.Error, match="JPEG"):
+        vbl.jpeg_decode_host_twin(b"\x89PNG\r\n\x1a\n" + bytes(64), 1)
+    d = encode(a, subsampling=0)
+    for cut in (2, 20, 200, len(d) // 2):
+        # truncated headers are errors; a truncated scan decodes (zeros fed past the end, as jdhuff.c does) or reports a bad code
+        try:
+            vbl.jpeg_decode_host_twin(d[:cut], 1)
+        except vbl.Error:
+            pass
+
+
+def test_jpegshrink_rule(vbl):
+    """thumbnail.c:489-517: shrink >= 16 -> 8, >= 8 -> 4, >= 4 -> 2, else 1, on the common shrink"""
+    assert vbl.thumbnail_jpegshrink(4096, 4096, 512) == 4
+    assert vbl.thumbnail_jpegshrink(4096, 4096, 256) == 8
+    assert vbl.thumbnail_jpegshrink(4096, 4096, 1024) == 2
+    assert vbl.thumbnail_jpegshrink(4096, 4096, 1025) == 1
+    assert vbl.thumbnail_jpegshrink(6000, 4000, 300) == 8
+    assert vbl.thumbnail_jpegshrink(6000, 4000, 300, 300, "force") == 4    # common = min(20, 13.3)
+    assert vbl.thumbnail_jpegshrink(800, 600, 1000) == 1
+
+
+def test_geometry_without_gpu(vbl):
+    a = synth(203, 301)
+    streams = [encode(a, 85, 2), encode(a[::-1].copy(), 60, 2)]
+    assert vbl.jpeg_geometry(streams, 4) == (75, 50, 3)
+    with pytest.raises(vbl.Error, match="geometry"):
+        vbl.jpeg_geometry([streams[0], encode(a[:100], 85, 2)], 4)
+
+
+# ------------------------------------------------------------------ GPU
+
+
+@pytest.mark.gpu
+def test_gpu_batch_decode_matches_libjpeg_turbo(vbl):
+    import libvips_b200 as vb
+    vb.init(0)
+    for (h, w) in ((256, 320), (203, 301), (1024, 1024)):
+        for sub in (2, 0):
+            for kw in ({}, {"restart_marker_rows": 1}, {"optimize": True}):
+                streams = [encode(synth(h, w, seed=i), (95, 75, 40)[i], sub, **kw) for i in range(3)]
+                for shrink in (8, 4, 2) + ((1,) if sub == 0 else ()):
+                    got = vb.jpeg_decode_batch(streams, shrink)
+                    want = np.stack([turbo_decode(s, shrink) for s in streams])
+                    assert got.shape == want.shape and np.array_equal(got, want), (h, w, sub, kw, shrink)
+    g = [encode(synth(150, 203, seed=i, grey=True), 90) for i in range(2)]
+    assert np.array_equal(vb.jpeg_decode_batch(g, 2), np.stack([turbo_decode(s, 2) for s in g]))
+
+
+@pytest.mark.gpu
+def test_gpu_corrupt_scan_is_an_error_or_decodes(vbl):
+    import libvips_b200 as vb
+    vb.init(0)
+    d = bytearray(encode(synth(128, 128), 85, 2, restart_marker_rows=1))
+    rng = np.random.default_rng(9)
+    for _ in range(8):
+        bad = bytearray(d)
+        for p in rng.integers(700, len(d) - 2, 12):
+            if bad[p] != 0xFF and bad[p - 1] != 0xFF:
+                bad[p] ^= 1 << int(rng.integers(0, 8))
+        try:
+            out = vb.jpeg_decode_batch([bytes(bad)], 2)     # never a crash, never an out-of-bounds access
+            assert out.shape == (1, 64, 64, 3)
+        except vb.Error:
+            pass
+
+
+@pytest.mark.gpu
+def test_gpu_thumbnail_from_jpeg_streams(vbl):
+    """vips_thumbnail_buffer's chain: shrink-on-load picked by thumbnail.c:489-517, then the thumbnail of the decoded
+    frame -- against the oracle thumbnail of libjpeg-turbo's own decode"""
+    import libvips_b200 as vb
+    from oracle import pyoracle
+    vb.init(0)
+    for (h, w, target) in ((2048, 2048, 256), (1536, 2048, 200), (1024, 1024, 200)):
+        streams = [encode(synth(h, w, seed=i), 88, 2, **({"restart_marker_rows": 1} if i else {})) for i in range(3)]
+        shrink = vb.thumbnail_jpegshrink(w, h, target)
+        assert shrink in (2, 4, 8)
+        dw, dh, bands = vb.jpeg_geometry(streams, shrink)
+        assert (dw, dh, bands) == (w // shrink, h // shrink, 3)
+        plan = vb.ThumbnailPlan(dw, dh, 3, target)
+        got = plan.run_jpeg(streams, shrink)
+        want = np.stack([pyoracle.thumbnail_image(turbo_decode(s, shrink), target) for s in streams])
+        assert got.shape == want.shape and np.array_equal(got, want), (h, w, target)
