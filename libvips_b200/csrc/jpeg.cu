@@ -30,6 +30,8 @@
  */
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -500,6 +502,33 @@ br_receive_extend(BitReader &b, int s)
 	return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
 }
 
+/* where the blocks of an MCU live: per block of the MCU (T.81 A.2.3 order) the element offset of MCU (0, 0)'s copy
+ * in the coefficient pool and the steps to the next MCU / MCU row, its component and its Huffman tables.  Built once
+ * per CTA into shared memory (every thread of a CTA decodes intervals of one frame); the CPU twin builds a local one.
+ */
+struct McuLayout {
+	int n, mcus_x;
+	unsigned long long plane[12];
+	int step_x[12], step_y[12];
+	unsigned char comp[12], dc[12], ac[12];
+};
+
+HD void
+mcu_layout(const JpegFrameDev &F, McuLayout &M)
+{
+	M.n = F.blocks_per_mcu;
+	M.mcus_x = F.mcus_x;
+	for (int i = 0; i < F.blocks_per_mcu; i++) {
+		const int c = F.blk_comp[i];
+		M.plane[i] = F.coef_off[c] + ((unsigned long long) F.blk_dy[i] * F.blocks_x[c] + F.blk_dx[i]) * 64;
+		M.step_x[i] = F.h[c] * 64;
+		M.step_y[i] = F.v[c] * F.blocks_x[c] * 64;
+		M.comp[i] = (unsigned char) c;
+		M.dc[i] = (unsigned char) F.td[c];
+		M.ac[i] = (unsigned char) (4 + F.ta[c]);
+	}
+}
+
 /* Decode the MCUs [mcu0, mcu1) of a frame from one restart interval's bytes into the coefficient planes.
  * ONE loop, one symbol per trip, for DC and AC alike: the threads of a warp decode different intervals, and with
  * the textbook nest (blocks / coefficients) a thread that ends its block early idles at the loop's reconvergence
@@ -507,7 +536,7 @@ br_receive_extend(BitReader &b, int s)
  * Returns 0, or -1 on a bad code (the remaining blocks of the interval stay zero).
  */
 HD int
-decode_interval(const JpegFrameDev &F, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned pos, unsigned end,
+decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned pos, unsigned end,
 	int mcu0, int mcu1, short *coef_pool)
 {
 	if (mcu0 >= mcu1)
@@ -515,11 +544,12 @@ decode_interval(const JpegFrameDev &F, const HuffDev *huff, const unsigned char 
 	BitReader b;
 	br_init(b, base, pos, end);
 	int pred0 = 0, pred1 = 0, pred2 = 0;
+	const int nb = M.n, mcus_x = M.mcus_x;
 	int mcu = mcu0, bi = 0, k = 0;
-	int my = mcu / F.mcus_x, mx = mcu - my * F.mcus_x;
-	int c = F.blk_comp[0];
-	const HuffDev *dc = huff + F.td[c], *ac = huff + 4 + F.ta[c];
-	short *blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + F.blk_dy[0]) * F.blocks_x[c] + (size_t) (mx * F.h[c] + F.blk_dx[0])) * 64;
+	int my = mcu / mcus_x, mx = mcu - my * mcus_x;
+	int c = M.comp[0];
+	const HuffDev *dc = huff + M.dc[0], *ac = huff + M.ac[0];
+	short *blk = coef_pool + M.plane[0] + (long long) my * M.step_y[0] + (long long) mx * M.step_x[0];
 	for (;;) {
 		br_fill(b);
 		const bool isdc = k == 0;
@@ -557,19 +587,19 @@ decode_interval(const JpegFrameDev &F, const HuffDev *huff, const unsigned char 
 		if (k >= 64) {
 			/* next block of the MCU, or the next MCU */
 			k = 0;
-			if (++bi == F.blocks_per_mcu) {
+			if (++bi == nb) {
 				bi = 0;
 				if (++mcu >= mcu1)
 					return 0;
-				if (++mx == F.mcus_x) {
+				if (++mx == mcus_x) {
 					mx = 0;
 					my++;
 				}
 			}
-			c = F.blk_comp[bi];
-			dc = huff + F.td[c];
-			ac = huff + 4 + F.ta[c];
-			blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + F.blk_dy[bi]) * F.blocks_x[c] + (size_t) (mx * F.h[c] + F.blk_dx[bi])) * 64;
+			c = M.comp[bi];
+			dc = huff + M.dc[bi];
+			ac = huff + M.ac[bi];
+			blk = coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
 		}
 	}
 }
@@ -867,14 +897,22 @@ reconstruct_mcu(const JpegFrameDev &F, const short *coef_pool, int mx, int my, u
 
 /* ------------------------------------------------------------------ kernels */
 
-/* one thread per restart interval of one frame; blockIdx.y = frame of the batch */
+/* One thread per restart interval of one frame; blockIdx.y = frame of the batch.  The block size is chosen by the host
+ * (1 .. 32): the lanes of a warp follow different bit streams, so a warp issues roughly the union of its lanes' paths, and
+ * while there are fewer intervals than the machine has warp slots, narrower CTAs -- down to one interval per warp -- decode
+ * faster.
+ */
 constexpr int kHuffThreads = 32;
 
 __global__ void __launch_bounds__(kHuffThreads)
 jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__restrict__ huff, const unsigned char *__restrict__ bytes,
 	const unsigned *__restrict__ offsets, short *__restrict__ coef, int *__restrict__ status)
 {
+	__shared__ McuLayout M;
 	const JpegFrameDev &F = frames[blockIdx.y];
+	if (threadIdx.x == 0)
+		mcu_layout(F, M);
+	__syncthreads();
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= F.n_intervals)
 		return;
@@ -883,7 +921,7 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 	const int total = F.mcus_x * F.mcus_y;
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
 	const int mcu0 = i * per, mcu1 = min(total, mcu0 + per);
-	if (decode_interval(F, huff + F.huff_base, d_zigzag, base, off[i], off[i + 1], mcu0, mcu1, coef))
+	if (decode_interval(M, huff + F.huff_base, d_zigzag, base, off[i], off[i + 1], mcu0, mcu1, coef))
 		atomicOr(status + blockIdx.y, 1);
 }
 
@@ -1075,6 +1113,9 @@ host_workers()
 struct JpegSlot {
 	void *pinned = nullptr;
 	size_t cap = 0;
+	void *dev = nullptr, *coef = nullptr; /* device twins of the staging block, and the coefficient pool (grow-only: a pool
+											* allocation per chunk cost more than the chunk's kernels) */
+	size_t dev_cap = 0, coef_cap = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	bool busy = false;
@@ -1089,6 +1130,10 @@ struct JpegPump {
 		for (auto &sl : slot) {
 			if (sl.pinned)
 				cudaFreeHost(sl.pinned);
+			if (sl.dev)
+				cudaFree(sl.dev);
+			if (sl.coef)
+				cudaFree(sl.coef);
 			if (sl.done)
 				cudaEventDestroy(sl.done);
 			if (sl.stream)
@@ -1140,6 +1185,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			error(domain, "frame %d: %s", i, prep[i].err.c_str());
 			return -1;
 		}
+	if (getenv("VB200_JPEG_TIMING") && getenv("VB200_JPEG_TIMING")[0] == '2')
+		fprintf(stderr, "[jpeg] %d headers parsed\n", n);
 	const int W = prep[0].F.out_w, Hh = prep[0].F.out_h, B = prep[0].bands;
 	for (int i = 1; i < n; i++)
 		if (prep[i].F.out_w != W || prep[i].F.out_h != Hh || prep[i].bands != B) {
@@ -1184,8 +1231,19 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	}
 	size_t free_b = 0, total_b = 0;
 	cudaMemGetInfo(&free_b, &total_b);
-	const size_t coef_budget = std::max<size_t>(free_b / 4, (size_t) 1 << 30);
+	/* the slots keep their pools: an eighth of the device per chunk, three chunks in flight */
+	const size_t coef_budget = std::max<size_t>(total_b / 8, (size_t) 1 << 30);
 	int chunk = max_int >= 32 ? 64 : n;
+	if (const char *e = getenv("VB200_JPEG_CHUNK"))
+		if (atoi(e) > 0)
+			chunk = atoi(e);
+	long long huff_cta_slots = 148 * 32; /* resident CTAs: 32 per SM */
+	if (const char *e = getenv("VB200_JPEG_CTAS"))
+		if (atoll(e) > 0)
+			huff_cta_slots = atoll(e);
+	const bool trace = getenv("VB200_JPEG_TIMING") && getenv("VB200_JPEG_TIMING")[0] == '2';
+	const auto t_start = std::chrono::steady_clock::now();
+	auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
 	chunk = (int) std::max<size_t>(1, std::min<size_t>(chunk, coef_budget / std::max<size_t>(1, max_coef * sizeof(short))));
 	chunk = std::min(chunk, n);
 
@@ -1250,18 +1308,32 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			memcpy(hst + off_o + int_off[i] * sizeof(unsigned), fp.offsets.data(), fp.offsets.size() * sizeof(unsigned));
 			memcpy(hst + off_b + data_off[i], fp.src, fp.src_len);
 		});
-		void *dev = nullptr, *coef = nullptr;
+		if (trace)
+			fprintf(stderr, "[jpeg] chunk %d (%d frames) staged at %.2f ms\n", k, cn, since());
 		cudaStream_t st = sl.stream;
 		if (k < kJpegSlots && cudaStreamWaitEvent(st, P.fork, 0) != cudaSuccess) {
 			rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
 			break;
 		}
-		if (dev_alloc(domain, &dev, total, st) || dev_alloc(domain, &coef, coef_total * sizeof(short), st)) {
-			if (dev)
-				dev_free(dev, st);
+		auto grow = [&](void **p, size_t *cap, size_t want) {
+			if (*cap >= want)
+				return true;
+			if (*p)
+				cudaFree(*p); /* waits for the device: nothing of this slot is in flight (sl.busy was waited for) */
+			*p = nullptr;
+			*cap = 0;
+			if (cudaMalloc(p, want + want / 8) != cudaSuccess) {
+				cuda_fail(domain, cudaGetLastError(), "cudaMalloc (jpeg slot)");
+				return false;
+			}
+			*cap = want + want / 8;
+			return true;
+		};
+		if (!grow(&sl.dev, &sl.dev_cap, total) || !grow(&sl.coef, &sl.coef_cap, coef_total * sizeof(short))) {
 			rc = -1;
 			break;
 		}
+		void *dev = sl.dev, *coef = sl.coef;
 		cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 		do {
 			if (cudaMemcpyAsync(dev, hst, total, cudaMemcpyHostToDevice, st) != cudaSuccess ||
@@ -1278,8 +1350,11 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 					cudaEventCreate(&e);
 				cudaEventRecord(ev[0], st);
 			}
-			jpeg_huffman_kernel<<<dim3((max_intervals + kHuffThreads - 1) / kHuffThreads, cn), kHuffThreads, 0, st>>>(dF, dH, dB, dO,
-				(short *) coef, status + c0);
+			/* CTA width: one interval per warp while the chunk has fewer intervals than the machine has CTA slots */
+			int ht = 1;
+			while (ht < kHuffThreads && (long long) cn * ((max_intervals + ht - 1) / ht) > huff_cta_slots)
+				ht *= 2;
+			jpeg_huffman_kernel<<<dim3((max_intervals + ht - 1) / ht, cn), ht, 0, st>>>(dF, dH, dB, dO, (short *) coef, status + c0);
 			cudaError_t e = cudaGetLastError();
 			if (e != cudaSuccess) {
 				rc = cuda_fail(domain, e, "jpeg_huffman_kernel launch");
@@ -1309,12 +1384,12 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		for (auto &e : ev)
 			if (e)
 				cudaEventDestroy(e);
-		dev_free(dev, st);
-		dev_free(coef, st);
 		if (!rc && cudaEventRecord(sl.done, st) == cudaSuccess)
 			sl.busy = true;
 	}
-	/* join: s continues after both internal streams; then wait for the verdict */
+	if (trace)
+		fprintf(stderr, "[jpeg] all chunks queued at %.2f ms\n", since());
+	/* join: s continues after the internal streams; then wait for the verdict */
 	for (auto &sl : P.slot)
 		if (sl.busy) {
 			cudaStreamWaitEvent(s, sl.done, 0);
@@ -1326,6 +1401,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
 	if (rc)
 		cudaDeviceSynchronize();
+	if (trace)
+		fprintf(stderr, "[jpeg] decoded at %.2f ms\n", since());
 	dev_free(status, s);
 	for (int i = 0; i < n && !rc; i++)
 		if (st[i]) {
@@ -1359,8 +1436,10 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 	const unsigned char *padded = (const unsigned char *) padded_w.data();
 	const int total = F.mcus_x * F.mcus_y;
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
+	McuLayout M;
+	mcu_layout(F, M);
 	for (int i = 0; i < F.n_intervals; i++)
-		if (decode_interval(F, P.huff, kZigzag, padded, P.offsets[i], P.offsets[i + 1], i * per, std::min(total, (i + 1) * per),
+		if (decode_interval(M, P.huff, kZigzag, padded, P.offsets[i], P.offsets[i + 1], i * per, std::min(total, (i + 1) * per),
 				coef.data())) {
 			error(domain, "corrupt JPEG data: bad Huffman code");
 			return -1;

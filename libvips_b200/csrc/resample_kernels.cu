@@ -317,7 +317,7 @@ reducev_u8x4_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uin
  * (c[u], c[u + 1]) for that pair of rows -- zero where a row lies outside the output row's window.  The pair table
  * of the block's rows is built in shared memory from the phase masks (the rows of a block may have any first tap
  * and any phase: the per-rect stepping of build_axis_table is kept).  Same integer sum as reducev_u8x4_kernel
- * (reducev.cpp:461-471), 12 instead of ~60 instructions per input word: config 1's 49-tap pass went 93 -> us.
+ * (reducev.cpp:461-471), 12 instead of ~60 instructions per input word: config 1's 49-tap pass went 93 -> 47 us under ncu.
  */
 constexpr int kRvRows = 4;
 constexpr int kRvThreads = 128;
@@ -356,7 +356,7 @@ reducev_u8_dp2a_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, 
 #pragma unroll
 		for (int c = 0; c < 4; c++)
 			acc[j][c] = VB200_INTERPOLATE_SCALE >> 1;
-#pragma unroll 4
+#pragma unroll 8
 	for (int k = 0; k < npairs; k++) {
 		const int ra = clampi(u0 + 2 * k, 0, in_h - 1), rb = clampi(u0 + 2 * k + 1, 0, in_h - 1);
 		const unsigned va = __ldg((const unsigned *) (in + (size_t) ra * in_bpl) + x);
@@ -400,7 +400,6 @@ reduceh_u8x4_dp2a_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_w
 {
 	extern __shared__ __align__(16) unsigned s_px[];
 	__shared__ int s_lo, s_hi;
-	const int n = t.n_point;
 	const int x = blockIdx.x * kRhThreads + threadIdx.x;
 	const int y = blockIdx.y;
 	const bool live = x < out_w;
