@@ -459,7 +459,7 @@ def side_workload(args):
         import io
         from PIL import Image
         restart = args.workload == "thumbnail_jpeg"
-        F = max(1, min(args.frames, 256 if restart else 1024))
+        F = max(1, min(args.frames, 1024))
         yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
         distinct = []
         for i in range(8):

@@ -78,6 +78,8 @@ struct JpegHeader {
 /* one Huffman table, device layout */
 struct HuffDev {
 	unsigned short look[1 << kLook]; /* (length << 8) | symbol, 0 = longer than kLook bits */
+	short fast[1 << kLook];			  /* AC tables: (value << 8) | (run << 4) | (code + magnitude bits) when both fit the lookahead and
+									   * the value a signed byte; 0 = take the general path (the trick stb_image calls fast_ac) */
 	int maxcode[18];				  /* maxcode[l]: largest code of length l (-1: none); [17] = sentinel */
 	int valoff[17];					  /* symbol index of the first code of length l, minus that code */
 	unsigned char sym[256];
@@ -385,6 +387,16 @@ build_huff(const unsigned char count[16], const unsigned char *sym, HuffDev *t)
 		code <<= 1;
 	}
 	t->maxcode[17] = 0x7fffffff;
+	for (int i = 0; i < (1 << kLook); i++) {
+		const unsigned e = t->look[i];
+		const int l = (int) (e >> 8), sym = (int) (e & 255), r = sym >> 4, sz = sym & 15;
+		if (!e || sz == 0 || l + sz > kLook)
+			continue;
+		const int bits = (i >> (kLook - l - sz)) & ((1 << sz) - 1);
+		const int v = bits < (1 << (sz - 1)) ? bits - (1 << sz) + 1 : bits;
+		if (v >= -128 && v <= 127)
+			t->fast[i] = (short) (v * 256 + r * 16 + l + sz);
+	}
 }
 
 /* ------------------------------------------------------------------ entropy decoding (host + device) */
@@ -552,12 +564,19 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
 	short *blk = coef_pool + M.plane[0] + (long long) my * M.step_y[0] + (long long) mx * M.step_x[0];
 	for (;;) {
 		br_fill(b);
-		const bool isdc = k == 0;
-		const int sym = huff_decode(b, isdc ? dc : ac);
-		if (sym < 0)
-			return -1;
-		if (isdc) {
-			if (sym > 11)
+		/* most AC symbols: run, size and the magnitude bits in one lookup */
+		const int f = k > 0 ? ac->fast[br_peek(b, kLook)] : 0;
+		if (f) {
+			k += (f >> 4) & 15;
+			if (k > 63)
+				return -1;
+			br_skip(b, f & 15);
+			blk[zz[k]] = (short) (f >> 8);
+			k++;
+		}
+		else if (k == 0) {
+			const int sym = huff_decode(b, dc);
+			if (sym < 0 || sym > 11)
 				return -1;
 			const int diff = br_receive_extend(b, sym);
 			int pr = c == 0 ? pred0 : (c == 1 ? pred1 : pred2);
@@ -572,6 +591,9 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
 			k = 1;
 		}
 		else {
+			const int sym = huff_decode(b, ac);
+			if (sym < 0)
+				return -1;
 			const int r = sym >> 4, sz = sym & 15;
 			if (sz == 0)
 				k = r == 15 ? k + 16 : 64; /* ZRL / EOB */
@@ -872,7 +894,8 @@ ycc_to_rgb(int y, int cb, int cr, unsigned char *rgb)
  * upsampler is the identity in every supported case), colour conversion, store of the part inside the crop.
  */
 HD void
-reconstruct_mcu(const JpegFrameDev &F, const short *coef_pool, int mx, int my, unsigned char *out, size_t out_bpl)
+reconstruct_mcu(const JpegFrameDev &F, const unsigned short (*qt)[64], const short *coef_pool, int mx, int my, unsigned char *out,
+	size_t out_bpl)
 {
 	unsigned char tile[kMaxComp][64];
 	const int tw = F.tile_w, th = F.tile_h;
@@ -880,7 +903,16 @@ reconstruct_mcu(const JpegFrameDev &F, const short *coef_pool, int mx, int my, u
 		for (int by = 0; by < F.v[c]; by++)
 			for (int bx = 0; bx < F.h[c]; bx++) {
 				const short *blk = coef_pool + F.coef_off[c] + ((size_t) (my * F.v[c] + by) * F.blocks_x[c] + (size_t) (mx * F.h[c] + bx)) * 64;
-				idct_scaled(F.dct[c], blk, F.qt[c], &tile[c][by * F.dct[c] * tw + bx * F.dct[c]], tw);
+				/* the block as eight 16-byte loads (blocks are 128-byte aligned) instead of up to 64 two-byte ones */
+				short cf[64];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+				for (int i = 0; i < 8; i++)
+					((uint4 *) cf)[i] = __ldg((const uint4 *) blk + i);
+#else
+				memcpy(cf, blk, sizeof(cf));
+#endif
+				idct_scaled(F.dct[c], cf, qt[c], &tile[c][by * F.dct[c] * tw + bx * F.dct[c]], tw);
 			}
 	const int x0 = mx * tw, y0 = my * th;
 	const int bands = F.ncomp == 3 ? 3 : 1;
@@ -930,14 +962,18 @@ __global__ void __launch_bounds__(128)
 jpeg_idct_kernel(const JpegFrameDev *__restrict__ frames, const short *__restrict__ coef, unsigned char *__restrict__ out, size_t out_bpl,
 	size_t out_frame_stride)
 {
+	__shared__ unsigned short s_qt[kMaxComp][64];
 	const JpegFrameDev &F = frames[blockIdx.y];
+	for (int j = threadIdx.x; j < kMaxComp * 64; j += blockDim.x)
+		s_qt[j >> 6][j & 63] = F.qt[j >> 6][j & 63];
+	__syncthreads();
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= F.mcus_x * F.mcus_y)
 		return;
 	const int my = i / F.mcus_x, mx = i - my * F.mcus_x;
 	if (mx * F.tile_w >= F.out_w || my * F.tile_h >= F.out_h)
 		return;
-	reconstruct_mcu(F, coef, mx, my, out + (size_t) blockIdx.y * out_frame_stride, out_bpl);
+	reconstruct_mcu(F, s_qt, coef, mx, my, out + (size_t) blockIdx.y * out_frame_stride, out_bpl);
 }
 
 /* ------------------------------------------------------------------ host: frame preparation and the pump */
@@ -1233,7 +1269,10 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	cudaMemGetInfo(&free_b, &total_b);
 	/* the slots keep their pools: an eighth of the device per chunk, three chunks in flight */
 	const size_t coef_budget = std::max<size_t>(total_b / 8, (size_t) 1 << 30);
-	int chunk = max_int >= 32 ? 64 : n;
+	/* more intervals in flight decode faster per frame (the kernel is latency-bound per thread), more chunks overlap
+	 * staging and copies better: a quarter of the batch, between 64 and 256 frames
+	 */
+	int chunk = max_int >= 32 ? std::max(64, std::min(256, (n + 3) / 4)) : n;
 	if (const char *e = getenv("VB200_JPEG_CHUNK"))
 		if (atoi(e) > 0)
 			chunk = atoi(e);
@@ -1275,6 +1314,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_o = off_h + ((sz_h + 15) & ~(size_t) 15);
 		const size_t off_b = off_o + ((ints_total * sizeof(unsigned) + 15) & ~(size_t) 15);
 		const size_t total = off_b + bytes_total + 16;
+		if (trace)
+			fprintf(stderr, "[jpeg] chunk %d begins at %.2f ms\n", k, since());
 		if (sl.busy) {
 			if (cudaEventSynchronize(sl.done) != cudaSuccess) {
 				rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
@@ -1295,6 +1336,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			sl.cap = want;
 		}
 		char *hst = (char *) sl.pinned;
+		if (trace)
+			fprintf(stderr, "[jpeg] chunk %d slot free at %.2f ms\n", k, since());
 		parallel_for(cn, host_workers(), [&](int i) {
 			const FramePrep &fp = prep[c0 + i];
 			JpegFrameDev F = fp.F;
@@ -1447,7 +1490,7 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 	for (int my = 0; my < F.mcus_y; my++)
 		for (int mx = 0; mx < F.mcus_x; mx++)
 			if (mx * F.tile_w < F.out_w && my * F.tile_h < F.out_h)
-				reconstruct_mcu(F, coef.data(), mx, my, out, out_bpl);
+				reconstruct_mcu(F, F.qt, coef.data(), mx, my, out, out_bpl);
 	return 0;
 }
 
