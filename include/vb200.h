@@ -409,6 +409,10 @@ int vb200_thumbnail_plan_run_jpeg(VB200ThumbnailPlan *plan, const void *const *b
 	void *out, int out_location, size_t out_frame_stride);
 int vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height,
 	int *bands);
+/* test hook, host only: the self-synchronising decode of a scan without restart markers (subsequences of sub_bytes,
+ * max_passes passes), *passes_used = the last pass that changed a record */
+int vb200_debug_jpeg_decode_sync(const void *buf, size_t len, int shrink, int sub_bytes, int max_passes, void *out, size_t out_bpl,
+	int *width, int *height, int *bands, int *passes_used);
 /* with env VB200_JPEG_TIMING: CUDA-event times of jpeg_huffman_kernel / jpeg_idct_kernel over the calling thread's last decode */
 void vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms);
 

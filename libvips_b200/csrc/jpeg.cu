@@ -103,6 +103,11 @@ struct JpegFrameDev {
 	int out_w, out_h, tile_w, tile_h; /* cropped output, and the MCU's footprint in output pixels */
 	int blocks_per_mcu;				  /* T.81 A.2.3: component by component, rows of blocks, left to right */
 	unsigned char blk_comp[12], blk_dx[12], blk_dy[12];
+	/* the self-synchronising path (frames with too few restart intervals to fill the machine) */
+	int sync;			 /* 1: decode by subsequences */
+	unsigned clean_len;	 /* bytes of the unstuffed scan (set while staging) */
+	unsigned sync_off;	 /* first of this frame's subsequence records in the chunk's arrays */
+	unsigned sync_cap;	 /* records reserved (from the stuffed length) */
 };
 
 const unsigned char kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14,
@@ -401,22 +406,17 @@ build_huff(const unsigned char count[16], const unsigned char *sym, HuffDev *t)
 
 /* ------------------------------------------------------------------ entropy decoding (host + device) */
 
+/* The reader works on the UNSTUFFED scan: the host removes the FF00 stuffing and the RSTn markers while it copies a
+ * frame's bytes into pinned staging (destuff_scan), so a position in the stream is a plain bit index -- which is what
+ * lets a decoder start anywhere (the self-synchronising path below) -- and four bytes go in at a time unconditionally.
+ */
 struct BitReader {
-	const unsigned char *base; /* 4-byte aligned start of the frame's bytes (readable 8 bytes past any interval's end) */
-	unsigned pos, end;			/* byte offsets from base */
+	const unsigned char *base; /* 4-byte aligned start of the frame's clean bytes (readable, zero, 16 bytes past the end) */
+	unsigned pos, end;			/* byte offsets from base: next byte to load, end of the interval */
 	unsigned long long acc;		/* bits are consumed from the top */
 	int n;
+	unsigned bit;				/* index of the next unread bit, from base */
 };
-
-HD void
-br_init(BitReader &b, const unsigned char *base, unsigned pos, unsigned end)
-{
-	b.base = base;
-	b.pos = pos;
-	b.end = end;
-	b.acc = 0;
-	b.n = 0;
-}
 
 /* bytes pos .. pos + 3 as one big-endian word, from two aligned loads */
 HD unsigned
@@ -433,41 +433,35 @@ br_load_be32(const unsigned char *base, unsigned pos)
 #endif
 }
 
-/* at least 32 valid bits (zeros past the end of the interval, as jdhuff.c feeds on a premature end).  Four bytes at
- * a time while none of them is 0xFF (one in ~256 is); the byte path handles FF00 (a stuffed FF) and markers.
- */
+/* at least 32 valid bits (zeros past the end of the interval, as jdhuff.c feeds on a premature end) */
 HD void
 br_fill(BitReader &b)
 {
 	if (b.n > 32)
 		return;
-	if (b.pos + 4 <= b.end) {
-		const unsigned w = br_load_be32(b.base, b.pos);
-		const unsigned x = ~w;
-		if (((x - 0x01010101u) & ~x & 0x80808080u) == 0) { /* no 0xFF byte */
-			b.acc |= (unsigned long long) w << (32 - b.n);
-			b.n += 32;
-			b.pos += 4;
-			return;
-		}
-	}
-	while (b.n <= 56) {
-		unsigned v = 0;
-		if (b.pos < b.end) {
-			v = b.base[b.pos++];
-			if (v == 0xFF) {
-				/* FF00 is a stuffed FF; anything else is a marker: the interval is over, feed zeros */
-				if (b.pos < b.end && b.base[b.pos] == 0x00)
-					b.pos++;
-				else {
-					b.pos = b.end;
-					v = 0;
-				}
-			}
-		}
-		b.acc |= (unsigned long long) v << (56 - b.n);
-		b.n += 8;
-	}
+	unsigned w = 0;
+	if (b.pos + 4 <= b.end)
+		w = br_load_be32(b.base, b.pos);
+	else if (b.pos < b.end)
+		w = br_load_be32(b.base, b.pos) & (0xffffffffu << (8 * (4 - (b.end - b.pos))));
+	b.acc |= (unsigned long long) w << (32 - b.n);
+	b.n += 32;
+	b.pos += 4;
+}
+
+/* start reading at bit index `bit` of the stream that ends at byte `end` */
+HD void
+br_init(BitReader &b, const unsigned char *base, unsigned bit, unsigned end)
+{
+	b.base = base;
+	b.pos = bit >> 3;
+	b.end = end;
+	b.acc = 0;
+	b.n = 0;
+	b.bit = bit;
+	br_fill(b);
+	b.acc <<= (bit & 7u);
+	b.n -= (int) (bit & 7u);
 }
 
 HD int
@@ -481,6 +475,7 @@ br_skip(BitReader &b, int bits)
 {
 	b.acc <<= bits;
 	b.n -= bits;
+	b.bit += (unsigned) bits;
 }
 
 /* one Huffman symbol (T.81 F.2.2.3); -1 on a code that is not in the table */
@@ -554,7 +549,7 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
 	if (mcu0 >= mcu1)
 		return 0;
 	BitReader b;
-	br_init(b, base, pos, end);
+	br_init(b, base, pos * 8u, end);
 	int pred0 = 0, pred1 = 0, pred2 = 0;
 	const int nb = M.n, mcus_x = M.mcus_x;
 	int mcu = mcu0, bi = 0, k = 0;
@@ -624,6 +619,212 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
 			blk = coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
 		}
 	}
+}
+
+/* ------------------------------------------------------------------ self-synchronising decode
+ *
+ * A scan without restart markers is one dependent chain: symbol n + 1 starts where symbol n ends.  But Huffman streams
+ * re-synchronise: a decoder started at a wrong bit, in a wrong position of a wrong block, falls into step with the true
+ * parse after a few dozen symbols with overwhelming probability, and from then on IS the true parse.  So (after Klein &
+ * Wiseman, and Weissenberger & Schmidt's GPU formulation of it for JPEG):
+ *   pass 0      one thread per subsequence of kSyncBytes, started blind at its first bit as if a block began there,
+ *               decodes to the first symbol boundary past its end and records that state (bit, k, block-in-MCU) and
+ *               the number of blocks it completed;
+ *   pass 1..n   every thread restarts from its LEFT neighbour's recorded end state; a thread whose start state did not
+ *               change since its last decode just copies its record (so converged stretches cost nothing), and a pass
+ *               in which nobody decodes ends the iteration.  Subsequence 0 starts from the true state, so truth advances
+ *               at least one subsequence per pass; every blind decode that fell into step lets it jump.  A JPEG decoder
+ *               falls into step fully only when bit position, zig-zag index AND block-in-MCU agree -- the last is a random
+ *               walk (Y0..Y3 share tables, so do Cb and Cr) -- so about half the subsequences of a photograph at q85 end
+ *               true after pass 0 and 5-10 passes settle it (measured, tests/test_jpeg.py); at q100, where blocks never
+ *               end early, hardly any do and the passes run into the dozens: correct, but no faster than one thread;
+ *   scan        an exclusive prefix sum of the block counts gives every subsequence the index of its first block;
+ *   write       the same decode once more, now storing coefficients (DC as the DIFFERENCE, the predictor is not known
+ *               mid-stream), and checking that start and end states are the recorded ones: any mismatch fails the frame;
+ *   DC          a per-component prefix sum over the blocks in scan order turns differences into values.
+ * The parse state is exactly (bit, k, block-in-MCU): it decides which table the next code is read with.
+ */
+struct SyncState {
+	unsigned bit;
+	unsigned short k, bi;
+};
+
+HD bool
+sync_same(const SyncState &a, const SyncState &b)
+{
+	return a.bit == b.bit && a.k == b.k && a.bi == b.bi;
+}
+
+/* Decode from state st while the next symbol starts before limit_bit.  WRITE: store coefficients of block blk_index
+ * onwards (never past total_blocks); else only count.  *nblocks = blocks completed.  Returns 0, or -1 on a code that
+ * is not in the table / a run past the block (a blind start that has not synchronised yet, or corrupt data): st is
+ * then (limit_bit, 0, 0).
+ */
+template <bool WRITE>
+HD int
+decode_span(const McuLayout &M, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned end_byte, SyncState &st,
+	unsigned limit_bit, unsigned blk_index, unsigned total_blocks, short *coef_pool, unsigned *nblocks)
+{
+	BitReader b;
+	br_init(b, base, st.bit, end_byte);
+	const int nb = M.n, mcus_x = M.mcus_x;
+	int k = st.k, bi = st.bi;
+	unsigned done = 0;
+	int mx = 0, my = 0;
+	short *blk = nullptr;
+	if (WRITE) {
+		const unsigned mcu = blk_index / (unsigned) nb;
+		my = (int) (mcu / (unsigned) mcus_x);
+		mx = (int) (mcu - (unsigned) my * (unsigned) mcus_x);
+		blk = coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
+	}
+	const HuffDev *dc = huff + M.dc[bi], *ac = huff + M.ac[bi];
+	int rc = 0;
+	while (b.bit < limit_bit && (!WRITE || blk_index + done < total_blocks)) {
+		br_fill(b);
+		const int f = k > 0 ? ac->fast[br_peek(b, kLook)] : 0;
+		if (f) {
+			k += (f >> 4) & 15;
+			if (k > 63) {
+				rc = -1;
+				break;
+			}
+			br_skip(b, f & 15);
+			if (WRITE)
+				blk[zz[k]] = (short) (f >> 8);
+			k++;
+		}
+		else if (k == 0) {
+			const int sym = huff_decode(b, dc);
+			if (sym < 0 || sym > 11) {
+				rc = -1;
+				break;
+			}
+			const int diff = br_receive_extend(b, sym);
+			if (WRITE)
+				blk[0] = (short) diff; /* the DC scan adds the predictor */
+			k = 1;
+		}
+		else {
+			const int sym = huff_decode(b, ac);
+			if (sym < 0) {
+				rc = -1;
+				break;
+			}
+			const int r = sym >> 4, sz = sym & 15;
+			if (sz == 0)
+				k = r == 15 ? k + 16 : 64;
+			else {
+				k += r;
+				const int v = br_receive_extend(b, sz);
+				if (k > 63) {
+					rc = -1;
+					break;
+				}
+				if (WRITE)
+					blk[zz[k]] = (short) v;
+				k++;
+			}
+		}
+		if (k >= 64) {
+			k = 0;
+			done++;
+			if (++bi == nb) {
+				bi = 0;
+				if (++mx == mcus_x) {
+					mx = 0;
+					my++;
+				}
+			}
+			dc = huff + M.dc[bi];
+			ac = huff + M.ac[bi];
+			if (WRITE)
+				blk = coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
+		}
+	}
+	*nblocks = done;
+	if (rc) {
+		st.bit = limit_bit;
+		st.k = 0;
+		st.bi = 0;
+		return -1;
+	}
+	st.bit = b.bit;
+	st.k = (unsigned short) k;
+	st.bi = (unsigned short) bi;
+	return 0;
+}
+
+/* one synchronisation pass of one subsequence (pass 0: blind start); true when it had to decode (its start state was
+ * not the one it decoded from last time): a pass in which nobody decodes means the records are final
+ */
+HD bool
+sync_pass(const McuLayout &M, const HuffDev *huff, const unsigned char *base, unsigned clean_len, unsigned sub_bytes, int pass, unsigned s,
+	const SyncState *Ein, const unsigned *Nin, SyncState *Eout, unsigned *Nout, SyncState *start_used)
+{
+	SyncState st;
+	if (pass == 0 || s == 0) {
+		st.bit = s * sub_bytes * 8u;
+		st.k = 0;
+		st.bi = 0;
+	}
+	else
+		st = Ein[s - 1];
+	if (pass > 0 && sync_same(st, start_used[s])) {
+		Eout[s] = Ein[s];
+		Nout[s] = Nin[s];
+		return false;
+	}
+	start_used[s] = st;
+	const unsigned long long lim = (unsigned long long) (s + 1) * sub_bytes * 8ull;
+	const unsigned limit = (unsigned) (lim < (unsigned long long) clean_len * 8ull ? lim : (unsigned long long) clean_len * 8ull);
+	unsigned n = 0;
+	decode_span<false>(M, huff, nullptr, base, clean_len, st, limit, 0, 0, nullptr, &n);
+	Eout[s] = st;
+	Nout[s] = n;
+	return true;
+}
+
+/* the write pass of one subsequence; returns 0, 1 (corrupt data) or 2 (the recorded states are not the ones met) */
+HD int
+sync_write(const McuLayout &M, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned clean_len, unsigned sub_bytes,
+	unsigned s, unsigned S, const SyncState *E, const unsigned *Base, const SyncState *start_used, unsigned total_blocks, short *coef_pool)
+{
+	SyncState st;
+	if (s == 0) {
+		st.bit = 0;
+		st.k = 0;
+		st.bi = 0;
+	}
+	else
+		st = E[s - 1];
+	if (!sync_same(st, start_used[s]))
+		return 2;
+	if (Base[s] >= total_blocks)
+		return 0; /* padding after the last block */
+	const unsigned long long lim = (unsigned long long) (s + 1) * sub_bytes * 8ull;
+	const unsigned limit = (unsigned) (lim < (unsigned long long) clean_len * 8ull ? lim : (unsigned long long) clean_len * 8ull);
+	unsigned n = 0;
+	const int rc = decode_span<true>(M, huff, zz, base, clean_len, st, limit, Base[s], total_blocks, coef_pool, &n);
+	if (Base[s] + n >= total_blocks)
+		return rc ? 1 : 0; /* the frame's last block ends here: what follows is padding */
+	if (rc)
+		return 1;
+	if (s + 1 < S && !sync_same(st, E[s]))
+		return 2;
+	if (s + 1 == S)
+		return 1; /* the data ended before the last block */
+	return 0;
+}
+
+/* DC differences -> values for component c of a frame: blocks in scan order, i = mcu * per + sub */
+HD short *
+dc_block(const McuLayout &M, const int *first, int per, unsigned i, short *coef_pool)
+{
+	const unsigned mcu = i / (unsigned) per;
+	const int bi = first[0] + (int) (i - mcu * (unsigned) per);
+	const unsigned my = mcu / (unsigned) M.mcus_x, mx = mcu - my * (unsigned) M.mcus_x;
+	return coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
 }
 
 /* ------------------------------------------------------------------ inverse DCTs (jidctint.c, jidctred.c) */
@@ -942,6 +1143,8 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 {
 	__shared__ McuLayout M;
 	const JpegFrameDev &F = frames[blockIdx.y];
+	if (F.sync)
+		return; /* the subsequence kernels decode this frame */
 	if (threadIdx.x == 0)
 		mcu_layout(F, M);
 	__syncthreads();
@@ -955,6 +1158,124 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 	const int mcu0 = i * per, mcu1 = min(total, mcu0 + per);
 	if (decode_interval(M, huff + F.huff_base, d_zigzag, base, off[i], off[i + 1], mcu0, mcu1, coef))
 		atomicOr(status + blockIdx.y, 1);
+}
+
+/* the self-synchronising path: one thread per subsequence; blockIdx.y = frame */
+constexpr int kSyncThreads = 64;
+
+__global__ void __launch_bounds__(kSyncThreads)
+jpeg_sync_pass_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__restrict__ huff, const unsigned char *__restrict__ bytes,
+	int pass, unsigned sub_bytes, const SyncState *__restrict__ Ein, const unsigned *__restrict__ Nin, SyncState *__restrict__ Eout,
+	unsigned *__restrict__ Nout, SyncState *__restrict__ start_used, int *__restrict__ redo)
+{
+	__shared__ McuLayout M;
+	const JpegFrameDev &F = frames[blockIdx.y];
+	if (!F.sync)
+		return;
+	if (threadIdx.x == 0)
+		mcu_layout(F, M);
+	__syncthreads();
+	const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned S = (F.clean_len + sub_bytes - 1) / sub_bytes;
+	if (s >= S)
+		return;
+	if (sync_pass(M, huff + F.huff_base, bytes + F.data_off, F.clean_len, sub_bytes, pass, s, Ein + F.sync_off, Nin + F.sync_off,
+			Eout + F.sync_off, Nout + F.sync_off, start_used + F.sync_off) &&
+		pass > 0)
+		*redo = 1; /* benign race: every writer stores 1 */
+}
+
+/* exclusive prefix sum of a frame's block counts: one CTA per frame, a contiguous run of subsequences per thread */
+__global__ void __launch_bounds__(1024)
+jpeg_sync_scan_kernel(const JpegFrameDev *__restrict__ frames, unsigned sub_bytes, const unsigned *__restrict__ N, unsigned *__restrict__ Base)
+{
+	__shared__ unsigned s_part[1024];
+	const JpegFrameDev &F = frames[blockIdx.x];
+	if (!F.sync)
+		return;
+	const unsigned S = (F.clean_len + sub_bytes - 1) / sub_bytes;
+	const unsigned per = (S + blockDim.x - 1) / blockDim.x;
+	const unsigned a = min(S, threadIdx.x * per), b = min(S, a + per);
+	const unsigned *n = N + F.sync_off;
+	unsigned sum = 0;
+	for (unsigned i = a; i < b; i++)
+		sum += n[i];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	/* Hillis-Steele over the 1024 partials */
+	for (unsigned o = 1; o < blockDim.x; o <<= 1) {
+		const unsigned v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned run = s_part[threadIdx.x] - sum; /* exclusive */
+	unsigned *base = Base + F.sync_off;
+	for (unsigned i = a; i < b; i++) {
+		base[i] = run;
+		run += n[i];
+	}
+}
+
+__global__ void __launch_bounds__(kSyncThreads)
+jpeg_sync_write_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__restrict__ huff, const unsigned char *__restrict__ bytes,
+	unsigned sub_bytes, const SyncState *__restrict__ E, const unsigned *__restrict__ Base, const SyncState *__restrict__ start_used,
+	short *__restrict__ coef, int *__restrict__ status)
+{
+	__shared__ McuLayout M;
+	const JpegFrameDev &F = frames[blockIdx.y];
+	if (!F.sync)
+		return;
+	if (threadIdx.x == 0)
+		mcu_layout(F, M);
+	__syncthreads();
+	const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned S = (F.clean_len + sub_bytes - 1) / sub_bytes;
+	if (s >= S)
+		return;
+	const int rc = sync_write(M, huff + F.huff_base, d_zigzag, bytes + F.data_off, F.clean_len, sub_bytes, s, S, E + F.sync_off, Base + F.sync_off,
+		start_used + F.sync_off, (unsigned) (F.mcus_x * F.mcus_y * F.blocks_per_mcu), coef);
+	if (rc)
+		atomicOr(status + blockIdx.y, rc);
+}
+
+/* DC differences -> DC values: blockIdx.x = component, blockIdx.y = frame; a contiguous run of blocks per thread */
+__global__ void __launch_bounds__(256)
+jpeg_dc_scan_kernel(const JpegFrameDev *__restrict__ frames, short *__restrict__ coef)
+{
+	__shared__ McuLayout M;
+	__shared__ int s_part[256];
+	const JpegFrameDev &F = frames[blockIdx.y];
+	const int c = blockIdx.x;
+	if (!F.sync || c >= F.ncomp)
+		return;
+	if (threadIdx.x == 0)
+		mcu_layout(F, M);
+	__syncthreads();
+	int first = 0;
+	while (first < M.n && M.comp[first] != c)
+		first++;
+	const int per = F.h[c] * F.v[c];
+	const unsigned total = (unsigned) (F.mcus_x * F.mcus_y * per);
+	const unsigned seg = (total + blockDim.x - 1) / blockDim.x;
+	const unsigned a = min(total, threadIdx.x * seg), b = min(total, a + seg);
+	int sum = 0;
+	for (unsigned i = a; i < b; i++)
+		sum += dc_block(M, &first, per, i, coef)[0];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	for (unsigned o = 1; o < blockDim.x; o <<= 1) {
+		const int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	int run = s_part[threadIdx.x] - sum;
+	for (unsigned i = a; i < b; i++) {
+		short *p = dc_block(M, &first, per, i, coef);
+		run += p[0];
+		p[0] = (short) run;
+	}
 }
 
 /* one thread per MCU */
@@ -1099,6 +1420,53 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 	return 0;
 }
 
+/* Copy a frame's entropy-coded segment into staging WITHOUT its byte stuffing and restart markers: FF00 -> FF, RSTn
+ * dropped with the clean offset of what follows recorded as an interval boundary (intervals start byte-aligned, T.81
+ * F.1.2.3 pads the one before with 1-bits).  offsets gets want + 1 entries; returns the clean length, or (size_t) -1
+ * when the markers found are not the want - 1 the header promised.  Runs on the staging workers: it is the copy
+ * into pinned memory they had to do anyway.
+ */
+size_t
+destuff_scan(const unsigned char *src, size_t len, unsigned char *dst, unsigned *offsets, int want)
+{
+	size_t p = 0, o = 0;
+	int found = 1;
+	offsets[0] = 0;
+	while (p < len) {
+		const unsigned char *q = (const unsigned char *) memchr(src + p, 0xFF, len - p);
+		if (!q) {
+			memcpy(dst + o, src + p, len - p);
+			o += len - p;
+			break;
+		}
+		const size_t i = q - src;
+		const int nx = i + 1 < len ? src[i + 1] : 0xD9;
+		if (nx == 0x00) {
+			memcpy(dst + o, src + p, i + 1 - p); /* through the FF */
+			o += i + 1 - p;
+			p = i + 2;
+		}
+		else {
+			memcpy(dst + o, src + p, i - p);
+			o += i - p;
+			if (nx >= 0xD0 && nx <= 0xD7) {
+				if (found >= want)
+					return (size_t) -1;
+				offsets[found++] = (unsigned) o;
+				p = i + 2;
+			}
+			else if (nx == 0xFF)
+				p = i + 1; /* a fill byte */
+			else
+				break; /* EOI or any other marker: the scan is over */
+		}
+	}
+	if (found != want)
+		return (size_t) -1;
+	offsets[want] = (unsigned) o;
+	return o;
+}
+
 /* run fn(i) for i in [0, n) on up to `threads` host threads */
 template <typename Fn>
 void
@@ -1152,6 +1520,8 @@ struct JpegSlot {
 	void *dev = nullptr, *coef = nullptr; /* device twins of the staging block, and the coefficient pool (grow-only: a pool
 											* allocation per chunk cost more than the chunk's kernels) */
 	size_t dev_cap = 0, coef_cap = 0;
+	void *sync = nullptr; /* subsequence records of the self-synchronising path */
+	size_t sync_cap = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	bool busy = false;
@@ -1170,6 +1540,8 @@ struct JpegPump {
 				cudaFree(sl.dev);
 			if (sl.coef)
 				cudaFree(sl.coef);
+			if (sl.sync)
+				cudaFree(sl.sync);
 			if (sl.done)
 				cudaEventDestroy(sl.done);
 			if (sl.stream)
@@ -1269,10 +1641,26 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	cudaMemGetInfo(&free_b, &total_b);
 	/* the slots keep their pools: an eighth of the device per chunk, three chunks in flight */
 	const size_t coef_budget = std::max<size_t>(total_b / 8, (size_t) 1 << 30);
+	/* frames with one restart interval (no DRI) and a scan worth splitting decode by self-synchronising subsequences;
+	 * VB200_JPEG_SYNC=0: never (one thread per frame), =N: subsequences of N bytes, any size of scan
+	 */
+	unsigned sub_bytes = 1024;
+	size_t sync_min_bytes = 64 * 1024;
+	if (const char *e = getenv("VB200_JPEG_SYNC")) {
+		sub_bytes = (unsigned) std::max(0, atoi(e));
+		sync_min_bytes = 0;
+	}
+	int sync_passes = 256;
+	if (const char *e = getenv("VB200_JPEG_SYNC_PASSES"))
+		sync_passes = std::max(1, atoi(e));
 	/* more intervals in flight decode faster per frame (the kernel is latency-bound per thread), more chunks overlap
 	 * staging and copies better: a quarter of the batch, between 64 and 256 frames
 	 */
-	int chunk = max_int >= 32 ? std::max(64, std::min(256, (n + 3) / 4)) : n;
+	bool any_plain_single = false;
+	for (int i = 0; i < n; i++)
+		if (prep[i].F.n_intervals == 1 && !(sub_bytes > 0 && prep[i].src_len >= sync_min_bytes && prep[i].src_len / sub_bytes >= 8))
+			any_plain_single = true;
+	int chunk = (max_int >= 32 || !any_plain_single) ? std::max(64, std::min(256, (n + 3) / 4)) : n;
 	if (const char *e = getenv("VB200_JPEG_CHUNK"))
 		if (atoi(e) > 0)
 			chunk = atoi(e);
@@ -1286,6 +1674,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	chunk = (int) std::max<size_t>(1, std::min<size_t>(chunk, coef_budget / std::max<size_t>(1, max_coef * sizeof(short))));
 	chunk = std::min(chunk, n);
 
+	std::atomic<int> bad_frame(-1);
 	int *status = nullptr;
 	if (dev_alloc(domain, (void **) &status, (size_t) n * sizeof(int), s))
 		return -1;
@@ -1297,18 +1686,26 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		JpegSlot &sl = P.slot[k % kJpegSlots];
 		/* layout of the chunk's block */
 		std::vector<size_t> data_off(cn), int_off(cn), coef_off(cn);
-		size_t bytes_total = 0, ints_total = 0, coef_total = 0;
+		std::vector<unsigned> sync_off(cn, 0), sync_cap(cn, 0);
+		size_t bytes_total = 0, ints_total = 0, coef_total = 0, sync_total = 0;
 		int max_intervals = 0, max_mcus = 0;
+		unsigned max_subs = 0;
 		for (int i = 0; i < cn; i++) {
 			const FramePrep &fp = prep[c0 + i];
 			data_off[i] = bytes_total;
-			bytes_total += (fp.src_len + 15) & ~(size_t) 15;
+			bytes_total += ((fp.src_len + 15) & ~(size_t) 15) + 16;
 			int_off[i] = ints_total;
 			ints_total += fp.offsets.size();
 			coef_off[i] = coef_total;
 			coef_total += fp.coef_count;
 			max_intervals = std::max(max_intervals, fp.F.n_intervals);
 			max_mcus = std::max(max_mcus, fp.F.mcus_x * fp.F.mcus_y);
+			if (fp.F.n_intervals == 1 && sub_bytes > 0 && fp.src_len >= sync_min_bytes && fp.src_len / sub_bytes >= 8) {
+				sync_off[i] = (unsigned) sync_total;
+				sync_cap[i] = (unsigned) ((fp.src_len + sub_bytes - 1) / sub_bytes + 1);
+				sync_total += sync_cap[i];
+				max_subs = std::max(max_subs, sync_cap[i]);
+			}
 		}
 		const size_t sz_f = (size_t) cn * sizeof(JpegFrameDev), sz_h = (size_t) cn * 8 * sizeof(HuffDev);
 		const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_o = off_h + ((sz_h + 15) & ~(size_t) 15);
@@ -1340,17 +1737,32 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			fprintf(stderr, "[jpeg] chunk %d slot free at %.2f ms\n", k, since());
 		parallel_for(cn, host_workers(), [&](int i) {
 			const FramePrep &fp = prep[c0 + i];
+			unsigned char *dst = (unsigned char *) hst + off_b + data_off[i];
+			const size_t clean = destuff_scan(fp.src, fp.src_len, dst, (unsigned *) (hst + off_o) + int_off[i], fp.F.n_intervals);
+			if (clean == (size_t) -1) {
+				int none = -1;
+				bad_frame.compare_exchange_strong(none, c0 + i);
+				return;
+			}
 			JpegFrameDev F = fp.F;
 			F.data_off = data_off[i];
 			F.interval_off = int_off[i];
 			for (int c = 0; c < F.ncomp; c++)
 				F.coef_off[c] += coef_off[i];
 			F.huff_base = 8 * i;
+			F.clean_len = (unsigned) clean;
+			F.sync = sync_cap[i] > 0;
+			F.sync_off = sync_off[i];
+			F.sync_cap = sync_cap[i];
 			memcpy(hst + (size_t) i * sizeof(JpegFrameDev), &F, sizeof(F));
 			memcpy(hst + off_h + (size_t) i * 8 * sizeof(HuffDev), fp.huff, 8 * sizeof(HuffDev));
-			memcpy(hst + off_o + int_off[i] * sizeof(unsigned), fp.offsets.data(), fp.offsets.size() * sizeof(unsigned));
-			memcpy(hst + off_b + data_off[i], fp.src, fp.src_len);
+			memset(dst + clean, 0, (((fp.src_len + 15) & ~(size_t) 15) + 16) - clean); /* the reader's look-ahead past the end */
 		});
+		if (bad_frame.load() >= 0) {
+			error(domain, "frame %d: restart markers do not match the restart interval", bad_frame.load());
+			rc = -1;
+			break;
+		}
 		if (trace)
 			fprintf(stderr, "[jpeg] chunk %d (%d frames) staged at %.2f ms\n", k, cn, since());
 		cudaStream_t st = sl.stream;
@@ -1372,7 +1784,10 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			*cap = want + want / 8;
 			return true;
 		};
-		if (!grow(&sl.dev, &sl.dev_cap, total) || !grow(&sl.coef, &sl.coef_cap, coef_total * sizeof(short))) {
+		/* per subsequence: two (state, count) records, the start state last decoded from, the first block's index */
+		const size_t sync_rec = 2 * sizeof(SyncState) + 2 * sizeof(unsigned) + sizeof(SyncState) + sizeof(unsigned);
+		if (!grow(&sl.dev, &sl.dev_cap, total) || !grow(&sl.coef, &sl.coef_cap, coef_total * sizeof(short)) ||
+			(sync_total && !grow(&sl.sync, &sl.sync_cap, sync_total * sync_rec + 256))) {
 			rc = -1;
 			break;
 		}
@@ -1392,6 +1807,50 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 				for (auto &e : ev)
 					cudaEventCreate(&e);
 				cudaEventRecord(ev[0], st);
+			}
+			if (sync_total) {
+				SyncState *Ea = (SyncState *) sl.sync, *Eb = Ea + sync_total, *Su = Eb + sync_total;
+				unsigned *Na = (unsigned *) (Su + sync_total), *Nb = Na + sync_total, *Bs = Nb + sync_total;
+				const dim3 sg((max_subs + kSyncThreads - 1) / kSyncThreads, cn);
+				/* passes until one in which no subsequence had to decode again: groups of four, each pass with its own flag
+				 * word (after the records), read back after the group -- this chunk's stream waits, the others run on
+				 */
+				int *redo = (int *) (Bs + sync_total);
+				int pass = 0;
+				bool settled = false;
+				while (!settled && pass < sync_passes) {
+					int flags[4] = {1, 1, 1, 1};
+					cudaMemsetAsync(redo, 0, sizeof(flags), st);
+					int g = 0;
+					for (; g < 4 && pass < sync_passes; g++, pass++) {
+						jpeg_sync_pass_kernel<<<sg, kSyncThreads, 0, st>>>(dF, dH, dB, pass, sub_bytes, Ea, Na, Eb, Nb, Su, redo + g);
+						std::swap(Ea, Eb);
+						std::swap(Na, Nb);
+						count_launch();
+					}
+					if (cudaMemcpyAsync(flags, redo, sizeof(flags), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+						cudaStreamSynchronize(st) != cudaSuccess) {
+						rc = cuda_fail(domain, cudaGetLastError(), "jpeg_sync_pass_kernel");
+						break;
+					}
+					for (int j = pass - g == 0 ? 1 : 0; j < g; j++)
+						if (flags[j] == 0)
+							settled = true; /* later passes of the group only copied */
+				}
+				if (rc)
+					break;
+				/* not settled: the write pass finds the inconsistency and fails the frame */
+				jpeg_sync_scan_kernel<<<cn, 1024, 0, st>>>(dF, sub_bytes, Na, Bs);
+				jpeg_sync_write_kernel<<<sg, kSyncThreads, 0, st>>>(dF, dH, dB, sub_bytes, Ea, Bs, Su, (short *) coef, status + c0);
+				jpeg_dc_scan_kernel<<<dim3(kMaxComp, cn), 256, 0, st>>>(dF, (short *) coef);
+				cudaError_t es = cudaGetLastError();
+				if (es != cudaSuccess) {
+					rc = cuda_fail(domain, es, "jpeg_sync kernels launch");
+					break;
+				}
+				count_launch();
+				count_launch();
+				count_launch();
 			}
 			/* CTA width: one interval per warp while the chunk has fewer intervals than the machine has CTA slots */
 			int ht = 1;
@@ -1449,16 +1908,19 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	dev_free(status, s);
 	for (int i = 0; i < n && !rc; i++)
 		if (st[i]) {
-			error(domain, "frame %d: corrupt JPEG data: bad Huffman code", i);
+			error(domain, (st[i] & 1) ? "frame %d: corrupt JPEG data: bad Huffman code" : "frame %d: the subsequence decode did not converge (VB200_JPEG_SYNC_PASSES)", i);
 			rc = -1;
 		}
 	return rc;
 }
 
-/* the same decode on the CPU, through the same per-block code: test hook (tests/test_jpeg.py against libjpeg-turbo) */
+/* the same decode on the CPU, through the same per-block code: test hook (tests/test_jpeg.py against libjpeg-turbo).
+ * sub_bytes > 0 runs the self-synchronising algorithm (one "thread" after another) on a scan without restart markers and
+ * reports how many passes changed anything.
+ */
 int
 host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, unsigned char *out, size_t out_bpl, int *out_w, int *out_h,
-	int *bands)
+	int *bands, unsigned sub_bytes, int max_passes, int *passes_used)
 {
 	FramePrep P;
 	if (frame_prep(domain, (const unsigned char *) buf, len, shrink, &P))
@@ -1473,20 +1935,69 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 		return 0;
 	const JpegFrameDev &F = P.F;
 	std::vector<short> coef(P.coef_count, 0);
-	/* the reader loads aligned words up to 8 bytes past an interval's end: an aligned, padded copy, as the pump stages it */
-	std::vector<unsigned> padded_w((P.src_len + 16) / 4 + 1, 0);
-	memcpy(padded_w.data(), P.src, P.src_len);
-	const unsigned char *padded = (const unsigned char *) padded_w.data();
+	/* unstuffed, aligned, zero-padded: as the pump stages it */
+	std::vector<unsigned> padded_w((P.src_len + 32) / 4 + 1, 0);
+	unsigned char *padded = (unsigned char *) padded_w.data();
+	std::vector<unsigned> offs(F.n_intervals + 1);
+	const size_t clean = destuff_scan(P.src, P.src_len, padded, offs.data(), F.n_intervals);
+	if (clean == (size_t) -1) {
+		error(domain, "restart markers do not match the restart interval");
+		return -1;
+	}
 	const int total = F.mcus_x * F.mcus_y;
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
 	McuLayout M;
 	mcu_layout(F, M);
-	for (int i = 0; i < F.n_intervals; i++)
-		if (decode_interval(M, P.huff, kZigzag, padded, P.offsets[i], P.offsets[i + 1], i * per, std::min(total, (i + 1) * per),
-				coef.data())) {
-			error(domain, "corrupt JPEG data: bad Huffman code");
+	if (sub_bytes > 0 && F.n_intervals == 1) {
+		const unsigned S = (unsigned) ((clean + sub_bytes - 1) / sub_bytes);
+		std::vector<SyncState> Ea(S + 1), Eb(S + 1), Su(S + 1);
+		std::vector<unsigned> Na(S + 1, 0), Nb(S + 1, 0), Bs(S + 1, 0);
+		int used = 0;
+		for (int pass = 0; pass < max_passes; pass++) {
+			bool redo = false;
+			for (unsigned sx = 0; sx < S; sx++)
+				redo |= sync_pass(M, P.huff, padded, (unsigned) clean, sub_bytes, pass, sx, Ea.data(), Na.data(), Eb.data(), Nb.data(), Su.data());
+			Ea.swap(Eb);
+			Na.swap(Nb);
+			if (pass > 0 && !redo)
+				break;
+			used = pass + 1;
+		}
+		if (passes_used)
+			*passes_used = used;
+		unsigned run = 0;
+		for (unsigned sx = 0; sx < S; sx++) {
+			Bs[sx] = run;
+			run += Na[sx];
+		}
+		const unsigned total_blocks = (unsigned) (total * F.blocks_per_mcu);
+		int bad = 0;
+		for (unsigned sx = 0; sx < S; sx++)
+			bad |= sync_write(M, P.huff, kZigzag, padded, (unsigned) clean, sub_bytes, sx, S, Ea.data(), Bs.data(), Su.data(), total_blocks,
+				coef.data());
+		if (bad) {
+			error(domain, (bad & 1) ? "corrupt JPEG data: bad Huffman code" : "the subsequence decode did not converge");
 			return -1;
 		}
+		for (int c = 0; c < F.ncomp; c++) {
+			int first = 0;
+			while (first < M.n && M.comp[first] != c)
+				first++;
+			const int pc = F.h[c] * F.v[c];
+			int runv = 0;
+			for (unsigned i = 0; i < (unsigned) (total * pc); i++) {
+				short *p = dc_block(M, &first, pc, i, coef.data());
+				runv += p[0];
+				p[0] = (short) runv;
+			}
+		}
+	}
+	else
+		for (int i = 0; i < F.n_intervals; i++)
+			if (decode_interval(M, P.huff, kZigzag, padded, offs[i], offs[i + 1], i * per, std::min(total, (i + 1) * per), coef.data())) {
+				error(domain, "corrupt JPEG data: bad Huffman code");
+				return -1;
+			}
 	for (int my = 0; my < F.mcus_y; my++)
 		for (int mx = 0; mx < F.mcus_x; mx++)
 			if (mx * F.tile_w < F.out_w && my * F.tile_h < F.out_h)
@@ -1514,7 +2025,7 @@ vb200_jpeg_decode_batch(const void *const *bufs, const size_t *lens, int n, int 
 		}
 		for (int i = 0; i < n; i++) {
 			int wi, hi, bi;
-			if (host_jpeg_decode(domain, bufs[i], lens[i], shrink, nullptr, 0, &wi, &hi, &bi))
+			if (host_jpeg_decode(domain, bufs[i], lens[i], shrink, nullptr, 0, &wi, &hi, &bi, 0, 0, nullptr))
 				return -1;
 			if (i && (wi != w || hi != h || bi != b)) {
 				error(domain, "frames of a batch must decode to one geometry");
@@ -1614,6 +2125,17 @@ vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms)
 extern "C" int
 vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height, int *bands)
 {
-	return host_jpeg_decode("jpeg_decode (host twin)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands);
+	return host_jpeg_decode("jpeg_decode (host twin)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands, 0, 0, nullptr);
+}
+
+/* the host twin of the self-synchronising path: subsequences of sub_bytes, max_passes passes; *passes_used = the last pass
+ * that changed a record (the device runs a fixed number and fails a frame that needed more)
+ */
+extern "C" int
+vb200_debug_jpeg_decode_sync(const void *buf, size_t len, int shrink, int sub_bytes, int max_passes, void *out, size_t out_bpl, int *width,
+	int *height, int *bands, int *passes_used)
+{
+	return host_jpeg_decode("jpeg_decode (host twin, subsequences)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands,
+		(unsigned) std::max(0, sub_bytes), max_passes, passes_used);
 }
 

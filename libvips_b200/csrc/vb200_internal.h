@@ -158,7 +158,7 @@ int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int s
 int dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t *lens, int n, int shrink, void *out, size_t out_bpl,
 	size_t out_frame_stride, int *out_w, int *out_h, int *bands, cudaStream_t s);
 int host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, unsigned char *out, size_t out_bpl, int *out_w,
-	int *out_h, int *bands);
+	int *out_h, int *bands, unsigned sub_bytes, int max_passes, int *passes_used);
 /* min(hshrink, vshrink) of vips_thumbnail_calculate_shrink, thumbnail.c:413-487 */
 double thumbnail_common_shrink(int w, int h, int tw, int th, int size);
 void resample_cache_clear(); /* cached axis tables (resample_kernels.cu); vb200_shutdown */

@@ -118,6 +118,43 @@ def test_declined_streams(vbl):
             pass
 
 
+def test_self_synchronising_decode_host_twin(vbl):
+    """Scans without restart markers decoded by subsequences (csrc/jpeg.cu: blind starts, passes from the left
+    neighbour's end state until nobody decodes again, prefix sum of block counts, write pass, DC scan): the same pixels
+    as libjpeg-turbo for every subsequence size that lets the passes settle, and a loud failure when they are cut short."""
+    import ctypes as C
+    L = vbl.lib()
+    PI = C.POINTER(C.c_int)
+    L.vb200_debug_jpeg_decode_sync.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, PI, PI, PI, PI]
+
+    def dec(d, shrink, sub, passes):
+        w, h, b, used = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        vbl._check(L.vb200_debug_jpeg_decode_sync(d, len(d), shrink, sub, passes, None, 0, C.byref(w), C.byref(h), C.byref(b), C.byref(used)))
+        out = np.zeros((h.value, w.value, b.value), np.uint8)
+        vbl._check(L.vb200_debug_jpeg_decode_sync(d, len(d), shrink, sub, passes, out.ctypes.data_as(C.c_void_p), w.value * b.value,
+                                                  C.byref(w), C.byref(h), C.byref(b), C.byref(used)))
+        return out, used.value
+
+    worst = 0
+    for (h, w) in ((256, 320), (203, 301), (64, 64)):
+        a = synth(h, w, seed=h)
+        for sub in (2, 0):
+            for q in (95, 75, 30):
+                d = encode(a, q, sub, **({"optimize": True} if q == 75 else {}))
+                for sb in (128, 256, 1024, 1 << 20):
+                    got, used = dec(d, 2, sb, 4096)
+                    assert np.array_equal(got, turbo_decode(d, 2)), (h, w, sub, q, sb)
+                    worst = max(worst, used)
+                    assert sb < (1 << 20) or used == 1
+    assert worst >= 3          # the passes really were needed
+    g = encode(synth(150, 203, seed=3, grey=True), 90)
+    assert np.array_equal(dec(g, 1, 256, 4096)[0], turbo_decode(g, 1))
+    # cut short: an error, never wrong pixels
+    d = encode(synth(256, 320, seed=9), 100, 0)
+    with pytest.raises(vbl.Error, match="converge|corrupt"):
+        dec(d, 2, 128, 3)
+
+
 def test_jpegshrink_rule(vbl):
     """thumbnail.c:489-517: shrink >= 16 -> 8, >= 8 -> 4, >= 4 -> 2, else 1, on the common shrink"""
     assert vbl.thumbnail_jpegshrink(4096, 4096, 512) == 4
@@ -154,6 +191,36 @@ def test_gpu_batch_decode_matches_libjpeg_turbo(vbl):
                     assert got.shape == want.shape and np.array_equal(got, want), (h, w, sub, kw, shrink)
     g = [encode(synth(150, 203, seed=i, grey=True), 90) for i in range(2)]
     assert np.array_equal(vb.jpeg_decode_batch(g, 2), np.stack([turbo_decode(s, 2) for s in g]))
+
+
+@pytest.mark.gpu
+def test_gpu_self_synchronising_decode(vbl):
+    """streams without restart markers through the subsequence kernels: forced onto small images with small
+    subsequences (VB200_JPEG_SYNC), and by default on frames big enough to take that path by themselves"""
+    import os
+    import libvips_b200 as vb
+    vb.init(0)
+    for sb in ("128", "512"):
+        os.environ["VB200_JPEG_SYNC"] = sb
+        try:
+            for (h, w) in ((256, 320), (203, 301)):
+                for sub in (2, 0):
+                    streams = [encode(synth(h, w, seed=i), (95, 75, 40)[i], sub, **({"optimize": True} if i == 1 else {})) for i in range(3)]
+                    streams.append(encode(synth(h, w, seed=7), 85, sub, restart_marker_rows=1))     # a DRI frame in the same batch
+                    for shrink in (4, 2):
+                        got = vb.jpeg_decode_batch(streams, shrink)
+                        want = np.stack([turbo_decode(s, shrink) for s in streams])
+                        assert np.array_equal(got, want), (sb, h, w, sub, shrink)
+        finally:
+            del os.environ["VB200_JPEG_SYNC"]
+    big = [encode(synth(2048, 2048, seed=i), (92, 80)[i], 2) for i in range(2)]
+    assert all(len(s) > 64 * 1024 for s in big)
+    assert np.array_equal(vb.jpeg_decode_batch(big, 4), np.stack([turbo_decode(s, 4) for s in big]))
+    os.environ["VB200_JPEG_SYNC"] = "0"         # one thread per frame: the same pixels
+    try:
+        assert np.array_equal(vb.jpeg_decode_batch(big[:1], 4), np.stack([turbo_decode(s, 4) for s in big[:1]]))
+    finally:
+        del os.environ["VB200_JPEG_SYNC"]
 
 
 @pytest.mark.gpu
