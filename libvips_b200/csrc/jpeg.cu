@@ -634,10 +634,11 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
  *               change since its last decode just copies its record (so converged stretches cost nothing), and a pass
  *               in which nobody decodes ends the iteration.  Subsequence 0 starts from the true state, so truth advances
  *               at least one subsequence per pass; every blind decode that fell into step lets it jump.  A JPEG decoder
- *               falls into step fully only when bit position, zig-zag index AND block-in-MCU agree -- the last is a random
- *               walk (Y0..Y3 share tables, so do Cb and Cr) -- so about half the subsequences of a photograph at q85 end
- *               true after pass 0 and 5-10 passes settle it (measured, tests/test_jpeg.py); at q100, where blocks never
- *               end early, hardly any do and the passes run into the dozens: correct, but no faster than one thread;
+ *               is in step only when bit position, zig-zag index AND block-in-MCU agree (the last is a random walk:
+ *               Y0..Y3 share tables, so do Cb and Cr), which takes a few KB of stream; a blind decoder that meets an
+ *               impossible code carries on one bit later rather than giving up.  Measured on the CPU twin
+ *               (tests/test_jpeg.py): with 2 KB subsequences photographs at q50-95 settle in 2-3 passes, noise at q95
+ *               in 5, q100 (blocks never end early, nothing to re-align on) in 5-14;
  *   scan        an exclusive prefix sum of the block counts gives every subsequence the index of its first block;
  *   write       the same decode once more, now storing coefficients (DC as the DIFFERENCE, the predictor is not known
  *               mid-stream), and checking that start and end states are the recorded ones: any mismatch fails the frame;
@@ -656,9 +657,8 @@ sync_same(const SyncState &a, const SyncState &b)
 }
 
 /* Decode from state st while the next symbol starts before limit_bit.  WRITE: store coefficients of block blk_index
- * onwards (never past total_blocks); else only count.  *nblocks = blocks completed.  Returns 0, or -1 on a code that
- * is not in the table / a run past the block (a blind start that has not synchronised yet, or corrupt data): st is
- * then (limit_bit, 0, 0).
+ * onwards (never past total_blocks); else only count.  *nblocks = blocks completed.  Returns 0, or -1 when it met a code
+ * that is not in the table / a run past the block (a blind start that was not in step yet, or corrupt data).
  */
 template <bool WRITE>
 HD int
@@ -682,49 +682,65 @@ decode_span(const McuLayout &M, const HuffDev *huff, const unsigned char *zz, co
 	int rc = 0;
 	while (b.bit < limit_bit && (!WRITE || blk_index + done < total_blocks)) {
 		br_fill(b);
+		bool bad = false;
 		const int f = k > 0 ? ac->fast[br_peek(b, kLook)] : 0;
 		if (f) {
 			k += (f >> 4) & 15;
-			if (k > 63) {
-				rc = -1;
-				break;
-			}
 			br_skip(b, f & 15);
-			if (WRITE)
-				blk[zz[k]] = (short) (f >> 8);
-			k++;
+			if (k > 63)
+				bad = true;
+			else {
+				if (WRITE)
+					blk[zz[k]] = (short) (f >> 8);
+				k++;
+			}
 		}
 		else if (k == 0) {
 			const int sym = huff_decode(b, dc);
 			if (sym < 0 || sym > 11) {
-				rc = -1;
-				break;
+				if (sym < 0)
+					br_skip(b, 1); /* no code matched, nothing was consumed: move on */
+				bad = true;
 			}
-			const int diff = br_receive_extend(b, sym);
-			if (WRITE)
-				blk[0] = (short) diff; /* the DC scan adds the predictor */
-			k = 1;
+			else {
+				const int diff = br_receive_extend(b, sym);
+				if (WRITE)
+					blk[0] = (short) diff; /* the DC scan adds the predictor */
+				k = 1;
+			}
 		}
 		else {
 			const int sym = huff_decode(b, ac);
 			if (sym < 0) {
-				rc = -1;
-				break;
+				br_skip(b, 1);
+				bad = true;
 			}
-			const int r = sym >> 4, sz = sym & 15;
-			if (sz == 0)
-				k = r == 15 ? k + 16 : 64;
 			else {
-				k += r;
-				const int v = br_receive_extend(b, sz);
-				if (k > 63) {
-					rc = -1;
-					break;
+				const int r = sym >> 4, sz = sym & 15;
+				if (sz == 0)
+					k = r == 15 ? k + 16 : 64;
+				else {
+					k += r;
+					const int v = br_receive_extend(b, sz);
+					if (k > 63)
+						bad = true;
+					else {
+						if (WRITE)
+							blk[zz[k]] = (short) v;
+						k++;
+					}
 				}
-				if (WRITE)
-					blk[zz[k]] = (short) v;
-				k++;
 			}
+		}
+		if (bad) {
+			/* a blind start that is not in step yet (or corrupt data, in the write pass): the write pass gives up, a
+			 * synchronisation pass carries on from here as if a block began -- it may still fall into step
+			 */
+			rc = -1;
+			if (WRITE)
+				break;
+			k = 0;
+			continue;
 		}
 		if (k >= 64) {
 			k = 0;
@@ -743,16 +759,10 @@ decode_span(const McuLayout &M, const HuffDev *huff, const unsigned char *zz, co
 		}
 	}
 	*nblocks = done;
-	if (rc) {
-		st.bit = limit_bit;
-		st.k = 0;
-		st.bi = 0;
-		return -1;
-	}
 	st.bit = b.bit;
 	st.k = (unsigned short) k;
 	st.bi = (unsigned short) bi;
-	return 0;
+	return rc;
 }
 
 /* one synchronisation pass of one subsequence (pass 0: blind start); true when it had to decode (its start state was
@@ -1644,7 +1654,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	/* frames with one restart interval (no DRI) and a scan worth splitting decode by self-synchronising subsequences;
 	 * VB200_JPEG_SYNC=0: never (one thread per frame), =N: subsequences of N bytes, any size of scan
 	 */
-	unsigned sub_bytes = 1024;
+	unsigned sub_bytes = 2048;
 	size_t sync_min_bytes = 64 * 1024;
 	if (const char *e = getenv("VB200_JPEG_SYNC")) {
 		sub_bytes = (unsigned) std::max(0, atoi(e));
