@@ -16,14 +16,15 @@
  * Parity is pinned against libjpeg-turbo itself as shipped inside this image's Pillow wheel (tests/test_jpeg.py:
  * PIL's draft mode = scale_denom; bit for bit).
  *
- * Scope: every case in which libjpeg's upsampler is the identity -- greyscale, 4:4:4 at any shrink, 4:2:0 /
- * 4:2:2 / 4:4:0 at the shrinks where the chroma IDCT absorbs the subsampling (e.g. 4:2:0 at 2, 4, 8: what a
- * thumbnail asks for).  Progressive, arithmetic, 12-bit, CMYK / RGB-coded files and full-size 4:2:0 (fancy
- * upsampling) return -1: the host keeps its loader for those.
+ * Scope: every case in which libjpeg's upsampler is the identity -- greyscale and 4:4:4 at any shrink, 4:2:0 at the
+ * shrinks where the chroma IDCT absorbs the subsampling (2, 4, 8: what a thumbnail asks for).  Progressive,
+ * arithmetic, 12-bit, CMYK / RGB-coded files, 4:2:2 / 4:4:0 and full-size 4:2:0 (fancy upsampling) return -1: the host
+ * keeps its loader for those.
  *
- * Device pipeline per batch (no host decode, the compressed bytes are all that crosses PCIe):
- *   jpeg_huffman_kernel   one thread per restart interval (or per frame when the file has none): bit reader with
- *                         inline FF00 unstuffing, 9-bit lookahead tables, DC prediction, coefficients as int16
+ * Device pipeline per batch (no host decode; the compressed bytes are all that crosses PCIe, unstuffed by the host
+ * workers while they copy them into pinned staging):
+ *   jpeg_huffman_kernel   streams with restart markers: one thread per restart interval
+ *   jpeg_sync_*_kernel    streams without: self-synchronising subsequences (see below), then a DC prefix sum
  *   jpeg_idct_kernel      one thread per MCU: dequantise + scaled IDCT of its blocks, YCbCr -> RGB, store
  * The per-block / per-pixel code is __host__ __device__: vb200_debug_jpeg_decode runs the same code on the CPU so
  * that the CPU test-suite pins it against libjpeg-turbo without a GPU.
@@ -1635,7 +1636,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		}
 	if (!P.fork)
 		VB200_CUDA(domain, cudaEventCreateWithFlags(&P.fork, cudaEventDisableTiming));
-	const bool timing = getenv("VB200_JPEG_TIMING") != nullptr;
+	const bool timing = getenv("VB200_JPEG_TIMING") && getenv("VB200_JPEG_TIMING")[0] == '1'; /* 2 = host-side trace only */
 	P.huff_ms = P.idct_ms = 0;
 
 	/* chunks: frames with many restart intervals fill the machine with few frames; a stream without them is one
@@ -1691,9 +1692,26 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	int rc = 0;
 	if (cudaMemsetAsync(status, 0, (size_t) n * sizeof(int), s) != cudaSuccess || cudaEventRecord(P.fork, s) != cudaSuccess)
 		rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode setup");
-	for (int c0 = 0, k = 0; c0 < n && !rc; c0 += chunk, k++) {
+	/* staging of a chunk: layout, the slot's pinned block, the unstuffing copies.  Runs on a helper thread for chunk
+	 * k + 1 while the calling thread queues (and, on the subsequence path, waits on) chunk k.
+	 */
+	struct Staged {
+		int rc = 0, c0 = 0, cn = 0, max_intervals = 0, max_mcus = 0;
+		unsigned max_subs = 0;
+		size_t total = 0, off_h = 0, off_o = 0, off_b = 0, coef_total = 0, sync_total = 0;
+		std::string err;
+	};
+	int device = 0;
+	cudaGetDevice(&device);
+	auto stage_chunk = [&](int k, bool helper) {
+		Staged R;
+		if (helper)
+			cudaSetDevice(device);
+		const int c0 = k * chunk;
 		const int cn = std::min(chunk, n - c0);
 		JpegSlot &sl = P.slot[k % kJpegSlots];
+		R.c0 = c0;
+		R.cn = cn;
 		/* layout of the chunk's block */
 		std::vector<size_t> data_off(cn), int_off(cn), coef_off(cn);
 		std::vector<unsigned> sync_off(cn, 0), sync_cap(cn, 0);
@@ -1725,8 +1743,9 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			fprintf(stderr, "[jpeg] chunk %d begins at %.2f ms\n", k, since());
 		if (sl.busy) {
 			if (cudaEventSynchronize(sl.done) != cudaSuccess) {
-				rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
-				break;
+				R.rc = -1;
+				R.err = std::string("jpeg decode: ") + cudaGetErrorString(cudaGetLastError());
+				return R;
 			}
 			sl.busy = false;
 		}
@@ -1737,8 +1756,9 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			sl.cap = 0;
 			const size_t want = total + total / 4;
 			if (cudaMallocHost(&sl.pinned, want) != cudaSuccess) {
-				rc = cuda_fail(domain, cudaGetLastError(), "cudaMallocHost (jpeg staging)");
-				break;
+				R.rc = -1;
+				R.err = std::string("cudaMallocHost (jpeg staging): ") + cudaGetErrorString(cudaGetLastError());
+				return R;
 			}
 			sl.cap = want;
 		}
@@ -1769,12 +1789,51 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			memset(dst + clean, 0, (((fp.src_len + 15) & ~(size_t) 15) + 16) - clean); /* the reader's look-ahead past the end */
 		});
 		if (bad_frame.load() >= 0) {
-			error(domain, "frame %d: restart markers do not match the restart interval", bad_frame.load());
-			rc = -1;
-			break;
+			R.rc = -1;
+			R.err = "frame " + std::to_string(bad_frame.load()) + ": restart markers do not match the restart interval";
+			return R;
 		}
 		if (trace)
 			fprintf(stderr, "[jpeg] chunk %d (%d frames) staged at %.2f ms\n", k, cn, since());
+		R.max_intervals = max_intervals;
+		R.max_mcus = max_mcus;
+		R.max_subs = max_subs;
+		R.total = total;
+		R.off_h = off_h;
+		R.off_o = off_o;
+		R.off_b = off_b;
+		R.coef_total = coef_total;
+		R.sync_total = sync_total;
+		return R;
+	};
+
+	const int n_chunks = (n + chunk - 1) / chunk;
+	Staged cur = stage_chunk(0, false);
+	for (int k = 0; k < n_chunks && !rc; k++) {
+		if (cur.rc) {
+			error(domain, "%s", cur.err.c_str());
+			rc = -1;
+			break;
+		}
+		/* the next chunk stages while this one is queued and decoded */
+		Staged next;
+		std::thread helper;
+		if (k + 1 < n_chunks)
+			helper = std::thread([&, k] { next = stage_chunk(k + 1, true); });
+		struct Joiner {
+			std::thread &t;
+			~Joiner()
+			{
+				if (t.joinable())
+					t.join();
+			}
+		} joiner{helper};
+		const int c0 = cur.c0, cn = cur.cn, max_intervals = cur.max_intervals, max_mcus = cur.max_mcus;
+		const unsigned max_subs = cur.max_subs;
+		const size_t total = cur.total, off_h = cur.off_h, off_o = cur.off_o, off_b = cur.off_b, coef_total = cur.coef_total,
+					 sync_total = cur.sync_total;
+		JpegSlot &sl = P.slot[k % kJpegSlots];
+		char *hst = (char *) sl.pinned;
 		cudaStream_t st = sl.stream;
 		if (k < kJpegSlots && cudaStreamWaitEvent(st, P.fork, 0) != cudaSuccess) {
 			rc = cuda_fail(domain, cudaGetLastError(), "jpeg decode");
@@ -1898,6 +1957,9 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 				cudaEventDestroy(e);
 		if (!rc && cudaEventRecord(sl.done, st) == cudaSuccess)
 			sl.busy = true;
+		if (helper.joinable())
+			helper.join();
+		cur = next;
 	}
 	if (trace)
 		fprintf(stderr, "[jpeg] all chunks queued at %.2f ms\n", since());
