@@ -1251,11 +1251,11 @@ jpeg_sync_write_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *_
 }
 
 /* DC differences -> DC values: blockIdx.x = component, blockIdx.y = frame; a contiguous run of blocks per thread */
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 jpeg_dc_scan_kernel(const JpegFrameDev *__restrict__ frames, short *__restrict__ coef)
 {
 	__shared__ McuLayout M;
-	__shared__ int s_part[256];
+	__shared__ int s_part[1024];
 	const JpegFrameDev &F = frames[blockIdx.y];
 	const int c = blockIdx.x;
 	if (!F.sync || c >= F.ncomp)
@@ -1524,7 +1524,7 @@ host_workers()
 	return n;
 }
 
-/* the pump's slots: pinned staging + a stream each, kept per host thread (grow-only) */
+/* the pump's slots: pinned staging, device twins and a stream each (grow-only; vb200_shutdown releases them) */
 struct JpegSlot {
 	void *pinned = nullptr;
 	size_t cap = 0;
@@ -1562,9 +1562,31 @@ struct JpegPump {
 			cudaEventDestroy(fork);
 	}
 };
-thread_local JpegPump g_pump;
+/* ONE pump per process: its slots hold gigabytes (coefficient pools), and a batch call fills the machine by itself, so
+ * concurrent callers (libvips' worker threads) take turns rather than each owning a set
+ */
+JpegPump g_pump;
+std::mutex g_pump_lock;
 
 } // namespace
+
+void
+jpeg_pump_release()
+{
+	std::lock_guard<std::mutex> lock(g_pump_lock);
+	for (auto &sl : g_pump.slot) {
+		if (sl.pinned)
+			cudaFreeHost(sl.pinned);
+		if (sl.dev)
+			cudaFree(sl.dev);
+		if (sl.coef)
+			cudaFree(sl.coef);
+		if (sl.sync)
+			cudaFree(sl.sync);
+		sl.pinned = sl.dev = sl.coef = sl.sync = nullptr;
+		sl.cap = sl.dev_cap = sl.coef_cap = sl.sync_cap = 0;
+	}
+}
 
 static void
 jpeg_last_kernel_times(float *huff_ms, float *idct_ms)
@@ -1628,6 +1650,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	static std::once_flag zz_once;
 	std::call_once(zz_once, [] { cudaMemcpyToSymbol(d_zigzag, kZigzag, 64); });
 
+	std::lock_guard<std::mutex> pump_lock(g_pump_lock);
 	JpegPump &P = g_pump;
 	for (auto &sl : P.slot)
 		if (!sl.stream) {
@@ -1911,7 +1934,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 				/* not settled: the write pass finds the inconsistency and fails the frame */
 				jpeg_sync_scan_kernel<<<cn, 1024, 0, st>>>(dF, sub_bytes, Na, Bs);
 				jpeg_sync_write_kernel<<<sg, kSyncThreads, 0, st>>>(dF, dH, dB, sub_bytes, Ea, Bs, Su, (short *) coef, status + c0);
-				jpeg_dc_scan_kernel<<<dim3(kMaxComp, cn), 256, 0, st>>>(dF, (short *) coef);
+				jpeg_dc_scan_kernel<<<dim3(kMaxComp, cn), 1024, 0, st>>>(dF, (short *) coef);
 				cudaError_t es = cudaGetLastError();
 				if (es != cudaSuccess) {
 					rc = cuda_fail(domain, es, "jpeg_sync kernels launch");

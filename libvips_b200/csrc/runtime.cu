@@ -387,6 +387,7 @@ vb200_shutdown(void)
 	if (g_device.load() >= 0) {
 		cudaDeviceSynchronize();
 		resample_cache_clear();
+		jpeg_pump_release();
 	}
 	g_device.store(-1);
 }

@@ -161,6 +161,7 @@ int host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink
 	int *out_h, int *bands, unsigned sub_bytes, int max_passes, int *passes_used);
 /* min(hshrink, vshrink) of vips_thumbnail_calculate_shrink, thumbnail.c:413-487 */
 double thumbnail_common_shrink(int w, int h, int tw, int th, int size);
+void jpeg_pump_release(); /* the JPEG pump's pinned / device slots (jpeg.cu); vb200_shutdown */
 void resample_cache_clear(); /* cached axis tables (resample_kernels.cu); vb200_shutdown */
 int launch_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *out, size_t out_bpl, int ne,
 	int out_rows, int fmt, const AxisTable &t, cudaStream_t s);
