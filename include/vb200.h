@@ -389,9 +389,9 @@ int vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_s
  * bytes are all that crosses PCIe.  libjpeg(-turbo) itself is a third-party dependency outside the reference
  * tree; its algorithm for the reference's configuration (JDCT_ISLOW, 8-bit Huffman baseline / extended
  * sequential) is restated in csrc/jpeg.cu and pinned bit for bit to the libjpeg-turbo inside this image's Pillow
- * (tests/test_jpeg.py).  Decoded: greyscale and 4:4:4 at shrink 1 / 2 / 4 / 8, and 4:2:0 at shrink 2 / 4 / 8 (what
- * vips_thumbnail asks for): the cases in which libjpeg's upsampler is the identity.  Progressive, arithmetic, 12-bit,
- * CMYK / RGB-coded streams, 4:2:2 / 4:4:0 and full-size 4:2:0 return -1 (host loader).  Streams with restart markers
+ * (tests/test_jpeg.py).  Decoded: greyscale, 4:4:4, 4:2:2 and 4:2:0 at shrink 1 / 2 / 4 / 8 (where libjpeg's upsampler has
+ * work left -- 4:2:0 at full size, 4:2:2 -- its h2v2 / h2v1 "fancy" triangle filters, jdsample.c).  Progressive,
+ * arithmetic, 12-bit, CMYK / RGB-coded and 4:4:0 / 4:1:1 streams return -1 (host loader).  Streams with restart markers
  * decode one interval per GPU thread, streams without them by self-synchronising subsequences.
  *
  * vb200_jpeg_decode_batch: n streams of ONE output geometry -> out[n][height][width][bands] uchar (bands 1 or 3),

@@ -16,16 +16,18 @@
  * Parity is pinned against libjpeg-turbo itself as shipped inside this image's Pillow wheel (tests/test_jpeg.py:
  * PIL's draft mode = scale_denom; bit for bit).
  *
- * Scope: every case in which libjpeg's upsampler is the identity -- greyscale and 4:4:4 at any shrink, 4:2:0 at the
- * shrinks where the chroma IDCT absorbs the subsampling (2, 4, 8: what a thumbnail asks for).  Progressive,
- * arithmetic, 12-bit, CMYK / RGB-coded files, 4:2:2 / 4:4:0 and full-size 4:2:0 (fancy upsampling) return -1: the host
- * keeps its loader for those.
+ * Scope: 8-bit Huffman baseline / extended-sequential streams, greyscale or YCbCr at 4:4:4, 4:2:2 or 4:2:0, shrink 1 / 2 /
+ * 4 / 8.  Where jdmaster.c's DCT scaling leaves the upsampler nothing to do (greyscale, 4:4:4, 4:2:0 at 2 / 4 / 8: what a
+ * thumbnail asks for) one kernel reconstructs an MCU to RGB; otherwise (4:2:0 at full size, 4:2:2) components go to planes
+ * and jdsample.c's h2v2 / h2v1 "fancy" upsamplers run per output pixel.  Progressive, arithmetic, 12-bit, CMYK /
+ * RGB-coded and 4:4:0 / 4:1:1 files return -1: the host keeps its loader for those.
  *
  * Device pipeline per batch (no host decode; the compressed bytes are all that crosses PCIe, unstuffed by the host
  * workers while they copy them into pinned staging):
  *   jpeg_huffman_kernel   streams with restart markers: one thread per restart interval
  *   jpeg_sync_*_kernel    streams without: self-synchronising subsequences (see below), then a DC prefix sum
  *   jpeg_idct_kernel      one thread per MCU: dequantise + scaled IDCT of its blocks, YCbCr -> RGB, store
+ *   jpeg_idct_planes_kernel + jpeg_upsample_kernel   the same through component planes when the upsampler has work
  * The per-block / per-pixel code is __host__ __device__: vb200_debug_jpeg_decode runs the same code on the CPU so
  * that the CPU test-suite pins it against libjpeg-turbo without a GPU.
  */
@@ -104,6 +106,13 @@ struct JpegFrameDev {
 	int out_w, out_h, tile_w, tile_h; /* cropped output, and the MCU's footprint in output pixels */
 	int blocks_per_mcu;				  /* T.81 A.2.3: component by component, rows of blocks, left to right */
 	unsigned char blk_comp[12], blk_dx[12], blk_dy[12];
+	/* frames that need libjpeg's upsampler (4:2:0 at full size, 4:2:2): components are reconstructed into planes first */
+	int planar;								 /* 1: jpeg_idct_planes_kernel + jpeg_upsample_kernel instead of jpeg_idct_kernel */
+	int fancy;								 /* jinit_upsampler: do_fancy_upsampling && min_DCT_scaled_size > 1 */
+	int ux[kMaxComp], uy[kMaxComp];			 /* upsampling factors 1 / 2 */
+	int pw[kMaxComp], ph[kMaxComp];			 /* plane size in samples (whole blocks) */
+	int dw[kMaxComp], dh[kMaxComp];			 /* the component's true size: jdmaster.c downsampled_width / height */
+	size_t plane_off[kMaxComp];				 /* in the chunk's plane pool (bytes) */
 	/* the self-synchronising path (frames with too few restart intervals to fill the machine) */
 	int sync;			 /* 1: decode by subsequences */
 	unsigned clean_len;	 /* bytes of the unstuffed scan (set while staging) */
@@ -315,7 +324,7 @@ parse_jpeg(const char *domain, const unsigned char *d, size_t len, JpegHeader *H
 
 /* the subset the device path decodes, and the scaled DCT size of every component (jdmaster.c) */
 int
-plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp])
+plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp], int up[kMaxComp][2])
 {
 	if (H.progressive || H.arithmetic) {
 		error(domain, "%s JPEG is not supported on the device path", H.progressive ? "progressive" : "arithmetic-coded");
@@ -363,12 +372,16 @@ plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp
 		while (ssize < 8 && (H.max_h * m) % (k.h * ssize * 2) == 0 && (H.max_v * m) % (k.v * ssize * 2) == 0)
 			ssize *= 2;
 		dct[c] = ssize;
-		/* the upsampler must be the identity: the component's samples per MCU already cover the MCU's output pixels */
-		if (k.h * ssize != H.max_h * m || k.v * ssize != H.max_v * m) {
-			error(domain, "JPEG with %dx%d chroma subsampling needs libjpeg's upsampler at shrink %d: not supported on the device path",
-				H.max_h / k.h, H.max_v / k.v, shrink);
+		/* what is left for the upsampler (jdsample.c): nothing, or a doubling horizontally (h2v1) / both ways (h2v2) */
+		const int ux = (H.max_h * m) / (k.h * ssize), uy = (H.max_v * m) / (k.v * ssize);
+		if ((H.max_h * m) % (k.h * ssize) || (H.max_v * m) % (k.v * ssize) || !((ux == 1 && uy == 1) || (ux == 2 && uy == 1) || (ux == 2 && uy == 2)) ||
+			(c == 0 && (ux != 1 || uy != 1))) {
+			error(domain, "JPEG with %dx%d chroma subsampling at shrink %d needs an upsampler that is not on the device path", H.max_h / k.h,
+				H.max_v / k.v, shrink);
 			return -1;
 		}
+		up[c][0] = ux;
+		up[c][1] = uy;
 	}
 	return 0;
 }
@@ -1139,6 +1152,76 @@ reconstruct_mcu(const JpegFrameDev &F, const unsigned short (*qt)[64], const sho
 	}
 }
 
+/* ---- the planar path: frames in which libjpeg's upsampler has work to do (jdsample.c, do_fancy_upsampling = TRUE) */
+
+/* one block of one component into its plane */
+HD void
+reconstruct_block(const JpegFrameDev &F, const unsigned short (*qt)[64], const short *coef_pool, int c, int bx, int by, unsigned char *planes)
+{
+	const short *blk = coef_pool + F.coef_off[c] + ((size_t) by * F.blocks_x[c] + (size_t) bx) * 64;
+	short cf[64];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+	for (int i = 0; i < 8; i++)
+		((uint4 *) cf)[i] = __ldg((const uint4 *) blk + i);
+#else
+	memcpy(cf, blk, sizeof(cf));
+#endif
+	unsigned char out[64];
+	const int sz = F.dct[c];
+	idct_scaled(sz, cf, qt[c], out, sz);
+	unsigned char *dst = planes + F.plane_off[c] + (size_t) by * sz * F.pw[c] + (size_t) bx * sz;
+	for (int y = 0; y < sz; y++)
+		for (int x = 0; x < sz; x++)
+			dst[(size_t) y * F.pw[c] + x] = out[y * sz + x];
+}
+
+/* the sample of component c at output position (x, y): jdsample.c's fullsize / h2v1_fancy / h2v2_fancy upsamplers
+ * (3/4 nearer + 1/4 further, the rounding constants alternating 1, 2 / 8, 7), and their plain replication when the
+ * component is at most 2 samples wide or the scale is 1/8 (jinit_upsampler: fancy only if downsampled_width > 2 and
+ * min_DCT_scaled_size > 1)
+ */
+HD int
+upsampled_sample(const JpegFrameDev &F, const unsigned char *planes, int c, int x, int y)
+{
+	const unsigned char *pl = planes + F.plane_off[c];
+	const int pw = F.pw[c];
+	if (F.ux[c] == 1)
+		return pl[(size_t) y * pw + x];
+	const int dw = F.dw[c], ci = x >> 1;
+	if (F.uy[c] == 1) {
+		const unsigned char *row = pl + (size_t) y * pw;
+		if (dw <= 2 || !F.fancy)
+			return row[ci];
+		const int v = row[ci];
+		if (!(x & 1))
+			return ci == 0 ? v : (3 * v + row[ci - 1] + 1) >> 2;
+		return ci == dw - 1 ? v : (3 * v + row[ci + 1] + 2) >> 2;
+	}
+	const int dh = F.dh[c], ri = y >> 1;
+	if (dw <= 2 || !F.fancy)
+		return pl[(size_t) ri * pw + ci];
+	/* the nearer row and the further one (above for the upper output row of the pair, below for the lower), rows past
+	 * the component's true first / last replicated (jdmainct.c context rows)
+	 */
+	const int rf = (y & 1) ? (ri + 1 < dh ? ri + 1 : dh - 1) : (ri > 0 ? ri - 1 : 0);
+	const unsigned char *r0 = pl + (size_t) (ri < dh ? ri : dh - 1) * pw, *r1 = pl + (size_t) rf * pw;
+	const int cur = 3 * r0[ci] + r1[ci];
+	if (!(x & 1))
+		return ci == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + 3 * r0[ci - 1] + r1[ci - 1] + 8) >> 4;
+	return ci == dw - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + 3 * r0[ci + 1] + r1[ci + 1] + 7) >> 4;
+}
+
+HD void
+upsample_pixel(const JpegFrameDev &F, const unsigned char *planes, int x, int y, unsigned char *out, size_t out_bpl)
+{
+	const int Y = upsampled_sample(F, planes, 0, x, y);
+	if (F.ncomp == 3)
+		ycc_to_rgb(Y, upsampled_sample(F, planes, 1, x, y), upsampled_sample(F, planes, 2, x, y), out + (size_t) y * out_bpl + (size_t) x * 3);
+	else
+		out[(size_t) y * out_bpl + x] = (unsigned char) Y;
+}
+
 /* ------------------------------------------------------------------ kernels */
 
 /* One thread per restart interval of one frame; blockIdx.y = frame of the batch.  The block size is chosen by the host
@@ -1302,10 +1385,49 @@ jpeg_idct_kernel(const JpegFrameDev *__restrict__ frames, const short *__restric
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= F.mcus_x * F.mcus_y)
 		return;
+	if (F.planar)
+		return; /* jpeg_idct_planes_kernel + jpeg_upsample_kernel */
 	const int my = i / F.mcus_x, mx = i - my * F.mcus_x;
 	if (mx * F.tile_w >= F.out_w || my * F.tile_h >= F.out_h)
 		return;
 	reconstruct_mcu(F, s_qt, coef, mx, my, out + (size_t) blockIdx.y * out_frame_stride, out_bpl);
+}
+
+/* planar path, step 1: one thread per block of any component */
+__global__ void __launch_bounds__(128)
+jpeg_idct_planes_kernel(const JpegFrameDev *__restrict__ frames, const short *__restrict__ coef, unsigned char *__restrict__ planes)
+{
+	__shared__ unsigned short s_qt[kMaxComp][64];
+	const JpegFrameDev &F = frames[blockIdx.y];
+	if (!F.planar)
+		return;
+	for (int j = threadIdx.x; j < kMaxComp * 64; j += blockDim.x)
+		s_qt[j >> 6][j & 63] = F.qt[j >> 6][j & 63];
+	__syncthreads();
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int c = 0; c < F.ncomp; c++) {
+		const int nb = F.blocks_x[c] * F.blocks_y[c];
+		if (i < nb) {
+			const int by = i / F.blocks_x[c];
+			reconstruct_block(F, s_qt, coef, c, i - by * F.blocks_x[c], by, planes);
+			return;
+		}
+		i -= nb;
+	}
+}
+
+/* planar path, step 2: one thread per output pixel */
+__global__ void __launch_bounds__(256)
+jpeg_upsample_kernel(const JpegFrameDev *__restrict__ frames, const unsigned char *__restrict__ planes, unsigned char *__restrict__ out,
+	size_t out_bpl, size_t out_frame_stride)
+{
+	const JpegFrameDev &F = frames[blockIdx.z];
+	if (!F.planar)
+		return;
+	const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+	if (x >= F.out_w || y >= F.out_h)
+		return;
+	upsample_pixel(F, planes, x, y, out + (size_t) blockIdx.z * out_frame_stride, out_bpl);
 }
 
 /* ------------------------------------------------------------------ host: frame preparation and the pump */
@@ -1316,7 +1438,7 @@ struct FramePrep {
 	HuffDev huff[8];
 	std::vector<unsigned> offsets; /* n_intervals + 1, relative to the entropy-coded segment */
 	const unsigned char *src = nullptr;
-	size_t src_len = 0, coef_count = 0;
+	size_t src_len = 0, coef_count = 0, plane_bytes = 0;
 	int bands = 0;
 	std::string err;
 };
@@ -1345,7 +1467,8 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 		H.max_v = std::max(H.max_v, H.comp[c].v);
 	}
 	int dct[kMaxComp] = {8, 8, 8};
-	if (plan_frame(domain, H, shrink, dct))
+	int up[kMaxComp][2] = {{1, 1}, {1, 1}, {1, 1}};
+	if (plan_frame(domain, H, shrink, dct, up))
 		return -1;
 	JpegFrameDev &F = P->F;
 	memset(&F, 0, sizeof(F));
@@ -1378,6 +1501,22 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 		P->coef_count += (size_t) F.blocks_x[c] * F.blocks_y[c] * 64;
 		memcpy(F.qt[c], H.qt[H.comp[c].tq], sizeof(F.qt[c]));
 	}
+	F.planar = 0;
+	F.fancy = m > 1;
+	P->plane_bytes = 0;
+	for (int c = 0; c < H.ncomp; c++) {
+		F.ux[c] = up[c][0];
+		F.uy[c] = up[c][1];
+		F.planar |= up[c][0] != 1 || up[c][1] != 1;
+		F.pw[c] = F.blocks_x[c] * dct[c];
+		F.ph[c] = F.blocks_y[c] * dct[c];
+		F.dw[c] = (int) (((long long) H.width * H.comp[c].h * dct[c] + (long long) H.max_h * 8 - 1) / ((long long) H.max_h * 8));
+		F.dh[c] = (int) (((long long) H.height * H.comp[c].v * dct[c] + (long long) H.max_v * 8 - 1) / ((long long) H.max_v * 8));
+		F.plane_off[c] = P->plane_bytes;
+		P->plane_bytes += ((size_t) F.pw[c] * F.ph[c] + 15) & ~(size_t) 15;
+	}
+	if (!F.planar)
+		P->plane_bytes = 0;
 	F.blocks_per_mcu = 0;
 	for (int c = 0; c < H.ncomp; c++)
 		for (int by = 0; by < F.v[c]; by++)
@@ -1533,6 +1672,8 @@ struct JpegSlot {
 	size_t dev_cap = 0, coef_cap = 0;
 	void *sync = nullptr; /* subsequence records of the self-synchronising path */
 	size_t sync_cap = 0;
+	void *planes = nullptr; /* component planes of the frames that need the upsampler */
+	size_t planes_cap = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t done = nullptr;
 	bool busy = false;
@@ -1553,6 +1694,8 @@ struct JpegPump {
 				cudaFree(sl.coef);
 			if (sl.sync)
 				cudaFree(sl.sync);
+			if (sl.planes)
+				cudaFree(sl.planes);
 			if (sl.done)
 				cudaEventDestroy(sl.done);
 			if (sl.stream)
@@ -1583,8 +1726,10 @@ jpeg_pump_release()
 			cudaFree(sl.coef);
 		if (sl.sync)
 			cudaFree(sl.sync);
-		sl.pinned = sl.dev = sl.coef = sl.sync = nullptr;
-		sl.cap = sl.dev_cap = sl.coef_cap = sl.sync_cap = 0;
+		if (sl.planes)
+			cudaFree(sl.planes);
+		sl.pinned = sl.dev = sl.coef = sl.sync = sl.planes = nullptr;
+		sl.cap = sl.dev_cap = sl.coef_cap = sl.sync_cap = sl.planes_cap = 0;
 	}
 }
 
@@ -1721,7 +1866,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	struct Staged {
 		int rc = 0, c0 = 0, cn = 0, max_intervals = 0, max_mcus = 0;
 		unsigned max_subs = 0;
-		size_t total = 0, off_h = 0, off_o = 0, off_b = 0, coef_total = 0, sync_total = 0;
+		size_t total = 0, off_h = 0, off_o = 0, off_b = 0, coef_total = 0, sync_total = 0, plane_total = 0;
+		int max_blocks = 0;
 		std::string err;
 	};
 	int device = 0;
@@ -1738,7 +1884,9 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		/* layout of the chunk's block */
 		std::vector<size_t> data_off(cn), int_off(cn), coef_off(cn);
 		std::vector<unsigned> sync_off(cn, 0), sync_cap(cn, 0);
-		size_t bytes_total = 0, ints_total = 0, coef_total = 0, sync_total = 0;
+		std::vector<size_t> plane_off(cn, 0);
+		size_t bytes_total = 0, ints_total = 0, coef_total = 0, sync_total = 0, plane_total = 0;
+		int max_blocks = 0;
 		int max_intervals = 0, max_mcus = 0;
 		unsigned max_subs = 0;
 		for (int i = 0; i < cn; i++) {
@@ -1751,6 +1899,10 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			coef_total += fp.coef_count;
 			max_intervals = std::max(max_intervals, fp.F.n_intervals);
 			max_mcus = std::max(max_mcus, fp.F.mcus_x * fp.F.mcus_y);
+			plane_off[i] = plane_total;
+			plane_total += fp.plane_bytes;
+			if (fp.F.planar)
+				max_blocks = std::max(max_blocks, fp.F.mcus_x * fp.F.mcus_y * fp.F.blocks_per_mcu);
 			if (fp.F.n_intervals == 1 && sub_bytes > 0 && fp.src_len >= sync_min_bytes && fp.src_len / sub_bytes >= 8) {
 				sync_off[i] = (unsigned) sync_total;
 				sync_cap[i] = (unsigned) ((fp.src_len + sub_bytes - 1) / sub_bytes + 1);
@@ -1807,6 +1959,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			F.sync = sync_cap[i] > 0;
 			F.sync_off = sync_off[i];
 			F.sync_cap = sync_cap[i];
+			for (int c = 0; c < F.ncomp; c++)
+				F.plane_off[c] += plane_off[i];
 			memcpy(hst + (size_t) i * sizeof(JpegFrameDev), &F, sizeof(F));
 			memcpy(hst + off_h + (size_t) i * 8 * sizeof(HuffDev), fp.huff, 8 * sizeof(HuffDev));
 			memset(dst + clean, 0, (((fp.src_len + 15) & ~(size_t) 15) + 16) - clean); /* the reader's look-ahead past the end */
@@ -1827,6 +1981,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		R.off_b = off_b;
 		R.coef_total = coef_total;
 		R.sync_total = sync_total;
+		R.plane_total = plane_total;
+		R.max_blocks = max_blocks;
 		return R;
 	};
 
@@ -1854,7 +2010,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		const int c0 = cur.c0, cn = cur.cn, max_intervals = cur.max_intervals, max_mcus = cur.max_mcus;
 		const unsigned max_subs = cur.max_subs;
 		const size_t total = cur.total, off_h = cur.off_h, off_o = cur.off_o, off_b = cur.off_b, coef_total = cur.coef_total,
-					 sync_total = cur.sync_total;
+					 sync_total = cur.sync_total, plane_total = cur.plane_total;
+		const int max_blocks = cur.max_blocks;
 		JpegSlot &sl = P.slot[k % kJpegSlots];
 		char *hst = (char *) sl.pinned;
 		cudaStream_t st = sl.stream;
@@ -1879,7 +2036,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		/* per subsequence: two (state, count) records, the start state last decoded from, the first block's index */
 		const size_t sync_rec = 2 * sizeof(SyncState) + 2 * sizeof(unsigned) + sizeof(SyncState) + sizeof(unsigned);
 		if (!grow(&sl.dev, &sl.dev_cap, total) || !grow(&sl.coef, &sl.coef_cap, coef_total * sizeof(short)) ||
-			(sync_total && !grow(&sl.sync, &sl.sync_cap, sync_total * sync_rec + 256))) {
+			(sync_total && !grow(&sl.sync, &sl.sync_cap, sync_total * sync_rec + 256)) ||
+			(plane_total && !grow(&sl.planes, &sl.planes_cap, plane_total))) {
 			rc = -1;
 			break;
 		}
@@ -1965,6 +2123,18 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 				break;
 			}
 			count_launch();
+			if (plane_total) {
+				jpeg_idct_planes_kernel<<<dim3((max_blocks + 127) / 128, cn), 128, 0, st>>>(dF, (const short *) coef, (unsigned char *) sl.planes);
+				jpeg_upsample_kernel<<<dim3((W + 31) / 32, (Hh + 7) / 8, cn), 256, 0, st>>>(dF, (const unsigned char *) sl.planes,
+					(unsigned char *) out + (size_t) c0 * out_frame_stride, out_bpl, out_frame_stride);
+				e = cudaGetLastError();
+				if (e != cudaSuccess) {
+					rc = cuda_fail(domain, e, "jpeg planar kernels launch");
+					break;
+				}
+				count_launch();
+				count_launch();
+			}
 			if (timing) {
 				cudaEventRecord(ev[2], st);
 				cudaEventSynchronize(ev[2]);
@@ -2093,6 +2263,17 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 				error(domain, "corrupt JPEG data: bad Huffman code");
 				return -1;
 			}
+	if (F.planar) {
+		std::vector<unsigned char> planes(P.plane_bytes);
+		for (int c = 0; c < F.ncomp; c++)
+			for (int by = 0; by < F.blocks_y[c]; by++)
+				for (int bx = 0; bx < F.blocks_x[c]; bx++)
+					reconstruct_block(F, F.qt, coef.data(), c, bx, by, planes.data());
+		for (int y = 0; y < F.out_h; y++)
+			for (int x = 0; x < F.out_w; x++)
+				upsample_pixel(F, planes.data(), x, y, out, out_bpl);
+		return 0;
+	}
 	for (int my = 0; my < F.mcus_y; my++)
 		for (int mx = 0; mx < F.mcus_x; mx++)
 			if (mx * F.tile_w < F.out_w && my * F.tile_h < F.out_h)

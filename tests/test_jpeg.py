@@ -53,16 +53,19 @@ def vbl():
 CASES = [(64, 64), (67, 93), (256, 200), (17, 300), (129, 31)]
 
 
+CASES += [(8, 3), (3, 40), (16, 16), (33, 5)]
+
+
 @pytest.mark.parametrize("size", CASES, ids=lambda s: "%dx%d" % s)
-@pytest.mark.parametrize("sub", [2, 0], ids=["420", "444"])
+@pytest.mark.parametrize("sub", [2, 1, 0], ids=["420", "422", "444"])
 def test_host_twin_matches_libjpeg_turbo(vbl, size, sub):
+    """every sampling x shrink: where libjpeg's upsampler is the identity (one kernel per MCU) and where it is not
+    (4:2:0 at full size: h2v2 fancy; 4:2:2: h2v1 fancy; plain replication at 1/8 and for components <= 2 samples wide)"""
     h, w = size
     a = synth(h, w, seed=h * 7 + w)
     for quality in (30, 85, 100):
         d = encode(a, quality, sub)
         for shrink in (8, 4, 2, 1):
-            if sub == 2 and shrink == 1:
-                continue  # full-size 4:2:0 needs libjpeg's fancy upsampler: declined, tested below
             if min(h, w) // shrink < 1:
                 continue
             got = vbl.jpeg_decode_host_twin(d, shrink)
@@ -93,7 +96,7 @@ def test_extreme_coefficients(vbl):
         for q in (100, 5):
             for sub in (2, 0):
                 d = encode(a, q, sub)
-                for shrink in (2, 4, 8) + ((1,) if sub == 0 else ()):
+                for shrink in (1, 2, 4, 8):
                     assert np.array_equal(vbl.jpeg_decode_host_twin(d, shrink), turbo_decode(d, shrink)), (q, sub, shrink)
 
 
@@ -101,10 +104,10 @@ def test_declined_streams(vbl):
     a = synth(64, 64)
     with pytest.raises(vbl.Error, match="progressive"):
         vbl.jpeg_decode_host_twin(encode(a, progressive=True), 2)
-    with pytest.raises(vbl.Error, match="upsampler"):
-        vbl.jpeg_decode_host_twin(encode(a, subsampling=2), 1)      # 4:2:0 at full size
-    with pytest.raises(vbl.Error, match="upsampler"):
-        vbl.jpeg_decode_host_twin(encode(a, subsampling=1), 2)      # 4:2:2
+    ycck = io.BytesIO()
+    PIL.fromarray(np.dstack([a, a[..., 0]]), "CMYK").save(ycck, "JPEG")
+    with pytest.raises(vbl.Error, match="component"):
+        vbl.jpeg_decode_host_twin(ycck.getvalue(), 1)               # 4 components
     with pytest.raises(vbl.Error, match="shrink"):
         vbl.jpeg_decode_host_twin(encode(a), 3)
     with pytest.raises(vbl.Error, match="JPEG"):
@@ -182,10 +185,10 @@ def test_gpu_batch_decode_matches_libjpeg_turbo(vbl):
     import libvips_b200 as vb
     vb.init(0)
     for (h, w) in ((256, 320), (203, 301), (1024, 1024)):
-        for sub in (2, 0):
+        for sub in (2, 1, 0):
             for kw in ({}, {"restart_marker_rows": 1}, {"optimize": True}):
                 streams = [encode(synth(h, w, seed=i), (95, 75, 40)[i], sub, **kw) for i in range(3)]
-                for shrink in (8, 4, 2) + ((1,) if sub == 0 else ()):
+                for shrink in (8, 4, 2, 1):
                     got = vb.jpeg_decode_batch(streams, shrink)
                     want = np.stack([turbo_decode(s, shrink) for s in streams])
                     assert got.shape == want.shape and np.array_equal(got, want), (h, w, sub, kw, shrink)
