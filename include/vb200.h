@@ -406,6 +406,9 @@ int vb200_jpeg_decode_batch(const void *const *bufs, const size_t *lens, int n, 
 	size_t out_bpl, size_t out_frame_stride, int *width, int *height, int *bands);
 int vb200_jpegload_buffer(const void *buf, size_t len, int shrink, VB200Image *out);
 int vb200_thumbnail_jpegshrink(int width, int height, int target_width, int target_height, int size);
+/* vips_thumbnail_buffer(buf, len, &out, width, "height", height, "size", size, NULL) for a JPEG stream (thumbnail.c:583-613,
+ * 848-902): load-time shrink by vb200_thumbnail_jpegshrink, decode and thumbnail on the device; out: allocate-or-fill */
+int vb200_thumbnail_buffer(const void *buf, size_t len, VB200Image *out, int width, int height, int size);
 int vb200_thumbnail_plan_run_jpeg(VB200ThumbnailPlan *plan, const void *const *bufs, const size_t *lens, int n, int shrink,
 	void *out, int out_location, size_t out_frame_stride);
 int vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height,

@@ -104,6 +104,7 @@ def lib():
                                               C.c_size_t, C.c_size_t, PI, PI, PI]
         L.vb200_debug_jpeg_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, PI, PI, PI]
         L.vb200_thumbnail_jpegshrink.argtypes = [C.c_int] * 5
+        L.vb200_thumbnail_buffer.argtypes = [C.c_void_p, C.c_size_t, IP, C.c_int, C.c_int, C.c_int]
         L.vb200_thumbnail_plan_run_jpeg.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int,
                                                     C.c_void_p, C.c_int, C.c_size_t]
         L.vb200_thumbnail_plan_free.argtypes = [C.c_void_p]
@@ -381,6 +382,19 @@ def jpeg_decode_host_twin(stream, shrink=1):
     _check(lib().vb200_debug_jpeg_decode(stream, len(stream), int(shrink), out.ctypes.data_as(C.c_void_p), w.value * bands.value,
                                          C.byref(w), C.byref(h), C.byref(bands)))
     return out
+
+
+def thumbnail_buffer(stream, width, height=None, size="both"):
+    """vips_thumbnail_buffer() of a JPEG stream: shrink-on-load decode + thumbnail on the device -> uint8 array"""
+    stream = bytes(stream)
+    out = CImage()
+    out.where = HOST
+    _check(lib().vb200_thumbnail_buffer(stream, len(stream), C.byref(out), int(width), int(height or 0), SIZES[size]))
+    n = out.Ysize * out.bpl
+    a = np.frombuffer(C.string_at(out.data, n), np.uint8).reshape(out.Ysize, out.bpl)[:, :out.Xsize * out.Bands]
+    a = a.reshape(out.Ysize, out.Xsize, out.Bands).copy()
+    lib().vb200_image_free(C.byref(out))
+    return a
 
 
 def thumbnail_jpegshrink(width, height, target_width, target_height=None, size="both"):

@@ -19,6 +19,7 @@
  */
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -381,6 +382,111 @@ reducev_u8_dp2a_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, 
 		}
 }
 
+/* The same kernel with the block's whole tap window staged in shared memory by bulk copies (cp.async.bulk, one per
+ * input row, all in flight at once behind one mbarrier) instead of being walked with dependent global loads: the
+ * register-blocked kernel above spends its time waiting on row loads from L2 (long_scoreboard 13.5 per issue), here the
+ * walk reads shared memory.  Needs 16-byte aligned rows and a window that fits (rows x 512 B <= kRvsMaxRows).
+ */
+constexpr int kRvsMaxRows = 160; /* 80 KB of staged rows per CTA: two CTAs per SM */
+
+__device__ __forceinline__ unsigned
+rv_smem_addr(const void *p)
+{
+	return (unsigned) __cvta_generic_to_shared(p);
+}
+
+__global__ void __launch_bounds__(kRvThreads)
+reducev_u8_dp2a_staged_kernel(const uint8_t *__restrict__ in, size_t in_bpl, int in_h, uint8_t *__restrict__ out, size_t out_bpl, int nwords,
+	int out_rows, AxisDev t, int max_pairs)
+{
+	extern __shared__ __align__(128) unsigned char s_raw[];
+	unsigned *s_c2 = (unsigned *) s_raw;								  /* [max_pairs][kRvRows] */
+	unsigned long long *bar = (unsigned long long *) (s_c2 + (size_t) max_pairs * kRvRows);
+	unsigned *s_rows = (unsigned *) (((uintptr_t) (bar + 1) + 127) & ~(uintptr_t) 127); /* [2 * npairs][kRvThreads] */
+	const int n = t.n_point;
+	const int y0 = blockIdx.y * kRvRows;
+	int u0 = 0x7fffffff, u1 = -0x7fffffff;
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++) {
+		const int py = __ldg(t.first + min(y0 + j, out_rows - 1)) - t.embed;
+		u0 = min(u0, py);
+		u1 = max(u1, py + n - 1);
+	}
+	const int npairs = (u1 - u0 + 2) >> 1;
+	const int x0 = blockIdx.x * kRvThreads;
+	const unsigned row_bytes = (unsigned) min(kRvThreads, nwords - x0) * 4u;
+	const unsigned bar_s = rv_smem_addr(bar);
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+		asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar_s),
+					 "r"(row_bytes * (unsigned) (2 * npairs))
+					 : "memory");
+	__syncthreads();
+	/* one bulk copy per window row, issued by as many threads as there are rows */
+	for (int r = threadIdx.x; r < 2 * npairs; r += kRvThreads) {
+		const int row = clampi(u0 + r, 0, in_h - 1);
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+						 rv_smem_addr(s_rows + (size_t) r * kRvThreads)),
+					 "l"(in + (size_t) row * in_bpl + (size_t) x0 * 4), "r"(row_bytes), "r"(bar_s)
+					 : "memory");
+	}
+	/* the coefficient pairs of the block's rows, while the copies fly */
+	for (int idx = threadIdx.x; idx < npairs * kRvRows; idx += kRvThreads) {
+		const int k = idx / kRvRows, j = idx - k * kRvRows;
+		const int yj = min(y0 + j, out_rows - 1);
+		const short *c = t.ms + (size_t) __ldg(t.phase + yj) * n;
+		const int i0 = u0 + 2 * k - (__ldg(t.first + yj) - t.embed);
+		const unsigned lo = i0 >= 0 && i0 < n ? (unsigned short) c[i0] : 0u;
+		const unsigned hi = i0 + 1 >= 0 && i0 + 1 < n ? (unsigned short) c[i0 + 1] : 0u;
+		s_c2[idx] = lo | (hi << 16);
+	}
+	__syncthreads();
+	{
+		unsigned done;
+		do {
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						 : "=r"(done)
+						 : "r"(bar_s), "r"(0u)
+						 : "memory");
+		} while (!done);
+	}
+	const int x = x0 + threadIdx.x;
+	if (x >= nwords)
+		return;
+	int acc[kRvRows][4];
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++)
+#pragma unroll
+		for (int c = 0; c < 4; c++)
+			acc[j][c] = VB200_INTERPOLATE_SCALE >> 1;
+	const unsigned *mine = s_rows + threadIdx.x;
+#pragma unroll 4
+	for (int k = 0; k < npairs; k++) {
+		const unsigned va = mine[(size_t) (2 * k) * kRvThreads], vb = mine[(size_t) (2 * k + 1) * kRvThreads];
+		const unsigned w0 = __byte_perm(va, vb, 0x5140), w1 = __byte_perm(va, vb, 0x7362);
+		const uint4 c4 = *(const uint4 *) (s_c2 + k * kRvRows);
+		const unsigned cj[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+		for (int j = 0; j < kRvRows; j++) {
+			acc[j][0] = dp2a_lo_(cj[j], w0, acc[j][0]);
+			acc[j][1] = dp2a_hi_(cj[j], w0, acc[j][1]);
+			acc[j][2] = dp2a_lo_(cj[j], w1, acc[j][2]);
+			acc[j][3] = dp2a_hi_(cj[j], w1, acc[j][3]);
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < kRvRows; j++)
+		if (y0 + j < out_rows) {
+			const unsigned b0 = clampi(acc[j][0] >> VB200_INTERPOLATE_SHIFT, 0, 255), b1 = clampi(acc[j][1] >> VB200_INTERPOLATE_SHIFT, 0, 255);
+			const unsigned b2 = clampi(acc[j][2] >> VB200_INTERPOLATE_SHIFT, 0, 255), b3 = clampi(acc[j][3] >> VB200_INTERPOLATE_SHIFT, 0, 255);
+			((unsigned *) (out + (size_t) (y0 + j) * out_bpl))[x] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+		}
+}
+
 /* uchar RGBA rows: a CTA stages the span of input pixels its kRhThreads output pixels read (clamp addressing =
  * the reference's EXTEND_COPY embed) into shared memory, padded one word in eight so that the stride-shrink reads
  * of a warp spread over the banks, then every thread runs its taps two pixels at a time: PRMT to [r r' g g'] /
@@ -717,7 +823,19 @@ run_reducev(const char *domain, const void *in, size_t in_bpl, int in_h, void *o
 	switch (fmt) {
 	case VB200_FORMAT_UCHAR:
 		if ((ne & 3) == 0 && aligned4(in, in_bpl) && aligned4(out, out_bpl)) {
-			if (dp2a_smem > 0 && dp2a_smem <= 40 * 1024 && out_rows >= 1)
+			const int max_pairs = (int) (dp2a_smem / (kRvRows * sizeof(unsigned)));
+			static const bool no_staged = getenv("VB200_NO_REDUCEV_STAGED") != nullptr;
+			if (dp2a_smem > 0 && 2 * max_pairs <= kRvsMaxRows && !no_staged && (((uintptr_t) in | in_bpl) & 15) == 0 && (ne & 15) == 0) {
+				const size_t smem = dp2a_smem + 8 + 128 + (size_t) 2 * max_pairs * kRvThreads * 4;
+				static bool attr_done = false;
+				if (!attr_done) {
+					cudaFuncSetAttribute(reducev_u8_dp2a_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+					attr_done = true;
+				}
+				reducev_u8_dp2a_staged_kernel<<<dim3((ne / 4 + kRvThreads - 1) / kRvThreads, (out_rows + kRvRows - 1) / kRvRows), kRvThreads, smem,
+					s>>>((const uint8_t *) in, in_bpl, in_h, (uint8_t *) out, out_bpl, ne / 4, out_rows, d, max_pairs);
+			}
+			else if (dp2a_smem > 0 && dp2a_smem <= 40 * 1024 && out_rows >= 1)
 				reducev_u8_dp2a_kernel<<<dim3((ne / 4 + kRvThreads - 1) / kRvThreads, (out_rows + kRvRows - 1) / kRvRows), kRvThreads,
 					dp2a_smem, s>>>((const uint8_t *) in, in_bpl, in_h, (uint8_t *) out, out_bpl, ne / 4, out_rows, d);
 			else

@@ -2663,6 +2663,68 @@ vb200_thumbnail_batch_device(VB200ThumbnailPlan *plan, const void *in, size_t in
 		current_stream());
 }
 
+/* reference: vips_thumbnail_buffer(buf, len, &out, width, "height", height, "size", size, NULL), resample/thumbnail.c:
+ * 583-613 (open with the load-time shrink vips_thumbnail_find_jpegshrink picks) then :848-902 on what was loaded.
+ * JPEG streams only; everything between the compressed bytes and the thumbnail stays on the device.
+ */
+extern "C" int
+vb200_thumbnail_buffer(const void *buf, size_t len, VB200Image *out, int width, int height, int size)
+{
+	const char *domain = "thumbnail_buffer";
+	if (!buf || !out) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	cudaStream_t s = current_stream();
+	int w0, h0, b0;
+	if (dev_jpeg_decode_batch(domain, &buf, &len, 1, 1, nullptr, 0, 0, &w0, &h0, &b0, s))
+		return -1;
+	const int shrink = vb200_thumbnail_jpegshrink(w0, h0, width, height, size);
+	int w, h, b;
+	if (dev_jpeg_decode_batch(domain, &buf, &len, 1, shrink, nullptr, 0, 0, &w, &h, &b, s))
+		return -1;
+	DevImage dec;
+	if (dev_image_new(domain, &dec, w, h, b, VB200_FORMAT_UCHAR, b == 1 ? VB200_INTERPRETATION_B_W : VB200_INTERPRETATION_sRGB, s))
+		return -1;
+	int rc = dev_jpeg_decode_batch(domain, &buf, &len, 1, shrink, dec.data, dec.bpl, dec.bpl * h, nullptr, nullptr, nullptr, s);
+	if (!rc) {
+		VB200Image din;
+		memset(&din, 0, sizeof(din));
+		din.Xsize = w;
+		din.Ysize = h;
+		din.Bands = b;
+		din.BandFmt = VB200_FORMAT_UCHAR;
+		din.Type = dec.type;
+		din.where = VB200_DEVICE;
+		din.data = dec.data;
+		din.bpl = dec.bpl;
+		const int where = out->where;
+		VB200Image tmp;
+		memset(&tmp, 0, sizeof(tmp));
+		tmp.where = VB200_DEVICE;
+		rc = vb200_thumbnail_image(&din, &tmp, width, height, size, 0);
+		if (!rc) {
+			/* deliver where the caller asked (allocate-or-fill) */
+			DevImage dt;
+			dt.w = tmp.Xsize;
+			dt.h = tmp.Ysize;
+			dt.bands = tmp.Bands;
+			dt.fmt = tmp.BandFmt;
+			dt.type = tmp.Type;
+			dt.data = tmp.data;
+			dt.bpl = tmp.bpl;
+			dt.owned = true;
+			VB200Image like = *out;
+			like.where = where;
+			rc = deliver(domain, &dt, &like, out, s);
+		}
+	}
+	dev_image_release(&dec, s);
+	return rc;
+}
+
 /* Decode staging feeding the plan: compressed JPEG bytes up, decoded at `shrink` on the device
  * (jpeg.cu), thumbnailed by the plan's kernels -- the decoded frames never exist in host memory.  What
  * vips_thumbnail_buffer() does with jpeg2vips + vips_thumbnail_image (thumbnail.c:583-613, 848-902).

@@ -261,3 +261,19 @@ def test_gpu_thumbnail_from_jpeg_streams(vbl):
         got = plan.run_jpeg(streams, shrink)
         want = np.stack([pyoracle.thumbnail_image(turbo_decode(s, shrink), target) for s in streams])
         assert got.shape == want.shape and np.array_equal(got, want), (h, w, target)
+
+
+@pytest.mark.gpu
+def test_gpu_thumbnail_buffer(vbl):
+    """vb200_thumbnail_buffer = vips_thumbnail_buffer for a JPEG stream: the load-time shrink of thumbnail.c:489-517 (1 for a
+    modest reduction: full-size 4:2:0 through the fancy upsampler), then the thumbnail of what was loaded"""
+    import libvips_b200 as vb
+    from oracle import pyoracle
+    vb.init(0)
+    for (h, w, target, sub) in ((1024, 1536, 200, 2), (600, 800, 300, 2), (512, 512, 100, 1), (900, 700, 64, 0)):
+        d = encode(synth(h, w, seed=target), 85, sub)
+        shrink = vb.thumbnail_jpegshrink(w, h, target)
+        got = vb.thumbnail_buffer(d, target)
+        want = pyoracle.thumbnail_image(turbo_decode(d, shrink), target)
+        assert got.shape == want.shape and np.array_equal(got, want), (h, w, target, sub, shrink)
+
