@@ -32,8 +32,8 @@ METRIC = "Mpixels/s for thumbnail(4K->512,lanczos3)"
 METRIC_PIPELINE = "Mpixels/s for thumbnail(4K->512,lanczos3) + sharpen + sRGB (BASELINE config 5 stream)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel per 4096x4096 frame, from the
 # committed `ncu --set full` capture (a launch of 148 frames: 10.1220 GB read, 159.4 MB written)
-DRAM_BYTES_PER_FRAME = (10.122020e9 + 159.401728e6) / 148
-DRAM_SOURCE = "profiles/r1q_ncu_summary.txt (ncu --set full, per frame x frames in the launch)"
+DRAM_BYTES_PER_FRAME = (10.124448e9 + 161.176576e6) / 148
+DRAM_SOURCE = "profiles/r2/headline_random_alpha_ncu_summary.txt (ncu --set full, 148 frames: per frame x frames in the launch)"
 WORKLOAD = "vips_thumbnail 4K->512 uchar RGBA (premultiply,shrinkv4,reducev13,shrinkh4,reduceh13,unpremultiply), synthetic frames, device-resident"
 WORKLOAD_PIPELINE = ("vips_thumbnail 4K->512 uchar RGBA then vips_sharpen (sRGB->LabS, 3-tap integer blur of L, LUT, LabS->sRGB) on the 512x512 "
                      "result, synthetic frames, device-resident")
