@@ -49,7 +49,7 @@ template <> struct Kind<uint16_t> { static constexpr int k = 2; static constexpr
 template <> struct Kind<int16_t> { static constexpr int k = 2; static constexpr double lo = -32768, hi = 32767; };
 template <> struct Kind<uint32_t> { static constexpr int k = 3; static constexpr double lo = 0, hi = 2147483647.0; };
 template <> struct Kind<int32_t> { static constexpr int k = 3; static constexpr double lo = -2147483648.0, hi = 2147483647.0; };
-template <> struct Kind<float> { static constexpr int k = 4; static constexpr double lo = 0, hi = 0; };
+template <> struct Kind<float> { static constexpr int k = 4; };
 
 __device__ __forceinline__ int
 ufr(int v)

@@ -25,9 +25,9 @@ namespace {
 enum ChainOp { C_RESIZE, C_REDUCE, C_COLOURSPACE, C_CONV, C_CONVSEP, C_GAUSSBLUR, C_SHARPEN, C_PREMULTIPLY, C_UNPREMULTIPLY, C_MORPH };
 
 struct ChainStep {
-	ChainOp op;
-	double d[6];
-	int i[2];
+	ChainOp op = C_RESIZE;
+	double d[6] = {0, 0, 0, 0, 0, 0};
+	int i[2] = {0, 0};
 	std::vector<double> mask;
 	int mw = 0, mh = 0;
 };

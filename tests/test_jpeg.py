@@ -277,3 +277,30 @@ def test_gpu_thumbnail_buffer(vbl):
         want = pyoracle.thumbnail_image(turbo_decode(d, shrink), target)
         assert got.shape == want.shape and np.array_equal(got, want), (h, w, target, sub, shrink)
 
+
+@pytest.mark.gpu
+def test_gpu_concurrent_callers(vbl):
+    """libvips calls loaders from worker threads: the pump (pinned / device slots) is one per process, callers take turns"""
+    import threading
+    import libvips_b200 as vb
+    vb.init(0)
+    jobs = [([encode(synth(256 + 16 * t, 320, seed=10 * t + i), 80, (2, 1, 0)[t % 3]) for i in range(3)], (2, 1, 4, 2)[t]) for t in range(4)]
+    want = [np.stack([turbo_decode(s, shrink) for s in streams]) for streams, shrink in jobs]
+    got, errs = [None] * len(jobs), []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                got[t] = vb.jpeg_decode_batch(jobs[t][0], jobs[t][1])
+        except Exception as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errs, errs
+    for t in range(len(jobs)):
+        assert np.array_equal(got[t], want[t]), t
+
