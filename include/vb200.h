@@ -417,6 +417,10 @@ int vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, 
  * max_passes passes), *passes_used = the last pass that changed a record */
 int vb200_debug_jpeg_decode_sync(const void *buf, size_t len, int shrink, int sub_bytes, int max_passes, void *out, size_t out_bpl,
 	int *width, int *height, int *bands, int *passes_used);
+/* test hook, host only: vips_jpegsave_buffer's stream (csrc/jpeg_encode.cu) through the encoder's per-block code on the CPU.
+ * subsample_mode: 0 auto (4:2:0 below Q 90, vips2jpeg.c:676-690), 1 on, 2 off.  *len = bytes written */
+int vb200_debug_jpeg_encode(const void *pixels, size_t bpl, int width, int height, int bands, int quality, int subsample_mode, void *out,
+	size_t cap, size_t *len);
 /* with env VB200_JPEG_TIMING: CUDA-event times of jpeg_huffman_kernel / jpeg_idct_kernel over the calling thread's last decode */
 void vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms);
 

@@ -139,6 +139,12 @@ rgb_to_ycc(int r, int g, int b, int *y, int *cb, int *cr)
 }
 
 HD int
+min_(int a, int b)
+{
+	return a < b ? a : b;
+}
+
+HD int
 fdescale(int x, int n)
 {
 	return (x + (1 << (n - 1))) >> n;
@@ -240,8 +246,20 @@ encode_mcu(const EncodeGeom &G, const unsigned short (*q)[64], const unsigned ch
 	 * alternates 1, 2 along an output row, starting at 1)
 	 */
 	const int x0 = mx * 16, y0 = my * 16;
+	/* luma blocks past the component's own block grid (an odd number of block columns / rows) are DUMMY blocks, not
+	 * encoded pixels: all zero but for a DC copied from a neighbour (jccoefct.c compress_data: at the right edge the block
+	 * before it; a dummy bottom row takes the last block of the row above it in the MCU)
+	 */
+	const int wb = (G.w + 7) / 8, hb = (G.h + 7) / 8;
 	for (int b = 0; b < 4; b++) {
 		const int bx = x0 + (b & 1) * 8, by = y0 + (b >> 1) * 8;
+		const bool dummy_row = my * 2 + (b >> 1) >= hb, dummy_col = mx * 2 + (b & 1) >= wb;
+		if (dummy_row || dummy_col) {
+			for (int i = 0; i < 64; i++)
+				coef[b * 64 + i] = 0;
+			coef[b * 64] = coef[(dummy_row ? 1 : b - 1) * 64];
+			continue;
+		}
 		for (int y = 0; y < 8; y++)
 			for (int x = 0; x < 8; x++) {
 				int yy, cb, cr;
@@ -255,11 +273,16 @@ encode_mcu(const EncodeGeom &G, const unsigned short (*q)[64], const unsigned ch
 	for (int c = 1; c < 3; c++) {
 		for (int y = 0; y < 8; y++)
 			for (int x = 0; x < 8; x++) {
+				/* rows: the colour buffer is padded to a whole row GROUP by repeating the last input row, but the rest
+				 * of the iMCU by repeating the last DOWNSAMPLED row (jcprepct.c pre_process_data); columns: the input
+				 * is padded (expand_right_edge)
+				 */
+				const int ry = min_(my * 8 + y, (G.h + 1) / 2 - 1);
 				int sum = 0;
 				for (int dy = 0; dy < 2; dy++)
 					for (int dx = 0; dx < 2; dx++) {
 						int v[3];
-						pixel_ycc(img, bpl, G.w, G.h, G.bands, x0 + 2 * x + dx, y0 + 2 * y + dy, &v[0], &v[1], &v[2]);
+						pixel_ycc(img, bpl, G.w, G.h, G.bands, x0 + 2 * x + dx, 2 * ry + dy, &v[0], &v[1], &v[2]);
 						sum += v[c];
 					}
 				/* the bias of output column (mx * 8 + x): 1, 2, 1, 2 ... from the row's first column */

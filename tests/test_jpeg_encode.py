@@ -49,7 +49,7 @@ def enc():
         a = np.ascontiguousarray(a)
         h, w = a.shape[:2]
         bands = 1 if a.ndim == 2 else a.shape[2]
-        cap = w * h * 3 + 4096
+        cap = w * h * 8 + 8192
         buf = (C.c_ubyte * cap)()
         n = C.c_size_t()
         vb._check(L.vb200_debug_jpeg_encode(a.ctypes.data_as(C.c_void_p), w * bands, w, h, bands, quality, mode, buf, cap, C.byref(n)))
@@ -80,7 +80,7 @@ def test_host_twin_writes_libjpeg_turbos_stream(enc, size):
     same_stream(enc(a, 75, 2), turbo_encode(a, 75, 0), (size, 75, "subsample off"))
     same_stream(enc(a, 95, 1), turbo_encode(a, 95, 2), (size, 95, "subsample on"))
     g = synth(h, w, seed=w, grey=True)
-    same_stream(enc(g, 75, 0), turbo_encode(g, 75, 2), (size, 75, "grey"))
+    same_stream(enc(g, 75, 0), turbo_encode(g, 75, 0), (size, 75, "grey"))     # vips2jpeg.c:678-684: one band is always 1 x 1
 
 
 def test_extremes(enc):
