@@ -417,6 +417,14 @@ int vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, 
  * max_passes passes), *passes_used = the last pass that changed a record */
 int vb200_debug_jpeg_decode_sync(const void *buf, size_t len, int shrink, int sub_bytes, int max_passes, void *out, size_t out_bpl,
 	int *width, int *height, int *bands, int *passes_used);
+/* vips_jpegsave_buffer (foreign/vips2jpeg.c:551-700: jpeg_set_quality(Q, TRUE), chroma subsampled 2 x 2 below Q 90 unless
+ * subsample_mode says otherwise -- 0 auto, 1 on, 2 off --, baseline, standard Huffman tables, JFIF header) for n equally sized
+ * 8-bit frames of 1 or 3 bands, encoded on the device (csrc/jpeg_encode.cu): the streams are libjpeg-turbo's byte for byte
+ * (tests/test_jpeg_encode.py).  frames / out in host or device memory; stream i at out + i * out_stride, lengths[i] bytes
+ * (host array); -1 when a stream does not fit its stride.
+ */
+int vb200_jpegsave_batch(const void *frames, int frames_location, size_t bpl, size_t frame_stride, int n, int width, int height, int bands,
+	int Q, int subsample_mode, void *out, int out_location, size_t out_stride, size_t *lengths);
 /* test hook, host only: vips_jpegsave_buffer's stream (csrc/jpeg_encode.cu) through the encoder's per-block code on the CPU.
  * subsample_mode: 0 auto (4:2:0 below Q 90, vips2jpeg.c:676-690), 1 on, 2 off.  *len = bytes written */
 int vb200_debug_jpeg_encode(const void *pixels, size_t bpl, int width, int height, int bands, int quality, int subsample_mode, void *out,

@@ -104,6 +104,8 @@ def lib():
                                               C.c_size_t, C.c_size_t, PI, PI, PI]
         L.vb200_debug_jpeg_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, PI, PI, PI]
         L.vb200_thumbnail_jpegshrink.argtypes = [C.c_int] * 5
+        L.vb200_jpegsave_batch.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_size_t)]
         L.vb200_thumbnail_buffer.argtypes = [C.c_void_p, C.c_size_t, IP, C.c_int, C.c_int, C.c_int]
         L.vb200_thumbnail_plan_run_jpeg.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_int, C.c_int,
                                                     C.c_void_p, C.c_int, C.c_size_t]
@@ -382,6 +384,27 @@ def jpeg_decode_host_twin(stream, shrink=1):
     _check(lib().vb200_debug_jpeg_decode(stream, len(stream), int(shrink), out.ctypes.data_as(C.c_void_p), w.value * bands.value,
                                          C.byref(w), C.byref(h), C.byref(bands)))
     return out
+
+
+def jpegsave_batch(frames, Q=75, subsample_mode="auto", in_ptr=None, shape=None, stride=None):
+    """vips_jpegsave_buffer() of every frame of a uint8 array [n, h, w, bands] (bands 1 or 3) on the device -> list of bytes.
+    in_ptr / shape: frames already on the device (packed), shape = (n, h, w, bands)"""
+    mode = {"auto": 0, "on": 1, "off": 2}[subsample_mode]
+    if in_ptr is None:
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim == 3:
+            frames = frames[..., None]
+        n, h, w, bands = frames.shape
+        src, where = frames.ctypes.data_as(C.c_void_p), HOST
+    else:
+        n, h, w, bands = shape
+        src, where = C.c_void_p(in_ptr), DEVICE
+    stride = int(stride or (w * h * bands * 2 + 4096))
+    out = np.empty((n, stride), np.uint8)
+    lens = (C.c_size_t * n)()
+    _check(lib().vb200_jpegsave_batch(src, where, w * bands, w * h * bands, n, w, h, bands, int(Q), mode, out.ctypes.data_as(C.c_void_p), HOST,
+                                      stride, lens))
+    return [out[i, :lens[i]].tobytes() for i in range(n)]
 
 
 def thumbnail_buffer(stream, width, height=None, size="both"):

@@ -470,7 +470,279 @@ make_geom(const char *domain, int w, int h, int bands, int quality, int subsampl
 	return 0;
 }
 
+/* ------------------------------------------------------------------ kernels */
+
+constexpr int kStuffChunk = 256; /* bytes of raw scan per thread of the stuffing kernels */
+constexpr int kMaxBlockBytes = 208; /* 64 coefficients x (16-bit code + 10 bits): the bit buffer's bound per block */
+
+/* one thread per MCU; blockIdx.y = frame */
+__global__ void __launch_bounds__(128)
+jpeg_fdct_kernel(const EncodeGeom G, const EncodeTables *__restrict__ T, const unsigned char *__restrict__ img, size_t bpl, size_t frame_stride,
+	short *__restrict__ coef)
+{
+	__shared__ unsigned short s_q[2][64];
+	for (int i = threadIdx.x; i < 128; i += blockDim.x)
+		s_q[i >> 6][i & 63] = T->q[i >> 6][i & 63];
+	__syncthreads();
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= G.mcus_x * G.mcus_y)
+		return;
+	const int my = i / G.mcus_x, mx = i - my * G.mcus_x;
+	__align__(16) short local[6 * 64];
+	encode_mcu(G, s_q, img + (size_t) blockIdx.y * frame_stride, bpl, mx, my, local);
+	short *dst = coef + ((size_t) blockIdx.y * G.blocks + (size_t) i * G.blocks_per_mcu) * 64;
+	for (int j = 0; j < G.blocks_per_mcu * 64; j += 8)
+		*(uint4 *) (dst + j) = *(const uint4 *) (local + j);
+}
+
+/* one thread per block: how many bits its code takes */
+__global__ void __launch_bounds__(128)
+jpeg_count_kernel(const EncodeGeom G, const EncodeTables *__restrict__ T, const short *__restrict__ coef, unsigned *__restrict__ bits)
+{
+	const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= (unsigned) G.blocks)
+		return;
+	const short *fc = coef + (size_t) blockIdx.y * G.blocks * 64;
+	bits[(size_t) blockIdx.y * G.blocks + b] = code_block(*T, fc + (size_t) b * 64, block_comp(G, (int) (b % (unsigned) G.blocks_per_mcu)),
+		previous_dc(G, fc, b), [](unsigned, int) {});
+}
+
+/* exclusive prefix sum of a frame's per-block bit counts (in place), total into totals[frame]: one CTA per frame */
+__global__ void __launch_bounds__(1024)
+jpeg_bitscan_kernel(int blocks, unsigned *__restrict__ bits, unsigned long long *__restrict__ totals)
+{
+	__shared__ unsigned long long s_part[1024];
+	unsigned *b = bits + (size_t) blockIdx.x * blocks;
+	const unsigned per = ((unsigned) blocks + blockDim.x - 1) / blockDim.x;
+	const unsigned a = min((unsigned) blocks, threadIdx.x * per), e = min((unsigned) blocks, a + per);
+	unsigned long long sum = 0;
+	for (unsigned i = a; i < e; i++)
+		sum += b[i];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	for (unsigned o = 1; o < blockDim.x; o <<= 1) {
+		const unsigned long long v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned long long run = s_part[threadIdx.x] - sum;
+	for (unsigned i = a; i < e; i++) {
+		const unsigned n = b[i];
+		b[i] = (unsigned) run; /* a frame's scan stays far below 2^32 bits (65535 x 65535 would not, and is refused) */
+		run += n;
+	}
+	if (threadIdx.x == blockDim.x - 1)
+		totals[blockIdx.x] = s_part[threadIdx.x];
+}
+
+/* one thread per block: its bits into the frame's (zeroed) raw bit buffer, whole bytes OR-ed in (neighbouring blocks share
+ * their boundary bytes); the thread that ends the frame also pads the last byte with 1-bits
+ */
+__global__ void __launch_bounds__(128)
+jpeg_emit_kernel(const EncodeGeom G, const EncodeTables *__restrict__ T, const short *__restrict__ coef, const unsigned *__restrict__ offs,
+	const unsigned long long *__restrict__ totals, unsigned *__restrict__ raw, size_t raw_words)
+{
+	const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= (unsigned) G.blocks)
+		return;
+	const short *fc = coef + (size_t) blockIdx.y * G.blocks * 64;
+	unsigned *out = raw + (size_t) blockIdx.y * raw_words;
+	unsigned pos = offs[(size_t) blockIdx.y * G.blocks + b]; /* bit index */
+	unsigned long long acc = 0;
+	int nacc = (int) (pos & 7u); /* the bits of the first byte that belong to the block before: zeros here, OR-ed there */
+	unsigned byte = pos >> 3;
+	auto put = [&](unsigned code, int len) {
+		acc = (acc << len) | code;
+		nacc += len;
+		while (nacc >= 8) {
+			const unsigned v = (unsigned) (acc >> (nacc - 8)) & 0xffu;
+			if (v)
+				atomicOr(out + (byte >> 2), v << (8 * (byte & 3u)));
+			byte++;
+			nacc -= 8;
+		}
+	};
+	code_block(*T, fc + (size_t) b * 64, block_comp(G, (int) (b % (unsigned) G.blocks_per_mcu)), previous_dc(G, fc, b), put);
+	if (nacc > 0) {
+		unsigned v = (unsigned) (acc << (8 - nacc)) & 0xffu;
+		if (b == (unsigned) G.blocks - 1)
+			v |= (1u << (8 - nacc)) - 1; /* jchuff.c flush_bits: pad the last byte with ones */
+		if (v)
+			atomicOr(out + (byte >> 2), v << (8 * (byte & 3u)));
+	}
+	(void) totals;
+}
+
+/* stuffing, pass 1: 0xFF bytes per kStuffChunk-byte span of each frame's raw scan */
+__global__ void __launch_bounds__(128)
+jpeg_ffcount_kernel(const unsigned long long *__restrict__ totals, const unsigned char *__restrict__ raw, size_t raw_bytes, int max_chunks,
+	unsigned *__restrict__ counts)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= max_chunks)
+		return;
+	const unsigned long long nbytes = (totals[blockIdx.y] + 7) >> 3;
+	const unsigned char *p = raw + (size_t) blockIdx.y * raw_bytes;
+	unsigned n = 0;
+	const unsigned long long a = (unsigned long long) c * kStuffChunk, e = min(nbytes, a + kStuffChunk);
+	for (unsigned long long i = a; i < e; i++)
+		n += p[i] == 0xFF;
+	counts[(size_t) blockIdx.y * max_chunks + c] = n;
+}
+
+/* stuffing, pass 2: prefix sum of the spans' counts, one CTA per frame; lengths[frame] = header + scan + stuffed zeros + EOI */
+__global__ void __launch_bounds__(1024)
+jpeg_ffscan_kernel(const unsigned long long *__restrict__ totals, int max_chunks, unsigned *__restrict__ counts, unsigned header_len,
+	unsigned long long *__restrict__ lengths)
+{
+	__shared__ unsigned s_part[1024];
+	unsigned *cnt = counts + (size_t) blockIdx.x * max_chunks;
+	const unsigned per = ((unsigned) max_chunks + blockDim.x - 1) / blockDim.x;
+	const unsigned a = min((unsigned) max_chunks, threadIdx.x * per), e = min((unsigned) max_chunks, a + per);
+	unsigned sum = 0;
+	for (unsigned i = a; i < e; i++)
+		sum += cnt[i];
+	s_part[threadIdx.x] = sum;
+	__syncthreads();
+	for (unsigned o = 1; o < blockDim.x; o <<= 1) {
+		const unsigned v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+		__syncthreads();
+		s_part[threadIdx.x] += v;
+		__syncthreads();
+	}
+	unsigned run = s_part[threadIdx.x] - sum;
+	for (unsigned i = a; i < e; i++) {
+		const unsigned n = cnt[i];
+		cnt[i] = run;
+		run += n;
+	}
+	if (threadIdx.x == blockDim.x - 1)
+		lengths[blockIdx.x] = (unsigned long long) header_len + ((totals[blockIdx.x] + 7) >> 3) + s_part[threadIdx.x] + 2;
+}
+
+/* stuffing, pass 3: header, stuffed scan, EOI into the caller's stream (a stream that does not fit is cut: the host
+ * compares lengths[frame] with the stride and reports it)
+ */
+__global__ void __launch_bounds__(128)
+jpeg_stuff_kernel(const unsigned long long *__restrict__ totals, const unsigned char *__restrict__ raw, size_t raw_bytes, int max_chunks,
+	const unsigned *__restrict__ counts, const unsigned char *__restrict__ header, unsigned header_len, unsigned char *__restrict__ out,
+	size_t out_stride, const unsigned long long *__restrict__ lengths)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned char *o = out + (size_t) blockIdx.y * out_stride;
+	const unsigned long long len = lengths[blockIdx.y];
+	if (len > out_stride)
+		return;
+	if (c < (int) ((header_len + kStuffChunk - 1) / kStuffChunk)) {
+		/* the first spans' threads also copy the header */
+		for (unsigned i = (unsigned) c * kStuffChunk; i < min(header_len, (unsigned) (c + 1) * kStuffChunk); i++)
+			o[i] = header[i];
+	}
+	if (c >= max_chunks)
+		return;
+	const unsigned long long nbytes = (totals[blockIdx.y] + 7) >> 3;
+	const unsigned char *p = raw + (size_t) blockIdx.y * raw_bytes;
+	const unsigned long long a = (unsigned long long) c * kStuffChunk, e = min(nbytes, a + kStuffChunk);
+	unsigned char *d = o + header_len + a + counts[(size_t) blockIdx.y * max_chunks + c];
+	for (unsigned long long i = a; i < e; i++) {
+		const unsigned char v = p[i];
+		*d++ = v;
+		if (v == 0xFF)
+			*d++ = 0;
+	}
+	if (c == 0) {
+		o[len - 2] = 0xFF;
+		o[len - 1] = 0xD9;
+	}
+}
+
 } // namespace
+
+/* n equally sized 8-bit frames (1 or 3 bands) on the device -> n JPEG streams at out + i * out_stride (device), their
+ * lengths to lengths_host[n].  Stream-ordered on s; returns after the lengths are known.
+ */
+int
+dev_jpeg_encode_batch(const char *domain, const void *frames, size_t bpl, size_t frame_stride, int n, int w, int h, int bands, int quality,
+	int subsample_mode, void *out, size_t out_stride, size_t *lengths_host, cudaStream_t s)
+{
+	EncodeGeom G;
+	if (make_geom(domain, w, h, bands, quality, subsample_mode, &G))
+		return -1;
+	if ((size_t) G.blocks * kMaxBlockBytes >= (size_t) 1 << 29) {
+		error(domain, "frame too large for the device encoder");
+		return -1;
+	}
+	EncodeTables T;
+	make_tables(quality, &T);
+	std::vector<unsigned char> header;
+	write_headers(G, T, header);
+	const size_t raw_bytes = (((size_t) G.blocks * kMaxBlockBytes + 3) & ~(size_t) 3) + 4;
+	const int max_chunks = (int) ((raw_bytes + kStuffChunk - 1) / kStuffChunk);
+	/* one block of device scratch: tables | header | coefficients | bit counts / offsets | totals | lengths | raw | span counts */
+	size_t off = 0;
+	auto take = [&](size_t bytes) {
+		const size_t o = off;
+		off += (bytes + 255) & ~(size_t) 255;
+		return o;
+	};
+	const size_t o_tab = take(sizeof(T)), o_hdr = take(header.size()), o_coef = take((size_t) n * G.blocks * 64 * sizeof(short)),
+				 o_bits = take((size_t) n * G.blocks * sizeof(unsigned)), o_tot = take((size_t) n * sizeof(unsigned long long)),
+				 o_len = take((size_t) n * sizeof(unsigned long long)), o_raw = take((size_t) n * raw_bytes),
+				 o_cnt = take((size_t) n * max_chunks * sizeof(unsigned));
+	char *scratch = nullptr;
+	if (dev_alloc(domain, (void **) &scratch, off, s))
+		return -1;
+	int rc = -1;
+	do {
+		/* tables and header from pageable memory: small, staged by the driver before the call returns */
+		if (cudaMemcpyAsync(scratch + o_tab, &T, sizeof(T), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+			cudaMemcpyAsync(scratch + o_hdr, header.data(), header.size(), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+			cudaMemsetAsync(scratch + o_raw, 0, (size_t) n * raw_bytes, s) != cudaSuccess) {
+			cuda_fail(domain, cudaGetLastError(), "jpeg encode setup");
+			break;
+		}
+		const EncodeTables *dT = (const EncodeTables *) (scratch + o_tab);
+		short *coef = (short *) (scratch + o_coef);
+		unsigned *bits = (unsigned *) (scratch + o_bits);
+		unsigned long long *totals = (unsigned long long *) (scratch + o_tot), *lengths = (unsigned long long *) (scratch + o_len);
+		unsigned *counts = (unsigned *) (scratch + o_cnt);
+		const int mcus = G.mcus_x * G.mcus_y;
+		jpeg_fdct_kernel<<<dim3((mcus + 127) / 128, n), 128, 0, s>>>(G, dT, (const unsigned char *) frames, bpl, frame_stride, coef);
+		jpeg_count_kernel<<<dim3((G.blocks + 127) / 128, n), 128, 0, s>>>(G, dT, coef, bits);
+		jpeg_bitscan_kernel<<<n, 1024, 0, s>>>(G.blocks, bits, totals);
+		jpeg_emit_kernel<<<dim3((G.blocks + 127) / 128, n), 128, 0, s>>>(G, dT, coef, bits, totals, (unsigned *) (scratch + o_raw), raw_bytes / 4);
+		jpeg_ffcount_kernel<<<dim3((max_chunks + 127) / 128, n), 128, 0, s>>>(totals, (const unsigned char *) (scratch + o_raw), raw_bytes, max_chunks,
+			counts);
+		jpeg_ffscan_kernel<<<n, 1024, 0, s>>>(totals, max_chunks, counts, (unsigned) header.size(), lengths);
+		jpeg_stuff_kernel<<<dim3((max_chunks + 127) / 128, n), 128, 0, s>>>(totals, (const unsigned char *) (scratch + o_raw), raw_bytes, max_chunks,
+			counts, (const unsigned char *) (scratch + o_hdr), (unsigned) header.size(), (unsigned char *) out, out_stride, lengths);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			cuda_fail(domain, e, "jpeg encode kernels launch");
+			break;
+		}
+		for (int k = 0; k < 7; k++)
+			count_launch();
+		std::vector<unsigned long long> len(n);
+		if (cudaMemcpyAsync(len.data(), lengths, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+			cudaStreamSynchronize(s) != cudaSuccess) {
+			cuda_fail(domain, cudaGetLastError(), "jpeg encode");
+			break;
+		}
+		rc = 0;
+		for (int i = 0; i < n; i++) {
+			if (lengths_host)
+				lengths_host[i] = (size_t) len[i];
+			if (len[i] > out_stride) {
+				error(domain, "frame %d: the stream takes %llu bytes, the output stride is %zu", i, len[i], out_stride);
+				rc = -1;
+			}
+		}
+	} while (0);
+	dev_free(scratch, s);
+	return rc;
+}
 
 /* the whole encoder on the CPU through the same per-block code: test hook */
 int
@@ -534,3 +806,76 @@ vb200_debug_jpeg_encode(const void *pixels, size_t bpl, int width, int height, i
 	memcpy(out, o.data(), o.size());
 	return 0;
 }
+
+/* vips_jpegsave_buffer (foreign/vips2jpeg.c) for a batch of equally sized 8-bit frames (1 or 3 bands), on the device:
+ * frames in host or device memory (frames_location), n streams to out + i * out_stride in host or device memory
+ * (out_location), lengths[n] on the host.  Q and subsample_mode as the reference's arguments (0 auto, 1 on, 2 off);
+ * everything else is the reference's default (baseline, standard Huffman tables, JFIF header).
+ */
+extern "C" int
+vb200_jpegsave_batch(const void *frames, int frames_location, size_t bpl, size_t frame_stride, int n, int width, int height, int bands, int Q,
+	int subsample_mode, void *out, int out_location, size_t out_stride, size_t *lengths)
+{
+	const char *domain = "jpegsave_batch";
+	if (!frames || !out || n < 1) {
+		error(domain, "null argument");
+		return -1;
+	}
+	if (ensure_init(domain))
+		return -1;
+	cudaStream_t s = current_stream();
+	const size_t line = (size_t) width * bands;
+	if (bpl < line || (n > 1 && frame_stride < bpl * height)) {
+		error(domain, "frame strides too small for %d x %d x %d", width, height, bands);
+		return -1;
+	}
+	void *din = nullptr, *dout = nullptr;
+	int rc = -1;
+	do {
+		const void *src = frames;
+		size_t sbpl = bpl, sstride = frame_stride;
+		if (frames_location != VB200_DEVICE) {
+			if (dev_alloc(domain, &din, line * height * n, s))
+				break;
+			bool bad = false;
+			for (int i = 0; i < n && !bad; i++)
+				bad = cudaMemcpy2DAsync((char *) din + (size_t) i * line * height, line, (const char *) frames + (size_t) i * frame_stride, bpl, line,
+						  height, cudaMemcpyHostToDevice, s) != cudaSuccess;
+			if (bad) {
+				cuda_fail(domain, cudaGetLastError(), "copy to device");
+				break;
+			}
+			src = din;
+			sbpl = line;
+			sstride = line * height;
+		}
+		void *dst = out;
+		if (out_location != VB200_DEVICE) {
+			if (dev_alloc(domain, &dout, out_stride * n, s))
+				break;
+			dst = dout;
+		}
+		std::vector<size_t> len(n);
+		if (dev_jpeg_encode_batch(domain, src, sbpl, sstride, n, width, height, bands, Q, subsample_mode, dst, out_stride, len.data(), s))
+			break;
+		if (lengths)
+			memcpy(lengths, len.data(), n * sizeof(size_t));
+		if (out_location != VB200_DEVICE) {
+			bool bad = false;
+			for (int i = 0; i < n && !bad; i++)
+				bad = cudaMemcpyAsync((char *) out + (size_t) i * out_stride, (char *) dout + (size_t) i * out_stride, len[i], cudaMemcpyDeviceToHost,
+						  s) != cudaSuccess;
+			if (bad || cudaStreamSynchronize(s) != cudaSuccess) {
+				cuda_fail(domain, cudaGetLastError(), "copy to host");
+				break;
+			}
+		}
+		rc = 0;
+	} while (0);
+	if (din)
+		dev_free(din, s);
+	if (dout)
+		dev_free(dout, s);
+	return rc;
+}
+

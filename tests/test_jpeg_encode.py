@@ -102,3 +102,50 @@ def test_round_trip_through_the_device_decoder_twin(enc):
     got = vb.jpeg_decode_host_twin(d, 1)
     want = np.asarray(PIL.open(io.BytesIO(d)))
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_writes_libjpeg_turbos_streams(enc):
+    import libvips_b200 as vb
+    vb.init(0)
+    for (h, w) in ((64, 64), (67, 93), (256, 200), (17, 300), (8, 8), (512, 512)):
+        frames = np.stack([synth(h, w, seed=i + h) for i in range(3)])
+        for quality, mode, sub in ((75, "auto", 2), (92, "auto", 0), (10, "auto", 2), (100, "on", 2), (60, "off", 0)):
+            got = vb.jpegsave_batch(frames, quality, mode)
+            for i in range(3):
+                same_stream(got[i], turbo_encode(frames[i], quality, sub), ((h, w), quality, mode, i))
+        grey = frames[..., 0].copy()
+        got = vb.jpegsave_batch(grey, 80)
+        for i in range(3):
+            same_stream(got[i], turbo_encode(grey[i], 80, 0), ((h, w), "grey", i))
+    rng = np.random.default_rng(4)
+    noise = rng.integers(0, 256, (2, 96, 128, 3), dtype=np.uint8)
+    for q in (1, 100):
+        got = vb.jpegsave_batch(noise, q)
+        for i in range(2):
+            same_stream(got[i], turbo_encode(noise[i], q, 2 if q < 90 else 0), ("noise", q, i))
+    with pytest.raises(vb.Error, match="stride"):
+        vb.jpegsave_batch(noise, 100, stride=4096)
+
+
+@pytest.mark.gpu
+def test_gpu_jpeg_in_jpeg_out(enc):
+    """the thumbnail server's whole loop on the device: JPEG streams -> shrink-on-load -> thumbnail -> JPEG streams"""
+    import torch
+    import libvips_b200 as vb
+    from oracle import pyoracle
+    from test_jpeg import encode, turbo_decode
+    vb.init(0)
+    h, w, target = 1024, 1536, 256
+    streams = [encode(synth(h, w, seed=i), 88, 2) for i in range(3)]
+    shrink = vb.thumbnail_jpegshrink(w, h, target)
+    dw, dh, bands = vb.jpeg_geometry(streams, shrink)
+    plan = vb.ThumbnailPlan(dw, dh, bands, target)
+    out = torch.empty((3, plan.out_height, plan.out_width, bands), dtype=torch.uint8, device="cuda")
+    plan.run_jpeg(streams, shrink, out_ptr=out.data_ptr())
+    torch.cuda.synchronize()
+    got = vb.jpegsave_batch(None, 75, in_ptr=out.data_ptr(), shape=tuple(out.shape))
+    for i in range(3):
+        thumb = pyoracle.thumbnail_image(turbo_decode(streams[i], shrink), target)
+        same_stream(got[i], turbo_encode(thumb, 75, 2), i)
+
