@@ -258,11 +258,16 @@ def _jpeg_cpu_worker(i):
     import numpy as np
     from PIL import Image
     from oracle import pyoracle
-    distinct, shrink = _JPEG_CPU
+    distinct, shrink, save = _JPEG_CPU
     im = Image.open(io.BytesIO(distinct[i % len(distinct)]))
     im.draft("RGB", (W // shrink, H // shrink))
     a = np.asarray(im)[: H // shrink, : W // shrink]
-    return int(pyoracle.thumbnail_image(a, TARGET)[0, 0, 0])
+    t = pyoracle.thumbnail_image(a, TARGET)
+    if save:
+        b = io.BytesIO()
+        Image.fromarray(t).save(b, "JPEG", quality=75, subsampling=2)
+        return len(b.getvalue())
+    return int(t[0, 0, 0])
 
 
 def side_workload(args):
@@ -483,12 +488,20 @@ def side_workload(args):
             im.draft("RGB", (W // shrink, H // shrink))
             return np.asarray(im)[: H // shrink, : W // shrink]
 
+        saved = []
+
         def fn():
             plan.run_jpeg(batch, shrink, out_ptr=outs.data_ptr())
+            if args.save:
+                saved[:] = vb.jpegsave_batch(None, 75, in_ptr=outs.data_ptr(), shape=tuple(outs.shape), stride=256 * 1024)
         fn()
         from oracle import pyoracle
         want = pyoracle.thumbnail_image(turbo(streams[0]), TARGET)
         assert np.array_equal(outs[0].cpu().numpy(), want), "GPU JPEG thumbnail differs from libjpeg-turbo + the oracle"
+        if args.save:
+            b = io.BytesIO()
+            Image.fromarray(want).save(b, "JPEG", quality=75, subsampling=2)
+            assert saved[0] == b.getvalue(), "the encoded thumbnail is not libjpeg-turbo's stream"
         for _ in range(max(0, args.warmup - 1)):
             fn()
         os.environ["VB200_JPEG_TIMING"] = "1"
@@ -508,7 +521,7 @@ def side_workload(args):
             import multiprocessing as mp
             threads = host_threads()
             global _JPEG_CPU
-            _JPEG_CPU = (distinct, shrink)
+            _JPEG_CPU = (distinct, shrink, args.save)
             with mp.get_context("fork").Pool(threads) as pool:
                 pool.map(_jpeg_cpu_worker, range(threads))
                 t1 = time.perf_counter()
@@ -517,8 +530,9 @@ def side_workload(args):
             cpu = {"value": 2 * threads * MPIX_PER_FRAME / ct, "unit": "Mpixels/s", "cores": threads, "kind": "reference + port",
                    "sample": "%d frames: libjpeg-turbo (Pillow's) decode at scale 1/%d, then the oracle port of the thumbnail chain, "
                              "one frame per process" % (2 * threads, shrink)}
-        label = ("vips_thumbnail_buffer: 4096x4096 4:2:0 JPEG streams (q85, %s) -> shrink-on-load 1/%d on the device -> 512x512, %d frames per step"
-                 % ("one restart interval per MCU row" if restart else "no restart markers", shrink, F))
+        label = ("vips_thumbnail_buffer: 4096x4096 4:2:0 JPEG streams (q85, %s) -> shrink-on-load 1/%d on the device -> 512x512%s, %d frames per step"
+                 % ("one restart interval per MCU row" if restart else "no restart markers", shrink,
+                    " -> vips_jpegsave_buffer (Q 75) on the device, streams to the host" if args.save else "", F))
         print(json.dumps({"metric": label, "value": F * MPIX_PER_FRAME / dt, "unit": "Mpixels/s (input pixels)", "n_gpus": 1,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "dtype": "u8",
                           "data": "synthetic", "config": {"workload": label, "device_resident": False, "frames_per_second": F / dt,
@@ -526,7 +540,8 @@ def side_workload(args):
                           "kernels": {"jpeg_huffman_kernel_ms": hm.value, "jpeg_idct_kernel_ms": im.value,
                                       "note": "CUDA events over one step (chunks serialised for the measurement)"},
                           "e2e": {"value": F * MPIX_PER_FRAME / dt, "unit": "Mpixels/s", "h2d_bytes_per_step": batch.nbytes,
-                                  "d2h_bytes_per_step": 0, "api": "vb200_thumbnail_plan_run_jpeg"},
+                                  "d2h_bytes_per_step": sum(len(x) for x in saved) if args.save else 0,
+                                  "api": "vb200_thumbnail_plan_run_jpeg" + (" + vb200_jpegsave_batch" if args.save else "")},
                           "cpu_baseline": cpu, "gpu_launches": int(vb.launch_count() - n0)}))
     else:
         raise SystemExit("unknown workload %s" % args.workload)
@@ -541,6 +556,9 @@ def main():
     ap.add_argument("--frames", type=int, default=1024, help="synthetic frames resident per GPU")
     ap.add_argument("--e2e-frames", type=int, default=24, help="host frames per end-to-end step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--save", action="store_true",
+                    help="thumbnail_jpeg workloads: also encode the thumbnails to JPEG on the device (vips_jpegsave_buffer, Q 75) and "
+                         "bring the streams to the host -- the thumbnail server's whole loop")
     ap.add_argument("--alpha", default="random", choices=["random", "opaque"],
                     help="alpha band of the synthetic frames: random (the headline) | opaque (255 everywhere, what a PNG without "
                          "transparency decodes to: the kernel's opaque-stage fast path; a second line, never the headline)")
