@@ -386,6 +386,9 @@ def jpeg_decode_host_twin(stream, shrink=1):
     return out
 
 
+_SAVE_BUFFERS = {}
+
+
 def jpegsave_batch(frames, Q=75, subsample_mode="auto", in_ptr=None, shape=None, stride=None):
     """vips_jpegsave_buffer() of every frame of a uint8 array [n, h, w, bands] (bands 1 or 3) on the device -> list of bytes.
     in_ptr / shape: frames already on the device (packed), shape = (n, h, w, bands)"""
@@ -400,7 +403,10 @@ def jpegsave_batch(frames, Q=75, subsample_mode="auto", in_ptr=None, shape=None,
         n, h, w, bands = shape
         src, where = C.c_void_p(in_ptr), DEVICE
     stride = int(stride or (w * h * bands * 2 + 4096))
-    out = np.empty((n, stride), np.uint8)
+    out = _SAVE_BUFFERS.get((n, stride))
+    if out is None:
+        _SAVE_BUFFERS.clear()          # one staging array, reused: a fresh quarter gigabyte per call is all page faults
+        out = _SAVE_BUFFERS[(n, stride)] = np.empty((n, stride), np.uint8)
     lens = (C.c_size_t * n)()
     _check(lib().vb200_jpegsave_batch(src, where, w * bands, w * h * bands, n, w, h, bands, int(Q), mode, out.ctypes.data_as(C.c_void_p), HOST,
                                       stride, lens))
