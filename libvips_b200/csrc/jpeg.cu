@@ -296,22 +296,10 @@ parse_jpeg(const char *domain, const unsigned char *d, size_t len, JpegHeader *H
 				H->comp[k].ta = s[2 + 2 * i] & 15;
 			}
 			H->scan_off = p + L;
-			/* the entropy-coded segment ends at the next marker that is neither FF00 nor RSTn: normally EOI */
-			size_t e = H->scan_off;
-			while (e + 1 < len) {
-				const unsigned char *q = (const unsigned char *) memchr(d + e, 0xFF, len - 1 - e);
-				if (!q) {
-					e = len;
-					break;
-				}
-				e = q - d;
-				const int nx = d[e + 1];
-				if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7) || nx == 0xFF) {
-					e += nx == 0xFF ? 1 : 2;
-					continue;
-				}
-				break;
-			}
+			/* the entropy-coded segment runs to the next marker that is neither FF00 nor RSTn (normally EOI): found by
+			 * the staging copy (destuff_scan), the only pass over the scan the host makes
+			 */
+			const size_t e = len;
 			H->scan_end = std::min(e, len);
 			return 0;
 		}
@@ -1436,7 +1424,6 @@ jpeg_upsample_kernel(const JpegFrameDev *__restrict__ frames, const unsigned cha
 struct FramePrep {
 	JpegFrameDev F;
 	HuffDev huff[8];
-	std::vector<unsigned> offsets; /* n_intervals + 1, relative to the entropy-coded segment */
 	const unsigned char *src = nullptr;
 	size_t src_len = 0, coef_count = 0, plane_bytes = 0;
 	int bands = 0;
@@ -1539,31 +1526,8 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 		error(domain, "entropy-coded segment too large");
 		return -1;
 	}
-	P->offsets.clear();
-	P->offsets.push_back(0);
-	int n_int = 1;
-	if (H.restart_interval > 0) {
-		const int want = (total + H.restart_interval - 1) / H.restart_interval;
-		const unsigned char *sp = d + H.scan_off;
-		size_t e = 0;
-		while (n_int < want && e + 1 < seg) {
-			const unsigned char *q = (const unsigned char *) memchr(sp + e, 0xFF, seg - 1 - e);
-			if (!q)
-				break;
-			e = q - sp;
-			const int nx = sp[e + 1];
-			if (nx >= 0xD0 && nx <= 0xD7) {
-				P->offsets.push_back((unsigned) (e + 2));
-				n_int++;
-			}
-			e += 2;
-		}
-		if (n_int != want) {
-			error(domain, "JPEG has %d restart intervals, its header promises %d", n_int, want);
-			return -1;
-		}
-	}
-	P->offsets.push_back((unsigned) seg);
+	/* the RSTn markers themselves are found (and counted against this) while the scan is staged */
+	const int n_int = H.restart_interval > 0 ? (total + H.restart_interval - 1) / H.restart_interval : 1;
 	F.n_intervals = n_int;
 	P->src = d + H.scan_off;
 	P->src_len = seg;
@@ -1894,7 +1858,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			data_off[i] = bytes_total;
 			bytes_total += ((fp.src_len + 15) & ~(size_t) 15) + 16;
 			int_off[i] = ints_total;
-			ints_total += fp.offsets.size();
+			ints_total += (size_t) fp.F.n_intervals + 1;
 			coef_off[i] = coef_total;
 			coef_total += fp.coef_count;
 			max_intervals = std::max(max_intervals, fp.F.n_intervals);
