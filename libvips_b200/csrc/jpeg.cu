@@ -61,7 +61,21 @@ struct JpegComp {
 	int id, h, v, tq, td, ta;
 };
 
+/* one scan of a progressive frame (T.81 G): its components, spectral band and bit position, and the Huffman tables and
+ * restart interval in force when its SOS arrived (both may be redefined between scans)
+ */
+struct JpegScan {
+	int ns = 0, ci[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+	int Ss = 0, Se = 63, Ah = 0, Al = 0;
+	int restart_interval = 0;
+	size_t off = 0, end = 0;
+	unsigned char hcount[2][4][16];
+	unsigned char hsym[2][4][256];
+	bool hset[2][4];
+};
+
 struct JpegHeader {
+	std::vector<JpegScan> scans; /* progressive frames only */
 	int width = 0, height = 0, ncomp = 0;
 	JpegComp comp[4];
 	bool progressive = false, arithmetic = false;
@@ -113,11 +127,24 @@ struct JpegFrameDev {
 	int pw[kMaxComp], ph[kMaxComp];			 /* plane size in samples (whole blocks) */
 	int dw[kMaxComp], dh[kMaxComp];			 /* the component's true size: jdmaster.c downsampled_width / height */
 	size_t plane_off[kMaxComp];				 /* in the chunk's plane pool (bytes) */
+	/* progressive frames: n_scans scan records from scan_base in the chunk's scan pool, decoded in order */
+	int progressive, n_scans;
+	unsigned scan_base;
 	/* the self-synchronising path (frames with too few restart intervals to fill the machine) */
 	int sync;			 /* 1: decode by subsequences */
 	unsigned clean_len;	 /* bytes of the unstuffed scan (set while staging) */
 	unsigned sync_off;	 /* first of this frame's subsequence records in the chunk's arrays */
 	unsigned sync_cap;	 /* records reserved (from the stuffed length) */
+};
+
+/* one scan of a progressive frame, device layout: offsets are into the chunk's pools */
+struct ScanDev {
+	int ns, comp[3], dc_tab[3], ac_tab; /* tables: indices from huff_base */
+	int Ss, Se, Ah, Al;
+	int restart_interval, n_intervals;
+	int units_x, units_y;	 /* MCUs (interleaved scans) or the component's own blocks (one-component scans, T.81 A.2.2) */
+	unsigned interval_off;	 /* first of n_intervals + 1 offsets (relative to the frame's data) */
+	int huff_base;			 /* the scan's four HuffDev */
 };
 
 const unsigned char kZigzag[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14,
@@ -155,6 +182,8 @@ parse_jpeg(const char *domain, const unsigned char *d, size_t len, JpegHeader *H
 		if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01)
 			continue; /* standalone markers */
 		if (m == 0xD9) {
+			if (!H->scans.empty())
+				return 0; /* a progressive frame: all its scans are in */
 			error(domain, "JPEG stream has no scan");
 			return -1;
 		}
@@ -275,11 +304,68 @@ parse_jpeg(const char *domain, const unsigned char *d, size_t len, JpegHeader *H
 				return -1;
 			}
 			const int ns = s[0];
+			if (H->progressive) {
+				/* T.81 G.1: a scan codes a band Ss..Se of one bit position of its components; what follows its header
+				 * runs to the next marker that is neither FF00 nor RSTn
+				 */
+				JpegScan sc;
+				if (ns < 1 || ns > 3 || ns > H->ncomp) {
+					error(domain, "malformed SOS");
+					return -1;
+				}
+				sc.ns = ns;
+				for (int i = 0; i < ns; i++) {
+					int k = -1;
+					for (int j = 0; j < H->ncomp; j++)
+						if (H->comp[j].id == s[1 + 2 * i])
+							k = j;
+					if (k < 0 || (i && k <= sc.ci[i - 1])) {
+						error(domain, "scan components out of frame order");
+						return -1;
+					}
+					sc.ci[i] = k;
+					sc.td[i] = s[2 + 2 * i] >> 4;
+					sc.ta[i] = s[2 + 2 * i] & 15;
+				}
+				sc.Ss = s[1 + 2 * ns];
+				sc.Se = s[2 + 2 * ns];
+				sc.Ah = s[3 + 2 * ns] >> 4;
+				sc.Al = s[3 + 2 * ns] & 15;
+				sc.restart_interval = H->restart_interval;
+				memcpy(sc.hcount, H->hcount, sizeof(sc.hcount));
+				memcpy(sc.hsym, H->hsym, sizeof(sc.hsym));
+				memcpy(sc.hset, H->hset, sizeof(sc.hset));
+				sc.off = p + L;
+				size_t e = sc.off;
+				while (e + 1 < len) {
+					const unsigned char *q = (const unsigned char *) memchr(d + e, 0xFF, len - 1 - e);
+					if (!q) {
+						e = len;
+						break;
+					}
+					e = q - d;
+					const int nx = d[e + 1];
+					if (nx == 0x00 || (nx >= 0xD0 && nx <= 0xD7) || nx == 0xFF) {
+						e += nx == 0xFF ? 1 : 2;
+						continue;
+					}
+					break;
+				}
+				if (e + 1 >= len)
+					e = len;
+				sc.end = e;
+				H->scans.push_back(sc);
+				if (H->scans.size() > 256) {
+					error(domain, "too many scans");
+					return -1;
+				}
+				if (e >= len)
+					return 0; /* no EOI: take what is there, as jdinput.c does with a warning */
+				p = e;
+				continue;
+			}
 			if (ns != H->ncomp) {
-				if (!H->progressive)
-					error(domain, "non-interleaved scans are not supported on the device path");
-				else
-					error(domain, "progressive JPEG is not supported on the device path");
+				error(domain, "non-interleaved scans are not supported on the device path");
 				return -1;
 			}
 			for (int i = 0; i < ns; i++) {
@@ -314,9 +400,23 @@ parse_jpeg(const char *domain, const unsigned char *d, size_t len, JpegHeader *H
 int
 plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp], int up[kMaxComp][2])
 {
-	if (H.progressive || H.arithmetic) {
-		error(domain, "%s JPEG is not supported on the device path", H.progressive ? "progressive" : "arithmetic-coded");
+	if (H.arithmetic) {
+		error(domain, "arithmetic-coded JPEG is not supported on the device path");
 		return -1;
+	}
+	for (const JpegScan &sc : H.scans) {
+		/* T.81 G.1.1.1.1: DC scans (Ss = 0) have Se = 0 and may interleave; AC scans have one component */
+		const bool dc = sc.Ss == 0;
+		if (sc.Ss > sc.Se || sc.Se > 63 || (dc && sc.Se != 0) || (!dc && sc.ns != 1) || sc.Al > 13 || (sc.Ah && sc.Ah != sc.Al + 1)) {
+			error(domain, "progressive scan parameters (Ss %d, Se %d, Ah %d, Al %d, %d components) not supported on the device path", sc.Ss, sc.Se,
+				sc.Ah, sc.Al, sc.ns);
+			return -1;
+		}
+		for (int i = 0; i < sc.ns; i++)
+			if ((dc && !sc.Ah && (sc.td[i] > 3 || !sc.hset[0][sc.td[i]])) || (!dc && (sc.ta[i] > 3 || !sc.hset[1][sc.ta[i]]))) {
+				error(domain, "progressive scan names a Huffman table that was not defined");
+				return -1;
+			}
 	}
 	if (H.precision != 8) {
 		error(domain, "%d-bit JPEG is not supported on the device path", H.precision);
@@ -351,7 +451,8 @@ plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp
 	const int m = 8 / shrink;
 	for (int c = 0; c < H.ncomp; c++) {
 		const JpegComp &k = H.comp[c];
-		if (k.h < 1 || k.v < 1 || k.h > 2 || k.v > 2 || k.tq > 3 || !H.qt_set[k.tq] || k.td > 3 || k.ta > 3 || !H.hset[0][k.td] || !H.hset[1][k.ta]) {
+		if (k.h < 1 || k.v < 1 || k.h > 2 || k.v > 2 || k.tq > 3 || !H.qt_set[k.tq] ||
+			(!H.progressive && (k.td > 3 || k.ta > 3 || !H.hset[0][k.td] || !H.hset[1][k.ta]))) {
 			error(domain, "JPEG component %d: unsupported sampling or missing table", c);
 			return -1;
 		}
@@ -621,6 +722,150 @@ decode_interval(const McuLayout &M, const HuffDev *huff, const unsigned char *zz
 			blk = coef_pool + M.plane[bi] + (long long) my * M.step_y[bi] + (long long) mx * M.step_x[bi];
 		}
 	}
+}
+
+/* ------------------------------------------------------------------ progressive scans (T.81 G.1.2, what jdphuff.c implements)
+ *
+ * A progressive frame sends its coefficients in several scans: the DC terms first (possibly all components interleaved),
+ * then bands Ss..Se of the AC terms one component at a time, each possibly in two or more precision steps (successive
+ * approximation: a first scan carries the bits above Al, refinement scans one more bit each).  Scans must be applied in
+ * order -- a refinement scan reads the coefficients the earlier ones left -- but inside a scan only the end-of-band run
+ * and the DC predictors chain blocks together, and both restart at a restart interval: one thread per (frame,
+ * interval), one launch per scan index.  What comes out is the same coefficient planes the baseline path fills; the
+ * inverse DCTs and everything after are shared.
+ */
+HD int
+br_get_bits(BitReader &b, int n)
+{
+	if (n == 0)
+		return 0;
+	br_fill(b);
+	const int v = br_peek(b, n);
+	br_skip(b, n);
+	return v;
+}
+
+/* one block of an AC refinement scan (jdphuff.c decode_mcu_AC_refine) */
+HD int
+prog_ac_refine(BitReader &b, const HuffDev *ac, const unsigned char *zz, short *blk, int Ss, int Se, int Al, unsigned &eobrun)
+{
+	const int p1 = 1 << Al, m1 = -p1;
+	int k = Ss;
+	if (eobrun == 0) {
+		for (; k <= Se; k++) {
+			br_fill(b);
+			const int sym = huff_decode(b, ac);
+			if (sym < 0)
+				return -1;
+			int r = sym >> 4, sv = sym & 15;
+			if (sv) {
+				/* a newly non-zero coefficient: its sign now, its position after the r still-zero ones */
+				sv = br_get_bits(b, 1) ? p1 : m1;
+			}
+			else if (r != 15) {
+				eobrun = 1u << r;
+				if (r)
+					eobrun += (unsigned) br_get_bits(b, r);
+				break; /* the rest of the block by the end-of-band logic below */
+			}
+			/* over already non-zero coefficients (a correction bit each) and r zero ones */
+			do {
+				short *c = blk + zz[k];
+				if (*c != 0) {
+					if (br_get_bits(b, 1) && (*c & p1) == 0)
+						*c = (short) (*c >= 0 ? *c + p1 : *c + m1);
+				}
+				else if (--r < 0)
+					break;
+				k++;
+			} while (k <= Se);
+			if (sv) {
+				if (k > 63)
+					return -1;
+				blk[zz[k]] = (short) sv;
+			}
+		}
+	}
+	if (eobrun > 0) {
+		/* the band's remaining positions: a correction bit for every coefficient that is already non-zero */
+		for (; k <= Se; k++) {
+			short *c = blk + zz[k];
+			if (*c != 0 && br_get_bits(b, 1) && (*c & p1) == 0)
+				*c = (short) (*c >= 0 ? *c + p1 : *c + m1);
+		}
+		eobrun--;
+	}
+	return 0;
+}
+
+/* the units [u0, u1) of one restart interval of one scan */
+HD int
+decode_scan_interval(const JpegFrameDev &F, const ScanDev &S, const HuffDev *huff, const unsigned char *zz, const unsigned char *base, unsigned pos,
+	unsigned end, int u0, int u1, short *coef_pool)
+{
+	BitReader b;
+	br_init(b, base, pos * 8u, end);
+	int pred[3] = {0, 0, 0};
+	unsigned eobrun = 0;
+	const bool interleaved = S.ns > 1 || F.ncomp == 1;
+	for (int u = u0; u < u1; u++) {
+		const int uy = u / S.units_x, ux = u - uy * S.units_x;
+		for (int i = 0; i < S.ns; i++) {
+			const int c = S.comp[i];
+			const int nh = interleaved ? F.h[c] : 1, nv = interleaved ? F.v[c] : 1;
+			for (int by = 0; by < nv; by++)
+				for (int bx = 0; bx < nh; bx++) {
+					short *blk = coef_pool + F.coef_off[c] + ((size_t) (uy * nv + by) * F.blocks_x[c] + (size_t) (ux * nh + bx)) * 64;
+					if (S.Ss == 0) {
+						if (S.Ah == 0) {
+							/* DC, first pass (decode_mcu_DC_first) */
+							br_fill(b);
+							const int sym = huff_decode(b, huff + S.dc_tab[i]);
+							if (sym < 0 || sym > 11)
+								return -1;
+							br_fill(b);
+							pred[i] += br_receive_extend(b, sym);
+							blk[0] = (short) (pred[i] * (1 << S.Al));
+						}
+						else if (br_get_bits(b, 1)) /* DC refinement: one bit per block */
+							blk[0] = (short) (blk[0] | (1 << S.Al));
+					}
+					else if (S.Ah == 0) {
+						/* AC, first pass (decode_mcu_AC_first) */
+						if (eobrun > 0) {
+							eobrun--;
+							continue;
+						}
+						for (int k = S.Ss; k <= S.Se; k++) {
+							br_fill(b);
+							const int sym = huff_decode(b, huff + S.ac_tab);
+							if (sym < 0)
+								return -1;
+							const int r = sym >> 4, sv = sym & 15;
+							if (sv) {
+								k += r;
+								if (k > 63)
+									return -1;
+								br_fill(b);
+								blk[zz[k]] = (short) (br_receive_extend(b, sv) * (1 << S.Al));
+							}
+							else if (r == 15)
+								k += 15;
+							else {
+								eobrun = 1u << r;
+								if (r)
+									eobrun += (unsigned) br_get_bits(b, r);
+								eobrun--;
+								break;
+							}
+						}
+					}
+					else if (prog_ac_refine(b, huff + S.ac_tab, zz, blk, S.Ss, S.Se, S.Al, eobrun))
+						return -1;
+				}
+		}
+	}
+	return 0;
 }
 
 /* ------------------------------------------------------------------ self-synchronising decode
@@ -1225,8 +1470,8 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 {
 	__shared__ McuLayout M;
 	const JpegFrameDev &F = frames[blockIdx.y];
-	if (F.sync)
-		return; /* the subsequence kernels decode this frame */
+	if (F.sync || F.progressive)
+		return; /* the subsequence / progressive kernels decode this frame */
 	if (threadIdx.x == 0)
 		mcu_layout(F, M);
 	__syncthreads();
@@ -1239,6 +1484,25 @@ jpeg_huffman_kernel(const JpegFrameDev *__restrict__ frames, const HuffDev *__re
 	const int per = F.restart_interval > 0 ? F.restart_interval : total;
 	const int mcu0 = i * per, mcu1 = min(total, mcu0 + per);
 	if (decode_interval(M, huff + F.huff_base, d_zigzag, base, off[i], off[i + 1], mcu0, mcu1, coef))
+		atomicOr(status + blockIdx.y, 1);
+}
+
+/* progressive frames: scan number `scan` of every frame, one thread per restart interval; blockIdx.y = frame */
+__global__ void __launch_bounds__(kHuffThreads)
+jpeg_progressive_kernel(const JpegFrameDev *__restrict__ frames, const ScanDev *__restrict__ scans, const HuffDev *__restrict__ huff,
+	const unsigned char *__restrict__ bytes, const unsigned *__restrict__ offsets, short *__restrict__ coef, int *__restrict__ status, int scan)
+{
+	const JpegFrameDev &F = frames[blockIdx.y];
+	if (!F.progressive || scan >= F.n_scans)
+		return;
+	const ScanDev &S = scans[F.scan_base + scan];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= S.n_intervals)
+		return;
+	const unsigned *off = offsets + S.interval_off;
+	const int total = S.units_x * S.units_y;
+	const int per = S.restart_interval > 0 ? S.restart_interval : total;
+	if (decode_scan_interval(F, S, huff + S.huff_base, d_zigzag, bytes + F.data_off, off[i], off[i + 1], i * per, min(total, (i + 1) * per), coef))
 		atomicOr(status + blockIdx.y, 1);
 }
 
@@ -1427,6 +1691,15 @@ struct FramePrep {
 	const unsigned char *src = nullptr;
 	size_t src_len = 0, coef_count = 0, plane_bytes = 0;
 	int bands = 0;
+	/* progressive frames: one record per scan */
+	struct ScanPrep {
+		ScanDev S;
+		HuffDev huff[4];
+		const unsigned char *src;
+		size_t len;
+	};
+	std::vector<ScanPrep> scans;
+	size_t stage_bytes = 0, stage_ints = 0, stage_huffs = 8; /* what the frame takes of the chunk's pools */
 	std::string err;
 };
 
@@ -1518,6 +1791,58 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 		for (int th = 0; th < 4; th++)
 			if (H.hset[tc][th])
 				build_huff(H.hcount[tc][th], H.hsym[tc][th], &P->huff[4 * tc + th]);
+	if (H.progressive) {
+		F.progressive = 1;
+		F.n_scans = (int) H.scans.size();
+		F.n_intervals = 0;
+		P->scans.resize(H.scans.size());
+		P->stage_bytes = P->stage_ints = 0;
+		P->stage_huffs = 4 * H.scans.size();
+		P->src = nullptr;
+		P->src_len = 0;
+		for (size_t j = 0; j < H.scans.size(); j++) {
+			const JpegScan &sc = H.scans[j];
+			FramePrep::ScanPrep &sp = P->scans[j];
+			memset(&sp.S, 0, sizeof(sp.S));
+			memset(sp.huff, 0, sizeof(sp.huff));
+			sp.S.ns = sc.ns;
+			for (int i = 0; i < sc.ns; i++) {
+				sp.S.comp[i] = sc.ci[i];
+				sp.S.dc_tab[i] = i; /* the scan's own tables: slots 0..2 DC per scan component, slot 3 AC */
+				if (sc.Ss == 0 && sc.Ah == 0)
+					build_huff(sc.hcount[0][sc.td[i]], sc.hsym[0][sc.td[i]], &sp.huff[i]);
+			}
+			sp.S.ac_tab = 3;
+			if (sc.Ss > 0)
+				build_huff(sc.hcount[1][sc.ta[0]], sc.hsym[1][sc.ta[0]], &sp.huff[3]);
+			sp.S.Ss = sc.Ss;
+			sp.S.Se = sc.Se;
+			sp.S.Ah = sc.Ah;
+			sp.S.Al = sc.Al;
+			sp.S.restart_interval = sc.restart_interval;
+			if (sc.ns > 1 || H.ncomp == 1) {
+				sp.S.units_x = F.mcus_x;
+				sp.S.units_y = F.mcus_y;
+			}
+			else {
+				/* a one-component scan of a multi-component frame walks the component's own block grid (T.81 A.2.2) */
+				const int c = sc.ci[0];
+				sp.S.units_x = (int) ((((long long) H.width * H.comp[c].h + H.max_h - 1) / H.max_h + 7) / 8);
+				sp.S.units_y = (int) ((((long long) H.height * H.comp[c].v + H.max_v - 1) / H.max_v + 7) / 8);
+			}
+			const int units = sp.S.units_x * sp.S.units_y;
+			sp.S.n_intervals = sc.restart_interval > 0 ? (units + sc.restart_interval - 1) / sc.restart_interval : 1;
+			sp.src = d + sc.off;
+			sp.len = sc.end - sc.off;
+			if (sp.len >= 0xffffff00u || P->stage_bytes >= 0xf0000000u) {
+				error(domain, "entropy-coded segment too large");
+				return -1;
+			}
+			P->stage_bytes += ((sp.len + 15) & ~(size_t) 15) + 16;
+			P->stage_ints += (size_t) sp.S.n_intervals + 1;
+		}
+		return 0;
+	}
 	/* restart intervals: RSTn markers are byte-aligned FFD0..FFD7 inside the entropy-coded segment */
 	const int total = F.mcus_x * F.mcus_y;
 	F.restart_interval = H.restart_interval;
@@ -1531,6 +1856,9 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
 	F.n_intervals = n_int;
 	P->src = d + H.scan_off;
 	P->src_len = seg;
+	P->stage_bytes = ((seg + 15) & ~(size_t) 15) + 16;
+	P->stage_ints = (size_t) n_int + 1;
+	P->stage_huffs = 8;
 	return 0;
 }
 
@@ -1541,11 +1869,11 @@ frame_prep(const char *domain, const unsigned char *d, size_t len, int shrink, F
  * into pinned memory they had to do anyway.
  */
 size_t
-destuff_scan(const unsigned char *src, size_t len, unsigned char *dst, unsigned *offsets, int want)
+destuff_scan(const unsigned char *src, size_t len, unsigned char *dst, unsigned *offsets, int want, unsigned base = 0)
 {
 	size_t p = 0, o = 0;
 	int found = 1;
-	offsets[0] = 0;
+	offsets[0] = base;
 	while (p < len) {
 		const unsigned char *q = (const unsigned char *) memchr(src + p, 0xFF, len - p);
 		if (!q) {
@@ -1566,7 +1894,7 @@ destuff_scan(const unsigned char *src, size_t len, unsigned char *dst, unsigned 
 			if (nx >= 0xD0 && nx <= 0xD7) {
 				if (found >= want)
 					return (size_t) -1;
-				offsets[found++] = (unsigned) o;
+				offsets[found++] = base + (unsigned) o;
 				p = i + 2;
 			}
 			else if (nx == 0xFF)
@@ -1577,7 +1905,7 @@ destuff_scan(const unsigned char *src, size_t len, unsigned char *dst, unsigned 
 	}
 	if (found != want)
 		return (size_t) -1;
-	offsets[want] = (unsigned) o;
+	offsets[want] = base + (unsigned) o;
 	return o;
 }
 
@@ -1801,7 +2129,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 	 */
 	bool any_plain_single = false;
 	for (int i = 0; i < n; i++)
-		if (prep[i].F.n_intervals == 1 && !(sub_bytes > 0 && prep[i].src_len >= sync_min_bytes && prep[i].src_len / sub_bytes >= 8))
+		if (!prep[i].F.progressive && prep[i].F.n_intervals == 1 &&
+			!(sub_bytes > 0 && prep[i].src_len >= sync_min_bytes && prep[i].src_len / sub_bytes >= 8))
 			any_plain_single = true;
 	int chunk = (max_int >= 32 || !any_plain_single) ? std::max(64, std::min(256, (n + 3) / 4)) : n;
 	if (const char *e = getenv("VB200_JPEG_CHUNK"))
@@ -1831,7 +2160,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		int rc = 0, c0 = 0, cn = 0, max_intervals = 0, max_mcus = 0;
 		unsigned max_subs = 0;
 		size_t total = 0, off_h = 0, off_o = 0, off_b = 0, coef_total = 0, sync_total = 0, plane_total = 0;
-		int max_blocks = 0;
+		int max_blocks = 0, max_scans = 0, max_scan_intervals = 0;
+		size_t off_s = 0;
 		std::string err;
 	};
 	int device = 0;
@@ -1848,17 +2178,25 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		/* layout of the chunk's block */
 		std::vector<size_t> data_off(cn), int_off(cn), coef_off(cn);
 		std::vector<unsigned> sync_off(cn, 0), sync_cap(cn, 0);
-		std::vector<size_t> plane_off(cn, 0);
-		size_t bytes_total = 0, ints_total = 0, coef_total = 0, sync_total = 0, plane_total = 0;
+		std::vector<size_t> plane_off(cn, 0), huff_off(cn, 0), scan_off(cn, 0);
+		size_t bytes_total = 0, ints_total = 0, coef_total = 0, sync_total = 0, plane_total = 0, huffs_total = 0, scans_total = 0;
+		int max_scans = 0, max_scan_intervals = 0;
 		int max_blocks = 0;
 		int max_intervals = 0, max_mcus = 0;
 		unsigned max_subs = 0;
 		for (int i = 0; i < cn; i++) {
 			const FramePrep &fp = prep[c0 + i];
 			data_off[i] = bytes_total;
-			bytes_total += ((fp.src_len + 15) & ~(size_t) 15) + 16;
+			bytes_total += fp.stage_bytes;
 			int_off[i] = ints_total;
-			ints_total += (size_t) fp.F.n_intervals + 1;
+			ints_total += fp.stage_ints;
+			huff_off[i] = huffs_total;
+			huffs_total += fp.stage_huffs;
+			scan_off[i] = scans_total;
+			scans_total += fp.scans.size();
+			max_scans = std::max(max_scans, (int) fp.scans.size());
+			for (const auto &sp : fp.scans)
+				max_scan_intervals = std::max(max_scan_intervals, sp.S.n_intervals);
 			coef_off[i] = coef_total;
 			coef_total += fp.coef_count;
 			max_intervals = std::max(max_intervals, fp.F.n_intervals);
@@ -1867,15 +2205,16 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			plane_total += fp.plane_bytes;
 			if (fp.F.planar)
 				max_blocks = std::max(max_blocks, fp.F.mcus_x * fp.F.mcus_y * fp.F.blocks_per_mcu);
-			if (fp.F.n_intervals == 1 && sub_bytes > 0 && fp.src_len >= sync_min_bytes && fp.src_len / sub_bytes >= 8) {
+			if (!fp.F.progressive && fp.F.n_intervals == 1 && sub_bytes > 0 && fp.src_len >= sync_min_bytes && fp.src_len / sub_bytes >= 8) {
 				sync_off[i] = (unsigned) sync_total;
 				sync_cap[i] = (unsigned) ((fp.src_len + sub_bytes - 1) / sub_bytes + 1);
 				sync_total += sync_cap[i];
 				max_subs = std::max(max_subs, sync_cap[i]);
 			}
 		}
-		const size_t sz_f = (size_t) cn * sizeof(JpegFrameDev), sz_h = (size_t) cn * 8 * sizeof(HuffDev);
-		const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_o = off_h + ((sz_h + 15) & ~(size_t) 15);
+		const size_t sz_f = (size_t) cn * sizeof(JpegFrameDev), sz_h = huffs_total * sizeof(HuffDev), sz_s = scans_total * sizeof(ScanDev);
+		const size_t off_h = (sz_f + 15) & ~(size_t) 15, off_s = off_h + ((sz_h + 15) & ~(size_t) 15);
+		const size_t off_o = off_s + ((sz_s + 15) & ~(size_t) 15);
 		const size_t off_b = off_o + ((ints_total * sizeof(unsigned) + 15) & ~(size_t) 15);
 		const size_t total = off_b + bytes_total + 16;
 		if (trace)
@@ -1907,6 +2246,39 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		parallel_for(cn, host_workers(), [&](int i) {
 			const FramePrep &fp = prep[c0 + i];
 			unsigned char *dst = (unsigned char *) hst + off_b + data_off[i];
+			if (fp.F.progressive) {
+				/* every scan's segment unstuffed one after the other; the scan records and their tables beside them */
+				JpegFrameDev F = fp.F;
+				F.data_off = data_off[i];
+				for (int c = 0; c < F.ncomp; c++)
+					F.coef_off[c] += coef_off[i];
+				F.huff_base = (int) huff_off[i];
+				F.scan_base = (unsigned) scan_off[i];
+				F.sync = 0;
+				for (int c = 0; c < F.ncomp; c++)
+					F.plane_off[c] += plane_off[i];
+				size_t pos = 0, ipos = int_off[i];
+				for (size_t j = 0; j < fp.scans.size(); j++) {
+					const FramePrep::ScanPrep &sp = fp.scans[j];
+					const size_t clean = destuff_scan(sp.src, sp.len, dst + pos, (unsigned *) (hst + off_o) + ipos, sp.S.n_intervals, (unsigned) pos);
+					if (clean == (size_t) -1) {
+						int none = -1;
+						bad_frame.compare_exchange_strong(none, c0 + i);
+						return;
+					}
+					const size_t room = ((sp.len + 15) & ~(size_t) 15) + 16;
+					memset(dst + pos + clean, 0, room - clean);
+					ScanDev S = sp.S;
+					S.interval_off = (unsigned) ipos;
+					S.huff_base = (int) (huff_off[i] + 4 * j);
+					memcpy(hst + off_s + (scan_off[i] + j) * sizeof(ScanDev), &S, sizeof(S));
+					memcpy(hst + off_h + (huff_off[i] + 4 * j) * sizeof(HuffDev), sp.huff, 4 * sizeof(HuffDev));
+					pos += room;
+					ipos += (size_t) sp.S.n_intervals + 1;
+				}
+				memcpy(hst + (size_t) i * sizeof(JpegFrameDev), &F, sizeof(F));
+				return;
+			}
 			const size_t clean = destuff_scan(fp.src, fp.src_len, dst, (unsigned *) (hst + off_o) + int_off[i], fp.F.n_intervals);
 			if (clean == (size_t) -1) {
 				int none = -1;
@@ -1918,7 +2290,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			F.interval_off = int_off[i];
 			for (int c = 0; c < F.ncomp; c++)
 				F.coef_off[c] += coef_off[i];
-			F.huff_base = 8 * i;
+			F.huff_base = (int) huff_off[i];
 			F.clean_len = (unsigned) clean;
 			F.sync = sync_cap[i] > 0;
 			F.sync_off = sync_off[i];
@@ -1926,7 +2298,7 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			for (int c = 0; c < F.ncomp; c++)
 				F.plane_off[c] += plane_off[i];
 			memcpy(hst + (size_t) i * sizeof(JpegFrameDev), &F, sizeof(F));
-			memcpy(hst + off_h + (size_t) i * 8 * sizeof(HuffDev), fp.huff, 8 * sizeof(HuffDev));
+			memcpy(hst + off_h + huff_off[i] * sizeof(HuffDev), fp.huff, 8 * sizeof(HuffDev));
 			memset(dst + clean, 0, (((fp.src_len + 15) & ~(size_t) 15) + 16) - clean); /* the reader's look-ahead past the end */
 		});
 		if (bad_frame.load() >= 0) {
@@ -1947,6 +2319,9 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		R.sync_total = sync_total;
 		R.plane_total = plane_total;
 		R.max_blocks = max_blocks;
+		R.max_scans = max_scans;
+		R.max_scan_intervals = max_scan_intervals;
+		R.off_s = off_s;
 		return R;
 	};
 
@@ -1975,7 +2350,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 		const unsigned max_subs = cur.max_subs;
 		const size_t total = cur.total, off_h = cur.off_h, off_o = cur.off_o, off_b = cur.off_b, coef_total = cur.coef_total,
 					 sync_total = cur.sync_total, plane_total = cur.plane_total;
-		const int max_blocks = cur.max_blocks;
+		const int max_blocks = cur.max_blocks, max_scans = cur.max_scans, max_scan_intervals = cur.max_scan_intervals;
+		const size_t off_s = cur.off_s;
 		JpegSlot &sl = P.slot[k % kJpegSlots];
 		char *hst = (char *) sl.pinned;
 		cudaStream_t st = sl.stream;
@@ -2065,6 +2441,20 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 				count_launch();
 				count_launch();
 				count_launch();
+			}
+			if (max_scans > 0) {
+				/* progressive frames: their scans in order, scan j of every frame in one launch */
+				const ScanDev *dS = (const ScanDev *) ((char *) dev + off_s);
+				for (int j = 0; j < max_scans; j++) {
+					jpeg_progressive_kernel<<<dim3((max_scan_intervals + kHuffThreads - 1) / kHuffThreads, cn), kHuffThreads, 0, st>>>(dF, dS, dH, dB, dO,
+						(short *) coef, status + c0, j);
+					count_launch();
+				}
+				cudaError_t ep = cudaGetLastError();
+				if (ep != cudaSuccess) {
+					rc = cuda_fail(domain, ep, "jpeg_progressive_kernel launch");
+					break;
+				}
 			}
 			/* CTA width: one interval per warp while the chunk has fewer intervals than the machine has CTA slots */
 			int ht = 1;
@@ -2164,6 +2554,25 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 		return 0;
 	const JpegFrameDev &F = P.F;
 	std::vector<short> coef(P.coef_count, 0);
+	if (F.progressive) {
+		for (const FramePrep::ScanPrep &sp : P.scans) {
+			std::vector<unsigned> pw((sp.len + 32) / 4 + 1, 0);
+			std::vector<unsigned> offs(sp.S.n_intervals + 1);
+			if (destuff_scan(sp.src, sp.len, (unsigned char *) pw.data(), offs.data(), sp.S.n_intervals) == (size_t) -1) {
+				error(domain, "restart markers do not match the restart interval");
+				return -1;
+			}
+			const int total = sp.S.units_x * sp.S.units_y;
+			const int per = sp.S.restart_interval > 0 ? sp.S.restart_interval : total;
+			for (int i = 0; i < sp.S.n_intervals; i++)
+				if (decode_scan_interval(F, sp.S, sp.huff, kZigzag, (const unsigned char *) pw.data(), offs[i], offs[i + 1], i * per,
+						std::min(total, (i + 1) * per), coef.data())) {
+					error(domain, "corrupt JPEG data: bad Huffman code");
+					return -1;
+				}
+		}
+	}
+	else {
 	/* unstuffed, aligned, zero-padded: as the pump stages it */
 	std::vector<unsigned> padded_w((P.src_len + 32) / 4 + 1, 0);
 	unsigned char *padded = (unsigned char *) padded_w.data();
@@ -2227,6 +2636,7 @@ host_jpeg_decode(const char *domain, const void *buf, size_t len, int shrink, un
 				error(domain, "corrupt JPEG data: bad Huffman code");
 				return -1;
 			}
+	}
 	if (F.planar) {
 		std::vector<unsigned char> planes(P.plane_bytes);
 		for (int c = 0; c < F.ncomp; c++)

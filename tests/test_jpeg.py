@@ -14,6 +14,9 @@ import numpy as np
 import pytest
 
 PIL = pytest.importorskip("PIL.Image")
+from PIL import ImageFile as _ImageFile  # noqa: E402
+
+_ImageFile.MAXBLOCK = 1 << 24   # Pillow's encoder buffer: progressive / optimised saves at Q 100 outgrow the default
 
 
 def synth(h, w, seed=0, grey=False):
@@ -73,6 +76,26 @@ def test_host_twin_matches_libjpeg_turbo(vbl, size, sub):
             assert got.shape == want.shape and np.array_equal(got, want), (size, sub, quality, shrink)
 
 
+@pytest.mark.parametrize("size", [(64, 64), (67, 93), (256, 200), (17, 300), (8, 3), (33, 5)], ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("sub", [2, 1, 0], ids=["420", "422", "444"])
+def test_progressive_host_twin_matches_libjpeg_turbo(vbl, size, sub):
+    """progressive frames (T.81 G: DC scans, AC bands per component, successive approximation with refinement scans) end in
+    the same coefficients, so the same pixels, as libjpeg-turbo decodes -- at every shrink"""
+    h, w = size
+    a = synth(h, w, seed=h + 11 * w)
+    for quality in (30, 85, 100):
+        for kw in ({}, {"restart_marker_rows": 1}):
+            d = encode(a, quality, sub, progressive=True, **kw)
+            for shrink in (8, 4, 2, 1):
+                if min(h, w) // shrink < 1:
+                    continue
+                got = vbl.jpeg_decode_host_twin(d, shrink)
+                want = turbo_decode(d, shrink)
+                assert got.shape == want.shape and np.array_equal(got, want), (size, sub, quality, kw, shrink)
+    g = encode(synth(h, w, seed=5, grey=True), 80, progressive=True)
+    assert np.array_equal(vbl.jpeg_decode_host_twin(g, 1), turbo_decode(g, 1))
+
+
 def test_greyscale_restart_markers_and_optimised_tables(vbl):
     g = synth(150, 203, seed=3, grey=True)
     d = encode(g, 90)
@@ -102,8 +125,6 @@ def test_extreme_coefficients(vbl):
 
 def test_declined_streams(vbl):
     a = synth(64, 64)
-    with pytest.raises(vbl.Error, match="progressive"):
-        vbl.jpeg_decode_host_twin(encode(a, progressive=True), 2)
     ycck = io.BytesIO()
     PIL.fromarray(np.dstack([a, a[..., 0]]), "CMYK").save(ycck, "JPEG")
     with pytest.raises(vbl.Error, match="component"):
@@ -186,8 +207,10 @@ def test_gpu_batch_decode_matches_libjpeg_turbo(vbl):
     vb.init(0)
     for (h, w) in ((256, 320), (203, 301), (1024, 1024)):
         for sub in (2, 1, 0):
-            for kw in ({}, {"restart_marker_rows": 1}, {"optimize": True}):
+            for kw in ({}, {"restart_marker_rows": 1}, {"optimize": True}, {"progressive": True}, {"progressive": True, "restart_marker_rows": 2}):
                 streams = [encode(synth(h, w, seed=i), (95, 75, 40)[i], sub, **kw) for i in range(3)]
+                if kw.get("progressive"):
+                    streams.append(encode(synth(h, w, seed=9), 85, sub))       # a baseline frame in the same batch
                 for shrink in (8, 4, 2, 1):
                     got = vb.jpeg_decode_batch(streams, shrink)
                     want = np.stack([turbo_decode(s, shrink) for s in streams])
