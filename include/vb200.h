@@ -387,12 +387,13 @@ int vb200_debug_mma_tables(int in_size, double shrink, int rect_size, int *int_s
  * vips_jpegload_buffer(buf, len, &out, "shrink", shrink) (foreign/jpeg2vips.c:532-538, 631-640: scale_num = 1,
  * scale_denom = shrink, output cropped to floor(size / shrink)) with the decoder on the device: the compressed
  * bytes are all that crosses PCIe.  libjpeg(-turbo) itself is a third-party dependency outside the reference
- * tree; its algorithm for the reference's configuration (JDCT_ISLOW, 8-bit Huffman baseline / extended
- * sequential) is restated in csrc/jpeg.cu and pinned bit for bit to the libjpeg-turbo inside this image's Pillow
- * (tests/test_jpeg.py).  Decoded: greyscale, 4:4:4, 4:2:2 and 4:2:0 at shrink 1 / 2 / 4 / 8 (where libjpeg's upsampler has
- * work left -- 4:2:0 at full size, 4:2:2 -- its h2v2 / h2v1 "fancy" triangle filters, jdsample.c).  Progressive,
- * arithmetic, 12-bit, CMYK / RGB-coded and 4:4:0 / 4:1:1 streams return -1 (host loader).  Streams with restart markers
- * decode one interval per GPU thread, streams without them by self-synchronising subsequences.
+ * tree; its algorithm for the reference's configuration (JDCT_ISLOW, 8-bit Huffman, sequential and progressive)
+ * is restated in csrc/jpeg.cu and pinned bit for bit to the libjpeg-turbo inside this image's Pillow
+ * (tests/test_jpeg.py).  Decoded: 8-bit Huffman streams, baseline / extended sequential and progressive, greyscale or
+ * YCbCr at 4:4:4, 4:2:2 and 4:2:0, at shrink 1 / 2 / 4 / 8 (where libjpeg's upsampler has work left -- 4:2:0 at full
+ * size, 4:2:2 -- its h2v2 / h2v1 "fancy" triangle filters, jdsample.c).  Arithmetic-coded, 12-bit, CMYK / RGB-coded and
+ * 4:4:0 / 4:1:1 streams return -1 (host loader).  Baseline streams with restart markers decode one interval per GPU
+ * thread, those without by self-synchronising subsequences; progressive streams one scan after the other.
  *
  * vb200_jpeg_decode_batch: n streams of ONE output geometry -> out[n][height][width][bands] uchar (bands 1 or 3),
  *   out in host or device memory (out_location VB200_HOST / VB200_DEVICE); out = NULL only reports the geometry.

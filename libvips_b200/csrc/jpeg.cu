@@ -16,16 +16,17 @@
  * Parity is pinned against libjpeg-turbo itself as shipped inside this image's Pillow wheel (tests/test_jpeg.py:
  * PIL's draft mode = scale_denom; bit for bit).
  *
- * Scope: 8-bit Huffman baseline / extended-sequential streams, greyscale or YCbCr at 4:4:4, 4:2:2 or 4:2:0, shrink 1 / 2 /
- * 4 / 8.  Where jdmaster.c's DCT scaling leaves the upsampler nothing to do (greyscale, 4:4:4, 4:2:0 at 2 / 4 / 8: what a
+ * Scope: 8-bit Huffman streams -- baseline, extended sequential and progressive --, greyscale or YCbCr at 4:4:4, 4:2:2 or
+ * 4:2:0, shrink 1 / 2 / 4 / 8.  Where jdmaster.c's DCT scaling leaves the upsampler nothing to do (greyscale, 4:4:4, 4:2:0 at 2 / 4 / 8: what a
  * thumbnail asks for) one kernel reconstructs an MCU to RGB; otherwise (4:2:0 at full size, 4:2:2) components go to planes
- * and jdsample.c's h2v2 / h2v1 "fancy" upsamplers run per output pixel.  Progressive, arithmetic, 12-bit, CMYK /
- * RGB-coded and 4:4:0 / 4:1:1 files return -1: the host keeps its loader for those.
+ * and jdsample.c's h2v2 / h2v1 "fancy" upsamplers run per output pixel.  Arithmetic, 12-bit, CMYK / RGB-coded and
+ * 4:4:0 / 4:1:1 files return -1: the host keeps its loader for those.
  *
  * Device pipeline per batch (no host decode; the compressed bytes are all that crosses PCIe, unstuffed by the host
  * workers while they copy them into pinned staging):
  *   jpeg_huffman_kernel   streams with restart markers: one thread per restart interval
  *   jpeg_sync_*_kernel    streams without: self-synchronising subsequences (see below), then a DC prefix sum
+ *   jpeg_progressive_kernel   progressive frames: one launch per scan index, one thread per (frame, restart interval)
  *   jpeg_idct_kernel      one thread per MCU: dequantise + scaled IDCT of its blocks, YCbCr -> RGB, store
  *   jpeg_idct_planes_kernel + jpeg_upsample_kernel   the same through component planes when the upsampler has work
  * The per-block / per-pixel code is __host__ __device__: vb200_debug_jpeg_decode runs the same code on the CPU so
