@@ -38,6 +38,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -433,6 +434,10 @@ plan_frame(const char *domain, const JpegHeader &H, int shrink, int dct[kMaxComp
 	}
 	if (H.width < 1 || H.height < 1) {
 		error(domain, "empty JPEG frame");
+		return -1;
+	}
+	if ((long long) H.width * H.height > (1LL << 28)) {
+		error(domain, "JPEG frame of %d x %d is too large for the device path", H.width, H.height);
 		return -1;
 	}
 	if (H.ncomp == 3) {
@@ -2776,7 +2781,13 @@ vb200_debug_jpeg_times(float *huffman_ms, float *idct_ms)
 extern "C" int
 vb200_debug_jpeg_decode(const void *buf, size_t len, int shrink, void *out, size_t out_bpl, int *width, int *height, int *bands)
 {
-	return host_jpeg_decode("jpeg_decode (host twin)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands, 0, 0, nullptr);
+	try {
+		return host_jpeg_decode("jpeg_decode (host twin)", buf, len, shrink, (unsigned char *) out, out_bpl, width, height, bands, 0, 0, nullptr);
+	}
+	catch (const std::exception &e) {
+		error("jpeg_decode (host twin)", "%s", e.what());
+		return -1;
+	}
 }
 
 /* the host twin of the self-synchronising path: subsequences of sub_bytes, max_passes passes; *passes_used = the last pass

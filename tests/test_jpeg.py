@@ -179,6 +179,36 @@ def test_self_synchronising_decode_host_twin(vbl):
         dec(d, 2, 128, 3)
 
 
+def test_damaged_streams_never_fault(vbl):
+    """bit flips, overwritten bytes and cuts anywhere in baseline / progressive / restart-marker streams: the decoder
+    returns pixels or an error (jpeg2vips.c's fail_on decides which the caller wants), it never reads or writes outside"""
+    rng = np.random.default_rng(123)
+    a = synth(96, 120, seed=1)
+    base = [encode(a, 70, sub, **kw) for kw in ({}, {"progressive": True}, {"restart_marker_rows": 1},
+                                                 {"progressive": True, "restart_marker_rows": 1}, {"optimize": True}) for sub in (2, 1, 0)]
+    decoded = rejected = 0
+    for it in range(900):
+        d = bytearray(base[it % len(base)])
+        for _ in range(int(rng.integers(1, 6))):
+            p = int(rng.integers(2, len(d)))
+            mode = rng.integers(0, 3)
+            if mode == 0:
+                d[p] ^= 1 << int(rng.integers(0, 8))
+            elif mode == 1:
+                d[p] = int(rng.integers(0, 256))
+            else:
+                d = d[:p] + d[p + int(rng.integers(1, 4)):]
+            if len(d) < 8:
+                break
+        try:
+            out = vbl.jpeg_decode_host_twin(bytes(d), int(rng.choice([1, 2, 4, 8])))
+            assert out.ndim == 3
+            decoded += 1
+        except vbl.Error:
+            rejected += 1
+    assert decoded > 100 and rejected > 100
+
+
 def test_jpegshrink_rule(vbl):
     """thumbnail.c:489-517: shrink >= 16 -> 8, >= 8 -> 4, >= 4 -> 2, else 1, on the common shrink"""
     assert vbl.thumbnail_jpegshrink(4096, 4096, 512) == 4
