@@ -456,14 +456,15 @@ def side_workload(args):
             cpu["kind"] = "reference"
         run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_icc_import + vips_icc_export (sRGB-like v4 profile) on 8192x8192",
             2 * n * n / 1e6, "Mpixels/s", cpu)
-    elif args.workload in ("thumbnail_jpeg", "thumbnail_jpeg_norestart"):
+    elif args.workload in ("thumbnail_jpeg", "thumbnail_jpeg_norestart", "thumbnail_jpeg_progressive"):
         # vips_thumbnail_buffer() of JPEG streams.  Host memory holds only the COMPRESSED frames; the
         # shrink-on-load decode (thumbnail.c:489-517 picks 1/4 for 4K -> 512) and the thumbnail run on the device.
         # End to end by construction: every step uploads its streams.  The CPU side is the reference's own recipe:
         # libjpeg-turbo (the one inside Pillow) at scale 1/4, then the thumbnail chain (oracle port), one frame per process.
         import io
         from PIL import Image
-        restart = args.workload == "thumbnail_jpeg"
+        restart = args.workload != "thumbnail_jpeg_norestart"
+        progressive = args.workload == "thumbnail_jpeg_progressive"
         F = max(1, min(args.frames, 1024))
         yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
         distinct = []
@@ -472,7 +473,9 @@ def side_workload(args):
             img = np.stack([128 + 100 * np.sin(xx / (37.0 + i) + yy / 91.0), 128 + 90 * np.cos(xx / 53.0 - yy / (29.0 + i)),
                             np.mod(xx * 3 + yy * 5, 256)], -1) + rng.normal(0, 10, (H, W, 3)).astype(np.float32)
             b = io.BytesIO()
-            Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(b, "JPEG", quality=85, subsampling=2,
+            from PIL import ImageFile
+            ImageFile.MAXBLOCK = 1 << 26
+            Image.fromarray(np.clip(img, 0, 255).astype(np.uint8)).save(b, "JPEG", quality=85, subsampling=2, progressive=progressive,
                                                                      **({"restart_marker_rows": 1} if restart else {}))
             distinct.append(b.getvalue())
         del yy, xx
@@ -531,7 +534,7 @@ def side_workload(args):
                    "sample": "%d frames: libjpeg-turbo (Pillow's) decode at scale 1/%d, then the oracle port of the thumbnail chain, "
                              "one frame per process" % (2 * threads, shrink)}
         label = ("vips_thumbnail_buffer: 4096x4096 4:2:0 JPEG streams (q85, %s) -> shrink-on-load 1/%d on the device -> 512x512%s, %d frames per step"
-                 % ("one restart interval per MCU row" if restart else "no restart markers", shrink,
+                 % (("progressive, " if progressive else "") + ("one restart interval per MCU row" if restart else "no restart markers"), shrink,
                     " -> vips_jpegsave_buffer (Q 75) on the device, streams to the host" if args.save else "", F))
         print(json.dumps({"metric": label, "value": F * MPIX_PER_FRAME / dt, "unit": "Mpixels/s (input pixels)", "n_gpus": 1,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "dtype": "u8",
@@ -564,7 +567,7 @@ def main():
                          "transparency decodes to: the kernel's opaque-stage fast path; a second line, never the headline)")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
-                         "--gpus N like the headline) | thumbnail_jpeg | thumbnail_jpeg_norestart (decode staging, SURVEY 8f) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
+                         "--gpus N like the headline) | thumbnail_jpeg | thumbnail_jpeg_norestart | thumbnail_jpeg_progressive (decode staging, SURVEY 8f; --save adds the encoder) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
