@@ -2466,7 +2466,8 @@ dev_jpeg_decode_batch(const char *domain, const void *const *bufs, const size_t 
 			int ht = 1;
 			while (ht < kHuffThreads && (long long) cn * ((max_intervals + ht - 1) / ht) > huff_cta_slots)
 				ht *= 2;
-			jpeg_huffman_kernel<<<dim3((max_intervals + ht - 1) / ht, cn), ht, 0, st>>>(dF, dH, dB, dO, (short *) coef, status + c0);
+			if (max_intervals > 0) /* a chunk of progressive frames only has no baseline interval */
+				jpeg_huffman_kernel<<<dim3((max_intervals + ht - 1) / ht, cn), ht, 0, st>>>(dF, dH, dB, dO, (short *) coef, status + c0);
 			cudaError_t e = cudaGetLastError();
 			if (e != cudaSuccess) {
 				rc = cuda_fail(domain, e, "jpeg_huffman_kernel launch");
