@@ -46,6 +46,10 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.ref_reduce_make_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.vips_reduce_get_points.argtypes = [C.c_int, C.c_double]
+        if hasattr(L, "ref_thumbnail_calculate_shrink"):
+            L.ref_thumbnail_calculate_shrink.restype = None
+            L.ref_thumbnail_calculate_shrink.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double)] * 2
+            L.ref_thumbnail_find_jpegshrink.argtypes = [C.c_int] * 7
         _LIB = L
     return _LIB
 
@@ -126,7 +130,7 @@ def thumbnail_image(a, width, height=None, size="both", tile=(0, 0)):
     """vips_thumbnail_build's pixel chain for an 8-bit sRGB / B_W image
     (thumbnail.c:827-902): [premultiply uchar] -> resize -> [unpremultiply uchar]."""
     h, w, b = a.shape
-    hs, vs, _, _ = pyoracle.thumbnail_size(w, h, width, height, size)
+    hs, vs = thumbnail_calculate_shrink(w, h, width, height, size)      # the reference's own arithmetic
     im = RefImage.from_array(a)
     premul = (b == 2 or b >= 4) and hs != 1.0 and vs != 1.0
     if premul:
@@ -158,3 +162,18 @@ def colour_table(which):
     p = L.ref_colour_table(which, C.byref(n))
     dt = np.int32 if which in (0, 2) else np.float32
     return np.frombuffer((C.c_uint8 * (n.value * 4)).from_address(p), dtype=dt).copy()
+
+
+# ------------------------------------------------------------------ vips_thumbnail's size arithmetic
+def thumbnail_calculate_shrink(w, h, width, height=None, size="both", crop=0):
+    """vips_thumbnail_calculate_shrink (thumbnail.c:412-466), the file-static function itself (ref_shim/ref_thumbnail.c)"""
+    hs, vs = C.c_double(), C.c_double()
+    lib().ref_thumbnail_calculate_shrink(w, h, width, width if height is None else height, pyoracle.SIZES[size], crop,
+                                         C.byref(hs), C.byref(vs))
+    return hs.value, vs.value
+
+
+def thumbnail_find_jpegshrink(w, h, width, height=None, size="both", crop=0, linear=False):
+    """vips_thumbnail_find_jpegshrink (thumbnail.c:490-517)"""
+    return int(lib().ref_thumbnail_find_jpegshrink(w, h, width, width if height is None else height, pyoracle.SIZES[size], crop,
+                                                   int(linear)))

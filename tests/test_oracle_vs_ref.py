@@ -8,6 +8,8 @@ must agree with it BIT FOR BIT, integer and float alike.
 
 Skipped (not failed) where _ref has not been built (no /root/reference).
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -138,6 +140,32 @@ def test_thumbnail_chain(shape, target, bands):
     rng = np.random.default_rng(8)
     a = rng.integers(0, 256, shape + (bands,), dtype=np.uint8)
     same(pyref.thumbnail_image(a, target), orc.thumbnail_image(a, target))
+
+
+def test_thumbnail_size_arithmetic():
+    """vips_thumbnail_calculate_shrink / _find_jpegshrink (thumbnail.c:412-517), the file-static functions themselves
+    (ref_shim/ref_thumbnail.c), against the oracle's restatement and the library's host-side rule"""
+    import libvips_b200 as vb
+    rng = np.random.default_rng(21)
+    dims = [(4096, 4096), (6000, 4000), (4000, 6000), (800, 600), (1, 1), (1, 5000), (5000, 1), (997, 761), (65535, 3), (33, 32)]
+    dims += [tuple(int(v) for v in rng.integers(1, 9000, 2)) for _ in range(300)]
+    targets = [(512, None), (1, None), (7, 9000), (9000, 7), (300, 300), (1024, 1025), (100000, 2)]
+    targets += [tuple(int(v) for v in rng.integers(1, 5000, 2)) for _ in range(40)]
+    n = 0
+    for (w, h) in dims:
+        for (tw, th) in targets:
+            for size in ("both", "up", "down", "force"):
+                hs, vs = pyref.thumbnail_calculate_shrink(w, h, tw, th, size)
+                # the shrinks are written before the resize geometry is worked out (which declines mixed up / down sizes)
+                ohs, ovs, ow, oh = C.c_double(), C.c_double(), C.c_int(), C.c_int()
+                orc.lib().orc_thumbnail_size(w, h, tw, tw if th is None else th, orc.SIZES[size], C.byref(ohs), C.byref(ovs),
+                                             C.byref(ow), C.byref(oh))
+                assert (hs, vs) == (ohs.value, ovs.value), (w, h, tw, th, size)
+                want = pyref.thumbnail_find_jpegshrink(w, h, tw, th, size)
+                assert vb.thumbnail_jpegshrink(w, h, tw, th, size) == want, (w, h, tw, th, size)
+                assert pyref.thumbnail_find_jpegshrink(w, h, tw, th, size, linear=True) == 1
+                n += 1
+    assert n > 50000
 
 
 def test_thumbnail_chain_tile_geometries():
