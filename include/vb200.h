@@ -186,7 +186,8 @@ int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int 
  * (sRGB2scRGB, scRGB2XYZ, XYZ2Lab, Lab2LabS, LabS2Lab, Lab2XYZ, XYZ2scRGB,
  * scRGB2sRGB, Lab2LCh, LCh2Lab, XYZ2Yxy, Yxy2XYZ) keeps its own arithmetic (the two LCh steps call
  * atan / cosf / sinf: float results within 1 ULP of the reference's glibc; everything else is exact).  Bands beyond the third are carried
- * as vips_colour_build does (colour.c:196-291).
+ * as vips_colour_build does (colour.c:196-291).  sRGB <-> RGB16 are the reference's two rows that are not colour
+ * conversions (colourspace.c:85-110, 372, 420): a shifting vips_cast over every band, alpha included (cast.c:137-164).
  */
 int vb200_colourspace(const VB200Image *in, VB200Image *out, int space);
 

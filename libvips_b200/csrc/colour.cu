@@ -325,6 +325,26 @@ cast_kernel(const void *__restrict__ in, size_t in_bpl, int in_fmt, void *__rest
 	store_elem(pout, out_fmt, x, cast_value(load_elem(pin, in_fmt, x), out_fmt));
 }
 
+/* sRGB <-> RGB16 are not colour conversions in the reference: vips_sRGB2RGB16 / vips_RGB162sRGB (colourspace.c:85-110)
+ * are vips_cast(..., "shift", TRUE) over EVERY band, extra bands included, and a re-tag.  cast.c:137-164: going down a
+ * right shift by the width difference; going up a left shift with the bottom bit copied into the new bits.
+ */
+__global__ void __launch_bounds__(256)
+shift_cast_kernel(const void *__restrict__ in, size_t in_bpl, void *__restrict__ out, size_t out_bpl, int up, int ne)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= ne)
+		return;
+	const char *pin = (const char *) in + (size_t) blockIdx.y * in_bpl;
+	char *pout = (char *) out + (size_t) blockIdx.y * out_bpl;
+	if (up) {
+		const unsigned v = ((const uint8_t *) pin)[x];
+		((uint16_t *) pout)[x] = (uint16_t) ((v << 8) | (((v & 1u) << 8) - (v & 1u)));
+	}
+	else
+		((uint8_t *) pout)[x] = (uint8_t) (((const uint16_t *) pin)[x] >> 8);
+}
+
 int
 space_format(int space)
 {
@@ -353,6 +373,9 @@ build_route(int from, int to, int *steps)
 		return -1;
 	if (from == to)
 		return 0;
+	/* colourspace.c:372, 420: these two rows are shifting casts, not steps of the route kernel (dev_colourspace) */
+	if ((from == sRGB && to == RGB16) || (from == RGB16 && to == sRGB))
+		return -1;
 	/* LCH hangs off LAB and YXY off XYZ in every row of the table (colourspace.c:226, 236, 242, 252, 275-290):
 	 * route to the hub, then one more step
 	 */
@@ -476,6 +499,26 @@ int
 dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space, cudaStream_t s)
 {
 	int steps[8];
+	const dim3 block(256);
+	const bool up = source_space == VB200_INTERPRETATION_sRGB && space == VB200_INTERPRETATION_RGB16;
+	const bool down = source_space == VB200_INTERPRETATION_RGB16 && space == VB200_INTERPRETATION_sRGB;
+	if (up || down) {
+		const int want = up ? VB200_FORMAT_UCHAR : VB200_FORMAT_USHORT;
+		if (in.fmt != want) {
+			/* cast.c:476-495: a copy, or a cast through the guessed format first: not built */
+			error(domain, "source space %d wants band format %d, image has %d", source_space, want, in.fmt);
+			return -1;
+		}
+		if (dev_image_new(domain, out, in.w, in.h, in.bands, up ? VB200_FORMAT_USHORT : VB200_FORMAT_UCHAR, space, s))
+			return -1;
+		const int ne = in.w * in.bands;
+		shift_cast_kernel<<<dim3((ne + 255) / 256, in.h), block, 0, s>>>(in.data, in.bpl, out->data, out->bpl, up ? 1 : 0, ne);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return cuda_fail(domain, e, "shift_cast_kernel");
+		count_launch();
+		return 0;
+	}
 	const int n = build_route(source_space, space, steps);
 	if (n < 0) {
 		error(domain, "no known route from %d to %d on the device path", source_space, space);
@@ -485,7 +528,6 @@ dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space
 		error(domain, "band format %d not supported on the device path", in.fmt);
 		return -1;
 	}
-	const dim3 block(256);
 	if (n == 0) {
 		const int ofmt = space_format(space);
 		if (dev_image_new(domain, out, in.w, in.h, in.bands, ofmt, space, s))

@@ -311,7 +311,7 @@ LabS2Lab_line(const int16_t *p, float *q, size_t n)
 /* ----------------------------------------------------------------- steps */
 
 enum { S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
-	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ };
+	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ, S_sRGB2RGB16, S_RGB162sRGB };
 
 /* ---- the next VipsColour converters: Lab <-> LCh, XYZ <-> Yxy */
 
@@ -475,6 +475,43 @@ cast_store(double v, bool from_float, int ofmt, uint8_t *q)
 	(void) from_float;
 }
 
+/* vips_sRGB2RGB16 / vips_RGB162sRGB, colourspace.c:85-110: not colour objects at all but vips_cast(..., "shift", TRUE)
+ * over EVERY band ("we can short-circuit the extra band processing"), then the interpretation is re-tagged.  The
+ * integer loops are cast.c:137-164: a right shift by the width difference going down; going up, a left shift with the
+ * bottom bit copied into the new bits.  A cast to the format the image already has is a copy (cast.c:476-477).
+ */
+static int
+shift_cast_step(int step, const Img &in, Img &out)
+{
+	const int ofmt = step == S_sRGB2RGB16 ? ORC_FORMAT_USHORT : ORC_FORMAT_UCHAR;
+	if (in.fmt != ORC_FORMAT_UCHAR && in.fmt != ORC_FORMAT_USHORT)
+		return -1; /* float pixels tagged as an integer space (cast.c:483-495): not restated */
+	const size_t cnt = in.npix() * in.bands;
+	out.w = in.w;
+	out.h = in.h;
+	out.bands = in.bands;
+	out.fmt = ofmt;
+	out.type = step == S_sRGB2RGB16 ? 25 : 22;
+	out.data.resize(cnt * orc_sizeof_format(ofmt));
+	if (in.fmt == ofmt) {
+		out.data = in.data;
+		return 0;
+	}
+	if (ofmt == ORC_FORMAT_USHORT) {
+		const uint8_t *p = in.data.data();
+		uint16_t *q = (uint16_t *) out.data.data();
+		for (size_t i = 0; i < cnt; i++)
+			q[i] = (uint16_t) ((p[i] << 8) | (((p[i] & 1) << 8) - (p[i] & 1)));
+	}
+	else {
+		const uint16_t *p = (const uint16_t *) in.data.data();
+		uint8_t *q = out.data.data();
+		for (size_t i = 0; i < cnt; i++)
+			q[i] = (uint8_t) (p[i] >> 8);
+	}
+	return 0;
+}
+
 /* One colour op on an image: first 3 bands through the line function, extra
  * bands through colour.c:252-291.
  */
@@ -482,6 +519,8 @@ static int
 run_step(int step, const Img &in, Img &out)
 {
 	make_tables();
+	if (step == S_sRGB2RGB16 || step == S_RGB162sRGB)
+		return shift_cast_step(step, in, out);
 	int in_fmt_wanted, out_fmt, out_type;
 	switch (step) {
 	case S_sRGB2scRGB: in_fmt_wanted = ORC_FORMAT_UCHAR; out_fmt = ORC_FORMAT_FLOAT; out_type = 28; break;
@@ -588,6 +627,15 @@ route_for(int from, int to, int steps[8])
 	auto push = [&](std::initializer_list<int> l) { for (int s : l) steps[n++] = s; };
 	if (from == to)
 		return 0;
+	/* colourspace.c:372, 420: the two rows that are not colour conversions */
+	if (from == sRGB && to == RGB16) {
+		steps[0] = S_sRGB2RGB16;
+		return 1;
+	}
+	if (from == RGB16 && to == sRGB) {
+		steps[0] = S_RGB162sRGB;
+		return 1;
+	}
 	/* LCH hangs off LAB and YXY off XYZ in every row of the table (colourspace.c:226, 236, 242, 252, 275-290 ...):
 	 * route to the hub, then one more step
 	 */

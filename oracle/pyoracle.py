@@ -183,7 +183,7 @@ def thumbnail_image(a, width, height=None, size="both", has_alpha=None, tile=(0,
 # ------------------------------------------------------------------ colour
 STEPS = {"sRGB2scRGB": 1, "scRGB2XYZ": 2, "XYZ2Lab": 3, "Lab2LabS": 4, "LabS2Lab": 5, "Lab2XYZ": 6,
          "XYZ2scRGB": 7, "scRGB2sRGB": 8, "scRGB2RGB16": 9, "RGB162scRGB": 10, "Lab2LCh": 11, "LCh2Lab": 12,
-         "XYZ2Yxy": 13, "Yxy2XYZ": 14}
+         "XYZ2Yxy": 13, "Yxy2XYZ": 14, "sRGB2RGB16": 15, "RGB162sRGB": 16}
 SPACES = {"xyz": 12, "lab": 13, "lch": 19, "labs": 21, "srgb": 22, "yxy": 23, "rgb16": 25, "scrgb": 28, "b-w": 1,
           "multiband": 0}
 # (input dtype the step wants, output dtype, output interpretation)
@@ -191,7 +191,8 @@ STEP_IO = {1: (np.uint8, np.float32, 28), 10: (np.uint16, np.float32, 28), 2: (n
            3: (np.float32, np.float32, 13), 4: (np.float32, np.int16, 21), 5: (np.int16, np.float32, 13),
            6: (np.float32, np.float32, 12), 7: (np.float32, np.float32, 28), 8: (np.float32, np.uint8, 22),
            9: (np.float32, np.uint16, 25), 11: (np.float32, np.float32, 19), 12: (np.float32, np.float32, 13),
-           13: (np.float32, np.float32, 23), 14: (np.float32, np.float32, 12)}
+           13: (np.float32, np.float32, 23), 14: (np.float32, np.float32, 12), 15: (np.uint8, np.uint16, 25),
+           16: (np.uint16, np.uint8, 22)}
 
 
 def _space(s):

@@ -29,7 +29,7 @@ def lib():
         for name in ("ref_image_new_from_memory", "ref_shrinkv", "ref_shrinkh", "ref_reducev", "ref_reduceh",
                      "ref_resize", "ref_premultiply", "ref_unpremultiply", "ref_colour_op", "ref_colourspace",
                      "ref_conv", "ref_convsep", "ref_gaussblur", "ref_sharpen", "ref_gaussmat", "ref_affine",
-                     "ref_cast"):
+                     "ref_cast", "ref_colourspace_build"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_void_p
         L.ref_error.restype = C.c_char_p
@@ -46,6 +46,9 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.ref_reduce_make_mask.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.vips_reduce_get_points.argtypes = [C.c_int, C.c_double]
+        if hasattr(L, "ref_colourspace_build"):
+            L.ref_colourspace_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            L.ref_cast.argtypes = [C.c_void_p, C.c_int, C.c_int]
         if hasattr(L, "ref_thumbnail_calculate_shrink"):
             L.ref_thumbnail_calculate_shrink.restype = None
             L.ref_thumbnail_calculate_shrink.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_double)] * 2
@@ -107,6 +110,14 @@ class RefImage:
     @property
     def dhint(self):
         return lib().ref_image_dhint(self.h)
+
+    def colourspace(self, space, source_space):
+        """vips_colourspace_build over colourspace.c's route table, every step a real VipsColour object (colour.c build,
+        vips_colour_gen, the converter's line function); alpha through cast.c / linear.c"""
+        return self._op(lib().ref_colourspace_build, pyoracle._space(space), pyoracle._space(source_space))
+
+    def cast(self, dtype, shift=False):
+        return self._op(lib().ref_cast, pyoracle.FMT[np.dtype(dtype)], int(shift))
 
     def numpy(self, tile=(0, 0)):
         """The sink: pull the image through generate() tile by tile."""

@@ -133,3 +133,65 @@ ref_colour_table(int which, int *n)
 	*n = 0;
 	return NULL;
 }
+
+/* vips_call_split (iofuncs/operation.c:1089-1120) for the converters above: each one's own varargs front end calls
+ * vips_call_split("nickname", optional, in, out).  The object is made from the converter's own type (its class_init and
+ * init run), "in" is set (VipsColourTransform and VipsColourCode both keep it first, pcolour.h:116-159), the class's
+ * build runs -- the converter's, then VipsColourTransform's / VipsColourCode's, then VipsColour's (colour.c under
+ * ref_colourbuild.c) -- and "out" is handed back lazy: pixels come through vips_colour_gen and the line function.
+ */
+int ref__castv(VipsImage *in, VipsImage **out, VipsBandFormat format, va_list ap);
+
+int
+vips_call_split(const char *operation_name, va_list optional, ...)
+{
+	static const struct {
+		const char *nickname;
+		GType (*get_type)(void);
+	} ops[] = {
+		{ "sRGB2scRGB", vips_sRGB2scRGB_get_type }, { "scRGB2XYZ", vips_scRGB2XYZ_get_type },
+		{ "XYZ2scRGB", vips_XYZ2scRGB_get_type }, { "XYZ2Lab", vips_XYZ2Lab_get_type }, { "Lab2XYZ", vips_Lab2XYZ_get_type },
+		{ "scRGB2sRGB", vips_scRGB2sRGB_get_type }, { "Lab2LabS", vips_Lab2LabS_get_type },
+		{ "LabS2Lab", vips_LabS2Lab_get_type }, { "Lab2LCh", vips_Lab2LCh_get_type }, { "LCh2Lab", vips_LCh2Lab_get_type },
+		{ "XYZ2Yxy", vips_XYZ2Yxy_get_type }, { "Yxy2XYZ", vips_Yxy2XYZ_get_type }
+	};
+	static const char *set_in[] = { "in", NULL };
+	va_list required;
+	VipsImage *in, **out;
+	VipsColour *colour;
+	const char *name;
+	int i;
+
+	va_start(required, optional);
+	in = va_arg(required, VipsImage *);
+	out = va_arg(required, VipsImage **);
+	if (strcmp(operation_name, "cast") == 0) {
+		/* cast.c's own front ends (parked in ref_cast.c): the third required argument is the format */
+		VipsBandFormat format = (VipsBandFormat) va_arg(required, int);
+		va_end(required);
+		return ref__castv(in, out, format, optional);
+	}
+	va_end(required);
+	for (i = 0; i < VIPS_NUMBER(ops); i++)
+		if (strcmp(ops[i].nickname, operation_name) == 0)
+			break;
+	if (i == VIPS_NUMBER(ops)) {
+		vips_error("shim", "vips_call_split: %s is not compiled into this shim", operation_name);
+		return -1;
+	}
+	colour = (VipsColour *) vips__shim_object_new(ops[i].get_type());
+	((VipsColourTransform *) colour)->in = in;
+	((VipsObject *) colour)->set_args = set_in; /* vips_sRGB2scRGB_build asks vips_object_argument_isset(object, "in") */
+	while ((name = va_arg(optional, const char *))) {
+		if (strcmp(name, "depth") == 0 && strcmp(operation_name, "scRGB2sRGB") == 0)
+			((VipsscRGB2sRGB *) colour)->depth = va_arg(optional, int);
+		else {
+			vips_error("shim", "vips_call_split: %s: option %s is not modelled", operation_name, name);
+			return -1;
+		}
+	}
+	if (VIPS_OBJECT_GET_CLASS(colour)->build((VipsObject *) colour))
+		return -1;
+	*out = colour->out;
+	return 0;
+}

@@ -1,16 +1,14 @@
 /* shim_ops.c -- eager stand-ins for the graph ops vips_sharpen_build / vips_convsep_build call that
  * are NOT on the hot path (band plumbing, copies, colourspace dispatch).  Each materialises its input
- * with the shim's sink and returns a memory image.  vips_colourspace runs the reference's own colour
- * *_line functions (ref_colour.c) in the order vips_colourspace_build's route table gives
- * (colourspace.c:317, 362-366).  TEST INFRASTRUCTURE ONLY.
+ * with the shim's sink and returns a memory image.  vips_colourspace, vips_cast* and vips_linear1 are NOT here: the
+ * reference's own colourspace.c / colour.c / cast.c / linear.c serve them (ref_colourspace.c, ref_colourbuild.c,
+ * ref_cast.c, ref_linear.c).  TEST INFRASTRUCTURE ONLY.
  */
 #include <stdarg.h>
 #include <vips/vips.h>
 
-int ref_colour_line(int step, const void *in, void *out, int n);
-
-static VipsImage *
-shim_new_memory(int w, int h, int bands, VipsBandFormat fmt, VipsInterpretation type)
+VipsImage *
+vips__shim_new_memory(int w, int h, int bands, VipsBandFormat fmt, VipsInterpretation type)
 {
 	VipsImage *im = vips_image_new();
 	vips_image_init_fields(im, w, h, bands, fmt, VIPS_CODING_NONE, type, 1.0, 1.0);
@@ -19,13 +17,13 @@ shim_new_memory(int w, int h, int bands, VipsBandFormat fmt, VipsInterpretation 
 	return im;
 }
 
-static VipsImage *
-shim_materialise(VipsImage *in)
+VipsImage *
+vips__shim_materialise(VipsImage *in)
 {
 	VipsImage *im;
 	if (in->data && !in->generate_fn)
 		return in;
-	im = shim_new_memory(in->Xsize, in->Ysize, in->Bands, in->BandFmt, in->Type);
+	im = vips__shim_new_memory(in->Xsize, in->Ysize, in->Bands, in->BandFmt, in->Type);
 	im->mat_scale = in->mat_scale;
 	im->mat_offset = in->mat_offset;
 	im->mat_meta_set = in->mat_meta_set;
@@ -37,27 +35,17 @@ shim_materialise(VipsImage *in)
 int
 vips_copy(VipsImage *in, VipsImage **out, ...)
 {
-	VipsImage *m = shim_materialise(in);
+	VipsImage *m = vips__shim_materialise(in);
 	VipsImage *im;
 	if (!m)
 		return -1;
-	im = shim_new_memory(m->Xsize, m->Ysize, m->Bands, m->BandFmt, m->Type);
+	im = vips__shim_new_memory(m->Xsize, m->Ysize, m->Bands, m->BandFmt, m->Type);
 	memcpy(im->data, m->data, (size_t) m->Xsize * m->Ysize * VIPS_IMAGE_SIZEOF_PEL(m));
 	im->mat_scale = m->mat_scale;
 	im->mat_offset = m->mat_offset;
 	im->mat_meta_set = m->mat_meta_set;
 	*out = im;
 	return 0;
-}
-
-int
-vips_cast_short(VipsImage *in, VipsImage **out, ...)
-{
-	if (in->BandFmt != VIPS_FORMAT_SHORT) {
-		vips_error("shim", "vips_cast_short: only short input is modelled");
-		return -1;
-	}
-	return vips_copy(in, out, NULL);
 }
 
 int
@@ -76,10 +64,10 @@ vips_extract_band(VipsImage *in, VipsImage **out, int band, ...)
 			return -1;
 	}
 	va_end(ap);
-	if (!(m = shim_materialise(in)) || band < 0 || n < 1 || band + n > m->Bands)
+	if (!(m = vips__shim_materialise(in)) || band < 0 || n < 1 || band + n > m->Bands)
 		return -1;
 	es = VIPS_IMAGE_SIZEOF_ELEMENT(m);
-	im = shim_new_memory(m->Xsize, m->Ysize, n, m->BandFmt, m->Type); /* bandary keeps the interpretation */
+	im = vips__shim_new_memory(m->Xsize, m->Ysize, n, m->BandFmt, m->Type); /* bandary keeps the interpretation */
 	for (x = 0; x < m->Xsize * m->Ysize; x++)
 		for (k = 0; k < n; k++)
 			memcpy(im->data + ((size_t) x * n + k) * es, m->data + ((size_t) x * m->Bands + band + k) * es, es);
@@ -90,69 +78,20 @@ vips_extract_band(VipsImage *in, VipsImage **out, int band, ...)
 int
 vips_bandjoin2(VipsImage *in1, VipsImage *in2, VipsImage **out, ...)
 {
-	VipsImage *a = shim_materialise(in1), *b = shim_materialise(in2), *im;
+	VipsImage *a = vips__shim_materialise(in1), *b = vips__shim_materialise(in2), *im;
 	size_t es;
 	int x;
 	if (!a || !b || a->Xsize != b->Xsize || a->Ysize != b->Ysize || a->BandFmt != b->BandFmt)
 		return -1;
 	es = VIPS_IMAGE_SIZEOF_ELEMENT(a);
 	/* vips_bandary_build copies the header of the first input: the interpretation is in1's */
-	im = shim_new_memory(a->Xsize, a->Ysize, a->Bands + b->Bands, a->BandFmt, a->Type);
+	im = vips__shim_new_memory(a->Xsize, a->Ysize, a->Bands + b->Bands, a->BandFmt, a->Type);
 	for (x = 0; x < a->Xsize * a->Ysize; x++) {
 		memcpy(im->data + (size_t) x * (a->Bands + b->Bands) * es, a->data + (size_t) x * a->Bands * es, a->Bands * es);
 		memcpy(im->data + ((size_t) x * (a->Bands + b->Bands) + a->Bands) * es, b->data + (size_t) x * b->Bands * es,
 			b->Bands * es);
 	}
 	*out = im;
-	return 0;
-}
-
-/* step numbers of ref_colour_line */
-static int
-shim_route(VipsInterpretation from, VipsInterpretation to, int *steps)
-{
-	int n = 0;
-	if (from == to)
-		return 0;
-	/* into LAB */
-	if (from == VIPS_INTERPRETATION_sRGB) { steps[n++] = 1; steps[n++] = 2; steps[n++] = 3; }
-	else if (from == VIPS_INTERPRETATION_LABS) steps[n++] = 5;
-	else if (from != VIPS_INTERPRETATION_LAB) return -1;
-	/* out of LAB */
-	if (to == VIPS_INTERPRETATION_sRGB) { steps[n++] = 6; steps[n++] = 7; steps[n++] = 8; }
-	else if (to == VIPS_INTERPRETATION_LABS) steps[n++] = 4;
-	else if (to != VIPS_INTERPRETATION_LAB) return -1;
-	/* LABS -> sRGB is LabS2Lab, Lab2XYZ, XYZ2scRGB, scRGB2sRGB; sRGB -> LABS ends Lab2LabS (colourspace.c:317, 366) */
-	return n;
-}
-
-int
-vips_colourspace(VipsImage *in, VipsImage **out, VipsInterpretation space, ...)
-{
-	int steps[8], n, i;
-	VipsImage *m = shim_materialise(in), *cur;
-	if (!m)
-		return -1;
-	if (m->Bands != 3) {
-		vips_error("shim", "vips_colourspace: only 3-band images are modelled");
-		return -1;
-	}
-	if ((n = shim_route(m->Type, space, steps)) < 0) {
-		vips_error("shim", "vips_colourspace: route %d -> %d not modelled", m->Type, space);
-		return -1;
-	}
-	cur = m;
-	if (n == 0)
-		return vips_copy(m, out, NULL);
-	for (i = 0; i < n; i++) {
-		static const VipsBandFormat ofmt[11] = { 0, VIPS_FORMAT_FLOAT, VIPS_FORMAT_FLOAT, VIPS_FORMAT_FLOAT, VIPS_FORMAT_SHORT,
-			VIPS_FORMAT_FLOAT, VIPS_FORMAT_FLOAT, VIPS_FORMAT_FLOAT, VIPS_FORMAT_UCHAR, VIPS_FORMAT_USHORT, VIPS_FORMAT_FLOAT };
-		VipsImage *next = shim_new_memory(m->Xsize, m->Ysize, 3, ofmt[steps[i]], space);
-		if (ref_colour_line(steps[i], cur->data, next->data, m->Xsize * m->Ysize))
-			return -1;
-		cur = next;
-	}
-	*out = cur;
 	return 0;
 }
 
@@ -198,14 +137,80 @@ vips_check_bands_atleast(const char *domain, VipsImage *im, int bands)
 	return 0;
 }
 
-/* vips_cast to the format the image already has is a copy; morph.c:868 asks for uchar */
+/* header.c:737-758 (vips_image_pio_input): memory and partial images are both readable as they are */
 int
-vips_cast(VipsImage *in, VipsImage **out, VipsBandFormat format, ...)
+vips_image_pio_input(VipsImage *image)
 {
-	if (in->BandFmt != format) {
-		vips_error("shim", "vips_cast: only the identity cast is modelled");
+	return 0;
+}
+
+/* iofuncs/error.c:862-873 */
+int
+vips_check_coding(const char *domain, VipsImage *im, VipsCoding coding)
+{
+	if (im->Coding != coding) {
+		vips_error(domain, "coding %d required", (int) coding);
 		return -1;
 	}
-	*out = in;
 	return 0;
+}
+
+const char *
+vips_enum_nick(GType enm, int value)
+{
+	static char txt[32];
+	snprintf(txt, sizeof(txt), "%d", value); /* only inside error messages here */
+	return txt;
+}
+
+/* vips_image_guess_interpretation (header.c:560-700) returns Type unchanged when it is sane for the image's bands and
+ * format; every image the tests make is tagged with the interpretation its pixels are in
+ */
+VipsInterpretation
+vips_image_guess_interpretation(const VipsImage *image)
+{
+	return image->Type;
+}
+
+/* conversion/bandjoin.c: n images band-interleaved, the first input's header */
+int
+vips_bandjoin(VipsImage **in, VipsImage **out, int n, ...)
+{
+	VipsImage *cur = in[0], *next;
+	int i;
+	for (i = 1; i < n; i++) {
+		if (vips_bandjoin2(cur, in[i], &next, NULL))
+			return -1;
+		cur = next;
+	}
+	*out = cur;
+	return 0;
+}
+
+VipsBandFormat
+vips_image_get_format(const VipsImage *image)
+{
+	return image->BandFmt;
+}
+
+/* vips_image_guess_format, header.c:486-558, the interpretations the tests tag images with */
+VipsBandFormat
+vips_image_guess_format(const VipsImage *image)
+{
+	switch (image->Type) {
+	case VIPS_INTERPRETATION_sRGB:
+		return VIPS_FORMAT_UCHAR;
+	case VIPS_INTERPRETATION_XYZ:
+	case VIPS_INTERPRETATION_LAB:
+	case VIPS_INTERPRETATION_LCH:
+	case VIPS_INTERPRETATION_scRGB:
+	case VIPS_INTERPRETATION_YXY:
+		return VIPS_FORMAT_FLOAT;
+	case VIPS_INTERPRETATION_LABS:
+		return VIPS_FORMAT_SHORT;
+	case VIPS_INTERPRETATION_RGB16:
+		return VIPS_FORMAT_USHORT;
+	default:
+		return image->BandFmt;
+	}
 }

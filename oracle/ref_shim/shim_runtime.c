@@ -101,6 +101,7 @@ SHIM_PLAIN_TYPE(vips_conversion_get_type)
 SHIM_PLAIN_TYPE(vips_convolution_get_type)
 SHIM_PLAIN_TYPE(vips_create_get_type)
 SHIM_PLAIN_TYPE(vips_morphology_get_type)
+SHIM_PLAIN_TYPE(vips_unary_get_type)
 
 void *g_object_ref(void *p) { return p; }
 

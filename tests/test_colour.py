@@ -193,6 +193,85 @@ def test_new_spaces_routes_follow_the_table():
         assert [name[steps[i]] for i in range(n)] == want, (a, b)
 
 
+ALL_SPACES = SPACES + ["lch", "yxy"]
+
+
+@needs_ref
+@pytest.mark.parametrize("bands", [3, 4, 5])
+def test_oracle_colourspace_matches_reference_build(bands):
+    """the whole of vips_colourspace, not only the line functions: colourspace.c's route table and build, a real VipsColour
+    object per step (colour.c: extra bands detached, alpha rescaled by the max_alpha ratio through linear.c, cast through
+    cast.c and re-attached; the input casts of VipsColourCode / VipsColourTransform), vips_colour_gen pulling tiles --
+    all compiled in place under oracle/ref_shim -- against the oracle's restatement, every pair of the 8 spaces"""
+    rng = np.random.default_rng(30 + bands)
+    for src in ALL_SPACES:
+        base = "lab" if src in ("lch", "yxy") else src
+        a = sample(base, rng, n=31 * 47)
+        if bands > 3:
+            a = np.concatenate([a, sample(base, rng, n=31 * 47)[:, :bands - 3]], axis=1)
+        a = a.reshape(31, 47, bands)
+        for dst in ALL_SPACES:
+            ref = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src)
+            want = ref.numpy(tile=(16, 8))
+            got = orc.colourspace(a, dst, src)
+            assert got.dtype == want.dtype, (src, dst)
+            assert np.array_equal(got, want, equal_nan=True), (src, dst, bands)
+
+
+@needs_ref
+def test_oracle_colourspace_wild_floats_and_foreign_formats_match_reference_build():
+    """NaN / Inf pixels AND alpha through the reference's builds (alpha: linear.c then cast.c's float -> int clip), and
+    images whose band format is not the one their interpretation implies (the reference casts the whole image first:
+    colour.c:338-347, 421-428)"""
+    rng = np.random.default_rng(41)
+    for bands in (3, 4):
+        for src in ("scrgb", "xyz", "lab", "lch", "yxy"):
+            a = sample("lab", rng, n=23 * 40, wild=True)
+            if bands > 3:
+                a = np.concatenate([a, sample("lab", rng, n=23 * 40, wild=True)[:, :1]], axis=1)
+            a = a.reshape(23, 40, bands)
+            for dst in ALL_SPACES:
+                want = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src).numpy()
+                assert np.array_equal(orc.colourspace(a, dst, src), want, equal_nan=True), (src, dst, bands)
+    declined = 0
+    for dt in (np.uint8, np.uint16, np.int16, np.int32, np.float32):
+        if dt == np.float32:
+            a = (rng.standard_normal((19, 21, 4)) * 200).astype(np.float32)
+        else:
+            a = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, (19, 21, 4)).astype(dt)
+        for src in ALL_SPACES:
+            for dst in ALL_SPACES:
+                want = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src).numpy()
+                try:
+                    got = orc.colourspace(a, dst, src)
+                except ValueError:
+                    # the one thing not restated: a shifting cast from a format that is neither uchar nor ushort
+                    assert {src, dst} == {"srgb", "rgb16"} and dt not in (np.uint8, np.uint16), (dt, src, dst)
+                    declined += 1
+                    continue
+                assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (dt, src, dst)
+    assert declined == 6
+
+
+@needs_ref
+def test_srgb_rgb16_rows_are_shifting_casts():
+    """colourspace.c:372, 420: sRGB <-> RGB16 never touch the scRGB tables -- vips_cast(shift) over every band, alpha too:
+    up, the bottom bit fills the new byte (cast.c:150-164); down, the high byte"""
+    v = np.arange(256, dtype=np.uint8)
+    a = np.stack([v, v[::-1], v, v], axis=1).reshape(16, 16, 4)
+    up = orc.colourspace(a, "rgb16", "srgb")
+    assert np.array_equal(up, (a.astype(np.uint16) << 8) | np.where(a & 1, 255, 0).astype(np.uint16))
+    assert np.array_equal(up, pyref.RefImage.from_array(a, 22).colourspace("rgb16", "srgb").numpy())
+    assert np.array_equal(up, pyref.RefImage.from_array(a, 22).cast(np.uint16, shift=True).numpy())
+    w = np.arange(65536, dtype=np.uint16).reshape(256, 64, 4)
+    down = orc.colourspace(w, "srgb", "rgb16")
+    assert np.array_equal(down, (w >> 8).astype(np.uint8))
+    assert np.array_equal(down, pyref.RefImage.from_array(w, 25).colourspace("srgb", "rgb16").numpy())
+    L, steps = orc.lib(), (__import__("ctypes").c_int * 8)()
+    assert L.orc_colourspace_route(22, 25, steps) == 1 and steps[0] == orc.STEPS["sRGB2RGB16"]
+    assert L.orc_colourspace_route(25, 22, steps) == 1 and steps[0] == orc.STEPS["RGB162sRGB"]
+
+
 def ulp_diff(a, b):
     """distance in float32 ULPs (both finite, same sign or zero)"""
     ia = a.view(np.int32).astype(np.int64)
