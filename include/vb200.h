@@ -324,6 +324,16 @@ const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
  */
 enum { VB200_MORPHOLOGY_ERODE = 0, VB200_MORPHOLOGY_DILATE = 1 };
 int vb200_morph(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int morph);
+/* reference: vips_rank(), morphology/rank.c:623-635 (build :459-525, generate :404-456: histogram / select / max / min
+ * loops, all "the index-th smallest element of the width x height window", per band; the window is centred at
+ * (width / 2, height / 2), edges replicated); vips_median(), :651-664 = rank(size, size, size * size / 2).
+ * uchar .. float images.  Errors as the reference: "window too large", "index out of range".
+ */
+int vb200_rank(const VB200Image *in, VB200Image *out, int width, int height, int index);
+int vb200_median(const VB200Image *in, VB200Image *out, int size);
+/* test hook, host only: rank.cu's staging + select code run tile by tile on the CPU (packed arrays) */
+int vb200_debug_rank_host(const void *in, int width, int height, int bands, int band_format, int rank_width, int rank_height,
+	int index, void *out);
 
 /* ------------------------------------------------- unfused graphs: the chain pump
  *
@@ -348,6 +358,7 @@ int vb200_chain_add_sharpen(VB200Chain *chain, double sigma, double x1, double y
 int vb200_chain_add_premultiply(VB200Chain *chain, double max_alpha, int uchar_mode);
 int vb200_chain_add_unpremultiply(VB200Chain *chain, double max_alpha, int uchar_mode);
 int vb200_chain_add_morph(VB200Chain *chain, const VB200Mask *mask, int morph);
+int vb200_chain_add_rank(VB200Chain *chain, int width, int height, int index);
 int vb200_chain_run_host(VB200Chain *chain, const VB200Image *in, VB200Image *out, int n_images);
 
 /* ------------------------------------------------------------------ ICC

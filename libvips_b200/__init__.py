@@ -137,6 +137,10 @@ def lib():
         L.vb200_device_numa_node.restype = C.c_int
         L.vb200_morph.argtypes = [IP, IP, MP, C.c_int]
         L.vb200_chain_add_morph.argtypes = [C.c_void_p, MP, C.c_int]
+        L.vb200_rank.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int]
+        L.vb200_median.argtypes = [IP, IP, C.c_int]
+        L.vb200_chain_add_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.vb200_debug_rank_host.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
         L.vb200_chain_new.restype = C.c_void_p
         L.vb200_chain_free.argtypes = [C.c_void_p]
         L.vb200_chain_add_resize.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double]
@@ -322,6 +326,13 @@ class Image:
     def dilate(self, mask):
         return self.morph(mask, "dilate")
 
+    def rank(self, width, height, index):
+        """vips_rank: the index-th smallest element of every width x height window"""
+        return self._call(lib().vb200_rank, int(width), int(height), int(index))
+
+    def median(self, size):
+        return self._call(lib().vb200_median, int(size))
+
     # ---- colour
     def colourspace(self, space, source_space=None):
         src = self if source_space is None else Image(self.array, source_space)
@@ -383,6 +394,17 @@ def jpeg_decode_host_twin(stream, shrink=1):
     out = np.empty((h.value, w.value, bands.value), np.uint8)
     _check(lib().vb200_debug_jpeg_decode(stream, len(stream), int(shrink), out.ctypes.data_as(C.c_void_p), w.value * bands.value,
                                          C.byref(w), C.byref(h), C.byref(bands)))
+    return out
+
+
+def rank_host_twin(a, width, height, index):
+    """rank.cu's tile staging + radix select compiled for the host (vb200_debug_rank_host): what the CPU tests pin to rank.c"""
+    a = np.ascontiguousarray(a)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    out = np.empty_like(a)
+    _check(lib().vb200_debug_rank_host(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.shape[2], FORMATS[a.dtype], int(width),
+                                       int(height), int(index), out.ctypes.data_as(C.c_void_p)))
     return out
 
 
@@ -547,6 +569,10 @@ class Chain:
     def morph(self, mask, morph):
         m, cm = Image._mask(mask, 1.0, 0.0)
         _check(lib().vb200_chain_add_morph(self._p, C.byref(cm), {"erode": 0, "dilate": 1}.get(morph, morph)))
+        return self
+
+    def rank(self, width, height, index):
+        _check(lib().vb200_chain_add_rank(self._p, int(width), int(height), int(index)))
         return self
 
     def gaussblur(self, sigma, min_ampl=0.2, precision="integer"):

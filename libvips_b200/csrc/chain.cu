@@ -22,12 +22,12 @@ using namespace vb200;
 
 namespace {
 
-enum ChainOp { C_RESIZE, C_REDUCE, C_COLOURSPACE, C_CONV, C_CONVSEP, C_GAUSSBLUR, C_SHARPEN, C_PREMULTIPLY, C_UNPREMULTIPLY, C_MORPH };
+enum ChainOp { C_RESIZE, C_REDUCE, C_COLOURSPACE, C_CONV, C_CONVSEP, C_GAUSSBLUR, C_SHARPEN, C_PREMULTIPLY, C_UNPREMULTIPLY, C_MORPH, C_RANK };
 
 struct ChainStep {
 	ChainOp op = C_RESIZE;
 	double d[6] = {0, 0, 0, 0, 0, 0};
-	int i[2] = {0, 0};
+	int i[3] = {0, 0, 0};
 	std::vector<double> mask;
 	int mw = 0, mh = 0;
 };
@@ -148,6 +148,17 @@ vb200_chain_add_morph(VB200Chain *chain, const VB200Mask *mask, int morph)
 }
 
 extern "C" int
+vb200_chain_add_rank(VB200Chain *chain, int width, int height, int index)
+{
+	ChainStep st;
+	st.op = C_RANK;
+	st.i[0] = width;
+	st.i[1] = height;
+	st.i[2] = index;
+	return chain_push(chain, std::move(st));
+}
+
+extern "C" int
 vb200_chain_add_gaussblur(VB200Chain *chain, double sigma, double min_ampl, int precision)
 {
 	ChainStep st;
@@ -208,6 +219,8 @@ chain_step(const char *domain, const ChainStep &st, const DevImage &in, DevImage
 		return dev_convsep(domain, in, out, st.mask.data(), st.mw, st.mh, st.d[0], st.d[1], st.i[0], s, true);
 	case C_MORPH:
 		return dev_morph(domain, in, out, st.mask.data(), st.mw, st.mh, st.i[0], s);
+	case C_RANK:
+		return dev_rank(domain, in, out, st.i[0], st.i[1], st.i[2], s);
 	case C_GAUSSBLUR:
 		return dev_gaussblur(domain, in, out, st.d[0], st.d[1], st.i[0], s);
 	case C_SHARPEN:

@@ -147,6 +147,9 @@ int dev_sharpen(const char *domain, const DevImage &in, DevImage *out, double si
 /* morph.cu */
 int dev_morph(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, int op, cudaStream_t s);
 
+/* rank.cu */
+int dev_rank(const char *domain, const DevImage &in, DevImage *out, int width, int height, int index, cudaStream_t s);
+
 /* colour.cu */
 int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space,
 	cudaStream_t s);

@@ -49,3 +49,51 @@ orc_morph(const uint8_t *in, int w, int h, int bands, const double *mask, int mw
 			}
 	return 0;
 }
+
+/* ------------------------------------------------------------------ vips_rank
+ * Follows morphology/rank.c:
+ *   :459-490  vips_rank_build: window no larger than the image, 0 <= index < width * height
+ *   :508-516  the image is embedded at (width / 2, height / 2) with VIPS_EXTEND_COPY, so output (x, y) sees the
+ *             window of input pixels (x - width / 2 + i, y - height / 2 + j), coordinates clamped
+ *   :154-221  (uchar histogram), :225-305 (select), :309-369 (max / min): all four paths return the index-th
+ *             smallest element of the window, per band; the restatement sorts the window.
+ * fmt: VipsBandFormat (0 uchar .. 6 float).  -1: bad window / index / format.
+ */
+#include <algorithm>
+
+template <typename T>
+static void
+rank_typed(const T *in, int w, int h, int bands, int rw, int rh, int index, T *out)
+{
+	std::vector<T> win((size_t) rw * rh);
+	for (int y = 0; y < h; y++)
+		for (int x = 0; x < w; x++)
+			for (int b = 0; b < bands; b++) {
+				size_t k = 0;
+				for (int j = 0; j < rh; j++)
+					for (int i = 0; i < rw; i++) {
+						const int sx = clampi(x - rw / 2 + i, 0, w - 1), sy = clampi(y - rh / 2 + j, 0, h - 1);
+						win[k++] = in[((size_t) sy * w + sx) * bands + b];
+					}
+				std::nth_element(win.begin(), win.begin() + index, win.end());
+				out[((size_t) y * w + x) * bands + b] = win[index];
+			}
+}
+
+extern "C" int
+orc_rank(const void *in, int w, int h, int bands, int fmt, int rw, int rh, int index, void *out)
+{
+	if (rw < 1 || rh < 1 || rw > w || rh > h || index < 0 || index > rw * rh - 1)
+		return -1;
+	switch (fmt) {
+	case 0: rank_typed((const uint8_t *) in, w, h, bands, rw, rh, index, (uint8_t *) out); break;
+	case 1: rank_typed((const int8_t *) in, w, h, bands, rw, rh, index, (int8_t *) out); break;
+	case 2: rank_typed((const uint16_t *) in, w, h, bands, rw, rh, index, (uint16_t *) out); break;
+	case 3: rank_typed((const int16_t *) in, w, h, bands, rw, rh, index, (int16_t *) out); break;
+	case 4: rank_typed((const uint32_t *) in, w, h, bands, rw, rh, index, (uint32_t *) out); break;
+	case 5: rank_typed((const int32_t *) in, w, h, bands, rw, rh, index, (int32_t *) out); break;
+	case 6: rank_typed((const float *) in, w, h, bands, rw, rh, index, (float *) out); break;
+	default: return -1;
+	}
+	return 0;
+}

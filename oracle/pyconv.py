@@ -201,3 +201,28 @@ def ref_morph(a, mask, op, tile=(0, 0)):
     m = L.ref_matrix(mask.ctypes.data, mask.shape[1], mask.shape[0], 1.0, 0.0)
     im = pyref.RefImage.from_array(a)
     return pyref.RefImage(L.ref_morph(im.h, m, {"erode": 0, "dilate": 1}[op]), (im, mask)).numpy(tile)
+
+
+def rank(a, width, height, index):
+    """vips_rank, oracle restatement: the index-th smallest of each width x height window, per band"""
+    a, h, w, b, f = pyoracle._img(a)
+    out = np.empty_like(a)
+    L = pyoracle.lib()
+    L.orc_rank.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+    if L.orc_rank(a.ctypes.data, w, h, b, f, width, height, index, out.ctypes.data):
+        raise ValueError("rank: bad window, index or format")
+    return out
+
+
+def median(a, size):
+    """vips_median, rank.c:651-664"""
+    return rank(a, size, size, (size * size) // 2)
+
+
+def ref_rank(a, width, height, index, tile=(0, 0)):
+    """vips_rank through the reference's own morphology/rank.c"""
+    L = _rl()
+    L.ref_rank.restype = C.c_void_p
+    L.ref_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    im = pyref.RefImage.from_array(a)
+    return pyref.RefImage(L.ref_rank(im.h, width, height, index), (im,)).numpy(tile)
