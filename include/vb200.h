@@ -318,6 +318,18 @@ size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
  */
 const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
 
+/* ------------------------------------------------------------ flatten
+ * reference: vips_flatten(), conversion/flatten.c:600-616 (build :421-527; generate functions :170-419).  Blends the
+ * last band (alpha) out against `background` (n = 1 or bands - 1 values; NULL / n = 0: black): bands - 1 bands out, same
+ * format.  max_alpha <= 0: the interpretation's default (255, 65535 for RGB16 / GREY16, 1 for scRGB).  One-band images are
+ * copied.  uchar .. float images; the integer cases where the reference's own arithmetic is undefined C (see flatten.cu)
+ * return -1 and stay on the host.
+ */
+int vb200_flatten(const VB200Image *in, VB200Image *out, const double *background, int n, double max_alpha);
+/* test hook, host only: flatten.cu's per-pixel code on the CPU (packed arrays); x4: the four-pixels-per-thread form */
+int vb200_debug_flatten_host(const void *in, int width, int height, int bands, int band_format, int interpretation,
+	const double *background, int n, double max_alpha, int x4, void *out);
+
 /* ------------------------------------------------------------ morphology
  * reference: vips_morph(), morphology/morph.c:1030-1042 (generate functions :657-826; the Highway kernels
  * morph_hwy.cpp give the same bytes).  mask elements 0 / 128 (do not care) / 255; uchar images.
@@ -359,6 +371,7 @@ int vb200_chain_add_premultiply(VB200Chain *chain, double max_alpha, int uchar_m
 int vb200_chain_add_unpremultiply(VB200Chain *chain, double max_alpha, int uchar_mode);
 int vb200_chain_add_morph(VB200Chain *chain, const VB200Mask *mask, int morph);
 int vb200_chain_add_rank(VB200Chain *chain, int width, int height, int index);
+int vb200_chain_add_flatten(VB200Chain *chain, const double *background, int n, double max_alpha);
 int vb200_chain_run_host(VB200Chain *chain, const VB200Image *in, VB200Image *out, int n_images);
 
 /* ------------------------------------------------------------------ ICC

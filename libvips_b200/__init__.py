@@ -138,6 +138,9 @@ def lib():
         L.vb200_morph.argtypes = [IP, IP, MP, C.c_int]
         L.vb200_chain_add_morph.argtypes = [C.c_void_p, MP, C.c_int]
         L.vb200_rank.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int]
+        L.vb200_flatten.argtypes = [IP, IP, C.c_void_p, C.c_int, C.c_double]
+        L.vb200_chain_add_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.vb200_debug_flatten_host.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.vb200_median.argtypes = [IP, IP, C.c_int]
         L.vb200_chain_add_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.vb200_debug_rank_host.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
@@ -314,6 +317,12 @@ class Image:
     def sharpen(self, sigma=0.5, x1=2.0, y2=10.0, y3=20.0, m1=0.0, m2=3.0):
         return self._call(lib().vb200_sharpen, float(sigma), float(x1), float(y2), float(y3), float(m1), float(m2))
 
+    # ---- conversion
+    def flatten(self, background=None, max_alpha=0.0):
+        """vips_flatten: blend the alpha band out against `background` (1 or bands - 1 values; None: black)"""
+        bg = np.ascontiguousarray([] if background is None else background, np.float64).ravel()
+        return self._call(lib().vb200_flatten, bg.ctypes.data_as(C.c_void_p) if len(bg) else None, len(bg), float(max_alpha))
+
     # ---- morphology
     def morph(self, mask, morph):
         """vips_morph: mask elements 0 / 128 / 255; morph "erode" or "dilate" """
@@ -405,6 +414,21 @@ def rank_host_twin(a, width, height, index):
     out = np.empty_like(a)
     _check(lib().vb200_debug_rank_host(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.shape[2], FORMATS[a.dtype], int(width),
                                        int(height), int(index), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def flatten_host_twin(a, background=None, max_alpha=0.0, interpretation=None, x4=False):
+    """flatten.cu's per-pixel code compiled for the host (vb200_debug_flatten_host): what the CPU tests pin to flatten.c"""
+    a = np.ascontiguousarray(a)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if interpretation is None:
+        interpretation = 1 if a.shape[2] < 3 else 22
+    bg = np.ascontiguousarray([] if background is None else background, np.float64).ravel()
+    out = np.empty((a.shape[0], a.shape[1], max(1, a.shape[2] - 1)), a.dtype)
+    _check(lib().vb200_debug_flatten_host(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.shape[2], FORMATS[a.dtype],
+                                          _interp(interpretation), bg.ctypes.data_as(C.c_void_p) if len(bg) else None, len(bg),
+                                          float(max_alpha), int(x4), out.ctypes.data_as(C.c_void_p)))
     return out
 
 
@@ -569,6 +593,11 @@ class Chain:
     def morph(self, mask, morph):
         m, cm = Image._mask(mask, 1.0, 0.0)
         _check(lib().vb200_chain_add_morph(self._p, C.byref(cm), {"erode": 0, "dilate": 1}.get(morph, morph)))
+        return self
+
+    def flatten(self, background=None, max_alpha=0.0):
+        bg = np.ascontiguousarray([] if background is None else background, np.float64).ravel()
+        _check(lib().vb200_chain_add_flatten(self._p, bg.ctypes.data_as(C.c_void_p) if len(bg) else None, len(bg), float(max_alpha)))
         return self
 
     def rank(self, width, height, index):

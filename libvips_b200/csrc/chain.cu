@@ -22,7 +22,7 @@ using namespace vb200;
 
 namespace {
 
-enum ChainOp { C_RESIZE, C_REDUCE, C_COLOURSPACE, C_CONV, C_CONVSEP, C_GAUSSBLUR, C_SHARPEN, C_PREMULTIPLY, C_UNPREMULTIPLY, C_MORPH, C_RANK };
+enum ChainOp { C_RESIZE, C_REDUCE, C_COLOURSPACE, C_CONV, C_CONVSEP, C_GAUSSBLUR, C_SHARPEN, C_PREMULTIPLY, C_UNPREMULTIPLY, C_MORPH, C_RANK, C_FLATTEN };
 
 struct ChainStep {
 	ChainOp op = C_RESIZE;
@@ -148,6 +148,17 @@ vb200_chain_add_morph(VB200Chain *chain, const VB200Mask *mask, int morph)
 }
 
 extern "C" int
+vb200_chain_add_flatten(VB200Chain *chain, const double *background, int n, double max_alpha)
+{
+	ChainStep st;
+	st.op = C_FLATTEN;
+	if (background && n > 0)
+		st.mask.assign(background, background + n);
+	st.d[0] = max_alpha;
+	return chain_push(chain, std::move(st));
+}
+
+extern "C" int
 vb200_chain_add_rank(VB200Chain *chain, int width, int height, int index)
 {
 	ChainStep st;
@@ -219,6 +230,8 @@ chain_step(const char *domain, const ChainStep &st, const DevImage &in, DevImage
 		return dev_convsep(domain, in, out, st.mask.data(), st.mw, st.mh, st.d[0], st.d[1], st.i[0], s, true);
 	case C_MORPH:
 		return dev_morph(domain, in, out, st.mask.data(), st.mw, st.mh, st.i[0], s);
+	case C_FLATTEN:
+		return dev_flatten(domain, in, out, st.mask.empty() ? nullptr : st.mask.data(), (int) st.mask.size(), st.d[0], s);
 	case C_RANK:
 		return dev_rank(domain, in, out, st.i[0], st.i[1], st.i[2], s);
 	case C_GAUSSBLUR:

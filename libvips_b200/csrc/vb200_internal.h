@@ -147,6 +147,10 @@ int dev_sharpen(const char *domain, const DevImage &in, DevImage *out, double si
 /* morph.cu */
 int dev_morph(const char *domain, const DevImage &in, DevImage *out, const double *mask, int mw, int mh, int op, cudaStream_t s);
 
+/* flatten.cu */
+int dev_flatten(const char *domain, const DevImage &in, DevImage *out, const double *background, int n, double max_alpha,
+	cudaStream_t s);
+
 /* rank.cu */
 int dev_rank(const char *domain, const DevImage &in, DevImage *out, int width, int height, int index, cudaStream_t s);
 

@@ -226,3 +226,30 @@ def ref_rank(a, width, height, index, tile=(0, 0)):
     L.ref_rank.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     im = pyref.RefImage.from_array(a)
     return pyref.RefImage(L.ref_rank(im.h, width, height, index), (im,)).numpy(tile)
+
+
+def ref_flatten(a, background=(0.0,), max_alpha=0.0, interpretation=None, tile=(0, 0)):
+    """vips_flatten through the reference's own conversion/flatten.c (+ cast.c for the ink and the double detour)"""
+    L = _rl()
+    L.ref_flatten.restype = C.c_void_p
+    L.ref_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    bg = np.ascontiguousarray(background, np.float64)
+    im = pyref.RefImage.from_array(a, interpretation)
+    return pyref.RefImage(L.ref_flatten(im.h, bg.ctypes.data, len(bg), max_alpha), (im, bg)).numpy(tile)
+
+
+def flatten(a, background=(0.0,), max_alpha=0.0, interpretation=None):
+    """vips_flatten, oracle restatement.  interpretation: VipsInterpretation value (default as pyref: B_W / sRGB by bands)"""
+    a, h, w, b, f = pyoracle._img(a)
+    if interpretation is None:
+        interpretation = 1 if b < 3 else 22
+    bg = np.ascontiguousarray(background, np.float64)
+    out = np.empty((h, w, max(1, b - 1)), a.dtype)
+    L = pyoracle.lib()
+    L.orc_flatten.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    rc = L.orc_flatten(a.ctypes.data, w, h, b, f, interpretation, bg.ctypes.data, len(bg), max_alpha, out.ctypes.data)
+    if rc == -2:
+        raise NotImplementedError("flatten: the reference's arithmetic is undefined here")
+    if rc:
+        raise ValueError("flatten: bad arguments")
+    return out

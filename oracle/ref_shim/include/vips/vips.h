@@ -455,6 +455,8 @@ VipsPel *vips__vector_to_ink(const char *domain, VipsImage *im, double *real, do
 void *g_object_ref(void *p);
 VipsArrayDouble *vips_array_double_newv(int n, ...);
 void vips_area_unref(VipsArea *area);
+double *vips_array_double_get(VipsArrayDouble *array, int *n);
+double vips_image_get_format_max(VipsBandFormat format);
 void vips_object_set_static(VipsObject *object, gboolean static_object);
 #define DBL_MIN_SHIM 2.2250738585072014e-308
 

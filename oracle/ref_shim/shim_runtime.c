@@ -13,6 +13,8 @@
  * Not kept: threads, buffer caching, sequential mode, ref counting (leaks).
  */
 #include <stdarg.h>
+#include <float.h>
+#include <limits.h>
 #include <vips/vips.h>
 
 /* --------------------------------------------------------------- type system */
@@ -120,6 +122,19 @@ VipsArrayDouble *vips_array_double_newv(int n, ...)
 	return (VipsArrayDouble *) area;
 }
 void vips_area_unref(VipsArea *area) {}
+double *vips_array_double_get(VipsArrayDouble *array, int *n)
+{
+	/* iofuncs/type.c:1115-1126 */
+	if (n)
+		*n = VIPS_AREA(array)->n;
+	return (double *) VIPS_AREA(array)->data;
+}
+double vips_image_get_format_max(VipsBandFormat format)
+{
+	/* iofuncs/header.c:440-473 */
+	static const double max[] = { UCHAR_MAX, SCHAR_MAX, USHRT_MAX, SHRT_MAX, UINT_MAX, INT_MAX, FLT_MAX, FLT_MAX, DBL_MAX, DBL_MAX };
+	return format >= VIPS_FORMAT_UCHAR && format <= VIPS_FORMAT_DPCOMPLEX ? max[format] : -1;
+}
 void vips_object_set_static(VipsObject *object, gboolean static_object) {}
 
 /* ------------------------------------------------------------------- rects */
