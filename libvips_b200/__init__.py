@@ -162,7 +162,7 @@ def lib():
 
 def _check(rc):
     if rc != 0:
-        msg = lib().vb200_error_buffer().decode()
+        msg = lib().vb200_error_buffer().decode(errors="replace")
         lib().vb200_error_clear()
         raise Error(msg.strip() or "vb200 call failed")
 

@@ -311,7 +311,8 @@ LabS2Lab_line(const int16_t *p, float *q, size_t n)
 /* ----------------------------------------------------------------- steps */
 
 enum { S_sRGB2scRGB = 1, S_scRGB2XYZ, S_XYZ2Lab, S_Lab2LabS, S_LabS2Lab, S_Lab2XYZ, S_XYZ2scRGB, S_scRGB2sRGB,
-	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ, S_sRGB2RGB16, S_RGB162sRGB };
+	S_scRGB2RGB16, S_RGB162scRGB, S_Lab2LCh, S_LCh2Lab, S_XYZ2Yxy, S_Yxy2XYZ, S_sRGB2RGB16, S_RGB162sRGB,
+	S_sRGB2HSV, S_HSV2sRGB, S_scRGB2BW, S_scRGB2BW16, S_BW2sRGB, S_GREY162RGB16 };
 
 /* ---- the next VipsColour converters: Lab <-> LCh, XYZ <-> Yxy */
 
@@ -423,6 +424,131 @@ Yxy2XYZ_line(const float *p, float *q, size_t n)
 	}
 }
 
+
+/* ---- SURVEY 8f rank 3, second lot: sRGB <-> HSV, scRGB -> B_W / GREY16, B_W -> sRGB, GREY16 -> RGB16 */
+
+/* vips_sRGB2HSV_line, sRGB2HSV.c:48-125: uchar in, uchar out; the double expressions are stored by C truncation */
+static void
+sRGB2HSV_line(const uint8_t *p, uint8_t *q, size_t n)
+{
+	for (size_t i = 0; i < n; i++, p += 3, q += 3) {
+		unsigned char c_max, c_min;
+		float secondary_diff, wrap_around_hue;
+		if (p[1] < p[2]) {
+			if (p[2] < p[0]) {
+				c_max = p[0];
+				c_min = p[1];
+				secondary_diff = p[1] - p[2];
+				wrap_around_hue = 255.0F;
+			}
+			else {
+				c_max = p[2];
+				c_min = p[1] < p[0] ? p[1] : p[0];
+				secondary_diff = p[0] - p[1];
+				wrap_around_hue = 170.0F;
+			}
+		}
+		else {
+			if (p[1] < p[0]) {
+				c_max = p[0];
+				c_min = p[2];
+				secondary_diff = p[1] - p[2];
+				wrap_around_hue = 0.0F;
+			}
+			else {
+				c_max = p[1];
+				c_min = p[2] < p[0] ? p[2] : p[0];
+				secondary_diff = p[2] - p[0];
+				wrap_around_hue = 85.0F;
+			}
+		}
+		if (c_max == 0)
+			q[0] = q[1] = q[2] = 0;
+		else {
+			q[2] = c_max;
+			const unsigned char delta = c_max - c_min;
+			if (delta == 0)
+				q[0] = 0;
+			else
+				q[0] = 42.5 * (secondary_diff / (float) delta) + wrap_around_hue;
+			q[1] = delta * 255.0 / (float) c_max;
+		}
+	}
+}
+
+/* vips_HSV2sRGB_line, HSV2sRGB.c:54-107 (SIXTH_OF_CHAR 42.5, a double) */
+static void
+HSV2sRGB_line(const uint8_t *p, uint8_t *q, size_t n)
+{
+	for (size_t i = 0; i < n; i++, p += 3, q += 3) {
+		float c, x, m;
+		c = p[2] * p[1] / 255.0;
+		x = c * (1 - fabsf(fmodf(p[0] / 42.5, 2) - 1));
+		m = p[2] - c;
+		if (p[0] < (int) 42.5) {
+			q[0] = c + m;
+			q[1] = x + m;
+			q[2] = 0 + m;
+		}
+		else if (p[0] < (int) (2 * 42.5)) {
+			q[0] = x + m;
+			q[1] = c + m;
+			q[2] = 0 + m;
+		}
+		else if (p[0] < (int) (3 * 42.5)) {
+			q[0] = 0 + m;
+			q[1] = c + m;
+			q[2] = x + m;
+		}
+		else if (p[0] < (int) (4 * 42.5)) {
+			q[0] = 0 + m;
+			q[1] = x + m;
+			q[2] = c + m;
+		}
+		else if (p[0] < (int) (5 * 42.5)) {
+			q[0] = x + m;
+			q[1] = 0 + m;
+			q[2] = c + m;
+		}
+		else {
+			q[0] = c + m;
+			q[1] = 0 + m;
+			q[2] = x + m;
+		}
+	}
+}
+
+/* vips_scRGB2BW_line, scRGB2BW.c:57-105, over vips_col_scRGB2BW, LabQ2sRGB.c:385-429: the CIE luminance of the linear
+ * pixel through the same interpolated gamma table as scRGB -> sRGB; three floats in, one uchar / ushort out
+ */
+static void
+scRGB2BW_line(const float *p, uint8_t *q, int depth, size_t n)
+{
+	const int maxval = depth == 16 ? 65535 : 255;
+	const int *lut = depth == 16 ? Y2v_16 : Y2v_8;
+	for (size_t i = 0; i < n; i++, p += 3) {
+		const float R = p[0], G = p[1], B = p[2];
+		const float Y = 0.2126F * R + 0.7152F * G + 0.0722F * B;
+		int g;
+		if (std::isnan(Y))
+			g = 0;
+		else {
+			float Yf = Y * maxval;
+			if (Yf < 0)
+				Yf = 0;
+			else if (Yf > maxval)
+				Yf = maxval;
+			const int Yi = (int) Yf;
+			const float v = lut[Yi] + (lut[Yi + 1] - lut[Yi]) * (Yf - Yi);
+			g = rintf(v);
+		}
+		if (depth == 16)
+			((uint16_t *) q)[i] = g;
+		else
+			q[i] = g;
+	}
+}
+
 struct Img {
 	int w = 0, h = 0, bands = 0, fmt = 0, type = 0;
 	std::vector<uint8_t> data;
@@ -512,6 +638,32 @@ shift_cast_step(int step, const Img &in, Img &out)
 	return 0;
 }
 
+/* vips_BW2sRGB / vips_GREY162RGB16, colourspace.c:150-186: not colour objects but vips__colourspace_process_n(in, 1,
+ * bandjoin(in, in, in)): the first band three times, the other bands cast to the same format (a copy) and re-attached;
+ * the format stays whatever it was, only Type changes.
+ */
+static int
+replicate_step(int step, const Img &in, Img &out)
+{
+	if (in.bands < 1)
+		return -1;
+	const size_t es = orc_sizeof_format(in.fmt), n = in.npix();
+	out.w = in.w;
+	out.h = in.h;
+	out.bands = in.bands + 2;
+	out.fmt = in.fmt;
+	out.type = step == S_BW2sRGB ? 22 : 25;
+	out.data.resize(n * out.bands * es);
+	for (size_t i = 0; i < n; i++) {
+		const uint8_t *p = &in.data[i * in.bands * es];
+		uint8_t *q = &out.data[i * out.bands * es];
+		for (int k = 0; k < 3; k++)
+			memcpy(q + k * es, p, es);
+		memcpy(q + 3 * es, p + es, (in.bands - 1) * es);
+	}
+	return 0;
+}
+
 /* One colour op on an image: first 3 bands through the line function, extra
  * bands through colour.c:252-291.
  */
@@ -521,8 +673,15 @@ run_step(int step, const Img &in, Img &out)
 	make_tables();
 	if (step == S_sRGB2RGB16 || step == S_RGB162sRGB)
 		return shift_cast_step(step, in, out);
+	if (step == S_BW2sRGB || step == S_GREY162RGB16)
+		return replicate_step(step, in, out);
 	int in_fmt_wanted, out_fmt, out_type;
+	int out_main = 3; /* bands the converter makes from its three input bands (colour->bands) */
 	switch (step) {
+	case S_sRGB2HSV: in_fmt_wanted = ORC_FORMAT_UCHAR; out_fmt = ORC_FORMAT_UCHAR; out_type = 29; break;
+	case S_HSV2sRGB: in_fmt_wanted = ORC_FORMAT_UCHAR; out_fmt = ORC_FORMAT_UCHAR; out_type = 22; break;
+	case S_scRGB2BW: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_UCHAR; out_type = 1; out_main = 1; break;
+	case S_scRGB2BW16: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_USHORT; out_type = 26; out_main = 1; break;
 	case S_sRGB2scRGB: in_fmt_wanted = ORC_FORMAT_UCHAR; out_fmt = ORC_FORMAT_FLOAT; out_type = 28; break;
 	case S_RGB162scRGB: in_fmt_wanted = ORC_FORMAT_USHORT; out_fmt = ORC_FORMAT_FLOAT; out_type = 28; break;
 	case S_scRGB2XYZ: in_fmt_wanted = ORC_FORMAT_FLOAT; out_fmt = ORC_FORMAT_FLOAT; out_type = 12; break;
@@ -564,8 +723,12 @@ run_step(int step, const Img &in, Img &out)
 		memcpy(&rgb[i * 3 * wes], src + i * in.bands * wes, 3 * wes);
 
 	const size_t oes = orc_sizeof_format(out_fmt);
-	std::vector<uint8_t> res(n * 3 * oes);
+	std::vector<uint8_t> res(n * out_main * oes);
 	switch (step) {
+	case S_sRGB2HSV: sRGB2HSV_line(rgb.data(), res.data(), n); break;
+	case S_HSV2sRGB: HSV2sRGB_line(rgb.data(), res.data(), n); break;
+	case S_scRGB2BW: scRGB2BW_line((const float *) rgb.data(), res.data(), 8, n); break;
+	case S_scRGB2BW16: scRGB2BW_line((const float *) rgb.data(), res.data(), 16, n); break;
 	case S_sRGB2scRGB:
 	case S_RGB162scRGB:
 		sRGB2scRGB_line(rgb.data(), in_fmt_wanted, (float *) res.data(), n);
@@ -584,12 +747,13 @@ run_step(int step, const Img &in, Img &out)
 	case S_Yxy2XYZ: Yxy2XYZ_line((const float *) rgb.data(), (float *) res.data(), n); break;
 	}
 
+	const int out_bands = in.bands - 3 + out_main;
 	out.w = in.w;
 	out.h = in.h;
-	out.bands = in.bands;
+	out.bands = out_bands;
 	out.fmt = out_fmt;
 	out.type = out_type;
-	out.data.resize(n * in.bands * oes);
+	out.data.resize(n * out_bands * oes);
 
 	const int extra = in.bands - 3;
 	const double before = max_alpha_of(in.type);
@@ -600,8 +764,8 @@ run_step(int step, const Img &in, Img &out)
 	 */
 	const double a_d = after / before;
 	for (size_t i = 0; i < n; i++) {
-		uint8_t *q = &out.data[i * in.bands * oes];
-		memcpy(q, &res[i * 3 * oes], 3 * oes);
+		uint8_t *q = &out.data[i * out_bands * oes];
+		memcpy(q, &res[i * out_main * oes], out_main * oes);
 		for (int e = 0; e < extra; e++) {
 			const uint8_t *p = src + (i * in.bands + 3 + e) * wes;
 			double v = elem_as_double(p, in_fmt_wanted);
@@ -612,7 +776,7 @@ run_step(int step, const Img &in, Img &out)
 				v = a1 * (float) v + b1;
 				is_float = true;
 			}
-			cast_store(v, is_float, out_fmt, q + (3 + e) * oes);
+			cast_store(v, is_float, out_fmt, q + (out_main + e) * oes);
 		}
 	}
 	return 0;
@@ -622,11 +786,47 @@ run_step(int step, const Img &in, Img &out)
 static int
 route_for(int from, int to, int steps[8])
 {
-	enum { XYZ = 12, LAB = 13, LCH = 19, LABS = 21, sRGB = 22, YXY = 23, RGB16 = 25, scRGB = 28 };
+	enum { BW = 1, XYZ = 12, LAB = 13, LCH = 19, LABS = 21, sRGB = 22, YXY = 23, RGB16 = 25, GREY16 = 26, scRGB = 28, HSV = 29 };
 	int n = 0;
 	auto push = [&](std::initializer_list<int> l) { for (int s : l) steps[n++] = s; };
 	if (from == to)
 		return 0;
+	/* B_W, GREY16 and HSV: every row of the table that starts there opens with BW2sRGB / GREY162RGB16 / HSV2sRGB and goes
+	 * on as the sRGB (RGB16) row does (colourspace.c:386-403, 367-384, 424-441); every row that ends there is the row to
+	 * scRGB + scRGB2BW[16], or the row to sRGB + sRGB2HSV (:234-236, 351-353, 372 ...)
+	 */
+	if (from == BW || from == GREY16 || from == HSV) {
+		const int first = from == BW ? S_BW2sRGB : (from == GREY16 ? S_GREY162RGB16 : S_HSV2sRGB);
+		const int hub = from == GREY16 ? RGB16 : sRGB;
+		int rest[8];
+		const int m = to == hub ? 0 : route_for(hub, to, rest);
+		if (m < 0 || m > 6)
+			return -1;
+		steps[0] = first;
+		for (int i = 0; i < m; i++)
+			steps[1 + i] = rest[i];
+		return m + 1;
+	}
+	if (to == BW || to == GREY16) {
+		int m = 0;
+		if (from != scRGB) {
+			m = route_for(from, scRGB, steps);
+			if (m < 0)
+				return -1;
+		}
+		steps[m++] = to == BW ? S_scRGB2BW : S_scRGB2BW16;
+		return m;
+	}
+	if (to == HSV) {
+		int m = 0;
+		if (from != sRGB) {
+			m = route_for(from, sRGB, steps);
+			if (m < 0)
+				return -1;
+		}
+		steps[m++] = S_sRGB2HSV;
+		return m;
+	}
 	/* colourspace.c:372, 420: the two rows that are not colour conversions */
 	if (from == sRGB && to == RGB16) {
 		steps[0] = S_sRGB2RGB16;
@@ -707,7 +907,10 @@ static int
 fmt_of_space(int space)
 {
 	switch (space) {
+	case 1:
+	case 29:
 	case 22: return ORC_FORMAT_UCHAR;
+	case 26:
 	case 25: return ORC_FORMAT_USHORT;
 	case 21: return ORC_FORMAT_SHORT;
 	default: return ORC_FORMAT_FLOAT;
@@ -718,6 +921,27 @@ extern "C" int
 orc_colourspace_format(int space)
 {
 	return fmt_of_space(space);
+}
+
+/* bands of vips_colourspace's output: B_W / GREY16 sources gain two bands, B_W / GREY16 targets lose two */
+extern "C" int
+orc_colourspace_bands(int from, int to, int bands)
+{
+	const bool grey_from = from == 1 || from == 26, grey_to = to == 1 || to == 26;
+	if (from == to)
+		return bands;
+	return bands + (grey_from ? 2 : 0) - (grey_to ? 2 : 0);
+}
+
+/* the format of the result: the space's own, except for the one-step rows B_W -> sRGB and GREY16 -> RGB16, which keep
+ * the image's (a bandjoin)
+ */
+extern "C" int
+orc_colourspace_out_format(int from, int to, int fmt)
+{
+	if ((from == 1 && to == 22) || (from == 26 && to == 25))
+		return fmt;
+	return fmt_of_space(to);
 }
 
 /* vips_colourspace(in, &out, space) with source_space = from.  out must hold

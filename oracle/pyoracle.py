@@ -183,16 +183,20 @@ def thumbnail_image(a, width, height=None, size="both", has_alpha=None, tile=(0,
 # ------------------------------------------------------------------ colour
 STEPS = {"sRGB2scRGB": 1, "scRGB2XYZ": 2, "XYZ2Lab": 3, "Lab2LabS": 4, "LabS2Lab": 5, "Lab2XYZ": 6,
          "XYZ2scRGB": 7, "scRGB2sRGB": 8, "scRGB2RGB16": 9, "RGB162scRGB": 10, "Lab2LCh": 11, "LCh2Lab": 12,
-         "XYZ2Yxy": 13, "Yxy2XYZ": 14, "sRGB2RGB16": 15, "RGB162sRGB": 16}
+         "XYZ2Yxy": 13, "Yxy2XYZ": 14, "sRGB2RGB16": 15, "RGB162sRGB": 16, "sRGB2HSV": 17, "HSV2sRGB": 18,
+         "scRGB2BW": 19, "scRGB2BW16": 20, "BW2sRGB": 21, "GREY162RGB16": 22}
 SPACES = {"xyz": 12, "lab": 13, "lch": 19, "labs": 21, "srgb": 22, "yxy": 23, "rgb16": 25, "scrgb": 28, "b-w": 1,
-          "multiband": 0}
+          "multiband": 0, "grey16": 26, "hsv": 29}
 # (input dtype the step wants, output dtype, output interpretation)
 STEP_IO = {1: (np.uint8, np.float32, 28), 10: (np.uint16, np.float32, 28), 2: (np.float32, np.float32, 12),
            3: (np.float32, np.float32, 13), 4: (np.float32, np.int16, 21), 5: (np.int16, np.float32, 13),
            6: (np.float32, np.float32, 12), 7: (np.float32, np.float32, 28), 8: (np.float32, np.uint8, 22),
            9: (np.float32, np.uint16, 25), 11: (np.float32, np.float32, 19), 12: (np.float32, np.float32, 13),
            13: (np.float32, np.float32, 23), 14: (np.float32, np.float32, 12), 15: (np.uint8, np.uint16, 25),
-           16: (np.uint16, np.uint8, 22)}
+           16: (np.uint16, np.uint8, 22), 17: (np.uint8, np.uint8, 29), 18: (np.uint8, np.uint8, 22),
+           19: (np.float32, np.uint8, 1), 20: (np.float32, np.uint16, 26), 21: (None, None, 22), 22: (None, None, 25)}
+# bands the step adds (BW2sRGB / GREY162RGB16: one band becomes three) or removes (scRGB2BW: three become one)
+STEP_BANDS = {19: -2, 20: -2, 21: 2, 22: 2}
 
 
 def _space(s):
@@ -212,7 +216,7 @@ def colour_step(a, step, interpretation):
     rescaled / cast / re-attached as vips_colour_build does)."""
     a, h, w, b, f = _img(a)
     step = STEPS[step] if isinstance(step, str) else step
-    out = np.empty((h, w, b), STEP_IO[step][1])
+    out = np.empty((h, w, b + STEP_BANDS.get(step, 0)), STEP_IO[step][1] or a.dtype)
     if lib().orc_colour_step(step, _p(a), w, h, b, f, _space(interpretation), _p(out)):
         raise ValueError("colour_step")
     return out
@@ -221,7 +225,7 @@ def colour_step(a, step, interpretation):
 def colourspace(a, space, source_space):
     a, h, w, b, f = _img(a)
     to, frm = _space(space), _space(source_space)
-    out = np.empty((h, w, b), DTYPE[lib().orc_colourspace_format(to)])
+    out = np.empty((h, w, lib().orc_colourspace_bands(frm, to, b)), DTYPE[lib().orc_colourspace_out_format(frm, to, f)])
     if lib().orc_colourspace(_p(a), w, h, b, f, frm, to, _p(out)):
         raise ValueError("colourspace %s -> %s" % (source_space, space))
     return out

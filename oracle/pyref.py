@@ -158,7 +158,7 @@ def colour_line(step, a):
     step = pyoracle.STEPS[step] if isinstance(step, str) else step
     a = np.ascontiguousarray(a).reshape(-1, 3)
     assert a.dtype == pyoracle.STEP_IO[step][0], (a.dtype, step)
-    out = np.empty(a.shape, pyoracle.STEP_IO[step][1])
+    out = np.empty((a.shape[0], 3 + pyoracle.STEP_BANDS.get(step, 0)), pyoracle.STEP_IO[step][1])
     L = lib()
     L.ref_colour_line.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     if L.ref_colour_line(step, a.ctypes.data, out.ctypes.data, a.shape[0]):

@@ -14,6 +14,9 @@
 #include "LCh2Lab.c"
 #include "XYZ2Yxy.c"
 #include "Yxy2XYZ.c"
+#include "sRGB2HSV.c"
+#include "HSV2sRGB.c"
+#include "scRGB2BW.c"
 
 /* step numbers as in oracle/colour_oracle.cpp */
 int
@@ -107,6 +110,26 @@ ref_colour_line(int step, const void *in, void *out, int n)
 		vips_Yxy2XYZ_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
 		return 0;
 	}
+	case 17: {
+		VipssRGB2HSV obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_sRGB2HSV_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 18: {
+		VipsHSV2sRGB obj;
+		memset(&obj, 0, sizeof(obj));
+		vips_HSV2sRGB_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
+	case 19:
+	case 20: {
+		VipsscRGB2BW obj;
+		memset(&obj, 0, sizeof(obj));
+		obj.depth = step == 19 ? 8 : 16;
+		vips_scRGB2BW_line((VipsColour *) &obj, (VipsPel *) out, inp, n);
+		return 0;
+	}
 	}
 	return -1;
 }
@@ -153,7 +176,8 @@ vips_call_split(const char *operation_name, va_list optional, ...)
 		{ "XYZ2scRGB", vips_XYZ2scRGB_get_type }, { "XYZ2Lab", vips_XYZ2Lab_get_type }, { "Lab2XYZ", vips_Lab2XYZ_get_type },
 		{ "scRGB2sRGB", vips_scRGB2sRGB_get_type }, { "Lab2LabS", vips_Lab2LabS_get_type },
 		{ "LabS2Lab", vips_LabS2Lab_get_type }, { "Lab2LCh", vips_Lab2LCh_get_type }, { "LCh2Lab", vips_LCh2Lab_get_type },
-		{ "XYZ2Yxy", vips_XYZ2Yxy_get_type }, { "Yxy2XYZ", vips_Yxy2XYZ_get_type }
+		{ "XYZ2Yxy", vips_XYZ2Yxy_get_type }, { "Yxy2XYZ", vips_Yxy2XYZ_get_type }, { "sRGB2HSV", vips_sRGB2HSV_get_type },
+		{ "HSV2sRGB", vips_HSV2sRGB_get_type }, { "scRGB2BW", vips_scRGB2BW_get_type }
 	};
 	static const char *set_in[] = { "in", NULL };
 	va_list required;
@@ -185,6 +209,8 @@ vips_call_split(const char *operation_name, va_list optional, ...)
 	while ((name = va_arg(optional, const char *))) {
 		if (strcmp(name, "depth") == 0 && strcmp(operation_name, "scRGB2sRGB") == 0)
 			((VipsscRGB2sRGB *) colour)->depth = va_arg(optional, int);
+		else if (strcmp(name, "depth") == 0 && strcmp(operation_name, "scRGB2BW") == 0)
+			((VipsscRGB2BW *) colour)->depth = va_arg(optional, int);
 		else {
 			vips_error("shim", "vips_call_split: %s: option %s is not modelled", operation_name, name);
 			return -1;

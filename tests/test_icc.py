@@ -34,7 +34,7 @@ def host_eval(mode, a, pa, pb=None, depth=8, pcs=0, intent=1):
     ob = L.vb200_debug_icc_eval(mode, a.ctypes.data, FMT[a.dtype], a.shape[-1], out.ctypes.data, n, pa, len(pa), pb,
                                 len(pb) if pb else 0, intent, depth, pcs)
     if ob < 0:
-        raise vb.Error(L.vb200_error_buffer().decode())
+        raise vb.Error(L.vb200_error_buffer().decode(errors="replace"))
     return np.ascontiguousarray(out.reshape(-1)[: n * ob].reshape(n, ob))
 
 

