@@ -52,7 +52,8 @@ typedef enum {
 	VB200_INTERPRETATION_YXY = 23,
 	VB200_INTERPRETATION_RGB16 = 25,
 	VB200_INTERPRETATION_GREY16 = 26,
-	VB200_INTERPRETATION_scRGB = 28
+	VB200_INTERPRETATION_scRGB = 28,
+	VB200_INTERPRETATION_HSV = 29
 } VB200Interpretation;
 
 /* reference: VipsKernel, include/vips/resample.h:41-51 (same values) */
@@ -188,6 +189,10 @@ int vb200_thumbnail_image(const VB200Image *in, VB200Image *out, int width, int 
  * atan / cosf / sinf: float results within 1 ULP of the reference's glibc; everything else is exact).  Bands beyond the third are carried
  * as vips_colour_build does (colour.c:196-291).  sRGB <-> RGB16 are the reference's two rows that are not colour
  * conversions (colourspace.c:85-110, 372, 420): a shifting vips_cast over every band, alpha included (cast.c:137-164).
+ * B_W (uchar), GREY16 (ushort) and HSV (uchar) as source or target run the table's rows for them (BW2sRGB /
+ * GREY162RGB16 / HSV2sRGB first, scRGB2BW / sRGB2HSV last: colour_ext.cu) as the leaf kernel(s) plus the fused route
+ * kernel between; sRGB / RGB16 / scRGB -> B_W / GREY16 is a single launch.  B_W / GREY16 sources gain two bands,
+ * targets lose two.  All exact.
  */
 int vb200_colourspace(const VB200Image *in, VB200Image *out, int space);
 
@@ -317,6 +322,9 @@ size_t vb200_thumbnail_plan_bytes_per_frame(const VB200ThumbnailPlan *plan);
  * or "leaf kernels" for an unfused plan.
  */
 const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
+
+/* test hook, host only: the sRGB <-> HSV per-pixel code of colour_ext.cu on the CPU; n pixels of 3 bytes */
+int vb200_debug_hsv_host(const void *in, size_t n, int to_hsv, void *out);
 
 /* ------------------------------------------------------------ flatten
  * reference: vips_flatten(), conversion/flatten.c:600-616 (build :421-527; generate functions :170-419).  Blends the

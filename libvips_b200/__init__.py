@@ -28,7 +28,7 @@ PRECISIONS = {"integer": 0, "float": 1, "approximate": 2}
 INTENTS = {"perceptual": 0, "relative": 1, "saturation": 2, "absolute": 3}
 PCS = {"lab": 0, "xyz": 1}
 INTERPRETATIONS = {"multiband": 0, "b-w": 1, "cmyk": 15, "xyz": 12, "lab": 13, "lch": 19, "labs": 21, "srgb": 22,
-                   "yxy": 23, "rgb16": 25, "grey16": 26, "scrgb": 28}
+                   "yxy": 23, "rgb16": 25, "grey16": 26, "scrgb": 28, "hsv": 29}
 
 
 class Error(Exception):
@@ -138,6 +138,7 @@ def lib():
         L.vb200_morph.argtypes = [IP, IP, MP, C.c_int]
         L.vb200_chain_add_morph.argtypes = [C.c_void_p, MP, C.c_int]
         L.vb200_rank.argtypes = [IP, IP, C.c_int, C.c_int, C.c_int]
+        L.vb200_debug_hsv_host.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
         L.vb200_flatten.argtypes = [IP, IP, C.c_void_p, C.c_int, C.c_double]
         L.vb200_chain_add_flatten.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         L.vb200_debug_flatten_host.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]
@@ -414,6 +415,14 @@ def rank_host_twin(a, width, height, index):
     out = np.empty_like(a)
     _check(lib().vb200_debug_rank_host(a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.shape[2], FORMATS[a.dtype], int(width),
                                        int(height), int(index), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def hsv_host_twin(a, to_hsv):
+    """colour_ext.cu's sRGB <-> HSV per-pixel code compiled for the host (vb200_debug_hsv_host); a: (n, 3) uint8"""
+    a = np.ascontiguousarray(a, np.uint8).reshape(-1, 3)
+    out = np.empty_like(a)
+    _check(lib().vb200_debug_hsv_host(a.ctypes.data_as(C.c_void_p), a.shape[0], int(bool(to_hsv)), out.ctypes.data_as(C.c_void_p)))
     return out
 
 

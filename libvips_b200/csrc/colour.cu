@@ -498,6 +498,8 @@ colour_route_params(const char *domain, int source_space, int space, RouteParams
 int
 dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space, cudaStream_t s)
 {
+	if (colour_ext_space(space) || colour_ext_space(source_space))
+		return dev_colourspace_ext(domain, in, out, space, source_space, s); /* colour_ext.cu */
 	int steps[8];
 	const dim3 block(256);
 	const bool up = source_space == VB200_INTERPRETATION_sRGB && space == VB200_INTERPRETATION_RGB16;
@@ -596,8 +598,8 @@ vb200_colourspace(const VB200Image *in, VB200Image *out, int space)
 	DevImage din, dout;
 	if (to_device(domain, in, &din, s))
 		return -1;
-	/* colour ops keep the geometry and band count; no output element is wider than a float */
-	preset_output(&dout, in, out, (size_t) in->Xsize * in->Bands * 4, in->Ysize);
+	/* colour ops keep the geometry; B_W / GREY16 sources gain two bands; no output element is wider than a float */
+	preset_output(&dout, in, out, (size_t) in->Xsize * (in->Bands + 2) * 4, in->Ysize);
 	int rc = dev_colourspace(domain, din, &dout, space, in->Type, s);
 	if (!rc)
 		rc = deliver(domain, &dout, in, out, s);

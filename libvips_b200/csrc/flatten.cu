@@ -20,7 +20,7 @@
  * to an integer type (`TYPE nalpha = max_alpha - alpha` with max_alpha beyond the format, flatten.c:135, undefined in C):
  * char / short / uint / int outside the double detour, ushort unless max_alpha is 65535; double images; > 17 bands.
  *
- * The per-pixel code is __host__ __device__: vb200_debug_flatten_host runs it on the CPU (tests/test_flatten.py).
+ * The per-pixel code is __host__ __device__: vb200_debug_flatten_host runs it on the CPU (tests/test_widen_flatten.py).
  */
 #include <climits>
 #include <cstring>

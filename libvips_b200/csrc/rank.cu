@@ -15,7 +15,7 @@
  * Algorithmic bytes: w * h * bands * sizeof(element), in and out.
  *
  * The tile staging and the per-element select are __host__ __device__ functions of (tid, nthreads):
- * vb200_debug_rank_host runs the very same code on the CPU, tile by tile (tests/test_rank.py, no GPU needed).
+ * vb200_debug_rank_host runs the very same code on the CPU, tile by tile (tests/test_widen_rank.py, no GPU needed).
  * Floats: NaNs order by their bit patterns (the reference's comparisons leave their place undefined); -0 < +0.
  */
 #include <cstring>

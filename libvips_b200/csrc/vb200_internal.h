@@ -158,6 +158,10 @@ int dev_rank(const char *domain, const DevImage &in, DevImage *out, int width, i
 int dev_colourspace(const char *domain, const DevImage &in, DevImage *out, int space, int source_space,
 	cudaStream_t s);
 
+/* colour_ext.cu: the B_W / GREY16 / HSV rows of the route table, composed of the route kernels and three leaf kernels */
+bool colour_ext_space(int space);
+int dev_colourspace_ext(const char *domain, const DevImage &in, DevImage *out, int space, int source_space, cudaStream_t s);
+
 /* Launchers of the row/column-table kernels on raw device pointers (used by
  * the generate()-shaped and scanline seams too).
  */

@@ -128,3 +128,52 @@ def test_oracle_colourspace_foreign_formats_match_reference_build():
                 assert dt not in (np.uint8, np.uint16), (dt, src, dst)
                 continue
             assert got.dtype == want.dtype and np.array_equal(got, want, equal_nan=True), (dt, src, dst)
+
+
+def test_hsv_host_twin_matches_oracle_on_every_input():
+    """hsv_kernel's per-pixel code (explicit round-to-nearest operations, fmodf(x, 2) as x - 2 floor(x / 2)) compiled
+    for the host, against the oracle (which the test above pins to the reference): all 2^24 inputs, both ways"""
+    import libvips_b200 as vb
+    a = all_triples()
+    for step, to_hsv in (("sRGB2HSV", True), ("HSV2sRGB", False)):
+        want = orc.colour_step(a.reshape(4096, 4096, 3), step, "srgb" if to_hsv else "hsv").reshape(-1, 3)
+        assert np.array_equal(vb.hsv_host_twin(a, to_hsv), want), step
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [0, 1])
+def test_gpu_routes(vb, extra):
+    rng = np.random.default_rng(80 + extra)
+    for src, dst in pairs():
+        if "lch" in (src, dst):
+            continue  # the two LCh steps call atan / cosf / sinf (1 ULP against glibc): tests/test_colour.py holds them
+        bands = (1 if src in ("b-w", "grey16") else 3) + extra
+        a = sample(src, rng, 67 * 129, bands).reshape(67, 129, bands)
+        got = vb.Image(a, src).colourspace(dst)
+        want = orc.colourspace(a, dst, src)
+        assert got.array.dtype == want.dtype and got.array.shape == want.shape, (src, dst)
+        assert np.array_equal(got.numpy(), want, equal_nan=True), (src, dst, extra)
+        assert got.interpretation == vb.INTERPRETATIONS[dst]
+
+
+@pytest.mark.gpu
+def test_gpu_hsv_every_input_and_greyscale_at_size(vb):
+    a = all_triples().reshape(4096, 4096, 3)
+    hsv = vb.Image(a, "srgb").colourspace("hsv").numpy()
+    assert np.array_equal(hsv, orc.colour_step(a, "sRGB2HSV", "srgb"))
+    assert np.array_equal(vb.Image(a, "hsv").colourspace("srgb").numpy(), orc.colour_step(a, "HSV2sRGB", "hsv"))
+    # the common call: sRGB -> B_W, one launch, every sRGB triple
+    before = vb.launch_count()
+    bw = vb.Image(a, "srgb").colourspace("b-w").numpy()
+    assert vb.launch_count() - before == 1
+    assert bw.shape == (4096, 4096, 1) and np.array_equal(bw, orc.colourspace(a, "b-w", "srgb"))
+    # grey -> rgb -> grey is the identity (8 and 16 bit)
+    g = np.arange(256, dtype=np.uint8).reshape(16, 16, 1)
+    assert np.array_equal(vb.Image(g, "b-w").colourspace("srgb").colourspace("b-w").numpy(), g)
+    with pytest.raises(vb.Error, match="wants band format"):
+        vb.Image(g.astype(np.float32), "b-w").colourspace("srgb")
+    # in a chain: greyscale, then a median
+    from oracle import pyconv
+    c = np.ascontiguousarray(a[:90, :120])
+    got = vb.Chain().colourspace("b-w").rank(3, 3, 4).run([c])[0].numpy()
+    assert np.array_equal(got, pyconv.median(orc.colourspace(c, "b-w", "srgb"), 3))
