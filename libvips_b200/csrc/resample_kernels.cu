@@ -1246,6 +1246,26 @@ dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale,
 		}
 		return dev_resize_up(domain, in, out, hscale, vscale, kernel, s);
 	}
+	if (kernel == VB200_KERNEL_NEAREST) {
+		/* resize.c:166-204: VIPS_KERNEL_NEAREST first drops whole pixels with vips_subsample (the integer part of the
+		 * shrink over gap), then reduces the residual.  The subsample step is not on the device path: when it would
+		 * run, decline -- a direct nearest reduce by the whole factor picks different pixels and another size.
+		 */
+		int xfac, yfac;
+		if (gap < 1.0) {
+			xfac = (int) floor(1.0 / hscale);
+			yfac = (int) floor(1.0 / vscale);
+		}
+		else {
+			const int target_width = VB200_ROUND_UINT(in.w * hscale), target_height = VB200_ROUND_UINT(in.h * vscale);
+			xfac = target_width > 0 ? (int) floor((double) in.w / target_width / gap) : 1;
+			yfac = target_height > 0 ? (int) floor((double) in.h / target_height / gap) : 1;
+		}
+		if (xfac > 1 || yfac > 1) {
+			error(domain, "nearest-neighbour resize with a subsample step (%d x %d) is not on the device path", xfac, yfac);
+			return -1;
+		}
+	}
 	const double vs = vscale < 1.0 ? 1.0 / vscale : 1.0;
 	const double hs = hscale < 1.0 ? 1.0 / hscale : 1.0;
 	return dev_reduce_chain(domain, in, out, hs, vs, kernel, gap, s);

@@ -847,6 +847,28 @@ resize_shrinks(int w, int h, double hscale, double vscale, double *hshrink, doub
 	*hshrink = hscale < 1.0 ? 1.0 / hscale : 1.0;
 }
 
+/* vips_resize with VIPS_KERNEL_NEAREST first drops whole pixels (resize.c:166-204): the integer part of the shrink, over
+ * `gap`, goes to vips_subsample -- out(x, y) = in(x * xfac, y * yfac), size in / fac rounded DOWN (subsample.c:83-190,
+ * 218-222) -- and the scales are multiplied up for the residual reducev / reduceh.
+ */
+static void
+nearest_subsample(int w, int h, double hscale, double vscale, double gap, int *xfac, int *yfac)
+{
+	int int_hshrink, int_vshrink;
+	if (gap < 1.0) {
+		int_hshrink = (int) floor(1.0 / hscale);
+		int_vshrink = (int) floor(1.0 / vscale);
+	}
+	else {
+		const int target_width = (int) (w * hscale + 0.5);	 /* VIPS_ROUND_UINT */
+		const int target_height = (int) (h * vscale + 0.5);
+		int_hshrink = (int) floor((double) w / target_width / gap);
+		int_vshrink = (int) floor((double) h / target_height / gap);
+	}
+	*xfac = std::max(1, int_hshrink);
+	*yfac = std::max(1, int_vshrink);
+}
+
 extern "C" int orc_affine_size(int w, int h, double a, double b, double c, double d, int *ow, int *oh);
 extern "C" int orc_affine(const void *in, int w, int h, int bands, int fmt, double a, double b, double c, double d,
 	int interp, double idx, double idy, double odx, double ody, int tile_w, int tile_h, void *out);
@@ -871,6 +893,18 @@ orc_resize_size(int w, int h, double hscale, double vscale, int kernel, double g
 	double hs, vs;
 	OrcReduceGeom g;
 	int mixed;
+	if (kernel == ORC_KERNEL_NEAREST && hscale > 0 && vscale > 0 && (int) (w * hscale + 0.5) > 0 && (int) (h * vscale + 0.5) > 0) {
+		int xfac, yfac;
+		nearest_subsample(w, h, hscale, vscale, gap, &xfac, &yfac);
+		if (xfac > 1 || yfac > 1) {
+			w /= xfac;
+			h /= yfac;
+			if (w <= 0 || h <= 0)
+				return -1; /* "image has shrunk to nothing", subsample.c:223-228 */
+			hscale *= xfac;
+			vscale *= yfac;
+		}
+	}
 	if (resize_is_upsize(w, h, hscale, vscale, &mixed)) {
 		double a, d, idx, idy;
 		int interp;
@@ -917,8 +951,9 @@ chain_tiles(int out_w, bool has_shrinkv, bool has_reduce, int *tile_w, int *tile
 	}
 }
 
-extern "C" int
-orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, double vscale, int kernel, double gap,
+/* vips_resize after the NEAREST pre-shrink (orc_resize below): residual reduce, or the affine for enlargements */
+static int
+resize_residual(const void *in, int w, int h, int bands, int fmt, double hscale, double vscale, int kernel, double gap,
 	int tile_w, int tile_h, void *out)
 {
 	double hs, vs;
@@ -996,6 +1031,28 @@ orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, doub
 		return orc_reduceh(src, w, gv.out_size, bands, fmt, hs, kernel, gap, rect_w, out);
 	memcpy(out, src, (size_t) w * gv.out_size * bands * es);
 	return 0;
+}
+
+extern "C" int
+orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, double vscale, int kernel, double gap,
+	int tile_w, int tile_h, void *out)
+{
+	if (kernel == ORC_KERNEL_NEAREST && hscale > 0 && vscale > 0 && (int) (w * hscale + 0.5) > 0 && (int) (h * vscale + 0.5) > 0) {
+		int xfac, yfac;
+		nearest_subsample(w, h, hscale, vscale, gap, &xfac, &yfac);
+		if (xfac > 1 || yfac > 1) {
+			const int sw = w / xfac, sh = h / yfac;
+			if (sw <= 0 || sh <= 0)
+				return -1; /* "image has shrunk to nothing", subsample.c:223-228 */
+			const size_t ps = orc_sizeof_format(fmt) * bands;
+			std::vector<uint8_t> sub((size_t) sw * sh * ps);
+			for (int y = 0; y < sh; y++)
+				for (int x = 0; x < sw; x++)
+					memcpy(&sub[((size_t) y * sw + x) * ps], (const char *) in + ((size_t) y * yfac * w + (size_t) x * xfac) * ps, ps);
+			return resize_residual(sub.data(), sw, sh, bands, fmt, hscale * xfac, vscale * yfac, kernel, gap, tile_w, tile_h, out);
+		}
+	}
+	return resize_residual(in, w, h, bands, fmt, hscale, vscale, kernel, gap, tile_w, tile_h, out);
 }
 
 /* ------------------------------------------------------------- thumbnail */

@@ -38,3 +38,16 @@ def test_error_buffer_without_gpu():
     L.vb200_error_clear()
     assert L.vb200_error_buffer() == b""
     assert L.vb200_format_sizeof(0) == 1 and L.vb200_format_sizeof(6) == 4
+
+
+def test_isenabled_switch(monkeypatch):
+    """vb200_isenabled mirrors vips_vector_isenabled / VIPS_NOVECTOR (iofuncs/vector.cpp:98-110): VB200_DISABLE switches the
+    device path off; otherwise it is on exactly when a CUDA device is present (none in the CPU container)"""
+    import libvips_b200 as vb
+    L = vb.lib()
+    monkeypatch.setenv("VB200_DISABLE", "1")
+    assert L.vb200_isenabled() == 0
+    monkeypatch.setenv("VB200_DISABLE", "0")
+    assert L.vb200_isenabled() in (0, 1)
+    monkeypatch.delenv("VB200_DISABLE")
+    assert L.vb200_isenabled() in (0, 1)
