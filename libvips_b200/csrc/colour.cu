@@ -598,8 +598,11 @@ vb200_colourspace(const VB200Image *in, VB200Image *out, int space)
 	DevImage din, dout;
 	if (to_device(domain, in, &din, s))
 		return -1;
-	/* colour ops keep the geometry; B_W / GREY16 sources gain two bands; no output element is wider than a float */
-	preset_output(&dout, in, out, (size_t) in->Xsize * (in->Bands + 2) * 4, in->Ysize);
+	/* colour ops keep the geometry and, but for B_W / GREY16 sources (two bands more), the band count; no output element is
+	 * wider than a float
+	 */
+	const bool grey_source = in->Type == VB200_INTERPRETATION_B_W || in->Type == VB200_INTERPRETATION_GREY16;
+	preset_output(&dout, in, out, (size_t) in->Xsize * (in->Bands + (grey_source ? 2 : 0)) * 4, in->Ysize);
 	int rc = dev_colourspace(domain, din, &dout, space, in->Type, s);
 	if (!rc)
 		rc = deliver(domain, &dout, in, out, s);
