@@ -389,7 +389,8 @@ int vb200_chain_run_host(VB200Chain *chain, const VB200Image *in, VB200Image *ou
  * pinned to lcms2 2.18 within a tolerance (tests/test_icc.py), not bit for bit.  Supported: RGB
  * matrix/TRC, grey TRC, lut8 / lut16 (e.g. CMYK) and v4 lutAtoB / lutBtoA profiles; intent VB200_INTENT_RELATIVE (the
  * reference's default), and PERCEPTUAL / SATURATION for matrix / grey profiles with a zero black point (where
- * lcms2's black point compensation is the identity); depth 8 or 16;
+ * lcms2's black point compensation is the identity), and ABSOLUTE for matrix / TRC profiles (lcms2's media-white scale,
+ * folded into the colorant matrix); depth 8 or 16;
  * bands after the profile's channels ride along as in vips_colour_build.  Everything else (the other
  * intents, black point compensation) returns -1: keep the host path.
  */

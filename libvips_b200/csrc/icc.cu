@@ -11,8 +11,10 @@
  *   - RGB matrix/TRC profiles (rXYZ gXYZ bXYZ + curv / para TRCs), grey TRC profiles,
  *   - lut16 / lut8 (mft2 / mft1) and v4 lutAtoB / lutBtoA (mAB / mBA) A2Bn / B2An profiles, XYZ or Lab PCS,
  *   - relative colorimetric (the reference's default intent); perceptual / saturation where lcms2's
- *     black point compensation is the identity (matrix / grey profiles whose TRCs map 0 to 0).
- * Absolute colorimetric, black point compensation proper, device-link and
+ *     black point compensation is the identity (matrix / grey profiles whose TRCs map 0 to 0);
+ *   - absolute colorimetric on matrix / TRC profiles (the media-white scale of lcms2's ComputeAbsoluteIntent folds into
+ *     the colorant matrix on the host, parse_side), and on any profile where that scale is the identity.
+ * Absolute colorimetric of lut / grey profiles with a scale, black point compensation proper, device-link and
  * named-colour profiles return -1 ("keep the host path").
  *
  * PARITY: pinned to lcms2 2.18 (oracle/pylcms.py makes the reference's exact lcms2 calls) within a
@@ -355,17 +357,55 @@ int black_is_zero(const char *domain, const IccSide *s, const std::vector<float>
 
 /* One direction of one profile: to_pcs (A2B / forward matrix) or from_pcs (B2A / inverse matrix). */
 int
-parse_side(const char *domain, const void *data, size_t len, int intent, bool to_pcs, IccSide *s, std::vector<float> &pool)
+parse_side(const char *domain, const void *data, size_t len, int intent, bool to_pcs, bool other_is_lab4_d65, IccSide *s,
+	std::vector<float> &pool)
 {
 	const Blob b{(const unsigned char *) data, len};
 	if (!data || len < 132 || b.u32(0) > len || memcmp(b.d + 36, "acsp", 4) != 0) {
 		error(domain, "not an ICC profile");
 		return -1;
 	}
-	if (intent < 0 || intent > 2) {
-		/* absolute colorimetric needs the media white points: not evaluated here */
+	if (intent < 0 || intent > 3) {
 		error(domain, "rendering intent %d not supported on the device path", intent);
 		return -1;
+	}
+	/* Absolute colorimetric (lcms2 cmscnvrt.c ComputeAbsoluteIntent at its default adaptation state 1.0): the relative
+	 * transform with PCS XYZ scaled by media white / D50 on the way in and D50 / media white on the way out.  The media
+	 * white is the wtpt tag, D50 when it is absent or for a v2 display-class profile (cmsio1.c _cmsReadMediaWhitePoint).
+	 * The profile at the other end is another device profile (vips_icc_transform: both sides scale against D50 and the
+	 * D50s cancel), the XYZ PCS profile (cmsCreateXYZProfile: D50), or the Lab PCS profile the reference makes with
+	 * cmsCreateLab4Profile(cmsWhitePointFromTemp(6504 K)) (icc_transform.c:355-362), whose media white in lcms2 2.18 is
+	 * that D65 white -- so with the Lab PCS absolute colorimetric scales even a D50 profile.
+	 * For a matrix / TRC profile the scale folds into the colorant matrix right here, on the host; where it is the
+	 * identity the intent is the relative one; anything else (a lut or grey profile with another media white) would need
+	 * the scale inside the evaluator and is declined.
+	 */
+	double white_scale[3] = {1.0, 1.0, 1.0};
+	bool scaled = false;
+	if (intent == 3) {
+		double wp[3] = {0.9642, 1.0, 0.8249}, other[3] = {0.9642, 1.0, 0.8249}; /* cmsD50X / Y / Z */
+		const bool v2_display = b.u32(8) < 0x04000000u && memcmp(b.d + 12, "mntr", 4) == 0;
+		double tag[3];
+		if (!v2_display && parse_xyz(b, "wtpt", tag))
+			memcpy(wp, tag, sizeof(wp));
+		if (other_is_lab4_d65) {
+			/* cmsWhitePointFromTemp(6504), cmswtpnt.c (4000 .. 7000 K branch), then xyY -> XYZ at Y = 1 */
+			const double T = 6504.0, T2 = T * T, T3 = T2 * T;
+			const double x = -4.6070 * (1E9 / T3) + 2.9678 * (1E6 / T2) + 0.09911 * (1E3 / T) + 0.244063;
+			const double y = -3.000 * (x * x) + 2.870 * x - 0.275;
+			other[0] = x / y;
+			other[1] = 1.0;
+			other[2] = (1.0 - x - y) / y;
+		}
+		for (int i = 0; i < 3; i++) {
+			if (!(wp[i] > 0.0)) {
+				error(domain, "bad media white point");
+				return -1;
+			}
+			white_scale[i] = to_pcs ? wp[i] / other[i] : other[i] / wp[i];
+			scaled = scaled || white_scale[i] != 1.0;
+		}
+		intent = 1;
 	}
 	const unsigned char *cs = b.d + 16, *pcs = b.d + 20;
 	s->pcs_lab = memcmp(pcs, "Lab ", 4) == 0;
@@ -389,6 +429,10 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 	size_t off, tl;
 	const char *want = find_tag(b, tags[intent], &off, &tl) ? tags[intent] : (find_tag(b, tags[0], &off, &tl) ? tags[0] : nullptr);
 	s->to_pcs = to_pcs;
+	if (want && scaled) {
+		error(domain, "absolute colorimetric intent of a lut-based profile whose media white is not D50 is not supported on the device path");
+		return -1;
+	}
 	if (want && intent != 1) {
 		/* perceptual / saturation against the v4 Lab / XYZ PCS profiles make lcms2 turn black point compensation
 		 * on (cmscnvrt.c); for a lut profile that needs its black point, which is not evaluated here
@@ -431,6 +475,10 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 			error(domain, "grey profile without a usable kTRC");
 			return -1;
 		}
+		if (scaled) {
+			error(domain, "absolute colorimetric intent of a grey profile whose media white is not D50 is not supported on the device path");
+			return -1;
+		}
 		s->model = MODEL_GREY;
 		return black_is_zero(domain, s, pool, intent);
 	}
@@ -446,11 +494,19 @@ parse_side(const char *domain, const void *data, size_t len, int intent, bool to
 		for (int r = 0; r < 3; r++)
 			for (int c = 0; c < 3; c++)
 				m[r * 3 + c] = col[c][r];
-		if (to_pcs)
-			memcpy(s->m, m, sizeof(m));
-		else if (!invert3(m, s->m)) {
-			error(domain, "singular colorant matrix");
-			return -1;
+		if (to_pcs) {
+			for (int r = 0; r < 3; r++) /* XYZ_abs = diag(white / D50) M lin */
+				for (int c = 0; c < 3; c++)
+					s->m[r * 3 + c] = white_scale[r] * m[r * 3 + c];
+		}
+		else {
+			if (!invert3(m, s->m)) {
+				error(domain, "singular colorant matrix");
+				return -1;
+			}
+			for (int r = 0; r < 3; r++) /* lin = M^-1 diag(D50 / white) XYZ_abs */
+				for (int c = 0; c < 3; c++)
+					s->m[r * 3 + c] *= white_scale[c];
 		}
 		s->model = MODEL_MATRIX;
 		return black_is_zero(domain, s, pool, intent);
@@ -1085,7 +1141,7 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, int i
 		return -1;
 	}
 	if (sp.mode == 0 || sp.mode == 2) {
-		if (parse_side(domain, sp.pa, sp.la, sp.intent, true, &J->in, pool))
+		if (parse_side(domain, sp.pa, sp.la, sp.intent, true, sp.mode == 0 && !sp.pcs_xyz, &J->in, pool))
 			return -1;
 		if (in_fmt != VB200_FORMAT_UCHAR && in_fmt != VB200_FORMAT_USHORT && in_fmt != VB200_FORMAT_FLOAT) {
 			error(domain, "band format %d not supported on the device path", in_fmt);
@@ -1100,7 +1156,7 @@ build_job(const char *domain, const JobSpec &sp, int in_fmt, int in_bands, int i
 	if (sp.mode == 1 || sp.mode == 2) {
 		const void *p = sp.mode == 1 ? sp.pa : sp.pb;
 		const size_t l = sp.mode == 1 ? sp.la : sp.lb;
-		if (parse_side(domain, p, l, sp.intent, false, &J->out, pool))
+		if (parse_side(domain, p, l, sp.intent, false, sp.mode == 1 && !sp.pcs_xyz, &J->out, pool))
 			return -1;
 	}
 	if (sp.mode == 1) {

@@ -84,6 +84,51 @@ def test_matrix_profiles_other_intents(intent):
     assert np.array_equal(pylcms.icc_import(g, F.grey_profile(), intent), pylcms.icc_import(g, F.grey_profile(), "relative"))
 
 
+def _rgb_profile_with_white(white, version=0x04200000, cls="mntr", trc="srgb"):
+    curve = F._para(*F._SRGB_PARA) if trc == "srgb" else F._curv([2.2])
+    tags = [("desc", F._text("desc", "vb200 test rgb")), ("cprt", F._text("cprt", "none")), ("wtpt", F._xyz_tag(*white))]
+    for name, col in zip("rgb", F._SRGB_COL):
+        tags.append((name + "XYZ", F._xyz_tag(*col)))
+    for name in "rgb":
+        tags.append((name + "TRC", curve))
+    return F._profile(version, cls, "RGB ", "XYZ ", tags)
+
+
+@needs_lcms
+@pytest.mark.parametrize("white", [(0.90, 1.0, 0.70), (0.9642, 1.0, 0.8249), (0.95, 0.98, 1.05)])
+@pytest.mark.parametrize("version,cls", [(0x04200000, "mntr"), (0x02100000, "mntr"), (0x02100000, "scnr")])
+def test_absolute_colorimetric_against_lcms2(white, version, cls):
+    """intent 3 on matrix / TRC profiles: the relative transform with PCS XYZ scaled by media white over the other end's
+    media white (lcms2 ComputeAbsoluteIntent, adaptation state 1): the wtpt tag, but D50 for a v2 display profile; D50 for
+    the XYZ PCS profile; the D65 white of cmsWhitePointFromTemp(6504) for the reference's Lab PCS profile -- so with the
+    default Lab PCS even a D50 profile is scaled.  Same tolerances as the relative intent."""
+    prof = _rgb_profile_with_white(white, version, cls)
+    rng = np.random.default_rng(13)
+    a8 = rng.integers(0, 256, (20000, 3), dtype=np.uint8)
+    lab = pylcms.icc_import(a8, prof, "absolute")
+    assert de(lab, pylcms.icc_import(a8, prof, "relative")).max() > 2      # it is another transform
+    d = de(host_eval(0, a8, prof, intent=3), lab)
+    assert d.max() < 0.8 and d.mean() < 0.05
+    af = rng.random((20000, 3), dtype=np.float32)
+    assert np.abs(host_eval(0, af, prof, intent=3) - pylcms.icc_import(af, prof, "absolute")).max() < 0.03
+    d = np.abs(host_eval(1, lab, prof, intent=3).astype(int) - pylcms.icc_export(lab, prof, "absolute").astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.002
+    xyz = pylcms.icc_import(a8, prof, "absolute", pcs="xyz")
+    assert np.abs(host_eval(0, a8, prof, pcs=1, intent=3) - xyz).max() < 0.08
+    d = np.abs(host_eval(1, xyz, prof, pcs=1, intent=3).astype(int) - pylcms.icc_export(xyz, prof, "absolute", pcs="xyz").astype(int))
+    assert d.max() <= 1
+    # device to device: the two media whites against each other.  lcms2 evaluates float input exactly and resamples 8-bit
+    # input into a CLUT (the scale stage defeats its matrix-shaper shortcut): hold the first to 1 / 65535, the second as colours
+    other = _rgb_profile_with_white((0.95, 0.98, 1.05), 0x02100000, "scnr", "gamma")
+    f = (a8 / 255.0).astype(np.float32)
+    d = np.abs(host_eval(2, f, prof, other, intent=3, depth=16).astype(int) - pylcms.icc_transform(f, prof, other, "absolute", depth=16).astype(int))
+    assert d.max() <= 2 and d.mean() < 0.01
+    ours, theirs = host_eval(2, a8, prof, other, intent=3), pylcms.icc_transform(a8, prof, other, "absolute")
+    d = de(pylcms.icc_import(ours, other), pylcms.icc_import(theirs, other))
+    # the differences sit where the scaled colour leaves the target gamut and lcms2's 33-point CLUT interpolates across the clip
+    assert d.max() < 6.0 and np.percentile(d, 99) < 3.0 and d.mean() < 0.2, (d.max(), np.percentile(d, 99), d.mean())
+
+
 @needs_lcms
 def test_rgb_to_rgb_transform_against_lcms2():
     pa, pb = F.rgb_profile("srgb"), F.rgb_profile("gamma")
@@ -173,7 +218,11 @@ def test_known_answers_and_refusals():
     assert np.abs(lab - [[100, 0, 0], [0, 0, 0]]).max() < 0.02
     assert np.array_equal(host_eval(1, lab, prof), [[255, 255, 255], [0, 0, 0]])
     with pytest.raises(vb.Error, match="intent"):
-        host_eval(0, np.zeros((1, 3), np.uint8), prof, intent=3)                       # absolute colorimetric
+        host_eval(0, np.zeros((1, 3), np.uint8), prof, intent=4)
+    with pytest.raises(vb.Error, match="absolute colorimetric intent of a lut-based"):
+        host_eval(0, np.zeros((1, 4), np.uint8), F.ink_profile(), intent=3)            # the scale would sit inside the evaluator
+    with pytest.raises(vb.Error, match="absolute colorimetric intent of a grey"):
+        host_eval(0, np.zeros((1, 1), np.uint8), F.grey_profile(), intent=3)
     with pytest.raises(vb.Error, match="lut-based"):
         host_eval(0, np.zeros((1, 4), np.uint8), F.ink_profile(), intent=0)            # needs black point compensation
     with pytest.raises(vb.Error, match="bands"):
