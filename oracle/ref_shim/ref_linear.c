@@ -19,7 +19,7 @@ VipsImage *vips__shim_new_memory(int w, int h, int bands, VipsBandFormat fmt, Vi
 void
 vips_arithmetic_set_format_table(VipsArithmeticClass *class, const VipsBandFormat *format_table)
 {
-	class->format_table = format_table; /* arithmetic.c:836-843 */
+	class->format_table = format_table; /* arithmetic.c:537-544 */
 }
 
 int
