@@ -327,7 +327,7 @@ const char *vb200_thumbnail_plan_kernel(const VB200ThumbnailPlan *plan);
 int vb200_debug_hsv_host(const void *in, size_t n, int to_hsv, void *out);
 
 /* ------------------------------------------------------------ flatten
- * reference: vips_flatten(), conversion/flatten.c:600-616 (build :421-527; generate functions :170-419).  Blends the
+ * reference: vips_flatten(), conversion/flatten.c:605-616 (build :421-529; generate functions :170-419).  Blends the
  * last band (alpha) out against `background` (n = 1 or bands - 1 values; NULL / n = 0: black): bands - 1 bands out, same
  * format.  max_alpha <= 0: the interpretation's default (255, 65535 for RGB16 / GREY16, 1 for scRGB).  One-band images are
  * copied.  uchar .. float images; the integer cases where the reference's own arithmetic is undefined C (see flatten.cu)
@@ -344,7 +344,7 @@ int vb200_debug_flatten_host(const void *in, int width, int height, int bands, i
  */
 enum { VB200_MORPHOLOGY_ERODE = 0, VB200_MORPHOLOGY_DILATE = 1 };
 int vb200_morph(const VB200Image *in, VB200Image *out, const VB200Mask *mask, int morph);
-/* reference: vips_rank(), morphology/rank.c:623-635 (build :459-525, generate :404-456: histogram / select / max / min
+/* reference: vips_rank(), morphology/rank.c:623-635 (build :458-525, generate :414-456: histogram / select / max / min
  * loops, all "the index-th smallest element of the width x height window", per band; the window is centred at
  * (width / 2, height / 2), edges replicated); vips_median(), :651-664 = rank(size, size, size * size / 2).
  * uchar .. float images.  Errors as the reference: "window too large", "index out of range".

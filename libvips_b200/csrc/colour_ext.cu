@@ -1,12 +1,12 @@
 /* colour_ext.cu -- the B_W, GREY16 and HSV rows of vips_colourspace on the device.
  *
  * reference: colour/colourspace.c:223-497.  Every row that STARTS in one of these spaces opens with
- *     vips_BW2sRGB / vips_GREY162RGB16 (:150-186: vips__colourspace_process_n over a bandjoin of the first band with
- *     itself, other bands re-attached; the format stays, the Type becomes sRGB / RGB16) or vips_HSV2sRGB (HSV2sRGB.c:54-107)
+ *     vips_BW2sRGB / vips_GREY162RGB16 (:152-188: vips__colourspace_process_n over a bandjoin of the first band with
+ *     itself, other bands re-attached; the format stays, the Type becomes sRGB / RGB16) or vips_HSV2sRGB (HSV2sRGB.c:54-108)
  * and goes on as the sRGB / RGB16 row does; every row that ENDS there is the row to scRGB followed by
- *     vips_scRGB2BW (scRGB2BW.c:57-105 over vips_col_scRGB2BW, LabQ2sRGB.c:385-429: Y = 0.2126 R + 0.7152 G + 0.0722 B in
+ *     vips_scRGB2BW (scRGB2BW.c:58-105 over vips_col_scRGB2BW, LabQ2sRGB.c:385-429: Y = 0.2126 R + 0.7152 G + 0.0722 B in
  *     float, then the interpolated gamma table of scRGB -> sRGB; depth 8 -> B_W uchar, depth 16 -> GREY16 ushort)
- * or the row to sRGB followed by vips_sRGB2HSV (sRGB2HSV.c:48-125).  dev_colourspace_ext composes exactly those rows out
+ * or the row to sRGB followed by vips_sRGB2HSV (sRGB2HSV.c:50-126).  dev_colourspace_ext composes exactly those rows out
  * of the route kernels of colour.cu (untouched) and three leaf kernels here:
  *   replicate_kernel   one band -> three (+ extra bands copied)
  *   hsv_kernel         uchar sRGB <-> uchar HSV; the per-pixel arithmetic (float / double mix as the reference writes it,
@@ -48,7 +48,7 @@ constexpr int sRGB = VB200_INTERPRETATION_sRGB, RGB16 = VB200_INTERPRETATION_RGB
 #define CX_D2F(a) ((float) (a))
 #endif
 
-/* vips_sRGB2HSV_line's body, sRGB2HSV.c:57-121 */
+/* vips_sRGB2HSV_line's body, sRGB2HSV.c:57-122 */
 __host__ __device__ __forceinline__ void
 srgb2hsv_px(const uint8_t *p, uint8_t *q)
 {

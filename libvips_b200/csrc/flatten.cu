@@ -1,11 +1,11 @@
 /* flatten.cu -- vips_flatten on the device, SURVEY 8f rank 3 (conversion ops that share the pixel-wise kernel shape).
  *
- * reference: conversion/flatten.c:421-527 (vips_flatten_build) and its generate functions
- *   :170-237  vips_flatten_black_gen_uchar   q = p * lut[a],  lut[i] = (float) ((double) i / max_alpha)
- *   :304-367  vips_flatten_gen_uchar         q = p * fa[a] + ink * fn[a],  fn[i] = (float) ((max_alpha - i) / max_alpha)
- *   :240-300, :369-419 the per-format loops (:86-166): double arithmetic for the wider formats,
+ * reference: conversion/flatten.c:421-529 (vips_flatten_build) and its generate functions
+ *   :170-225  vips_flatten_black_gen_uchar   q = p * lut[a],  lut[i] = (float) ((double) i / max_alpha)
+ *   :293-354  vips_flatten_gen_uchar         q = p * fa[a] + ink * fn[a],  fn[i] = (float) ((max_alpha - i) / max_alpha)
+ *   :227-288, :358-419 the per-format loops (:88-166): double arithmetic for the wider formats,
  *                                            q = ((double) p * alpha + (double) ink * nalpha) / max_alpha
- *   :458-465, :519-523 integer images whose max_alpha is below the format's range are cast to double, flattened
+ *   :463-470, :519-523 integer images whose max_alpha is below the format's range are cast to double, flattened
  *             there and cast back (cast.c:123-131, 231-238: clip in double, truncate)
  * and vips__vector_to_ink (conversion/insert.c:244-359) for the background pixel: (float) bg through vips_linear, then
  * vips_cast to the working format.
@@ -17,7 +17,7 @@
  * Algorithmic bytes: w * h * (2 * bands - 1) * sizeof(element).
  *
  * Declined (-1, the host keeps its C path): the integer loops where the reference itself converts an out-of-range double
- * to an integer type (`TYPE nalpha = max_alpha - alpha` with max_alpha beyond the format, flatten.c:135, undefined in C):
+ * to an integer type (`TYPE nalpha = max_alpha - alpha` with max_alpha beyond the format, flatten.c:134, undefined in C):
  * char / short / uint / int outside the double detour, ushort unless max_alpha is 65535; double images; > 17 bands.
  *
  * The per-pixel code is __host__ __device__: vb200_debug_flatten_host runs it on the CPU (tests/test_widen_flatten.py).
@@ -221,7 +221,7 @@ flatten_plan(const char *domain, int bands, int fmt, int type, const double *bac
 		return -1;
 	}
 	if (max_alpha <= 0)
-		max_alpha = interpretation_max_alpha(type); /* flatten.c:449-450 */
+		max_alpha = interpretation_max_alpha(type); /* flatten.c:454-455 */
 	static const double zero = 0.0;
 	if (!background || n < 1) {
 		background = &zero; /* vips_flatten_init: background = {0} */
@@ -314,7 +314,7 @@ int
 dev_flatten(const char *domain, const DevImage &in, DevImage *out, const double *background, int n, double max_alpha, cudaStream_t s)
 {
 	if (in.bands == 1) {
-		/* flatten.c:440-443: a copy */
+		/* flatten.c:445-446: a copy */
 		if (dev_image_new(domain, out, in.w, in.h, 1, in.fmt, in.type, s))
 			return -1;
 		VB200_CUDA(domain, cudaMemcpy2DAsync(out->data, out->bpl, in.data, in.bpl, (size_t) in.w * format_sizeof(in.fmt), in.h,
@@ -363,7 +363,7 @@ dev_flatten(const char *domain, const DevImage &in, DevImage *out, const double 
 
 using namespace vb200;
 
-/* reference: vips_flatten(), conversion/flatten.c:600-616.  background: n = 1 or bands - 1 values (NULL: black);
+/* reference: vips_flatten(), conversion/flatten.c:605-616.  background: n = 1 or bands - 1 values (NULL: black);
  * max_alpha <= 0: the interpretation's default
  */
 extern "C" int

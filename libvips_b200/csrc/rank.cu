@@ -1,8 +1,8 @@
 /* rank.cu -- vips_rank / vips_median on the device, SURVEY 8f rank 4.
  *
- * reference: morphology/rank.c:459-525 (vips_rank_build: window within the image, 0 <= index < n, embed at
- * (width / 2, height / 2) with VIPS_EXTEND_COPY), :404-456 (vips_rank_generate), and its four inner loops -- uchar
- * histogram :154-221, Numerical-Recipes select :225-305, max :309-338, min :342-369.  All four return the same
+ * reference: morphology/rank.c:458-525 (vips_rank_build: window within the image, 0 <= index < n, embed at
+ * (width / 2, height / 2) with VIPS_EXTEND_COPY), :414-456 (vips_rank_generate), and its four inner loops -- uchar
+ * histogram :165-232, Numerical-Recipes select :236-323, max :327-352, min :356-381.  All four return the same
  * thing, the index-th smallest element of the width x height window of every band, which is what is computed here.
  *
  * One CTA stages the (TX + width - 1) x (TY + height - 1) pixel window of a TX x TY output tile into shared memory,
@@ -161,7 +161,7 @@ int
 rank_plan(const char *domain, int w, int h, int bands, int fmt, int rw, int rh, int index, RankDev *P, size_t *smem)
 {
 	if (rw < 1 || rh < 1 || rw > w || rh > h) {
-		error(domain, "window too large"); /* rank.c:479-483 */
+		error(domain, "window too large"); /* rank.c:478-483 */
 		return -1;
 	}
 	if (index < 0 || index > rw * rh - 1) {

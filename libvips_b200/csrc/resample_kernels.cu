@@ -1247,7 +1247,7 @@ dev_resize(const char *domain, const DevImage &in, DevImage *out, double hscale,
 		return dev_resize_up(domain, in, out, hscale, vscale, kernel, s);
 	}
 	if (kernel == VB200_KERNEL_NEAREST) {
-		/* resize.c:166-204: VIPS_KERNEL_NEAREST first drops whole pixels with vips_subsample (the integer part of the
+		/* resize.c:167-205: VIPS_KERNEL_NEAREST first drops whole pixels with vips_subsample (the integer part of the
 		 * shrink over gap), then reduces the residual.  The subsample step is not on the device path: when it would
 		 * run, decline -- a direct nearest reduce by the whole factor picks different pixels and another size.
 		 */

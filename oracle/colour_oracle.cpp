@@ -427,7 +427,7 @@ Yxy2XYZ_line(const float *p, float *q, size_t n)
 
 /* ---- SURVEY 8f rank 3, second lot: sRGB <-> HSV, scRGB -> B_W / GREY16, B_W -> sRGB, GREY16 -> RGB16 */
 
-/* vips_sRGB2HSV_line, sRGB2HSV.c:48-125: uchar in, uchar out; the double expressions are stored by C truncation */
+/* vips_sRGB2HSV_line, sRGB2HSV.c:50-126: uchar in, uchar out; the double expressions are stored by C truncation */
 static void
 sRGB2HSV_line(const uint8_t *p, uint8_t *q, size_t n)
 {
@@ -476,7 +476,7 @@ sRGB2HSV_line(const uint8_t *p, uint8_t *q, size_t n)
 	}
 }
 
-/* vips_HSV2sRGB_line, HSV2sRGB.c:54-107 (SIXTH_OF_CHAR 42.5, a double) */
+/* vips_HSV2sRGB_line, HSV2sRGB.c:54-108 (SIXTH_OF_CHAR 42.5, a double) */
 static void
 HSV2sRGB_line(const uint8_t *p, uint8_t *q, size_t n)
 {
@@ -518,7 +518,7 @@ HSV2sRGB_line(const uint8_t *p, uint8_t *q, size_t n)
 	}
 }
 
-/* vips_scRGB2BW_line, scRGB2BW.c:57-105, over vips_col_scRGB2BW, LabQ2sRGB.c:385-429: the CIE luminance of the linear
+/* vips_scRGB2BW_line, scRGB2BW.c:58-105, over vips_col_scRGB2BW, LabQ2sRGB.c:385-429: the CIE luminance of the linear
  * pixel through the same interpolated gamma table as scRGB -> sRGB; three floats in, one uchar / ushort out
  */
 static void
@@ -638,7 +638,7 @@ shift_cast_step(int step, const Img &in, Img &out)
 	return 0;
 }
 
-/* vips_BW2sRGB / vips_GREY162RGB16, colourspace.c:150-186: not colour objects but vips__colourspace_process_n(in, 1,
+/* vips_BW2sRGB / vips_GREY162RGB16, colourspace.c:152-188: not colour objects but vips__colourspace_process_n(in, 1,
  * bandjoin(in, in, in)): the first band three times, the other bands cast to the same format (a copy) and re-attached;
  * the format stays whatever it was, only Type changes.
  */

@@ -2,12 +2,12 @@
  * TEST INFRASTRUCTURE ONLY (see oracle.h).
  *
  * Follows conversion/flatten.c:
- *   :421-527  vips_flatten_build: 1 band = copy; max_alpha defaults to the interpretation's (:449-450); integer images
- *             with max_alpha below the format's range go through double and are cast back (:458-465, :519-523); an
- *             all-zero background picks the "black" loops (:474-497); otherwise the background becomes `ink` in the
+ *   :421-529  vips_flatten_build: 1 band = copy; max_alpha defaults to the interpretation's (:454-455); integer images
+ *             with max_alpha below the format's range go through double and are cast back (:463-470, :519-523); an
+ *             all-zero background picks the "black" loops (:479-497); otherwise the background becomes `ink` in the
  *             working format (vips__vector_to_ink, insert.c:244-359: (float) bg, then vips_cast: clip in double, truncate)
- *   :170-237  vips_flatten_black_gen_uchar (float LUT i / max_alpha), :304-367 vips_flatten_gen_uchar (two LUTs)
- *   :86-166   the per-format loops: integer arithmetic in int for char, double for the wider formats
+ *   :170-225  vips_flatten_black_gen_uchar (float LUT i / max_alpha), :293-354 vips_flatten_gen_uchar (two LUTs)
+ *   :88-166   the per-format loops: integer arithmetic in int for char, double for the wider formats
  * Declined (-2), because the reference's own arithmetic converts an out-of-range double to an integer type there
  * (undefined in C): the non-uchar integer loops outside the double detour except ushort with max_alpha 65535.
  */
@@ -72,7 +72,7 @@ flatten_wide(const T *p, size_t n, int bands, const double *bg, int nbg, bool bl
 	}
 }
 
-/* VIPS_FLATTEN_FLOAT / VIPS_FLATTEN_BLACK_FLOAT(TYPE), flatten.c:105-166, for TYPE = ushort (max_alpha 65535) and float */
+/* VIPS_FLATTEN_FLOAT / VIPS_FLATTEN_BLACK_FLOAT(TYPE), flatten.c:108-166, for TYPE = ushort (max_alpha 65535) and float */
 template <typename T>
 static void
 flatten_float_loops(const T *p, size_t n, int bands, const double *bg, int nbg, bool black, double max_alpha, T *q)
@@ -91,7 +91,7 @@ flatten_float_loops(const T *p, size_t n, int bands, const double *bg, int nbg, 
 	}
 }
 
-/* vips_flatten_black_gen_uchar / vips_flatten_gen_uchar, flatten.c:170-237, 304-367 */
+/* vips_flatten_black_gen_uchar / vips_flatten_gen_uchar, flatten.c:170-225, 293-354 */
 static void
 flatten_uchar(const uint8_t *p, size_t n, int bands, const double *bg, int nbg, bool black, double max_alpha, uint8_t *q)
 {

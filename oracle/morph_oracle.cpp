@@ -52,10 +52,10 @@ orc_morph(const uint8_t *in, int w, int h, int bands, const double *mask, int mw
 
 /* ------------------------------------------------------------------ vips_rank
  * Follows morphology/rank.c:
- *   :459-490  vips_rank_build: window no larger than the image, 0 <= index < width * height
- *   :508-516  the image is embedded at (width / 2, height / 2) with VIPS_EXTEND_COPY, so output (x, y) sees the
+ *   :458-490  vips_rank_build: window no larger than the image, 0 <= index < width * height
+ *   :507-512  the image is embedded at (width / 2, height / 2) with VIPS_EXTEND_COPY, so output (x, y) sees the
  *             window of input pixels (x - width / 2 + i, y - height / 2 + j), coordinates clamped
- *   :154-221  (uchar histogram), :225-305 (select), :309-369 (max / min): all four paths return the index-th
+ *   :165-232  (uchar histogram), :236-323 (select), :327-381 (max / min): all four paths return the index-th
  *             smallest element of the window, per band; the restatement sorts the window.
  * fmt: VipsBandFormat (0 uchar .. 6 float).  -1: bad window / index / format.
  */

@@ -33,7 +33,7 @@ ref__flatten_ink(const char *domain, VipsImage *im, double *real, double *imag, 
 #include "flatten.c"
 #undef vips_flatten
 
-/* max_alpha <= 0: unset (the interpretation's default, flatten.c:449-450) */
+/* max_alpha <= 0: unset (the interpretation's default, flatten.c:454-455) */
 void *ref_flatten(void *in, const double *background, int n, double max_alpha)
 {
 	static const char *set_max_alpha[] = { "max_alpha", NULL };

@@ -1,5 +1,5 @@
 /* ref_subsample.c -- the reference's conversion/subsample.c compiled in place: vips_resize's pre-shrink for
- * VIPS_KERNEL_NEAREST (resize.c:166-204).  TEST INFRASTRUCTURE ONLY. */
+ * VIPS_KERNEL_NEAREST (resize.c:167-205).  TEST INFRASTRUCTURE ONLY. */
 #include <stdarg.h>
 #include <vips/vips.h>
 #define VIPS_MEMCPY(Q, P, N) memcpy((Q), (P), (N)) /* include/vips/util.h:92 */

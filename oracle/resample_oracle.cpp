@@ -847,7 +847,7 @@ resize_shrinks(int w, int h, double hscale, double vscale, double *hshrink, doub
 	*hshrink = hscale < 1.0 ? 1.0 / hscale : 1.0;
 }
 
-/* vips_resize with VIPS_KERNEL_NEAREST first drops whole pixels (resize.c:166-204): the integer part of the shrink, over
+/* vips_resize with VIPS_KERNEL_NEAREST first drops whole pixels (resize.c:167-205): the integer part of the shrink, over
  * `gap`, goes to vips_subsample -- out(x, y) = in(x * xfac, y * yfac), size in / fac rounded DOWN (subsample.c:83-190,
  * 218-222) -- and the scales are multiplied up for the residual reducev / reduceh.
  */
@@ -900,7 +900,7 @@ orc_resize_size(int w, int h, double hscale, double vscale, int kernel, double g
 			w /= xfac;
 			h /= yfac;
 			if (w <= 0 || h <= 0)
-				return -1; /* "image has shrunk to nothing", subsample.c:223-228 */
+				return -1; /* "image has shrunk to nothing", subsample.c:223-229 */
 			hscale *= xfac;
 			vscale *= yfac;
 		}
@@ -1043,7 +1043,7 @@ orc_resize(const void *in, int w, int h, int bands, int fmt, double hscale, doub
 		if (xfac > 1 || yfac > 1) {
 			const int sw = w / xfac, sh = h / yfac;
 			if (sw <= 0 || sh <= 0)
-				return -1; /* "image has shrunk to nothing", subsample.c:223-228 */
+				return -1; /* "image has shrunk to nothing", subsample.c:223-229 */
 			const size_t ps = orc_sizeof_format(fmt) * bands;
 			std::vector<uint8_t> sub((size_t) sw * sh * ps);
 			for (int y = 0; y < sh; y++)

@@ -1,4 +1,4 @@
-"""vips_resize with VIPS_KERNEL_NEAREST when the shrink is large enough for resize.c:166-204 to subsample first
+"""vips_resize with VIPS_KERNEL_NEAREST when the shrink is large enough for resize.c:167-205 to subsample first
 (vips_subsample: the integer part of the shrink over gap), then reduce the residual.
 
 Found by a random oracle-vs-reference campaign over sizes / scales / kernels / formats (the only disagreement in 15 000
@@ -25,7 +25,7 @@ def test_oracle_nearest_resize_subsamples_like_the_reference():
             want = pyref.RefImage.from_array(a).resize(sc, vs, "nearest").numpy()
             got = orc.resize(a, sc, vs, "nearest")
             assert want.shape == got.shape and np.array_equal(want, got), (w, h, sc, vs, dt)
-    # gap < 1: the integer part of 1 / scale, not of size / target / gap (resize.c:172-175)
+    # gap < 1: the integer part of 1 / scale, not of size / target / gap (resize.c:173-176)
     a = rng.integers(0, 256, (90, 120, 1), dtype=np.uint8)
     for gap in (0.0, 0.5, 1.0, 3.0):
         want = pyref.RefImage.from_array(a).resize(0.2, 0.3, "nearest", gap).numpy()
