@@ -84,7 +84,7 @@ def main():
             p = mutate(rng, profiles[rng.integers(0, len(profiles))])
             for mode in (0, 1):
                 try:
-                    T.host_eval(mode, px if mode == 0 else px.astype(np.float32), p)
+                    T.host_eval(mode, px if mode == 0 else px.astype(np.float32), p, intent=int(rng.integers(0, 4)), pcs=int(rng.integers(0, 2)))
                     ok += 1
                 except vb.Error:
                     fails += 1
