@@ -177,3 +177,21 @@ def test_gpu_hsv_every_input_and_greyscale_at_size(vb):
     c = np.ascontiguousarray(a[:90, :120])
     got = vb.Chain().colourspace("b-w").rank(3, 3, 4).run([c])[0].numpy()
     assert np.array_equal(got, pyconv.median(orc.colourspace(c, "b-w", "srgb"), 3))
+
+
+def test_known_answer_grey_colour_grey():
+    """test/test-suite/test_colour.py:59-74: Lab (50, 0, 0) + alpha 42 to a mono space, from there through every colour
+    space in turn and back to the mono space: the 8-bit grey comes back exactly, the 16-bit one within 30, alpha within 1
+    (the reference's list also holds CMC and the Oklab pair, which are not built here)"""
+    test = np.empty((20, 20, 4), np.float32)
+    test[:] = (50, 0, 0, 42)
+    for mono, bound in (("b-w", 1), ("grey16", 30)):
+        grey = orc.colourspace(test, mono, "lab")
+        assert grey.shape == (20, 20, 2)
+        im, space = grey, mono
+        for col in ("xyz", "lab", "lch", "labs", "scrgb", "hsv", "srgb", "yxy", mono):
+            im = orc.colourspace(im, col, space)
+            space = col
+        assert im.shape == grey.shape and im.dtype == grey.dtype
+        assert abs(int(im[10, 10, 0]) - int(grey[10, 10, 0])) < bound, (mono, im[10, 10], grey[10, 10])
+        assert abs(int(im[10, 10, 1]) - int(grey[10, 10, 1])) < 1, (mono, im[10, 10], grey[10, 10])
