@@ -81,19 +81,31 @@ def test_host_twin_matches_oracle():
         vb.flatten_host_twin(np.zeros((2, 2, 18), np.uint8))
 
 
-def test_known_answer():
-    """test/test-suite/test_conversion.py test_flatten: a constant (100, 128, 200 | alpha 12.5) pixel over black is
-    [int(x) * 12.5 / 255]; for uchar the float result truncates"""
-    px = np.empty((4, 4, 4), np.uint8)
-    px[:] = (100, 128, 200, 12)
-    got = pyconv.flatten(px)
-    for b, v in enumerate((100, 128, 200)):
-        assert abs(float(got[0, 0, b]) - v * 12 / 255.0) < 1.0
-    f = np.empty((4, 4, 4), np.float32)
-    f[:] = (100, 128, 200, 12.5)
-    got = pyconv.flatten(f, (100.0,))
-    for b, v in enumerate((100, 128, 200)):
-        assert abs(float(got[0, 0, b]) - (v * 12.5 / 255.0 + 100.0 * (255 - 12.5) / 255.0)) < 1e-4
+def test_known_answers():
+    """test/test-suite/test_conversion.py:369-413, restated on the oracle: (100, 128, 200 | alpha 127.5) cast to each
+    format, flattened over black and over (100, 100, 100), lands within 2 of the arithmetic prediction; and an image whose
+    max_alpha (255) is below its format's range clips the way the cast-at-the-end order says: flatten(ushort(rgba * 256))
+    == ushort(flatten(float(rgba * 256)))"""
+    import os
+    for dt in (np.uint8, np.uint16, np.uint32, np.int16, np.int32, np.float32):
+        px = np.empty((40, 40, 4), np.float64)
+        px[:] = (100, 128, 200, 127.5)
+        test = px.astype(dt)
+        pixel = test[30, 30].astype(np.float64)
+        mx, alpha = 255, 127.5
+        nalpha = mx - alpha
+        got = pyconv.flatten(test)
+        assert got.shape == (40, 40, 3) and got.dtype == test.dtype
+        for x, y in zip(got[30, 30], [int(v) * alpha / mx for v in pixel[:-1]]):
+            assert abs(float(x) - y) < 2, (dt, x, y)
+        got = pyconv.flatten(test, (100, 100, 100))
+        for x, y in zip(got[30, 30], [int(v) * alpha / mx + 100 * nalpha / mx for v in pixel[:-1]]):
+            assert abs(float(x) - y) < 2, (dt, x, y)
+    rgba = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rgba_fixture.npz"))["rgba"]
+    big = rgba.astype(np.float32) * 256
+    im = pyconv.flatten(np.clip(big, 0, 65535).astype(np.uint16))           # rgba * 256, cast ushort, flatten
+    im2 = np.clip(pyconv.flatten(big), 0, 65535).astype(np.uint16)          # rgba * 256, flatten, cast ushort
+    assert np.array_equal(im, im2)
 
 
 @pytest.mark.gpu

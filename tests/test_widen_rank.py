@@ -1,6 +1,6 @@
 """vips_rank / vips_median.  CPU: the oracle against the reference's own morphology/rank.c under
 oracle/_ref (histogram, select, max and min paths, tiled and untiled), the kernel's staging + radix-select code
-compiled for the host (vb200_debug_rank_host) against the oracle, and the reference test-suite's known answers.
+compiled for the host (vb200_debug_rank_host) against the oracle, and the reference test-suite's known answer.
 GPU: rank_kernel against the oracle, bit for bit."""
 import numpy as np
 import pytest
@@ -60,15 +60,20 @@ def test_host_twin_matches_oracle():
 
 
 def test_known_answers():
-    """test/test-suite/test_morphology.py test_rank: a 10 x 10 white square under rank(3, 3, 8) (the max) grows by one
-    pixel on every side; median of a constant image is the constant"""
-    im = np.zeros((100, 100, 1), np.uint8)
-    im[45:55, 45:55] = 255
+    """test/test-suite/test_morphology.py:44-51 (test_rank): a filled white circle of radius 25 on black under rank(3, 3, 8)
+    -- the window's maximum -- keeps its geometry and gets brighter on average; plus what follows from the definition: a
+    10 x 10 square grows by one pixel on every side, the median of a constant image is the constant"""
+    yy, xx = np.mgrid[0:100, 0:100]
+    im = (((xx - 50) ** 2 + (yy - 50) ** 2 <= 25 * 25) * 255).astype(np.uint8)[:, :, None]
     im2 = pyconv.rank(im, 3, 3, 8)
-    assert im2.sum() > im.sum() and im2[44:56, 44:56].min() == 255 and im2.sum() == 144 * 255
+    assert im2.shape == im.shape and im2.mean() > im.mean()
+    sq = np.zeros((100, 100, 1), np.uint8)
+    sq[45:55, 45:55] = 255
+    sq2 = pyconv.rank(sq, 3, 3, 8)
+    assert sq2[44:56, 44:56].min() == 255 and sq2.sum() == 144 * 255
     assert np.array_equal(pyconv.median(np.full((20, 20, 3), 7, np.uint8), 5), np.full((20, 20, 3), 7, np.uint8))
     with pytest.raises(ValueError):
-        pyconv.rank(im, 3, 3, 9)
+        pyconv.rank(sq, 3, 3, 9)
 
 
 @pytest.mark.gpu
