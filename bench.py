@@ -456,6 +456,46 @@ def side_workload(args):
             cpu["kind"] = "reference"
         run(fn, 2 * (a.numel() + lab.numel() * 4), "vips_icc_import + vips_icc_export (sRGB-like v4 profile) on 8192x8192",
             2 * n * n / 1e6, "Mpixels/s", cpu)
+    elif args.workload in ("rank", "flatten", "greyscale"):
+        # parity-green in round 2, never timed there (the GPU budget was spent)
+        n = 4096
+        from oracle import pyconv
+        rng = np.random.default_rng(1234)
+        if args.workload == "rank":
+            a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
+            out = torch.empty_like(a)
+            cin = dimg(a, 22)
+
+            def fn():
+                cout = dimg(out, 22)
+                vb._check(L.vb200_rank(C.byref(cin), C.byref(cout), 3, 3, 4))
+            ca = rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+            cpu = cpu_side(lambda: pyconv.median(ca, 3), 1024 * 1024 / 1e6, "1024x1024 RGB")
+            run(fn, 2 * a.numel(), "vips_median 3x3 on 4096x4096 sRGB uchar", n * n / 1e6, "Mpixels/s", cpu)
+        elif args.workload == "flatten":
+            a = torch.randint(0, 256, (n, n, 4), dtype=torch.uint8, device=dev)
+            out = torch.empty((n, n, 3), dtype=torch.uint8, device=dev)
+            cin = dimg(a, 22)
+            bg = (C.c_double * 3)(255.0, 255.0, 255.0)
+
+            def fn():
+                cout = dimg(out, 22)
+                vb._check(L.vb200_flatten(C.byref(cin), C.byref(cout), bg, 3, 0.0))
+            ca = rng.integers(0, 256, (1024, 1024, 4), dtype=np.uint8)
+            cpu = cpu_side(lambda: pyconv.flatten(ca, (255, 255, 255)), 1024 * 1024 / 1e6, "1024x1024 RGBA")
+            run(fn, a.numel() + out.numel(), "vips_flatten (white background) on 4096x4096 RGBA uchar", n * n / 1e6, "Mpixels/s", cpu)
+        else:
+            from oracle import pyoracle
+            a = torch.randint(0, 256, (n, n, 3), dtype=torch.uint8, device=dev)
+            out = torch.empty((n, n, 1), dtype=torch.uint8, device=dev)
+            cin = dimg(a, 22)
+
+            def fn():
+                cout = dimg(out, 1)
+                vb._check(L.vb200_colourspace(C.byref(cin), C.byref(cout), 1))
+            ca = rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
+            cpu = cpu_side(lambda: pyoracle.colourspace(ca, "b-w", "srgb"), 1024 * 1024 / 1e6, "1024x1024 RGB")
+            run(fn, a.numel() + out.numel(), "vips_colourspace sRGB -> B_W on 4096x4096 uchar", n * n / 1e6, "Mpixels/s", cpu)
     elif args.workload in ("thumbnail_jpeg", "thumbnail_jpeg_norestart", "thumbnail_jpeg_progressive"):
         # vips_thumbnail_buffer() of JPEG streams.  Host memory holds only the COMPRESSED frames; the
         # shrink-on-load decode (thumbnail.c:489-517 picks 1/4 for 4K -> 512) and the thumbnail run on the device.
@@ -567,7 +607,7 @@ def main():
                          "transparency decodes to: the kernel's opaque-stage fast path; a second line, never the headline)")
     ap.add_argument("--workload", default="thumbnail",
                     help="thumbnail (the headline, default) | pipeline (BASELINE config 5: thumbnail + sharpen + sRGB, runs under "
-                         "--gpus N like the headline) | thumbnail_jpeg | thumbnail_jpeg_norestart | thumbnail_jpeg_progressive (decode staging, SURVEY 8f; --save adds the encoder) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc: the other BASELINE.json "
+                         "--gpus N like the headline) | thumbnail_jpeg | thumbnail_jpeg_norestart | thumbnail_jpeg_progressive (decode staging, SURVEY 8f; --save adds the encoder) | thumbnail_linear | convsep | colour | reduce49 | upsize | sharpen | icc | rank | flatten | greyscale: the other BASELINE.json "
                          "configs, one device-resident JSON line each (1 GPU)")
     args = ap.parse_args()
 
