@@ -195,3 +195,22 @@ def test_known_answer_grey_colour_grey():
         assert im.shape == grey.shape and im.dtype == grey.dtype
         assert abs(int(im[10, 10, 0]) - int(grey[10, 10, 0])) < bound, (mono, im[10, 10], grey[10, 10])
         assert abs(int(im[10, 10, 1]) - int(grey[10, 10, 1])) < 1, (mono, im[10, 10], grey[10, 10])
+
+
+@needs_ref
+def test_oracle_colourspace_wild_floats_match_reference_build():
+    """NaN / Inf pixels and NaN alpha into the three spaces: scRGB2BW throws NaN luminance out (LabQ2sRGB.c:405-409), the clip
+    handles the infinities, the alpha cast is the reference's own"""
+    rng = np.random.default_rng(9)
+    for bands in (3, 4):
+        for src in ("scrgb", "xyz", "lab", "lch", "yxy"):
+            a = (rng.standard_normal((23, 40, bands)) * 150).astype(np.float32)
+            a[::7, ::5, 0] = np.nan
+            a[::5, ::3, 1] = np.inf
+            a[::3, ::7, 2] = -np.inf
+            if bands == 4:
+                a[::2, ::2, 3] = np.nan
+            for dst in EXT:
+                want = pyref.RefImage.from_array(a, orc.SPACES[src]).colourspace(dst, src).numpy()
+                got = orc.colourspace(a, dst, src)
+                assert got.dtype == want.dtype and np.array_equal(got, want), (src, dst, bands)
